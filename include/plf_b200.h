@@ -1,0 +1,244 @@
+/*
+ * plf_b200.h — C ABI of the B200-native stereo point-line frontend.
+ *
+ * This is the drop-in boundary for the hot path of VealFang/PLI-SLAM.  The reference has
+ * no FFI layer; its seam is five C++ call signatures.  Every entry point below names the reference
+ * interface it replaces (paths relative to the reference tree).  Plain pointers and sizes only: no C++
+ * types, no torch types.  All functions return a plf_status (0 = OK).
+ *
+ * Two libraries export this ABI with different prefixes:
+ *   libplf_b200.so    plf_*      — the product: hand-written sm_100a CUDA kernels.  No CPU fallback: every
+ *                                  call fails with PLF_ERR_CUDA / PLF_ERR_NO_DEVICE if the GPU is unusable.
+ *   libplf_oracle.so  plf_cpu_*  — TEST INFRASTRUCTURE ONLY (oracle/): CPU restatement of the reference path.
+ * The macro PLF_FN(name) selects the prefix so both share these declarations.
+ */
+#ifndef PLF_B200_H
+#define PLF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifdef PLF_ORACLE_BUILD
+#define PLF_FN(name) plf_cpu_##name
+#else
+#define PLF_FN(name) plf_##name
+#endif
+
+#if defined(__GNUC__)
+#define PLF_API __attribute__((visibility("default")))
+#else
+#define PLF_API
+#endif
+
+typedef enum plf_status {
+    PLF_OK = 0,
+    PLF_ERR_INVALID = 1,      /* bad argument (null pointer, size mismatch, capacity too small)          */
+    PLF_ERR_EMPTY_IMAGE = 2,  /* ORBextractor::operator() returns -1 on an empty image (ORBextractor.cc:1072) */
+    PLF_ERR_CUDA = 3,         /* a CUDA call failed; plf_last_error() has the text                         */
+    PLF_ERR_NO_DEVICE = 4,    /* no usable sm_100 device: the product path never falls back to the CPU     */
+    PLF_ERR_UNSUPPORTED = 5,  /* parameter combination not built (e.g. lsd_refine != 0)                    */
+    PLF_ERR_SIZE_MISMATCH = 6,/* std::runtime_error sites of LineMatcher.cpp:148-149,322-323                */
+    PLF_ERR_STATE = 7         /* call order violated (e.g. stereo match before both extractions)           */
+} plf_status;
+
+/* Layout-identical to cv::KeyPoint (28 B): pt.x pt.y size angle response octave class_id. */
+typedef struct plf_keypoint {
+    float x, y;
+    float size;
+    float angle;
+    float response;
+    int32_t octave;
+    int32_t class_id;
+} plf_keypoint;
+
+/* Layout-identical to cv::line_descriptor::KeyLine (68 B), Thirdparty/line_descriptor/include/
+ * line_descriptor/descriptor_custom.hpp:105-181. */
+typedef struct plf_keyline {
+    float angle;
+    int32_t class_id;
+    int32_t octave;
+    float pt_x, pt_y;
+    float response;
+    float size;
+    float startPointX, startPointY;
+    float endPointX, endPointY;
+    float sPointInOctaveX, sPointInOctaveY;
+    float ePointInOctaveX, ePointInOctaveY;
+    float lineLength;
+    int32_t numOfPixels;
+} plf_keyline;
+
+/* All tunables of the path as one POD.  Defaults (plf_default_params) are Examples/Stereo/Config/EuRoC.yaml
+ * and src/Config.cpp:26-160. */
+typedef struct plf_params {
+    int32_t width, height;        /* image size the context is built for                                  */
+    int32_t max_batch;            /* stereo pairs per batched call (>=1)                                   */
+    /* ORBextractor ctor, src/ORBextractor.cc:408-411 */
+    int32_t n_features;           /* 1200 */
+    float   scale_factor;         /* 1.2  */
+    int32_t n_levels;             /* 8    */
+    int32_t ini_th_fast;          /* 20   */
+    int32_t min_th_fast;          /* 7    */
+    /* Lineextractor ctor, include/LineExtractor.h:45-47 */
+    int32_t has_lines;            /* Config::hasLines()                                                    */
+    int32_t lsd_nfeatures;        /* 500 in EuRoC.yaml:156 (300 = Config default); 0 keeps all             */
+    int32_t lsd_refine;           /* 0 (only 0 is built this round)                                        */
+    int32_t lsd_n_bins;           /* 1024 */
+    double  min_line_length;      /* 0.025 (relative to min(W,H))                                          */
+    double  lsd_scale;            /* 1.2  */
+    double  lsd_sigma_scale;      /* 0.6  */
+    double  lsd_quant;            /* 2.0  */
+    double  lsd_ang_th;           /* 22.5 */
+    double  lsd_log_eps;          /* 1.0  */
+    double  lsd_density_th;       /* 0.6  */
+    /* stereo geometry: mbf and mb of src/Frame.cc:105,197 */
+    float   bf;                   /* 47.90639 */
+    float   fx;                   /* 435.2047; mb := bf/fx is applied BEFORE matching (oracle rule) */
+    /* Config values read by Frame::ComputeStereoMatches_Lines / matchGrid */
+    int32_t best_lr_matches;      /* true */
+    int32_t matching_s_ws;        /* 10   */
+    double  min_ratio_12_l;       /* 0.9  */
+    double  line_sim_th;          /* 0.75 */
+    double  min_disp;             /* 1.0  */
+    double  line_horiz_th;        /* 0.1  */
+    double  stereo_overlap_th;    /* 0.75 */
+    double  ls_min_disp_ratio;    /* 0.7  */
+} plf_params;
+
+typedef struct plf_ctx plf_ctx;
+
+/* Host-side result block of one batched call; the caller owns every array.
+ * Strides: keypoint arrays are [batch][kp_cap], keyline arrays [batch][kl_cap]. */
+typedef struct plf_frame_out {
+    int32_t kp_cap, kl_cap;
+    int32_t* n_kp_left;  int32_t* n_kp_right;     /* [batch] == Frame::N, mvKeysRight.size()               */
+    int32_t* n_kl_left;  int32_t* n_kl_right;     /* [batch] == mvKeys_Line.size(), mvKeysRight_Line.size()*/
+    plf_keypoint* kp_left;  plf_keypoint* kp_right;   /* mvKeys, mvKeysRight                               */
+    uint8_t* desc_left;     uint8_t* desc_right;      /* mDescriptors(Right): [batch][kp_cap][32]          */
+    float* u_right;         float* depth;             /* mvuRight, mvDepth: [batch][kp_cap]                */
+    plf_keyline* kl_left;   plf_keyline* kl_right;    /* mvKeys_Line, mvKeysRight_Line                     */
+    uint8_t* ldesc_left;    uint8_t* ldesc_right;     /* mDescriptors_Line(Right): [batch][kl_cap][32]     */
+    float* disp_se;                                   /* mvDisparity_l: [batch][kl_cap][2]                 */
+    double* le;                                       /* mvle_l: [batch][kl_cap][3]                        */
+    int32_t* line_match12;                            /* matches_12 of matchGrid: [batch][kl_cap]          */
+} plf_frame_out;
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* lifetime                                                                                               */
+
+PLF_API int PLF_FN(default_params)(plf_params* p);
+/* Replaces: ORBextractor::ORBextractor (src/ORBextractor.cc:408-468) x2 + Lineextractor ctor x2
+ * (src/Tracking.cc:87-98,743-749).  One context = the four extractor objects of one Tracking instance plus
+ * device buffers for max_batch stereo pairs and one CUDA stream.  `device` is the CUDA ordinal (ignored by the
+ * oracle). */
+PLF_API int PLF_FN(create)(const plf_params* p, int device, plf_ctx** out);
+PLF_API int PLF_FN(destroy)(plf_ctx* ctx);
+PLF_API const char* PLF_FN(last_error)(void);
+/* Capacity each out_kp/out_desc row block needs: n_features + 3*n_levels rounded up (DistributeOctTree can
+ * overshoot N by <=3 per level, src/ORBextractor.cc:728). */
+PLF_API int PLF_FN(keypoint_capacity)(const plf_ctx* ctx);
+PLF_API int PLF_FN(keyline_capacity)(const plf_ctx* ctx);
+/* ORBextractor getters (include/ORBextractor.h:65-85): scale_factors/inv/sigma2/inv_sigma2, each n_levels floats;
+ * features_per_level n_levels ints.  Null pointers are skipped. */
+PLF_API int PLF_FN(get_scale_tables)(const plf_ctx* ctx, float* scale, float* inv_scale, float* sigma2,
+                                     float* inv_sigma2, int32_t* features_per_level);
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* single-frame drop-in calls (batch slot 0).  `side`: 0 = left extractor, 1 = right extractor.           */
+
+/* Replaces: int ORBextractor::operator()(InputArray im, InputArray mask, vector<KeyPoint>&, OutputArray desc,
+ * vector<int>& vLappingArea)  (include/ORBextractor.h:61-63, src/ORBextractor.cc:1068-1150).
+ * img: 8-bit single channel, `stride` bytes per row.  Writes *n keypoints/descriptor rows in the reference's row
+ * order (mono rows front-to-back, lapping rows back-to-front) and *mono_index = the reference's return value. */
+PLF_API int PLF_FN(orb_extract)(plf_ctx* ctx, int side, const uint8_t* img, int w, int h, int stride,
+                                int lap0, int lap1, plf_keypoint* out_kp, uint8_t* out_desc, int cap,
+                                int* n, int* mono_index);
+/* Replaces: public member ORBextractor::mvImagePyramid[level] (include/ORBextractor.h:87) read by
+ * Frame::ComputeStereoMatches.  Copies the level image (no 19-px border) to `out` with `out_stride`. */
+PLF_API int PLF_FN(get_pyramid_level)(plf_ctx* ctx, int side, int level, uint8_t* out, int out_stride,
+                                      int* w, int* h);
+/* Replaces: void Lineextractor::operator()(const Mat& im, const Mat& mask, vector<KeyLine>&, Mat& desc)
+ * (include/LineExtractor.h:49-51, src/LineExtractor.cc:31-70): LSDDetectorC::detect(opts) + top-N by response +
+ * BinaryDescriptor::compute. */
+PLF_API int PLF_FN(line_extract)(plf_ctx* ctx, int side, const uint8_t* img, int w, int h, int stride,
+                                 plf_keyline* out_kl, uint8_t* out_desc, int cap, int* n);
+/* Replaces: void Frame::ComputeStereoMatches() (include/Frame.h:152, src/Frame.cc:976-1154).  Uses the keypoints,
+ * descriptors and pyramids left in the context by the two orb_extract calls.  u_right/depth: Frame::N floats. */
+PLF_API int PLF_FN(stereo_match_points)(plf_ctx* ctx, float* u_right, float* depth, int cap);
+/* Replaces: void Frame::ComputeStereoMatches_Lines(bool) (include/Frame.h:154, src/Frame.cc:1156-1307) incl.
+ * matchGrid(lines) (src/LineMatcher.cpp:317-396).  disp_se: n x 2 floats (-1,-1 = mono line), le: n x 3 doubles,
+ * match12: n ints (matches_12 after the mutual check; may be null). */
+PLF_API int PLF_FN(stereo_match_lines)(plf_ctx* ctx, float* disp_se, double* le, int32_t* match12, int cap);
+/* Replaces: int matchNNR(const Mat& d1, const Mat& d2, float nnr, vector<int>& m12) (include/LineMatcher.h:59,
+ * src/LineMatcher.cpp:139-159).  d1: n1 x 32, d2: n2 x 32, row-major.  n2 < 2 -> no matches (oracle rule). */
+PLF_API int PLF_FN(match_nnr)(plf_ctx* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr,
+                              int32_t* m12, int* n_matches);
+/* Replaces: int match(const Mat&, const Mat&, float nnr, vector<int>&) (src/LineMatcher.cpp:201-229); mutual-best
+ * when best_lr != 0 (Config::bestLRMatches()). */
+PLF_API int PLF_FN(match)(plf_ctx* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr,
+                          int best_lr, int32_t* m12, int* n_matches);
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* batched calls: `batch` independent stereo pairs per call (<= max_batch); images are [batch][h][stride].  */
+
+/* Replaces: Frame::Frame(stereo) extraction + matching (src/Frame.cc:128-163) for `batch` frames at once.
+ * Host buffers; the H2D/D2H copies are part of the call. */
+PLF_API int PLF_FN(frontend_batch)(plf_ctx* ctx, const uint8_t* left, const uint8_t* right, int batch,
+                                   int stride, plf_frame_out* out);
+/* The same split into its three phases so a caller can overlap them or keep inputs resident:
+ *   upload  : H2D of `batch` pairs (async on the context stream)
+ *   run     : every kernel of the path on the images currently resident in the context (async)
+ *   download: D2H of the results + stream synchronise. */
+PLF_API int PLF_FN(batch_upload)(plf_ctx* ctx, const uint8_t* left, const uint8_t* right, int batch, int stride);
+PLF_API int PLF_FN(batch_run)(plf_ctx* ctx, int batch);
+PLF_API int PLF_FN(batch_download)(plf_ctx* ctx, int batch, plf_frame_out* out);
+PLF_API int PLF_FN(sync)(plf_ctx* ctx);
+/* Bytes moved per stereo pair by upload and download (for the bench's e2e accounting). */
+PLF_API int PLF_FN(batch_io_bytes)(const plf_ctx* ctx, int64_t* h2d_per_pair, int64_t* d2h_per_pair);
+/* Number of kernel launches issued by the last batch_run (bench "gpu_launches"). 0 for the oracle. */
+PLF_API int PLF_FN(last_launch_count)(const plf_ctx* ctx);
+/* Device-time per stage of the last batch_run, in ms (CUDA events on the context stream; oracle: wall clock).
+ * names: pointer to a static array of `*n_stages` C strings. Requires plf_set_stage_timing(ctx,1) before run. */
+PLF_API int PLF_FN(set_stage_timing)(plf_ctx* ctx, int on);
+PLF_API int PLF_FN(get_stage_ms)(plf_ctx* ctx, const char* const** names, const float** ms, int* n_stages);
+/* Raw CUDA stream (cudaStream_t as void*) so a harness can record events on the launching stream. */
+PLF_API void* PLF_FN(stream)(plf_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* stage taps for parity tests (slot = batch index, side 0/1).  Not part of the reference interface.       */
+
+PLF_API int PLF_FN(tap_blurred_level)(plf_ctx* ctx, int slot, int side, int level, uint8_t* out, int out_stride);
+PLF_API int PLF_FN(tap_pyramid_level)(plf_ctx* ctx, int slot, int side, int level, uint8_t* out, int out_stride,
+                                      int* w, int* h);
+/* vToDistributeKeys of one level (src/ORBextractor.cc:776-853): x,y (level coords incl. the 16-px min border),
+ * response; cell-major then raster order. */
+PLF_API int PLF_FN(tap_fast_candidates)(plf_ctx* ctx, int slot, int side, int level, float* xyr, int cap, int* n);
+/* LSD internals: the x1.2 scaled image, the level-line angle (degrees, float; -1024 = NOTDEF), segments in
+ * detection order (x1,y1,x2,y2 in input-image coordinates). */
+PLF_API int PLF_FN(tap_lsd_scaled)(plf_ctx* ctx, int slot, int side, uint8_t* out, int out_stride, int* w, int* h);
+PLF_API int PLF_FN(tap_lsd_angles)(plf_ctx* ctx, int slot, int side, float* out, int* w, int* h);
+PLF_API int PLF_FN(tap_lsd_segments)(plf_ctx* ctx, int slot, int side, float* xyxy, int cap, int* n);
+/* LBD float descriptor (72 floats per line) before binarisation. */
+PLF_API int PLF_FN(tap_lbd_float)(plf_ctx* ctx, int slot, int side, float* out, int cap, int* n);
+
+/* Replaces: static int ORBmatcher::DescriptorDistance(const Mat&, const Mat&) (include/ORBmatcher.h:42,
+ * src/ORBmatcher.cc:2495-2511) and int distance(const Mat&, const Mat&) (src/LineMatcher.cpp:231-247):
+ * Hamming distance of two 32-byte rows.  Pure host inline (the reference calls it from several threads). */
+static inline int plf_hamming256(const uint8_t* a, const uint8_t* b) {
+    int d = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint64_t x, y;
+        __builtin_memcpy(&x, a + 8 * i, 8);
+        __builtin_memcpy(&y, b + 8 * i, 8);
+        d += __builtin_popcountll(x ^ y);
+    }
+    return d;
+}
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLF_B200_H */

@@ -1,0 +1,263 @@
+// TEST INFRASTRUCTURE ONLY — CPU oracle, LSD + KeyLine construction.  See lsd.h for provenance.
+#include "lsd.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace plfo {
+
+static const double kPi = 3.14159265358979323846;
+static const double kNotDef = -1024.0;
+static const double kDegToRad = kPi / 180.0;
+
+void gaussian_taps_fixed(int ksize, double sigma, std::vector<int>& taps) {
+    std::vector<double> k(ksize);
+    double sum = 0;
+    const int r = ksize / 2;
+    for (int i = 0; i < ksize; ++i) {
+        double x = i - r;
+        k[i] = std::exp(-(x * x) / (2 * sigma * sigma));
+        sum += k[i];
+    }
+    for (double& v : k) v /= sum;
+    taps.assign(ksize, 0);
+    double err = 0;
+    int s = 0;
+    for (int i = 0; i < r; ++i) {
+        double adj = k[i] * 256.0 + err;
+        int v0 = cv_round(adj);
+        err = adj - v0;
+        taps[i] = taps[ksize - 1 - i] = v0;
+        s += v0;
+    }
+    taps[r] = 256 - 2 * s;
+}
+
+namespace {
+struct RegPt { int x, y; };
+
+struct Lsd {
+    const LsdConfig& c;
+    int W = 0, H = 0;
+    std::vector<double> angles, modgrad;
+    std::vector<uint8_t> used;
+    struct NormPt { int x, y, norm; };
+    std::vector<NormPt> ordered;
+    explicit Lsd(const LsdConfig& cc) : c(cc) {}
+
+    void ll_angle(const Img8& U, double threshold, std::vector<float>& angDeg) {
+        W = U.w; H = U.h;
+        angles.assign((size_t)W * H, kNotDef);
+        modgrad.assign((size_t)W * H, 0.0);
+        angDeg.assign((size_t)W * H, (float)kNotDef);
+        double max_grad = -1;
+        for (int y = 0; y < H - 1; ++y) {
+            const uint8_t* r0 = U.row(y);
+            const uint8_t* r1 = U.row(y + 1);
+            for (int x = 0; x < W - 1; ++x) {
+                int DA = r1[x + 1] - r0[x];
+                int BC = r0[x + 1] - r1[x];
+                int gx = DA + BC, gy = DA - BC;
+                double norm = std::sqrt((gx * gx + gy * gy) / 4.0);
+                modgrad[(size_t)y * W + x] = norm;
+                if (norm <= threshold) {
+                    angles[(size_t)y * W + x] = kNotDef;
+                } else {
+                    float deg = fast_atan2((float)gx, (float)-gy);
+                    angDeg[(size_t)y * W + x] = deg;
+                    angles[(size_t)y * W + x] = deg * kDegToRad;
+                    if (norm > max_grad) max_grad = norm;
+                }
+            }
+        }
+        const double bin_coef = (max_grad > 0) ? double(c.n_bins - 1) / max_grad : 0;
+        ordered.clear();
+        ordered.reserve((size_t)(W - 1) * (H - 1));
+        for (int y = 0; y < H - 1; ++y)
+            for (int x = 0; x < W - 1; ++x)
+                ordered.push_back({x, y, (int)(modgrad[(size_t)y * W + x] * bin_coef)});
+        auto cmp = [](const NormPt& a, const NormPt& b) { return a.norm > b.norm; };
+        if (c.stable_order) std::stable_sort(ordered.begin(), ordered.end(), cmp);
+        else std::sort(ordered.begin(), ordered.end(), cmp);
+    }
+
+    bool is_aligned(int x, int y, double theta, double prec) const {
+        if (x < 0 || y < 0 || x >= W || y >= H) return false;
+        const double a = angles[(size_t)y * W + x];
+        if (a == kNotDef) return false;
+        double n_theta = theta - a;
+        if (n_theta < 0) n_theta = -n_theta;
+        if (n_theta > (3 * kPi) / 2) {
+            n_theta -= 2 * kPi;
+            if (n_theta < 0) n_theta = -n_theta;
+        }
+        return n_theta <= prec;
+    }
+
+    void region_grow(int sx, int sy, std::vector<RegPt>& reg, double& reg_angle, double prec) {
+        reg.clear();
+        reg.push_back({sx, sy});
+        reg_angle = angles[(size_t)sy * W + sx];
+        float sumdx = (float)std::cos(reg_angle);
+        float sumdy = (float)std::sin(reg_angle);
+        used[(size_t)sy * W + sx] = 1;
+        for (size_t i = 0; i < reg.size(); ++i) {
+            const RegPt rp = reg[i];
+            int xx_min = std::max(rp.x - 1, 0), xx_max = std::min(rp.x + 1, W - 1);
+            int yy_min = std::max(rp.y - 1, 0), yy_max = std::min(rp.y + 1, H - 1);
+            for (int yy = yy_min; yy <= yy_max; ++yy)
+                for (int xx = xx_min; xx <= xx_max; ++xx) {
+                    uint8_t& u = used[(size_t)yy * W + xx];
+                    if (u != 1 && is_aligned(xx, yy, reg_angle, prec)) {
+                        const double angle = angles[(size_t)yy * W + xx];
+                        u = 1;
+                        reg.push_back({xx, yy});
+                        sumdx += cosf((float)angle);
+                        sumdy += sinf((float)angle);
+                        reg_angle = fast_atan2(sumdy, sumdx) * kDegToRad;
+                    }
+                }
+        }
+    }
+
+    static double angle_diff(double a, double b) {
+        double diff = a - b;
+        while (diff <= -kPi) diff += 2 * kPi;
+        while (diff > kPi) diff -= 2 * kPi;
+        if (diff < 0) diff = -diff;
+        return diff;
+    }
+
+    double get_theta(const std::vector<RegPt>& reg, double x, double y, double reg_angle, double prec) const {
+        double Ixx = 0, Iyy = 0, Ixy = 0;
+        for (const RegPt& p : reg) {
+            const double w = modgrad[(size_t)p.y * W + p.x];
+            double dx = (double)p.x - x, dy = (double)p.y - y;
+            Ixx += dy * dy * w;
+            Iyy += dx * dx * w;
+            Ixy -= dx * dy * w;
+        }
+        double lambda = 0.5 * (Ixx + Iyy - std::sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+        double theta = (std::fabs(Ixx) > std::fabs(Iyy)) ? (double)fast_atan2((float)(lambda - Ixx), (float)Ixy)
+                                                         : (double)fast_atan2((float)Ixy, (float)(lambda - Iyy));
+        theta *= kDegToRad;
+        if (angle_diff(theta, reg_angle) > prec) theta += kPi;
+        return theta;
+    }
+
+    // region2rect: returns endpoints (before the +0.5 shift)
+    void region2rect(const std::vector<RegPt>& reg, double reg_angle, double prec, double out[4]) const {
+        double x = 0, y = 0, sum = 0;
+        for (const RegPt& p : reg) {
+            const double w = modgrad[(size_t)p.y * W + p.x];
+            x += (double)p.x * w;
+            y += (double)p.y * w;
+            sum += w;
+        }
+        x /= sum;
+        y /= sum;
+        double theta = get_theta(reg, x, y, reg_angle, prec);
+        double dx = std::cos(theta), dy = std::sin(theta);
+        double l_min = 0, l_max = 0;
+        for (const RegPt& p : reg) {
+            double rdx = (double)p.x - x, rdy = (double)p.y - y;
+            double l = rdx * dx + rdy * dy;
+            if (l > l_max) l_max = l;
+            else if (l < l_min) l_min = l;
+        }
+        out[0] = x + l_min * dx;
+        out[1] = y + l_min * dy;
+        out[2] = x + l_max * dx;
+        out[3] = y + l_max * dy;
+    }
+};
+}  // namespace
+
+void lsd_detect(const LsdConfig& c, const Img8& img, LsdState& st) {
+    st.valid = false;
+    st.segs.clear();
+    const double prec = kPi * c.ang_th / 180;
+    const double p = c.ang_th / 180;
+    const double rho = c.quant / std::sin(prec);
+    Lsd L(c);
+    if (c.scale != 1) {
+        const double sigma = (c.scale < 1) ? (c.sigma_scale / c.scale) : c.sigma_scale;
+        const double sprec = 3;
+        const unsigned h = (unsigned)std::ceil(sigma * std::sqrt(2 * sprec * std::log(10.0)));
+        const int ksize = 1 + 2 * (int)h;
+        std::vector<int> taps;
+        gaussian_taps_fixed(ksize, sigma, taps);
+        Img8 g;
+        gaussian_blur_u8(img, g, taps.data(), ksize);
+        resize_linear_exact_u8(g, st.scaled, c.scale);
+    } else {
+        st.scaled = img;
+    }
+    L.ll_angle(st.scaled, rho, st.angleDeg);
+    const int W = L.W, H = L.H;
+    const double logNT = 5 * (std::log10((double)W) + std::log10((double)H)) / 2 + std::log10(11.0);
+    const size_t min_reg_size = (size_t)(-logNT / std::log10(p));
+    L.used.assign((size_t)W * H, 0);
+    std::vector<RegPt> reg;
+    for (const auto& op : L.ordered) {
+        const size_t idx = (size_t)op.y * W + op.x;
+        if (L.used[idx] != 0 || L.angles[idx] == kNotDef) continue;
+        double reg_angle;
+        L.region_grow(op.x, op.y, reg, reg_angle, prec);
+        if (reg.size() < min_reg_size) continue;
+        double r[4];
+        L.region2rect(reg, reg_angle, prec, r);
+        for (int k = 0; k < 4; ++k) {
+            r[k] += 0.5;
+            if (c.scale != 1) r[k] /= c.scale;
+            st.segs.push_back((float)r[k]);
+        }
+    }
+    st.valid = true;
+}
+
+// cv::LineIterator(img, Point2f, Point2f).count for endpoints inside the image.
+int line_iterator_count(float x1, float y1, float x2, float y2) {
+    int ax = cv_roundf(x1), ay = cv_roundf(y1), bx = cv_roundf(x2), by = cv_roundf(y2);
+    return std::max(std::abs(bx - ax), std::abs(by - ay)) + 1;
+}
+
+// LSDDetector_custom.cpp:76-102,268-308 then src/LineExtractor.cc:56-65
+void lines_to_keylines(const std::vector<float>& segs, int w, int h, double min_length, int nfeatures,
+                       std::vector<plf_keyline>& kls) {
+    kls.clear();
+    int class_counter = -1;
+    for (size_t k = 0; k + 3 < segs.size(); k += 4) {
+        float e[4] = {segs[k], segs[k + 1], segs[k + 2], segs[k + 3]};
+        for (int q = 0; q < 4; q += 2) {
+            if (e[q] < 0) e[q] = 0;
+            if (e[q] >= w) e[q] = (float)w - 1.0f;
+            if (e[q + 1] < 0) e[q + 1] = 0;
+            if (e[q + 1] >= h) e[q + 1] = (float)h - 1.0f;
+        }
+        double length = (float)std::sqrt(std::pow((double)(e[0] - e[2]), 2) + std::pow((double)(e[1] - e[3]), 2));
+        if (!(length > min_length)) continue;
+        plf_keyline kl;
+        kl.startPointX = e[0]; kl.startPointY = e[1]; kl.endPointX = e[2]; kl.endPointY = e[3];
+        kl.sPointInOctaveX = e[0]; kl.sPointInOctaveY = e[1]; kl.ePointInOctaveX = e[2]; kl.ePointInOctaveY = e[3];
+        kl.lineLength = (float)length;
+        kl.numOfPixels = line_iterator_count(e[0], e[1], e[2], e[3]);
+        kl.angle = (float)std::atan2((double)(kl.endPointY - kl.startPointY), (double)(kl.endPointX - kl.startPointX));
+        kl.class_id = ++class_counter;
+        kl.octave = 0;
+        kl.size = (kl.endPointX - kl.startPointX) * (kl.endPointY - kl.startPointY);
+        kl.response = kl.lineLength / (float)std::max(w, h);
+        kl.pt_x = (kl.endPointX + kl.startPointX) / 2;
+        kl.pt_y = (kl.endPointY + kl.startPointY) / 2;
+        kls.push_back(kl);
+    }
+    if ((int)kls.size() > nfeatures && nfeatures != 0) {
+        // oracle rule: stable order (response desc, detection index asc) in place of the unstable std::sort
+        std::stable_sort(kls.begin(), kls.end(),
+                         [](const plf_keyline& a, const plf_keyline& b) { return a.response > b.response; });
+        kls.resize(nfeatures);
+        for (int i = 0; i < nfeatures; ++i) kls[i].class_id = i;
+    }
+}
+
+}  // namespace plfo

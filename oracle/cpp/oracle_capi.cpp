@@ -1,0 +1,430 @@
+// TEST INFRASTRUCTURE ONLY — CPU oracle exported through the same C ABI as the product (prefix plf_cpu_).
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
+#define PLF_ORACLE_BUILD 1
+#include "../../include/plf_b200.h"
+#include "linematch.h"
+#include "lsd.h"
+#include "orb.h"
+#include "stereo.h"
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <thread>
+
+using namespace plfo;
+
+struct Slot {
+    OrbState orb[2];
+    LsdState lsd[2];
+    Img8 img[2];
+    std::vector<float> uRight, depth, disp;
+    std::vector<double> le;
+    std::vector<int> m12;
+};
+
+struct plf_ctx {
+    plf_params p;
+    OrbConfig oc;
+    OrbTables ot;
+    LsdConfig lc;
+    LineMatchConfig mc;
+    std::vector<Slot> slots;
+    int kp_cap = 0, kl_cap = 0;
+    int threads = 0;         // worker threads for batch calls (0 = hardware concurrency)
+    int batch_resident = 0;
+};
+
+static thread_local std::string g_err;
+static int fail(int code, const char* msg) { g_err = msg; return code; }
+
+extern "C" {
+
+PLF_API const char* plf_cpu_last_error(void) { return g_err.c_str(); }
+
+PLF_API int plf_cpu_default_params(plf_params* p) {
+    if (!p) return PLF_ERR_INVALID;
+    std::memset(p, 0, sizeof(*p));
+    p->width = 752; p->height = 480; p->max_batch = 1;
+    p->n_features = 1200; p->scale_factor = 1.2f; p->n_levels = 8; p->ini_th_fast = 20; p->min_th_fast = 7;
+    p->has_lines = 1; p->lsd_nfeatures = 500; p->lsd_refine = 0; p->lsd_n_bins = 1024;
+    p->min_line_length = 0.025; p->lsd_scale = 1.2; p->lsd_sigma_scale = 0.6; p->lsd_quant = 2.0;
+    p->lsd_ang_th = 22.5; p->lsd_log_eps = 1.0; p->lsd_density_th = 0.6;
+    p->bf = 47.90639384423901f; p->fx = 435.2046959714599f;
+    p->best_lr_matches = 1; p->matching_s_ws = 10; p->min_ratio_12_l = 0.9; p->line_sim_th = 0.75;
+    p->min_disp = 1.0; p->line_horiz_th = 0.1; p->stereo_overlap_th = 0.75; p->ls_min_disp_ratio = 0.7;
+    return PLF_OK;
+}
+
+PLF_API int plf_cpu_create(const plf_params* p, int /*device*/, plf_ctx** out) {
+    if (!p || !out) return fail(PLF_ERR_INVALID, "null argument");
+    if (p->width < 64 || p->height < 64 || p->max_batch < 1 || p->n_levels < 1 || p->n_levels > 16)
+        return fail(PLF_ERR_INVALID, "bad image size / batch / levels");
+    if (p->lsd_refine != 0) return fail(PLF_ERR_UNSUPPORTED, "lsd_refine != 0 is not built");
+    plf_ctx* c = new plf_ctx();
+    c->p = *p;
+    c->oc.nfeatures = p->n_features; c->oc.scaleFactor = p->scale_factor; c->oc.nlevels = p->n_levels;
+    c->oc.iniThFAST = p->ini_th_fast; c->oc.minThFAST = p->min_th_fast;
+    orb_tables(c->oc, c->ot);
+    c->lc.refine = p->lsd_refine; c->lc.scale = p->lsd_scale; c->lc.sigma_scale = p->lsd_sigma_scale;
+    c->lc.quant = p->lsd_quant; c->lc.ang_th = p->lsd_ang_th; c->lc.log_eps = p->lsd_log_eps;
+    c->lc.density_th = p->lsd_density_th; c->lc.n_bins = p->lsd_n_bins;
+    c->mc.best_lr_matches = p->best_lr_matches; c->mc.matching_s_ws = p->matching_s_ws;
+    c->mc.min_ratio_12_l = p->min_ratio_12_l; c->mc.line_sim_th = p->line_sim_th; c->mc.min_disp = p->min_disp;
+    c->mc.line_horiz_th = p->line_horiz_th; c->mc.stereo_overlap_th = p->stereo_overlap_th;
+    c->mc.ls_min_disp_ratio = p->ls_min_disp_ratio;
+    c->slots.resize(p->max_batch);
+    c->kp_cap = ((p->n_features + 3 * p->n_levels + 31) / 32) * 32;
+    c->kl_cap = p->lsd_nfeatures > 0 ? p->lsd_nfeatures : 4096;
+    *out = c;
+    return PLF_OK;
+}
+
+PLF_API int plf_cpu_destroy(plf_ctx* c) { delete c; return PLF_OK; }
+PLF_API int plf_cpu_keypoint_capacity(const plf_ctx* c) { return c ? c->kp_cap : 0; }
+PLF_API int plf_cpu_keyline_capacity(const plf_ctx* c) { return c ? c->kl_cap : 0; }
+
+PLF_API int plf_cpu_get_scale_tables(const plf_ctx* c, float* s, float* is, float* s2, float* is2, int32_t* n) {
+    if (!c) return PLF_ERR_INVALID;
+    const int L = c->oc.nlevels;
+    if (s) std::memcpy(s, c->ot.scale.data(), L * 4);
+    if (is) std::memcpy(is, c->ot.invScale.data(), L * 4);
+    if (s2) std::memcpy(s2, c->ot.sigma2.data(), L * 4);
+    if (is2) std::memcpy(is2, c->ot.invSigma2.data(), L * 4);
+    if (n) std::memcpy(n, c->ot.nPerLevel.data(), L * 4);
+    return PLF_OK;
+}
+
+// oracle-only knobs
+PLF_API int plf_cpu_set_threads(plf_ctx* c, int n) { if (!c) return PLF_ERR_INVALID; c->threads = n; return PLF_OK; }
+PLF_API int plf_cpu_set_lsd_stable_order(plf_ctx* c, int on) { if (!c) return PLF_ERR_INVALID; c->lc.stable_order = on != 0; return PLF_OK; }
+
+static int orb_slot(plf_ctx* c, int slot, int side, const uint8_t* img, int w, int h, int stride, int lap0, int lap1) {
+    return orb_extract(c->oc, c->ot, img, w, h, stride, lap0, lap1, c->slots[slot].orb[side]);
+}
+
+static void line_slot(plf_ctx* c, int slot, int side, const uint8_t* img, int w, int h, int stride) {
+    Slot& s = c->slots[slot];
+    LsdState& st = s.lsd[side];
+    st.kls.clear(); st.desc.clear(); st.lbd.clear(); st.segs.clear();
+    if (!c->p.has_lines) { st.valid = true; return; }
+    Img8 im(w, h);
+    for (int y = 0; y < h; ++y) std::memcpy(im.row(y), img + (size_t)y * stride, w);
+    lsd_detect(c->lc, im, st);
+    const double min_len = c->p.min_line_length * std::min(w, h);
+    lines_to_keylines(st.segs, w, h, min_len, c->p.lsd_nfeatures, st.kls);
+    lbd_compute(im, st.kls, st.lbd, st.desc);
+}
+
+PLF_API int plf_cpu_orb_extract(plf_ctx* c, int side, const uint8_t* img, int w, int h, int stride, int lap0,
+                                int lap1, plf_keypoint* out_kp, uint8_t* out_desc, int cap, int* n, int* mono) {
+    if (!c || side < 0 || side > 1) return fail(PLF_ERR_INVALID, "bad ctx/side");
+    if (!img || w <= 0 || h <= 0) return PLF_ERR_EMPTY_IMAGE;
+    if (w != c->p.width || h != c->p.height) return fail(PLF_ERR_INVALID, "image size differs from context");
+    int m = orb_slot(c, 0, side, img, w, h, stride, lap0, lap1);
+    const OrbState& st = c->slots[0].orb[side];
+    if ((int)st.kps.size() > cap) return fail(PLF_ERR_INVALID, "keypoint capacity too small");
+    if (out_kp) std::memcpy(out_kp, st.kps.data(), st.kps.size() * sizeof(plf_keypoint));
+    if (out_desc) std::memcpy(out_desc, st.desc.data(), st.desc.size());
+    if (n) *n = (int)st.kps.size();
+    if (mono) *mono = m;
+    return PLF_OK;
+}
+
+static int copy_level(const Img8& im, uint8_t* out, int out_stride, int* w, int* h) {
+    if (w) *w = im.w;
+    if (h) *h = im.h;
+    if (out)
+        for (int y = 0; y < im.h; ++y) std::memcpy(out + (size_t)y * out_stride, im.row(y), im.w);
+    return PLF_OK;
+}
+
+PLF_API int plf_cpu_tap_pyramid_level(plf_ctx* c, int slot, int side, int level, uint8_t* out, int out_stride, int* w, int* h) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || side < 0 || side > 1 || level < 0 || level >= c->oc.nlevels) return PLF_ERR_INVALID;
+    if (!c->slots[slot].orb[side].valid) return PLF_ERR_STATE;
+    return copy_level(c->slots[slot].orb[side].pyr[level], out, out_stride, w, h);
+}
+PLF_API int plf_cpu_get_pyramid_level(plf_ctx* c, int side, int level, uint8_t* out, int out_stride, int* w, int* h) {
+    return plf_cpu_tap_pyramid_level(c, 0, side, level, out, out_stride, w, h);
+}
+PLF_API int plf_cpu_tap_blurred_level(plf_ctx* c, int slot, int side, int level, uint8_t* out, int out_stride) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || side < 0 || side > 1 || level < 0 || level >= c->oc.nlevels) return PLF_ERR_INVALID;
+    OrbState& st = c->slots[slot].orb[side];
+    if (!st.valid) return PLF_ERR_STATE;
+    if (st.blur[level].w == 0) gaussian_blur_u8(st.pyr[level], st.blur[level], TAPS_ORB7, 7);
+    return copy_level(st.blur[level], out, out_stride, nullptr, nullptr);
+}
+PLF_API int plf_cpu_tap_fast_candidates(plf_ctx* c, int slot, int side, int level, float* xyr, int cap, int* n) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || side < 0 || side > 1 || level < 0 || level >= c->oc.nlevels) return PLF_ERR_INVALID;
+    const OrbState& st = c->slots[slot].orb[side];
+    if (!st.valid) return PLF_ERR_STATE;
+    const auto& v = st.cands[level];
+    if (n) *n = (int)v.size();
+    if ((int)v.size() > cap) return PLF_ERR_INVALID;
+    for (size_t i = 0; i < v.size(); ++i) { xyr[3 * i] = v[i].x + 16; xyr[3 * i + 1] = v[i].y + 16; xyr[3 * i + 2] = v[i].resp; }
+    return PLF_OK;
+}
+
+PLF_API int plf_cpu_line_extract(plf_ctx* c, int side, const uint8_t* img, int w, int h, int stride,
+                                 plf_keyline* out_kl, uint8_t* out_desc, int cap, int* n) {
+    if (!c || side < 0 || side > 1 || !img) return fail(PLF_ERR_INVALID, "bad ctx/side/img");
+    if (w != c->p.width || h != c->p.height) return fail(PLF_ERR_INVALID, "image size differs from context");
+    line_slot(c, 0, side, img, w, h, stride);
+    const LsdState& st = c->slots[0].lsd[side];
+    if ((int)st.kls.size() > cap) return fail(PLF_ERR_INVALID, "keyline capacity too small");
+    if (out_kl) std::memcpy(out_kl, st.kls.data(), st.kls.size() * sizeof(plf_keyline));
+    if (out_desc) std::memcpy(out_desc, st.desc.data(), st.desc.size());
+    if (n) *n = (int)st.kls.size();
+    return PLF_OK;
+}
+
+PLF_API int plf_cpu_tap_lsd_scaled(plf_ctx* c, int slot, int side, uint8_t* out, int out_stride, int* w, int* h) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || side < 0 || side > 1) return PLF_ERR_INVALID;
+    if (!c->slots[slot].lsd[side].valid) return PLF_ERR_STATE;
+    return copy_level(c->slots[slot].lsd[side].scaled, out, out_stride, w, h);
+}
+PLF_API int plf_cpu_tap_lsd_angles(plf_ctx* c, int slot, int side, float* out, int* w, int* h) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || side < 0 || side > 1) return PLF_ERR_INVALID;
+    const LsdState& st = c->slots[slot].lsd[side];
+    if (!st.valid) return PLF_ERR_STATE;
+    if (w) *w = st.scaled.w;
+    if (h) *h = st.scaled.h;
+    if (out) std::memcpy(out, st.angleDeg.data(), st.angleDeg.size() * 4);
+    return PLF_OK;
+}
+PLF_API int plf_cpu_tap_lsd_segments(plf_ctx* c, int slot, int side, float* xyxy, int cap, int* n) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || side < 0 || side > 1) return PLF_ERR_INVALID;
+    const LsdState& st = c->slots[slot].lsd[side];
+    if (!st.valid) return PLF_ERR_STATE;
+    int m = (int)st.segs.size() / 4;
+    if (n) *n = m;
+    if (m > cap) return PLF_ERR_INVALID;
+    if (xyxy) std::memcpy(xyxy, st.segs.data(), st.segs.size() * 4);
+    return PLF_OK;
+}
+PLF_API int plf_cpu_tap_lbd_float(plf_ctx* c, int slot, int side, float* out, int cap, int* n) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || side < 0 || side > 1) return PLF_ERR_INVALID;
+    const LsdState& st = c->slots[slot].lsd[side];
+    if (!st.valid) return PLF_ERR_STATE;
+    int m = (int)st.kls.size();
+    if (n) *n = m;
+    if (m > cap) return PLF_ERR_INVALID;
+    if (out) std::memcpy(out, st.lbd.data(), st.lbd.size() * 4);
+    return PLF_OK;
+}
+
+static int match_points_slot(plf_ctx* c, int slot) {
+    Slot& s = c->slots[slot];
+    if (!s.orb[0].valid || !s.orb[1].valid) return PLF_ERR_STATE;
+    stereo_match_points(c->ot, s.orb[0], s.orb[1], c->p.bf, c->p.fx, s.uRight, s.depth);
+    return PLF_OK;
+}
+static int match_lines_slot(plf_ctx* c, int slot) {
+    Slot& s = c->slots[slot];
+    if (!s.lsd[0].valid || !s.lsd[1].valid) return PLF_ERR_STATE;
+    stereo_match_lines(c->mc, c->p.width, c->p.height, s.lsd[0].kls, s.lsd[0].desc, s.lsd[1].kls, s.lsd[1].desc,
+                       s.disp, s.le, s.m12);
+    return PLF_OK;
+}
+
+PLF_API int plf_cpu_stereo_match_points(plf_ctx* c, float* u_right, float* depth, int cap) {
+    if (!c) return PLF_ERR_INVALID;
+    int rc = match_points_slot(c, 0);
+    if (rc) return fail(rc, "stereo_match_points before both orb_extract calls");
+    Slot& s = c->slots[0];
+    if ((int)s.uRight.size() > cap) return fail(PLF_ERR_INVALID, "capacity too small");
+    if (u_right) std::memcpy(u_right, s.uRight.data(), s.uRight.size() * 4);
+    if (depth) std::memcpy(depth, s.depth.data(), s.depth.size() * 4);
+    return PLF_OK;
+}
+
+PLF_API int plf_cpu_stereo_match_lines(plf_ctx* c, float* disp_se, double* le, int32_t* match12, int cap) {
+    if (!c) return PLF_ERR_INVALID;
+    int rc = match_lines_slot(c, 0);
+    if (rc) return fail(rc, "stereo_match_lines before both line_extract calls");
+    Slot& s = c->slots[0];
+    if ((int)s.m12.size() > cap) return fail(PLF_ERR_INVALID, "capacity too small");
+    if (disp_se) std::memcpy(disp_se, s.disp.data(), s.disp.size() * 4);
+    if (le) std::memcpy(le, s.le.data(), s.le.size() * 8);
+    if (match12) std::memcpy(match12, s.m12.data(), s.m12.size() * 4);
+    return PLF_OK;
+}
+
+PLF_API int plf_cpu_match_nnr(plf_ctx*, const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int32_t* m12, int* nm) {
+    if (n1 < 0 || n2 < 0 || (n1 && !d1) || (n2 && !d2) || (n1 && !m12)) return fail(PLF_ERR_INVALID, "bad descriptors");
+    int m = match_nnr(d1, n1, d2, n2, nnr, m12);
+    if (nm) *nm = m;
+    return PLF_OK;
+}
+PLF_API int plf_cpu_match(plf_ctx*, const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int best_lr, int32_t* m12, int* nm) {
+    if (n1 < 0 || n2 < 0 || (n1 && !d1) || (n2 && !d2) || (n1 && !m12)) return fail(PLF_ERR_INVALID, "bad descriptors");
+    int m = match_lr(d1, n1, d2, n2, nnr, best_lr, m12);
+    if (nm) *nm = m;
+    return PLF_OK;
+}
+
+// ---- batch -----------------------------------------------------------------------------------------------
+PLF_API int plf_cpu_batch_upload(plf_ctx* c, const uint8_t* left, const uint8_t* right, int batch, int stride) {
+    if (!c || !left || !right || batch < 1 || batch > (int)c->slots.size()) return fail(PLF_ERR_INVALID, "bad batch");
+    const int w = c->p.width, h = c->p.height;
+    for (int b = 0; b < batch; ++b)
+        for (int s = 0; s < 2; ++s) {
+            Img8& im = c->slots[b].img[s];
+            im = Img8(w, h);
+            const uint8_t* src = (s ? right : left) + (size_t)b * h * stride;
+            for (int y = 0; y < h; ++y) std::memcpy(im.row(y), src + (size_t)y * stride, w);
+        }
+    c->batch_resident = batch;
+    return PLF_OK;
+}
+
+static void run_pair(plf_ctx* c, int b) {
+    Slot& s = c->slots[b];
+    const int w = c->p.width, h = c->p.height;
+    for (int side = 0; side < 2; ++side) {
+        orb_slot(c, b, side, s.img[side].d.data(), w, h, w, 0, 0);
+        line_slot(c, b, side, s.img[side].d.data(), w, h, w);
+    }
+    // Frame.cc:146-149: both matchers are skipped when there are no keypoints or no lines
+    s.uRight.assign(s.orb[0].kps.size(), -1.f);
+    s.depth.assign(s.orb[0].kps.size(), -1.f);
+    s.disp.assign(s.lsd[0].kls.size() * 2, -1.f);
+    s.le.assign(s.lsd[0].kls.size() * 3, 0.0);
+    s.m12.assign(s.lsd[0].kls.size(), -1);
+    if (s.orb[0].kps.empty()) return;
+    if (c->p.has_lines && s.lsd[0].kls.empty()) return;
+    if (c->p.has_lines) match_lines_slot(c, b);
+    match_points_slot(c, b);
+}
+
+PLF_API int plf_cpu_batch_run(plf_ctx* c, int batch) {
+    if (!c || batch < 1 || batch > c->batch_resident) return fail(PLF_ERR_INVALID, "bad batch");
+    int nt = c->threads > 0 ? c->threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, batch));
+    std::atomic<int> next(0);
+    auto worker = [&]() { for (int b; (b = next.fetch_add(1)) < batch;) run_pair(c, b); };
+    std::vector<std::thread> th;
+    for (int i = 1; i < nt; ++i) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+    return PLF_OK;
+}
+
+PLF_API int plf_cpu_batch_download(plf_ctx* c, int batch, plf_frame_out* o) {
+    if (!c || !o || batch < 1 || batch > c->batch_resident) return fail(PLF_ERR_INVALID, "bad batch");
+    const int kc = o->kp_cap, lc = o->kl_cap;
+    for (int b = 0; b < batch; ++b) {
+        Slot& s = c->slots[b];
+        const int nl = (int)s.orb[0].kps.size(), nr = (int)s.orb[1].kps.size();
+        const int ll = (int)s.lsd[0].kls.size(), lr = (int)s.lsd[1].kls.size();
+        if (nl > kc || nr > kc || ll > lc || lr > lc) return fail(PLF_ERR_INVALID, "output capacity too small");
+        if (o->n_kp_left) o->n_kp_left[b] = nl;
+        if (o->n_kp_right) o->n_kp_right[b] = nr;
+        if (o->n_kl_left) o->n_kl_left[b] = ll;
+        if (o->n_kl_right) o->n_kl_right[b] = lr;
+        if (o->kp_left) std::memcpy(o->kp_left + (size_t)b * kc, s.orb[0].kps.data(), nl * sizeof(plf_keypoint));
+        if (o->kp_right) std::memcpy(o->kp_right + (size_t)b * kc, s.orb[1].kps.data(), nr * sizeof(plf_keypoint));
+        if (o->desc_left) std::memcpy(o->desc_left + (size_t)b * kc * 32, s.orb[0].desc.data(), (size_t)nl * 32);
+        if (o->desc_right) std::memcpy(o->desc_right + (size_t)b * kc * 32, s.orb[1].desc.data(), (size_t)nr * 32);
+        if (o->u_right) std::memcpy(o->u_right + (size_t)b * kc, s.uRight.data(), s.uRight.size() * 4);
+        if (o->depth) std::memcpy(o->depth + (size_t)b * kc, s.depth.data(), s.depth.size() * 4);
+        if (o->kl_left) std::memcpy(o->kl_left + (size_t)b * lc, s.lsd[0].kls.data(), ll * sizeof(plf_keyline));
+        if (o->kl_right) std::memcpy(o->kl_right + (size_t)b * lc, s.lsd[1].kls.data(), lr * sizeof(plf_keyline));
+        if (o->ldesc_left) std::memcpy(o->ldesc_left + (size_t)b * lc * 32, s.lsd[0].desc.data(), (size_t)ll * 32);
+        if (o->ldesc_right) std::memcpy(o->ldesc_right + (size_t)b * lc * 32, s.lsd[1].desc.data(), (size_t)lr * 32);
+        if (o->disp_se) std::memcpy(o->disp_se + (size_t)b * lc * 2, s.disp.data(), s.disp.size() * 4);
+        if (o->le) std::memcpy(o->le + (size_t)b * lc * 3, s.le.data(), s.le.size() * 8);
+        if (o->line_match12) std::memcpy(o->line_match12 + (size_t)b * lc, s.m12.data(), s.m12.size() * 4);
+    }
+    return PLF_OK;
+}
+
+PLF_API int plf_cpu_frontend_batch(plf_ctx* c, const uint8_t* left, const uint8_t* right, int batch, int stride, plf_frame_out* out) {
+    int rc = plf_cpu_batch_upload(c, left, right, batch, stride);
+    if (rc) return rc;
+    rc = plf_cpu_batch_run(c, batch);
+    if (rc) return rc;
+    return plf_cpu_batch_download(c, batch, out);
+}
+
+PLF_API int plf_cpu_sync(plf_ctx*) { return PLF_OK; }
+PLF_API int plf_cpu_batch_io_bytes(const plf_ctx* c, int64_t* a, int64_t* b) {
+    if (!c) return PLF_ERR_INVALID;
+    if (a) *a = 0;
+    if (b) *b = 0;
+    return PLF_OK;
+}
+PLF_API int plf_cpu_last_launch_count(const plf_ctx*) { return 0; }
+PLF_API int plf_cpu_set_stage_timing(plf_ctx*, int) { return PLF_OK; }
+PLF_API int plf_cpu_get_stage_ms(plf_ctx*, const char* const** names, const float** ms, int* n) {
+    if (names) *names = nullptr;
+    if (ms) *ms = nullptr;
+    if (n) *n = 0;
+    return PLF_OK;
+}
+PLF_API void* plf_cpu_stream(plf_ctx*) { return nullptr; }
+
+// stage-level entry points used by tests/test_oracle_cv2.py to pin each primitive against cv2
+PLF_API float plf_cpu_fast_atan2(float y, float x) { return fast_atan2(y, x); }
+PLF_API int plf_cpu_prim_resize_linear(const uint8_t* src, int w, int h, uint8_t* dst, int dw, int dh) {
+    Img8 s(w, h), d;
+    std::memcpy(s.d.data(), src, (size_t)w * h);
+    resize_linear_u8(s, d, dw, dh);
+    std::memcpy(dst, d.d.data(), (size_t)dw * dh);
+    return PLF_OK;
+}
+PLF_API int plf_cpu_prim_resize_exact(const uint8_t* src, int w, int h, double scale, uint8_t* dst, int* dw, int* dh) {
+    Img8 s(w, h), d;
+    std::memcpy(s.d.data(), src, (size_t)w * h);
+    resize_linear_exact_u8(s, d, scale);
+    if (dw) *dw = d.w;
+    if (dh) *dh = d.h;
+    if (dst) std::memcpy(dst, d.d.data(), d.d.size());
+    return PLF_OK;
+}
+PLF_API int plf_cpu_prim_gaussian(const uint8_t* src, int w, int h, int ksize, double sigma, uint8_t* dst, int* taps_out) {
+    Img8 s(w, h), d;
+    std::memcpy(s.d.data(), src, (size_t)w * h);
+    std::vector<int> taps;
+    gaussian_taps_fixed(ksize, sigma, taps);
+    if (taps_out) std::memcpy(taps_out, taps.data(), ksize * 4);
+    gaussian_blur_u8(s, d, taps.data(), ksize);
+    std::memcpy(dst, d.d.data(), d.d.size());
+    return PLF_OK;
+}
+PLF_API int plf_cpu_prim_sobel(const uint8_t* src, int w, int h, int16_t* dx, int16_t* dy) {
+    Img8 s(w, h);
+    std::memcpy(s.d.data(), src, (size_t)w * h);
+    Img16 a, b;
+    sobel3_16s(s, a, b);
+    std::memcpy(dx, a.d.data(), a.d.size() * 2);
+    std::memcpy(dy, b.d.data(), b.d.size() * 2);
+    return PLF_OK;
+}
+PLF_API int plf_cpu_prim_fast(const uint8_t* src, int w, int h, int th, float* xyr, int cap, int* n) {
+    Img8 s(w, h);
+    std::memcpy(s.d.data(), src, (size_t)w * h);
+    std::vector<Cand> v;
+    fast_window(s, 0, 0, w, h, th, v);
+    if (n) *n = (int)v.size();
+    if ((int)v.size() > cap) return PLF_ERR_INVALID;
+    for (size_t i = 0; i < v.size(); ++i) { xyr[3 * i] = v[i].x; xyr[3 * i + 1] = v[i].y; xyr[3 * i + 2] = v[i].resp; }
+    return PLF_OK;
+}
+PLF_API int plf_cpu_prim_lsd(const uint8_t* src, int w, int h, double scale, int stable, float* xyxy, int cap, int* n) {
+    Img8 s(w, h);
+    std::memcpy(s.d.data(), src, (size_t)w * h);
+    LsdConfig c;
+    c.scale = scale;
+    c.stable_order = stable != 0;
+    LsdState st;
+    lsd_detect(c, s, st);
+    int m = (int)st.segs.size() / 4;
+    if (n) *n = m;
+    if (m > cap) return PLF_ERR_INVALID;
+    std::memcpy(xyxy, st.segs.data(), st.segs.size() * 4);
+    return PLF_OK;
+}
+
+}  // extern "C"

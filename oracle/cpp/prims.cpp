@@ -1,0 +1,162 @@
+// TEST INFRASTRUCTURE ONLY — see prims.h.
+#include "prims.h"
+#include <algorithm>
+#include <cstring>
+
+namespace plfo {
+
+const int TAPS_ORB7[7] = {18, 34, 48, 56, 48, 34, 18};
+const int TAPS_LBD5[5] = {14, 62, 104, 62, 14};
+const int TAPS_LSD7[7] = {0, 1, 42, 170, 42, 1, 0};
+
+// Degree-7 odd polynomial in float, no FMA (this TU is built with -ffp-contract=off).
+float fast_atan2(float y, float x) {
+    const float k = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * k;
+    const float p3 = -0.3258083974640975f * k;
+    const float p5 = 0.1555786518463281f * k;
+    const float p7 = -0.04432655554792128f * k;
+    float ax = std::fabs(x), ay = std::fabs(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + (float)DBL_EPSILON);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+void resize_linear_u8(const Img8& src, Img8& dst, int dw, int dh) {
+    dst = Img8(dw, dh);
+    const int sw = src.w, sh = src.h;
+    const double scale_x = (double)sw / dw, scale_y = (double)sh / dh;
+    std::vector<int> xofs(dw), yofs(dh);
+    std::vector<int> ax0(dw), ax1(dw), ay0(dh), ay1(dh);
+    for (int dx = 0; dx < dw; ++dx) {
+        float fx = (float)((dx + 0.5) * scale_x - 0.5);
+        int sx = cv_floor(fx);
+        fx -= sx;
+        if (sx < 0) { fx = 0; sx = 0; }
+        if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+        xofs[dx] = sx;
+        ax0[dx] = cv_roundf((1.f - fx) * 2048.f);
+        ax1[dx] = cv_roundf(fx * 2048.f);
+    }
+    for (int dy = 0; dy < dh; ++dy) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = cv_floor(fy);
+        fy -= sy;
+        if (sy < 0) { fy = 0; sy = 0; }
+        if (sy >= sh - 1) { fy = 0; sy = sh - 1; }
+        yofs[dy] = sy;
+        ay0[dy] = cv_roundf((1.f - fy) * 2048.f);
+        ay1[dy] = cv_roundf(fy * 2048.f);
+    }
+    std::vector<int> r0(dw), r1(dw);
+    for (int dy = 0; dy < dh; ++dy) {
+        const uint8_t* s0 = src.row(yofs[dy]);
+        const uint8_t* s1 = src.row(std::min(yofs[dy] + 1, sh - 1));
+        for (int dx = 0; dx < dw; ++dx) {
+            int sx = xofs[dx], sx1 = std::min(sx + 1, sw - 1);
+            r0[dx] = s0[sx] * ax0[dx] + s0[sx1] * ax1[dx];
+            r1[dx] = s1[sx] * ax0[dx] + s1[sx1] * ax1[dx];
+        }
+        uint8_t* d = dst.row(dy);
+        const int b0 = ay0[dy], b1 = ay1[dy];
+        for (int dx = 0; dx < dw; ++dx)
+            d[dx] = (uint8_t)((((b0 * (r0[dx] >> 4)) >> 16) + ((b1 * (r1[dx] >> 4)) >> 16) + 2) >> 2);
+    }
+}
+
+void resize_linear_exact_u8(const Img8& src, Img8& dst, double scale) {
+    const int sw = src.w, sh = src.h;
+    const int dw = cv_round(sw * scale), dh = cv_round(sh * scale);
+    dst = Img8(dw, dh);
+    const double inv = 1.0 / scale;
+    auto coeffs = [&](int n_dst, int n_src, std::vector<int>& ofs, std::vector<int>& a1) {
+        ofs.resize(n_dst);
+        a1.resize(n_dst);
+        for (int d = 0; d < n_dst; ++d) {
+            double f = inv * (d + 0.5) - 0.5;
+            int i = cv_floor(f);
+            if (i >= 0 && n_src > 1) {
+                if (i < n_src - 1) {
+                    ofs[d] = i;
+                    a1[d] = cv_round((f - i) * 256.0);
+                } else {
+                    ofs[d] = n_src - 1;
+                    a1[d] = 0;
+                }
+            } else {
+                ofs[d] = 0;
+                a1[d] = 0;
+            }
+        }
+    };
+    std::vector<int> xo, xa, yo, ya;
+    coeffs(dw, sw, xo, xa);
+    coeffs(dh, sh, yo, ya);
+    std::vector<int> r0(dw), r1(dw);
+    for (int dy = 0; dy < dh; ++dy) {
+        const uint8_t* s0 = src.row(yo[dy]);
+        const uint8_t* s1 = src.row(std::min(yo[dy] + 1, sh - 1));
+        for (int dx = 0; dx < dw; ++dx) {
+            int sx = xo[dx], sx1 = std::min(sx + 1, sw - 1);
+            int a = xa[dx];
+            r0[dx] = s0[sx] * (256 - a) + s0[sx1] * a;
+            r1[dx] = s1[sx] * (256 - a) + s1[sx1] * a;
+        }
+        uint8_t* d = dst.row(dy);
+        const int b = ya[dy];
+        for (int dx = 0; dx < dw; ++dx) d[dx] = (uint8_t)((r0[dx] * (256 - b) + r1[dx] * b + 32768) >> 16);
+    }
+}
+
+void gaussian_blur_u8(const Img8& src, Img8& dst, const int* taps, int ksize) {
+    const int w = src.w, h = src.h, r = ksize / 2;
+    std::vector<uint16_t> tmp((size_t)w * h);
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* s = src.row(y);
+        uint16_t* t = tmp.data() + (size_t)y * w;
+        for (int x = 0; x < w; ++x) {
+            int acc = 0;
+            for (int k = 0; k < ksize; ++k) acc += taps[k] * s[reflect101(x + k - r, w)];
+            t[x] = (uint16_t)acc;
+        }
+    }
+    dst = Img8(w, h);
+    for (int y = 0; y < h; ++y) {
+        uint8_t* d = dst.row(y);
+        for (int x = 0; x < w; ++x) {
+            uint32_t acc = 0;
+            for (int k = 0; k < ksize; ++k) acc += (uint32_t)taps[k] * tmp[(size_t)reflect101(y + k - r, h) * w + x];
+            d[x] = (uint8_t)((acc + 32768u) >> 16);
+        }
+    }
+}
+
+void sobel3_16s(const Img8& src, Img16& dx, Img16& dy) {
+    const int w = src.w, h = src.h;
+    dx = Img16(w, h);
+    dy = Img16(w, h);
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* r0 = src.row(reflect101(y - 1, h));
+        const uint8_t* r1 = src.row(y);
+        const uint8_t* r2 = src.row(reflect101(y + 1, h));
+        for (int x = 0; x < w; ++x) {
+            int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+            int gx = (r0[xp] - r0[xm]) + 2 * (r1[xp] - r1[xm]) + (r2[xp] - r2[xm]);
+            int gy = (r2[xm] - r0[xm]) + 2 * (r2[x] - r0[x]) + (r2[xp] - r0[xp]);
+            dx.d[(size_t)y * w + x] = (int16_t)gx;
+            dy.d[(size_t)y * w + x] = (int16_t)gy;
+        }
+    }
+}
+
+}  // namespace plfo

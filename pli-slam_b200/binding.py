@@ -1,0 +1,352 @@
+"""ctypes binding of the C ABI declared in include/plf_b200.h.
+
+The same declarations serve two libraries: the product `libplf_b200.so` (prefix ``plf_``, hand-written sm_100a
+CUDA) and the test-only CPU oracle `oracle/libplf_oracle.so` (prefix ``plf_cpu_``).  This module never falls back
+from one to the other: `load_product()` raises if the CUDA library is missing.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PRODUCT_LIB = os.path.join(ROOT, "pli-slam_b200", "libplf_b200.so")
+ORACLE_LIB = os.path.join(ROOT, "oracle", "libplf_oracle.so")
+
+PLF_OK = 0
+STATUS = {0: "OK", 1: "INVALID", 2: "EMPTY_IMAGE", 3: "CUDA", 4: "NO_DEVICE", 5: "UNSUPPORTED", 6: "SIZE_MISMATCH",
+          7: "STATE"}
+
+
+class PlfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("plf status %d (%s): %s" % (code, STATUS.get(code, "?"), msg))
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("max_batch", C.c_int32),
+        ("n_features", C.c_int32), ("scale_factor", C.c_float), ("n_levels", C.c_int32),
+        ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32),
+        ("has_lines", C.c_int32), ("lsd_nfeatures", C.c_int32), ("lsd_refine", C.c_int32), ("lsd_n_bins", C.c_int32),
+        ("min_line_length", C.c_double), ("lsd_scale", C.c_double), ("lsd_sigma_scale", C.c_double),
+        ("lsd_quant", C.c_double), ("lsd_ang_th", C.c_double), ("lsd_log_eps", C.c_double),
+        ("lsd_density_th", C.c_double),
+        ("bf", C.c_float), ("fx", C.c_float),
+        ("best_lr_matches", C.c_int32), ("matching_s_ws", C.c_int32),
+        ("min_ratio_12_l", C.c_double), ("line_sim_th", C.c_double), ("min_disp", C.c_double),
+        ("line_horiz_th", C.c_double), ("stereo_overlap_th", C.c_double), ("ls_min_disp_ratio", C.c_double),
+    ]
+
+
+class FrameOut(C.Structure):
+    _fields_ = [
+        ("kp_cap", C.c_int32), ("kl_cap", C.c_int32),
+        ("n_kp_left", C.c_void_p), ("n_kp_right", C.c_void_p), ("n_kl_left", C.c_void_p), ("n_kl_right", C.c_void_p),
+        ("kp_left", C.c_void_p), ("kp_right", C.c_void_p), ("desc_left", C.c_void_p), ("desc_right", C.c_void_p),
+        ("u_right", C.c_void_p), ("depth", C.c_void_p),
+        ("kl_left", C.c_void_p), ("kl_right", C.c_void_p), ("ldesc_left", C.c_void_p), ("ldesc_right", C.c_void_p),
+        ("disp_se", C.c_void_p), ("le", C.c_void_p), ("line_match12", C.c_void_p),
+    ]
+
+
+KEYPOINT_DT = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"),
+                        ("octave", "i4"), ("class_id", "i4")])
+KEYLINE_DT = np.dtype([("angle", "f4"), ("class_id", "i4"), ("octave", "i4"), ("pt_x", "f4"), ("pt_y", "f4"),
+                       ("response", "f4"), ("size", "f4"), ("startPointX", "f4"), ("startPointY", "f4"),
+                       ("endPointX", "f4"), ("endPointY", "f4"), ("sPointInOctaveX", "f4"), ("sPointInOctaveY", "f4"),
+                       ("ePointInOctaveX", "f4"), ("ePointInOctaveY", "f4"), ("lineLength", "f4"),
+                       ("numOfPixels", "i4")])
+assert KEYPOINT_DT.itemsize == 28 and KEYLINE_DT.itemsize == 68
+
+# every symbol include/plf_b200.h declares (without prefix)
+ABI_SYMBOLS = [
+    "default_params", "create", "destroy", "last_error", "keypoint_capacity", "keyline_capacity", "get_scale_tables",
+    "orb_extract", "get_pyramid_level", "line_extract", "stereo_match_points", "stereo_match_lines", "match_nnr",
+    "match", "frontend_batch", "batch_upload", "batch_run", "batch_download", "sync", "batch_io_bytes",
+    "last_launch_count", "set_stage_timing", "get_stage_ms", "stream", "tap_blurred_level", "tap_pyramid_level",
+    "tap_fast_candidates", "tap_lsd_scaled", "tap_lsd_angles", "tap_lsd_segments", "tap_lbd_float",
+]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Library:
+    """One loaded ABI library (product or oracle)."""
+
+    def __init__(self, path, prefix):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                "%s is not built (run `python -c 'import __graft_entry__ as g; g.build()'`)" % path)
+        self.path, self.prefix = path, prefix
+        self.dll = C.CDLL(path)
+        for s in ABI_SYMBOLS:
+            getattr(self.dll, prefix + s)   # raises AttributeError if a declared symbol is not exported
+        self.fn("last_error").restype = C.c_char_p
+        self.fn("stream").restype = C.c_void_p
+
+    def fn(self, name):
+        return getattr(self.dll, self.prefix + name)
+
+    def check(self, rc):
+        if rc != PLF_OK:
+            raise PlfError(rc, (self.fn("last_error")() or b"").decode())
+
+    def default_params(self, **kw):
+        p = Params()
+        self.check(self.fn("default_params")(C.byref(p)))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+        return p
+
+
+_product = None
+_oracle = None
+
+
+def load_product():
+    """The CUDA library.  Fails loudly when it is not built; there is no CPU fallback."""
+    global _product
+    if _product is None:
+        _product = Library(PRODUCT_LIB, "plf_")
+    return _product
+
+
+def load_oracle():
+    """TEST INFRASTRUCTURE ONLY: the CPU oracle.  Callers: tests/, __graft_entry__.smoke(), bench.py baseline legs."""
+    global _oracle
+    if _oracle is None:
+        _oracle = Library(ORACLE_LIB, "plf_cpu_")
+        _oracle.dll.plf_cpu_fast_atan2.restype = C.c_float
+        _oracle.dll.plf_cpu_fast_atan2.argtypes = [C.c_float, C.c_float]
+    return _oracle
+
+
+class BatchResult:
+    """Host arrays of one batched call; mirrors the Frame members named in plf_frame_out."""
+
+    def __init__(self, batch, kp_cap, kl_cap, pinned=False):
+        self.batch, self.kp_cap, self.kl_cap = batch, kp_cap, kl_cap
+        self._keep = []
+
+        def alloc(shape, dt):
+            if pinned:
+                import torch
+                n = int(np.prod(shape)) * np.dtype(dt).itemsize
+                t = torch.empty(max(n, 1), dtype=torch.uint8).pin_memory()
+                self._keep.append(t)
+                return t.numpy()[:n].view(dt).reshape(shape)
+            return np.zeros(shape, dt)
+
+        self.n_kp_left = alloc((batch,), "i4"); self.n_kp_right = alloc((batch,), "i4")
+        self.n_kl_left = alloc((batch,), "i4"); self.n_kl_right = alloc((batch,), "i4")
+        self.kp_left = alloc((batch, kp_cap), KEYPOINT_DT); self.kp_right = alloc((batch, kp_cap), KEYPOINT_DT)
+        self.desc_left = alloc((batch, kp_cap, 32), "u1"); self.desc_right = alloc((batch, kp_cap, 32), "u1")
+        self.u_right = alloc((batch, kp_cap), "f4"); self.depth = alloc((batch, kp_cap), "f4")
+        self.kl_left = alloc((batch, kl_cap), KEYLINE_DT); self.kl_right = alloc((batch, kl_cap), KEYLINE_DT)
+        self.ldesc_left = alloc((batch, kl_cap, 32), "u1"); self.ldesc_right = alloc((batch, kl_cap, 32), "u1")
+        self.disp_se = alloc((batch, kl_cap, 2), "f4"); self.le = alloc((batch, kl_cap, 3), "f8")
+        self.line_match12 = alloc((batch, kl_cap), "i4")
+        o = FrameOut()
+        o.kp_cap, o.kl_cap = kp_cap, kl_cap
+        for name, _ in FrameOut._fields_[2:]:
+            setattr(o, name, getattr(self, name).ctypes.data)
+        self.c = o
+
+    def nbytes(self):
+        return sum(getattr(self, n).nbytes for n, _ in FrameOut._fields_[2:])
+
+
+class Frontend:
+    """Host-side handle over one plf_ctx: the two ORBextractor + two Lineextractor objects of a Tracking instance
+    (src/Tracking.cc:87-98,743-749) plus the stereo matchers of Frame (src/Frame.cc:160-163)."""
+
+    def __init__(self, lib, params=None, device=0, **kw):
+        self.lib = lib
+        self.params = params if params is not None else lib.default_params(**kw)
+        self.ctx = C.c_void_p()
+        lib.check(lib.fn("create")(C.byref(self.params), int(device), C.byref(self.ctx)))
+        self.kp_cap = lib.fn("keypoint_capacity")(self.ctx)
+        self.kl_cap = lib.fn("keyline_capacity")(self.ctx)
+        self.W, self.H = self.params.width, self.params.height
+
+    def close(self):
+        if self.ctx:
+            self.lib.fn("destroy")(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- reference-shaped single-frame calls ---------------------------------------------------------------
+    def orb_extract(self, side, img, lapping=(0, 0)):
+        """ORBextractor::operator()(im, mask, kps, desc, vLappingArea) -> (monoIndex, keypoints, descriptors)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        kps = np.zeros(self.kp_cap, KEYPOINT_DT)
+        desc = np.zeros((self.kp_cap, 32), np.uint8)
+        n, mono = C.c_int(0), C.c_int(0)
+        self.lib.check(self.lib.fn("orb_extract")(self.ctx, side, _ptr(img), w, h, img.strides[0], int(lapping[0]),
+                                                  int(lapping[1]), _ptr(kps), _ptr(desc), self.kp_cap, C.byref(n),
+                                                  C.byref(mono)))
+        return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def line_extract(self, side, img):
+        """Lineextractor::operator()(im, mask, keylines, desc) -> (keylines, descriptors)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape
+        kls = np.zeros(self.kl_cap, KEYLINE_DT)
+        desc = np.zeros((self.kl_cap, 32), np.uint8)
+        n = C.c_int(0)
+        self.lib.check(self.lib.fn("line_extract")(self.ctx, side, _ptr(img), w, h, img.strides[0], _ptr(kls),
+                                                   _ptr(desc), self.kl_cap, C.byref(n)))
+        return kls[:n.value].copy(), desc[:n.value].copy()
+
+    def stereo_match_points(self, n):
+        """Frame::ComputeStereoMatches -> (mvuRight, mvDepth)."""
+        u = np.zeros(self.kp_cap, np.float32)
+        d = np.zeros(self.kp_cap, np.float32)
+        self.lib.check(self.lib.fn("stereo_match_points")(self.ctx, _ptr(u), _ptr(d), self.kp_cap))
+        return u[:n].copy(), d[:n].copy()
+
+    def stereo_match_lines(self, n):
+        """Frame::ComputeStereoMatches_Lines -> (mvDisparity_l, mvle_l, matches_12)."""
+        disp = np.zeros((self.kl_cap, 2), np.float32)
+        le = np.zeros((self.kl_cap, 3), np.float64)
+        m12 = np.zeros(self.kl_cap, np.int32)
+        self.lib.check(self.lib.fn("stereo_match_lines")(self.ctx, _ptr(disp), _ptr(le), _ptr(m12), self.kl_cap))
+        return disp[:n].copy(), le[:n].copy(), m12[:n].copy()
+
+    def match_nnr(self, d1, d2, nnr):
+        """matchNNR(desc1, desc2, nnr, matches_12) -> (count, matches_12)."""
+        d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32)
+        d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        m = np.full(max(len(d1), 1), -1, np.int32)
+        nm = C.c_int(0)
+        self.lib.check(self.lib.fn("match_nnr")(self.ctx, _ptr(d1), len(d1), _ptr(d2), len(d2), C.c_float(nnr),
+                                                _ptr(m), C.byref(nm)))
+        return nm.value, m[:len(d1)]
+
+    def match(self, d1, d2, nnr, best_lr=True):
+        """match(desc1, desc2, nnr, matches_12) with Config::bestLRMatches() = best_lr."""
+        d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32)
+        d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        m = np.full(max(len(d1), 1), -1, np.int32)
+        nm = C.c_int(0)
+        self.lib.check(self.lib.fn("match")(self.ctx, _ptr(d1), len(d1), _ptr(d2), len(d2), C.c_float(nnr),
+                                            int(bool(best_lr)), _ptr(m), C.byref(nm)))
+        return nm.value, m[:len(d1)]
+
+    def pyramid_level(self, side, level, slot=0):
+        w, h = C.c_int(0), C.c_int(0)
+        self.lib.check(self.lib.fn("tap_pyramid_level")(self.ctx, slot, side, level, None, 0, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), np.uint8)
+        self.lib.check(self.lib.fn("tap_pyramid_level")(self.ctx, slot, side, level, _ptr(out), w.value, C.byref(w),
+                                                        C.byref(h)))
+        return out
+
+    def blurred_level(self, side, level, slot=0):
+        w, h = C.c_int(0), C.c_int(0)
+        self.lib.check(self.lib.fn("tap_pyramid_level")(self.ctx, slot, side, level, None, 0, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), np.uint8)
+        self.lib.check(self.lib.fn("tap_blurred_level")(self.ctx, slot, side, level, _ptr(out), w.value))
+        return out
+
+    def fast_candidates(self, side, level, slot=0, cap=200000):
+        out = np.zeros((cap, 3), np.float32)
+        n = C.c_int(0)
+        self.lib.check(self.lib.fn("tap_fast_candidates")(self.ctx, slot, side, level, _ptr(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def lsd_scaled(self, side, slot=0):
+        w, h = C.c_int(0), C.c_int(0)
+        self.lib.check(self.lib.fn("tap_lsd_scaled")(self.ctx, slot, side, None, 0, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), np.uint8)
+        self.lib.check(self.lib.fn("tap_lsd_scaled")(self.ctx, slot, side, _ptr(out), w.value, C.byref(w), C.byref(h)))
+        return out
+
+    def lsd_angles(self, side, slot=0):
+        w, h = C.c_int(0), C.c_int(0)
+        self.lib.check(self.lib.fn("tap_lsd_angles")(self.ctx, slot, side, None, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), np.float32)
+        self.lib.check(self.lib.fn("tap_lsd_angles")(self.ctx, slot, side, _ptr(out), C.byref(w), C.byref(h)))
+        return out
+
+    def lsd_segments(self, side, slot=0, cap=20000):
+        out = np.zeros((cap, 4), np.float32)
+        n = C.c_int(0)
+        self.lib.check(self.lib.fn("tap_lsd_segments")(self.ctx, slot, side, _ptr(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def lbd_float(self, side, slot=0):
+        out = np.zeros((self.kl_cap, 72), np.float32)
+        n = C.c_int(0)
+        self.lib.check(self.lib.fn("tap_lbd_float")(self.ctx, slot, side, _ptr(out), self.kl_cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def scale_tables(self):
+        L = self.params.n_levels
+        a = [np.zeros(L, np.float32) for _ in range(4)]
+        n = np.zeros(L, np.int32)
+        self.lib.check(self.lib.fn("get_scale_tables")(self.ctx, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]),
+                                                       _ptr(n)))
+        return a[0], a[1], a[2], a[3], n
+
+    # --- batched calls --------------------------------------------------------------------------------------
+    def new_result(self, batch, pinned=False):
+        return BatchResult(batch, self.kp_cap, self.kl_cap, pinned)
+
+    def frontend_batch(self, left, right, out=None):
+        """Frame::Frame(stereo) extraction + matching for left/right arrays of shape [batch, H, W]."""
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        b = left.shape[0]
+        out = out or self.new_result(b)
+        self.lib.check(self.lib.fn("frontend_batch")(self.ctx, _ptr(left), _ptr(right), b, left.strides[1],
+                                                     C.byref(out.c)))
+        return out
+
+    def batch_upload(self, left, right):
+        self.lib.check(self.lib.fn("batch_upload")(self.ctx, _ptr(left), _ptr(right), left.shape[0],
+                                                   left.strides[1]))
+
+    def batch_upload_raw(self, left_ptr, right_ptr, batch, stride):
+        self.lib.check(self.lib.fn("batch_upload")(self.ctx, C.c_void_p(left_ptr), C.c_void_p(right_ptr), batch,
+                                                   stride))
+
+    def batch_run(self, batch):
+        self.lib.check(self.lib.fn("batch_run")(self.ctx, batch))
+
+    def batch_download(self, batch, out):
+        self.lib.check(self.lib.fn("batch_download")(self.ctx, batch, C.byref(out.c)))
+
+    def sync(self):
+        self.lib.check(self.lib.fn("sync")(self.ctx))
+
+    def io_bytes(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self.lib.check(self.lib.fn("batch_io_bytes")(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def launch_count(self):
+        return self.lib.fn("last_launch_count")(self.ctx)
+
+    def set_stage_timing(self, on):
+        self.lib.check(self.lib.fn("set_stage_timing")(self.ctx, int(on)))
+
+    def stage_ms(self):
+        names = C.POINTER(C.c_char_p)()
+        ms = C.POINTER(C.c_float)()
+        n = C.c_int(0)
+        self.lib.check(self.lib.fn("get_stage_ms")(self.ctx, C.byref(names), C.byref(ms), C.byref(n)))
+        return {names[i].decode(): ms[i] for i in range(n.value)}
+
+    def stream(self):
+        return self.lib.fn("stream")(self.ctx)

@@ -1,0 +1,93 @@
+"""Synthetic EuRoC-shape stereo pairs: there are no datasets offline.
+
+Pure numpy, deterministic in (W, H, seed).  Left image: grey background, 150 axis-aligned rectangles (even index
+outlined with thickness 3, odd filled), 40 straight segments of thickness 1-3, a 3x3 Gaussian (sigma 0.8) and
+additive uniform noise in [-4, 4].  Right image: the same objects, each shifted left by its own disparity
+d in {2..60}, with an independent noise stream.
+"""
+import numpy as np
+
+N_RECT, N_SEG = 150, 40
+
+
+def _draw_rect(img, x0, y0, x1, y1, g, filled):
+    H, W = img.shape
+    xa, xb = sorted((x0, x1))
+    ya, yb = sorted((y0, y1))
+    if filled:
+        img[max(ya, 0):max(yb + 1, 0), max(xa, 0):max(xb + 1, 0)] = g
+        return
+    t = 1   # thickness 3 = centre +-1
+    for (ra, rb, ca, cb) in ((ya - t, ya + t, xa - t, xb + t), (yb - t, yb + t, xa - t, xb + t),
+                             (ya - t, yb + t, xa - t, xa + t), (ya - t, yb + t, xb - t, xb + t)):
+        ra, ca = max(ra, 0), max(ca, 0)
+        rb, cb = max(rb + 1, 0), max(cb + 1, 0)
+        if ra < rb and ca < cb:
+            img[ra:rb, ca:cb] = g
+
+
+def _draw_seg(img, x0, y0, x1, y1, g, thick):
+    H, W = img.shape
+    r = thick / 2.0
+    xa, xb = int(np.floor(min(x0, x1) - r - 1)), int(np.ceil(max(x0, x1) + r + 1))
+    ya, yb = int(np.floor(min(y0, y1) - r - 1)), int(np.ceil(max(y0, y1) + r + 1))
+    xa, ya = max(xa, 0), max(ya, 0)
+    xb, yb = min(xb, W - 1), min(yb, H - 1)
+    if xa > xb or ya > yb:
+        return
+    ys, xs = np.mgrid[ya:yb + 1, xa:xb + 1].astype(np.float64)
+    dx, dy = x1 - x0, y1 - y0
+    L2 = dx * dx + dy * dy
+    if L2 == 0:
+        return
+    t = np.clip(((xs - x0) * dx + (ys - y0) * dy) / L2, 0.0, 1.0)
+    d2 = (xs - (x0 + t * dx)) ** 2 + (ys - (y0 + t * dy)) ** 2
+    sub = img[ya:yb + 1, xa:xb + 1]
+    sub[d2 <= r * r + 1e-9] = g
+
+
+def _blur3(img):
+    k = np.exp(-np.array([-1.0, 0.0, 1.0]) ** 2 / (2 * 0.8 * 0.8))
+    k /= k.sum()
+    f = img.astype(np.float64)
+    p = np.pad(f, 1, mode="reflect")
+    f = k[0] * p[1:-1, :-2] + k[1] * p[1:-1, 1:-1] + k[2] * p[1:-1, 2:]
+    p = np.pad(f, 1, mode="reflect")
+    f = k[0] * p[:-2, 1:-1] + k[1] * p[1:-1, 1:-1] + k[2] * p[2:, 1:-1]
+    return f
+
+
+def synth_pair(W=752, H=480, seed=1):
+    rng = np.random.default_rng(seed)
+    rx = rng.integers(0, W, size=(N_RECT, 2))
+    ry = rng.integers(0, H, size=(N_RECT, 2))
+    rg = rng.integers(30, 255, size=N_RECT)
+    rd = rng.integers(2, 61, size=N_RECT)
+    sx = rng.integers(0, W, size=(N_SEG, 2))
+    sy = rng.integers(0, H, size=(N_SEG, 2))
+    sg = rng.integers(30, 255, size=N_SEG)
+    st = rng.integers(1, 4, size=N_SEG)
+    sd = rng.integers(2, 61, size=N_SEG)
+    out = []
+    for side in (0, 1):
+        img = np.full((H, W), 90, np.uint8)
+        for i in range(N_RECT):
+            d = int(rd[i]) * side
+            _draw_rect(img, int(rx[i, 0]) - d, int(ry[i, 0]), int(rx[i, 1]) - d, int(ry[i, 1]), int(rg[i]), i % 2 == 1)
+        for i in range(N_SEG):
+            d = int(sd[i]) * side
+            _draw_seg(img, float(sx[i, 0]) - d, float(sy[i, 0]), float(sx[i, 1]) - d, float(sy[i, 1]), int(sg[i]),
+                      int(st[i]))
+        f = _blur3(img)
+        nrng = np.random.default_rng(seed + 1 if side else seed + 7919)
+        f = f + nrng.integers(-4, 5, size=f.shape)
+        out.append(np.clip(np.rint(f), 0, 255).astype(np.uint8))
+    return out[0], out[1]
+
+
+def synth_batch(W, H, seeds):
+    L = np.empty((len(seeds), H, W), np.uint8)
+    R = np.empty((len(seeds), H, W), np.uint8)
+    for i, s in enumerate(seeds):
+        L[i], R[i] = synth_pair(W, H, int(s))
+    return L, R

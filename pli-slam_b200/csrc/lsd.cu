@@ -1,0 +1,649 @@
+// Line extraction on sm_100a: LSD (pre-blur + x1.2 upscale, level-line field, ordered seeds, region growing,
+// rectangle fit) -> KeyLine construction / top-N by response -> LBD band descriptor and its binarisation.
+// Replaces Lineextractor::operator() (reference src/LineExtractor.cc:31-70), LSDDetectorC::detectImpl
+// (Thirdparty/line_descriptor/src/LSDDetector_custom.cpp:227-324) with the OpenCV LSD it wraps, and
+// BinaryDescriptor::compute (Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp:524-687,1026-1372).
+// The arithmetic follows oracle/cpp/lsd.cpp + lbd.cpp operation for operation (double where OpenCV uses double, float
+// with explicit _rn intrinsics where it uses float), including the greedy, order-dependent region growing: seeds are
+// visited in (gradient bin descending, raster ascending) order — the order cv2 4.13 was measured to use — and every
+// region is grown with the exact sequential acceptance rule, one warp per image.
+#include "plf_ctx.cuh"
+#include "blur.cuh"
+
+namespace {
+
+__constant__ float c_gaussL[21];
+__constant__ float c_gaussG[63];
+__constant__ int c_comb[64];
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kDegToRad = kPi / 180.0;
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4a  pre-blur (cv::GaussianBlur 8U, ksize/sigma from sigma_scale) and x`scale` upscale (INTER_LINEAR_EXACT)
+template <int K>
+__global__ void __launch_bounds__(256) blur_image_kernel(const uint8_t* src, size_t srcImgStride, int sp, uint8_t* dst,
+                                                         size_t dstImgStride, int dp, int w, int h, int imgFirst,
+                                                         const int t0, const int t1, const int t2, const int t3,
+                                                         const int t4, const int t5, const int t6) {
+    const int tx = (w + 31) >> 5;
+    const int img = imgFirst + blockIdx.y;
+    BlurJob j;
+    j.src = src + (size_t)img * srcImgStride;
+    j.dst = dst + (size_t)img * dstImgStride;
+    j.w = w; j.h = h; j.sp = sp; j.dp = dp;
+    const int all[7] = {t0, t1, t2, t3, t4, t5, t6};
+    int taps[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) taps[k] = all[k];
+    blur_tile<K>(j, taps, (blockIdx.x % tx) * 32, (blockIdx.x / tx) * 32);
+}
+
+__global__ void __launch_bounds__(256) lsd_upscale_kernel(PlfGeom g, const uint8_t* src, size_t srcImgStride, int sp,
+                                                          uint8_t* dst, int imgFirst) {
+    const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
+    if (dx >= g.Ws || dy >= g.Hs) return;
+    const int img = imgFirst + blockIdx.z;
+    const uint8_t* s = src + (size_t)img * srcImgStride;
+    const double inv = 1.0 / g.lsdScale;
+    int xo, xa, yo, ya;
+    {
+        const double f = inv * (dx + 0.5) - 0.5;
+        const int i = (int)floor(f);
+        if (i >= 0 && g.W > 1) {
+            if (i < g.W - 1) { xo = i; xa = __double2int_rn((f - i) * 256.0); } else { xo = g.W - 1; xa = 0; }
+        } else { xo = 0; xa = 0; }
+    }
+    {
+        const double f = inv * (dy + 0.5) - 0.5;
+        const int i = (int)floor(f);
+        if (i >= 0 && g.H > 1) {
+            if (i < g.H - 1) { yo = i; ya = __double2int_rn((f - i) * 256.0); } else { yo = g.H - 1; ya = 0; }
+        } else { yo = 0; ya = 0; }
+    }
+    const uint8_t* r0 = s + (size_t)yo * sp;
+    const uint8_t* r1 = s + (size_t)min(yo + 1, g.H - 1) * sp;
+    const int x1 = min(xo + 1, g.W - 1);
+    const int h0 = r0[xo] * (256 - xa) + r0[x1] * xa;
+    const int h1 = r1[xo] * (256 - xa) + r1[x1] * xa;
+    dst[(size_t)img * g.Ps * g.Hs + (size_t)dy * g.Ps + dx] = (uint8_t)((h0 * (256 - ya) + h1 * ya + 32768) >> 16);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4b  level-line field (LSD ll_angle): 2x2 gradient, squared norm, fastAtan2 angle (degrees), cosf/sinf of the angle,
+// per-image max of the squared norm over defined pixels.
+__global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, float* ang, float2* cs, int* n2o,
+                                                       int* n2max, int imgFirst) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int img = imgFirst + blockIdx.z;
+    int best = 0;
+    if (x < g.Ws && y < g.Hs) {
+        const size_t o = (size_t)img * g.Ws * g.Hs + (size_t)y * g.Ws + x;
+        float a = PLF_NOTDEF;
+        float2 c = make_float2(0.f, 0.f);
+        int n2 = 0;
+        if (x < g.Ws - 1 && y < g.Hs - 1) {
+            const uint8_t* r0 = U + (size_t)img * g.Ps * g.Hs + (size_t)y * g.Ps;
+            const uint8_t* r1 = r0 + g.Ps;
+            const int DA = (int)r1[x + 1] - (int)r0[x], BC = (int)r0[x + 1] - (int)r1[x];
+            const int gx = DA + BC, gy = DA - BC;
+            n2 = gx * gx + gy * gy;
+            const double norm = sqrt((double)n2 / 4.0);
+            if (!(norm <= g.rho)) {
+                a = fast_atan2_deg((float)gx, (float)-gy);
+                const float af = (float)((double)a * kDegToRad);
+                c.x = (float)cos((double)af);   // == glibc cosf(af) up to double rounding
+                c.y = (float)sin((double)af);
+                best = n2;
+            }
+        }
+        ang[o] = a;
+        cs[o] = c;
+        n2o[o] = n2;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(n2max + img, best);
+}
+
+__device__ __forceinline__ int lsd_bin(int n2, double binCoef) { return (int)(sqrt((double)n2 / 4.0) * binCoef); }
+__device__ __forceinline__ double lsd_bin_coef(int n2max, int nBins) {
+    const double maxGrad = n2max > 0 ? sqrt((double)n2max / 4.0) : -1.0;
+    return maxGrad > 0 ? (double)(nBins - 1) / maxGrad : 0.0;
+}
+
+__global__ void __launch_bounds__(256) lsd_hist_kernel(PlfGeom g, const float* ang, const int* n2, const int* n2max,
+                                                       int* hist, int imgFirst) {
+    extern __shared__ int s_hist[];
+    const int img = imgFirst + blockIdx.y;
+    for (int i = threadIdx.x; i < g.nBins; i += 256) s_hist[i] = 0;
+    __syncthreads();
+    const double coef = lsd_bin_coef(n2max[img], g.nBins);
+    const size_t base = (size_t)img * g.Ws * g.Hs;
+    const int npx = g.Ws * g.Hs;
+    for (int p = blockIdx.x * 256 + threadIdx.x; p < npx; p += gridDim.x * 256)
+        if (ang[base + p] != PLF_NOTDEF) atomicAdd(&s_hist[lsd_bin(n2[base + p], coef)], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < g.nBins; i += 256)
+        if (s_hist[i]) atomicAdd(hist + (size_t)img * g.nBins + i, s_hist[i]);
+}
+
+// Ordered seed list: defined pixels sorted by (bin descending, raster index ascending).  One 1024-thread block per
+// image walks the image in raster order; per-bin write cursors live in shared memory and the 32 warps of a chunk take
+// turns (only warps that hold a defined pixel), so the order inside a bin is raster order by construction.
+__global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float* ang, const int* n2, const int* n2max,
+                                                         const int* hist, int* seeds, int* nSeeds, int imgFirst) {
+    extern __shared__ int s_cur[];          // nBins cursors
+    __shared__ int s_scan[32];
+    __shared__ int s_any[32];
+    __shared__ int s_carry;
+    const int img = imgFirst + blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nBins = g.nBins;
+    // exclusive scan of the histogram in descending bin order
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nBins; b0 += 1024) {
+        const int r = b0 + tid;                 // position in descending order
+        const int b = nBins - 1 - r;
+        const int v = (r < nBins) ? hist[(size_t)img * nBins + b] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_scan[warp] = inc;
+        __syncthreads();
+        int base = s_carry;
+        for (int w = 0; w < warp; ++w) base += s_scan[w];
+        if (r < nBins) s_cur[b] = base + inc - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = base + inc;
+        __syncthreads();
+    }
+    if (tid == 0) nSeeds[img] = s_carry;
+    const double coef = lsd_bin_coef(n2max[img], nBins);
+    const size_t base = (size_t)img * g.Ws * g.Hs;
+    int* out = seeds + (size_t)img * g.seedCap;
+    const int npx = g.Ws * g.Hs;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int p0 = 0; p0 < npx; p0 += 1024) {
+        const int p = p0 + tid;
+        bool def = false;
+        int bin = 0;
+        if (p < npx && ang[base + p] != PLF_NOTDEF) { def = true; bin = lsd_bin(n2[base + p], coef); }
+        const unsigned wm = __ballot_sync(0xffffffffu, def);
+        if (lane == 0) s_any[warp] = wm != 0;
+        __syncthreads();
+        int pos = -1;
+        for (int w = 0; w < 32; ++w) {
+            if (!s_any[w]) continue;            // uniform across the block
+            if (warp == w && def) {
+                const unsigned grp = __match_any_sync(wm, bin);
+                const int b = s_cur[bin];
+                __syncwarp(wm);
+                pos = b + __popc(grp & lt);
+                if ((grp & lt) == 0) s_cur[bin] = b + __popc(grp);
+            }
+            __syncthreads();
+        }
+        if (pos >= 0) out[pos] = p;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4c  region growing + rectangle fit (LSD region_grow / region2rect / get_theta), refine = 0.
+// One warp per image; seeds in order; every region is grown with the exact sequential rule: list entries are expanded
+// front to back, their 8 neighbours in raster order, a neighbour is accepted iff unused and aligned with the CURRENT
+// region angle, which is updated after every acceptance.  A batch covers 4 list entries x 8 neighbours = 32 lanes in
+// processing order; the loads of a batch are issued together and the acceptance chain is resolved with ballots.
+__device__ __forceinline__ bool lsd_aligned(double a, double theta, double prec) {
+    double n = theta - a;
+    if (n < 0) n = -n;
+    if (n > (3 * kPi) / 2) {
+        n -= 2 * kPi;
+        if (n < 0) n = -n;
+    }
+    return n <= prec;
+}
+
+__device__ __forceinline__ double seq_sum_warp(double v, unsigned cnt, double acc) {
+    // acc += v[0]; acc += v[1]; ... in lane order (sequential rounding, like the scalar loop)
+    for (unsigned j = 0; j < cnt; ++j) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, v, j));
+    return acc;
+}
+
+__global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float* ang, const float2* cs, const int* n2,
+                                                      const int* seeds, const int* nSeeds, uint8_t* used, int* reg,
+                                                      float* segs, int* nSegsOut, int* err, int imgFirst) {
+    const int img = imgFirst + blockIdx.x, lane = threadIdx.x;
+    const int W = g.Ws, H = g.Hs;
+    const size_t base = (size_t)img * W * H;
+    const float* A = ang + base;
+    const float2* CS = cs + base;
+    const int* N2 = n2 + base;
+    uint8_t* U = used + base;
+    int* R = reg + base;
+    const int* S = seeds + (size_t)img * g.seedCap;
+    float* out = segs + (size_t)img * g.segCap * 4;
+    const int ns = nSeeds[img];
+    const double prec = g.prec;
+    int nSeg = 0;
+    const int e = lane >> 3, k = lane & 7;
+    const int ddx = (k < 3) ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6));
+    const int ddy = (k < 3) ? -1 : (k < 5 ? 0 : 1);
+    for (int s0 = 0; s0 < ns; s0 += 32) {
+        const int mySeed = (s0 + lane < ns) ? S[s0 + lane] : -1;
+        const int cntS = min(32, ns - s0);
+        for (int si = 0; si < cntS; ++si) {
+            const int p = __shfl_sync(0xffffffffu, mySeed, si);
+            if (U[p]) continue;        // uniform (same address)
+            // ---- region_grow -------------------------------------------------------------------------------------
+            int n = 1;
+            if (lane == 0) { R[0] = p; U[p] = 1; }
+            double regAngle = (double)A[p] * kDegToRad;
+            float sumdx = (float)cos(regAngle), sumdy = (float)sin(regAngle);
+            __syncwarp();
+            int i = 0;
+            while (i < n) {
+                const int nb = min(4, n - i);
+                int q = -1;
+                float a = PLF_NOTDEF;
+                float2 c = make_float2(0.f, 0.f);
+                bool valid = false;
+                if (e < nb) {
+                    const int rp = R[i + e];
+                    const int ry = rp / W, rx = rp - ry * W;
+                    const int xx = rx + ddx, yy = ry + ddy;
+                    if (xx >= 0 && yy >= 0 && xx < W && yy < H) {
+                        q = yy * W + xx;
+                        const uint8_t u = U[q];
+                        a = A[q];
+                        c = CS[q];
+                        valid = (u == 0) && (a != PLF_NOTDEF);
+                    }
+                }
+                const unsigned dup = __match_any_sync(0xffffffffu, valid ? q : -1 - lane);
+                unsigned pending = __ballot_sync(0xffffffffu, valid);
+                const double aRad = (double)a * kDegToRad;
+                while (pending) {
+                    const bool al = valid && lsd_aligned(aRad, regAngle, prec);
+                    const unsigned am = __ballot_sync(0xffffffffu, al) & pending;
+                    if (!am) break;
+                    const int Lw = __ffs(am) - 1;
+                    const int qL = __shfl_sync(0xffffffffu, q, Lw);
+                    const float cx = __shfl_sync(0xffffffffu, c.x, Lw), cy = __shfl_sync(0xffffffffu, c.y, Lw);
+                    const unsigned dupL = __shfl_sync(0xffffffffu, dup, Lw);
+                    if (lane == 0) { R[n] = qL; U[qL] = 1; }
+                    ++n;
+                    sumdx = __fadd_rn(sumdx, cx);
+                    sumdy = __fadd_rn(sumdy, cy);
+                    regAngle = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad;
+                    pending &= ~((2u << Lw) - 1u);
+                    pending &= ~dupL;
+                }
+                __syncwarp();
+                i += nb;
+            }
+            if (n < g.minRegSize) continue;
+            // ---- region2rect (sequential summation order reproduced with lane-ordered adds) -------------------------
+            double sx = 0, sy = 0, sw = 0;
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const unsigned cnt = min(32, n - i0);
+                double wv = 0, xw = 0, yw = 0;
+                if (lane < cnt) {
+                    const int rp = R[i0 + lane];
+                    const int ry = rp / W, rx = rp - ry * W;
+                    wv = sqrt((double)N2[rp] / 4.0);
+                    xw = __dmul_rn((double)rx, wv);
+                    yw = __dmul_rn((double)ry, wv);
+                }
+                sx = seq_sum_warp(xw, cnt, sx);
+                sy = seq_sum_warp(yw, cnt, sy);
+                sw = seq_sum_warp(wv, cnt, sw);
+            }
+            const double cxm = sx / sw, cym = sy / sw;
+            double Ixx = 0, Iyy = 0, Ixy = 0;
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const unsigned cnt = min(32, n - i0);
+                double vxx = 0, vyy = 0, vxy = 0;
+                if (lane < cnt) {
+                    const int rp = R[i0 + lane];
+                    const int ry = rp / W, rx = rp - ry * W;
+                    const double wv = sqrt((double)N2[rp] / 4.0);
+                    const double dx = __dsub_rn((double)rx, cxm), dy = __dsub_rn((double)ry, cym);
+                    vxx = __dmul_rn(__dmul_rn(dy, dy), wv);
+                    vyy = __dmul_rn(__dmul_rn(dx, dx), wv);
+                    vxy = -__dmul_rn(__dmul_rn(dx, dy), wv);
+                }
+                Ixx = seq_sum_warp(vxx, cnt, Ixx);
+                Iyy = seq_sum_warp(vyy, cnt, Iyy);
+                Ixy = seq_sum_warp(vxy, cnt, Ixy);
+            }
+            const double dI = __dsub_rn(Ixx, Iyy);
+            const double lambda = __dmul_rn(0.5, __dsub_rn(__dadd_rn(Ixx, Iyy),
+                                                           sqrt(__dadd_rn(__dmul_rn(dI, dI), __dmul_rn(__dmul_rn(4.0, Ixy), Ixy)))));
+            double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)__dsub_rn(lambda, Ixx), (float)Ixy)
+                                                   : (double)fast_atan2_deg((float)Ixy, (float)__dsub_rn(lambda, Iyy));
+            theta *= kDegToRad;
+            {
+                double diff = theta - regAngle;
+                while (diff <= -kPi) diff += 2 * kPi;
+                while (diff > kPi) diff -= 2 * kPi;
+                if (diff < 0) diff = -diff;
+                if (diff > prec) theta += kPi;
+            }
+            const double dxr = cos(theta), dyr = sin(theta);
+            double lmin = 0, lmax = 0;
+            for (int i0 = lane; i0 < n; i0 += 32) {
+                const int rp = R[i0];
+                const int ry = rp / W, rx = rp - ry * W;
+                const double l = __dadd_rn(__dmul_rn(__dsub_rn((double)rx, cxm), dxr), __dmul_rn(__dsub_rn((double)ry, cym), dyr));
+                lmax = fmax(lmax, l);
+                lmin = fmin(lmin, l);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+                lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+            }
+            if (lane == 0) {
+                if (nSeg < g.segCap) {
+                    double r[4] = {__dadd_rn(cxm, __dmul_rn(lmin, dxr)), __dadd_rn(cym, __dmul_rn(lmin, dyr)),
+                                   __dadd_rn(cxm, __dmul_rn(lmax, dxr)), __dadd_rn(cym, __dmul_rn(lmax, dyr))};
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        double v = r[q4] + 0.5;
+                        if (g.lsdScale != 1) v /= g.lsdScale;
+                        out[nSeg * 4 + q4] = (float)v;
+                    }
+                } else {
+                    atomicOr(err, 2);
+                }
+            }
+            if (nSeg < g.segCap) ++nSeg;
+            __syncwarp();
+        }
+    }
+    if (lane == 0) nSegsOut[img] = nSeg;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4d  KeyLine construction (LSDDetector_custom.cpp:268-308) and top-N by response (src/LineExtractor.cc:56-65;
+// declared rule: stable order, response descending then detection index ascending).  One block per image.
+__global__ void __launch_bounds__(256) keylines_kernel(PlfGeom g, const float* segs, const int* nSegs, plf_keyline* klAll,
+                                                       plf_keyline* klOut, int* nKl, int* err, double minLength,
+                                                       int nFeatures, int imgFirst) {
+    extern __shared__ float s_resp[];
+    __shared__ int s_warp[8];
+    __shared__ int s_carry;
+    const int img = imgFirst + blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = nSegs[img];
+    const float* sg = segs + (size_t)img * g.segCap * 4;
+    plf_keyline* all = klAll + (size_t)img * g.segCap;
+    plf_keyline* outk = klOut + (size_t)img * g.klCap;
+    const int W = g.W, H = g.H;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < m; i0 += 256) {
+        const int i = i0 + tid;
+        bool keep = false;
+        plf_keyline kl;
+        if (i < m) {
+            float ex[4] = {sg[i * 4], sg[i * 4 + 1], sg[i * 4 + 2], sg[i * 4 + 3]};
+#pragma unroll
+            for (int q = 0; q < 4; q += 2) {
+                if (ex[q] < 0) ex[q] = 0;
+                if (ex[q] >= W) ex[q] = (float)W - 1.0f;
+                if (ex[q + 1] < 0) ex[q + 1] = 0;
+                if (ex[q + 1] >= H) ex[q + 1] = (float)H - 1.0f;
+            }
+            const double dxx = (double)__fsub_rn(ex[0], ex[2]), dyy = (double)__fsub_rn(ex[1], ex[3]);
+            const double length = (double)(float)sqrt(__dadd_rn(__dmul_rn(dxx, dxx), __dmul_rn(dyy, dyy)));
+            keep = length > minLength;
+            kl.startPointX = ex[0]; kl.startPointY = ex[1]; kl.endPointX = ex[2]; kl.endPointY = ex[3];
+            kl.sPointInOctaveX = ex[0]; kl.sPointInOctaveY = ex[1]; kl.ePointInOctaveX = ex[2]; kl.ePointInOctaveY = ex[3];
+            kl.lineLength = (float)length;
+            const int ax = __float2int_rn(ex[0]), ay = __float2int_rn(ex[1]), bx = __float2int_rn(ex[2]), by = __float2int_rn(ex[3]);
+            kl.numOfPixels = max(abs(bx - ax), abs(by - ay)) + 1;   // cv::LineIterator(...).count, 8-connected
+            kl.angle = (float)atan2((double)__fsub_rn(ex[3], ex[1]), (double)__fsub_rn(ex[2], ex[0]));
+            kl.octave = 0;
+            kl.size = __fmul_rn(__fsub_rn(ex[2], ex[0]), __fsub_rn(ex[3], ex[1]));
+            kl.response = __fdiv_rn(kl.lineLength, (float)max(W, H));
+            kl.pt_x = __fdiv_rn(__fadd_rn(ex[2], ex[0]), 2.f);
+            kl.pt_y = __fdiv_rn(__fadd_rn(ex[3], ex[1]), 2.f);
+            kl.class_id = 0;
+        }
+        int inc = keep ? 1 : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        int base = s_carry;
+        for (int w = 0; w < warp; ++w) base += s_warp[w];
+        if (keep) {
+            const int pos = base + inc - 1;
+            kl.class_id = pos;
+            all[pos] = kl;
+            s_resp[pos] = kl.response;
+        }
+        __syncthreads();
+        if (tid == 255) s_carry = base + inc;
+        __syncthreads();
+    }
+    const int cnt = s_carry;
+    if (cnt > nFeatures && nFeatures != 0) {
+        for (int i = tid; i < cnt; i += 256) {
+            const float r = s_resp[i];
+            int rank = 0;
+            for (int j = 0; j < cnt; ++j) {
+                const float rj = s_resp[j];
+                rank += (rj > r) || (rj == r && j < i);
+            }
+            if (rank < nFeatures) {
+                plf_keyline kl = all[i];
+                kl.class_id = rank;
+                outk[rank] = kl;
+            }
+        }
+        if (tid == 0) nKl[img] = nFeatures;
+    } else {
+        if (cnt > g.klCap && tid == 0) atomicOr(err, 4);
+        const int c2 = min(cnt, g.klCap);
+        for (int i = tid; i < c2; i += 256) outk[i] = all[i];
+        if (tid == 0) nKl[img] = c2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4e  LBD: 5x5 sigma-1 blur (blur_image_kernel<5>), 3x3 Sobel to int16 pairs, band descriptor, binarisation.
+__global__ void __launch_bounds__(256) sobel_kernel(const uint8_t* src, size_t imgStride, int sp, short2* dst, int w, int h,
+                                                    int imgFirst) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const int img = imgFirst + blockIdx.z;
+    const uint8_t* s = src + (size_t)img * imgStride;
+    const uint8_t* r0 = s + (size_t)reflect101(y - 1, h) * sp;
+    const uint8_t* r1 = s + (size_t)y * sp;
+    const uint8_t* r2 = s + (size_t)reflect101(y + 1, h) * sp;
+    const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+    const int gx = ((int)r0[xp] - r0[xm]) + 2 * ((int)r1[xp] - r1[xm]) + ((int)r2[xp] - r2[xm]);
+    const int gy = ((int)r2[xm] - r0[xm]) + 2 * ((int)r2[x] - r0[x]) + ((int)r2[xp] - r0[xp]);
+    dst[(size_t)img * w * h + (size_t)y * w + x] = make_short2((short)gx, (short)gy);
+}
+
+// One warp per line.  Lane = row hID of the 63-row line support region (two passes of 32): each lane walks its row
+// sequentially (sCorX += dL[0] ...) exactly like the scalar loop, so the four row sums are bit-identical; the band
+// accumulation is then done in hID order by one lane per band.
+__global__ void __launch_bounds__(128) lbd_kernel(PlfGeom g, const short2* sobel, const plf_keyline* kls, const int* nKl,
+                                                  float* lbdOut, uint8_t* descOut, int imgFirst) {
+    __shared__ float s_row[4][63][4];
+    __shared__ float s_des[4][72];
+    const int img = imgFirst + blockIdx.y;
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int li = blockIdx.x * 4 + wl;
+    const int n = nKl[img];
+    if (li >= n) return;
+    const plf_keyline kl = kls[(size_t)img * g.klCap + li];
+    const short2* sb = sobel + (size_t)img * g.W * g.H;
+    const short realWidth = (short)g.W, imageWidth = realWidth - 1, imageHeight = (short)(g.H - 1);
+    const short lengthOfLSP = (short)kl.numOfPixels;
+    const short halfWidth = (lengthOfLSP - 1) / 2, halfHeight = 31;
+    const float midX = (float)(0.5 * (double)__fadd_rn(kl.sPointInOctaveX, kl.ePointInOctaveX));
+    const float midY = (float)(0.5 * (double)__fadd_rn(kl.sPointInOctaveY, kl.ePointInOctaveY));
+    const float dL0 = (float)cos((double)kl.angle), dL1 = (float)sin((double)kl.angle);
+    const float dO0 = -dL1, dO1 = dL0;
+    const float sX00 = __fadd_rn(__fadd_rn(__fmul_rn(-dL0, (float)halfWidth), __fmul_rn(dL1, (float)halfHeight)), midX);
+    const float sY00 = __fadd_rn(__fsub_rn(__fmul_rn(-dL1, (float)halfWidth), __fmul_rn(dL0, (float)halfHeight)), midY);
+    for (int hID = lane; hID < 63; hID += 32) {
+        // sCorX0 after hID steps of "sCorX0 -= dL[1]; sCorY0 += dL[0]" (sequential float updates)
+        float sX0 = sX00, sY0 = sY00;
+        for (int t = 0; t < hID; ++t) { sX0 = __fsub_rn(sX0, dL1); sY0 = __fadd_rn(sY0, dL0); }
+        float sX = sX0, sY = sY0;
+        float pgdL = 0, ngdL = 0, pgdO = 0, ngdO = 0;
+        for (short wID = 0; wID < lengthOfLSP; ++wID) {
+            short t = (short)roundf(sX);
+            const short xCor = (t < 0) ? 0 : (t > imageWidth) ? imageWidth : t;
+            t = (short)roundf(sY);
+            const short yCor = (t < 0) ? 0 : (t > imageHeight) ? imageHeight : t;
+            const short2 d = sb[(int)yCor * realWidth + xCor];
+            const float gDL = __fadd_rn(__fmul_rn((float)d.x, dL0), __fmul_rn((float)d.y, dL1));
+            const float gDO = __fadd_rn(__fmul_rn((float)d.x, dO0), __fmul_rn((float)d.y, dO1));
+            if (gDL > 0) pgdL = __fadd_rn(pgdL, gDL); else ngdL = __fsub_rn(ngdL, gDL);
+            if (gDO > 0) pgdO = __fadd_rn(pgdO, gDO); else ngdO = __fsub_rn(ngdO, gDO);
+            sX = __fadd_rn(sX, dL0);
+            sY = __fadd_rn(sY, dL1);
+        }
+        const float coef = c_gaussG[hID];
+        s_row[wl][hID][0] = __fmul_rn(coef, pgdL);
+        s_row[wl][hID][1] = __fmul_rn(coef, ngdL);
+        s_row[wl][hID][2] = __fmul_rn(coef, pgdO);
+        s_row[wl][hID][3] = __fmul_rn(coef, ngdO);
+    }
+    __syncwarp();
+    if (lane < 9) {
+        const int b = lane;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // pgdL ngdL pgdL2 ngdL2 pgdO ngdO pgdO2 ngdO2
+        const int h0 = max(0, 7 * (b - 1)), h1 = min(63, 7 * (b + 2));
+        for (int hID = h0; hID < h1; ++hID) {
+            const int hb = hID / 7;
+            // own band: gaussL[hID%7+7]; band above (b == hb-1): gaussL[hID%7+14]; band below (b == hb+1): gaussL[hID%7]
+            const float cf = c_gaussL[hID % 7 + (b == hb ? 7 : (b == hb - 1 ? 14 : 0))];
+            const float pL = s_row[wl][hID][0], nL = s_row[wl][hID][1], pO = s_row[wl][hID][2], nO = s_row[wl][hID][3];
+            const float cf2 = __fmul_rn(cf, cf);
+            acc[0] = __fadd_rn(acc[0], __fmul_rn(cf, pL));
+            acc[1] = __fadd_rn(acc[1], __fmul_rn(cf, nL));
+            acc[2] = __fadd_rn(acc[2], __fmul_rn(cf2, __fmul_rn(pL, pL)));
+            acc[3] = __fadd_rn(acc[3], __fmul_rn(cf2, __fmul_rn(nL, nL)));
+            acc[4] = __fadd_rn(acc[4], __fmul_rn(cf, pO));
+            acc[5] = __fadd_rn(acc[5], __fmul_rn(cf, nO));
+            acc[6] = __fadd_rn(acc[6], __fmul_rn(cf2, __fmul_rn(pO, pO)));
+            acc[7] = __fadd_rn(acc[7], __fmul_rn(cf2, __fmul_rn(nO, nO)));
+        }
+        const float invN = (b == 0 || b == 8) ? (float)(1.0 / (7 * 2.0)) : (float)(1.0 / (7 * 3.0));
+        float* des = &s_des[wl][b * 8];
+        float temp;
+        temp = __fmul_rn(acc[0], invN); des[0] = temp; des[4] = sqrtf(__fsub_rn(__fmul_rn(acc[2], invN), __fmul_rn(temp, temp)));
+        temp = __fmul_rn(acc[1], invN); des[1] = temp; des[5] = sqrtf(__fsub_rn(__fmul_rn(acc[3], invN), __fmul_rn(temp, temp)));
+        temp = __fmul_rn(acc[4], invN); des[2] = temp; des[6] = sqrtf(__fsub_rn(__fmul_rn(acc[6], invN), __fmul_rn(temp, temp)));
+        temp = __fmul_rn(acc[5], invN); des[3] = temp; des[7] = sqrtf(__fsub_rn(__fmul_rn(acc[7], invN), __fmul_rn(temp, temp)));
+    }
+    __syncwarp();
+    float* des = s_des[wl];
+    if (lane == 0) {
+        float tempM = 0, tempS = 0;
+        for (int b = 0; b < 9; ++b) {
+            for (int q = 0; q < 4; ++q) tempM = __fadd_rn(tempM, __fmul_rn(des[b * 8 + q], des[b * 8 + q]));
+            for (int q = 4; q < 8; ++q) tempS = __fadd_rn(tempS, __fmul_rn(des[b * 8 + q], des[b * 8 + q]));
+        }
+        tempM = __fdiv_rn(1.f, sqrtf(tempM));
+        tempS = __fdiv_rn(1.f, sqrtf(tempS));
+        for (int b = 0; b < 9; ++b) {
+            for (int q = 0; q < 4; ++q) des[b * 8 + q] = __fmul_rn(des[b * 8 + q], tempM);
+            for (int q = 4; q < 8; ++q) des[b * 8 + q] = __fmul_rn(des[b * 8 + q], tempS);
+        }
+        for (int i = 0; i < 72; ++i)
+            if ((double)des[i] > 0.4) des[i] = (float)0.4;
+        float temp = 0;
+        for (int i = 0; i < 72; ++i) temp = __fadd_rn(temp, __fmul_rn(des[i], des[i]));
+        temp = __fdiv_rn(1.f, sqrtf(temp));
+        for (int i = 0; i < 72; ++i) des[i] = __fmul_rn(des[i], temp);
+    }
+    __syncwarp();
+    float* lo = lbdOut + ((size_t)img * g.klCap + li) * 72;
+    for (int i = lane; i < 72; i += 32) lo[i] = des[i];
+    {
+        const float* f1 = &des[8 * c_comb[lane * 2]];
+        const float* f2 = &des[8 * c_comb[lane * 2 + 1]];
+        int r = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r |= (f1[i] > f2[i]) << i;
+        descOut[((size_t)img * g.klCap + li) * 32 + lane] = (uint8_t)r;
+    }
+}
+
+}  // namespace
+
+static bool s_tablesReady[64] = {};
+
+static void upload_lbd_tables(int device) {
+    if (device < 64 && s_tablesReady[device]) return;
+    // weight tables of the BinaryDescriptor constructor (binary_descriptor_custom.cpp:227-258), integer divisions kept
+    float gl[21], gg[63];
+    {
+        const int w = 7;
+        double u = (w * 3 - 1) / 2, sigma = (w * 2 + 1) / 2, inv = -1 / (2 * sigma * sigma);
+        for (int i = 0; i < 21; ++i) { double d = i - u; gl[i] = (float)std::exp(d * d * inv); }
+        u = (9 * w - 1) / 2; sigma = u; inv = -1 / (2 * sigma * sigma);
+        for (int i = 0; i < 63; ++i) { double d = i - u; gg[i] = (float)std::exp(d * d * inv); }
+    }
+    static const int comb[64] = {0, 1, 0, 2, 0, 3, 0, 4, 0, 5, 0, 6, 1, 2, 1, 3, 1, 4, 1, 5, 1, 6, 2, 3, 2, 4, 2, 5, 2, 6, 2, 7,
+                                 2, 8, 3, 4, 3, 5, 3, 6, 3, 7, 3, 8, 4, 5, 4, 6, 4, 7, 4, 8, 5, 6, 5, 7, 5, 8, 6, 7, 6, 8, 7, 8};
+    cudaMemcpyToSymbol(c_gaussL, gl, sizeof gl);
+    cudaMemcpyToSymbol(c_gaussG, gg, sizeof gg);
+    cudaMemcpyToSymbol(c_comb, comb, sizeof comb);
+    if (device < 64) s_tablesReady[device] = true;
+}
+
+int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
+    const PlfGeom& g = c->g;
+    cudaStream_t s = c->stream;
+    upload_lbd_tables(c->device);
+    const uint8_t* in = c->d_pyr + g.lv[0].off;      // level 0 of the pyramid block is the input image
+    const size_t inStride = (size_t)g.pyrBytes;
+    const int ip = g.lv[0].pitch;
+    const size_t imgBytes = (size_t)ip * g.H;
+    const int tiles = ((g.W + 31) / 32) * ((g.H + 31) / 32);
+    int launches = 0;
+    const uint8_t* upSrc = in;
+    size_t upStride = inStride;
+    if (g.lsdK > 0) {
+        const int* t = g.lsdTaps;
+        if (g.lsdK == 7) blur_image_kernel<7><<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(in, inStride, ip, c->d_lsdBlur, imgBytes, ip, g.W, g.H, imgFirst, t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
+        else if (g.lsdK == 5) blur_image_kernel<5><<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(in, inStride, ip, c->d_lsdBlur, imgBytes, ip, g.W, g.H, imgFirst, t[0], t[1], t[2], t[3], t[4], 0, 0);
+        else blur_image_kernel<3><<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(in, inStride, ip, c->d_lsdBlur, imgBytes, ip, g.W, g.H, imgFirst, t[0], t[1], t[2], 0, 0, 0, 0);
+        upSrc = c->d_lsdBlur;
+        upStride = imgBytes;
+        ++launches;
+    }
+    lsd_upscale_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, imgFirst);
+    cudaMemsetAsync(c->d_n2max + imgFirst, 0, nImg * sizeof(int), s);
+    cudaMemsetAsync(c->d_hist + (size_t)imgFirst * g.nBins, 0, (size_t)nImg * g.nBins * sizeof(int), s);
+    lsd_grad_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_ang, c->d_cs, c->d_n2, c->d_n2max, imgFirst);
+    lsd_hist_kernel<<<dim3(64, nImg), 256, g.nBins * sizeof(int), s>>>(g, c->d_ang, c->d_n2, c->d_n2max, c->d_hist, imgFirst);
+    lsd_order_kernel<<<nImg, 1024, g.nBins * sizeof(int), s>>>(g, c->d_ang, c->d_n2, c->d_n2max, c->d_hist, c->d_seeds, c->d_nSeeds, imgFirst);
+    cudaMemsetAsync(c->d_used + (size_t)imgFirst * g.Ws * g.Hs, 0, (size_t)nImg * g.Ws * g.Hs, s);
+    lsd_grow_kernel<<<nImg, 32, 0, s>>>(g, c->d_ang, c->d_cs, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_err, imgFirst);
+    const double minLen = c->p.min_line_length * std::min(g.W, g.H);
+    keylines_kernel<<<nImg, 256, g.segCap * sizeof(float), s>>>(g, c->d_segs, c->d_nSegs, c->d_klAll, c->d_kl, c->d_nKl, c->d_err, minLen, c->p.lsd_nfeatures, imgFirst);
+    const int lt[5] = {14, 62, 104, 62, 14};
+    blur_image_kernel<5><<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(in, inStride, ip, c->d_lbdBlur, imgBytes, ip, g.W, g.H, imgFirst, lt[0], lt[1], lt[2], lt[3], lt[4], 0, 0);
+    sobel_kernel<<<dim3((g.W + 31) / 32, (g.H + 7) / 8, nImg), dim3(32, 8), 0, s>>>(c->d_lbdBlur, imgBytes, ip, c->d_sobel, g.W, g.H, imgFirst);
+    lbd_kernel<<<dim3((g.klCap + 3) / 4, nImg), 128, 0, s>>>(g, c->d_sobel, c->d_kl, c->d_nKl, c->d_lbd, c->d_ldesc, imgFirst);
+    return launches + 9;
+}

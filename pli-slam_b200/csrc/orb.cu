@@ -1,0 +1,651 @@
+// ORB extraction on sm_100a: scale pyramid, 7x7 blur, per-cell FAST-9 with threshold retry, quadtree keypoint
+// distribution, intensity-centroid orientation and 256-bit rBRIEF.  Replaces ORBextractor::operator()
+// (reference src/ORBextractor.cc:1068-1150) and everything it calls.  Integer/byte work, bit-exact against
+// oracle/cpp/orb.cpp; float expressions are written with explicit _rn intrinsics (the TU is also built with
+// -fmad=false) so that nothing is contracted into FMA.
+#include "plf_ctx.cuh"
+#include "blur.cuh"
+
+namespace {
+
+__constant__ int c_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1a  pyramid level l from level l-1: cv::resize(INTER_LINEAR) 8U, 11-bit fixed point (src/ORBextractor.cc:1165).
+// One thread per output pixel, 32x8 tiles; the four taps come through L1/L2 (each source byte is reused by ~1.4
+// output pixels in x and y, so the level is read from HBM once).
+__global__ void __launch_bounds__(256) pyr_resize_kernel(PlfGeom g, uint8_t* pyr, int level, int imgFirst) {
+    const PlfLevel& d = g.lv[level];
+    const PlfLevel& s = g.lv[level - 1];
+    const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
+    if (dx >= d.w || dy >= d.h) return;
+    const int img = imgFirst + blockIdx.z;
+    const uint8_t* src = pyr + (size_t)img * g.pyrBytes + s.off;
+    uint8_t* dst = pyr + (size_t)img * g.pyrBytes + d.off;
+    const double scale_x = (double)s.w / d.w, scale_y = (double)s.h / d.h;
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+    int sx = (int)floorf(fx);
+    fx = __fsub_rn(fx, (float)sx);
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= s.w - 1) { fx = 0.f; sx = s.w - 1; }
+    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+    int sy = (int)floorf(fy);
+    fy = __fsub_rn(fy, (float)sy);
+    if (sy < 0) { fy = 0.f; sy = 0; }
+    if (sy >= s.h - 1) { fy = 0.f; sy = s.h - 1; }
+    const int ax0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f)), ax1 = __float2int_rn(__fmul_rn(fx, 2048.f));
+    const int ay0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fy), 2048.f)), ay1 = __float2int_rn(__fmul_rn(fy, 2048.f));
+    const int sx1 = min(sx + 1, s.w - 1), sy1 = min(sy + 1, s.h - 1);
+    const uint8_t* r0 = src + (size_t)sy * s.pitch;
+    const uint8_t* r1 = src + (size_t)sy1 * s.pitch;
+    const int h0 = r0[sx] * ax0 + r0[sx1] * ax1;
+    const int h1 = r1[sx] * ax0 + r1[sx1] * ax1;
+    dst[(size_t)dy * d.pitch + dx] = (uint8_t)((((ay0 * (h0 >> 4)) >> 16) + ((ay1 * (h1 >> 4)) >> 16) + 2) >> 2);
+}
+
+// all pyramid levels in one launch: blockIdx.x enumerates the 32x32 tiles of every level
+__global__ void __launch_bounds__(256) blur_pyramid_kernel(PlfGeom g, const uint8_t* pyr, uint8_t* blur, int imgFirst) {
+    int t = blockIdx.x, l = 0, tx = 0;
+    for (; l < g.nLevels; ++l) {
+        tx = (g.lv[l].w + 31) >> 5;
+        int n = tx * ((g.lv[l].h + 31) >> 5);
+        if (t < n) break;
+        t -= n;
+    }
+    if (l >= g.nLevels) return;
+    const int img = imgFirst + blockIdx.y;
+    BlurJob j;
+    j.src = pyr + (size_t)img * g.pyrBytes + g.lv[l].off;
+    j.dst = blur + (size_t)img * g.pyrBytes + g.lv[l].off;
+    j.w = g.lv[l].w; j.h = g.lv[l].h; j.sp = j.dp = g.lv[l].pitch;
+    const int taps[7] = {18, 34, 48, 56, 48, 34, 18};
+    blur_tile<7>(j, taps, (t % tx) * 32, (t / tx) * 32);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2a  FAST-9/16 per grid cell with the ORB_SLAM3 retry: cv::FAST(window, iniTh, nms) and, only if the cell came back
+// empty, cv::FAST(window, minTh, nms) (src/ORBextractor.cc:787-854).  One block per cell window.  The corner score
+// s = max{t : still a corner} does not depend on the threshold, and for a pixel with s >= t strict 3x3 NMS against
+// thresholded neighbours equals NMS against raw scores, so one score map serves both thresholds.
+// Corner score s = max{t : a 9-arc has all d > t or all d < -t} by bisection on t with 16-bit arc masks.
+// Compare/logic ops only, on purpose: a min/max formulation (OpenCV's cornerScore) is fused by ptxas 12.9 — and by
+// the 580 driver's JIT — into VIMNMX3 chains that return wrong values on sm_100a when min, max and negation are mixed
+// (reproduced in isolation; ptxas -O0, which emits no VIMNMX3, is correct).  tests/test_build.py asserts that the
+// library contains no VIMNMX3.
+__device__ __forceinline__ bool fast_run9(unsigned m) {
+    const unsigned m2 = m | (m << 16);
+    unsigned r = m2 & (m2 >> 1);
+    r &= r >> 2;
+    r &= r >> 4;
+    r &= (m2 >> 8);
+    return (r & 0xFFFFu) != 0u;
+}
+__device__ __forceinline__ int fast_score16(const int* d) {
+    int t = -1;
+#pragma unroll
+    for (int bit = 128; bit > 0; bit >>= 1) {
+        const int c = t + bit;
+        unsigned mb = 0, md = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            mb |= (unsigned)(d[k] > c) << k;
+            md |= (unsigned)(d[k] < -c) << k;
+        }
+        if (fast_run9(mb) || fast_run9(md)) t = c;
+    }
+    return t;
+}
+
+#define FAST_MAXW 72   // window side limit: wCell+6 < 2*30+6
+__global__ void __launch_bounds__(256) fast_cells_kernel(PlfGeom g, const uint8_t* pyr, const PlfCell* cells,
+                                                         int* cellCount, uint32_t* cand, int imgFirst) {
+    __shared__ uint8_t s_win[FAST_MAXW * FAST_MAXW];
+    __shared__ uint8_t s_sc[FAST_MAXW * FAST_MAXW];
+    __shared__ int s_warp[8];
+    __shared__ int s_anyIni;
+    const PlfCell c = cells[blockIdx.x];
+    const int img = imgFirst + blockIdx.y;
+    const PlfLevel& lv = g.lv[c.level];
+    const uint8_t* src = pyr + (size_t)img * g.pyrBytes + lv.off;
+    const int cols = c.x1 - c.x0, rows = c.y1 - c.y0;
+    const int aw = cols - 6, ah = rows - 6;
+    const int tid = threadIdx.x;
+    int* outCount = cellCount + (size_t)img * g.nCellsTotal + blockIdx.x;
+    if (aw <= 0 || ah <= 0) {
+        if (tid == 0) *outCount = 0;
+        return;
+    }
+    if (tid == 0) s_anyIni = 0;
+    for (int i = tid; i < cols * rows; i += 256) {
+        int y = i / cols, x = i - y * cols;
+        s_win[y * FAST_MAXW + x] = src[(size_t)(c.y0 + y) * lv.pitch + c.x0 + x];
+    }
+    __syncthreads();
+    const int offs[16] = {3 * FAST_MAXW,      3 * FAST_MAXW + 1,  2 * FAST_MAXW + 2,  FAST_MAXW + 3,
+                          3,                  -FAST_MAXW + 3,     -2 * FAST_MAXW + 2, -3 * FAST_MAXW + 1,
+                          -3 * FAST_MAXW,     -3 * FAST_MAXW - 1, -2 * FAST_MAXW - 2, -FAST_MAXW - 3,
+                          -3,                 FAST_MAXW - 3,      2 * FAST_MAXW - 2,  3 * FAST_MAXW - 1};
+    const int minTh = g.minTh, iniTh = g.iniTh;
+    for (int i = tid; i < aw * ah; i += 256) {
+        const int y = i / aw, x = i - y * aw;
+        const uint8_t* p = &s_win[(y + 3) * FAST_MAXW + x + 3];
+        const int v = *p;
+        // cheap reject at minTh: 16-bit brighter/darker masks, look for a run of 9
+        unsigned mb = 0, md = 0;
+        int d[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            d[k] = v - (int)p[offs[k]];
+            mb |= (unsigned)(d[k] > minTh) << k;
+            md |= (unsigned)(d[k] < -minTh) << k;
+        }
+        int s = 0;
+        if (fast_run9(mb) || fast_run9(md)) s = fast_score16(d);   // corner at minTh => s >= minTh
+        s_sc[y * FAST_MAXW + x] = (uint8_t)s;
+    }
+    __syncthreads();
+    // strict 3x3 NMS inside the detection area (outside counts as 0); flags overwrite s_win
+    bool anyIni = false;
+    for (int i = tid; i < aw * ah; i += 256) {
+        const int y = i / aw, x = i - y * aw;
+        const int s = s_sc[y * FAST_MAXW + x];
+        bool keep = s > 0;
+        if (keep) {
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    if (dx == 0 && dy == 0) continue;
+                    const int yy = y + dy, xx = x + dx;
+                    const int n = (yy < 0 || xx < 0 || yy >= ah || xx >= aw) ? 0 : s_sc[yy * FAST_MAXW + xx];
+                    keep = keep && (s > n);
+                }
+        }
+        s_win[y * FAST_MAXW + x] = keep ? 1 : 0;
+        anyIni |= keep && s >= iniTh;
+    }
+    if (__syncthreads_or(anyIni)) anyIni = true;
+    const int th = anyIni ? iniTh : minTh;
+    // ordered (raster) compaction: each thread owns a contiguous run of pixels
+    const int n = aw * ah, per = (n + 255) / 256;
+    const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i) {
+        const int y = i / aw, x = i - y * aw;
+        cnt += (s_win[y * FAST_MAXW + x] && s_sc[y * FAST_MAXW + x] >= th);
+    }
+    // block exclusive scan of cnt
+    const int lane = tid & 31, warp = tid >> 5;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        if (w < warp) base += s_warp[w];
+        total += s_warp[w];
+    }
+    int pos = base + inc - cnt;
+    uint32_t* out = cand + (size_t)img * g.candCapTotal + c.outBase;
+    const int relx = c.x0 + 3 - PLF_MINB, rely = c.y0 + 3 - PLF_MINB;
+    for (int i = i0; i < i1; ++i) {
+        const int y = i / aw, x = i - y * aw;
+        const int s = s_sc[y * FAST_MAXW + x];
+        if (s_win[y * FAST_MAXW + x] && s >= th) {
+            if (pos < c.cap) out[pos] = (uint32_t)(relx + x) | ((uint32_t)(rely + y) << 12) | ((uint32_t)s << 24);
+            ++pos;
+        }
+    }
+    if (tid == 0) *outCount = min(total, c.cap);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2b  quadtree ("octree") keypoint distribution, ORBextractor::DistributeOctTree (src/ORBextractor.cc:537-761).
+// One warp per (level, image).  The std::list of nodes is a doubly linked list in shared memory that every lane
+// reads uniformly and lane 0 mutates; the per-node key vectors are contiguous slices of two ping-pong point buffers
+// and a node is split by a warp-wide stable 4-way partition (ballot + popc).  List order, the expansion order of the
+// final phase ((count, creation order) largest first — the declared stand-in for the reference's heap-address tie
+// break) and the first-max-response rule are reproduced exactly, so the retained set AND its order are bit-exact.
+struct QNode {
+    short ulx, uly, brx, bry;
+    int start, cnt;
+    int seq;
+    short next, prev;
+    short buf;      // which ping-pong buffer holds the points
+    short pad;
+};
+
+struct QState {
+    int head, tail, size, freeHead, seq;
+};
+
+__device__ __forceinline__ int q_alloc(QNode* nodes, QState* st) {
+    int n = st->freeHead;
+    st->freeHead = nodes[n].next;
+    return n;
+}
+__device__ __forceinline__ void q_free(QNode* nodes, QState* st, int n) {
+    nodes[n].next = (short)st->freeHead;
+    st->freeHead = n;
+}
+__device__ __forceinline__ void q_push_front(QNode* nodes, QState* st, int n) {
+    nodes[n].prev = -1;
+    nodes[n].next = (short)st->head;
+    if (st->head >= 0) nodes[st->head].prev = (short)n; else st->tail = n;
+    st->head = n;
+    st->size++;
+}
+__device__ __forceinline__ void q_push_back(QNode* nodes, QState* st, int n) {
+    nodes[n].next = -1;
+    nodes[n].prev = (short)st->tail;
+    if (st->tail >= 0) nodes[st->tail].next = (short)n; else st->head = n;
+    st->tail = n;
+    st->size++;
+}
+__device__ __forceinline__ void q_unlink(QNode* nodes, QState* st, int n) {
+    const int p = nodes[n].prev, q = nodes[n].next;
+    if (p >= 0) nodes[p].next = (short)q; else st->head = q;
+    if (q >= 0) nodes[q].prev = (short)p; else st->tail = p;
+    st->size--;
+}
+
+// Splits node n (ExtractorNode::DivideNode, :479-535): partitions its points into the other buffer, pushes the
+// non-empty children to the list front in order n1..n4, appends children with >1 points to expandList.
+// Executed by the whole warp; returns the number of children with more than one point.
+__device__ int q_divide(QNode* nodes, QState* st, int n, uint32_t* buf0, uint32_t* buf1, int* expandList,
+                        int* nExpand, int lane) {
+    const QNode nd = nodes[n];
+    const int halfX = (nd.brx - nd.ulx + 1) >> 1, halfY = (nd.bry - nd.uly + 1) >> 1;   // ceil(w/2)
+    const int mx = nd.ulx + halfX, my = nd.uly + halfY;
+    const uint32_t* src = (nd.buf ? buf1 : buf0) + nd.start;
+    uint32_t* dst = (nd.buf ? buf0 : buf1) + nd.start;
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int i = lane; i < ((nd.cnt + 31) & ~31); i += 32) {
+        int q = -1;
+        if (i < nd.cnt) {
+            const uint32_t p = src[i];
+            const int x = p & 0xFFF, y = (p >> 12) & 0xFFF;
+            q = (x < mx) ? ((y < my) ? 0 : 2) : ((y < my) ? 1 : 3);
+        }
+        c0 += __popc(__ballot_sync(0xffffffffu, q == 0));
+        c1 += __popc(__ballot_sync(0xffffffffu, q == 1));
+        c2 += __popc(__ballot_sync(0xffffffffu, q == 2));
+        c3 += __popc(__ballot_sync(0xffffffffu, q == 3));
+    }
+    int b0 = 0, b1 = c0, b2 = c0 + c1, b3 = c0 + c1 + c2;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int i = lane; i < ((nd.cnt + 31) & ~31); i += 32) {
+        int q = -1;
+        uint32_t p = 0;
+        if (i < nd.cnt) {
+            p = src[i];
+            const int x = p & 0xFFF, y = (p >> 12) & 0xFFF;
+            q = (x < mx) ? ((y < my) ? 0 : 2) : ((y < my) ? 1 : 3);
+        }
+        const unsigned m0 = __ballot_sync(0xffffffffu, q == 0), m1 = __ballot_sync(0xffffffffu, q == 1);
+        const unsigned m2 = __ballot_sync(0xffffffffu, q == 2), m3 = __ballot_sync(0xffffffffu, q == 3);
+        if (q == 0) dst[b0 + __popc(m0 & lt)] = p;
+        else if (q == 1) dst[b1 + __popc(m1 & lt)] = p;
+        else if (q == 2) dst[b2 + __popc(m2 & lt)] = p;
+        else if (q == 3) dst[b3 + __popc(m3 & lt)] = p;
+        b0 += __popc(m0); b1 += __popc(m1); b2 += __popc(m2); b3 += __popc(m3);
+    }
+    __syncwarp();
+    int nBig = 0;
+    const int cnts[4] = {c0, c1, c2, c3};
+    const int starts[4] = {nd.start, nd.start + c0, nd.start + c0 + c1, nd.start + c0 + c1 + c2};
+    if (lane == 0) {
+        for (int q = 0; q < 4; ++q) {
+            if (cnts[q] == 0) continue;
+            const int k = q_alloc(nodes, st);
+            QNode& ch = nodes[k];
+            ch.ulx = (q & 1) ? (short)mx : nd.ulx;
+            ch.brx = (q & 1) ? nd.brx : (short)mx;
+            ch.uly = (q & 2) ? (short)my : nd.uly;
+            ch.bry = (q & 2) ? nd.bry : (short)my;
+            ch.start = starts[q];
+            ch.cnt = cnts[q];
+            ch.buf = nd.buf ^ 1;
+            ch.seq = st->seq++;
+            q_push_front(nodes, st, k);
+            if (cnts[q] > 1) expandList[(*nExpand)++] = k;
+        }
+    }
+    for (int q = 0; q < 4; ++q) nBig += cnts[q] > 1;
+    __syncwarp();
+    return nBig;
+}
+
+__global__ void __launch_bounds__(32) octree_kernel(PlfGeom g, const PlfCell* cells, const int* cellCount,
+                                                    const uint32_t* cand, uint32_t* scratch, uint32_t* lvlKp,
+                                                    int* lvlN, int* err, int imgFirst, int poolSize) {
+    extern __shared__ unsigned char smem_raw[];
+    const int level = blockIdx.x, img = imgFirst + blockIdx.y, lane = threadIdx.x;
+    const PlfLevel& lv = g.lv[level];
+    QNode* nodes = reinterpret_cast<QNode*>(smem_raw);
+    int* listA = reinterpret_cast<int*>(nodes + poolSize);
+    int* listB = listA + poolSize;
+    __shared__ QState st;
+    __shared__ int s_nA, s_nB;
+    const int N = lv.quota;
+    uint32_t* buf0 = scratch + ((size_t)img * 2 + 0) * g.candCapTotal + lv.candOff;
+    uint32_t* buf1 = scratch + ((size_t)img * 2 + 1) * g.candCapTotal + lv.candOff;
+    const uint32_t* cnd = cand + (size_t)img * g.candCapTotal;
+    const int* cc = cellCount + (size_t)img * g.nCellsTotal + lv.cellFirst;
+    const PlfCell* cl = cells + lv.cellFirst;
+    uint32_t* outKp = lvlKp + (size_t)img * g.kpLevelCapTotal + lv.kpOff;
+    int* outN = lvlN + (size_t)img * g.nLevels + level;
+    const unsigned lt = (1u << lane) - 1u;
+
+    // root nodes (:541-561): nIni = round(W'/H'), hX = W'/nIni in float; a point goes to root (int)(x/hX)
+    const int Wd = lv.w - 2 * PLF_MINB, Hd = lv.h - 2 * PLF_MINB;
+    const int nIni = lv.nIni;   // <= 4, checked at plf_create
+    const float hX = __fdiv_rn((float)Wd, (float)nIni);
+    if (lane == 0) {
+        st.head = st.tail = -1;
+        st.size = 0;
+        st.seq = 0;
+        st.freeHead = 0;
+        for (int i = 0; i < poolSize; ++i) nodes[i].next = (short)(i + 1 < poolSize ? i + 1 : -1);
+        s_nA = s_nB = 0;
+    }
+    __syncwarp();
+    // stable bucketing of vToDistributeKeys (cell-major, raster inside a cell) into the roots -> buf0
+    int rc[4] = {0, 0, 0, 0};
+    for (int ci = 0; ci < lv.nCells; ++ci) {
+        const int cnt = cc[ci], base = cl[ci].outBase;
+        for (int i = lane; i < ((cnt + 31) & ~31); i += 32) {
+            int r = -1;
+            if (i < cnt) r = (int)__fdiv_rn((float)(cnd[base + i] & 0xFFF), hX);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rc[q] += __popc(__ballot_sync(0xffffffffu, r == q));
+        }
+    }
+    int rs[4] = {0, rc[0], rc[0] + rc[1], rc[0] + rc[1] + rc[2]};
+    {
+        int run[4] = {rs[0], rs[1], rs[2], rs[3]};
+        for (int ci = 0; ci < lv.nCells; ++ci) {
+            const int cnt = cc[ci], base = cl[ci].outBase;
+            for (int i = lane; i < ((cnt + 31) & ~31); i += 32) {
+                int r = -1;
+                uint32_t p = 0;
+                if (i < cnt) {
+                    p = cnd[base + i];
+                    r = (int)__fdiv_rn((float)(p & 0xFFF), hX);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned m = __ballot_sync(0xffffffffu, r == q);
+                    if (r == q) buf0[run[q] + __popc(m & lt)] = p;
+                    run[q] += __popc(m);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = 0; i < nIni; ++i) {
+            const int seq = st.seq++;
+            if (rc[i] == 0) continue;   // empty roots are erased (:579-580)
+            const int k = q_alloc(nodes, &st);
+            QNode& nd = nodes[k];
+            nd.ulx = (short)(int)__fmul_rn(hX, (float)i);
+            nd.brx = (short)(int)__fmul_rn(hX, (float)(i + 1));
+            nd.uly = 0;
+            nd.bry = (short)Hd;
+            nd.start = rs[i];
+            nd.cnt = rc[i];
+            nd.buf = 0;
+            nd.seq = seq;
+            q_push_back(nodes, &st, k);
+        }
+    }
+    __syncwarp();
+
+    bool finish = (st.size == 0);
+    while (!finish) {
+        const int prevSize = st.size;
+        int nToExpand = 0;
+        if (lane == 0) s_nA = 0;
+        __syncwarp();
+        int cur = st.head;
+        while (cur >= 0) {
+            const int nxt = nodes[cur].next;
+            if (nodes[cur].cnt > 1) {
+                nToExpand += q_divide(nodes, &st, cur, buf0, buf1, listA, &s_nA, lane);
+                if (lane == 0) { q_unlink(nodes, &st, cur); q_free(nodes, &st, cur); }
+                __syncwarp();
+            }
+            cur = nxt;
+        }
+        if (st.size >= N || st.size == prevSize) {
+            finish = true;
+        } else if (st.size + nToExpand * 3 > N) {
+            int* prev = listA;
+            int* nextL = listB;
+            int* nPrev = &s_nA;
+            int* nNext = &s_nB;
+            while (!finish) {
+                const int prevSize2 = st.size;
+                if (lane == 0) *nNext = 0;
+                __syncwarp();
+                const int m = *nPrev;
+                for (int it = 0; it < m; ++it) {
+                    // next node to expand: largest (count, creation order) among the unprocessed entries
+                    unsigned long long best = 0;
+                    int bestIdx = -1;
+                    for (int i = lane; i < m; i += 32) {
+                        const int k = prev[i];
+                        if (k < 0) continue;
+                        const unsigned long long key = ((unsigned long long)nodes[k].cnt << 32) | (unsigned)nodes[k].seq;
+                        if (bestIdx < 0 || key > best) { best = key; bestIdx = i; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bestIdx, o);
+                        if (oi >= 0 && (bestIdx < 0 || ob > best)) { best = ob; bestIdx = oi; }
+                    }
+                    const int k = prev[bestIdx];
+                    __syncwarp();
+                    if (lane == 0) prev[bestIdx] = -1;
+                    q_divide(nodes, &st, k, buf0, buf1, nextL, nNext, lane);
+                    if (lane == 0) { q_unlink(nodes, &st, k); q_free(nodes, &st, k); }
+                    __syncwarp();
+                    if (st.size >= N) break;
+                }
+                if (st.size >= N || st.size == prevSize2) finish = true;
+                int* t = prev; prev = nextL; nextL = t;
+                int* tn = nPrev; nPrev = nNext; nNext = tn;
+            }
+        }
+    }
+    // retain the best point of each node, in list order (:739-758): max response, first wins
+    const int nOut = st.size;
+    if (lane == 0) {
+        int k = 0;
+        for (int cur = st.head; cur >= 0; cur = nodes[cur].next) listA[k++] = cur;
+        if (nOut > lv.kpCap) atomicOr(err, 1);
+        *outN = min(nOut, lv.kpCap);
+    }
+    __syncwarp();
+    for (int k = lane; k < min(nOut, lv.kpCap); k += 32) {
+        const QNode& nd = nodes[listA[k]];
+        const uint32_t* src = (nd.buf ? buf1 : buf0) + nd.start;
+        uint32_t bp = src[0];
+        for (int i = 1; i < nd.cnt; ++i) {
+            const uint32_t p = src[i];
+            if ((p >> 24) > (bp >> 24)) bp = p;
+        }
+        outKp[k] = bp;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3  orientation (IC_Angle, :75-102) + steered BRIEF (computeOrbDescriptor, :106-145): one warp per keypoint.
+// Lanes own the 31 patch rows for the moments (integer sums -> order-free, exact) and one descriptor byte each.
+__global__ void __launch_bounds__(256) orient_desc_kernel(PlfGeom g, const uint8_t* pyr, const uint8_t* blur,
+                                                          const uint32_t* lvlKp, const int* lvlN,
+                                                          plf_keypoint* kpTmp, uint8_t* descTmp, int* nKp,
+                                                          int imgFirst) {
+    const int img = imgFirst + blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int gk = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int* ln = lvlN + (size_t)img * g.nLevels;
+    int level = 0, base = 0, total = 0;
+    bool found = false;
+    for (int l = 0; l < g.nLevels; ++l) {
+        const int n = ln[l];
+        if (!found && gk < total + n) { level = l; base = total; found = true; }
+        total += n;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) nKp[img] = min(total, g.kpCap);
+    if (!found || gk >= g.kpCap) return;
+    const PlfLevel& lv = g.lv[level];
+    const uint32_t p = lvlKp[(size_t)img * g.kpLevelCapTotal + lv.kpOff + (gk - base)];
+    const int x = (int)(p & 0xFFF) + PLF_MINB, y = (int)((p >> 12) & 0xFFF) + PLF_MINB;
+    const uint8_t* im = pyr + (size_t)img * g.pyrBytes + lv.off;
+    // moments: lane v+15 owns row v
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int v = lane - 15;
+        const int d = g.umax[v < 0 ? -v : v];
+        const uint8_t* row = im + (size_t)(y + v) * lv.pitch + x;
+        int s = 0;
+        for (int u = -d; u <= d; ++u) {
+            const int val = row[u];
+            m10 += u * val;
+            s += val;
+        }
+        m01 = v * s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    // descriptor: lane = byte
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    const float ar = __fmul_rn(angle, factorPI);
+    // glibc cosf/sinf are correctly rounded for all practical purposes; reproduce by rounding the double result
+    const float a = (float)cos((double)ar), b = (float)sin((double)ar);
+    const uint8_t* bl = blur + (size_t)img * g.pyrBytes + lv.off + (size_t)y * lv.pitch + x;
+    const int* pat = c_pattern + lane * 32;
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1], x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
+        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int t0 = bl[r0 * lv.pitch + c0], t1 = bl[r1 * lv.pitch + c1];
+        val |= (t0 < t1) << k;
+    }
+    descTmp[((size_t)img * g.kpCap + gk) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        plf_keypoint kp;
+        kp.x = (float)x;
+        kp.y = (float)y;
+        if (level != 0) {   // :1131-1133
+            kp.x = __fmul_rn(kp.x, lv.scale);
+            kp.y = __fmul_rn(kp.y, lv.scale);
+        }
+        kp.size = (float)lv.scaledPatch;
+        kp.angle = angle;
+        kp.response = (float)(p >> 24);
+        kp.octave = level;
+        kp.class_id = -1;
+        kpTmp[(size_t)img * g.kpCap + gk] = kp;
+    }
+}
+
+// Row placement of ORBextractor::operator() (:1102-1146): rows outside the lapping area are written front to back,
+// rows inside back to front.  One block per image, ordered block scan of the "inside" predicate.
+__global__ void __launch_bounds__(1024) place_rows_kernel(PlfGeom g, const plf_keypoint* kpTmp, const uint8_t* descTmp,
+                                                          const int* nKp, plf_keypoint* kpOut, uint8_t* descOut,
+                                                          int* mono, int lap0, int lap1, int imgFirst) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int img = imgFirst + blockIdx.x;
+    const int n = nKp[img];
+    const plf_keypoint* src = kpTmp + (size_t)img * g.kpCap;
+    const uint4* dsrc = reinterpret_cast<const uint4*>(descTmp + (size_t)img * g.kpCap * 32);
+    plf_keypoint* dst = kpOut + (size_t)img * g.kpCap;
+    uint4* ddst = reinterpret_cast<uint4*>(descOut + (size_t)img * g.kpCap * 32);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + tid;
+        plf_keypoint kp;
+        int inside = 0;
+        if (i < n) {
+            kp = src[i];
+            inside = (kp.x >= (float)lap0 && kp.x <= (float)lap1) ? 1 : 0;
+        }
+        int inc = inside;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        int base = s_carry;
+        for (int w = 0; w < warp; ++w) base += s_warp[w];
+        const int insideBefore = base + inc - inside;   // # inside rows among [0, i)
+        if (i < n) {
+            const int pos = inside ? (n - 1 - insideBefore) : (i - insideBefore);
+            dst[pos] = kp;
+            ddst[pos * 2] = dsrc[i * 2];
+            ddst[pos * 2 + 1] = dsrc[i * 2 + 1];
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = base + inc;
+        __syncthreads();
+    }
+    if (tid == 0) mono[img] = n - s_carry;
+}
+
+}  // namespace
+
+int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1) {
+    const PlfGeom& g = c->g;
+    cudaStream_t s = c->stream;
+    int launches = 0;
+    for (int l = 1; l < g.nLevels; ++l) {
+        dim3 grid((g.lv[l].w + 31) / 32, (g.lv[l].h + 7) / 8, nImg);
+        pyr_resize_kernel<<<grid, dim3(32, 8), 0, s>>>(g, c->d_pyr, l, imgFirst);
+        ++launches;
+    }
+    int tiles = 0;
+    for (int l = 0; l < g.nLevels; ++l) tiles += ((g.lv[l].w + 31) / 32) * ((g.lv[l].h + 31) / 32);
+    blur_pyramid_kernel<<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(g, c->d_pyr, c->d_blur, imgFirst);
+    fast_cells_kernel<<<dim3(g.nCellsTotal, nImg), 256, 0, s>>>(g, c->d_pyr, c->d_cells, c->d_cellCount, c->d_cand,
+                                                               imgFirst);
+    int maxQ = 0;
+    for (int l = 0; l < g.nLevels; ++l) maxQ = max(maxQ, max(g.lv[l].quota, 4 * g.lv[l].nIni));
+    const int pool = maxQ + 16;
+    const size_t smem = (size_t)pool * (sizeof(QNode) + 2 * sizeof(int));
+    static size_t s_attr = 0;
+    if (smem > 48 * 1024 && smem > s_attr) {
+        cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        s_attr = smem;
+    }
+    octree_kernel<<<dim3(g.nLevels, nImg), 32, smem, s>>>(g, c->d_cells, c->d_cellCount, c->d_cand, c->d_scratch,
+                                                         c->d_lvlKp, c->d_lvlN, c->d_err, imgFirst, pool);
+    orient_desc_kernel<<<dim3((g.kpCap + 7) / 8, nImg), 256, 0, s>>>(g, c->d_pyr, c->d_blur, c->d_lvlKp, c->d_lvlN,
+                                                                    c->d_kpTmp, c->d_descTmp, c->d_nKp, imgFirst);
+    place_rows_kernel<<<nImg, 1024, 0, s>>>(g, c->d_kpTmp, c->d_descTmp, c->d_nKp, c->d_kp, c->d_desc, c->d_mono,
+                                            lap0, lap1, imgFirst);
+    return launches + 5;
+}

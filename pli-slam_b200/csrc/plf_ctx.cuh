@@ -1,0 +1,139 @@
+// Internal context of the CUDA frontend: geometry tables, device buffers, stream.  All device work of one context
+// is issued on ctx->stream; buffers are sized once in plf_create for max_batch stereo pairs (2*max_batch images,
+// image index = slot*2 + side) so that a batch run performs no allocation and no host synchronisation.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/plf_b200.h"
+
+#define PLF_MAX_LEVELS 16
+#define PLF_EDGE 19               // EDGE_THRESHOLD, src/ORBextractor.cc:72
+#define PLF_MINB 16               // minBorder = EDGE_THRESHOLD-3, src/ORBextractor.cc:771
+#define PLF_NOTDEF (-1024.0f)
+#define PLF_GRID_COLS 64          // FRAME_GRID_COLS, include/Frame.h:60
+#define PLF_GRID_ROWS 48          // FRAME_GRID_ROWS, include/Frame.h:59
+
+struct PlfLevel {
+    int w, h, pitch;
+    long long off;        // byte offset of the level inside one image's pyramid block
+    int nCells;           // FAST cells of this level that are actually run
+    int cellFirst;        // index of the first cell in the cell table
+    int quota;            // mnFeaturesPerLevel[level]
+    int nIni;             // root nodes of the quadtree
+    int candOff, candCap; // slice of the per-image candidate buffer
+    int kpOff, kpCap;     // slice of the per-image per-level keypoint buffer
+    float scale, invScale;
+    int scaledPatch;      // (int)(31*scale)
+};
+
+struct PlfCell {          // one FAST window, src/ORBextractor.cc:787-804
+    short level;
+    short x0, y0, x1, y1; // window [x0,x1) x [y0,y1) in level coordinates
+    int outBase;          // first slot in the per-image candidate buffer
+    int cap;
+};
+
+struct PlfGeom {          // passed by value to kernels (fits the 4 KB parameter space)
+    int nLevels;
+    int W, H;
+    PlfLevel lv[PLF_MAX_LEVELS];
+    int nCellsTotal, candCapTotal, kpLevelCapTotal;
+    long long pyrBytes;   // bytes of one image's pyramid block (same layout for the blurred pyramid)
+    int kpCap, klCap;     // output capacities per image
+    int iniTh, minTh;
+    int umax[16];
+    // LSD
+    int Ws, Hs, Ps;       // scaled image size and pitch (floats/ints use Ws*Hs dense)
+    int lsdTaps[16], lsdK;
+    double lsdScale, rho, prec;
+    int nBins, minRegSize;
+    int segCap;           // max segments kept per image
+    int seedCap;
+};
+
+struct plf_ctx {
+    plf_params p;
+    PlfGeom g;
+    int device = 0;
+    int nImgMax = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<float> scale, invScale, sigma2, invSigma2;
+    std::vector<int> quota;
+    // ORB device buffers
+    uint8_t* d_pyr = nullptr;        // [nImg][pyrBytes]
+    uint8_t* d_blur = nullptr;       // [nImg][pyrBytes]
+    PlfCell* d_cells = nullptr;      // [nCellsTotal]
+    int* d_cellCount = nullptr;      // [nImg][nCellsTotal]
+    uint32_t* d_cand = nullptr;      // [nImg][candCapTotal] packed x | y<<12 | score<<24 (relative to min border)
+    uint32_t* d_scratch = nullptr;   // [nImg][2][candCapTotal] quadtree ping-pong point buffers
+    uint32_t* d_lvlKp = nullptr;     // [nImg][kpLevelCapTotal] retained keypoints per level (packed, list order)
+    int* d_lvlN = nullptr;           // [nImg][nLevels]
+    plf_keypoint* d_kpTmp = nullptr; // [nImg][kpCap] level-major
+    uint8_t* d_descTmp = nullptr;    // [nImg][kpCap][32]
+    plf_keypoint* d_kp = nullptr;    // [nImg][kpCap] final row order
+    uint8_t* d_desc = nullptr;       // [nImg][kpCap][32]
+    int* d_nKp = nullptr;            // [nImg]
+    int* d_mono = nullptr;           // [nImg]
+    int* d_err = nullptr;            // [1] device-side overflow / invariant flags
+    // stereo points
+    float* d_uRight = nullptr;       // [slots][kpCap]
+    float* d_depth = nullptr;
+    int* d_sad = nullptr;            // [slots][kpCap] best SAD (-1 = unmatched)
+    // LSD / LBD
+    uint8_t* d_lsdBlur = nullptr;    // [nImg][H][pitch0]
+    uint8_t* d_lsdU = nullptr;       // [nImg][Hs][Ps]
+    float* d_ang = nullptr;          // [nImg][Hs*Ws] degrees, NOTDEF
+    float2* d_cs = nullptr;          // [nImg][Hs*Ws] cosf/sinf of the level-line angle
+    int* d_n2 = nullptr;             // [nImg][Hs*Ws] gx^2+gy^2
+    int* d_n2max = nullptr;          // [nImg]
+    int* d_hist = nullptr;           // [nImg][nBins]
+    int* d_seeds = nullptr;          // [nImg][seedCap] pixel indices in processing order
+    int* d_nSeeds = nullptr;         // [nImg]
+    uint8_t* d_used = nullptr;       // [nImg][Hs*Ws]
+    int* d_reg = nullptr;            // [nImg][Hs*Ws] region pixel list (reused per region)
+    float* d_segs = nullptr;         // [nImg][segCap][4]
+    int* d_nSegs = nullptr;          // [nImg]
+    plf_keyline* d_kl = nullptr;     // [nImg][klCap]
+    plf_keyline* d_klAll = nullptr;  // [nImg][segCap] before top-N
+    int* d_nKl = nullptr;            // [nImg]
+    uint8_t* d_lbdBlur = nullptr;    // [nImg][H][pitch0]
+    short2* d_sobel = nullptr;       // [nImg][H][W] (dx,dy)
+    float* d_lbd = nullptr;          // [nImg][klCap][72]
+    uint8_t* d_ldesc = nullptr;      // [nImg][klCap][32]
+    // line stereo matching
+    unsigned long long* d_rowMask = nullptr;  // [slots][klCap][48]
+    double2* d_dirR = nullptr;       // [slots][klCap]
+    unsigned short* d_dmat = nullptr;// [slots][klCap][klCap] Hamming distance or 0xFFFF (not a surviving candidate)
+    int* d_m21 = nullptr;            // [slots][klCap]
+    int* d_m12 = nullptr;            // [slots][klCap]
+    float* d_disp = nullptr;         // [slots][klCap][2]
+    double* d_le = nullptr;          // [slots][klCap][3]
+    // generic matcher scratch (match_nnr / match)
+    uint8_t* d_mA = nullptr; uint8_t* d_mB = nullptr; int* d_mOut = nullptr; int* d_mOut2 = nullptr; int mCap = 0;
+    // pinned host staging for small result reads
+    int* h_counts = nullptr;         // pinned
+    // state
+    int batchResident = 0;
+    bool orbValid[2] = {false, false};
+    bool lineValid[2] = {false, false};
+    int launches = 0;
+    bool stageTiming = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<float> stageMs;
+};
+
+// --- stage launchers (each returns the number of kernel launches it issued) ---------------------------------------
+int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1);
+int plf_launch_stereo_points(plf_ctx* c, int slotFirst, int nSlots);
+int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg);
+int plf_launch_stereo_lines(plf_ctx* c, int slotFirst, int nSlots);
+int plf_launch_match_nnr(plf_ctx* c, const uint8_t* dA, int nA, const uint8_t* dB, int nB, float nnr, int* dOut);
+
+#define PLF_CUDA_OK(expr)                                                                       \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) return plf_set_cuda_error(_e, #expr, __FILE__, __LINE__);        \
+    } while (0)
+int plf_set_cuda_error(cudaError_t e, const char* what, const char* file, int line);

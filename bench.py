@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Headline benchmark: stereo frames/s of the point+line frontend on synthetic EuRoC-shape 752x480 pairs.
+
+Workload = BASELINE.json configs[1]: stereo stream 752x480, 1200 ORB features / 8 levels, LSD+LBD lines (top 300 by
+response), stereo point + line matching, batch 64 pairs per call.  One process per GPU; streams (= independent stereo
+sequences) are sharded across ranks with no data-path collective (replicas only, weak scaling); torch.distributed is
+used for the barrier and the max-over-ranks of the device time only.
+
+A "step" = one pass of the hot path over `contexts` batches of 64 pairs on this rank (several contexts are kept in
+flight on their own CUDA streams because the region-growing kernel is latency-bound, one warp per image).
+
+  value : pairs/s with the inputs already resident in HBM (plf_batch_run only), all ranks
+  e2e   : pairs/s through the C ABI with pinned HOST buffers: H2D of the images + kernels + D2H of every result array
+
+  python bench.py --gpus 1 --steps 4 --warmup 3
+  python -m torch.distributed.run --nproc-per-node 8 ... bench.py --gpus 8 ...
+  python bench.py --impl reference       # the CPU port (oracle) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 752, 480
+WORKLOAD = dict(n_features=1200, n_levels=8, lsd_nfeatures=300)
+# algorithmic bytes of one stereo pair through the whole path (752x480, 1200 kp, 300 lines)
+BYTES_PER_PAIR = 50_661_326
+S_PIXELS = 902 * 576                 # scaled LSD image
+GROW_BYTES_PER_IMAGE = 9 * S_PIXELS  # region growing reads angle + modgrad (2 x f32) and the u8 used map once
+
+
+def shard_streams(n_streams, world_size, rank):
+    """Stream s -> rank s mod world_size.  Returns the stream ids this rank owns."""
+    return list(range(rank, n_streams, world_size))
+
+
+def stream_seed(stream, frame):
+    """Seed convention of SURVEY §8d for C5: stream s, frame f -> 10000*(s+1)+f."""
+    return 10_000 * (stream + 1) + frame
+
+
+def _gen_pair(seed):
+    import plf
+    return plf.synth_pair(W, H, seed)
+
+
+def make_inputs(seeds):
+    """Distinct synthetic pairs, generated on the host cores in parallel (pure numpy, deterministic per seed)."""
+    from concurrent.futures import ProcessPoolExecutor
+    L = np.empty((len(seeds), H, W), np.uint8)
+    R = np.empty((len(seeds), H, W), np.uint8)
+    workers = max(1, min(len(seeds), (os.cpu_count() or 2)))
+    try:
+        with ProcessPoolExecutor(max_workers=workers) as ex:
+            for i, (l, r) in enumerate(ex.map(_gen_pair, seeds, chunksize=2)):
+                L[i], R[i] = l, r
+    except Exception:
+        for i, s in enumerate(seeds):
+            L[i], R[i] = _gen_pair(s)
+    return L, R
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_baseline(sample_pairs, threads, seeds):
+    """The CPU port of the reference path (oracle/) on the host cores, `threads` workers over independent pairs."""
+    import plf
+    orc = plf.load_oracle()     # bench.py's cpu_baseline / --impl reference legs are allowed to execute oracle/
+    f = plf.Frontend(orc, width=W, height=H, max_batch=sample_pairs, **WORKLOAD)
+    orc.dll.plf_cpu_set_threads(f.ctx, threads)
+    L, R = make_inputs(seeds[:sample_pairs])
+    out = f.new_result(sample_pairs)
+    f.batch_upload(L, R)
+    t0 = time.perf_counter()
+    f.batch_run(sample_pairs)
+    dt = time.perf_counter() - t0
+    f.batch_download(sample_pairs, out)
+    return sample_pairs / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  Its own sources cannot be built here (they
+    need OpenCV 3 / Eigen / Pangolin headers, none present), so the timed code is the CPU port in oracle/ with every
+    host thread, on the same workload, each step a bounded sample."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = max(2 * cores, 8)
+    seeds = [1000 + i for i in range(sample)]
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_baseline(min(sample, cores), cores, seeds)
+    vals = []
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_baseline(sample, cores, seeds)
+        vals.append(v)
+        t_all += dt
+    value = sample * args.steps / t_all
+    line = {"impl": "reference", "metric": "stereo_frames_per_sec", "value": value, "unit": "stereo pairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "euroc_752x480_stereo_pointline_batch64", "width": W, "height": H, **WORKLOAD,
+                       "timing": "host wall clock, inputs in host memory"},
+            "cpu_baseline": {"value": value, "unit": "stereo pairs/s", "cores": cores, "kind": "port",
+                             "sample": "%d pairs per step, %d worker threads over independent pairs" % (sample, cores)},
+            "e2e": {"value": value, "unit": "stereo pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--contexts", type=int, default=8, help="batches kept in flight per GPU (one CUDA stream each)")
+    ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic pairs generated per rank")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import plf
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    prod = plf.load_product()
+    B, C = args.batch, args.contexts
+    # this rank's streams: C contexts = C independent stereo streams in flight, 64 consecutive frames each
+    my_streams = shard_streams(C * world, world, rank)
+    distinct = min(args.distinct, B)
+    seeds = [stream_seed(my_streams[0], f) for f in range(distinct)]
+    Ld, Rd = make_inputs(seeds)
+    ctxs, hostL, hostR, results = [], [], [], []
+    for ci in range(C):
+        f = plf.Frontend(prod, device=local_rank, width=W, height=H, max_batch=B, **WORKLOAD)
+        # every context gets its own rotation of the distinct pairs (own device copy: C x 46 MB of inputs > L2)
+        idx = (np.arange(B) * 7 + ci * 11) % distinct
+        l = torch.from_numpy(np.ascontiguousarray(Ld[idx])).pin_memory()
+        r = torch.from_numpy(np.ascontiguousarray(Rd[idx])).pin_memory()
+        ctxs.append(f); hostL.append(l); hostR.append(r); results.append(f.new_result(B, pinned=True))
+    ext = [torch.cuda.ExternalStream(f.stream(), device=local_rank) for f in ctxs]
+    main_stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        for f in ctxs:
+            f.batch_run(B)
+
+    def step_e2e():
+        for f, l, r in zip(ctxs, hostL, hostR):
+            f.batch_upload_raw(l.data_ptr(), r.data_ptr(), B, W)
+            f.batch_run(B)
+        for f, out in zip(ctxs, results):
+            f.batch_download(B, out)      # D2H of every result array + stream sync
+
+    def timed(step_fn, steps):
+        """K steps bracketed by barrier+synchronize; device time by CUDA events fanned out to / joined from every
+        context stream; returns seconds (max over ranks)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main_stream)
+        for s in ext:
+            s.wait_event(e0)
+        for _ in range(steps):
+            step_fn()
+        for s in ext:
+            d = torch.cuda.Event()
+            d.record(s)
+            main_stream.wait_event(d)
+        e1.record(main_stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / 1e3
+
+    # inputs resident for the `value` leg
+    for f, l, r in zip(ctxs, hostL, hostR):
+        f.batch_upload_raw(l.data_ptr(), r.data_ptr(), B, W)
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_res = timed(step_resident, args.steps)
+    sampler.stop_flag = True
+    launches = sum(f.launch_count() for f in ctxs) * args.steps
+    for _ in range(2):
+        step_e2e()
+    t_e2e = timed(step_e2e, args.steps)
+    sampler.join(timeout=2)
+
+    # per-stage device time and the dominant kernel's own duration (CUDA events on the launching stream, one context
+    # alone so that stages do not overlap each other)
+    f0 = ctxs[0]
+    f0.set_stage_timing(True)
+    stage_acc = {}
+    reps = 3
+    for _ in range(reps):
+        f0.batch_run(B)
+        f0.batch_download(B, results[0])
+        for k, v in f0.stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / reps
+    f0.set_stage_timing(False)
+    barrier()
+
+    pairs_per_step = B * C * world
+    value = pairs_per_step * args.steps / t_res
+    e2e = pairs_per_step * args.steps / t_e2e
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    grow_ms = stage_acc.get("lsd_grow", 0.0)
+    achieved = (GROW_BYTES_PER_IMAGE * 2 * B / (grow_ms * 1e-3) / 1e9) if grow_ms > 0 else 0.0
+    h2d, d2h = f0.io_bytes()
+    if rank == 0:
+        line = {
+            "metric": "stereo_frames_per_sec", "value": value, "unit": "stereo pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "euroc_752x480_stereo_pointline_batch64", "width": W, "height": H, **WORKLOAD,
+                       "batch": B, "contexts_in_flight": C, "pairs_per_step": pairs_per_step,
+                       "distinct_pairs_per_rank": distinct,
+                       "l2": "inputs larger than L2: %d contexts x %.0f MB of resident images" % (C, 2 * B * W * H / 1e6),
+                       "parallelism": "replicas%d (streams sharded, no collective)" % world},
+            "e2e": {"value": e2e, "unit": "stereo pairs/s", "h2d_bytes_per_step": h2d * B * C,
+                    "d2h_bytes_per_step": d2h * B * C},
+            "gpu_launches": launches,
+            "ms_per_stage": {k: round(v, 4) for k, v in stage_acc.items()},
+            "roofline": {"bound": "hbm", "kernel": "lsd_grow_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                         "algorithmic_bytes_per_launch": GROW_BYTES_PER_IMAGE * 2 * B,
+                         "whole_path_frac": BYTES_PER_PAIR * value / world / (peak * 1e9)},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sample = max(2 * cores, 8)
+            v, dt = cpu_baseline(sample, cores, [1000 + i for i in range(sample)])
+            line["cpu_baseline"] = {"value": v, "unit": "stereo pairs/s", "cores": cores, "kind": "port",
+                                    "sample": "%d pairs, %d worker threads over independent pairs, %.1f s" % (sample, cores, dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -112,8 +112,9 @@ struct Lsd {
                         const double angle = angles[(size_t)yy * W + xx];
                         u = 1;
                         reg.push_back({xx, yy});
-                        sumdx += cosf((float)angle);
-                        sumdy += sinf((float)angle);
+                        // cos(float)/sin(float) of OpenCV's region_grow, taken as correctly rounded (see orb.cpp)
+                        sumdx += (float)std::cos((double)(float)angle);
+                        sumdy += (float)std::sin((double)(float)angle);
                         reg_angle = fast_atan2(sumdy, sumdx) * kDegToRad;
                     }
                 }

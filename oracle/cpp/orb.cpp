@@ -269,7 +269,10 @@ float ic_angle(const Img8& lvl, int x, int y, const int* umax) {
 void orb_descriptor(const Img8& blur, int x, int y, float angleDeg, uint8_t* desc) {
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     float angle = angleDeg * factorPI;
-    float a = cosf(angle), b = sinf(angle);
+    // Declared oracle rule: cosf/sinf are taken as correctly rounded, i.e. the double libm result rounded to float.
+    // glibc's cosf differs from that by 1 ulp for ~0.9 % of arguments and its ifunc variant depends on the host CPU,
+    // which would make the oracle machine-dependent.
+    float a = (float)std::cos((double)angle), b = (float)std::sin((double)angle);
     const int* pat = kPattern;
     for (int i = 0; i < 32; ++i, pat += 32) {
         int val = 0;

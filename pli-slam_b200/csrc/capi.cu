@@ -16,9 +16,13 @@ int plf_set_cuda_error(cudaError_t e, const char* what, const char* file, int li
 }
 static int fail(int code, const char* msg) { g_err = msg; return code; }
 
-static const char* kStageNames[] = {"h2d", "orb_pyramid_blur_fast_octree_desc", "lsd_lbd", "stereo_lines",
-                                    "stereo_points", "d2h"};
-enum { ST_H2D = 0, ST_ORB, ST_LINES, ST_SLINES, ST_SPOINTS, ST_D2H, ST_COUNT };
+#define PLF_MAX_MARKS 48
+void plf_mark(plf_ctx* c, const char* name) {
+    if (!c->stageTiming || c->nMarks >= PLF_MAX_MARKS) return;
+    cudaEventRecord(c->ev[c->nMarks], c->stream);
+    c->markNames[c->nMarks] = name;
+    c->nMarks++;
+}
 
 template <typename T>
 static cudaError_t dalloc(T** p, size_t n) {
@@ -246,9 +250,10 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
     PLF_CUDA_OK(dalloc(&c->d_disp, nSlot * (size_t)g.klCap * 2));
     PLF_CUDA_OK(dalloc(&c->d_le, nSlot * (size_t)g.klCap * 3));
     PLF_CUDA_OK(cudaMallocHost((void**)&c->h_counts, (nImg * 4 + 16) * sizeof(int)));
-    c->ev.resize(ST_COUNT + 1);
+    c->ev.resize(PLF_MAX_MARKS);
     for (auto& e : c->ev) PLF_CUDA_OK(cudaEventCreate(&e));
-    c->stageMs.assign(ST_COUNT, 0.f);
+    c->markNames.assign(PLF_MAX_MARKS, "");
+    c->stageMs.assign(PLF_MAX_MARKS, 0.f);
     *out = c;
     return PLF_OK;
 }
@@ -539,7 +544,8 @@ PLF_API int plf_batch_upload(plf_ctx* c, const uint8_t* left, const uint8_t* rig
     if (!c || !left || !right || batch < 1 || batch > c->p.max_batch || stride < c->g.W) return fail(PLF_ERR_INVALID, "bad batch");
     PLF_CUDA_OK(cudaSetDevice(c->device));
     const PlfGeom& g = c->g;
-    if (c->stageTiming) PLF_CUDA_OK(cudaEventRecord(c->ev[ST_H2D], c->stream));
+    c->nMarks = 0;
+    plf_mark(c, "h2d");
     // images of one side are strided by 2*pyrBytes on the device: one 2-D copy per (side, frame)
     for (int b = 0; b < batch; ++b) {
         PLF_CUDA_OK(cudaMemcpy2DAsync(c->d_pyr + (size_t)(2 * b) * g.pyrBytes + g.lv[0].off, g.lv[0].pitch, left + (size_t)b * g.H * stride, stride, g.W, g.H, cudaMemcpyHostToDevice, c->stream));
@@ -553,15 +559,13 @@ PLF_API int plf_batch_run(plf_ctx* c, int batch) {
     if (!c || batch < 1 || batch > c->batchResident) return fail(PLF_ERR_INVALID, "bad batch (upload first)");
     PLF_CUDA_OK(cudaSetDevice(c->device));
     int n = 0;
-    if (c->stageTiming) PLF_CUDA_OK(cudaEventRecord(c->ev[ST_ORB], c->stream));
+    if (c->nMarks && strcmp(c->markNames[0], "h2d") != 0) c->nMarks = 0;   // run without a fresh upload: restart marks
+    if (c->nMarks > 1) c->nMarks = 0;
     n += plf_launch_orb(c, 0, 2 * batch, 0, 0);
-    if (c->stageTiming) PLF_CUDA_OK(cudaEventRecord(c->ev[ST_LINES], c->stream));
     if (c->p.has_lines) n += plf_launch_lines(c, 0, 2 * batch);
-    if (c->stageTiming) PLF_CUDA_OK(cudaEventRecord(c->ev[ST_SLINES], c->stream));
     if (c->p.has_lines) n += plf_launch_stereo_lines(c, 0, batch);
-    if (c->stageTiming) PLF_CUDA_OK(cudaEventRecord(c->ev[ST_SPOINTS], c->stream));
     n += plf_launch_stereo_points(c, 0, batch);
-    if (c->stageTiming) PLF_CUDA_OK(cudaEventRecord(c->ev[ST_D2H], c->stream));
+    plf_mark(c, "d2h");
     PLF_CUDA_OK(cudaGetLastError());
     c->launches = n;
     c->orbValid[0] = c->orbValid[1] = c->lineValid[0] = c->lineValid[1] = true;
@@ -598,11 +602,13 @@ PLF_API int plf_batch_download(plf_ctx* c, int batch, plf_frame_out* o) {
     if (o->le) D2H_2D(o->le, lc * 24, c->d_le, (size_t)g.klCap * 24, (size_t)g.klCap * 24, batch);
     if (o->line_match12) D2H_2D(o->line_match12, lc * 4, c->d_m12, (size_t)g.klCap * 4, (size_t)g.klCap * 4, batch);
 #undef D2H_2D
-    if (c->stageTiming) PLF_CUDA_OK(cudaEventRecord(c->ev[ST_COUNT], s));
+    plf_mark(c, "end");
     int rc = check_device_flags(c);   // synchronises the stream
     if (rc) return rc;
-    if (c->stageTiming)
-        for (int i = 0; i < ST_COUNT; ++i) cudaEventElapsedTime(&c->stageMs[i], c->ev[i], c->ev[i + 1]);
+    if (c->stageTiming) {
+        for (int i = 0; i + 1 < c->nMarks; ++i) cudaEventElapsedTime(&c->stageMs[i], c->ev[i], c->ev[i + 1]);
+        if (c->nMarks > 0) c->nMarks--;   // the terminating mark is not a stage
+    }
     return PLF_OK;
 }
 
@@ -634,9 +640,9 @@ PLF_API int plf_last_launch_count(const plf_ctx* c) { return c ? c->launches : 0
 PLF_API int plf_set_stage_timing(plf_ctx* c, int on) { if (!c) return PLF_ERR_INVALID; c->stageTiming = on != 0; return PLF_OK; }
 PLF_API int plf_get_stage_ms(plf_ctx* c, const char* const** names, const float** ms, int* n) {
     if (!c) return PLF_ERR_INVALID;
-    if (names) *names = kStageNames;
+    if (names) *names = c->markNames.data();
     if (ms) *ms = c->stageMs.data();
-    if (n) *n = ST_COUNT;
+    if (n) *n = c->nMarks;
     return PLF_OK;
 }
 

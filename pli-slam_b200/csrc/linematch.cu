@@ -229,6 +229,7 @@ int plf_launch_stereo_lines(plf_ctx* c, int slotFirst, int nSlots) {
     cudaStream_t s = c->stream;
     const int kb = (g.klCap + 127) / 128;
     int n = 0;
+    plf_mark(c, "stereo_lines");
     line_grid_kernel<<<dim3(kb, nSlots), 128, 0, s>>>(g, c->d_kl, c->d_nKl, c->d_rowMask, c->d_dirR, slotFirst); ++n;
     line_cand_kernel<<<dim3(kb, g.klCap, nSlots), 128, 0, s>>>(g, c->d_kl, c->d_ldesc, c->d_nKl, c->d_rowMask, c->d_dirR,
                                                               c->d_dmat, c->p.matching_s_ws, c->p.line_sim_th, slotFirst); ++n;

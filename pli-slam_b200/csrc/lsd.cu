@@ -620,6 +620,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     const size_t imgBytes = (size_t)ip * g.H;
     const int tiles = ((g.W + 31) / 32) * ((g.H + 31) / 32);
     int launches = 0;
+    plf_mark(c, "lsd_prefilter");
     const uint8_t* upSrc = in;
     size_t upStride = inStride;
     if (g.lsdK > 0) {
@@ -632,18 +633,24 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         ++launches;
     }
     lsd_upscale_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, imgFirst);
+    plf_mark(c, "lsd_gradient");
     cudaMemsetAsync(c->d_n2max + imgFirst, 0, nImg * sizeof(int), s);
     cudaMemsetAsync(c->d_hist + (size_t)imgFirst * g.nBins, 0, (size_t)nImg * g.nBins * sizeof(int), s);
     lsd_grad_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_ang, c->d_cs, c->d_n2, c->d_n2max, imgFirst);
     lsd_hist_kernel<<<dim3(64, nImg), 256, g.nBins * sizeof(int), s>>>(g, c->d_ang, c->d_n2, c->d_n2max, c->d_hist, imgFirst);
+    plf_mark(c, "lsd_order");
     lsd_order_kernel<<<nImg, 1024, g.nBins * sizeof(int), s>>>(g, c->d_ang, c->d_n2, c->d_n2max, c->d_hist, c->d_seeds, c->d_nSeeds, imgFirst);
+    plf_mark(c, "lsd_grow");
     cudaMemsetAsync(c->d_used + (size_t)imgFirst * g.Ws * g.Hs, 0, (size_t)nImg * g.Ws * g.Hs, s);
     lsd_grow_kernel<<<nImg, 32, 0, s>>>(g, c->d_ang, c->d_cs, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_err, imgFirst);
+    plf_mark(c, "line_keylines");
     const double minLen = c->p.min_line_length * std::min(g.W, g.H);
     keylines_kernel<<<nImg, 256, g.segCap * sizeof(float), s>>>(g, c->d_segs, c->d_nSegs, c->d_klAll, c->d_kl, c->d_nKl, c->d_err, minLen, c->p.lsd_nfeatures, imgFirst);
+    plf_mark(c, "lbd_blur_sobel");
     const int lt[5] = {14, 62, 104, 62, 14};
     blur_image_kernel<5><<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(in, inStride, ip, c->d_lbdBlur, imgBytes, ip, g.W, g.H, imgFirst, lt[0], lt[1], lt[2], lt[3], lt[4], 0, 0);
     sobel_kernel<<<dim3((g.W + 31) / 32, (g.H + 7) / 8, nImg), dim3(32, 8), 0, s>>>(c->d_lbdBlur, imgBytes, ip, c->d_sobel, g.W, g.H, imgFirst);
+    plf_mark(c, "lbd_descriptor");
     lbd_kernel<<<dim3((g.klCap + 3) / 4, nImg), 128, 0, s>>>(g, c->d_sobel, c->d_kl, c->d_nKl, c->d_lbd, c->d_ldesc, imgFirst);
     return launches + 9;
 }

@@ -622,6 +622,7 @@ int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1) {
     const PlfGeom& g = c->g;
     cudaStream_t s = c->stream;
     int launches = 0;
+    plf_mark(c, "orb_pyramid");
     for (int l = 1; l < g.nLevels; ++l) {
         dim3 grid((g.lv[l].w + 31) / 32, (g.lv[l].h + 7) / 8, nImg);
         pyr_resize_kernel<<<grid, dim3(32, 8), 0, s>>>(g, c->d_pyr, l, imgFirst);
@@ -629,7 +630,9 @@ int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1) {
     }
     int tiles = 0;
     for (int l = 0; l < g.nLevels; ++l) tiles += ((g.lv[l].w + 31) / 32) * ((g.lv[l].h + 31) / 32);
+    plf_mark(c, "orb_blur");
     blur_pyramid_kernel<<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(g, c->d_pyr, c->d_blur, imgFirst);
+    plf_mark(c, "orb_fast");
     fast_cells_kernel<<<dim3(g.nCellsTotal, nImg), 256, 0, s>>>(g, c->d_pyr, c->d_cells, c->d_cellCount, c->d_cand,
                                                                imgFirst);
     int maxQ = 0;
@@ -641,8 +644,10 @@ int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1) {
         cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         s_attr = smem;
     }
+    plf_mark(c, "orb_octree");
     octree_kernel<<<dim3(g.nLevels, nImg), 32, smem, s>>>(g, c->d_cells, c->d_cellCount, c->d_cand, c->d_scratch,
                                                          c->d_lvlKp, c->d_lvlN, c->d_err, imgFirst, pool);
+    plf_mark(c, "orb_orient_desc");
     orient_desc_kernel<<<dim3((g.kpCap + 7) / 8, nImg), 256, 0, s>>>(g, c->d_pyr, c->d_blur, c->d_lvlKp, c->d_lvlN,
                                                                     c->d_kpTmp, c->d_descTmp, c->d_nKp, imgFirst);
     place_rows_kernel<<<nImg, 1024, 0, s>>>(g, c->d_kpTmp, c->d_descTmp, c->d_nKp, c->d_kp, c->d_desc, c->d_mono,

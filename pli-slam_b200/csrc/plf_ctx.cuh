@@ -120,9 +120,15 @@ struct plf_ctx {
     bool lineValid[2] = {false, false};
     int launches = 0;
     bool stageTiming = false;
-    std::vector<cudaEvent_t> ev;
+    std::vector<cudaEvent_t> ev;          // pool of timing events (marks)
+    std::vector<const char*> markNames;   // name of the stage that STARTS at mark i
     std::vector<float> stageMs;
+    int nMarks = 0;
 };
+
+// Stage marks: when stage timing is on, every launcher drops a CUDA event on the context stream before each stage;
+// the elapsed times between consecutive marks are the ms/stage figures of bench.py.
+void plf_mark(plf_ctx* c, const char* name);
 
 // --- stage launchers (each returns the number of kernel launches it issued) ---------------------------------------
 int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1);

@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(1024) stereo_cull_kernel(PlfGeom g, const int*
 
 int plf_launch_stereo_points(plf_ctx* c, int slotFirst, int nSlots) {
     const PlfGeom& g = c->g;
+    plf_mark(c, "stereo_points");
     stereo_points_kernel<<<dim3((g.kpCap + 7) / 8, nSlots), 256, 0, c->stream>>>(
         g, c->d_pyr, c->d_kp, c->d_desc, c->d_nKp, c->d_uRight, c->d_depth, c->d_sad, c->p.bf, c->p.fx, slotFirst);
     stereo_cull_kernel<<<nSlots, 1024, g.kpCap * sizeof(int), c->stream>>>(g, c->d_nKp, c->d_uRight, c->d_depth,

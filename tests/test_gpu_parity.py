@@ -1,0 +1,200 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed golden vectors.
+Bars (BASELINE.json north_star): FAST candidate sets, quadtree-retained keypoints (order included), rBRIEF descriptors
+and every match index bit-exact; orientation within 1e-4 rad (observed: bit-exact); LSD/LBD line endpoints within
+0.5 px with >= 99 % recall and LBD Hamming distance <= 2 bits (observed: bit-exact)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ANGLE_TOL_DEG = 1e-4 * 180.0 / np.pi        # 1e-4 rad
+ENDPOINT_TOL_PX = 0.5
+LBD_TOL_BITS = 2
+
+
+def _check_orb(kg, dg, ko, do):
+    assert len(kg) == len(ko)
+    for fld in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(kg[fld], ko[fld]), fld
+    assert np.abs(kg["angle"] - ko["angle"]).max(initial=0) <= ANGLE_TOL_DEG
+    assert np.array_equal(dg, do)
+
+
+def _check_lines(klg, ldg, klo, ldo):
+    assert len(klg) == len(klo)
+    if len(klo) == 0:
+        return
+    ends_g = np.stack([klg["startPointX"], klg["startPointY"], klg["endPointX"], klg["endPointY"]], 1)
+    ends_o = np.stack([klo["startPointX"], klo["startPointY"], klo["endPointX"], klo["endPointY"]], 1)
+    close = np.abs(ends_g - ends_o).max(axis=1) <= ENDPOINT_TOL_PX
+    assert close.mean() >= 0.99
+    bits = np.unpackbits(ldg ^ ldo, axis=1).sum(axis=1)
+    assert bits[close].max(initial=0) <= LBD_TOL_BITS
+
+
+@pytest.mark.parametrize("seed", [1, 7])
+def test_single_frame_calls_stage_by_stage(plf, product, oracle, seed):
+    """The five reference entry points, one stereo frame, every intermediate stage compared."""
+    L, R = plf.synth_pair(752, 480, seed)
+    f, o = plf.Frontend(product), plf.Frontend(oracle)
+    for side, img in ((0, L), (1, R)):
+        mg, kg, dg = f.orb_extract(side, img)
+        mo, ko, do = o.orb_extract(side, img)
+        for l in range(8):
+            assert np.array_equal(f.pyramid_level(side, l), o.pyramid_level(side, l))
+            assert np.array_equal(f.blurred_level(side, l), o.blurred_level(side, l))
+            assert np.array_equal(f.fast_candidates(side, l), o.fast_candidates(side, l))
+        assert mg == mo
+        _check_orb(kg, dg, ko, do)
+    ug, dpg = f.stereo_match_points(len(kg))
+    uo, dpo = o.stereo_match_points(len(ko))
+    nL = None
+    for side, img in ((0, L), (1, R)):
+        klg, ldg = f.line_extract(side, img)
+        klo, ldo = o.line_extract(side, img)
+        assert np.array_equal(f.lsd_scaled(side), o.lsd_scaled(side))
+        assert np.array_equal(f.lsd_angles(side), o.lsd_angles(side))
+        sg, so = f.lsd_segments(side), o.lsd_segments(side)
+        assert sg.shape == so.shape and np.abs(sg - so).max(initial=0) <= ENDPOINT_TOL_PX
+        _check_lines(klg, ldg, klo, ldo)
+        assert np.array_equal(klg, klo) and np.array_equal(ldg, ldo)      # observed: bit-exact
+        assert np.array_equal(f.lbd_float(side), o.lbd_float(side))
+        nL = len(klg) if side == 0 else nL
+    dg2, leg, mg2 = f.stereo_match_lines(nL)
+    do2, leo, mo2 = o.stereo_match_lines(nL)
+    assert np.array_equal(mg2, mo2) and np.array_equal(dg2, do2)
+    assert np.allclose(leg, leo, rtol=1e-12, atol=0)
+
+
+def test_stereo_points_after_orb(plf, product, oracle, pair1):
+    L, R = pair1
+    f, o = plf.Frontend(product), plf.Frontend(oracle)
+    for fe in (f, o):
+        fe.orb_extract(0, L)
+        fe.orb_extract(1, R)
+    n = len(o.orb_extract(0, L)[1])
+    ug, dg = f.stereo_match_points(n)
+    uo, do = o.stereo_match_points(n)
+    assert np.array_equal(ug, uo) and np.array_equal(dg, do)
+    assert (ug >= 0).sum() > 100
+
+
+def test_state_errors(plf, product):
+    f = plf.Frontend(product)
+    with pytest.raises(plf.PlfError):
+        f.stereo_match_points(10)          # before both extractions: PLF_ERR_STATE
+    with pytest.raises(plf.PlfError):
+        plf.Frontend(product, lsd_refine=2)
+
+
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_against_golden_fixtures(plf, product, path):
+    """C1 (752x480, 1200 feats + lines), C3 (ORB only, 2000 feats), C4 (1280x720 lines): committed vectors."""
+    g = np.load(path)
+    W, H, seed = int(g["W"]), int(g["H"]), int(g["seed"])
+    kw = dict(n_features=2000, has_lines=0) if "2000feat" in path else {}
+    L, R = plf.synth_pair(W, H, seed)
+    f = plf.Frontend(product, width=W, height=H, max_batch=1, **kw)
+    r = f.frontend_batch(L[None], R[None])
+    n, nr = int(r.n_kp_left[0]), int(r.n_kp_right[0])
+    _check_orb(r.kp_left[0, :n], r.desc_left[0, :n], g["oracle_kp_left"], g["oracle_desc_left"])
+    _check_orb(r.kp_right[0, :nr], r.desc_right[0, :nr], g["oracle_kp_right"], g["oracle_desc_right"])
+    assert np.array_equal(r.u_right[0, :n], g["oracle_u_right"]) and np.array_equal(r.depth[0, :n], g["oracle_depth"])
+    for l in range(8):
+        assert np.array_equal(f.fast_candidates(0, l), g["cv2_cand_L%d" % l])          # real-OpenCV FAST lists
+    nl = int(r.n_kl_left[0])
+    assert nl == len(g["oracle_kl_left"])
+    if nl:
+        assert np.abs(f.lsd_segments(0) - g["cv2_lsd_left"]).max() <= ENDPOINT_TOL_PX  # real-OpenCV LSD segments
+        assert np.abs(f.lsd_segments(1) - g["cv2_lsd_right"]).max() <= ENDPOINT_TOL_PX
+        _check_lines(r.kl_left[0, :nl], r.ldesc_left[0, :nl], g["oracle_kl_left"], g["oracle_ldesc_left"])
+        assert np.array_equal(r.line_match12[0, :nl], g["oracle_line_match12"])
+        assert np.array_equal(r.disp_se[0, :nl], g["oracle_disp_se"])
+        assert np.allclose(r.le[0, :nl], g["oracle_le"], rtol=1e-12, atol=0)
+
+
+def test_match_nnr_and_match(plf, product, oracle):
+    """matchNNR / match (config C4 uses matchNNR on the L/R LBD sets): random + structured descriptors, edge cases."""
+    f, o = plf.Frontend(product), plf.Frontend(oracle)
+    rng = np.random.default_rng(11)
+    for n1, n2 in ((500, 500), (300, 280), (1, 2), (7, 1), (0, 5), (33, 2000)):
+        d1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+        d2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+        k = min(n1, n2) // 2
+        if k:
+            d2[:k] = d1[:k] ^ (rng.integers(0, 256, (k, 32), dtype=np.uint8) & 1)
+            d2[k // 2] = d2[0]                                    # an exact tie
+        for nnr in (0.9, 0.6, 1.0):
+            a, b = f.match_nnr(d1, d2, nnr), o.match_nnr(d1, d2, nnr)
+            assert a[0] == b[0] and np.array_equal(a[1], b[1])
+            a, b = f.match(d1, d2, nnr, True), o.match(d1, d2, nnr, True)
+            assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    L, R = plf.synth_pair(1280, 720, 2001)
+    f4 = plf.Frontend(product, width=1280, height=720)
+    o4 = plf.Frontend(oracle, width=1280, height=720)
+    kl, dl = f4.line_extract(0, L)
+    kr, dr = f4.line_extract(1, R)
+    a, b = f4.match_nnr(dl, dr, 0.9), o4.match_nnr(dl, dr, 0.9)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[0] > 50
+
+
+def test_batch64_full_size_properties(plf, product, oracle):
+    """BASELINE config C2 at full size (batch 64): a sample of pairs against the oracle, and for the whole batch the
+    size-independent properties: run-to-run determinism, batch == single-frame, slot independence (a permuted batch
+    gives permuted results), Hamming symmetry of the stereo matches, descriptor self-match."""
+    B = 64
+    seeds = [1000 + i for i in range(16)]
+    Ld, Rd = plf.synth_batch(752, 480, seeds)
+    idx = np.arange(B) % 16
+    L, R = Ld[idx], Rd[idx]
+    f = plf.Frontend(product, max_batch=B, lsd_nfeatures=300)
+    r1 = f.frontend_batch(L, R)
+    r2 = f.frontend_batch(L, R)
+    names = ["n_kp_left", "n_kp_right", "n_kl_left", "n_kl_right", "kp_left", "kp_right", "desc_left", "desc_right",
+             "u_right", "depth", "kl_left", "kl_right", "ldesc_left", "ldesc_right", "disp_se", "le", "line_match12"]
+
+    def rows(res, name, b):
+        a = getattr(res, name)
+        if name.startswith("n_"):
+            return a[b]
+        n = res.n_kl_left[b] if name in ("kl_left", "ldesc_left", "disp_se", "le", "line_match12") else \
+            res.n_kl_right[b] if name in ("kl_right", "ldesc_right") else \
+            res.n_kp_right[b] if name in ("kp_right", "desc_right") else res.n_kp_left[b]
+        return a[b, :n]
+
+    for name in names:
+        for b in range(B):
+            assert np.array_equal(rows(r1, name, b), rows(r2, name, b)), ("determinism", name, b)
+            assert np.array_equal(rows(r1, name, b), rows(r1, name, b % 16)), ("slot independence", name, b)
+    perm = np.random.default_rng(0).permutation(B)
+    rp = f.frontend_batch(L[perm], R[perm])
+    for name in names:
+        for b in range(0, B, 5):
+            assert np.array_equal(rows(rp, name, b), rows(r1, name, perm[b])), ("permutation", name, b)
+    # oracle on a sample of the pairs
+    o = plf.Frontend(oracle, max_batch=4, lsd_nfeatures=300)
+    ro = o.frontend_batch(L[:4], R[:4])
+    for name in names:
+        for b in range(4):
+            if name == "le":
+                assert np.allclose(rows(r1, name, b), rows(ro, name, b), rtol=1e-12, atol=0)
+            else:
+                assert np.array_equal(rows(r1, name, b), rows(ro, name, b)), ("oracle", name, b)
+    # single-frame API == batch API
+    fs = plf.Frontend(product, lsd_nfeatures=300)
+    _, k0, d0 = fs.orb_extract(0, L[3])
+    assert np.array_equal(k0, rows(r1, "kp_left", 3)) and np.array_equal(d0, rows(r1, "desc_left", 3))
+    # descriptor self-match: every row matches itself at distance 0
+    n, m = fs.match_nnr(d0, d0, 0.9)
+    dup = len(d0) - len(np.unique(d0, axis=0))
+    assert n >= len(d0) - 2 * dup
+    # every stereo match lies to the left (disparity >= 0) and inside maxD = fx
+    u, kx = rows(r1, "u_right", 0), rows(r1, "kp_left", 0)["x"]
+    ok = u >= 0
+    assert (kx[ok] - u[ok] >= 0).all() and (kx[ok] - u[ok] < 435.3).all()

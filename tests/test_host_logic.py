@@ -1,0 +1,129 @@
+"""Host-side logic on CPU: parameter defaults against the reference's EuRoC.yaml, scale tables / quotas, Hamming
+distance, matcher edge cases (empty, one-row train set, ties), reference UB rules, stream sharding incl. a
+world_size-2 gloo run."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_default_params_match_euroc_yaml(plf, oracle):
+    p = oracle.default_params()
+    # Examples/Stereo/Config/EuRoC.yaml:91-104,130-175 and src/Config.cpp:100-108 of the reference
+    assert (p.width, p.height, p.n_features, p.n_levels, p.ini_th_fast, p.min_th_fast) == (752, 480, 1200, 8, 20, 7)
+    assert abs(p.scale_factor - 1.2) < 1e-7
+    assert (p.lsd_nfeatures, p.lsd_refine, p.lsd_n_bins, p.matching_s_ws, p.best_lr_matches) == (500, 0, 1024, 10, 1)
+    assert (p.lsd_scale, p.lsd_sigma_scale, p.lsd_quant, p.lsd_ang_th) == (1.2, 0.6, 2.0, 22.5)
+    assert (p.min_ratio_12_l, p.line_sim_th, p.min_disp, p.line_horiz_th) == (0.9, 0.75, 1.0, 0.1)
+    assert (p.stereo_overlap_th, p.ls_min_disp_ratio, p.min_line_length) == (0.75, 0.7, 0.025)
+    assert abs(p.fx - 435.2047) < 1e-3 and abs(p.bf - 47.90639) < 1e-4
+
+
+def test_scale_tables_and_quotas(plf, oracle):
+    f = plf.Frontend(oracle)
+    s, inv, s2, inv2, n = f.scale_tables()
+    assert list(n) == [261, 217, 181, 151, 126, 105, 87, 72]
+    assert s[0] == 1.0 and np.allclose(s[1:] / s[:-1], 1.2, rtol=1e-6)
+    assert np.array_equal(inv, np.float32(1.0) / s) and np.array_equal(s2, s * s)
+    f2 = plf.Frontend(oracle, n_features=2000)
+    assert list(f2.scale_tables()[4]) == [434, 362, 302, 251, 209, 175, 145, 122]
+
+
+def test_unsupported_parameters_fail(plf, oracle):
+    with pytest.raises(plf.PlfError):
+        plf.Frontend(oracle, lsd_refine=1)
+    with pytest.raises(plf.PlfError):
+        plf.Frontend(oracle, width=16, height=16)
+
+
+def test_matchers_edge_cases(plf, oracle):
+    f = plf.Frontend(oracle)
+    rng = np.random.default_rng(3)
+    d1 = rng.integers(0, 256, (40, 32), dtype=np.uint8)
+    # identical sets: every row matches itself (distance 0 < d1*nnr)
+    n, m = f.match_nnr(d1, d1, 0.9)
+    assert n == 40 and np.array_equal(m, np.arange(40))
+    # train set with a single row: no second neighbour -> no matches (declared rule, LineMatcher.cpp:152)
+    n, m = f.match_nnr(d1, d1[:1], 0.9)
+    assert n == 0 and (m == -1).all()
+    # empty query
+    n, m = f.match_nnr(np.zeros((0, 32), np.uint8), d1, 0.9)
+    assert n == 0 and len(m) == 0
+    # duplicated best neighbour: tie -> ratio test fails for nnr < 1
+    d2 = np.concatenate([d1[:1], d1[:1], d1[5:]])
+    n, m = f.match_nnr(d1[:1], d2, 0.9)
+    assert n == 0
+    # mutual-best drops one-sided matches
+    n1, m1 = f.match(d1, d1[::-1].copy(), 0.9, True)
+    assert n1 == 40 and np.array_equal(m1, np.arange(40)[::-1])
+
+
+def test_empty_frame_rules(plf, oracle):
+    """A textureless pair: no keypoints, no lines, and the matchers must return cleanly (Frame.cc:146-149)."""
+    f = plf.Frontend(oracle)
+    flat = np.full((1, 480, 752), 127, np.uint8)
+    r = f.frontend_batch(flat, flat)
+    assert r.n_kp_left[0] == 0 and r.n_kl_left[0] == 0
+
+
+def test_lapping_area_row_order(plf, oracle, pair1):
+    """ORBextractor::operator() writes rows inside vLappingArea back to front (src/ORBextractor.cc:1135-1144)."""
+    L, _ = pair1
+    f = plf.Frontend(oracle)
+    mono0, k0, d0 = f.orb_extract(0, L, (0, 0))
+    mono1, k1, d1 = f.orb_extract(0, L, (0, 1000))      # monocular ctor: everything is "lapping"
+    assert mono0 == len(k0) and mono1 == 0
+    assert np.array_equal(k1[::-1], k0) and np.array_equal(d1[::-1], d0)
+    mono2, k2, d2 = f.orb_extract(0, L, (300, 500))
+    inside = (k0["x"] >= 300) & (k0["x"] <= 500)
+    assert mono2 == int((~inside).sum())
+    assert np.array_equal(k2[:mono2], k0[~inside]) and np.array_equal(k2[mono2:][::-1], k0[inside])
+
+
+def test_shard_streams():
+    sys.path.insert(0, ROOT)
+    import bench
+    for world in (1, 2, 4, 8):
+        got = sorted(s for r in range(world) for s in bench.shard_streams(512, world, r))
+        assert got == list(range(512))
+        assert all(len(bench.shard_streams(512, world, r)) == 512 // world for r in range(world))
+    assert bench.stream_seed(0, 0) == 10_000 and bench.stream_seed(511, 63) == 5_120_063
+
+
+GLOO_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+import bench, plf
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+streams = bench.shard_streams(4, world, rank)
+orc = plf.load_oracle()
+f = plf.Frontend(orc, width=752, height=480, max_batch=len(streams), has_lines=0, n_features=300)
+L, R = plf.synth_batch(752, 480, [bench.stream_seed(s, 0) for s in streams])
+r = f.frontend_batch(L, R)
+cnt = torch.tensor([float(r.n_kp_left[:len(streams)].sum()), float(len(streams))])
+dist.all_reduce(cnt)                       # bookkeeping only: the data path has no collective
+t = torch.tensor([1.0 + rank]); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print(json.dumps({"kps": cnt[0].item(), "pairs": cnt[1].item(), "tmax": t.item(), "streams": streams}))
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)
+    assert res["pairs"] == 4 and res["tmax"] == 2.0 and res["streams"] == [0, 2] and res["kps"] > 4 * 250

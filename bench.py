@@ -176,6 +176,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     prod = plf.load_product()
     B, C = args.batch, args.contexts
+    if os.environ.get("PLF_BENCH_NO_LINES"):      # developer switch: ORB + stereo points only
+        WORKLOAD["has_lines"] = 0
     # this rank's streams: C contexts = C independent stereo streams in flight, 64 consecutive frames each
     my_streams = shard_streams(C * world, world, rank)
     distinct = min(args.distinct, B)

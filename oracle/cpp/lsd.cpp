@@ -262,3 +262,37 @@ void lines_to_keylines(const std::vector<float>& segs, int w, int h, double min_
 }
 
 }  // namespace plfo
+
+// oracle-only diagnostics for the design of the CUDA region grower: number of seeds that start a region, total pixels
+// claimed, histogram of region sizes
+namespace plfo {
+void lsd_stats(const LsdConfig& c, const Img8& img, long long out[8]) {
+    const double prec = kPi * c.ang_th / 180;
+    const double rho = c.quant / std::sin(prec);
+    Lsd L(c);
+    LsdState st;
+    std::vector<int> taps;
+    gaussian_taps_fixed(7, 0.6, taps);
+    Img8 g;
+    gaussian_blur_u8(img, g, taps.data(), 7);
+    resize_linear_exact_u8(g, st.scaled, c.scale);
+    L.ll_angle(st.scaled, rho, st.angleDeg);
+    L.used.assign((size_t)L.W * L.H, 0);
+    std::vector<RegPt> reg;
+    for (int k = 0; k < 8; ++k) out[k] = 0;
+    for (const auto& op : L.ordered) {
+        const size_t idx = (size_t)op.y * L.W + op.x;
+        if (L.angles[idx] == kNotDef) continue;
+        out[0]++;                       // defined pixels
+        if (L.used[idx] != 0) continue;
+        double ra;
+        L.region_grow(op.x, op.y, reg, ra, prec);
+        out[1]++;                       // regions
+        out[2] += (long long)reg.size();
+        if (reg.size() == 1) out[3]++;
+        else if (reg.size() < 4) out[4]++;
+        else if (reg.size() < 16) out[5]++;
+        else { out[6]++; out[7] += (long long)reg.size(); }
+    }
+}
+}  // namespace plfo

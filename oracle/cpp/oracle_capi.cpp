@@ -428,3 +428,12 @@ PLF_API int plf_cpu_prim_lsd(const uint8_t* src, int w, int h, double scale, int
 }
 
 }  // extern "C"
+
+namespace plfo { void lsd_stats(const LsdConfig& c, const Img8& img, long long out[8]); }
+extern "C" PLF_API int plf_cpu_prim_lsd_stats(const uint8_t* src, int w, int h, long long* out) {
+    Img8 s(w, h);
+    std::memcpy(s.d.data(), src, (size_t)w * h);
+    LsdConfig c;
+    plfo::lsd_stats(c, s, out);
+    return PLF_OK;
+}

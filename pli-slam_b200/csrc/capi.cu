@@ -173,7 +173,7 @@ static int build_geometry(plf_ctx* c, std::vector<PlfCell>& cells) {
     g.segCap = 8192;
     g.seedCap = g.Ws * g.Hs;
     if (g.nBins < 2 || g.nBins > 4096) return fail(PLF_ERR_UNSUPPORTED, "lsd_n_bins outside [2,4096]");
-    if ((long long)g.Ws * g.Hs >= (1LL << 24)) return fail(PLF_ERR_UNSUPPORTED, "scaled LSD image has >= 2^24 pixels");
+    if (g.Ws >= 32768 || g.Hs >= 32768) return fail(PLF_ERR_UNSUPPORTED, "scaled LSD image side >= 32768 (packed coordinates)");
     return PLF_OK;
 }
 
@@ -224,13 +224,13 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
         PLF_CUDA_OK(dalloc(&c->d_lsdBlur, nImg * (size_t)g.lv[0].pitch * g.H));
         PLF_CUDA_OK(dalloc(&c->d_lsdU, nImg * (size_t)g.Ps * g.Hs));
         PLF_CUDA_OK(dalloc(&c->d_ang, nImg * npx));
-        PLF_CUDA_OK(dalloc(&c->d_cs, nImg * npx));
+        PLF_CUDA_OK(dalloc(&c->d_rec, nImg * npx));
         PLF_CUDA_OK(dalloc(&c->d_n2, nImg * npx));
         PLF_CUDA_OK(dalloc(&c->d_n2max, nImg));
         PLF_CUDA_OK(dalloc(&c->d_hist, nImg * g.nBins));
         PLF_CUDA_OK(dalloc(&c->d_seeds, nImg * (size_t)g.seedCap));
         PLF_CUDA_OK(dalloc(&c->d_nSeeds, nImg));
-        PLF_CUDA_OK(dalloc(&c->d_used, nImg * npx));
+        PLF_CUDA_OK(dalloc(&c->d_used, nImg * ((npx + 31) / 32)));
         PLF_CUDA_OK(dalloc(&c->d_reg, nImg * npx));
         PLF_CUDA_OK(dalloc(&c->d_segs, nImg * (size_t)g.segCap * 4));
         PLF_CUDA_OK(dalloc(&c->d_nSegs, nImg));
@@ -264,7 +264,7 @@ PLF_API int plf_destroy(plf_ctx* c) {
     cudaStreamSynchronize(c->stream);
     void* ptrs[] = {c->d_pyr, c->d_blur, c->d_cells, c->d_cellCount, c->d_cand, c->d_scratch, c->d_lvlKp, c->d_lvlN,
                     c->d_kpTmp, c->d_descTmp, c->d_kp, c->d_desc, c->d_nKp, c->d_mono, c->d_err, c->d_uRight, c->d_depth,
-                    c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_ang, c->d_cs, c->d_n2, c->d_n2max, c->d_hist, c->d_seeds,
+                    c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_ang, c->d_rec, c->d_n2, c->d_n2max, c->d_hist, c->d_seeds,
                     c->d_nSeeds, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
                     c->d_sobel, c->d_lbd, c->d_ldesc, c->d_rowMask, c->d_dirR, c->d_dmat, c->d_m21, c->d_m12, c->d_disp,
                     c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2};

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) lsd_upscale_kernel(PlfGeom g, const uint8
 // ---------------------------------------------------------------------------------------------------------------
 // K4b  level-line field (LSD ll_angle): 2x2 gradient, squared norm, fastAtan2 angle (degrees), cosf/sinf of the angle,
 // per-image max of the squared norm over defined pixels.
-__global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, float* ang, float2* cs, int* n2o,
+__global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, float* ang, float4* rec, int* n2o,
                                                        int* n2max, int imgFirst) {
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     const int img = imgFirst + blockIdx.z;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t*
             }
         }
         ang[o] = a;
-        cs[o] = c;
+        rec[o] = make_float4(a, c.x, c.y, __int_as_float(n2));
         n2o[o] = n2;
     }
 #pragma unroll
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float*
             }
             __syncthreads();
         }
-        if (pos >= 0) out[pos] = p;
+        if (pos >= 0) out[pos] = ((p / g.Ws) << 16) | (p % g.Ws);   // packed (y<<16 | x)
         __syncthreads();
     }
 }
@@ -197,17 +197,16 @@ __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float*
 // K4c  region growing + rectangle fit (LSD region_grow / region2rect / get_theta), refine = 0.
 // One warp per image; seeds in order; every region is grown with the exact sequential rule: list entries are expanded
 // front to back, their 8 neighbours in raster order, a neighbour is accepted iff unused and aligned with the CURRENT
-// region angle, which is updated after every acceptance.  A batch covers 4 list entries x 8 neighbours = 32 lanes in
-// processing order; the loads of a batch are issued together and the acceptance chain is resolved with ballots.
-__device__ __forceinline__ bool lsd_aligned(double a, double theta, double prec) {
-    double n = theta - a;
-    if (n < 0) n = -n;
-    if (n > (3 * kPi) / 2) {
-        n -= 2 * kPi;
-        if (n < 0) n = -n;
-    }
-    return n <= prec;
-}
+// region angle, which is updated after every acceptance.  The kernel is bound by dependent-instruction latency (ncu:
+// ~270 warp instructions per accepted pixel at 0.14 IPC, DRAM idle), so the design minimises instructions per pixel and
+// shared memory per block (many images in flight per SM), not bytes:
+//  * per-pixel data is one read-only 16-byte record (angle, cosf, sinf, |g|^2) -> one LDG.128 per neighbour;
+//  * the `used` map is a bitmap in global memory (64 KB per image, L2-resident), cleared by a memset node;
+//  * list entries are packed (y<<16|x) so no integer division is ever needed; the BFS frontier lives in a small
+//    shared-memory ring, the full list also goes to global memory for the rectangle fit;
+//  * a batch covers 8 list entries x 8 neighbours = 2 candidates per lane in processing order; the loads of a batch are
+//    issued together and the acceptance chain is resolved with ballots, one fastAtan2 per accepted pixel.
+#define GROW_RING 512
 
 __device__ __forceinline__ double seq_sum_warp(double v, unsigned cnt, double acc) {
     // acc += v[0]; acc += v[1]; ... in lane order (sequential rounding, like the scalar loop)
@@ -215,78 +214,119 @@ __device__ __forceinline__ double seq_sum_warp(double v, unsigned cnt, double ac
     return acc;
 }
 
-__global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float* ang, const float2* cs, const int* n2,
-                                                      const int* seeds, const int* nSeeds, uint8_t* used, int* reg,
-                                                      float* segs, int* nSegsOut, int* err, int imgFirst) {
+struct GrowState {
+    int n;            // region size
+    float sumdx, sumdy;
+    double regAngle;
+};
+
+// resolves one set of 32 candidates (lane order = processing order); `valid` lanes hold pixel q (packed pk) with record r
+__device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int pk, const float4& r, double prec,
+                                           int lane, uint32_t* used, int* ring, int* R) {
+    unsigned pending = __ballot_sync(0xffffffffu, valid);
+    if (!pending) return;
+    const unsigned dup = __match_any_sync(0xffffffffu, valid ? q : -1 - lane);
+    const double aRad = (double)r.x * kDegToRad;
+    while (pending) {
+        // LSD isAligned(): |theta - a|, folded once around 2*pi, <= prec  (branch-free, same arithmetic)
+        double nd = fabs(__dsub_rn(st.regAngle, aRad));
+        const double nw = fabs(__dsub_rn(nd, 2 * kPi));
+        nd = (nd > (3 * kPi) / 2) ? nw : nd;
+        const unsigned am = __ballot_sync(0xffffffffu, nd <= prec) & pending;
+        if (!am) break;
+        const int Lw = __ffs(am) - 1;
+        const int pkL = __shfl_sync(0xffffffffu, pk, Lw);
+        const float cx = __shfl_sync(0xffffffffu, r.y, Lw), cy = __shfl_sync(0xffffffffu, r.z, Lw);
+        const unsigned dupL = __shfl_sync(0xffffffffu, dup, Lw);
+        if (lane == Lw) atomicOr(used + (q >> 5), 1u << (q & 31));
+        if (lane == 0) {
+            ring[st.n & (GROW_RING - 1)] = pkL;
+            R[st.n] = pkL;
+        }
+        ++st.n;
+        st.sumdx = __fadd_rn(st.sumdx, cx);
+        st.sumdy = __fadd_rn(st.sumdy, cy);
+        st.regAngle = (double)fast_atan2_deg(st.sumdy, st.sumdx) * kDegToRad;
+        pending &= ~((2u << Lw) - 1u) & ~dupL;
+    }
+}
+
+__global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* rec, const int* seeds, const int* nSeeds,
+                                                      uint32_t* usedAll, int* reg, float* segs, int* nSegsOut, int* err,
+                                                      int nWords, int imgFirst) {
+    __shared__ int ring[GROW_RING];
     const int img = imgFirst + blockIdx.x, lane = threadIdx.x;
     const int W = g.Ws, H = g.Hs;
     const size_t base = (size_t)img * W * H;
-    const float* A = ang + base;
-    const float2* CS = cs + base;
-    const int* N2 = n2 + base;
-    uint8_t* U = used + base;
+    const float4* REC = rec + base;
+    uint32_t* used = usedAll + (size_t)img * nWords;
     int* R = reg + base;
     const int* S = seeds + (size_t)img * g.seedCap;
     float* out = segs + (size_t)img * g.segCap * 4;
     const int ns = nSeeds[img];
     const double prec = g.prec;
     int nSeg = 0;
-    const int e = lane >> 3, k = lane & 7;
+    const int k = lane & 7;
     const int ddx = (k < 3) ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6));
     const int ddy = (k < 3) ? -1 : (k < 5 ? 0 : 1);
     for (int s0 = 0; s0 < ns; s0 += 32) {
-        const int mySeed = (s0 + lane < ns) ? S[s0 + lane] : -1;
-        const int cntS = min(32, ns - s0);
-        for (int si = 0; si < cntS; ++si) {
-            const int p = __shfl_sync(0xffffffffu, mySeed, si);
-            if (U[p]) continue;        // uniform (same address)
+        const int mySeed = (s0 + lane < ns) ? S[s0 + lane] : -1;       // packed (y<<16 | x)
+        const int myQ = (mySeed >> 16) * W + (mySeed & 0xFFFF);
+        const bool myFree = mySeed >= 0 && !((used[myQ >> 5] >> (myQ & 31)) & 1u);
+        unsigned fm = __ballot_sync(0xffffffffu, myFree);
+        while (fm) {
+            const int si = __ffs(fm) - 1;
+            fm &= fm - 1;
+            const int pk0 = __shfl_sync(0xffffffffu, mySeed, si);
+            const int p = __shfl_sync(0xffffffffu, myQ, si);
+            if ((used[p >> 5] >> (p & 31)) & 1u) continue;   // claimed by a region grown earlier in this chunk
             // ---- region_grow -------------------------------------------------------------------------------------
-            int n = 1;
-            if (lane == 0) { R[0] = p; U[p] = 1; }
-            double regAngle = (double)A[p] * kDegToRad;
-            float sumdx = (float)cos(regAngle), sumdy = (float)sin(regAngle);
+            GrowState st;
+            st.n = 1;
+            if (lane == 0) { ring[0] = pk0; R[0] = pk0; atomicOr(used + (p >> 5), 1u << (p & 31)); }
+            st.regAngle = (double)REC[p].x * kDegToRad;
+            st.sumdx = (float)cos(st.regAngle);
+            st.sumdy = (float)sin(st.regAngle);
             __syncwarp();
             int i = 0;
-            while (i < n) {
-                const int nb = min(4, n - i);
-                int q = -1;
-                float a = PLF_NOTDEF;
-                float2 c = make_float2(0.f, 0.f);
-                bool valid = false;
-                if (e < nb) {
-                    const int rp = R[i + e];
-                    const int ry = rp / W, rx = rp - ry * W;
-                    const int xx = rx + ddx, yy = ry + ddy;
-                    if (xx >= 0 && yy >= 0 && xx < W && yy < H) {
-                        q = yy * W + xx;
-                        const uint8_t u = U[q];
-                        a = A[q];
-                        c = CS[q];
-                        valid = (u == 0) && (a != PLF_NOTDEF);
+            while (i < st.n) {
+                const int nb = min(8, st.n - i);
+                const bool inRing = (st.n - i) <= GROW_RING;
+                int q[2], pk[2];
+                float4 r[2];
+                bool valid[2];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int e = s * 4 + (lane >> 3);
+                    q[s] = -1;
+                    pk[s] = 0;
+                    valid[s] = false;
+                    r[s] = make_float4(PLF_NOTDEF, 0.f, 0.f, 0.f);
+                    if (e < nb) {
+                        const int rp = inRing ? ring[(i + e) & (GROW_RING - 1)] : R[i + e];
+                        const int xx = (rp & 0xFFFF) + ddx, yy = (rp >> 16) + ddy;
+                        if (xx >= 0 && yy >= 0 && xx < W && yy < H) {
+                            q[s] = yy * W + xx;
+                            pk[s] = (yy << 16) | xx;
+                            if (!((used[q[s] >> 5] >> (q[s] & 31)) & 1u)) {
+                                r[s] = REC[q[s]];
+                                valid[s] = r[s].x != PLF_NOTDEF;
+                            }
+                        }
                     }
                 }
-                const unsigned dup = __match_any_sync(0xffffffffu, valid ? q : -1 - lane);
-                unsigned pending = __ballot_sync(0xffffffffu, valid);
-                const double aRad = (double)a * kDegToRad;
-                while (pending) {
-                    const bool al = valid && lsd_aligned(aRad, regAngle, prec);
-                    const unsigned am = __ballot_sync(0xffffffffu, al) & pending;
-                    if (!am) break;
-                    const int Lw = __ffs(am) - 1;
-                    const int qL = __shfl_sync(0xffffffffu, q, Lw);
-                    const float cx = __shfl_sync(0xffffffffu, c.x, Lw), cy = __shfl_sync(0xffffffffu, c.y, Lw);
-                    const unsigned dupL = __shfl_sync(0xffffffffu, dup, Lw);
-                    if (lane == 0) { R[n] = qL; U[qL] = 1; }
-                    ++n;
-                    sumdx = __fadd_rn(sumdx, cx);
-                    sumdy = __fadd_rn(sumdy, cy);
-                    regAngle = (double)fast_atan2_deg(sumdy, sumdx) * kDegToRad;
-                    pending &= ~((2u << Lw) - 1u);
-                    pending &= ~dupL;
-                }
+                grow_chain(st, valid[0], q[0], pk[0], r[0], prec, lane, used, ring, R);
                 __syncwarp();
+                if (nb > 4) {
+                    // pixels accepted while resolving the first set are no longer available
+                    if (valid[1] && ((used[q[1] >> 5] >> (q[1] & 31)) & 1u)) valid[1] = false;
+                    grow_chain(st, valid[1], q[1], pk[1], r[1], prec, lane, used, ring, R);
+                    __syncwarp();
+                }
                 i += nb;
             }
+            const int n = st.n;
+            const double regAngle = st.regAngle;
             if (n < g.minRegSize) continue;
             // ---- region2rect (sequential summation order reproduced with lane-ordered adds) -------------------------
             double sx = 0, sy = 0, sw = 0;
@@ -295,8 +335,8 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float* an
                 double wv = 0, xw = 0, yw = 0;
                 if (lane < cnt) {
                     const int rp = R[i0 + lane];
-                    const int ry = rp / W, rx = rp - ry * W;
-                    wv = sqrt((double)N2[rp] / 4.0);
+                    const int ry = rp >> 16, rx = rp & 0xFFFF;
+                    wv = sqrt((double)__float_as_int(REC[ry * W + rx].w) / 4.0);
                     xw = __dmul_rn((double)rx, wv);
                     yw = __dmul_rn((double)ry, wv);
                 }
@@ -311,8 +351,8 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float* an
                 double vxx = 0, vyy = 0, vxy = 0;
                 if (lane < cnt) {
                     const int rp = R[i0 + lane];
-                    const int ry = rp / W, rx = rp - ry * W;
-                    const double wv = sqrt((double)N2[rp] / 4.0);
+                    const int ry = rp >> 16, rx = rp & 0xFFFF;
+                    const double wv = sqrt((double)__float_as_int(REC[ry * W + rx].w) / 4.0);
                     const double dx = __dsub_rn((double)rx, cxm), dy = __dsub_rn((double)ry, cym);
                     vxx = __dmul_rn(__dmul_rn(dy, dy), wv);
                     vyy = __dmul_rn(__dmul_rn(dx, dx), wv);
@@ -339,7 +379,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float* an
             double lmin = 0, lmax = 0;
             for (int i0 = lane; i0 < n; i0 += 32) {
                 const int rp = R[i0];
-                const int ry = rp / W, rx = rp - ry * W;
+                const int ry = rp >> 16, rx = rp & 0xFFFF;
                 const double l = __dadd_rn(__dmul_rn(__dsub_rn((double)rx, cxm), dxr), __dmul_rn(__dsub_rn((double)ry, cym), dyr));
                 lmax = fmax(lmax, l);
                 lmin = fmin(lmin, l);
@@ -351,10 +391,10 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float* an
             }
             if (lane == 0) {
                 if (nSeg < g.segCap) {
-                    double r[4] = {__dadd_rn(cxm, __dmul_rn(lmin, dxr)), __dadd_rn(cym, __dmul_rn(lmin, dyr)),
-                                   __dadd_rn(cxm, __dmul_rn(lmax, dxr)), __dadd_rn(cym, __dmul_rn(lmax, dyr))};
+                    double rr[4] = {__dadd_rn(cxm, __dmul_rn(lmin, dxr)), __dadd_rn(cym, __dmul_rn(lmin, dyr)),
+                                    __dadd_rn(cxm, __dmul_rn(lmax, dxr)), __dadd_rn(cym, __dmul_rn(lmax, dyr))};
                     for (int q4 = 0; q4 < 4; ++q4) {
-                        double v = r[q4] + 0.5;
+                        double v = rr[q4] + 0.5;
                         if (g.lsdScale != 1) v /= g.lsdScale;
                         out[nSeg * 4 + q4] = (float)v;
                     }
@@ -636,13 +676,17 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     plf_mark(c, "lsd_gradient");
     cudaMemsetAsync(c->d_n2max + imgFirst, 0, nImg * sizeof(int), s);
     cudaMemsetAsync(c->d_hist + (size_t)imgFirst * g.nBins, 0, (size_t)nImg * g.nBins * sizeof(int), s);
-    lsd_grad_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_ang, c->d_cs, c->d_n2, c->d_n2max, imgFirst);
+    lsd_grad_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_ang, c->d_rec, c->d_n2, c->d_n2max, imgFirst);
     lsd_hist_kernel<<<dim3(64, nImg), 256, g.nBins * sizeof(int), s>>>(g, c->d_ang, c->d_n2, c->d_n2max, c->d_hist, imgFirst);
     plf_mark(c, "lsd_order");
     lsd_order_kernel<<<nImg, 1024, g.nBins * sizeof(int), s>>>(g, c->d_ang, c->d_n2, c->d_n2max, c->d_hist, c->d_seeds, c->d_nSeeds, imgFirst);
     plf_mark(c, "lsd_grow");
-    cudaMemsetAsync(c->d_used + (size_t)imgFirst * g.Ws * g.Hs, 0, (size_t)nImg * g.Ws * g.Hs, s);
-    lsd_grow_kernel<<<nImg, 32, 0, s>>>(g, c->d_ang, c->d_cs, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_err, imgFirst);
+    {
+        const int nWords = (g.Ws * g.Hs + 31) / 32;
+        cudaMemsetAsync(c->d_used + (size_t)imgFirst * nWords, 0, (size_t)nImg * nWords * 4, s);
+        lsd_grow_kernel<<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
+                                            c->d_nSegs, c->d_err, nWords, imgFirst);
+    }
     plf_mark(c, "line_keylines");
     const double minLen = c->p.min_line_length * std::min(g.W, g.H);
     keylines_kernel<<<nImg, 256, g.segCap * sizeof(float), s>>>(g, c->d_segs, c->d_nSegs, c->d_klAll, c->d_kl, c->d_nKl, c->d_err, minLen, c->p.lsd_nfeatures, imgFirst);

@@ -85,14 +85,14 @@ struct plf_ctx {
     uint8_t* d_lsdBlur = nullptr;    // [nImg][H][pitch0]
     uint8_t* d_lsdU = nullptr;       // [nImg][Hs][Ps]
     float* d_ang = nullptr;          // [nImg][Hs*Ws] degrees, NOTDEF
-    float2* d_cs = nullptr;          // [nImg][Hs*Ws] cosf/sinf of the level-line angle
+    float4* d_rec = nullptr;         // [nImg][Hs*Ws] per-pixel record of the region grower: angle, cosf, sinf, |g|^2 (as int bits)
     int* d_n2 = nullptr;             // [nImg][Hs*Ws] gx^2+gy^2
     int* d_n2max = nullptr;          // [nImg]
     int* d_hist = nullptr;           // [nImg][nBins]
-    int* d_seeds = nullptr;          // [nImg][seedCap] pixel indices in processing order
+    int* d_seeds = nullptr;          // [nImg][seedCap] seed pixels (packed y<<16|x) in processing order
     int* d_nSeeds = nullptr;         // [nImg]
-    uint8_t* d_used = nullptr;       // [nImg][Hs*Ws]
-    int* d_reg = nullptr;            // [nImg][Hs*Ws] region pixel list (reused per region)
+    uint32_t* d_used = nullptr;      // [nImg][ceil(Hs*Ws/32)] used bitmap of the region grower
+    int* d_reg = nullptr;            // [nImg][Hs*Ws] region pixel list, packed y<<16|x (reused per region)
     float* d_segs = nullptr;         // [nImg][segCap][4]
     int* d_nSegs = nullptr;          // [nImg]
     plf_keyline* d_kl = nullptr;     // [nImg][klCap]

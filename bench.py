@@ -6,8 +6,11 @@ response), stereo point + line matching, batch 64 pairs per call.  One process p
 sequences) are sharded across ranks with no data-path collective (replicas only, weak scaling); torch.distributed is
 used for the barrier and the max-over-ranks of the device time only.
 
-A "step" = one pass of the hot path over `contexts` batches of 64 pairs on this rank (several contexts are kept in
-flight on their own CUDA streams because the region-growing kernel is latency-bound, one warp per image).
+Each camera stream contributes a batch of 64 consecutive frames; a rank serves `streams` independent streams per
+context, so one call of the C ABI processes streams x 64 pairs (the region-growing kernel is latency-bound with one
+warp per image, hence many images per launch), and `contexts` such calls are kept in flight on their own CUDA streams
+so that the copies and the wide kernels of one overlap the narrow kernels of the other.
+A "step" = one pass of the hot path over contexts x streams x 64 pairs on this rank.
 
   value : pairs/s with the inputs already resident in HBM (plf_batch_run only), all ranks
   e2e   : pairs/s through the C ABI with pinned HOST buffers: H2D of the images + kernels + D2H of every result array
@@ -151,8 +154,9 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--contexts", type=int, default=8, help="batches kept in flight per GPU (one CUDA stream each)")
+    ap.add_argument("--batch", type=int, default=64, help="frames per camera stream per call (BASELINE config C2)")
+    ap.add_argument("--streams", type=int, default=16, help="independent camera streams served by one context")
+    ap.add_argument("--contexts", type=int, default=2, help="calls kept in flight per GPU (one CUDA stream each)")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic pairs generated per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -175,11 +179,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     prod = plf.load_product()
-    B, C = args.batch, args.contexts
+    B, C = args.batch * args.streams, args.contexts       # pairs per call, calls in flight
     if os.environ.get("PLF_BENCH_NO_LINES"):      # developer switch: ORB + stereo points only
         WORKLOAD["has_lines"] = 0
-    # this rank's streams: C contexts = C independent stereo streams in flight, 64 consecutive frames each
-    my_streams = shard_streams(C * world, world, rank)
+    # this rank's camera streams (global ids), args.streams of them per context
+    my_streams = shard_streams(C * args.streams * world, world, rank)
     distinct = min(args.distinct, B)
     seeds = [stream_seed(my_streams[0], f) for f in range(distinct)]
     Ld, Rd = make_inputs(seeds)
@@ -203,12 +207,23 @@ def main():
         for f in ctxs:
             f.batch_run(B)
 
+    pending = [False] * C
+
     def step_e2e():
-        for f, l, r in zip(ctxs, hostL, hostR):
+        # per context: collect the previous call's results (D2H + sync), then queue the next upload + kernels, so the
+        # other contexts keep the GPU busy while the host waits
+        for i, (f, l, r, out) in enumerate(zip(ctxs, hostL, hostR, results)):
+            if pending[i]:
+                f.batch_download(B, out)      # D2H of every result array + stream sync
             f.batch_upload_raw(l.data_ptr(), r.data_ptr(), B, W)
             f.batch_run(B)
-        for f, out in zip(ctxs, results):
-            f.batch_download(B, out)      # D2H of every result array + stream sync
+            pending[i] = True
+
+    def drain_e2e():
+        for i, (f, out) in enumerate(zip(ctxs, results)):
+            if pending[i]:
+                f.batch_download(B, out)
+                pending[i] = False
 
     def timed(step_fn, steps):
         """K steps bracketed by barrier+synchronize; device time by CUDA events fanned out to / joined from every
@@ -245,7 +260,32 @@ def main():
     launches = sum(f.launch_count() for f in ctxs) * args.steps
     for _ in range(2):
         step_e2e()
-    t_e2e = timed(step_e2e, args.steps)
+    drain_e2e()
+
+    def e2e_steps():
+        step_e2e()
+
+    barrier()
+    t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(main_stream)
+    for s_ in ext:
+        s_.wait_event(ev0)
+    for _ in range(args.steps):
+        step_e2e()
+    drain_e2e()                               # every result of the K steps is on the host when the clock stops
+    for s_ in ext:
+        d_ = torch.cuda.Event()
+        d_.record(s_)
+        main_stream.wait_event(d_)
+    ev1.record(main_stream)
+    barrier()
+    t_e2e = ev0.elapsed_time(ev1) / 1e3
+    t_e2e_wall = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([t_e2e], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.item())
     sampler.join(timeout=2)
 
     # per-stage device time and the dominant kernel's own duration (CUDA events on the launching stream, one context
@@ -280,12 +320,13 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "euroc_752x480_stereo_pointline_batch64", "width": W, "height": H, **WORKLOAD,
-                       "batch": B, "contexts_in_flight": C, "pairs_per_step": pairs_per_step,
+                       "frames_per_stream": args.batch, "streams_per_context": args.streams, "pairs_per_call": B,
+                       "contexts_in_flight": C, "pairs_per_step": pairs_per_step,
                        "distinct_pairs_per_rank": distinct,
                        "l2": "inputs larger than L2: %d contexts x %.0f MB of resident images" % (C, 2 * B * W * H / 1e6),
                        "parallelism": "replicas%d (streams sharded, no collective)" % world},
             "e2e": {"value": e2e, "unit": "stereo pairs/s", "h2d_bytes_per_step": h2d * B * C,
-                    "d2h_bytes_per_step": d2h * B * C},
+                    "d2h_bytes_per_step": d2h * B * C, "host_wall_s": round(t_e2e_wall, 4)},
             "gpu_launches": launches,
             "ms_per_stage": {k: round(v, 4) for k, v in stage_acc.items()},
             "roofline": {"bound": "hbm", "kernel": "lsd_grow_kernel", "achieved": achieved, "peak": peak,

@@ -172,7 +172,7 @@ static int build_geometry(plf_ctx* c, std::vector<PlfCell>& cells) {
     }
     g.segCap = 8192;
     g.seedCap = g.Ws * g.Hs;
-    if (g.nBins < 2 || g.nBins > 4096) return fail(PLF_ERR_UNSUPPORTED, "lsd_n_bins outside [2,4096]");
+    if (g.nBins < 2 || g.nBins > 1536) return fail(PLF_ERR_UNSUPPORTED, "lsd_n_bins outside [2,1536] (32 x n_bins cursors must fit shared memory)");
     if (g.Ws >= 32768 || g.Hs >= 32768) return fail(PLF_ERR_UNSUPPORTED, "scaled LSD image side >= 32768 (packed coordinates)");
     return PLF_OK;
 }
@@ -203,6 +203,7 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
     const size_t npx = (size_t)g.Ws * g.Hs;
     PLF_CUDA_OK(dalloc(&c->d_pyr, nImg * g.pyrBytes));
     PLF_CUDA_OK(dalloc(&c->d_blur, nImg * g.pyrBytes));
+    PLF_CUDA_OK(dalloc(&c->d_score, nImg * g.pyrBytes));
     PLF_CUDA_OK(dalloc(&c->d_cells, cells.size()));
     PLF_CUDA_OK(cudaMemcpy(c->d_cells, cells.data(), cells.size() * sizeof(PlfCell), cudaMemcpyHostToDevice));
     PLF_CUDA_OK(dalloc(&c->d_cellCount, nImg * g.nCellsTotal));
@@ -262,7 +263,7 @@ PLF_API int plf_destroy(plf_ctx* c) {
     if (!c) return PLF_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    void* ptrs[] = {c->d_pyr, c->d_blur, c->d_cells, c->d_cellCount, c->d_cand, c->d_scratch, c->d_lvlKp, c->d_lvlN,
+    void* ptrs[] = {c->d_pyr, c->d_blur, c->d_score, c->d_cells, c->d_cellCount, c->d_cand, c->d_scratch, c->d_lvlKp, c->d_lvlN,
                     c->d_kpTmp, c->d_descTmp, c->d_kp, c->d_desc, c->d_nKp, c->d_mono, c->d_err, c->d_uRight, c->d_depth,
                     c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_ang, c->d_rec, c->d_n2, c->d_n2max, c->d_hist, c->d_seeds,
                     c->d_nSeeds, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,

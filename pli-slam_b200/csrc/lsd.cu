@@ -128,26 +128,43 @@ __global__ void __launch_bounds__(256) lsd_hist_kernel(PlfGeom g, const float* a
         if (s_hist[i]) atomicAdd(hist + (size_t)img * g.nBins + i, s_hist[i]);
 }
 
-// Ordered seed list: defined pixels sorted by (bin descending, raster index ascending).  One 1024-thread block per
-// image walks the image in raster order; per-bin write cursors live in shared memory and the 32 warps of a chunk take
-// turns (only warps that hold a defined pixel), so the order inside a bin is raster order by construction.
+// Ordered seed list: defined pixels sorted by (bin descending, raster index ascending) — a stable counting sort.
+// One 1024-thread block per image; warp w owns the w-th contiguous raster segment.  Pass 1 counts per (warp, bin) in
+// shared memory, pass 2 turns the counts into write cursors (bins descending, then warps ascending), pass 3 lets every
+// warp walk its segment again and place its pixels: lanes of one 32-pixel step that share a bin are ranked with
+// __match_any_sync, so the order inside a bin is raster order by construction and no warp waits for another.
 __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float* ang, const int* n2, const int* n2max,
-                                                         const int* hist, int* seeds, int* nSeeds, int imgFirst) {
-    extern __shared__ int s_cur[];          // nBins cursors
+                                                         int* seeds, int* nSeeds, int imgFirst) {
+    extern __shared__ int s_cur[];          // [32][nBins]
     __shared__ int s_scan[32];
-    __shared__ int s_any[32];
     __shared__ int s_carry;
     const int img = imgFirst + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nBins = g.nBins;
-    // exclusive scan of the histogram in descending bin order
+    const double coef = lsd_bin_coef(n2max[img], nBins);
+    const size_t base = (size_t)img * g.Ws * g.Hs;
+    const int npx = g.Ws * g.Hs;
+    const int segLen = ((npx + 31) / 32 + 31) & ~31;
+    const int p0 = warp * segLen, p1 = min(p0 + segLen, npx);
+    int* mine = s_cur + warp * nBins;
+    for (int i = tid; i < 32 * nBins; i += 1024) s_cur[i] = 0;
     if (tid == 0) s_carry = 0;
     __syncthreads();
+    for (int p = p0 + lane; p < p1; p += 32)
+        if (ang[base + p] != PLF_NOTDEF) atomicAdd(&mine[lsd_bin(n2[base + p], coef)], 1);
+    __syncthreads();
+    // cursors: for bins in descending order, for warps in ascending order
     for (int b0 = 0; b0 < nBins; b0 += 1024) {
-        const int r = b0 + tid;                 // position in descending order
+        const int r = b0 + tid;                 // position in descending bin order
         const int b = nBins - 1 - r;
-        const int v = (r < nBins) ? hist[(size_t)img * nBins + b] : 0;
-        int inc = v;
+        int tot = 0;
+        if (r < nBins)
+            for (int w = 0; w < 32; ++w) {
+                const int t = s_cur[w * nBins + b];
+                s_cur[w * nBins + b] = tot;
+                tot += t;
+            }
+        int inc = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -155,41 +172,34 @@ __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float*
         }
         if (lane == 31) s_scan[warp] = inc;
         __syncthreads();
-        int base = s_carry;
-        for (int w = 0; w < warp; ++w) base += s_scan[w];
-        if (r < nBins) s_cur[b] = base + inc - v;
+        int start = s_carry;
+        for (int w = 0; w < warp; ++w) start += s_scan[w];
+        start += inc - tot;
+        if (r < nBins)
+            for (int w = 0; w < 32; ++w) s_cur[w * nBins + b] += start;
         __syncthreads();
-        if (tid == 1023) s_carry = base + inc;
+        if (tid == 1023) s_carry = start + tot;
         __syncthreads();
     }
     if (tid == 0) nSeeds[img] = s_carry;
-    const double coef = lsd_bin_coef(n2max[img], nBins);
-    const size_t base = (size_t)img * g.Ws * g.Hs;
     int* out = seeds + (size_t)img * g.seedCap;
-    const int npx = g.Ws * g.Hs;
     const unsigned lt = (1u << lane) - 1u;
-    for (int p0 = 0; p0 < npx; p0 += 1024) {
-        const int p = p0 + tid;
+    const int W = g.Ws;
+    for (int pb = p0; pb < p1; pb += 32) {
+        const int p = pb + lane;
         bool def = false;
         int bin = 0;
-        if (p < npx && ang[base + p] != PLF_NOTDEF) { def = true; bin = lsd_bin(n2[base + p], coef); }
+        if (p < p1 && ang[base + p] != PLF_NOTDEF) { def = true; bin = lsd_bin(n2[base + p], coef); }
         const unsigned wm = __ballot_sync(0xffffffffu, def);
-        if (lane == 0) s_any[warp] = wm != 0;
-        __syncthreads();
-        int pos = -1;
-        for (int w = 0; w < 32; ++w) {
-            if (!s_any[w]) continue;            // uniform across the block
-            if (warp == w && def) {
-                const unsigned grp = __match_any_sync(wm, bin);
-                const int b = s_cur[bin];
-                __syncwarp(wm);
-                pos = b + __popc(grp & lt);
-                if ((grp & lt) == 0) s_cur[bin] = b + __popc(grp);
-            }
-            __syncthreads();
+        if (def) {
+            const unsigned grp = __match_any_sync(wm, bin);
+            const int b = mine[bin];
+            __syncwarp(wm);
+            if ((grp & lt) == 0) mine[bin] = b + __popc(grp);
+            const int y = p / W;
+            out[b + __popc(grp & lt)] = (y << 16) | (p - y * W);   // packed (y<<16 | x)
         }
-        if (pos >= 0) out[pos] = ((p / g.Ws) << 16) | (p % g.Ws);   // packed (y<<16 | x)
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -675,11 +685,17 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     lsd_upscale_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, imgFirst);
     plf_mark(c, "lsd_gradient");
     cudaMemsetAsync(c->d_n2max + imgFirst, 0, nImg * sizeof(int), s);
-    cudaMemsetAsync(c->d_hist + (size_t)imgFirst * g.nBins, 0, (size_t)nImg * g.nBins * sizeof(int), s);
     lsd_grad_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_ang, c->d_rec, c->d_n2, c->d_n2max, imgFirst);
-    lsd_hist_kernel<<<dim3(64, nImg), 256, g.nBins * sizeof(int), s>>>(g, c->d_ang, c->d_n2, c->d_n2max, c->d_hist, imgFirst);
     plf_mark(c, "lsd_order");
-    lsd_order_kernel<<<nImg, 1024, g.nBins * sizeof(int), s>>>(g, c->d_ang, c->d_n2, c->d_n2max, c->d_hist, c->d_seeds, c->d_nSeeds, imgFirst);
+    {
+        const size_t smem = (size_t)32 * g.nBins * sizeof(int);
+        static size_t s_attr = 0;
+        if (smem > 48 * 1024 && smem > s_attr) {
+            cudaFuncSetAttribute(lsd_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            s_attr = smem;
+        }
+        lsd_order_kernel<<<nImg, 1024, smem, s>>>(g, c->d_ang, c->d_n2, c->d_n2max, c->d_seeds, c->d_nSeeds, imgFirst);
+    }
     plf_mark(c, "lsd_grow");
     {
         const int nWords = (g.Ws * g.Hs + 31) / 32;
@@ -696,5 +712,5 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     sobel_kernel<<<dim3((g.W + 31) / 32, (g.H + 7) / 8, nImg), dim3(32, 8), 0, s>>>(c->d_lbdBlur, imgBytes, ip, c->d_sobel, g.W, g.H, imgFirst);
     plf_mark(c, "lbd_descriptor");
     lbd_kernel<<<dim3((g.klCap + 3) / 4, nImg), 128, 0, s>>>(g, c->d_sobel, c->d_kl, c->d_nKl, c->d_lbd, c->d_ldesc, imgFirst);
-    return launches + 9;
+    return launches + 8;
 }

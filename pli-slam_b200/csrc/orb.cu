@@ -66,14 +66,18 @@ __global__ void __launch_bounds__(256) blur_pyramid_kernel(PlfGeom g, const uint
 
 // ---------------------------------------------------------------------------------------------------------------
 // K2a  FAST-9/16 per grid cell with the ORB_SLAM3 retry: cv::FAST(window, iniTh, nms) and, only if the cell came back
-// empty, cv::FAST(window, minTh, nms) (src/ORBextractor.cc:787-854).  One block per cell window.  The corner score
-// s = max{t : still a corner} does not depend on the threshold, and for a pixel with s >= t strict 3x3 NMS against
-// thresholded neighbours equals NMS against raw scores, so one score map serves both thresholds.
-// Corner score s = max{t : a 9-arc has all d > t or all d < -t} by bisection on t with 16-bit arc masks.
-// Compare/logic ops only, on purpose: a min/max formulation (OpenCV's cornerScore) is fused by ptxas 12.9 — and by
-// the 580 driver's JIT — into VIMNMX3 chains that return wrong values on sm_100a when min, max and negation are mixed
-// (reproduced in isolation; ptxas -O0, which emits no VIMNMX3, is correct).  tests/test_build.py asserts that the
-// library contains no VIMNMX3.
+// empty, cv::FAST(window, minTh, nms) (src/ORBextractor.cc:787-854).  The corner score s = max{t : still a corner} does
+// not depend on the threshold, and for a pixel with s >= t strict 3x3 NMS against thresholded neighbours equals NMS
+// against raw scores, so ONE score map serves both thresholds.  Two kernels:
+//   fast_score_kernel : pixel-parallel score map of every level (32x8 tiles staged in shared memory, all levels in
+//                       one launch); scores below minTh are stored as 0.
+//   fast_cells_kernel : block per cell window: strict NMS restricted to the cell's detection area (neighbours outside
+//                       count as 0, exactly like FAST on the sub-image), ini/min threshold choice, ordered compaction.
+//
+// Corner score by bisection on t with 16-bit arc masks — compare/logic ops only, on purpose: a min/max formulation
+// (OpenCV's cornerScore) is fused by ptxas 12.9 — and by the 580 driver's JIT — into VIMNMX3 chains that return wrong
+// values on sm_100a when min, max and negation are mixed (reproduced in isolation; ptxas -O0, which emits no VIMNMX3,
+// is correct).  tests/test_build.py asserts that the library contains no VIMNMX3.
 __device__ __forceinline__ bool fast_run9(unsigned m) {
     const unsigned m2 = m | (m << 16);
     unsigned r = m2 & (m2 >> 1);
@@ -82,75 +86,132 @@ __device__ __forceinline__ bool fast_run9(unsigned m) {
     r &= (m2 >> 8);
     return (r & 0xFFFFu) != 0u;
 }
-__device__ __forceinline__ int fast_score16(const int* d) {
-    int t = -1;
+// Exact corner score of a pixel that IS a corner at some threshold >= 0, single polarity (a bright and a dark 9-arc
+// cannot coexist on a 16-pixel circle).  Bit-sliced bisection: B[b] holds bit b of e[k] = clamp(+-d[k], 0, 255) for the
+// 16 circle pixels; walking the bit planes from the top keeps the sets {e > prefix} and {e == prefix}, so each of the 8
+// steps costs a handful of logic ops plus one 9-run test.  Returns M-1 with M = max over 9-arcs of min(e).
+__device__ __forceinline__ int fast_score16(const int* d, bool bright) {
+    unsigned B[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int bit = 128; bit > 0; bit >>= 1) {
-        const int c = t + bit;
+    for (int k = 0; k < 16; ++k) {
+        int e = bright ? d[k] : -d[k];
+        e = e < 0 ? 0 : e;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) B[b] |= ((unsigned)(e >> b) & 1u) << k;
+    }
+    unsigned gt = 0u, eq = 0xFFFFu;
+    int M = 0;
+#pragma unroll
+    for (int b = 7; b >= 0; --b) {
+        if (fast_run9(gt | (eq & B[b]))) { M |= 1 << b; eq &= B[b]; }
+        else { gt |= eq & B[b]; eq &= ~B[b]; }
+    }
+    return M - 1;
+}
+
+#define FS_TW 32
+#define FS_TH 8
+#define FS_IW (FS_TW + 6)
+#define FS_IH (FS_TH + 6)
+__global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_t* pyr, uint8_t* score, int imgFirst) {
+    __shared__ uint8_t s_in[FS_IH][FS_IW + 2];
+    // locate (level, tile): tiles cover [19, w-19) x [19, h-19), the union of all cell detection areas
+    int t = blockIdx.x, l = 0, tx = 0;
+    for (; l < g.nLevels; ++l) {
+        tx = (g.lv[l].w - 2 * PLF_EDGE + FS_TW - 1) / FS_TW;
+        const int n = tx * ((g.lv[l].h - 2 * PLF_EDGE + FS_TH - 1) / FS_TH);
+        if (t < n) break;
+        t -= n;
+    }
+    if (l >= g.nLevels) return;
+    const PlfLevel& lv = g.lv[l];
+    const int img = imgFirst + blockIdx.y;
+    const uint8_t* src = pyr + (size_t)img * g.pyrBytes + lv.off;
+    uint8_t* dst = score + (size_t)img * g.pyrBytes + lv.off;
+    const int x0 = PLF_EDGE + (t % tx) * FS_TW, y0 = PLF_EDGE + (t / tx) * FS_TH;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < FS_IW * FS_IH; i += 256) {
+        const int iy = i / FS_IW, ix = i - iy * FS_IW;
+        const int gx = min(x0 - 3 + ix, lv.w - 1), gy = min(y0 - 3 + iy, lv.h - 1);
+        s_in[iy][ix] = src[(size_t)gy * lv.pitch + gx];
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const bool inside = x < lv.w - PLF_EDGE && y < lv.h - PLF_EDGE;
+    constexpr int ST = FS_IW + 2;
+    const uint8_t* p = &s_in[threadIdx.y + 3][threadIdx.x + 3];
+    const int v = *p;
+    const int th = g.minTh;
+    // high-speed test: every 9-arc contains one pixel of each opposite pair {k, k+8}
+    auto cls = [&](int off) { const int d = v - (int)p[off]; return (d > th ? 1 : 0) | (d < -th ? 2 : 0); };
+    int m = cls(3 * ST) | cls(-3 * ST);
+    m &= cls(3) | cls(-3);
+    m &= cls(2 * ST + 2) | cls(-2 * ST - 2);
+    m &= cls(-2 * ST + 2) | cls(2 * ST - 2);
+    const int offs[16] = {3 * ST,  3 * ST + 1,  2 * ST + 2,  ST + 3,  3,  -ST + 3, -2 * ST + 2, -3 * ST + 1,
+                          -3 * ST, -3 * ST - 1, -2 * ST - 2, -ST - 3, -3, ST - 3,  2 * ST - 2,  3 * ST - 1};
+    // full 16-pixel test at minTh for the survivors; corners are queued so that the (expensive) exact score is computed
+    // densely, one queued corner per thread, instead of once per warp that happens to contain a corner
+    __shared__ int s_cnt;
+    __shared__ unsigned short s_queue[FS_TW * FS_TH];
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    bool corner = false;
+    if (m != 0 && inside) {
         unsigned mb = 0, md = 0;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            mb |= (unsigned)(d[k] > c) << k;
-            md |= (unsigned)(d[k] < -c) << k;
+            const int d = v - (int)p[offs[k]];
+            mb |= (unsigned)(d > th) << k;
+            md |= (unsigned)(d < -th) << k;
         }
-        if (fast_run9(mb) || fast_run9(md)) t = c;
+        const bool br = fast_run9(mb);
+        corner = br || fast_run9(md);
+        if (corner) s_queue[atomicAdd(&s_cnt, 1)] = (unsigned short)(tid | (br ? 0x8000 : 0));
     }
-    return t;
+    if (inside && !corner) dst[(size_t)y * lv.pitch + x] = 0;
+    __syncthreads();
+    const int nq = s_cnt;
+    for (int i = tid; i < nq; i += 256) {
+        const int e = s_queue[i];
+        const int t2 = e & 0x7FFF, ty = t2 >> 5, txx = t2 & 31;
+        const uint8_t* q = &s_in[ty + 3][txx + 3];
+        const int vq = *q;
+        int d[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[k] = vq - (int)q[offs[k]];
+        dst[(size_t)(y0 + ty) * lv.pitch + x0 + txx] = (uint8_t)fast_score16(d, (e & 0x8000) != 0);   // >= minTh
+    }
 }
 
 #define FAST_MAXW 72   // window side limit: wCell+6 < 2*30+6
-__global__ void __launch_bounds__(256) fast_cells_kernel(PlfGeom g, const uint8_t* pyr, const PlfCell* cells,
+__global__ void __launch_bounds__(128) fast_cells_kernel(PlfGeom g, const uint8_t* score, const PlfCell* cells,
                                                          int* cellCount, uint32_t* cand, int imgFirst) {
-    __shared__ uint8_t s_win[FAST_MAXW * FAST_MAXW];
-    __shared__ uint8_t s_sc[FAST_MAXW * FAST_MAXW];
-    __shared__ int s_warp[8];
-    __shared__ int s_anyIni;
+    __shared__ uint8_t s_sc[(FAST_MAXW - 6) * (FAST_MAXW - 6)];
+    __shared__ uint8_t s_keep[(FAST_MAXW - 6) * (FAST_MAXW - 6)];
+    __shared__ int s_warp[4];
     const PlfCell c = cells[blockIdx.x];
     const int img = imgFirst + blockIdx.y;
     const PlfLevel& lv = g.lv[c.level];
-    const uint8_t* src = pyr + (size_t)img * g.pyrBytes + lv.off;
-    const int cols = c.x1 - c.x0, rows = c.y1 - c.y0;
-    const int aw = cols - 6, ah = rows - 6;
+    const uint8_t* src = score + (size_t)img * g.pyrBytes + lv.off;
+    const int aw = c.x1 - c.x0 - 6, ah = c.y1 - c.y0 - 6;     // detection area of cv::FAST on the window
     const int tid = threadIdx.x;
     int* outCount = cellCount + (size_t)img * g.nCellsTotal + blockIdx.x;
     if (aw <= 0 || ah <= 0) {
         if (tid == 0) *outCount = 0;
         return;
     }
-    if (tid == 0) s_anyIni = 0;
-    for (int i = tid; i < cols * rows; i += 256) {
-        int y = i / cols, x = i - y * cols;
-        s_win[y * FAST_MAXW + x] = src[(size_t)(c.y0 + y) * lv.pitch + c.x0 + x];
-    }
-    __syncthreads();
-    const int offs[16] = {3 * FAST_MAXW,      3 * FAST_MAXW + 1,  2 * FAST_MAXW + 2,  FAST_MAXW + 3,
-                          3,                  -FAST_MAXW + 3,     -2 * FAST_MAXW + 2, -3 * FAST_MAXW + 1,
-                          -3 * FAST_MAXW,     -3 * FAST_MAXW - 1, -2 * FAST_MAXW - 2, -FAST_MAXW - 3,
-                          -3,                 FAST_MAXW - 3,      2 * FAST_MAXW - 2,  3 * FAST_MAXW - 1};
-    const int minTh = g.minTh, iniTh = g.iniTh;
-    for (int i = tid; i < aw * ah; i += 256) {
+    const int n = aw * ah;
+    for (int i = tid; i < n; i += 128) {
         const int y = i / aw, x = i - y * aw;
-        const uint8_t* p = &s_win[(y + 3) * FAST_MAXW + x + 3];
-        const int v = *p;
-        // cheap reject at minTh: 16-bit brighter/darker masks, look for a run of 9
-        unsigned mb = 0, md = 0;
-        int d[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            d[k] = v - (int)p[offs[k]];
-            mb |= (unsigned)(d[k] > minTh) << k;
-            md |= (unsigned)(d[k] < -minTh) << k;
-        }
-        int s = 0;
-        if (fast_run9(mb) || fast_run9(md)) s = fast_score16(d);   // corner at minTh => s >= minTh
-        s_sc[y * FAST_MAXW + x] = (uint8_t)s;
+        s_sc[i] = src[(size_t)(c.y0 + 3 + y) * lv.pitch + c.x0 + 3 + x];
     }
     __syncthreads();
-    // strict 3x3 NMS inside the detection area (outside counts as 0); flags overwrite s_win
+    const int iniTh = g.iniTh, minTh = g.minTh;
     bool anyIni = false;
-    for (int i = tid; i < aw * ah; i += 256) {
+    for (int i = tid; i < n; i += 128) {
         const int y = i / aw, x = i - y * aw;
-        const int s = s_sc[y * FAST_MAXW + x];
+        const int s = s_sc[i];
         bool keep = s > 0;
         if (keep) {
 #pragma unroll
@@ -159,36 +220,31 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(PlfGeom g, const uint8_
                 for (int dx = -1; dx <= 1; ++dx) {
                     if (dx == 0 && dy == 0) continue;
                     const int yy = y + dy, xx = x + dx;
-                    const int n = (yy < 0 || xx < 0 || yy >= ah || xx >= aw) ? 0 : s_sc[yy * FAST_MAXW + xx];
-                    keep = keep && (s > n);
+                    const int nb = (yy < 0 || xx < 0 || yy >= ah || xx >= aw) ? 0 : s_sc[yy * aw + xx];
+                    keep = keep && (s > nb);
                 }
         }
-        s_win[y * FAST_MAXW + x] = keep ? 1 : 0;
+        s_keep[i] = keep ? 1 : 0;
         anyIni |= keep && s >= iniTh;
     }
-    if (__syncthreads_or(anyIni)) anyIni = true;
-    const int th = anyIni ? iniTh : minTh;
+    const int th = __syncthreads_or(anyIni) ? iniTh : minTh;
     // ordered (raster) compaction: each thread owns a contiguous run of pixels
-    const int n = aw * ah, per = (n + 255) / 256;
+    const int per = (n + 127) / 128;
     const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
     int cnt = 0;
-    for (int i = i0; i < i1; ++i) {
-        const int y = i / aw, x = i - y * aw;
-        cnt += (s_win[y * FAST_MAXW + x] && s_sc[y * FAST_MAXW + x] >= th);
-    }
-    // block exclusive scan of cnt
+    for (int i = i0; i < i1; ++i) cnt += (s_keep[i] && s_sc[i] >= th);
     const int lane = tid & 31, warp = tid >> 5;
     int inc = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     int base = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < 4; ++w) {
         if (w < warp) base += s_warp[w];
         total += s_warp[w];
     }
@@ -196,14 +252,15 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(PlfGeom g, const uint8_
     uint32_t* out = cand + (size_t)img * g.candCapTotal + c.outBase;
     const int relx = c.x0 + 3 - PLF_MINB, rely = c.y0 + 3 - PLF_MINB;
     for (int i = i0; i < i1; ++i) {
-        const int y = i / aw, x = i - y * aw;
-        const int s = s_sc[y * FAST_MAXW + x];
-        if (s_win[y * FAST_MAXW + x] && s >= th) {
+        const int s = s_sc[i];
+        if (s_keep[i] && s >= th) {
+            const int y = i / aw, x = i - y * aw;
             if (pos < c.cap) out[pos] = (uint32_t)(relx + x) | ((uint32_t)(rely + y) << 12) | ((uint32_t)s << 24);
             ++pos;
         }
     }
     if (tid == 0) *outCount = min(total, c.cap);
+    (void)minTh;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -633,7 +690,13 @@ int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1) {
     plf_mark(c, "orb_blur");
     blur_pyramid_kernel<<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(g, c->d_pyr, c->d_blur, imgFirst);
     plf_mark(c, "orb_fast");
-    fast_cells_kernel<<<dim3(g.nCellsTotal, nImg), 256, 0, s>>>(g, c->d_pyr, c->d_cells, c->d_cellCount, c->d_cand,
+    {
+        int st = 0;
+        for (int l = 0; l < g.nLevels; ++l)
+            st += ((g.lv[l].w - 2 * PLF_EDGE + FS_TW - 1) / FS_TW) * ((g.lv[l].h - 2 * PLF_EDGE + FS_TH - 1) / FS_TH);
+        fast_score_kernel<<<dim3(st, nImg), dim3(32, 8), 0, s>>>(g, c->d_pyr, c->d_score, imgFirst);
+    }
+    fast_cells_kernel<<<dim3(g.nCellsTotal, nImg), 128, 0, s>>>(g, c->d_score, c->d_cells, c->d_cellCount, c->d_cand,
                                                                imgFirst);
     int maxQ = 0;
     for (int l = 0; l < g.nLevels; ++l) maxQ = max(maxQ, max(g.lv[l].quota, 4 * g.lv[l].nIni));
@@ -652,5 +715,5 @@ int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1) {
                                                                     c->d_kpTmp, c->d_descTmp, c->d_nKp, imgFirst);
     place_rows_kernel<<<nImg, 1024, 0, s>>>(g, c->d_kpTmp, c->d_descTmp, c->d_nKp, c->d_kp, c->d_desc, c->d_mono,
                                             lap0, lap1, imgFirst);
-    return launches + 5;
+    return launches + 6;
 }

@@ -64,6 +64,7 @@ struct plf_ctx {
     // ORB device buffers
     uint8_t* d_pyr = nullptr;        // [nImg][pyrBytes]
     uint8_t* d_blur = nullptr;       // [nImg][pyrBytes]
+    uint8_t* d_score = nullptr;      // [nImg][pyrBytes] FAST corner score map (0 below minTh), pyramid layout
     PlfCell* d_cells = nullptr;      // [nCellsTotal]
     int* d_cellCount = nullptr;      // [nImg][nCellsTotal]
     uint32_t* d_cand = nullptr;      // [nImg][candCapTotal] packed x | y<<12 | score<<24 (relative to min border)

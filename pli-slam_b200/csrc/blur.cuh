@@ -18,30 +18,40 @@ __device__ __forceinline__ void blur_tile(const BlurJob& j, const int* taps, int
     constexpr int R = K / 2, TW = 32, TH = 32, IW = TW + 2 * R, IH = TH + 2 * R;
     __shared__ uint8_t s_in[IH][IW + 2];
     __shared__ uint16_t s_h[IH][TW];
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int i = tid; i < IW * IH; i += 256) {
-        int iy = i / IW, ix = i - iy * IW;
-        int gx = reflect101(tx0 + ix - R, j.w), gy = reflect101(ty0 + iy - R, j.h);
-        gx = min(max(gx, 0), j.w - 1);
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    // (32+2R)^2 source window, REFLECT_101 at the image border; block is 32x8 threads
+    int gx0 = reflect101(tx0 + tx - R, j.w);
+    gx0 = min(max(gx0, 0), j.w - 1);
+    int gx1 = reflect101(tx0 + 32 + tx - R, j.w);
+    gx1 = min(max(gx1, 0), j.w - 1);
+#pragma unroll
+    for (int iy = ty; iy < IH; iy += 8) {
+        int gy = reflect101(ty0 + iy - R, j.h);
         gy = min(max(gy, 0), j.h - 1);
-        s_in[iy][ix] = j.src[(size_t)gy * j.sp + gx];
+        const uint8_t* row = j.src + (size_t)gy * j.sp;
+        s_in[iy][tx] = row[gx0];
+        if (tx < 2 * R) s_in[iy][32 + tx] = row[gx1];
     }
     __syncthreads();
-    for (int i = tid; i < TW * IH; i += 256) {
-        int iy = i / TW, ix = i - iy * TW;
+#pragma unroll
+    for (int iy = ty; iy < IH; iy += 8) {
         int acc = 0;
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc += taps[k] * s_in[iy][ix + k];
-        s_h[iy][ix] = (uint16_t)acc;
+        for (int k = 0; k < K; ++k) acc += taps[k] * s_in[iy][tx + k];
+        s_h[iy][tx] = (uint16_t)acc;
     }
     __syncthreads();
-    for (int oy = threadIdx.y; oy < TH; oy += 8) {
-        const int gx = tx0 + threadIdx.x, gy = ty0 + oy;
-        if (gx < j.w && gy < j.h) {
-            unsigned acc = 0;
+    const int gx = tx0 + tx;
+    if (gx < j.w) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc += (unsigned)taps[k] * s_h[oy + k][threadIdx.x];
-            j.dst[(size_t)gy * j.dp + gx] = (uint8_t)((acc + 32768u) >> 16);
+        for (int oy = ty; oy < TH; oy += 8) {
+            const int gy = ty0 + oy;
+            if (gy < j.h) {
+                unsigned acc = 0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc += (unsigned)taps[k] * s_h[oy + k][tx];
+                j.dst[(size_t)gy * j.dp + gx] = (uint8_t)((acc + 32768u) >> 16);
+            }
         }
     }
 }

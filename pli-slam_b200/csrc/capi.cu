@@ -128,6 +128,9 @@ static int build_geometry(plf_ctx* c, std::vector<PlfCell>& cells) {
                 ce.level = (short)l; ce.x0 = (short)iniX; ce.y0 = (short)iniY; ce.x1 = (short)maxX; ce.y1 = (short)maxY;
                 const int aw = std::max(maxX - iniX - 6, 0), ah = std::max(maxY - iniY - 6, 0);
                 ce.cap = ((aw + 1) / 2) * ((ah + 1) / 2);
+                ce.magic = aw > 0 ? ((1 << 20) + aw - 1) / aw : 0;
+                for (int i = 0; i < aw * ah; ++i)
+                    if ((int)(((unsigned)i * (unsigned)ce.magic) >> 20) != i / aw) return fail(PLF_ERR_UNSUPPORTED, "FAST cell index magic is inexact");
                 ce.outBase = candOff;
                 candOff += ce.cap;
                 cells.push_back(ce);
@@ -196,7 +199,7 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
     std::vector<PlfCell> cells;
     int rc = build_geometry(c, cells);
     if (rc) { delete c; return rc; }
-    const PlfGeom& g = c->g;
+    PlfGeom& g = c->g;
     const size_t nImg = (size_t)p->max_batch * 2, nSlot = p->max_batch;
     c->nImgMax = (int)nImg;
     PLF_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -206,6 +209,61 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
     PLF_CUDA_OK(dalloc(&c->d_score, nImg * g.pyrBytes));
     PLF_CUDA_OK(dalloc(&c->d_cells, cells.size()));
     PLF_CUDA_OK(cudaMemcpy(c->d_cells, cells.data(), cells.size() * sizeof(PlfCell), cudaMemcpyHostToDevice));
+    {
+        // tile tables (one entry per thread block) and bilinear coefficient tables, built once on the host
+        std::vector<PlfTile> tb, tf;
+        std::vector<PlfLin> lin;
+        for (int l = 0; l < g.nLevels; ++l) {
+            const PlfLevel& lv = g.lv[l];
+            for (int y = 0; y < lv.h; y += 32)
+                for (int x = 0; x < lv.w; x += 32) tb.push_back(PlfTile{(short)l, (short)x, (short)y, 0});
+            for (int y = PLF_EDGE; y < lv.h - PLF_EDGE; y += 8)
+                for (int x = PLF_EDGE; x < lv.w - PLF_EDGE; x += 32) tf.push_back(PlfTile{(short)l, (short)x, (short)y, 0});
+        }
+        // cv::resize(INTER_LINEAR) 8U coefficients of level l from level l-1
+        auto lin11 = [&](int nSrc, int nDst) {
+            const double scale = (double)nSrc / nDst;
+            for (int d = 0; d < nDst; ++d) {
+                float f = (float)((d + 0.5) * scale - 0.5);
+                int sx = (int)std::floor(f);
+                f -= sx;
+                if (sx < 0) { f = 0; sx = 0; }
+                if (sx >= nSrc - 1) { f = 0; sx = nSrc - 1; }
+                lin.push_back(PlfLin{(unsigned short)sx, (short)std::nearbyintf((1.f - f) * 2048.f), (short)std::nearbyintf(f * 2048.f), 0});
+            }
+        };
+        for (int l = 1; l < g.nLevels; ++l) {
+            c->g.lv[l].xTab = (int)lin.size();
+            lin11(g.lv[l - 1].w, g.lv[l].w);
+            c->g.lv[l].yTab = (int)lin.size();
+            lin11(g.lv[l - 1].h, g.lv[l].h);
+        }
+        // cv::resize(INTER_LINEAR_EXACT) Q8 coefficients of the LSD upscale (fact 4)
+        auto lin8 = [&](int nSrc, int nDst) {
+            const double inv = 1.0 / g.lsdScale;
+            for (int d = 0; d < nDst; ++d) {
+                const double f = inv * (d + 0.5) - 0.5;
+                const int i = (int)std::floor(f);
+                int o = 0, a = 0;
+                if (i >= 0 && nSrc > 1) {
+                    if (i < nSrc - 1) { o = i; a = (int)std::nearbyint((f - i) * 256.0); } else { o = nSrc - 1; a = 0; }
+                }
+                lin.push_back(PlfLin{(unsigned short)o, (short)(256 - a), (short)a, 0});
+            }
+        };
+        c->linLsdX = (int)lin.size();
+        lin8(g.W, g.Ws);
+        c->linLsdY = (int)lin.size();
+        lin8(g.H, g.Hs);
+        c->nTilesBlur = (int)tb.size();
+        c->nTilesFast = (int)tf.size();
+        PLF_CUDA_OK(dalloc(&c->d_tilesBlur, tb.size()));
+        PLF_CUDA_OK(dalloc(&c->d_tilesFast, tf.size()));
+        PLF_CUDA_OK(dalloc(&c->d_lin, lin.size()));
+        PLF_CUDA_OK(cudaMemcpy(c->d_tilesBlur, tb.data(), tb.size() * sizeof(PlfTile), cudaMemcpyHostToDevice));
+        PLF_CUDA_OK(cudaMemcpy(c->d_tilesFast, tf.data(), tf.size() * sizeof(PlfTile), cudaMemcpyHostToDevice));
+        PLF_CUDA_OK(cudaMemcpy(c->d_lin, lin.data(), lin.size() * sizeof(PlfLin), cudaMemcpyHostToDevice));
+    }
     PLF_CUDA_OK(dalloc(&c->d_cellCount, nImg * g.nCellsTotal));
     PLF_CUDA_OK(dalloc(&c->d_cand, nImg * g.candCapTotal));
     PLF_CUDA_OK(dalloc(&c->d_scratch, nImg * 2 * g.candCapTotal));
@@ -224,11 +282,8 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
     if (p->has_lines) {
         PLF_CUDA_OK(dalloc(&c->d_lsdBlur, nImg * (size_t)g.lv[0].pitch * g.H));
         PLF_CUDA_OK(dalloc(&c->d_lsdU, nImg * (size_t)g.Ps * g.Hs));
-        PLF_CUDA_OK(dalloc(&c->d_ang, nImg * npx));
         PLF_CUDA_OK(dalloc(&c->d_rec, nImg * npx));
-        PLF_CUDA_OK(dalloc(&c->d_n2, nImg * npx));
         PLF_CUDA_OK(dalloc(&c->d_n2max, nImg));
-        PLF_CUDA_OK(dalloc(&c->d_hist, nImg * g.nBins));
         PLF_CUDA_OK(dalloc(&c->d_seeds, nImg * (size_t)g.seedCap));
         PLF_CUDA_OK(dalloc(&c->d_nSeeds, nImg));
         PLF_CUDA_OK(dalloc(&c->d_used, nImg * ((npx + 31) / 32)));
@@ -263,9 +318,9 @@ PLF_API int plf_destroy(plf_ctx* c) {
     if (!c) return PLF_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    void* ptrs[] = {c->d_pyr, c->d_blur, c->d_score, c->d_cells, c->d_cellCount, c->d_cand, c->d_scratch, c->d_lvlKp, c->d_lvlN,
+    void* ptrs[] = {c->d_pyr, c->d_blur, c->d_score, c->d_tilesBlur, c->d_tilesFast, c->d_lin, c->d_cells, c->d_cellCount, c->d_cand, c->d_scratch, c->d_lvlKp, c->d_lvlN,
                     c->d_kpTmp, c->d_descTmp, c->d_kp, c->d_desc, c->d_nKp, c->d_mono, c->d_err, c->d_uRight, c->d_depth,
-                    c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_ang, c->d_rec, c->d_n2, c->d_n2max, c->d_hist, c->d_seeds,
+                    c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_rec, c->d_n2max, c->d_seeds,
                     c->d_nSeeds, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
                     c->d_sobel, c->d_lbd, c->d_ldesc, c->d_rowMask, c->d_dirR, c->d_dmat, c->d_m21, c->d_m12, c->d_disp,
                     c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2};
@@ -511,7 +566,7 @@ PLF_API int plf_tap_lsd_angles(plf_ctx* c, int slot, int side, float* out, int* 
     if (!out) return PLF_OK;
     PLF_CUDA_OK(cudaSetDevice(c->device));
     const size_t npx = (size_t)c->g.Ws * c->g.Hs;
-    PLF_CUDA_OK(cudaMemcpyAsync(out, c->d_ang + (size_t)(slot * 2 + side) * npx, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+    PLF_CUDA_OK(cudaMemcpy2DAsync(out, 4, c->d_rec + (size_t)(slot * 2 + side) * npx, 16, 4, npx, cudaMemcpyDeviceToHost, c->stream));
     PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
     return PLF_OK;
 }

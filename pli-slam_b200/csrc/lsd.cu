@@ -40,40 +40,25 @@ __global__ void __launch_bounds__(256) blur_image_kernel(const uint8_t* src, siz
 }
 
 __global__ void __launch_bounds__(256) lsd_upscale_kernel(PlfGeom g, const uint8_t* src, size_t srcImgStride, int sp,
-                                                          uint8_t* dst, int imgFirst) {
+                                                          uint8_t* dst, const PlfLin* linX, const PlfLin* linY,
+                                                          int imgFirst) {
     const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
     if (dx >= g.Ws || dy >= g.Hs) return;
     const int img = imgFirst + blockIdx.z;
     const uint8_t* s = src + (size_t)img * srcImgStride;
-    const double inv = 1.0 / g.lsdScale;
-    int xo, xa, yo, ya;
-    {
-        const double f = inv * (dx + 0.5) - 0.5;
-        const int i = (int)floor(f);
-        if (i >= 0 && g.W > 1) {
-            if (i < g.W - 1) { xo = i; xa = __double2int_rn((f - i) * 256.0); } else { xo = g.W - 1; xa = 0; }
-        } else { xo = 0; xa = 0; }
-    }
-    {
-        const double f = inv * (dy + 0.5) - 0.5;
-        const int i = (int)floor(f);
-        if (i >= 0 && g.H > 1) {
-            if (i < g.H - 1) { yo = i; ya = __double2int_rn((f - i) * 256.0); } else { yo = g.H - 1; ya = 0; }
-        } else { yo = 0; ya = 0; }
-    }
-    const uint8_t* r0 = s + (size_t)yo * sp;
-    const uint8_t* r1 = s + (size_t)min(yo + 1, g.H - 1) * sp;
-    const int x1 = min(xo + 1, g.W - 1);
-    const int h0 = r0[xo] * (256 - xa) + r0[x1] * xa;
-    const int h1 = r1[xo] * (256 - xa) + r1[x1] * xa;
-    dst[(size_t)img * g.Ps * g.Hs + (size_t)dy * g.Ps + dx] = (uint8_t)((h0 * (256 - ya) + h1 * ya + 32768) >> 16);
+    const PlfLin cx = linX[dx], cy = linY[dy];      // Q8 weights built on the host (a0 = 256 - a1)
+    const uint8_t* r0 = s + (size_t)cy.ofs * sp;
+    const uint8_t* r1 = s + (size_t)min(cy.ofs + 1, g.H - 1) * sp;
+    const int x1 = min(cx.ofs + 1, g.W - 1);
+    const int h0 = r0[cx.ofs] * cx.a0 + r0[x1] * cx.a1;
+    const int h1 = r1[cx.ofs] * cx.a0 + r1[x1] * cx.a1;
+    dst[(size_t)img * g.Ps * g.Hs + (size_t)dy * g.Ps + dx] = (uint8_t)((h0 * cy.a0 + h1 * cy.a1 + 32768) >> 16);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // K4b  level-line field (LSD ll_angle): 2x2 gradient, squared norm, fastAtan2 angle (degrees), cosf/sinf of the angle,
 // per-image max of the squared norm over defined pixels.
-__global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, float* ang, float4* rec, int* n2o,
-                                                       int* n2max, int imgFirst) {
+__global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, float4* rec, int* n2max, int imgFirst) {
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     const int img = imgFirst + blockIdx.z;
     int best = 0;
@@ -97,9 +82,7 @@ __global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t*
                 best = n2;
             }
         }
-        ang[o] = a;
         rec[o] = make_float4(a, c.x, c.y, __int_as_float(n2));
-        n2o[o] = n2;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -112,29 +95,13 @@ __device__ __forceinline__ double lsd_bin_coef(int n2max, int nBins) {
     return maxGrad > 0 ? (double)(nBins - 1) / maxGrad : 0.0;
 }
 
-__global__ void __launch_bounds__(256) lsd_hist_kernel(PlfGeom g, const float* ang, const int* n2, const int* n2max,
-                                                       int* hist, int imgFirst) {
-    extern __shared__ int s_hist[];
-    const int img = imgFirst + blockIdx.y;
-    for (int i = threadIdx.x; i < g.nBins; i += 256) s_hist[i] = 0;
-    __syncthreads();
-    const double coef = lsd_bin_coef(n2max[img], g.nBins);
-    const size_t base = (size_t)img * g.Ws * g.Hs;
-    const int npx = g.Ws * g.Hs;
-    for (int p = blockIdx.x * 256 + threadIdx.x; p < npx; p += gridDim.x * 256)
-        if (ang[base + p] != PLF_NOTDEF) atomicAdd(&s_hist[lsd_bin(n2[base + p], coef)], 1);
-    __syncthreads();
-    for (int i = threadIdx.x; i < g.nBins; i += 256)
-        if (s_hist[i]) atomicAdd(hist + (size_t)img * g.nBins + i, s_hist[i]);
-}
-
 // Ordered seed list: defined pixels sorted by (bin descending, raster index ascending) — a stable counting sort.
 // One 1024-thread block per image; warp w owns the w-th contiguous raster segment.  Pass 1 counts per (warp, bin) in
 // shared memory, pass 2 turns the counts into write cursors (bins descending, then warps ascending), pass 3 lets every
 // warp walk its segment again and place its pixels: lanes of one 32-pixel step that share a bin are ranked with
 // __match_any_sync, so the order inside a bin is raster order by construction and no warp waits for another.
-__global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float* ang, const int* n2, const int* n2max,
-                                                         int* seeds, int* nSeeds, int imgFirst) {
+__global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float4* rec, const int* n2max, int* seeds,
+                                                         int* nSeeds, int imgFirst) {
     extern __shared__ int s_cur[];          // [32][nBins]
     __shared__ int s_scan[32];
     __shared__ int s_carry;
@@ -150,8 +117,9 @@ __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float*
     for (int i = tid; i < 32 * nBins; i += 1024) s_cur[i] = 0;
     if (tid == 0) s_carry = 0;
     __syncthreads();
+    const float* recf = reinterpret_cast<const float*>(rec + base);       // record = (angle, cos, sin, |g|^2 bits)
     for (int p = p0 + lane; p < p1; p += 32)
-        if (ang[base + p] != PLF_NOTDEF) atomicAdd(&mine[lsd_bin(n2[base + p], coef)], 1);
+        if (recf[4 * (size_t)p] != PLF_NOTDEF) atomicAdd(&mine[lsd_bin(__float_as_int(recf[4 * (size_t)p + 3]), coef)], 1);
     __syncthreads();
     // cursors: for bins in descending order, for warps in ascending order
     for (int b0 = 0; b0 < nBins; b0 += 1024) {
@@ -189,7 +157,7 @@ __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float*
         const int p = pb + lane;
         bool def = false;
         int bin = 0;
-        if (p < p1 && ang[base + p] != PLF_NOTDEF) { def = true; bin = lsd_bin(n2[base + p], coef); }
+        if (p < p1 && recf[4 * (size_t)p] != PLF_NOTDEF) { def = true; bin = lsd_bin(__float_as_int(recf[4 * (size_t)p + 3]), coef); }
         const unsigned wm = __ballot_sync(0xffffffffu, def);
         if (def) {
             const unsigned grp = __match_any_sync(wm, bin);
@@ -682,10 +650,10 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         upStride = imgBytes;
         ++launches;
     }
-    lsd_upscale_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, imgFirst);
+    lsd_upscale_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, c->d_lin + c->linLsdX, c->d_lin + c->linLsdY, imgFirst);
     plf_mark(c, "lsd_gradient");
     cudaMemsetAsync(c->d_n2max + imgFirst, 0, nImg * sizeof(int), s);
-    lsd_grad_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_ang, c->d_rec, c->d_n2, c->d_n2max, imgFirst);
+    lsd_grad_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_rec, c->d_n2max, imgFirst);
     plf_mark(c, "lsd_order");
     {
         const size_t smem = (size_t)32 * g.nBins * sizeof(int);
@@ -694,7 +662,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
             cudaFuncSetAttribute(lsd_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             s_attr = smem;
         }
-        lsd_order_kernel<<<nImg, 1024, smem, s>>>(g, c->d_ang, c->d_n2, c->d_n2max, c->d_seeds, c->d_nSeeds, imgFirst);
+        lsd_order_kernel<<<nImg, 1024, smem, s>>>(g, c->d_rec, c->d_n2max, c->d_seeds, c->d_nSeeds, imgFirst);
     }
     plf_mark(c, "lsd_grow");
     {

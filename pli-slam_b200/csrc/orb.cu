@@ -16,7 +16,7 @@ __constant__ int c_pattern[1024] = {
 // K1a  pyramid level l from level l-1: cv::resize(INTER_LINEAR) 8U, 11-bit fixed point (src/ORBextractor.cc:1165).
 // One thread per output pixel, 32x8 tiles; the four taps come through L1/L2 (each source byte is reused by ~1.4
 // output pixels in x and y, so the level is read from HBM once).
-__global__ void __launch_bounds__(256) pyr_resize_kernel(PlfGeom g, uint8_t* pyr, int level, int imgFirst) {
+__global__ void __launch_bounds__(256) pyr_resize_kernel(PlfGeom g, uint8_t* pyr, const PlfLin* lin, int level, int imgFirst) {
     const PlfLevel& d = g.lv[level];
     const PlfLevel& s = g.lv[level - 1];
     const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
@@ -24,44 +24,28 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(PlfGeom g, uint8_t* pyr
     const int img = imgFirst + blockIdx.z;
     const uint8_t* src = pyr + (size_t)img * g.pyrBytes + s.off;
     uint8_t* dst = pyr + (size_t)img * g.pyrBytes + d.off;
-    const double scale_x = (double)s.w / d.w, scale_y = (double)s.h / d.h;
-    float fx = (float)((dx + 0.5) * scale_x - 0.5);
-    int sx = (int)floorf(fx);
-    fx = __fsub_rn(fx, (float)sx);
-    if (sx < 0) { fx = 0.f; sx = 0; }
-    if (sx >= s.w - 1) { fx = 0.f; sx = s.w - 1; }
-    float fy = (float)((dy + 0.5) * scale_y - 0.5);
-    int sy = (int)floorf(fy);
-    fy = __fsub_rn(fy, (float)sy);
-    if (sy < 0) { fy = 0.f; sy = 0; }
-    if (sy >= s.h - 1) { fy = 0.f; sy = s.h - 1; }
-    const int ax0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fx), 2048.f)), ax1 = __float2int_rn(__fmul_rn(fx, 2048.f));
-    const int ay0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fy), 2048.f)), ay1 = __float2int_rn(__fmul_rn(fy, 2048.f));
+    const PlfLin cx = lin[d.xTab + dx], cy = lin[d.yTab + dy];     // source index + 11-bit weights, built on the host
+    const int sx = cx.ofs, sy = cy.ofs;
     const int sx1 = min(sx + 1, s.w - 1), sy1 = min(sy + 1, s.h - 1);
     const uint8_t* r0 = src + (size_t)sy * s.pitch;
     const uint8_t* r1 = src + (size_t)sy1 * s.pitch;
-    const int h0 = r0[sx] * ax0 + r0[sx1] * ax1;
-    const int h1 = r1[sx] * ax0 + r1[sx1] * ax1;
-    dst[(size_t)dy * d.pitch + dx] = (uint8_t)((((ay0 * (h0 >> 4)) >> 16) + ((ay1 * (h1 >> 4)) >> 16) + 2) >> 2);
+    const int h0 = r0[sx] * cx.a0 + r0[sx1] * cx.a1;
+    const int h1 = r1[sx] * cx.a0 + r1[sx1] * cx.a1;
+    dst[(size_t)dy * d.pitch + dx] = (uint8_t)((((cy.a0 * (h0 >> 4)) >> 16) + ((cy.a1 * (h1 >> 4)) >> 16) + 2) >> 2);
 }
 
 // all pyramid levels in one launch: blockIdx.x enumerates the 32x32 tiles of every level
-__global__ void __launch_bounds__(256) blur_pyramid_kernel(PlfGeom g, const uint8_t* pyr, uint8_t* blur, int imgFirst) {
-    int t = blockIdx.x, l = 0, tx = 0;
-    for (; l < g.nLevels; ++l) {
-        tx = (g.lv[l].w + 31) >> 5;
-        int n = tx * ((g.lv[l].h + 31) >> 5);
-        if (t < n) break;
-        t -= n;
-    }
-    if (l >= g.nLevels) return;
+__global__ void __launch_bounds__(256) blur_pyramid_kernel(PlfGeom g, const uint8_t* pyr, uint8_t* blur,
+                                                           const PlfTile* tiles, int imgFirst) {
+    const PlfTile t = tiles[blockIdx.x];
     const int img = imgFirst + blockIdx.y;
+    const PlfLevel& lv = g.lv[t.level];
     BlurJob j;
-    j.src = pyr + (size_t)img * g.pyrBytes + g.lv[l].off;
-    j.dst = blur + (size_t)img * g.pyrBytes + g.lv[l].off;
-    j.w = g.lv[l].w; j.h = g.lv[l].h; j.sp = j.dp = g.lv[l].pitch;
+    j.src = pyr + (size_t)img * g.pyrBytes + lv.off;
+    j.dst = blur + (size_t)img * g.pyrBytes + lv.off;
+    j.w = lv.w; j.h = lv.h; j.sp = j.dp = lv.pitch;
     const int taps[7] = {18, 34, 48, 56, 48, 34, 18};
-    blur_tile<7>(j, taps, (t % tx) * 32, (t / tx) * 32);
+    blur_tile<7>(j, taps, t.x0, t.y0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -113,27 +97,25 @@ __device__ __forceinline__ int fast_score16(const int* d, bool bright) {
 #define FS_TH 8
 #define FS_IW (FS_TW + 6)
 #define FS_IH (FS_TH + 6)
-__global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_t* pyr, uint8_t* score, int imgFirst) {
+__global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_t* pyr, uint8_t* score,
+                                                         const PlfTile* tiles, int imgFirst) {
     __shared__ uint8_t s_in[FS_IH][FS_IW + 2];
-    // locate (level, tile): tiles cover [19, w-19) x [19, h-19), the union of all cell detection areas
-    int t = blockIdx.x, l = 0, tx = 0;
-    for (; l < g.nLevels; ++l) {
-        tx = (g.lv[l].w - 2 * PLF_EDGE + FS_TW - 1) / FS_TW;
-        const int n = tx * ((g.lv[l].h - 2 * PLF_EDGE + FS_TH - 1) / FS_TH);
-        if (t < n) break;
-        t -= n;
-    }
-    if (l >= g.nLevels) return;
-    const PlfLevel& lv = g.lv[l];
+    // tiles cover [19, w-19) x [19, h-19) of every level: the union of all cell detection areas
+    const PlfTile t = tiles[blockIdx.x];
+    const PlfLevel& lv = g.lv[t.level];
     const int img = imgFirst + blockIdx.y;
     const uint8_t* src = pyr + (size_t)img * g.pyrBytes + lv.off;
     uint8_t* dst = score + (size_t)img * g.pyrBytes + lv.off;
-    const int x0 = PLF_EDGE + (t % tx) * FS_TW, y0 = PLF_EDGE + (t / tx) * FS_TH;
+    const int x0 = t.x0, y0 = t.y0;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int i = tid; i < FS_IW * FS_IH; i += 256) {
-        const int iy = i / FS_IW, ix = i - iy * FS_IW;
-        const int gx = min(x0 - 3 + ix, lv.w - 1), gy = min(y0 - 3 + iy, lv.h - 1);
-        s_in[iy][ix] = src[(size_t)gy * lv.pitch + gx];
+    {
+        const int gx0 = min(x0 - 3 + (int)threadIdx.x, lv.w - 1), gx1 = min(x0 + 29 + (int)threadIdx.x, lv.w - 1);
+#pragma unroll
+        for (int iy = threadIdx.y; iy < FS_IH; iy += 8) {
+            const uint8_t* row = src + (size_t)min(y0 - 3 + iy, lv.h - 1) * lv.pitch;
+            s_in[iy][threadIdx.x] = row[gx0];
+            if (threadIdx.x < 6) s_in[iy][32 + threadIdx.x] = row[gx1];
+        }
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
@@ -202,15 +184,16 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(PlfGeom g, const uint8_
         return;
     }
     const int n = aw * ah;
+    const unsigned magic = (unsigned)c.magic;      // i / aw == (i * magic) >> 20 for every i < n (checked at plf_create)
     for (int i = tid; i < n; i += 128) {
-        const int y = i / aw, x = i - y * aw;
+        const int y = (int)(((unsigned)i * magic) >> 20), x = i - y * aw;
         s_sc[i] = src[(size_t)(c.y0 + 3 + y) * lv.pitch + c.x0 + 3 + x];
     }
     __syncthreads();
     const int iniTh = g.iniTh, minTh = g.minTh;
     bool anyIni = false;
     for (int i = tid; i < n; i += 128) {
-        const int y = i / aw, x = i - y * aw;
+        const int y = (int)(((unsigned)i * magic) >> 20), x = i - y * aw;
         const int s = s_sc[i];
         bool keep = s > 0;
         if (keep) {
@@ -254,7 +237,7 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(PlfGeom g, const uint8_
     for (int i = i0; i < i1; ++i) {
         const int s = s_sc[i];
         if (s_keep[i] && s >= th) {
-            const int y = i / aw, x = i - y * aw;
+            const int y = (int)(((unsigned)i * magic) >> 20), x = i - y * aw;
             if (pos < c.cap) out[pos] = (uint32_t)(relx + x) | ((uint32_t)(rely + y) << 12) | ((uint32_t)s << 24);
             ++pos;
         }
@@ -553,8 +536,8 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(PlfGeom g, const uint8
                                                           plf_keypoint* kpTmp, uint8_t* descTmp, int* nKp,
                                                           int imgFirst) {
     const int img = imgFirst + blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int gk = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int gk = blockIdx.x * 8 + wl;
     const int* ln = lvlN + (size_t)img * g.nLevels;
     int level = 0, base = 0, total = 0;
     bool found = false;
@@ -568,20 +551,20 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(PlfGeom g, const uint8
     const PlfLevel& lv = g.lv[level];
     const uint32_t p = lvlKp[(size_t)img * g.kpLevelCapTotal + lv.kpOff + (gk - base)];
     const int x = (int)(p & 0xFFF) + PLF_MINB, y = (int)((p >> 12) & 0xFFF) + PLF_MINB;
-    const uint8_t* im = pyr + (size_t)img * g.pyrBytes + lv.off;
-    // moments: lane v+15 owns row v
+    const uint8_t* im = pyr + (size_t)img * g.pyrBytes + lv.off + (size_t)y * lv.pitch + x;
+    const uint8_t* bl = blur + (size_t)img * g.pyrBytes + lv.off + (size_t)y * lv.pitch + x;
+    // moments: lane = column u of the 31x31 patch, loop over rows v (integer sums -> order-free, exact)
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int v = lane - 15;
-        const int d = g.umax[v < 0 ? -v : v];
-        const uint8_t* row = im + (size_t)(y + v) * lv.pitch + x;
-        int s = 0;
-        for (int u = -d; u <= d; ++u) {
-            const int val = row[u];
-            m10 += u * val;
-            s += val;
+    {
+        const int u = lane - 15, au = u < 0 ? -u : u;
+        if (lane < 31) {
+#pragma unroll
+            for (int v = -15; v <= 15; ++v) {
+                const int val = (au <= g.umax[v < 0 ? -v : v]) ? (int)im[v * lv.pitch + u] : 0;
+                m10 += u * val;
+                m01 += v * val;
+            }
         }
-        m01 = v * s;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -592,9 +575,8 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(PlfGeom g, const uint8
     // descriptor: lane = byte
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     const float ar = __fmul_rn(angle, factorPI);
-    // glibc cosf/sinf are correctly rounded for all practical purposes; reproduce by rounding the double result
+    // cosf/sinf taken as correctly rounded: the double result rounded to float (declared oracle rule)
     const float a = (float)cos((double)ar), b = (float)sin((double)ar);
-    const uint8_t* bl = blur + (size_t)img * g.pyrBytes + lv.off + (size_t)y * lv.pitch + x;
     const int* pat = c_pattern + lane * 32;
     int val = 0;
 #pragma unroll
@@ -682,20 +664,13 @@ int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1) {
     plf_mark(c, "orb_pyramid");
     for (int l = 1; l < g.nLevels; ++l) {
         dim3 grid((g.lv[l].w + 31) / 32, (g.lv[l].h + 7) / 8, nImg);
-        pyr_resize_kernel<<<grid, dim3(32, 8), 0, s>>>(g, c->d_pyr, l, imgFirst);
+        pyr_resize_kernel<<<grid, dim3(32, 8), 0, s>>>(g, c->d_pyr, c->d_lin, l, imgFirst);
         ++launches;
     }
-    int tiles = 0;
-    for (int l = 0; l < g.nLevels; ++l) tiles += ((g.lv[l].w + 31) / 32) * ((g.lv[l].h + 31) / 32);
     plf_mark(c, "orb_blur");
-    blur_pyramid_kernel<<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(g, c->d_pyr, c->d_blur, imgFirst);
+    blur_pyramid_kernel<<<dim3(c->nTilesBlur, nImg), dim3(32, 8), 0, s>>>(g, c->d_pyr, c->d_blur, c->d_tilesBlur, imgFirst);
     plf_mark(c, "orb_fast");
-    {
-        int st = 0;
-        for (int l = 0; l < g.nLevels; ++l)
-            st += ((g.lv[l].w - 2 * PLF_EDGE + FS_TW - 1) / FS_TW) * ((g.lv[l].h - 2 * PLF_EDGE + FS_TH - 1) / FS_TH);
-        fast_score_kernel<<<dim3(st, nImg), dim3(32, 8), 0, s>>>(g, c->d_pyr, c->d_score, imgFirst);
-    }
+    fast_score_kernel<<<dim3(c->nTilesFast, nImg), dim3(32, 8), 0, s>>>(g, c->d_pyr, c->d_score, c->d_tilesFast, imgFirst);
     fast_cells_kernel<<<dim3(g.nCellsTotal, nImg), 128, 0, s>>>(g, c->d_score, c->d_cells, c->d_cellCount, c->d_cand,
                                                                imgFirst);
     int maxQ = 0;

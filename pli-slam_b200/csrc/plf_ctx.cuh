@@ -26,13 +26,18 @@ struct PlfLevel {
     int kpOff, kpCap;     // slice of the per-image per-level keypoint buffer
     float scale, invScale;
     int scaledPatch;      // (int)(31*scale)
+    int xTab, yTab;       // offsets into the bilinear coefficient table (levels >= 1)
 };
+
+struct PlfTile { short level, x0, y0, pad; };   // one thread-block tile of a per-pyramid-level kernel
+struct PlfLin { unsigned short ofs; short a0, a1, pad; };   // source index and the two fixed-point weights of one output coordinate
 
 struct PlfCell {          // one FAST window, src/ORBextractor.cc:787-804
     short level;
     short x0, y0, x1, y1; // window [x0,x1) x [y0,y1) in level coordinates
     int outBase;          // first slot in the per-image candidate buffer
     int cap;
+    int magic;            // ceil(2^20 / detection-area width): division-free raster index -> (x, y)
 };
 
 struct PlfGeom {          // passed by value to kernels (fits the 4 KB parameter space)
@@ -66,6 +71,11 @@ struct plf_ctx {
     uint8_t* d_blur = nullptr;       // [nImg][pyrBytes]
     uint8_t* d_score = nullptr;      // [nImg][pyrBytes] FAST corner score map (0 below minTh), pyramid layout
     PlfCell* d_cells = nullptr;      // [nCellsTotal]
+    PlfTile* d_tilesBlur = nullptr;  // 32x32 tiles of every pyramid level
+    PlfTile* d_tilesFast = nullptr;  // 32x8 tiles of the FAST detection area of every level
+    int nTilesBlur = 0, nTilesFast = 0;
+    PlfLin* d_lin = nullptr;         // bilinear tables: pyramid levels (11-bit weights) then the LSD upscale (Q8)
+    int linLsdX = 0, linLsdY = 0;    // offsets of the LSD upscale tables inside d_lin
     int* d_cellCount = nullptr;      // [nImg][nCellsTotal]
     uint32_t* d_cand = nullptr;      // [nImg][candCapTotal] packed x | y<<12 | score<<24 (relative to min border)
     uint32_t* d_scratch = nullptr;   // [nImg][2][candCapTotal] quadtree ping-pong point buffers
@@ -85,11 +95,8 @@ struct plf_ctx {
     // LSD / LBD
     uint8_t* d_lsdBlur = nullptr;    // [nImg][H][pitch0]
     uint8_t* d_lsdU = nullptr;       // [nImg][Hs][Ps]
-    float* d_ang = nullptr;          // [nImg][Hs*Ws] degrees, NOTDEF
     float4* d_rec = nullptr;         // [nImg][Hs*Ws] per-pixel record of the region grower: angle, cosf, sinf, |g|^2 (as int bits)
-    int* d_n2 = nullptr;             // [nImg][Hs*Ws] gx^2+gy^2
     int* d_n2max = nullptr;          // [nImg]
-    int* d_hist = nullptr;           // [nImg][nBins]
     int* d_seeds = nullptr;          // [nImg][seedCap] seed pixels (packed y<<16|x) in processing order
     int* d_nSeeds = nullptr;         // [nImg]
     uint32_t* d_used = nullptr;      // [nImg][ceil(Hs*Ws/32)] used bitmap of the region grower

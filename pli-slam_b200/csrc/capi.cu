@@ -157,6 +157,10 @@ static int build_geometry(plf_ctx* c, std::vector<PlfCell>& cells) {
     g.prec = kPi * p.lsd_ang_th / 180;
     g.rho = p.lsd_quant / std::sin(g.prec);
     g.nBins = p.lsd_n_bins;
+    g.n2Thresh = 0;
+    for (int n2 = 0; n2 <= 2 * 510 * 510; ++n2) {      // exact integer image of LSD's `norm <= threshold` test
+        if (std::sqrt((double)n2 / 4.0) <= g.rho) g.n2Thresh = n2; else break;
+    }
     if (p.lsd_scale != 1) {
         const double sigma = (p.lsd_scale < 1) ? (p.lsd_sigma_scale / p.lsd_scale) : p.lsd_sigma_scale;
         const unsigned h = (unsigned)std::ceil(sigma * std::sqrt(2 * 3.0 * std::log(10.0)));
@@ -204,7 +208,7 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
     c->nImgMax = (int)nImg;
     PLF_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t npx = (size_t)g.Ws * g.Hs;
-    PLF_CUDA_OK(dalloc(&c->d_pyr, nImg * g.pyrBytes));
+    PLF_CUDA_OK(dalloc(&c->d_pyr, nImg * g.pyrBytes + 256));   // +256: the FAST tile loader reads whole 32-bit words
     PLF_CUDA_OK(dalloc(&c->d_blur, nImg * g.pyrBytes));
     PLF_CUDA_OK(dalloc(&c->d_score, nImg * g.pyrBytes));
     PLF_CUDA_OK(dalloc(&c->d_cells, cells.size()));

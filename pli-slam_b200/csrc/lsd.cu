@@ -59,34 +59,52 @@ __global__ void __launch_bounds__(256) lsd_upscale_kernel(PlfGeom g, const uint8
 // K4b  level-line field (LSD ll_angle): 2x2 gradient, squared norm, fastAtan2 angle (degrees), cosf/sinf of the angle,
 // per-image max of the squared norm over defined pixels.
 __global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, float4* rec, int* n2max, int imgFirst) {
+    // Two phases per 32x8 tile: (1) every thread: 2x2 gradient and |g|^2; a pixel is defined iff |g|^2 > n2Thresh, the
+    // integer image of LSD's "norm > rho" test (exact: host-searched with the same IEEE sqrt).  Undefined pixels are
+    // written at once; defined ones are queued.  (2) the queue is processed densely, one defined pixel per thread, so
+    // the expensive part (fastAtan2 + double cos/sin) costs in proportion to the defined pixels, not to the warps that
+    // happen to contain one.
+    __shared__ int s_cnt;
+    __shared__ int s_q[256];          // tid | (gx+1024)<<8 | (gy+1024)<<20
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     const int img = imgFirst + blockIdx.z;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    const size_t base = (size_t)img * g.Ws * g.Hs;
     int best = 0;
     if (x < g.Ws && y < g.Hs) {
-        const size_t o = (size_t)img * g.Ws * g.Hs + (size_t)y * g.Ws + x;
-        float a = PLF_NOTDEF;
-        float2 c = make_float2(0.f, 0.f);
-        int n2 = 0;
+        int n2 = 0, gx = 0, gy = 0;
         if (x < g.Ws - 1 && y < g.Hs - 1) {
             const uint8_t* r0 = U + (size_t)img * g.Ps * g.Hs + (size_t)y * g.Ps;
             const uint8_t* r1 = r0 + g.Ps;
             const int DA = (int)r1[x + 1] - (int)r0[x], BC = (int)r0[x + 1] - (int)r1[x];
-            const int gx = DA + BC, gy = DA - BC;
+            gx = DA + BC;
+            gy = DA - BC;
             n2 = gx * gx + gy * gy;
-            const double norm = sqrt((double)n2 / 4.0);
-            if (!(norm <= g.rho)) {
-                a = fast_atan2_deg((float)gx, (float)-gy);
-                const float af = (float)((double)a * kDegToRad);
-                c.x = (float)cos((double)af);   // == glibc cosf(af) up to double rounding
-                c.y = (float)sin((double)af);
-                best = n2;
-            }
         }
-        rec[o] = make_float4(a, c.x, c.y, __int_as_float(n2));
+        if (n2 > g.n2Thresh) {
+            s_q[atomicAdd(&s_cnt, 1)] = tid | ((gx + 1024) << 8) | ((gy + 1024) << 20);
+            best = n2;
+        } else {
+            rec[base + (size_t)y * g.Ws + x] = make_float4(PLF_NOTDEF, 0.f, 0.f, __int_as_float(n2));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
     if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(n2max + img, best);
+    __syncthreads();
+    if (tid < s_cnt) {
+        const int e = s_q[tid];
+        const int t2 = e & 0xFF, gx = ((e >> 8) & 0xFFF) - 1024, gy = ((e >> 20) & 0xFFF) - 1024;
+        const int px = blockIdx.x * 32 + (t2 & 31), py = blockIdx.y * 8 + (t2 >> 5);
+        const float a = fast_atan2_deg((float)gx, (float)-gy);
+        const float af = (float)((double)a * kDegToRad);
+        // cosf/sinf taken as correctly rounded (double result rounded to float), the declared oracle rule
+        double sn, cs;
+        sincos((double)af, &sn, &cs);
+        rec[base + (size_t)py * g.Ws + px] = make_float4(a, (float)cs, (float)sn, __int_as_float(gx * gx + gy * gy));
+    }
 }
 
 __device__ __forceinline__ int lsd_bin(int n2, double binCoef) { return (int)(sqrt((double)n2 / 4.0) * binCoef); }
@@ -186,10 +204,18 @@ __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float4
 //    issued together and the acceptance chain is resolved with ballots, one fastAtan2 per accepted pixel.
 #define GROW_RING 512
 
-__device__ __forceinline__ double seq_sum_warp(double v, unsigned cnt, double acc) {
-    // acc += v[0]; acc += v[1]; ... in lane order (sequential rounding, like the scalar loop)
-    for (unsigned j = 0; j < cnt; ++j) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, v, j));
-    return acc;
+// Sequential (scalar-loop order) accumulation of three quantities over the pixels of a region: the 32 lanes write
+// their three products to shared memory, then lanes 0..2 each own one accumulator and add the 32 values in order.
+// Same rounding sequence as the scalar loop, a third of the instructions of a shuffle chain.
+__device__ __forceinline__ void seq_sum3(double (*buf)[33], double a, double b, double c, unsigned cnt, int lane,
+                                         double& acc) {
+    buf[0][lane] = a;
+    buf[1][lane] = b;
+    buf[2][lane] = c;
+    __syncwarp();
+    if (lane < 3)
+        for (unsigned j = 0; j < cnt; ++j) acc = __dadd_rn(acc, buf[lane][j]);
+    __syncwarp();
 }
 
 struct GrowState {
@@ -233,6 +259,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
                                                       uint32_t* usedAll, int* reg, float* segs, int* nSegsOut, int* err,
                                                       int nWords, int imgFirst) {
     __shared__ int ring[GROW_RING];
+    __shared__ double s_sum[3][33];
     const int img = imgFirst + blockIdx.x, lane = threadIdx.x;
     const int W = g.Ws, H = g.Hs;
     const size_t base = (size_t)img * W * H;
@@ -263,8 +290,12 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
             st.n = 1;
             if (lane == 0) { ring[0] = pk0; R[0] = pk0; atomicOr(used + (p >> 5), 1u << (p & 31)); }
             st.regAngle = (double)REC[p].x * kDegToRad;
-            st.sumdx = (float)cos(st.regAngle);
-            st.sumdy = (float)sin(st.regAngle);
+            {
+                double sn, cs;
+                sincos(st.regAngle, &sn, &cs);
+                st.sumdx = (float)cs;
+                st.sumdy = (float)sn;
+            }
             __syncwarp();
             int i = 0;
             while (i < st.n) {
@@ -307,7 +338,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
             const double regAngle = st.regAngle;
             if (n < g.minRegSize) continue;
             // ---- region2rect (sequential summation order reproduced with lane-ordered adds) -------------------------
-            double sx = 0, sy = 0, sw = 0;
+            double acc3 = 0;      // lane 0: sum x*w, lane 1: sum y*w, lane 2: sum w
             for (int i0 = 0; i0 < n; i0 += 32) {
                 const unsigned cnt = min(32, n - i0);
                 double wv = 0, xw = 0, yw = 0;
@@ -318,12 +349,11 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
                     xw = __dmul_rn((double)rx, wv);
                     yw = __dmul_rn((double)ry, wv);
                 }
-                sx = seq_sum_warp(xw, cnt, sx);
-                sy = seq_sum_warp(yw, cnt, sy);
-                sw = seq_sum_warp(wv, cnt, sw);
+                seq_sum3(s_sum, xw, yw, wv, cnt, lane, acc3);
             }
-            const double cxm = sx / sw, cym = sy / sw;
-            double Ixx = 0, Iyy = 0, Ixy = 0;
+            const double sw = __shfl_sync(0xffffffffu, acc3, 2);
+            const double cxm = __shfl_sync(0xffffffffu, acc3, 0) / sw, cym = __shfl_sync(0xffffffffu, acc3, 1) / sw;
+            acc3 = 0;             // lane 0: Ixx, lane 1: Iyy, lane 2: Ixy
             for (int i0 = 0; i0 < n; i0 += 32) {
                 const unsigned cnt = min(32, n - i0);
                 double vxx = 0, vyy = 0, vxy = 0;
@@ -336,10 +366,10 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
                     vyy = __dmul_rn(__dmul_rn(dx, dx), wv);
                     vxy = -__dmul_rn(__dmul_rn(dx, dy), wv);
                 }
-                Ixx = seq_sum_warp(vxx, cnt, Ixx);
-                Iyy = seq_sum_warp(vyy, cnt, Iyy);
-                Ixy = seq_sum_warp(vxy, cnt, Ixy);
+                seq_sum3(s_sum, vxx, vyy, vxy, cnt, lane, acc3);
             }
+            const double Ixx = __shfl_sync(0xffffffffu, acc3, 0), Iyy = __shfl_sync(0xffffffffu, acc3, 1);
+            const double Ixy = __shfl_sync(0xffffffffu, acc3, 2);
             const double dI = __dsub_rn(Ixx, Iyy);
             const double lambda = __dmul_rn(0.5, __dsub_rn(__dadd_rn(Ixx, Iyy),
                                                            sqrt(__dadd_rn(__dmul_rn(dI, dI), __dmul_rn(__dmul_rn(4.0, Ixy), Ixy)))));
@@ -353,7 +383,8 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
                 if (diff < 0) diff = -diff;
                 if (diff > prec) theta += kPi;
             }
-            const double dxr = cos(theta), dyr = sin(theta);
+            double dxr, dyr;
+            sincos(theta, &dyr, &dxr);
             double lmin = 0, lmax = 0;
             for (int i0 = lane; i0 < n; i0 += 32) {
                 const int rp = R[i0];

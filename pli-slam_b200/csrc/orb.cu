@@ -99,7 +99,7 @@ __device__ __forceinline__ int fast_score16(const int* d, bool bright) {
 #define FS_IH (FS_TH + 6)
 __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_t* pyr, uint8_t* score,
                                                          const PlfTile* tiles, int imgFirst) {
-    __shared__ uint8_t s_in[FS_IH][FS_IW + 2];
+    __shared__ __align__(16) uint8_t s_in[FS_IH][FS_IW + 2];
     // tiles cover [19, w-19) x [19, h-19) of every level: the union of all cell detection areas
     const PlfTile t = tiles[blockIdx.x];
     const PlfLevel& lv = g.lv[t.level];
@@ -108,14 +108,12 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
     uint8_t* dst = score + (size_t)img * g.pyrBytes + lv.off;
     const int x0 = t.x0, y0 = t.y0;
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    {
-        const int gx0 = min(x0 - 3 + (int)threadIdx.x, lv.w - 1), gx1 = min(x0 + 29 + (int)threadIdx.x, lv.w - 1);
-#pragma unroll
-        for (int iy = threadIdx.y; iy < FS_IH; iy += 8) {
-            const uint8_t* row = src + (size_t)min(y0 - 3 + iy, lv.h - 1) * lv.pitch;
-            s_in[iy][threadIdx.x] = row[gx0];
-            if (threadIdx.x < 6) s_in[iy][32 + threadIdx.x] = row[gx1];
-        }
+    // the window starts at x0-3 = 16 (mod 32) and level rows are 64-byte aligned: 10 aligned 32-bit words per row
+    // (the row pitch is padded to 64 B, so the last word never leaves the allocation of the pyramid block)
+    if (tid < FS_IH * 10) {
+        const int iy = tid / 10, wx = tid - iy * 10;
+        const uint8_t* row = src + (size_t)min(y0 - 3 + iy, lv.h - 1) * lv.pitch + (x0 - 3);
+        *reinterpret_cast<uint32_t*>(&s_in[iy][wx * 4]) = *reinterpret_cast<const uint32_t*>(row + wx * 4);
     }
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
@@ -124,12 +122,14 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
     const uint8_t* p = &s_in[threadIdx.y + 3][threadIdx.x + 3];
     const int v = *p;
     const int th = g.minTh;
-    // high-speed test: every 9-arc contains one pixel of each opposite pair {k, k+8}
+    // high-speed test: every 9-arc contains one pixel of each opposite pair {k, k+8}; most warps leave after one pair
     auto cls = [&](int off) { const int d = v - (int)p[off]; return (d > th ? 1 : 0) | (d < -th ? 2 : 0); };
-    int m = cls(3 * ST) | cls(-3 * ST);
-    m &= cls(3) | cls(-3);
-    m &= cls(2 * ST + 2) | cls(-2 * ST - 2);
-    m &= cls(-2 * ST + 2) | cls(2 * ST - 2);
+    int m = inside ? (cls(3 * ST) | cls(-3 * ST)) : 0;
+    if (__any_sync(0xffffffffu, m != 0)) {
+        m &= cls(3) | cls(-3);
+        m &= cls(2 * ST + 2) | cls(-2 * ST - 2);
+        m &= cls(-2 * ST + 2) | cls(2 * ST - 2);
+    }
     const int offs[16] = {3 * ST,  3 * ST + 1,  2 * ST + 2,  ST + 3,  3,  -ST + 3, -2 * ST + 2, -3 * ST + 1,
                           -3 * ST, -3 * ST - 1, -2 * ST - 2, -ST - 3, -3, ST - 3,  2 * ST - 2,  3 * ST - 1};
     // full 16-pixel test at minTh for the survivors; corners are queued so that the (expensive) exact score is computed

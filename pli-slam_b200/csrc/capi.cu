@@ -327,7 +327,7 @@ PLF_API int plf_destroy(plf_ctx* c) {
                     c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_rec, c->d_n2max, c->d_seeds,
                     c->d_nSeeds, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
                     c->d_sobel, c->d_lbd, c->d_ldesc, c->d_rowMask, c->d_dirR, c->d_dmat, c->d_m21, c->d_m12, c->d_disp,
-                    c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2};
+                    c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -606,11 +606,19 @@ PLF_API int plf_batch_upload(plf_ctx* c, const uint8_t* left, const uint8_t* rig
     const PlfGeom& g = c->g;
     c->nMarks = 0;
     plf_mark(c, "h2d");
-    // images of one side are strided by 2*pyrBytes on the device: one 2-D copy per (side, frame)
-    for (int b = 0; b < batch; ++b) {
-        PLF_CUDA_OK(cudaMemcpy2DAsync(c->d_pyr + (size_t)(2 * b) * g.pyrBytes + g.lv[0].off, g.lv[0].pitch, left + (size_t)b * g.H * stride, stride, g.W, g.H, cudaMemcpyHostToDevice, c->stream));
-        PLF_CUDA_OK(cudaMemcpy2DAsync(c->d_pyr + (size_t)(2 * b + 1) * g.pyrBytes + g.lv[0].off, g.lv[0].pitch, right + (size_t)b * g.H * stride, stride, g.W, g.H, cudaMemcpyHostToDevice, c->stream));
+    // one bulk H2D copy per side into a staging buffer, then a device-side scatter into level 0 of every pyramid block
+    // (2 DMA transfers per call instead of 2*batch strided ones)
+    const size_t sideBytes = (size_t)batch * g.H * stride;
+    if (c->stageCap < 2 * sideBytes) {
+        if (c->d_stage) cudaFree(c->d_stage);
+        c->d_stage = nullptr;
+        c->stageCap = 0;
+        PLF_CUDA_OK(cudaMalloc((void**)&c->d_stage, 2 * (size_t)c->p.max_batch * g.H * stride));
+        c->stageCap = 2 * (size_t)c->p.max_batch * g.H * stride;
     }
+    PLF_CUDA_OK(cudaMemcpyAsync(c->d_stage, left, sideBytes, cudaMemcpyHostToDevice, c->stream));
+    PLF_CUDA_OK(cudaMemcpyAsync(c->d_stage + sideBytes, right, sideBytes, cudaMemcpyHostToDevice, c->stream));
+    plf_launch_unpack(c, c->d_stage, sideBytes, stride, batch);
     c->batchResident = batch;
     return PLF_OK;
 }

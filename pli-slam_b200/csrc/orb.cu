@@ -657,6 +657,30 @@ __global__ void __launch_bounds__(1024) place_rows_kernel(PlfGeom g, const plf_k
 
 }  // namespace
 
+namespace {
+// staging buffer [side][frame][H][stride] -> level 0 of the pyramid block of image frame*2+side (16-byte vectors when
+// the geometry allows it)
+__global__ void __launch_bounds__(64) unpack_kernel(PlfGeom g, const uint8_t* stage, size_t sideBytes, int stride,
+                                                     uint8_t* pyr) {
+    const int img = blockIdx.z, frame = img >> 1, side = img & 1;
+    const int y = blockIdx.y;
+    const uint8_t* src = stage + side * sideBytes + ((size_t)frame * g.H + y) * stride;
+    uint8_t* dst = pyr + (size_t)img * g.pyrBytes + g.lv[0].off + (size_t)y * g.lv[0].pitch;
+    if ((stride & 15) == 0 && (g.W & 15) == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        for (int i = threadIdx.x; i < g.W / 16; i += 64) d4[i] = s4[i];
+    } else {
+        for (int i = threadIdx.x; i < g.W; i += 64) dst[i] = src[i];
+    }
+}
+}  // namespace
+
+int plf_launch_unpack(plf_ctx* c, const uint8_t* stage, size_t sideBytes, int stride, int batch) {
+    unpack_kernel<<<dim3(1, c->g.H, 2 * batch), 64, 0, c->stream>>>(c->g, stage, sideBytes, stride, c->d_pyr);
+    return 1;
+}
+
 int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1) {
     const PlfGeom& g = c->g;
     cudaStream_t s = c->stream;

@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per camera stream per call (BASELINE config C2)")
     ap.add_argument("--streams", type=int, default=16, help="independent camera streams served by one context")
-    ap.add_argument("--contexts", type=int, default=2, help="calls kept in flight per GPU (one CUDA stream each)")
+    ap.add_argument("--contexts", type=int, default=3, help="calls kept in flight per GPU (one CUDA stream each)")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic pairs generated per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -314,6 +314,13 @@ def main():
     grow_ms = stage_acc.get("lsd_grow", 0.0)
     achieved = (GROW_BYTES_PER_IMAGE * 2 * B / (grow_ms * 1e-3) / 1e9) if grow_ms > 0 else 0.0
     h2d, d2h = f0.io_bytes()
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of one lsd_grow_kernel launch (ncu --set full, profiles/)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_lsd_grow_traffic.json")))
+        if prof.get("images_per_launch") == 2 * B:
+            traffic = prof["dram_bytes_per_launch"]
+    except Exception:
+        pass
     if rank == 0:
         line = {
             "metric": "stereo_frames_per_sec", "value": value, "unit": "stereo pairs/s", "n_gpus": world,
@@ -330,7 +337,7 @@ def main():
             "gpu_launches": launches,
             "ms_per_stage": {k: round(v, 4) for k, v in stage_acc.items()},
             "roofline": {"bound": "hbm", "kernel": "lsd_grow_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "algorithmic_bytes_per_launch": GROW_BYTES_PER_IMAGE * 2 * B,
                          "whole_path_frac": BYTES_PER_PAIR * value / world / (peak * 1e9)},

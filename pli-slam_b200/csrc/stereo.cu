@@ -13,11 +13,6 @@ __global__ void __launch_bounds__(256) stereo_points_kernel(PlfGeom g, const uin
                                                             const uint8_t* desc, const int* nKp, float* uRight,
                                                             float* depth, int* sadOut, float mbf, float fx,
                                                             int slotFirst) {
-    // per-level scale in shared memory: indexed by each candidate's octave (lane-varying), which the constant bank of
-    // the kernel parameters would serialise
-    __shared__ float s_scale[PLF_MAX_LEVELS];
-    if (threadIdx.x < PLF_MAX_LEVELS) s_scale[threadIdx.x] = g.lv[threadIdx.x].scale;
-    __syncthreads();
     const int slot = slotFirst + blockIdx.y;
     const int imgL = slot * 2, imgR = slot * 2 + 1;
     const int lane = threadIdx.x & 31;
@@ -44,7 +39,7 @@ __global__ void __launch_bounds__(256) stereo_points_kernel(PlfGeom g, const uin
     const int levelL = kpL.octave;
     for (int iR = lane; iR < Nr; iR += 32) {
         const plf_keypoint k = kR[iR];
-        const float r = __fmul_rn(2.0f, s_scale[k.octave]);
+        const float r = __fmul_rn(2.0f, g.lv[k.octave].scale);
         const int maxr = (int)ceilf(__fadd_rn(k.y, r)), minr = (int)floorf(__fsub_rn(k.y, r));
         if (row < minr || row > maxr) continue;
         if (k.octave < levelL - 1 || k.octave > levelL + 1) continue;

@@ -85,7 +85,7 @@ typedef struct plf_params {
     /* Lineextractor ctor, include/LineExtractor.h:45-47 */
     int32_t has_lines;            /* Config::hasLines()                                                    */
     int32_t lsd_nfeatures;        /* 500 in EuRoC.yaml:156 (300 = Config default); 0 keeps all             */
-    int32_t lsd_refine;           /* 0 (only 0 is built this round)                                        */
+    int32_t lsd_refine;           /* 0 none (EuRoC.yaml), 1 standard; 2 (advanced, NFA) -> PLF_ERR_UNSUPPORTED    */
     int32_t lsd_n_bins;           /* 1024 */
     double  min_line_length;      /* 0.025 (relative to min(W,H))                                          */
     double  lsd_scale;            /* 1.2  */

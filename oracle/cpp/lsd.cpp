@@ -146,30 +146,101 @@ struct Lsd {
         return theta;
     }
 
-    // region2rect: returns endpoints (before the +0.5 shift)
-    void region2rect(const std::vector<RegPt>& reg, double reg_angle, double prec, double out[4]) const {
+    struct Rect { double x1, y1, x2, y2, width, x, y, theta, dx, dy, prec, p; };
+
+    // region2rect (endpoints before the +0.5 shift)
+    void region2rect(const std::vector<RegPt>& reg, double reg_angle, double prec, double p, Rect& rec) const {
         double x = 0, y = 0, sum = 0;
-        for (const RegPt& p : reg) {
-            const double w = modgrad[(size_t)p.y * W + p.x];
-            x += (double)p.x * w;
-            y += (double)p.y * w;
+        for (const RegPt& q : reg) {
+            const double w = modgrad[(size_t)q.y * W + q.x];
+            x += (double)q.x * w;
+            y += (double)q.y * w;
             sum += w;
         }
         x /= sum;
         y /= sum;
         double theta = get_theta(reg, x, y, reg_angle, prec);
         double dx = std::cos(theta), dy = std::sin(theta);
-        double l_min = 0, l_max = 0;
-        for (const RegPt& p : reg) {
-            double rdx = (double)p.x - x, rdy = (double)p.y - y;
+        double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
+        for (const RegPt& q : reg) {
+            double rdx = (double)q.x - x, rdy = (double)q.y - y;
             double l = rdx * dx + rdy * dy;
+            double w = -rdx * dy + rdy * dx;
             if (l > l_max) l_max = l;
             else if (l < l_min) l_min = l;
+            if (w > w_max) w_max = w;
+            else if (w < w_min) w_min = w;
         }
-        out[0] = x + l_min * dx;
-        out[1] = y + l_min * dy;
-        out[2] = x + l_max * dx;
-        out[3] = y + l_max * dy;
+        rec.x1 = x + l_min * dx;
+        rec.y1 = y + l_min * dy;
+        rec.x2 = x + l_max * dx;
+        rec.y2 = y + l_max * dy;
+        rec.width = w_max - w_min;
+        rec.x = x; rec.y = y; rec.theta = theta; rec.dx = dx; rec.dy = dy; rec.prec = prec; rec.p = p;
+        if (rec.width < 1.0) rec.width = 1.0;
+    }
+
+    static double dist(double x1, double y1, double x2, double y2) {
+        return std::sqrt((x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1));
+    }
+    static double dist_sq(double x1, double y1, double x2, double y2) { return (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1); }
+    static double angle_diff_signed(double a, double b) {
+        double diff = a - b;
+        while (diff <= -kPi) diff += 2 * kPi;
+        while (diff > kPi) diff -= 2 * kPi;
+        return diff;
+    }
+
+    // LSD reduce_region_radius (refine >= 1)
+    bool reduce_region_radius(std::vector<RegPt>& reg, double reg_angle, double prec, double p, Rect& rec, double density,
+                              double density_th) {
+        double xc = (double)reg[0].x, yc = (double)reg[0].y;
+        double radSq1 = dist_sq(xc, yc, rec.x1, rec.y1), radSq2 = dist_sq(xc, yc, rec.x2, rec.y2);
+        double radSq = radSq1 > radSq2 ? radSq1 : radSq2;
+        while (density < density_th) {
+            radSq *= 0.75 * 0.75;
+            for (size_t i = 0; i < reg.size(); ++i) {
+                if (dist_sq(xc, yc, (double)reg[i].x, (double)reg[i].y) > radSq) {
+                    used[(size_t)reg[i].y * W + reg[i].x] = 0;
+                    std::swap(reg[i], reg[reg.size() - 1]);
+                    reg.pop_back();
+                    --i;
+                }
+            }
+            if (reg.size() < 2) return false;
+            region2rect(reg, reg_angle, prec, p, rec);
+            density = (double)reg.size() / (dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+        }
+        return true;
+    }
+
+    // LSD refine (refine >= 1): density check, re-grow with a tolerance from the local angle spread, radius reduction
+    bool refine(std::vector<RegPt>& reg, double reg_angle, double prec, double p, Rect& rec, double density_th) {
+        double density = (double)reg.size() / (dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+        if (density >= density_th) return true;
+        double xc = (double)reg[0].x, yc = (double)reg[0].y;
+        const double ang_c = angles[(size_t)reg[0].y * W + reg[0].x];
+        double sum = 0, s_sum = 0;
+        int n = 0;
+        for (size_t i = 0; i < reg.size(); ++i) {
+            used[(size_t)reg[i].y * W + reg[i].x] = 0;
+            if (dist(xc, yc, (double)reg[i].x, (double)reg[i].y) < rec.width) {
+                const double angle = angles[(size_t)reg[i].y * W + reg[i].x];
+                double ang_d = angle_diff_signed(angle, ang_c);
+                sum += ang_d;
+                s_sum += ang_d * ang_d;
+                ++n;
+            }
+        }
+        double mean_angle = sum / (double)n;
+        double tau = 2.0 * std::sqrt((s_sum - 2.0 * mean_angle * sum) / (double)n + mean_angle * mean_angle);
+        const int sx = reg[0].x, sy = reg[0].y;
+        region_grow(sx, sy, reg, reg_angle, tau);
+        if (reg.size() < 2) return false;
+        region2rect(reg, reg_angle, prec, p, rec);
+        density = (double)reg.size() / (dist(rec.x1, rec.y1, rec.x2, rec.y2) * rec.width);
+        if (density < density_th) return reduce_region_radius(reg, reg_angle, prec, p, rec, density, density_th);
+        return true;
     }
 };
 }  // namespace
@@ -206,8 +277,10 @@ void lsd_detect(const LsdConfig& c, const Img8& img, LsdState& st) {
         double reg_angle;
         L.region_grow(op.x, op.y, reg, reg_angle, prec);
         if (reg.size() < min_reg_size) continue;
-        double r[4];
-        L.region2rect(reg, reg_angle, prec, r);
+        Lsd::Rect rec;
+        L.region2rect(reg, reg_angle, prec, p, rec);
+        if (c.refine >= 1 && !L.refine(reg, reg_angle, prec, p, rec, c.density_th)) continue;
+        double r[4] = {rec.x1, rec.y1, rec.x2, rec.y2};
         for (int k = 0; k < 4; ++k) {
             r[k] += 0.5;
             if (c.scale != 1) r[k] /= c.scale;

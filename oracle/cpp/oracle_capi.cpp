@@ -61,7 +61,7 @@ PLF_API int plf_cpu_create(const plf_params* p, int /*device*/, plf_ctx** out) {
     if (!p || !out) return fail(PLF_ERR_INVALID, "null argument");
     if (p->width < 64 || p->height < 64 || p->max_batch < 1 || p->n_levels < 1 || p->n_levels > 16)
         return fail(PLF_ERR_INVALID, "bad image size / batch / levels");
-    if (p->lsd_refine != 0) return fail(PLF_ERR_UNSUPPORTED, "lsd_refine != 0 is not built");
+    if (p->lsd_refine < 0 || p->lsd_refine > 1) return fail(PLF_ERR_UNSUPPORTED, "lsd_refine = 2 (ADVANCED: NFA rectangle improvement) is not built");
     plf_ctx* c = new plf_ctx();
     c->p = *p;
     c->oc.nfeatures = p->n_features; c->oc.scaleFactor = p->scale_factor; c->oc.nlevels = p->n_levels;
@@ -417,6 +417,8 @@ PLF_API int plf_cpu_prim_lsd(const uint8_t* src, int w, int h, double scale, int
     std::memcpy(s.d.data(), src, (size_t)w * h);
     LsdConfig c;
     c.scale = scale;
+    c.refine = stable >> 4;           // bits 4..: refine mode (test hook)
+    stable &= 15;
     c.stable_order = stable != 0;
     LsdState st;
     lsd_detect(c, s, st);

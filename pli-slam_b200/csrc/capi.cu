@@ -157,6 +157,8 @@ static int build_geometry(plf_ctx* c, std::vector<PlfCell>& cells) {
     g.prec = kPi * p.lsd_ang_th / 180;
     g.rho = p.lsd_quant / std::sin(g.prec);
     g.nBins = p.lsd_n_bins;
+    g.refine = p.lsd_refine;
+    g.densityTh = p.lsd_density_th;
     g.n2Thresh = 0;
     for (int n2 = 0; n2 <= 2 * 510 * 510; ++n2) {      // exact integer image of LSD's `norm <= threshold` test
         if (std::sqrt((double)n2 / 4.0) <= g.rho) g.n2Thresh = n2; else break;
@@ -189,7 +191,7 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
     if (p->width < 64 || p->height < 64 || p->max_batch < 1 || p->n_levels < 1 || p->n_levels > PLF_MAX_LEVELS ||
         p->n_features < 1)
         return fail(PLF_ERR_INVALID, "bad image size / batch / levels / features");
-    if (p->lsd_refine != 0) return fail(PLF_ERR_UNSUPPORTED, "lsd_refine != 0 is not built");
+    if (p->lsd_refine < 0 || p->lsd_refine > 1) return fail(PLF_ERR_UNSUPPORTED, "lsd_refine = 2 (ADVANCED: NFA rectangle improvement) is not built");
     if (p->min_th_fast < 1 || p->min_th_fast > 126 || p->ini_th_fast < p->min_th_fast || p->ini_th_fast > 254)
         return fail(PLF_ERR_UNSUPPORTED, "FAST thresholds outside 1 <= minTh <= 126, minTh <= iniTh <= 254");
     int ndev = 0;

@@ -190,23 +190,25 @@ __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float4
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K4c  region growing + rectangle fit (LSD region_grow / region2rect / get_theta), refine = 0.
+// K4c  region growing + rectangle fit (LSD region_grow / region2rect / get_theta / refine / reduce_region_radius).
 // One warp per image; seeds in order; every region is grown with the exact sequential rule: list entries are expanded
 // front to back, their 8 neighbours in raster order, a neighbour is accepted iff unused and aligned with the CURRENT
 // region angle, which is updated after every acceptance.  The kernel is bound by dependent-instruction latency (ncu:
-// ~270 warp instructions per accepted pixel at 0.14 IPC, DRAM idle), so the design minimises instructions per pixel and
-// shared memory per block (many images in flight per SM), not bytes:
+// ~200 warp instructions per accepted pixel at 0.14 IPC per warp, DRAM idle), so the design minimises instructions per
+// pixel and shared memory per block (many images in flight per SM), not bytes:
 //  * per-pixel data is one read-only 16-byte record (angle, cosf, sinf, |g|^2) -> one LDG.128 per neighbour;
 //  * the `used` map is a bitmap in global memory (64 KB per image, L2-resident), cleared by a memset node;
 //  * list entries are packed (y<<16|x) so no integer division is ever needed; the BFS frontier lives in a small
 //    shared-memory ring, the full list also goes to global memory for the rectangle fit;
 //  * a batch covers 8 list entries x 8 neighbours = 2 candidates per lane in processing order; the loads of a batch are
-//    issued together and the acceptance chain is resolved with ballots, one fastAtan2 per accepted pixel.
+//    issued together and the acceptance chain is resolved with ballots, one fastAtan2 per accepted pixel;
+//  * the rectangle sums keep the scalar loop's summation order (three lanes own one accumulator each).
+// (A variant with four images per warp — 8 lanes per image, lock-step state machine — was measured: same instruction
+// count per image, 4x the latency; one warp per image is kept.)
 #define GROW_RING 512
 
 // Sequential (scalar-loop order) accumulation of three quantities over the pixels of a region: the 32 lanes write
 // their three products to shared memory, then lanes 0..2 each own one accumulator and add the 32 values in order.
-// Same rounding sequence as the scalar loop, a third of the instructions of a shuffle chain.
 __device__ __forceinline__ void seq_sum3(double (*buf)[33], double a, double b, double c, unsigned cnt, int lane,
                                          double& acc) {
     buf[0][lane] = a;
@@ -224,28 +226,42 @@ struct GrowState {
     double regAngle;
 };
 
+struct GrowCtx {
+    const float4* REC;
+    uint32_t* used;
+    int* R;
+    int* ring;
+    int W, H, lane, ddx, ddy;
+};
+
+__device__ __forceinline__ bool used_bit(const uint32_t* used, int q) {
+    // plain (L1-cached) load: the bitmap is only updated by this warp's own SM (stores/atomics keep the SM's L1
+    // coherent, __syncwarp orders them), and re-reading L1 hits is what keeps the batch preamble short
+    return (used[q >> 5] >> (q & 31)) & 1u;
+}
+
 // resolves one set of 32 candidates (lane order = processing order); `valid` lanes hold pixel q (packed pk) with record r
-__device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int pk, const float4& r, double prec,
-                                           int lane, uint32_t* used, int* ring, int* R) {
+__device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int pk, const float4& r, double tol,
+                                           const GrowCtx& c) {
     unsigned pending = __ballot_sync(0xffffffffu, valid);
     if (!pending) return;
-    const unsigned dup = __match_any_sync(0xffffffffu, valid ? q : -1 - lane);
+    const unsigned dup = __match_any_sync(0xffffffffu, valid ? q : -1 - c.lane);
     const double aRad = (double)r.x * kDegToRad;
     while (pending) {
-        // LSD isAligned(): |theta - a|, folded once around 2*pi, <= prec  (branch-free, same arithmetic)
+        // LSD isAligned(): |theta - a|, folded once around 2*pi, <= tolerance  (branch-free, same arithmetic)
         double nd = fabs(__dsub_rn(st.regAngle, aRad));
         const double nw = fabs(__dsub_rn(nd, 2 * kPi));
         nd = (nd > (3 * kPi) / 2) ? nw : nd;
-        const unsigned am = __ballot_sync(0xffffffffu, nd <= prec) & pending;
+        const unsigned am = __ballot_sync(0xffffffffu, nd <= tol) & pending;
         if (!am) break;
         const int Lw = __ffs(am) - 1;
         const int pkL = __shfl_sync(0xffffffffu, pk, Lw);
         const float cx = __shfl_sync(0xffffffffu, r.y, Lw), cy = __shfl_sync(0xffffffffu, r.z, Lw);
         const unsigned dupL = __shfl_sync(0xffffffffu, dup, Lw);
-        if (lane == Lw) atomicOr(used + (q >> 5), 1u << (q & 31));
-        if (lane == 0) {
-            ring[st.n & (GROW_RING - 1)] = pkL;
-            R[st.n] = pkL;
+        if (c.lane == Lw) atomicOr(c.used + (q >> 5), 1u << (q & 31));
+        if (c.lane == 0) {
+            c.ring[st.n & (GROW_RING - 1)] = pkL;
+            c.R[st.n] = pkL;
         }
         ++st.n;
         st.sumdx = __fadd_rn(st.sumdx, cx);
@@ -255,153 +271,269 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
     }
 }
 
+// LSD region_grow from the seed (packed pk0, linear index p) with angle tolerance `tol`; returns the region size, the
+// pixel list is left in c.R[0..n)
+__device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, double tol, double& regAngleOut) {
+    GrowState st;
+    st.n = 1;
+    if (c.lane == 0) { c.ring[0] = pk0; c.R[0] = pk0; atomicOr(c.used + (p >> 5), 1u << (p & 31)); }
+    st.regAngle = (double)c.REC[p].x * kDegToRad;
+    {
+        double sn, cs;
+        sincos(st.regAngle, &sn, &cs);
+        st.sumdx = (float)cs;
+        st.sumdy = (float)sn;
+    }
+    __syncwarp();
+    int i = 0;
+    while (i < st.n) {
+        const int nb = min(8, st.n - i);
+        const bool inRing = (st.n - i) <= GROW_RING;
+        int q[2], pk[2];
+        float4 r[2];
+        bool valid[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int e = s * 4 + (c.lane >> 3);
+            q[s] = -1;
+            pk[s] = 0;
+            valid[s] = false;
+            r[s] = make_float4(PLF_NOTDEF, 0.f, 0.f, 0.f);
+            if (e < nb) {
+                const int rp = inRing ? c.ring[(i + e) & (GROW_RING - 1)] : c.R[i + e];
+                const int xx = (rp & 0xFFFF) + c.ddx, yy = (rp >> 16) + c.ddy;
+                if (xx >= 0 && yy >= 0 && xx < c.W && yy < c.H) {
+                    q[s] = yy * c.W + xx;
+                    pk[s] = (yy << 16) | xx;
+                    if (!used_bit(c.used, q[s])) {
+                        r[s] = c.REC[q[s]];
+                        valid[s] = r[s].x != PLF_NOTDEF;
+                    }
+                }
+            }
+        }
+        grow_chain(st, valid[0], q[0], pk[0], r[0], tol, c);
+        __syncwarp();
+        if (nb > 4) {
+            // pixels accepted while resolving the first set are no longer available
+            if (valid[1] && used_bit(c.used, q[1])) valid[1] = false;
+            grow_chain(st, valid[1], q[1], pk[1], r[1], tol, c);
+            __syncwarp();
+        }
+        i += nb;
+    }
+    regAngleOut = st.regAngle;
+    return st.n;
+}
+
+struct RectFit { double x1, y1, x2, y2, width; };
+
+// LSD region2rect + get_theta over c.R[0..n): scalar-loop summation order for the weighted sums
+template <bool WIDTH>
+__device__ __forceinline__ void rect_fit(const GrowCtx& c, double (*s_sum)[33], int n, double regAngle, double prec, RectFit& rf) {
+    const int lane = c.lane, W = c.W;
+    double acc3 = 0;      // lane 0: sum x*w, lane 1: sum y*w, lane 2: sum w
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const unsigned cnt = min(32, n - i0);
+        double wv = 0, xw = 0, yw = 0;
+        if (lane < cnt) {
+            const int rp = c.R[i0 + lane];
+            const int ry = rp >> 16, rx = rp & 0xFFFF;
+            wv = sqrt((double)__float_as_int(c.REC[ry * W + rx].w) / 4.0);
+            xw = __dmul_rn((double)rx, wv);
+            yw = __dmul_rn((double)ry, wv);
+        }
+        seq_sum3(s_sum, xw, yw, wv, cnt, lane, acc3);
+    }
+    const double sw = __shfl_sync(0xffffffffu, acc3, 2);
+    const double cxm = __shfl_sync(0xffffffffu, acc3, 0) / sw, cym = __shfl_sync(0xffffffffu, acc3, 1) / sw;
+    acc3 = 0;             // lane 0: Ixx, lane 1: Iyy, lane 2: Ixy
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const unsigned cnt = min(32, n - i0);
+        double vxx = 0, vyy = 0, vxy = 0;
+        if (lane < cnt) {
+            const int rp = c.R[i0 + lane];
+            const int ry = rp >> 16, rx = rp & 0xFFFF;
+            const double wv = sqrt((double)__float_as_int(c.REC[ry * W + rx].w) / 4.0);
+            const double dx = __dsub_rn((double)rx, cxm), dy = __dsub_rn((double)ry, cym);
+            vxx = __dmul_rn(__dmul_rn(dy, dy), wv);
+            vyy = __dmul_rn(__dmul_rn(dx, dx), wv);
+            vxy = -__dmul_rn(__dmul_rn(dx, dy), wv);
+        }
+        seq_sum3(s_sum, vxx, vyy, vxy, cnt, lane, acc3);
+    }
+    const double Ixx = __shfl_sync(0xffffffffu, acc3, 0), Iyy = __shfl_sync(0xffffffffu, acc3, 1);
+    const double Ixy = __shfl_sync(0xffffffffu, acc3, 2);
+    const double dI = __dsub_rn(Ixx, Iyy);
+    const double lambda = __dmul_rn(0.5, __dsub_rn(__dadd_rn(Ixx, Iyy),
+                                                   sqrt(__dadd_rn(__dmul_rn(dI, dI), __dmul_rn(__dmul_rn(4.0, Ixy), Ixy)))));
+    double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)__dsub_rn(lambda, Ixx), (float)Ixy)
+                                           : (double)fast_atan2_deg((float)Ixy, (float)__dsub_rn(lambda, Iyy));
+    theta *= kDegToRad;
+    {
+        double diff = theta - regAngle;
+        while (diff <= -kPi) diff += 2 * kPi;
+        while (diff > kPi) diff -= 2 * kPi;
+        if (diff < 0) diff = -diff;
+        if (diff > prec) theta += kPi;
+    }
+    double dxr, dyr;
+    sincos(theta, &dyr, &dxr);
+    double lmin = 0, lmax = 0, wmin = 0, wmax = 0;
+    for (int i0 = lane; i0 < n; i0 += 32) {
+        const int rp = c.R[i0];
+        const int ry = rp >> 16, rx = rp & 0xFFFF;
+        const double rdx = __dsub_rn((double)rx, cxm), rdy = __dsub_rn((double)ry, cym);
+        const double l = __dadd_rn(__dmul_rn(rdx, dxr), __dmul_rn(rdy, dyr));
+        lmax = fmax(lmax, l);
+        lmin = fmin(lmin, l);
+        if (WIDTH) {      // the rectangle width is only needed by refine()
+            const double w = __dadd_rn(__dmul_rn(-rdx, dyr), __dmul_rn(rdy, dxr));
+            wmax = fmax(wmax, w);
+            wmin = fmin(wmin, w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        if (WIDTH) {
+            wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+            wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+        }
+    }
+    rf.x1 = __dadd_rn(cxm, __dmul_rn(lmin, dxr));
+    rf.y1 = __dadd_rn(cym, __dmul_rn(lmin, dyr));
+    rf.x2 = __dadd_rn(cxm, __dmul_rn(lmax, dxr));
+    rf.y2 = __dadd_rn(cym, __dmul_rn(lmax, dyr));
+    rf.width = __dsub_rn(wmax, wmin);
+    if (rf.width < 1.0) rf.width = 1.0;
+}
+
+__device__ __forceinline__ double lsd_dist(double x1, double y1, double x2, double y2) {
+    const double dx = __dsub_rn(x2, x1), dy = __dsub_rn(y2, y1);
+    return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+__device__ __forceinline__ double lsd_dist_sq(double x1, double y1, double x2, double y2) {
+    const double dx = __dsub_rn(x2, x1), dy = __dsub_rn(y2, y1);
+    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+
+// LSD refine() for refine = 1 (STANDARD): if the rectangle is too sparse, re-grow with a tolerance taken from the local
+// angle spread, then shrink the region radius until it is dense.  Returns false if the region is rejected.
+__device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[33], int& n, double& regAngle, double prec, double densityTh,
+                           RectFit& rf) {
+    const int lane = c.lane, W = c.W;
+    double density = (double)n / __dmul_rn(lsd_dist(rf.x1, rf.y1, rf.x2, rf.y2), rf.width);
+    if (density >= densityTh) return true;
+    const int pk0 = c.R[0];
+    const int sy = pk0 >> 16, sx = pk0 & 0xFFFF, p0 = sy * W + sx;
+    const double xc = (double)sx, yc = (double)sy;
+    const double angC = (double)c.REC[p0].x * kDegToRad;
+    double acc3 = 0;      // lane 0: sum of signed angle differences, lane 1: sum of their squares
+    int cntIn = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const unsigned cnt = min(32, n - i0);
+        double v0 = 0, v1 = 0;
+        bool in = false;
+        if (lane < cnt) {
+            const int rp = c.R[i0 + lane];
+            const int ry = rp >> 16, rx = rp & 0xFFFF, q = ry * W + rx;
+            atomicAnd(c.used + (q >> 5), ~(1u << (q & 31)));                      // *(reg[i].used) = NOTUSED
+            if (lsd_dist(xc, yc, (double)rx, (double)ry) < rf.width) {
+                double d = __dsub_rn((double)c.REC[q].x * kDegToRad, angC);         // angle_diff_signed
+                while (d <= -kPi) d += 2 * kPi;
+                while (d > kPi) d -= 2 * kPi;
+                v0 = d;
+                v1 = __dmul_rn(d, d);
+                in = true;
+            }
+        }
+        cntIn += __popc(__ballot_sync(0xffffffffu, in));
+        seq_sum3(s_sum, v0, v1, 0.0, cnt, lane, acc3);
+    }
+    const double sum = __shfl_sync(0xffffffffu, acc3, 0), ssum = __shfl_sync(0xffffffffu, acc3, 1);
+    const double mean = sum / (double)cntIn;
+    const double tau = __dmul_rn(2.0, sqrt(__dadd_rn(__dsub_rn(ssum, __dmul_rn(__dmul_rn(2.0, mean), sum)) / (double)cntIn,
+                                                     __dmul_rn(mean, mean))));
+    __syncwarp();
+    __threadfence_block();
+    n = grow_region(c, pk0, p0, tau, regAngle);
+    if (n < 2) return false;
+    rect_fit<true>(c, s_sum, n, regAngle, prec, rf);
+    density = (double)n / __dmul_rn(lsd_dist(rf.x1, rf.y1, rf.x2, rf.y2), rf.width);
+    if (density >= densityTh) return true;
+    // reduce_region_radius: drop the points farther than 75 % of the radius (swap-with-last removal, list order matters
+    // for the next rectangle fit, so the removal is done serially by lane 0), refit, until dense
+    const double r1 = lsd_dist_sq(xc, yc, rf.x1, rf.y1), r2 = lsd_dist_sq(xc, yc, rf.x2, rf.y2);
+    double radSq = r1 > r2 ? r1 : r2;
+    while (density < densityTh) {
+        radSq = __dmul_rn(radSq, 0.75 * 0.75);
+        int sz = n;
+        if (lane == 0) {
+            for (int i = 0; i < sz; ++i) {
+                const int rp = c.R[i];
+                const int ry = rp >> 16, rx = rp & 0xFFFF;
+                if (lsd_dist_sq(xc, yc, (double)rx, (double)ry) > radSq) {
+                    const int q = ry * W + rx;
+                    atomicAnd(c.used + (q >> 5), ~(1u << (q & 31)));
+                    c.R[i] = c.R[sz - 1];
+                    --sz;
+                    --i;
+                }
+            }
+        }
+        n = __shfl_sync(0xffffffffu, sz, 0);
+        __syncwarp();
+        if (n < 2) return false;
+        rect_fit<true>(c, s_sum, n, regAngle, prec, rf);
+        density = (double)n / __dmul_rn(lsd_dist(rf.x1, rf.y1, rf.x2, rf.y2), rf.width);
+    }
+    return true;
+}
+
+template <bool REFINE>
 __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* rec, const int* seeds, const int* nSeeds,
                                                       uint32_t* usedAll, int* reg, float* segs, int* nSegsOut, int* err,
                                                       int nWords, int imgFirst) {
     __shared__ int ring[GROW_RING];
     __shared__ double s_sum[3][33];
     const int img = imgFirst + blockIdx.x, lane = threadIdx.x;
-    const int W = g.Ws, H = g.Hs;
-    const size_t base = (size_t)img * W * H;
-    const float4* REC = rec + base;
-    uint32_t* used = usedAll + (size_t)img * nWords;
-    int* R = reg + base;
+    GrowCtx c;
+    c.W = g.Ws; c.H = g.Hs; c.lane = lane;
+    const size_t base = (size_t)img * c.W * c.H;
+    c.REC = rec + base;
+    c.used = usedAll + (size_t)img * nWords;
+    c.R = reg + base;
+    c.ring = ring;
+    const int k = lane & 7;
+    c.ddx = (k < 3) ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6));
+    c.ddy = (k < 3) ? -1 : (k < 5 ? 0 : 1);
     const int* S = seeds + (size_t)img * g.seedCap;
     float* out = segs + (size_t)img * g.segCap * 4;
     const int ns = nSeeds[img];
     const double prec = g.prec;
     int nSeg = 0;
-    const int k = lane & 7;
-    const int ddx = (k < 3) ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6));
-    const int ddy = (k < 3) ? -1 : (k < 5 ? 0 : 1);
     for (int s0 = 0; s0 < ns; s0 += 32) {
         const int mySeed = (s0 + lane < ns) ? S[s0 + lane] : -1;       // packed (y<<16 | x)
-        const int myQ = (mySeed >> 16) * W + (mySeed & 0xFFFF);
-        const bool myFree = mySeed >= 0 && !((used[myQ >> 5] >> (myQ & 31)) & 1u);
+        const int myQ = (mySeed >> 16) * c.W + (mySeed & 0xFFFF);
+        const bool myFree = mySeed >= 0 && !used_bit(c.used, myQ);
         unsigned fm = __ballot_sync(0xffffffffu, myFree);
         while (fm) {
             const int si = __ffs(fm) - 1;
             fm &= fm - 1;
             const int pk0 = __shfl_sync(0xffffffffu, mySeed, si);
             const int p = __shfl_sync(0xffffffffu, myQ, si);
-            if ((used[p >> 5] >> (p & 31)) & 1u) continue;   // claimed by a region grown earlier in this chunk
-            // ---- region_grow -------------------------------------------------------------------------------------
-            GrowState st;
-            st.n = 1;
-            if (lane == 0) { ring[0] = pk0; R[0] = pk0; atomicOr(used + (p >> 5), 1u << (p & 31)); }
-            st.regAngle = (double)REC[p].x * kDegToRad;
-            {
-                double sn, cs;
-                sincos(st.regAngle, &sn, &cs);
-                st.sumdx = (float)cs;
-                st.sumdy = (float)sn;
-            }
-            __syncwarp();
-            int i = 0;
-            while (i < st.n) {
-                const int nb = min(8, st.n - i);
-                const bool inRing = (st.n - i) <= GROW_RING;
-                int q[2], pk[2];
-                float4 r[2];
-                bool valid[2];
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int e = s * 4 + (lane >> 3);
-                    q[s] = -1;
-                    pk[s] = 0;
-                    valid[s] = false;
-                    r[s] = make_float4(PLF_NOTDEF, 0.f, 0.f, 0.f);
-                    if (e < nb) {
-                        const int rp = inRing ? ring[(i + e) & (GROW_RING - 1)] : R[i + e];
-                        const int xx = (rp & 0xFFFF) + ddx, yy = (rp >> 16) + ddy;
-                        if (xx >= 0 && yy >= 0 && xx < W && yy < H) {
-                            q[s] = yy * W + xx;
-                            pk[s] = (yy << 16) | xx;
-                            if (!((used[q[s] >> 5] >> (q[s] & 31)) & 1u)) {
-                                r[s] = REC[q[s]];
-                                valid[s] = r[s].x != PLF_NOTDEF;
-                            }
-                        }
-                    }
-                }
-                grow_chain(st, valid[0], q[0], pk[0], r[0], prec, lane, used, ring, R);
-                __syncwarp();
-                if (nb > 4) {
-                    // pixels accepted while resolving the first set are no longer available
-                    if (valid[1] && ((used[q[1] >> 5] >> (q[1] & 31)) & 1u)) valid[1] = false;
-                    grow_chain(st, valid[1], q[1], pk[1], r[1], prec, lane, used, ring, R);
-                    __syncwarp();
-                }
-                i += nb;
-            }
-            const int n = st.n;
-            const double regAngle = st.regAngle;
+            if (used_bit(c.used, p)) continue;   // claimed by a region grown earlier in this chunk
+            double regAngle;
+            int n = grow_region(c, pk0, p, prec, regAngle);
             if (n < g.minRegSize) continue;
-            // ---- region2rect (sequential summation order reproduced with lane-ordered adds) -------------------------
-            double acc3 = 0;      // lane 0: sum x*w, lane 1: sum y*w, lane 2: sum w
-            for (int i0 = 0; i0 < n; i0 += 32) {
-                const unsigned cnt = min(32, n - i0);
-                double wv = 0, xw = 0, yw = 0;
-                if (lane < cnt) {
-                    const int rp = R[i0 + lane];
-                    const int ry = rp >> 16, rx = rp & 0xFFFF;
-                    wv = sqrt((double)__float_as_int(REC[ry * W + rx].w) / 4.0);
-                    xw = __dmul_rn((double)rx, wv);
-                    yw = __dmul_rn((double)ry, wv);
-                }
-                seq_sum3(s_sum, xw, yw, wv, cnt, lane, acc3);
-            }
-            const double sw = __shfl_sync(0xffffffffu, acc3, 2);
-            const double cxm = __shfl_sync(0xffffffffu, acc3, 0) / sw, cym = __shfl_sync(0xffffffffu, acc3, 1) / sw;
-            acc3 = 0;             // lane 0: Ixx, lane 1: Iyy, lane 2: Ixy
-            for (int i0 = 0; i0 < n; i0 += 32) {
-                const unsigned cnt = min(32, n - i0);
-                double vxx = 0, vyy = 0, vxy = 0;
-                if (lane < cnt) {
-                    const int rp = R[i0 + lane];
-                    const int ry = rp >> 16, rx = rp & 0xFFFF;
-                    const double wv = sqrt((double)__float_as_int(REC[ry * W + rx].w) / 4.0);
-                    const double dx = __dsub_rn((double)rx, cxm), dy = __dsub_rn((double)ry, cym);
-                    vxx = __dmul_rn(__dmul_rn(dy, dy), wv);
-                    vyy = __dmul_rn(__dmul_rn(dx, dx), wv);
-                    vxy = -__dmul_rn(__dmul_rn(dx, dy), wv);
-                }
-                seq_sum3(s_sum, vxx, vyy, vxy, cnt, lane, acc3);
-            }
-            const double Ixx = __shfl_sync(0xffffffffu, acc3, 0), Iyy = __shfl_sync(0xffffffffu, acc3, 1);
-            const double Ixy = __shfl_sync(0xffffffffu, acc3, 2);
-            const double dI = __dsub_rn(Ixx, Iyy);
-            const double lambda = __dmul_rn(0.5, __dsub_rn(__dadd_rn(Ixx, Iyy),
-                                                           sqrt(__dadd_rn(__dmul_rn(dI, dI), __dmul_rn(__dmul_rn(4.0, Ixy), Ixy)))));
-            double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)fast_atan2_deg((float)__dsub_rn(lambda, Ixx), (float)Ixy)
-                                                   : (double)fast_atan2_deg((float)Ixy, (float)__dsub_rn(lambda, Iyy));
-            theta *= kDegToRad;
-            {
-                double diff = theta - regAngle;
-                while (diff <= -kPi) diff += 2 * kPi;
-                while (diff > kPi) diff -= 2 * kPi;
-                if (diff < 0) diff = -diff;
-                if (diff > prec) theta += kPi;
-            }
-            double dxr, dyr;
-            sincos(theta, &dyr, &dxr);
-            double lmin = 0, lmax = 0;
-            for (int i0 = lane; i0 < n; i0 += 32) {
-                const int rp = R[i0];
-                const int ry = rp >> 16, rx = rp & 0xFFFF;
-                const double l = __dadd_rn(__dmul_rn(__dsub_rn((double)rx, cxm), dxr), __dmul_rn(__dsub_rn((double)ry, cym), dyr));
-                lmax = fmax(lmax, l);
-                lmin = fmin(lmin, l);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-                lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-            }
+            RectFit rf;
+            rect_fit<REFINE>(c, s_sum, n, regAngle, prec, rf);
+            if (REFINE && !lsd_refine(c, s_sum, n, regAngle, prec, g.densityTh, rf)) continue;
             if (lane == 0) {
                 if (nSeg < g.segCap) {
-                    double rr[4] = {__dadd_rn(cxm, __dmul_rn(lmin, dxr)), __dadd_rn(cym, __dmul_rn(lmin, dyr)),
-                                    __dadd_rn(cxm, __dmul_rn(lmax, dxr)), __dadd_rn(cym, __dmul_rn(lmax, dyr))};
+                    const double rr[4] = {rf.x1, rf.y1, rf.x2, rf.y2};
                     for (int q4 = 0; q4 < 4; ++q4) {
                         double v = rr[q4] + 0.5;
                         if (g.lsdScale != 1) v /= g.lsdScale;
@@ -699,8 +831,12 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     {
         const int nWords = (g.Ws * g.Hs + 31) / 32;
         cudaMemsetAsync(c->d_used + (size_t)imgFirst * nWords, 0, (size_t)nImg * nWords * 4, s);
-        lsd_grow_kernel<<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
-                                            c->d_nSegs, c->d_err, nWords, imgFirst);
+        if (g.refine >= 1)
+            lsd_grow_kernel<true><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
+                                                      c->d_nSegs, c->d_err, nWords, imgFirst);
+        else
+            lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
+                                                       c->d_nSegs, c->d_err, nWords, imgFirst);
     }
     plf_mark(c, "line_keylines");
     const double minLen = c->p.min_line_length * std::min(g.W, g.H);

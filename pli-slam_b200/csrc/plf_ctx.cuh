@@ -54,6 +54,8 @@ struct PlfGeom {          // passed by value to kernels (fits the 4 KB parameter
     int lsdTaps[16], lsdK;
     double lsdScale, rho, prec;
     int nBins, minRegSize;
+    int refine;           // LSD refine mode (0 none, 1 standard)
+    double densityTh;
     int n2Thresh;         // largest |g|^2 (integer) with sqrt(|g|^2 / 4.0) <= rho: pixel defined iff |g|^2 > n2Thresh
     int segCap;           // max segments kept per image
     int seedCap;

@@ -207,6 +207,8 @@ def test_batch64_full_size_properties(plf, product, oracle):
     (752, 480, dict(scale_factor=1.5, n_levels=4, ini_th_fast=30, min_th_fast=10, lsd_nfeatures=100)),
     (752, 480, dict(has_lines=0, n_features=3000)),               # ORB only, many features
     (752, 480, dict(best_lr_matches=0, matching_s_ws=20, min_ratio_12_l=0.8, line_sim_th=0.5)),
+    (752, 480, dict(lsd_refine=1)),                               # LSD_REFINE_STD: re-grow + radius reduction
+    (1280, 720, dict(lsd_refine=1, lsd_density_th=0.8, lsd_nfeatures=0)),
 ])
 def test_shapes_and_parameters(plf, product, oracle, W, H, kw):
     """Geometry and parameter sweep (batch of 2 pairs): every output array identical to the oracle."""

@@ -35,7 +35,7 @@ def test_scale_tables_and_quotas(plf, oracle):
 
 def test_unsupported_parameters_fail(plf, oracle):
     with pytest.raises(plf.PlfError):
-        plf.Frontend(oracle, lsd_refine=1)
+        plf.Frontend(oracle, lsd_refine=2)       # ADVANCED (NFA rectangle improvement) is not built
     with pytest.raises(plf.PlfError):
         plf.Frontend(oracle, width=16, height=16)
 

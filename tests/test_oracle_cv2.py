@@ -178,3 +178,16 @@ def test_lsd_vs_cv2(oracle, plf, w, h, seed):
         assert np.array_equal(out[:n.value], ref)
         assert oracle.dll.plf_cpu_prim_lsd(_p(img), w, h, C.c_double(1.2), 0, _p(out), 20000, C.byref(n)) == 0
         assert _match_segments(ref, out[:n.value].copy(), 0.5) >= 0.95
+
+
+@pytest.mark.parametrize("w,h,seed", [(752, 480, 1), (752, 480, 5), (1280, 720, 2000), (640, 480, 9)])
+def test_lsd_refine_standard_vs_cv2(oracle, plf, w, h, seed):
+    """LSD_REFINE_STD (opts.refine = 1: density check, re-grow with the local angle spread, radius reduction) is
+    bit-identical to cv2 as well."""
+    L, R = plf.synth_pair(w, h, seed)
+    for img in (L, R):
+        ref = cv2.createLineSegmentDetector(1, 1.2, 0.6, 2.0, 22.5, 1.0, 0.6, 1024).detect(img)[0].reshape(-1, 4)
+        out = np.zeros((20000, 4), np.float32)
+        n = C.c_int(0)
+        assert oracle.dll.plf_cpu_prim_lsd(_p(img), w, h, C.c_double(1.2), 1 | (1 << 4), _p(out), 20000, C.byref(n)) == 0
+        assert n.value == len(ref) and np.array_equal(out[:n.value], ref)

@@ -223,8 +223,8 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
         std::vector<PlfLin> lin;
         for (int l = 0; l < g.nLevels; ++l) {
             const PlfLevel& lv = g.lv[l];
-            for (int y = 0; y < lv.h; y += 32)
-                for (int x = 0; x < lv.w; x += 32) tb.push_back(PlfTile{(short)l, (short)x, (short)y, 0});
+            for (int y = 0; y < lv.h; y += 8)
+                for (int x = 0; x < lv.w; x += 128) tb.push_back(PlfTile{(short)l, (short)x, (short)y, 0});
             for (int y = PLF_EDGE; y < lv.h - PLF_EDGE; y += 8)
                 for (int x = PLF_EDGE; x < lv.w - PLF_EDGE; x += 128) tf.push_back(PlfTile{(short)l, (short)x, (short)y, 0});
         }

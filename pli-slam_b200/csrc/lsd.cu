@@ -21,22 +21,19 @@ constexpr double kDegToRad = kPi / 180.0;
 
 // ---------------------------------------------------------------------------------------------------------------
 // K4a  pre-blur (cv::GaussianBlur 8U, ksize/sigma from sigma_scale) and x`scale` upscale (INTER_LINEAR_EXACT)
-template <int K>
+// 7-tap separable blur of a whole image batch (LSD pre-blur; LBD 5x5 blur as 7 taps with zero ends)
 __global__ void __launch_bounds__(256) blur_image_kernel(const uint8_t* src, size_t srcImgStride, int sp, uint8_t* dst,
                                                          size_t dstImgStride, int dp, int w, int h, int imgFirst,
                                                          const int t0, const int t1, const int t2, const int t3,
                                                          const int t4, const int t5, const int t6) {
-    const int tx = (w + 31) >> 5;
+    const int tx = (w + BL_TW - 1) / BL_TW;
     const int img = imgFirst + blockIdx.y;
     BlurJob j;
     j.src = src + (size_t)img * srcImgStride;
     j.dst = dst + (size_t)img * dstImgStride;
     j.w = w; j.h = h; j.sp = sp; j.dp = dp;
-    const int all[7] = {t0, t1, t2, t3, t4, t5, t6};
-    int taps[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) taps[k] = all[k];
-    blur_tile<K>(j, taps, (blockIdx.x % tx) * 32, (blockIdx.x / tx) * 32);
+    const int taps[7] = {t0, t1, t2, t3, t4, t5, t6};
+    blur_tile7(j, taps, (blockIdx.x % tx) * BL_TW, (blockIdx.x / tx) * BL_TH);
 }
 
 __global__ void __launch_bounds__(256) lsd_upscale_kernel(PlfGeom g, const uint8_t* src, size_t srcImgStride, int sp,
@@ -799,16 +796,17 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     const size_t inStride = (size_t)g.pyrBytes;
     const int ip = g.lv[0].pitch;
     const size_t imgBytes = (size_t)ip * g.H;
-    const int tiles = ((g.W + 31) / 32) * ((g.H + 31) / 32);
+    const int tiles = ((g.W + BL_TW - 1) / BL_TW) * ((g.H + BL_TH - 1) / BL_TH);
     int launches = 0;
     plf_mark(c, "lsd_prefilter");
     const uint8_t* upSrc = in;
     size_t upStride = inStride;
     if (g.lsdK > 0) {
         const int* t = g.lsdTaps;
-        if (g.lsdK == 7) blur_image_kernel<7><<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(in, inStride, ip, c->d_lsdBlur, imgBytes, ip, g.W, g.H, imgFirst, t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
-        else if (g.lsdK == 5) blur_image_kernel<5><<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(in, inStride, ip, c->d_lsdBlur, imgBytes, ip, g.W, g.H, imgFirst, t[0], t[1], t[2], t[3], t[4], 0, 0);
-        else blur_image_kernel<3><<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(in, inStride, ip, c->d_lsdBlur, imgBytes, ip, g.W, g.H, imgFirst, t[0], t[1], t[2], 0, 0, 0, 0);
+        int t7[7] = {0, 0, 0, 0, 0, 0, 0};                 // centre the ksize taps in a 7-tap window
+        for (int k = 0; k < g.lsdK; ++k) t7[(7 - g.lsdK) / 2 + k] = t[k];
+        blur_image_kernel<<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(in, inStride, ip, c->d_lsdBlur, imgBytes, ip, g.W, g.H, imgFirst,
+                                                                   t7[0], t7[1], t7[2], t7[3], t7[4], t7[5], t7[6]);
         upSrc = c->d_lsdBlur;
         upStride = imgBytes;
         ++launches;
@@ -843,7 +841,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     keylines_kernel<<<nImg, 256, g.segCap * sizeof(float), s>>>(g, c->d_segs, c->d_nSegs, c->d_klAll, c->d_kl, c->d_nKl, c->d_err, minLen, c->p.lsd_nfeatures, imgFirst);
     plf_mark(c, "lbd_blur_sobel");
     const int lt[5] = {14, 62, 104, 62, 14};
-    blur_image_kernel<5><<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(in, inStride, ip, c->d_lbdBlur, imgBytes, ip, g.W, g.H, imgFirst, lt[0], lt[1], lt[2], lt[3], lt[4], 0, 0);
+    blur_image_kernel<<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(in, inStride, ip, c->d_lbdBlur, imgBytes, ip, g.W, g.H, imgFirst, 0, lt[0], lt[1], lt[2], lt[3], lt[4], 0);
     sobel_kernel<<<dim3((g.W + 31) / 32, (g.H + 7) / 8, nImg), dim3(32, 8), 0, s>>>(c->d_lbdBlur, imgBytes, ip, c->d_sobel, g.W, g.H, imgFirst);
     plf_mark(c, "lbd_descriptor");
     lbd_kernel<<<dim3((g.klCap + 3) / 4, nImg), 128, 0, s>>>(g, c->d_sobel, c->d_kl, c->d_nKl, c->d_lbd, c->d_ldesc, imgFirst);

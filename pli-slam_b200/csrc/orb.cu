@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) blur_pyramid_kernel(PlfGeom g, const uint
     j.dst = blur + (size_t)img * g.pyrBytes + lv.off;
     j.w = lv.w; j.h = lv.h; j.sp = j.dp = lv.pitch;
     const int taps[7] = {18, 34, 48, 56, 48, 34, 18};
-    blur_tile<7>(j, taps, t.x0, t.y0);
+    blur_tile7(j, taps, t.x0, t.y0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -56,14 +56,15 @@ __global__ void __launch_bounds__(256) lsd_upscale_kernel(PlfGeom g, const uint8
 // K4b  level-line field (LSD ll_angle): 2x2 gradient, squared norm, fastAtan2 angle (degrees), cosf/sinf of the angle,
 // per-image max of the squared norm over defined pixels.
 __global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, float4* rec, int* n2max, int imgFirst) {
-    // Two phases per 32x8 tile: (1) every thread: 2x2 gradient and |g|^2; a pixel is defined iff |g|^2 > n2Thresh, the
-    // integer image of LSD's "norm > rho" test (exact: host-searched with the same IEEE sqrt).  Undefined pixels are
-    // written at once; defined ones are queued.  (2) the queue is processed densely, one defined pixel per thread, so
-    // the expensive part (fastAtan2 + double cos/sin) costs in proportion to the defined pixels, not to the warps that
-    // happen to contain one.
+    // Two phases per 128x8 tile, 4 horizontally adjacent pixels per thread (aligned 32-bit loads of the u8 image, 64
+    // contiguous bytes of records written per thread):
+    // (1) 2x2 gradient and |g|^2; a pixel is defined iff |g|^2 > n2Thresh, the integer image of LSD's "norm > rho" test
+    //     (exact: host-searched with the same IEEE sqrt).  Undefined pixels are written at once, defined ones queued.
+    // (2) the queue is processed densely, one defined pixel per thread, so the expensive part (fastAtan2 + double
+    //     sincos) costs in proportion to the defined pixels, not to the warps that happen to contain one.
     __shared__ int s_cnt;
-    __shared__ int s_q[256];          // tid | (gx+1024)<<8 | (gy+1024)<<20
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    __shared__ int s_q[1024];          // (ty<<7 | column) | (gx+1024)<<10 | (gy+1024)<<21
+    const int x = blockIdx.x * 128 + threadIdx.x * 4, y = blockIdx.y * 8 + threadIdx.y;
     const int img = imgFirst + blockIdx.z;
     const int tid = threadIdx.y * 32 + threadIdx.x;
     if (tid == 0) s_cnt = 0;
@@ -71,30 +72,44 @@ __global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t*
     const size_t base = (size_t)img * g.Ws * g.Hs;
     int best = 0;
     if (x < g.Ws && y < g.Hs) {
-        int n2 = 0, gx = 0, gy = 0;
-        if (x < g.Ws - 1 && y < g.Hs - 1) {
-            const uint8_t* r0 = U + (size_t)img * g.Ps * g.Hs + (size_t)y * g.Ps;
-            const uint8_t* r1 = r0 + g.Ps;
-            const int DA = (int)r1[x + 1] - (int)r0[x], BC = (int)r0[x + 1] - (int)r1[x];
-            gx = DA + BC;
-            gy = DA - BC;
-            n2 = gx * gx + gy * gy;
-        }
-        if (n2 > g.n2Thresh) {
-            s_q[atomicAdd(&s_cnt, 1)] = tid | ((gx + 1024) << 8) | ((gy + 1024) << 20);
-            best = n2;
-        } else {
-            rec[base + (size_t)y * g.Ws + x] = make_float4(PLF_NOTDEF, 0.f, 0.f, __int_as_float(n2));
+        const uint8_t* r0 = U + (size_t)img * g.Ps * g.Hs + (size_t)y * g.Ps + x;
+        const uint8_t* r1 = r0 + (y + 1 < g.Hs ? g.Ps : 0);
+        // bytes x .. x+4 of both rows (the row pitch is padded, the 5th byte is only used when x+4 < Ws)
+        const unsigned a0 = *reinterpret_cast<const unsigned*>(r0), b0 = *reinterpret_cast<const unsigned*>(r1);
+        const unsigned a1 = (x + 4 < g.Ps) ? *reinterpret_cast<const unsigned*>(r0 + 4) : 0u;
+        const unsigned b1 = (x + 4 < g.Ps) ? *reinterpret_cast<const unsigned*>(r1 + 4) : 0u;
+        float4* out = rec + base + (size_t)y * g.Ws + x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (x + j >= g.Ws) break;
+            int n2 = 0, gx = 0, gy = 0;
+            if (x + j < g.Ws - 1 && y < g.Hs - 1) {
+                const int pa = (a0 >> (8 * j)) & 0xFF;                                             // (x, y)
+                const int pb = j < 3 ? (a0 >> (8 * j + 8)) & 0xFF : a1 & 0xFF;                     // (x+1, y)
+                const int pc = (b0 >> (8 * j)) & 0xFF;                                             // (x, y+1)
+                const int pd = j < 3 ? (b0 >> (8 * j + 8)) & 0xFF : b1 & 0xFF;                     // (x+1, y+1)
+                const int DA = pd - pa, BC = pb - pc;
+                gx = DA + BC;
+                gy = DA - BC;
+                n2 = gx * gx + gy * gy;
+            }
+            if (n2 > g.n2Thresh) {
+                s_q[atomicAdd(&s_cnt, 1)] = (threadIdx.y << 7) | (threadIdx.x * 4 + j) | ((gx + 1024) << 10) | ((gy + 1024) << 21);
+                best = max(best, n2);
+            } else {
+                out[j] = make_float4(PLF_NOTDEF, 0.f, 0.f, __int_as_float(n2));
+            }
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
     if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(n2max + img, best);
     __syncthreads();
-    if (tid < s_cnt) {
-        const int e = s_q[tid];
-        const int t2 = e & 0xFF, gx = ((e >> 8) & 0xFFF) - 1024, gy = ((e >> 20) & 0xFFF) - 1024;
-        const int px = blockIdx.x * 32 + (t2 & 31), py = blockIdx.y * 8 + (t2 >> 5);
+    const int nq = s_cnt;
+    for (int i = tid; i < nq; i += 256) {
+        const int e = s_q[i];
+        const int col = e & 0x7F, row = (e >> 7) & 0x7, gx = ((e >> 10) & 0x7FF) - 1024, gy = ((e >> 21) & 0x7FF) - 1024;
+        const int px = blockIdx.x * 128 + col, py = blockIdx.y * 8 + row;
         const float a = fast_atan2_deg((float)gx, (float)-gy);
         const float af = (float)((double)a * kDegToRad);
         // cosf/sinf taken as correctly rounded (double result rounded to float), the declared oracle rule
@@ -814,7 +829,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     lsd_upscale_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, c->d_lin + c->linLsdX, c->d_lin + c->linLsdY, imgFirst);
     plf_mark(c, "lsd_gradient");
     cudaMemsetAsync(c->d_n2max + imgFirst, 0, nImg * sizeof(int), s);
-    lsd_grad_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_rec, c->d_n2max, imgFirst);
+    lsd_grad_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_rec, c->d_n2max, imgFirst);
     plf_mark(c, "lsd_order");
     {
         const size_t smem = (size_t)32 * g.nBins * sizeof(int);

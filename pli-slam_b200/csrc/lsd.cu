@@ -657,17 +657,51 @@ __global__ void __launch_bounds__(256) keylines_kernel(PlfGeom g, const float* s
 // K4e  LBD: 5x5 sigma-1 blur (blur_image_kernel<5>), 3x3 Sobel to int16 pairs, band descriptor, binarisation.
 __global__ void __launch_bounds__(256) sobel_kernel(const uint8_t* src, size_t imgStride, int sp, short2* dst, int w, int h,
                                                     int imgFirst) {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    // 4 horizontally adjacent pixels per thread: three aligned words per row (x-4.., x.., x+4..) give bytes x-1 .. x+4;
+    // REFLECT_101 only matters in the first / last column group and the first / last row
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y;
     if (x >= w || y >= h) return;
     const int img = imgFirst + blockIdx.z;
     const uint8_t* s = src + (size_t)img * imgStride;
-    const uint8_t* r0 = s + (size_t)reflect101(y - 1, h) * sp;
-    const uint8_t* r1 = s + (size_t)y * sp;
-    const uint8_t* r2 = s + (size_t)reflect101(y + 1, h) * sp;
-    const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
-    const int gx = ((int)r0[xp] - r0[xm]) + 2 * ((int)r1[xp] - r1[xm]) + ((int)r2[xp] - r2[xm]);
-    const int gy = ((int)r2[xm] - r0[xm]) + 2 * ((int)r2[x] - r0[x]) + ((int)r2[xp] - r0[xp]);
-    dst[(size_t)img * w * h + (size_t)y * w + x] = make_short2((short)gx, (short)gy);
+    const int ys[3] = {reflect101(y - 1, h), y, reflect101(y + 1, h)};
+    int v[3][6];        // bytes x-1 .. x+4 of the three rows
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const uint8_t* row = s + (size_t)ys[r] * sp;
+        const unsigned cur = *reinterpret_cast<const unsigned*>(row + x);
+        v[r][1] = cur & 0xFF; v[r][2] = (cur >> 8) & 0xFF; v[r][3] = (cur >> 16) & 0xFF; v[r][4] = cur >> 24;
+        v[r][0] = row[reflect101(x - 1, w)];
+        v[r][5] = row[min(reflect101(x + 4, w), w - 1)];
+        // columns beyond the image inside my group of 4 (w not a multiple of 4): reflect them too
+        if (x + 3 >= w) {
+#pragma unroll
+            for (int j = 1; j < 4; ++j)
+                if (x + j >= w) v[r][1 + j] = row[max(reflect101(x + j, w), 0)];
+        }
+    }
+    short2 o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        // pixel x+j: left = v[.][j], centre = v[.][j+1], right = v[.][j+2]; at the right image border the "right"
+        // neighbour is the reflection of column x+j+1
+        int l0 = v[0][j], l1 = v[1][j], l2 = v[2][j], c0 = v[0][j + 1], c2 = v[2][j + 1];
+        int r0 = v[0][j + 2], r1 = v[1][j + 2], r2 = v[2][j + 2];
+        if (x + j + 1 >= w && x + j < w) {      // last column: reflect101(w) = w-2 = column x+j-1 = the left neighbour
+            r0 = l0; r1 = l1; r2 = l2;
+        }
+        const int gx = (r0 - l0) + 2 * (r1 - l1) + (r2 - l2);
+        const int gy = (l2 - l0) + 2 * (c2 - c0) + (r2 - r0);
+        o[j] = make_short2((short)gx, (short)gy);
+    }
+    short2* d = dst + (size_t)img * w * h + (size_t)y * w + x;
+    if (x + 3 < w && (w & 3) == 0) {
+        *reinterpret_cast<uint4*>(d) = make_uint4(*reinterpret_cast<unsigned*>(&o[0]), *reinterpret_cast<unsigned*>(&o[1]),
+                                                  *reinterpret_cast<unsigned*>(&o[2]), *reinterpret_cast<unsigned*>(&o[3]));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (x + j < w) d[j] = o[j];
+    }
 }
 
 // One warp per line.  Lane = row hID of the 63-row line support region (two passes of 32): each lane walks its row
@@ -857,7 +891,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     plf_mark(c, "lbd_blur_sobel");
     const int lt[5] = {14, 62, 104, 62, 14};
     blur_image_kernel<<<dim3(tiles, nImg), dim3(32, 8), 0, s>>>(in, inStride, ip, c->d_lbdBlur, imgBytes, ip, g.W, g.H, imgFirst, 0, lt[0], lt[1], lt[2], lt[3], lt[4], 0);
-    sobel_kernel<<<dim3((g.W + 31) / 32, (g.H + 7) / 8, nImg), dim3(32, 8), 0, s>>>(c->d_lbdBlur, imgBytes, ip, c->d_sobel, g.W, g.H, imgFirst);
+    sobel_kernel<<<dim3((g.W + 127) / 128, (g.H + 7) / 8, nImg), dim3(32, 8), 0, s>>>(c->d_lbdBlur, imgBytes, ip, c->d_sobel, g.W, g.H, imgFirst);
     plf_mark(c, "lbd_descriptor");
     lbd_kernel<<<dim3((g.klCap + 3) / 4, nImg), 128, 0, s>>>(g, c->d_sobel, c->d_kl, c->d_nKl, c->d_lbd, c->d_ldesc, imgFirst);
     return launches + 8;

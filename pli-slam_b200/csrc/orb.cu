@@ -196,84 +196,114 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
     }
 }
 
-#define FAST_MAXW 72   // window side limit: wCell+6 < 2*30+6
-__global__ void __launch_bounds__(128) fast_cells_kernel(PlfGeom g, const uint8_t* score, const PlfCell* cells,
-                                                         int* cellCount, uint32_t* cand, int imgFirst) {
-    __shared__ uint8_t s_sc[(FAST_MAXW - 6) * (FAST_MAXW - 6)];
-    __shared__ uint8_t s_keep[(FAST_MAXW - 6) * (FAST_MAXW - 6)];
-    __shared__ int s_warp[4];
-    const PlfCell c = cells[blockIdx.x];
+#define FC_WARPS 4
+#define FC_PITCH 20    // words per staged row: detection areas are <= 66 px wide (window <= 72, checked at plf_create),
+#define FC_ROWS 68     // i.e. <= 18 aligned words, plus one zero word / zero row on every side
+// One warp per cell.  The detection areas of a level tile it without overlap, so every score byte is read once, as
+// aligned 32-bit words whose bytes outside the area are masked to 0 (FAST on the sub-image never sees them).  Scores
+// are sparse: only non-zero words do the 3x3 strict-maximum test (byte-SIMD compares against the 8 shifted neighbour
+// words), survivors are appended in raster order with two ballots (strict NMS leaves at most 2 per word), and the
+// iniTh/minTh choice of src/ORBextractor.cc:806-827 becomes an in-place ordered filter of that short list.
+__global__ void __launch_bounds__(32 * FC_WARPS) fast_cells_kernel(PlfGeom g, const uint8_t* score, const PlfCell* cells,
+                                                                   int* cellCount, uint32_t* cand, int imgFirst) {
+    __shared__ unsigned s_all[FC_WARPS][FC_ROWS * FC_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ci = blockIdx.x * FC_WARPS + warp;
+    if (ci >= g.nCellsTotal) return;                 // warp-uniform; no block-level barrier below
+    const PlfCell c = cells[ci];
     const int img = imgFirst + blockIdx.y;
     const PlfLevel& lv = g.lv[c.level];
-    const uint8_t* src = score + (size_t)img * g.pyrBytes + lv.off + 1;     // score(x,y) lives at byte x+1
     const int aw = c.x1 - c.x0 - 6, ah = c.y1 - c.y0 - 6;     // detection area of cv::FAST on the window
-    const int tid = threadIdx.x;
-    int* outCount = cellCount + (size_t)img * g.nCellsTotal + blockIdx.x;
+    int* outCount = cellCount + (size_t)img * g.nCellsTotal + ci;
     if (aw <= 0 || ah <= 0) {
-        if (tid == 0) *outCount = 0;
+        if (lane == 0) *outCount = 0;
         return;
     }
-    const int n = aw * ah;
-    const unsigned magic = (unsigned)c.magic;      // i / aw == (i * magic) >> 20 for every i < n (checked at plf_create)
-    for (int i = tid; i < n; i += 128) {
-        const int y = (int)(((unsigned)i * magic) >> 20), x = i - y * aw;
-        s_sc[i] = src[(size_t)(c.y0 + 3 + y) * lv.pitch + c.x0 + 3 + x];
-    }
-    __syncthreads();
-    const int iniTh = g.iniTh, minTh = g.minTh;
-    bool anyIni = false;
-    for (int i = tid; i < n; i += 128) {
-        const int y = (int)(((unsigned)i * magic) >> 20), x = i - y * aw;
-        const int s = s_sc[i];
-        bool keep = s > 0;
-        if (keep) {
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    if (dx == 0 && dy == 0) continue;
-                    const int yy = y + dy, xx = x + dx;
-                    const int nb = (yy < 0 || xx < 0 || yy >= ah || xx >= aw) ? 0 : s_sc[yy * aw + xx];
-                    keep = keep && (s > nb);
-                }
+    unsigned* sw = s_all[warp];
+    const int bx0 = c.x0 + 4;                        // score(x, y) lives at byte x+1 of its row
+    const int wb0 = bx0 >> 2, nw = ((bx0 + aw + 3) >> 2) - wb0, pw = nw + 2;
+    const unsigned maskFirst = 0xFFFFFFFFu << (8 * (bx0 & 3));
+    const unsigned maskLast = ((bx0 + aw) & 3) ? (0xFFFFFFFFu >> (8 * (4 - ((bx0 + aw) & 3)))) : 0xFFFFFFFFu;
+    const unsigned* src = reinterpret_cast<const unsigned*>(score + (size_t)img * g.pyrBytes + lv.off) +
+                          (size_t)(c.y0 + 3) * (lv.pitch >> 2) + wb0;
+    const int pitchW = lv.pitch >> 2;
+    {
+        const unsigned inv = (65536u + pw - 1) / pw;          // i / pw == (i * inv) >> 16 for i < 68 * 20
+        const int n = (ah + 2) * pw;
+        for (int i = lane; i < n; i += 32) {
+            const int r = (int)(((unsigned)i * inv) >> 16), wx = i - r * pw;
+            unsigned v = 0u;
+            if (r >= 1 && r <= ah && wx >= 1 && wx <= nw) {
+                v = src[(size_t)(r - 1) * pitchW + (wx - 1)];
+                if (wx == 1) v &= maskFirst;
+                if (wx == nw) v &= maskLast;
+            }
+            sw[i] = v;
         }
-        s_keep[i] = keep ? 1 : 0;
-        anyIni |= keep && s >= iniTh;
     }
-    const int th = __syncthreads_or(anyIni) ? iniTh : minTh;
-    // ordered (raster) compaction: each thread owns a contiguous run of pixels
-    const int per = (n + 127) / 128;
-    const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
-    int cnt = 0;
-    for (int i = i0; i < i1; ++i) cnt += (s_keep[i] && s_sc[i] >= th);
-    const int lane = tid & 31, warp = tid >> 5;
-    int inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        if (w < warp) base += s_warp[w];
-        total += s_warp[w];
-    }
-    int pos = base + inc - cnt;
+    __syncwarp();
     uint32_t* out = cand + (size_t)img * g.candCapTotal + c.outBase;
-    const int relx = c.x0 + 3 - PLF_MINB, rely = c.y0 + 3 - PLF_MINB;
-    for (int i = i0; i < i1; ++i) {
-        const int s = s_sc[i];
-        if (s_keep[i] && s >= th) {
-            const int y = (int)(((unsigned)i * magic) >> 20), x = i - y * aw;
-            if (pos < c.cap) out[pos] = (uint32_t)(relx + x) | ((uint32_t)(rely + y) << 12) | ((uint32_t)s << 24);
-            ++pos;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned ini4 = (unsigned)g.iniTh * 0x01010101u;
+    const int yBase = c.y0 + 3 - PLF_MINB;
+    int total = 0;
+    bool anyIni = false;
+    {
+        const unsigned inv = (65536u + nw - 1) / nw;
+        const int n = ah * nw, nIter = (n + 31) >> 5;
+        for (int it = 0; it < nIter; ++it) {
+            const int i = it * 32 + lane;
+            int r = 0, wx = 0;
+            unsigned W = 0u;
+            if (i < n) {
+                r = (int)(((unsigned)i * inv) >> 16); wx = i - r * nw;
+                W = sw[(r + 1) * pw + wx + 1];
+            }
+            if (__ballot_sync(0xffffffffu, W != 0u) == 0u) continue;
+            unsigned K = 0u;
+            if (W) {
+                const unsigned* q = sw + r * pw + wx;             // top-left neighbour word
+                unsigned keep = __vcmpgtu4(W, 0u);
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    const unsigned a = q[dy * pw], m = q[dy * pw + 1], b = q[dy * pw + 2];
+                    keep &= __vcmpgtu4(W, __funnelshift_r(a, m, 24));   // x-1
+                    keep &= __vcmpgtu4(W, __funnelshift_r(m, b, 8));    // x+1
+                    if (dy != 1) keep &= __vcmpgtu4(W, m);
+                }
+                K = W & keep;
+            }
+            const int cnt = __popc(__vcmpgtu4(K, 0u) & 0x01010101u);
+            const unsigned b1 = __ballot_sync(0xffffffffu, cnt >= 1), b2 = __ballot_sync(0xffffffffu, cnt >= 2);
+            if (cnt) {
+                anyIni |= __vcmpgeu4(K, ini4) != 0u;
+                int pos = total + __popc(b1 & lt) + __popc(b2 & lt);
+                const int x = 4 * (wb0 + wx) - 1 - PLF_MINB;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned sv = (K >> (8 * j)) & 0xFFu;
+                    if (sv) out[pos++] = (uint32_t)(x + j) | ((uint32_t)(yBase + r) << 12) | (sv << 24);
+                }
+            }
+            total += __popc(b1) + __popc(b2);
         }
     }
-    if (tid == 0) *outCount = min(total, c.cap);
-    (void)minTh;
+    // scores below minTh were stored as 0, so the list already is the minTh result; iniTh keeps its >= iniTh subset
+    if (__any_sync(0xffffffffu, anyIni) && g.iniTh > g.minTh) {
+        __syncwarp();
+        int wpos = 0;
+        for (int base = 0; base < total; base += 32) {
+            const int i = base + lane;
+            const uint32_t v = i < total ? out[i] : 0u;
+            const bool k = (int)(v >> 24) >= g.iniTh;
+            const unsigned b = __ballot_sync(0xffffffffu, k);
+            if (k) out[wpos + __popc(b & lt)] = v;
+            wpos += __popc(b);
+            __syncwarp();
+        }
+        total = wpos;
+    }
+    if (lane == 0) *outCount = total;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -738,7 +768,7 @@ int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1) {
     blur_pyramid_kernel<<<dim3(c->nTilesBlur, nImg), dim3(32, 8), 0, s>>>(g, c->d_pyr, c->d_blur, c->d_tilesBlur, imgFirst);
     plf_mark(c, "orb_fast");
     fast_score_kernel<<<dim3(c->nTilesFast, nImg), dim3(32, 8), 0, s>>>(g, c->d_pyr, c->d_score, c->d_tilesFast, imgFirst);
-    fast_cells_kernel<<<dim3(g.nCellsTotal, nImg), 128, 0, s>>>(g, c->d_score, c->d_cells, c->d_cellCount, c->d_cand,
+    fast_cells_kernel<<<dim3((g.nCellsTotal + FC_WARPS - 1) / FC_WARPS, nImg), 32 * FC_WARPS, 0, s>>>(g, c->d_score, c->d_cells, c->d_cellCount, c->d_cand,
                                                                imgFirst);
     int maxQ = 0;
     for (int l = 0; l < g.nLevels; ++l) maxQ = max(maxQ, max(g.lv[l].quota, 4 * g.lv[l].nIni));

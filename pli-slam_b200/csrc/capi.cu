@@ -174,7 +174,7 @@ static int build_geometry(plf_ctx* c, std::vector<PlfCell>& cells) {
     } else {
         g.lsdK = 0; g.Ws = p.width; g.Hs = p.height;
     }
-    g.Ps = (g.Ws + 63) & ~63;
+    g.Ps = (g.Ws + 127) & ~127;
     {
         const double logNT = 5 * (std::log10((double)g.Ws) + std::log10((double)g.Hs)) / 2 + std::log10(11.0);
         g.minRegSize = (int)(size_t)(-logNT / std::log10(p.lsd_ang_th / 180));
@@ -294,7 +294,8 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
         PLF_CUDA_OK(dalloc(&c->d_n2max, nImg));
         PLF_CUDA_OK(dalloc(&c->d_seeds, nImg * (size_t)g.seedCap));
         PLF_CUDA_OK(dalloc(&c->d_nSeeds, nImg));
-        PLF_CUDA_OK(dalloc(&c->d_used, nImg * ((npx + 31) / 32)));
+        PLF_CUDA_OK(dalloc(&c->d_n2, nImg * (size_t)g.Ps * g.Hs));
+        PLF_CUDA_OK(dalloc(&c->d_used, nImg * (size_t)(g.Ps / 32) * g.Hs));
         PLF_CUDA_OK(dalloc(&c->d_reg, nImg * npx));
         PLF_CUDA_OK(dalloc(&c->d_segs, nImg * (size_t)g.segCap * 4));
         PLF_CUDA_OK(dalloc(&c->d_nSegs, nImg));
@@ -329,7 +330,7 @@ PLF_API int plf_destroy(plf_ctx* c) {
     void* ptrs[] = {c->d_pyr, c->d_blur, c->d_score, c->d_tilesBlur, c->d_tilesFast, c->d_lin, c->d_cells, c->d_cellCount, c->d_cand, c->d_scratch, c->d_lvlKp, c->d_lvlN,
                     c->d_kpTmp, c->d_descTmp, c->d_kp, c->d_desc, c->d_nKp, c->d_mono, c->d_err, c->d_uRight, c->d_depth,
                     c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_rec, c->d_n2max, c->d_seeds,
-                    c->d_nSeeds, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
+                    c->d_nSeeds, c->d_n2, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
                     c->d_sobel, c->d_lbd, c->d_ldesc, c->d_rowMask, c->d_dirR, c->d_dmat, c->d_m21, c->d_m12, c->d_disp,
                     c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -575,7 +576,12 @@ PLF_API int plf_tap_lsd_angles(plf_ctx* c, int slot, int side, float* out, int* 
     PLF_CUDA_OK(cudaSetDevice(c->device));
     const size_t npx = (size_t)c->g.Ws * c->g.Hs;
     PLF_CUDA_OK(cudaMemcpy2DAsync(out, 4, c->d_rec + (size_t)(slot * 2 + side) * npx, 16, 4, npx, cudaMemcpyDeviceToHost, c->stream));
+    // records exist only for defined pixels; the |g|^2 map (0 = undefined) says which ones those are
+    std::vector<int> n2(npx);
+    PLF_CUDA_OK(cudaMemcpy2DAsync(n2.data(), (size_t)c->g.Ws * 4, c->d_n2 + (size_t)(slot * 2 + side) * c->g.Ps * c->g.Hs, (size_t)c->g.Ps * 4,
+                                  (size_t)c->g.Ws * 4, c->g.Hs, cudaMemcpyDeviceToHost, c->stream));
     PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < npx; ++i) if (n2[i] == 0) out[i] = PLF_NOTDEF;
     return PLF_OK;
 }
 PLF_API int plf_tap_lsd_segments(plf_ctx* c, int slot, int side, float* xyxy, int cap, int* n) {

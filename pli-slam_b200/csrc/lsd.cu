@@ -55,11 +55,12 @@ __global__ void __launch_bounds__(256) lsd_upscale_kernel(PlfGeom g, const uint8
 // ---------------------------------------------------------------------------------------------------------------
 // K4b  level-line field (LSD ll_angle): 2x2 gradient, squared norm, fastAtan2 angle (degrees), cosf/sinf of the angle,
 // per-image max of the squared norm over defined pixels.
-__global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, float4* rec, int* n2max, int imgFirst) {
-    // Two phases per 128x8 tile, 4 horizontally adjacent pixels per thread (aligned 32-bit loads of the u8 image, 64
-    // contiguous bytes of records written per thread):
+__global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, float4* rec, int* n2map, uint32_t* used,
+                                                       int* n2max, int imgFirst) {
+    // Two phases per 128x8 tile, 4 horizontally adjacent pixels per thread (aligned 32-bit loads of the u8 image, one
+    // 16-byte store of the |g|^2 map per thread, one bitmap word per 8 threads):
     // (1) 2x2 gradient and |g|^2; a pixel is defined iff |g|^2 > n2Thresh, the integer image of LSD's "norm > rho" test
-    //     (exact: host-searched with the same IEEE sqrt).  Undefined pixels are written at once, defined ones queued.
+    //     (exact: host-searched with the same IEEE sqrt).  Undefined pixels get no record; defined ones are queued.
     // (2) the queue is processed densely, one defined pixel per thread, so the expensive part (fastAtan2 + double
     //     sincos) costs in proportion to the defined pixels, not to the warps that happen to contain one.
     __shared__ int s_cnt;
@@ -71,35 +72,42 @@ __global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t*
     __syncthreads();
     const size_t base = (size_t)img * g.Ws * g.Hs;
     int best = 0;
-    if (x < g.Ws && y < g.Hs) {
-        const uint8_t* r0 = U + (size_t)img * g.Ps * g.Hs + (size_t)y * g.Ps + x;
-        const uint8_t* r1 = r0 + (y + 1 < g.Hs ? g.Ps : 0);
-        // bytes x .. x+4 of both rows (the row pitch is padded, the 5th byte is only used when x+4 < Ws)
-        const unsigned a0 = *reinterpret_cast<const unsigned*>(r0), b0 = *reinterpret_cast<const unsigned*>(r1);
-        const unsigned a1 = (x + 4 < g.Ps) ? *reinterpret_cast<const unsigned*>(r0 + 4) : 0u;
-        const unsigned b1 = (x + 4 < g.Ps) ? *reinterpret_cast<const unsigned*>(r1 + 4) : 0u;
-        float4* out = rec + base + (size_t)y * g.Ws + x;
+    if (y < g.Hs) {                                    // warp-uniform: a warp is one row of the tile
+        int n2v[4] = {0, 0, 0, 0};
+        if (x < g.Ws) {
+            const uint8_t* r0 = U + (size_t)img * g.Ps * g.Hs + (size_t)y * g.Ps + x;
+            const uint8_t* r1 = r0 + (y + 1 < g.Hs ? g.Ps : 0);
+            // bytes x .. x+4 of both rows (the row pitch is padded, the 5th byte is only used when x+4 < Ws)
+            const unsigned a0 = *reinterpret_cast<const unsigned*>(r0), b0 = *reinterpret_cast<const unsigned*>(r1);
+            const unsigned a1 = (x + 4 < g.Ps) ? *reinterpret_cast<const unsigned*>(r0 + 4) : 0u;
+            const unsigned b1 = (x + 4 < g.Ps) ? *reinterpret_cast<const unsigned*>(r1 + 4) : 0u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (x + j >= g.Ws) break;
-            int n2 = 0, gx = 0, gy = 0;
-            if (x + j < g.Ws - 1 && y < g.Hs - 1) {
-                const int pa = (a0 >> (8 * j)) & 0xFF;                                             // (x, y)
-                const int pb = j < 3 ? (a0 >> (8 * j + 8)) & 0xFF : a1 & 0xFF;                     // (x+1, y)
-                const int pc = (b0 >> (8 * j)) & 0xFF;                                             // (x, y+1)
-                const int pd = j < 3 ? (b0 >> (8 * j + 8)) & 0xFF : b1 & 0xFF;                     // (x+1, y+1)
-                const int DA = pd - pa, BC = pb - pc;
-                gx = DA + BC;
-                gy = DA - BC;
-                n2 = gx * gx + gy * gy;
-            }
-            if (n2 > g.n2Thresh) {
-                s_q[atomicAdd(&s_cnt, 1)] = (threadIdx.y << 7) | (threadIdx.x * 4 + j) | ((gx + 1024) << 10) | ((gy + 1024) << 21);
-                best = max(best, n2);
-            } else {
-                out[j] = make_float4(PLF_NOTDEF, 0.f, 0.f, __int_as_float(n2));
+            for (int j = 0; j < 4; ++j) {
+                if (x + j < g.Ws - 1 && y < g.Hs - 1) {
+                    const int pa = (a0 >> (8 * j)) & 0xFF;                                             // (x, y)
+                    const int pb = j < 3 ? (a0 >> (8 * j + 8)) & 0xFF : a1 & 0xFF;                     // (x+1, y)
+                    const int pc = (b0 >> (8 * j)) & 0xFF;                                             // (x, y+1)
+                    const int pd = j < 3 ? (b0 >> (8 * j + 8)) & 0xFF : b1 & 0xFF;                     // (x+1, y+1)
+                    const int DA = pd - pa, BC = pb - pc;
+                    const int gx = DA + BC, gy = DA - BC;
+                    const int n2 = gx * gx + gy * gy;
+                    if (n2 > g.n2Thresh) {
+                        s_q[atomicAdd(&s_cnt, 1)] = (threadIdx.y << 7) | (threadIdx.x * 4 + j) | ((gx + 1024) << 10) | ((gy + 1024) << 21);
+                        best = max(best, n2);
+                        n2v[j] = n2;
+                    }
+                }
             }
         }
+        // |g|^2 map (0 = undefined) and the grower's bitmap with the undefined pixels pre-marked as used: undefined
+        // pixels need no record at all, and the grower never loads one for them
+        *reinterpret_cast<int4*>(n2map + (size_t)img * g.Ps * g.Hs + (size_t)y * g.Ps + x) = make_int4(n2v[0], n2v[1], n2v[2], n2v[3]);
+        unsigned w = ((n2v[0] == 0) | ((n2v[1] == 0) << 1) | ((n2v[2] == 0) << 2) | ((n2v[3] == 0) << 3)) << (4 * (threadIdx.x & 7));
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        if ((threadIdx.x & 7) == 0)
+            used[((size_t)img * g.Hs + y) * (g.Ps >> 5) + blockIdx.x * 4 + (threadIdx.x >> 3)] = w;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -130,7 +138,7 @@ __device__ __forceinline__ double lsd_bin_coef(int n2max, int nBins) {
 // shared memory, pass 2 turns the counts into write cursors (bins descending, then warps ascending), pass 3 lets every
 // warp walk its segment again and place its pixels: lanes of one 32-pixel step that share a bin are ranked with
 // __match_any_sync, so the order inside a bin is raster order by construction and no warp waits for another.
-__global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float4* rec, const int* n2max, int* seeds,
+__global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const int* n2map, const int* n2max, int* seeds,
                                                          int* nSeeds, int imgFirst) {
     extern __shared__ int s_cur[];          // [32][nBins]
     __shared__ int s_scan[32];
@@ -139,17 +147,19 @@ __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float4
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nBins = g.nBins;
     const double coef = lsd_bin_coef(n2max[img], nBins);
-    const size_t base = (size_t)img * g.Ws * g.Hs;
-    const int npx = g.Ws * g.Hs;
+    // raster walk over the pitched |g|^2 map: the padding columns hold 0 (undefined) and cost one compare
+    const int npx = g.Ps * g.Hs;
     const int segLen = ((npx + 31) / 32 + 31) & ~31;
     const int p0 = warp * segLen, p1 = min(p0 + segLen, npx);
+    const int* N2 = n2map + (size_t)img * npx;
     int* mine = s_cur + warp * nBins;
     for (int i = tid; i < 32 * nBins; i += 1024) s_cur[i] = 0;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    const float* recf = reinterpret_cast<const float*>(rec + base);       // record = (angle, cos, sin, |g|^2 bits)
-    for (int p = p0 + lane; p < p1; p += 32)
-        if (recf[4 * (size_t)p] != PLF_NOTDEF) atomicAdd(&mine[lsd_bin(__float_as_int(recf[4 * (size_t)p + 3]), coef)], 1);
+    for (int p = p0 + lane; p < p1; p += 32) {
+        const int v = N2[p];
+        if (v) atomicAdd(&mine[lsd_bin(v, coef)], 1);
+    }
     __syncthreads();
     // cursors: for bins in descending order, for warps in ascending order
     for (int b0 = 0; b0 < nBins; b0 += 1024) {
@@ -182,12 +192,12 @@ __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const float4
     if (tid == 0) nSeeds[img] = s_carry;
     int* out = seeds + (size_t)img * g.seedCap;
     const unsigned lt = (1u << lane) - 1u;
-    const int W = g.Ws;
+    const int W = g.Ps;
     for (int pb = p0; pb < p1; pb += 32) {
         const int p = pb + lane;
-        bool def = false;
-        int bin = 0;
-        if (p < p1 && recf[4 * (size_t)p] != PLF_NOTDEF) { def = true; bin = lsd_bin(__float_as_int(recf[4 * (size_t)p + 3]), coef); }
+        const int v = p < p1 ? N2[p] : 0;
+        const bool def = v != 0;
+        const int bin = def ? lsd_bin(v, coef) : 0;
         const unsigned wm = __ballot_sync(0xffffffffu, def);
         if (def) {
             const unsigned grp = __match_any_sync(wm, bin);
@@ -235,51 +245,109 @@ __device__ __forceinline__ void seq_sum3(double (*buf)[33], double a, double b, 
 struct GrowState {
     int n;            // region size
     float sumdx, sumdy;
-    double regAngle;
+    double regAngle;  // exact angle of (sumdx, sumdy) unless `dirty`
+    bool dirty;
 };
 
 struct GrowCtx {
     const float4* REC;
     uint32_t* used;
+    const int* N2;   // pitched |g|^2 map
     int* R;
     int* ring;
-    int W, H, lane, ddx, ddy;
+    int W, H, PB, lane, ddx, ddy;   // PB: bits per bitmap row (= pitch of N2)
 };
 
+// q is a BIT index, y * PB + x
 __device__ __forceinline__ bool used_bit(const uint32_t* used, int q) {
     // plain (L1-cached) load: the bitmap is only updated by this warp's own SM (stores/atomics keep the SM's L1
     // coherent, __syncwarp orders them), and re-reading L1 hits is what keeps the batch preamble short
     return (used[q >> 5] >> (q & 31)) & 1u;
 }
 
-// resolves one set of 32 candidates (lane order = processing order); `valid` lanes hold pixel q (packed pk) with record r
+// LSD isAligned(): |theta - a|, folded once around 2*pi, <= tolerance  (branch-free, same arithmetic)
+__device__ __forceinline__ bool lsd_aligned(double theta, double a, double tol) {
+    double nd = fabs(__dsub_rn(theta, a));
+    const double nw = fabs(__dsub_rn(nd, 2 * kPi));
+    nd = (nd > (3 * kPi) / 2) ? nw : nd;
+    return nd <= tol;
+}
+
+// Resolves one set of 32 candidates (lane order = processing order); `valid` lanes hold pixel q (packed pk) with
+// record r.  The sequential rule — a candidate is tested against the region angle left by every acceptance before it
+// — is evaluated speculatively, all lanes at once: predict the accepted set A with the current exact angle, let every
+// lane rebuild the running sums it would see (the float additions of the A-lanes below it, in lane order: the scalar
+// loop's chain, bit for bit), take its own fastAtan2 and test itself.  Up to and including the first lane whose test
+// contradicts the prediction every lane has seen the true state, so those decisions are final; they are committed in
+// one SIMD step and the rest goes round again.  The angle drifts slowly, so one round usually settles a set:
+// ~100 + 9/accepted-pixel warp instructions per round instead of ~95 per accepted pixel.
 __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int pk, const float4& r, double tol,
                                            const GrowCtx& c) {
     unsigned pending = __ballot_sync(0xffffffffu, valid);
     if (!pending) return;
-    const unsigned dup = __match_any_sync(0xffffffffu, valid ? q : -1 - c.lane);
+    const unsigned dup = __match_any_sync(0xffffffffu, valid ? q : -1 - c.lane);   // lanes holding my pixel
     const double aRad = (double)r.x * kDegToRad;
+    const unsigned myBit = 1u << c.lane, lt = myBit - 1u;
     while (pending) {
-        // LSD isAligned(): |theta - a|, folded once around 2*pi, <= tolerance  (branch-free, same arithmetic)
-        double nd = fabs(__dsub_rn(st.regAngle, aRad));
-        const double nw = fabs(__dsub_rn(nd, 2 * kPi));
-        nd = (nd > (3 * kPi) / 2) ? nw : nd;
-        const unsigned am = __ballot_sync(0xffffffffu, nd <= tol) & pending;
-        if (!am) break;
-        const int Lw = __ffs(am) - 1;
-        const int pkL = __shfl_sync(0xffffffffu, pk, Lw);
-        const float cx = __shfl_sync(0xffffffffu, r.y, Lw), cy = __shfl_sync(0xffffffffu, r.z, Lw);
-        const unsigned dupL = __shfl_sync(0xffffffffu, dup, Lw);
-        if (c.lane == Lw) atomicOr(c.used + (q >> 5), 1u << (q & 31));
-        if (c.lane == 0) {
-            c.ring[st.n & (GROW_RING - 1)] = pkL;
-            c.R[st.n] = pkL;
+        if (st.dirty) {
+            st.regAngle = (double)fast_atan2_deg(st.sumdy, st.sumdx) * kDegToRad;
+            st.dirty = false;
         }
-        ++st.n;
-        st.sumdx = __fadd_rn(st.sumdx, cx);
-        st.sumdy = __fadd_rn(st.sumdy, cy);
-        st.regAngle = (double)fast_atan2_deg(st.sumdy, st.sumdx) * kDegToRad;
-        pending &= ~((2u << Lw) - 1u) & ~dupL;
+        const bool mine = (pending & myBit) != 0u;
+        const unsigned am = __ballot_sync(0xffffffffu, mine && lsd_aligned(st.regAngle, aRad, tol));
+        if (!am) break;
+        // prediction: the aligned lanes, first instance of every pixel only (a later instance finds it used)
+        const bool pred = (am & myBit) && !(dup & lt & am);
+        const unsigned A = __ballot_sync(0xffffffffu, pred);
+        const bool shadowed = (dup & lt & A) != 0u;
+        // a lane outside the set (if any) accumulates all of A: the state after the set if the prediction holds
+        const unsigned spare = ~pending;
+        const int v = spare ? 31 - __clz(spare) : -1;
+        float sx = st.sumdx, sy = st.sumdy;
+        for (unsigned m = A; m; m &= m - 1u) {
+            const int b = __ffs(m) - 1;
+            const float cxb = __shfl_sync(0xffffffffu, r.y, b), cyb = __shfl_sync(0xffffffffu, r.z, b);
+            if (c.lane > b || c.lane == v) {
+                sx = __fadd_rn(sx, cxb);
+                sy = __fadd_rn(sy, cyb);
+            }
+        }
+        // lanes below the first A-lane still see the current state: its angle is st.regAngle (for a fresh region
+        // that is the seed's angle, not the arctangent of the sums)
+        const double ang = ((A & lt) || c.lane == v) ? (double)fast_atan2_deg(sy, sx) * kDegToRad : st.regAngle;
+        const bool t = mine && !shadowed && lsd_aligned(ang, aRad, tol);
+        const unsigned mm = __ballot_sync(0xffffffffu, mine && (t != pred));
+        unsigned acc;
+        int e;
+        if (mm == 0u) {
+            acc = A;
+            e = 31 - __clz(A);
+        } else {
+            e = __ffs(mm) - 1;
+            const unsigned tb = __ballot_sync(0xffffffffu, t);
+            acc = (A & ((1u << e) - 1u)) | (tb & (1u << e));
+        }
+        if (acc & myBit) {
+            const int at = st.n + __popc(acc & lt);
+            c.ring[at & (GROW_RING - 1)] = pk;
+            c.R[at] = pk;
+            atomicOr(c.used + (q >> 5), 1u << (q & 31));
+        }
+        st.n += __popc(acc);
+        float ex = __shfl_sync(0xffffffffu, sx, e), ey = __shfl_sync(0xffffffffu, sy, e);
+        if ((acc >> e) & 1u) {
+            ex = __fadd_rn(ex, __shfl_sync(0xffffffffu, r.y, e));
+            ey = __fadd_rn(ey, __shfl_sync(0xffffffffu, r.z, e));
+        }
+        st.sumdx = ex;
+        st.sumdy = ey;
+        if (mm == 0u) {
+            if (v >= 0) st.regAngle = __shfl_sync(0xffffffffu, ang, v); else st.dirty = true;
+            break;
+        }
+        st.dirty = true;
+        const unsigned dupAcc = __reduce_or_sync(0xffffffffu, (acc & myBit) ? dup : 0u);
+        pending &= ~((2u << e) - 1u) & ~dupAcc;
     }
 }
 
@@ -288,8 +356,12 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
 __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, double tol, double& regAngleOut) {
     GrowState st;
     st.n = 1;
-    if (c.lane == 0) { c.ring[0] = pk0; c.R[0] = pk0; atomicOr(c.used + (p >> 5), 1u << (p & 31)); }
+    if (c.lane == 0) {
+        const int pb = (pk0 >> 16) * c.PB + (pk0 & 0xFFFF);
+        c.ring[0] = pk0; c.R[0] = pk0; atomicOr(c.used + (pb >> 5), 1u << (pb & 31));
+    }
     st.regAngle = (double)c.REC[p].x * kDegToRad;
+    st.dirty = false;
     {
         double sn, cs;
         sincos(st.regAngle, &sn, &cs);
@@ -315,11 +387,11 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, dou
                 const int rp = inRing ? c.ring[(i + e) & (GROW_RING - 1)] : c.R[i + e];
                 const int xx = (rp & 0xFFFF) + c.ddx, yy = (rp >> 16) + c.ddy;
                 if (xx >= 0 && yy >= 0 && xx < c.W && yy < c.H) {
-                    q[s] = yy * c.W + xx;
+                    q[s] = yy * c.PB + xx;
                     pk[s] = (yy << 16) | xx;
-                    if (!used_bit(c.used, q[s])) {
-                        r[s] = c.REC[q[s]];
-                        valid[s] = r[s].x != PLF_NOTDEF;
+                    if (!used_bit(c.used, q[s])) {        // unused implies defined: undefined pixels start as used
+                        r[s] = c.REC[yy * c.W + xx];
+                        valid[s] = true;
                     }
                 }
             }
@@ -334,7 +406,7 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, dou
         }
         i += nb;
     }
-    regAngleOut = st.regAngle;
+    regAngleOut = st.dirty ? (double)fast_atan2_deg(st.sumdy, st.sumdx) * kDegToRad : st.regAngle;
     return st.n;
 }
 
@@ -343,7 +415,7 @@ struct RectFit { double x1, y1, x2, y2, width; };
 // LSD region2rect + get_theta over c.R[0..n): scalar-loop summation order for the weighted sums
 template <bool WIDTH>
 __device__ __forceinline__ void rect_fit(const GrowCtx& c, double (*s_sum)[33], int n, double regAngle, double prec, RectFit& rf) {
-    const int lane = c.lane, W = c.W;
+    const int lane = c.lane;
     double acc3 = 0;      // lane 0: sum x*w, lane 1: sum y*w, lane 2: sum w
     for (int i0 = 0; i0 < n; i0 += 32) {
         const unsigned cnt = min(32, n - i0);
@@ -351,7 +423,7 @@ __device__ __forceinline__ void rect_fit(const GrowCtx& c, double (*s_sum)[33], 
         if (lane < cnt) {
             const int rp = c.R[i0 + lane];
             const int ry = rp >> 16, rx = rp & 0xFFFF;
-            wv = sqrt((double)__float_as_int(c.REC[ry * W + rx].w) / 4.0);
+            wv = sqrt((double)c.N2[ry * c.PB + rx] / 4.0);
             xw = __dmul_rn((double)rx, wv);
             yw = __dmul_rn((double)ry, wv);
         }
@@ -366,7 +438,7 @@ __device__ __forceinline__ void rect_fit(const GrowCtx& c, double (*s_sum)[33], 
         if (lane < cnt) {
             const int rp = c.R[i0 + lane];
             const int ry = rp >> 16, rx = rp & 0xFFFF;
-            const double wv = sqrt((double)__float_as_int(c.REC[ry * W + rx].w) / 4.0);
+            const double wv = sqrt((double)c.N2[ry * c.PB + rx] / 4.0);
             const double dx = __dsub_rn((double)rx, cxm), dy = __dsub_rn((double)ry, cym);
             vxx = __dmul_rn(__dmul_rn(dy, dy), wv);
             vyy = __dmul_rn(__dmul_rn(dx, dx), wv);
@@ -450,8 +522,8 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[33], int& n, double
         bool in = false;
         if (lane < cnt) {
             const int rp = c.R[i0 + lane];
-            const int ry = rp >> 16, rx = rp & 0xFFFF, q = ry * W + rx;
-            atomicAnd(c.used + (q >> 5), ~(1u << (q & 31)));                      // *(reg[i].used) = NOTUSED
+            const int ry = rp >> 16, rx = rp & 0xFFFF, q = ry * W + rx, qb = ry * c.PB + rx;
+            atomicAnd(c.used + (qb >> 5), ~(1u << (qb & 31)));                    // *(reg[i].used) = NOTUSED
             if (lsd_dist(xc, yc, (double)rx, (double)ry) < rf.width) {
                 double d = __dsub_rn((double)c.REC[q].x * kDegToRad, angC);         // angle_diff_signed
                 while (d <= -kPi) d += 2 * kPi;
@@ -487,7 +559,7 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[33], int& n, double
                 const int rp = c.R[i];
                 const int ry = rp >> 16, rx = rp & 0xFFFF;
                 if (lsd_dist_sq(xc, yc, (double)rx, (double)ry) > radSq) {
-                    const int q = ry * W + rx;
+                    const int q = ry * c.PB + rx;
                     atomicAnd(c.used + (q >> 5), ~(1u << (q & 31)));
                     c.R[i] = c.R[sz - 1];
                     --sz;
@@ -505,17 +577,18 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[33], int& n, double
 }
 
 template <bool REFINE>
-__global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* rec, const int* seeds, const int* nSeeds,
-                                                      uint32_t* usedAll, int* reg, float* segs, int* nSegsOut, int* err,
-                                                      int nWords, int imgFirst) {
+__global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* rec, const int* n2map, const int* seeds,
+                                                      const int* nSeeds, uint32_t* usedAll, int* reg, float* segs,
+                                                      int* nSegsOut, int* err, int imgFirst) {
     __shared__ int ring[GROW_RING];
     __shared__ double s_sum[3][33];
     const int img = imgFirst + blockIdx.x, lane = threadIdx.x;
     GrowCtx c;
-    c.W = g.Ws; c.H = g.Hs; c.lane = lane;
+    c.W = g.Ws; c.H = g.Hs; c.PB = g.Ps; c.lane = lane;
     const size_t base = (size_t)img * c.W * c.H;
     c.REC = rec + base;
-    c.used = usedAll + (size_t)img * nWords;
+    c.N2 = n2map + (size_t)img * g.Ps * g.Hs;
+    c.used = usedAll + (size_t)img * (g.Ps >> 5) * g.Hs;
     c.R = reg + base;
     c.ring = ring;
     const int k = lane & 7;
@@ -528,15 +601,15 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
     int nSeg = 0;
     for (int s0 = 0; s0 < ns; s0 += 32) {
         const int mySeed = (s0 + lane < ns) ? S[s0 + lane] : -1;       // packed (y<<16 | x)
-        const int myQ = (mySeed >> 16) * c.W + (mySeed & 0xFFFF);
-        const bool myFree = mySeed >= 0 && !used_bit(c.used, myQ);
+        const int myQ = (mySeed >> 16) * c.W + (mySeed & 0xFFFF), myB = (mySeed >> 16) * c.PB + (mySeed & 0xFFFF);
+        const bool myFree = mySeed >= 0 && !used_bit(c.used, myB);
         unsigned fm = __ballot_sync(0xffffffffu, myFree);
         while (fm) {
             const int si = __ffs(fm) - 1;
             fm &= fm - 1;
             const int pk0 = __shfl_sync(0xffffffffu, mySeed, si);
             const int p = __shfl_sync(0xffffffffu, myQ, si);
-            if (used_bit(c.used, p)) continue;   // claimed by a region grown earlier in this chunk
+            if (used_bit(c.used, __shfl_sync(0xffffffffu, myB, si))) continue;   // claimed by a region grown earlier in this chunk
             double regAngle;
             int n = grow_region(c, pk0, p, prec, regAngle);
             if (n < g.minRegSize) continue;
@@ -863,7 +936,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     lsd_upscale_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, c->d_lin + c->linLsdX, c->d_lin + c->linLsdY, imgFirst);
     plf_mark(c, "lsd_gradient");
     cudaMemsetAsync(c->d_n2max + imgFirst, 0, nImg * sizeof(int), s);
-    lsd_grad_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_rec, c->d_n2max, imgFirst);
+    lsd_grad_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_rec, c->d_n2, c->d_used, c->d_n2max, imgFirst);
     plf_mark(c, "lsd_order");
     {
         const size_t smem = (size_t)32 * g.nBins * sizeof(int);
@@ -872,18 +945,16 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
             cudaFuncSetAttribute(lsd_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             s_attr = smem;
         }
-        lsd_order_kernel<<<nImg, 1024, smem, s>>>(g, c->d_rec, c->d_n2max, c->d_seeds, c->d_nSeeds, imgFirst);
+        lsd_order_kernel<<<nImg, 1024, smem, s>>>(g, c->d_n2, c->d_n2max, c->d_seeds, c->d_nSeeds, imgFirst);
     }
     plf_mark(c, "lsd_grow");
     {
-        const int nWords = (g.Ws * g.Hs + 31) / 32;
-        cudaMemsetAsync(c->d_used + (size_t)imgFirst * nWords, 0, (size_t)nImg * nWords * 4, s);
         if (g.refine >= 1)
-            lsd_grow_kernel<true><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
-                                                      c->d_nSegs, c->d_err, nWords, imgFirst);
+            lsd_grow_kernel<true><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
+                                                      c->d_nSegs, c->d_err, imgFirst);
         else
-            lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
-                                                       c->d_nSegs, c->d_err, nWords, imgFirst);
+            lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
+                                                       c->d_nSegs, c->d_err, imgFirst);
     }
     plf_mark(c, "line_keylines");
     const double minLen = c->p.min_line_length * std::min(g.W, g.H);

@@ -50,7 +50,7 @@ struct PlfGeom {          // passed by value to kernels (fits the 4 KB parameter
     int iniTh, minTh;
     int umax[16];
     // LSD
-    int Ws, Hs, Ps;       // scaled image size and pitch (floats/ints use Ws*Hs dense)
+    int Ws, Hs, Ps;       // scaled image size and pitch (a multiple of 128; also the pitch of the |g|^2 map and, in bits, of the used bitmap)
     int lsdTaps[16], lsdK;
     double lsdScale, rho, prec;
     int nBins, minRegSize;
@@ -102,7 +102,8 @@ struct plf_ctx {
     int* d_n2max = nullptr;          // [nImg]
     int* d_seeds = nullptr;          // [nImg][seedCap] seed pixels (packed y<<16|x) in processing order
     int* d_nSeeds = nullptr;         // [nImg]
-    uint32_t* d_used = nullptr;      // [nImg][ceil(Hs*Ws/32)] used bitmap of the region grower
+    int* d_n2 = nullptr;             // [nImg][Hs][Ps] |g|^2 of defined pixels, 0 where undefined (seed ordering, rectangle weights)
+    uint32_t* d_used = nullptr;      // [nImg][Hs][Ps/32] used bitmap of the region grower; undefined pixels start as used
     int* d_reg = nullptr;            // [nImg][Hs*Ws] region pixel list, packed y<<16|x (reused per region)
     float* d_segs = nullptr;         // [nImg][segCap][4]
     int* d_nSegs = nullptr;          // [nImg]

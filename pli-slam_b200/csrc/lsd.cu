@@ -134,14 +134,16 @@ __device__ __forceinline__ double lsd_bin_coef(int n2max, int nBins) {
 }
 
 // Ordered seed list: defined pixels sorted by (bin descending, raster index ascending) — a stable counting sort.
-// One 1024-thread block per image; warp w owns the w-th contiguous raster segment.  Pass 1 counts per (warp, bin) in
+// One block of ORD_WARPS warps per image (16 warps x nBins counters = 64 KB of shared memory: three blocks per SM);
+// warp w owns the w-th contiguous raster segment.  Pass 1 counts per (warp, bin) in
 // shared memory, pass 2 turns the counts into write cursors (bins descending, then warps ascending), pass 3 lets every
 // warp walk its segment again and place its pixels: lanes of one 32-pixel step that share a bin are ranked with
 // __match_any_sync, so the order inside a bin is raster order by construction and no warp waits for another.
-__global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const int* n2map, const int* n2max, int* seeds,
+#define ORD_WARPS 16
+__global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, const int* n2map, const int* n2max, int* seeds,
                                                          int* nSeeds, int imgFirst) {
-    extern __shared__ int s_cur[];          // [32][nBins]
-    __shared__ int s_scan[32];
+    extern __shared__ int s_cur[];          // [ORD_WARPS][nBins]
+    __shared__ int s_scan[ORD_WARPS];
     __shared__ int s_carry;
     const int img = imgFirst + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,11 +151,11 @@ __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const int* n
     const double coef = lsd_bin_coef(n2max[img], nBins);
     // raster walk over the pitched |g|^2 map: the padding columns hold 0 (undefined) and cost one compare
     const int npx = g.Ps * g.Hs;
-    const int segLen = ((npx + 31) / 32 + 31) & ~31;
+    const int segLen = ((npx + ORD_WARPS - 1) / ORD_WARPS + 31) & ~31;
     const int p0 = warp * segLen, p1 = min(p0 + segLen, npx);
     const int* N2 = n2map + (size_t)img * npx;
     int* mine = s_cur + warp * nBins;
-    for (int i = tid; i < 32 * nBins; i += 1024) s_cur[i] = 0;
+    for (int i = tid; i < ORD_WARPS * nBins; i += 32 * ORD_WARPS) s_cur[i] = 0;
     if (tid == 0) s_carry = 0;
     __syncthreads();
     for (int p = p0 + lane; p < p1; p += 32) {
@@ -162,12 +164,12 @@ __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const int* n
     }
     __syncthreads();
     // cursors: for bins in descending order, for warps in ascending order
-    for (int b0 = 0; b0 < nBins; b0 += 1024) {
+    for (int b0 = 0; b0 < nBins; b0 += 32 * ORD_WARPS) {
         const int r = b0 + tid;                 // position in descending bin order
         const int b = nBins - 1 - r;
         int tot = 0;
         if (r < nBins)
-            for (int w = 0; w < 32; ++w) {
+            for (int w = 0; w < ORD_WARPS; ++w) {
                 const int t = s_cur[w * nBins + b];
                 s_cur[w * nBins + b] = tot;
                 tot += t;
@@ -184,16 +186,18 @@ __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const int* n
         for (int w = 0; w < warp; ++w) start += s_scan[w];
         start += inc - tot;
         if (r < nBins)
-            for (int w = 0; w < 32; ++w) s_cur[w * nBins + b] += start;
+            for (int w = 0; w < ORD_WARPS; ++w) s_cur[w * nBins + b] += start;
         __syncthreads();
-        if (tid == 1023) s_carry = start + tot;
+        if (tid == 32 * ORD_WARPS - 1) s_carry = start + tot;
         __syncthreads();
     }
     if (tid == 0) nSeeds[img] = s_carry;
     int* out = seeds + (size_t)img * g.seedCap;
     const unsigned lt = (1u << lane) - 1u;
-    const int W = g.Ps;
-    for (int pb = p0; pb < p1; pb += 32) {
+    const int W = g.Ps;                      // a multiple of 128 and segments start on multiples of 32: my (x, y) advances
+    int y = (p0 + lane) / W, x = (p0 + lane) - y * W;     // by 32 columns per step with at most one row wrap
+    for (int pb = p0; pb < p1; pb += 32, x += 32) {
+        if (x >= W) { x -= W; ++y; }
         const int p = pb + lane;
         const int v = p < p1 ? N2[p] : 0;
         const bool def = v != 0;
@@ -204,8 +208,7 @@ __global__ void __launch_bounds__(1024) lsd_order_kernel(PlfGeom g, const int* n
             const int b = mine[bin];
             __syncwarp(wm);
             if ((grp & lt) == 0) mine[bin] = b + __popc(grp);
-            const int y = p / W;
-            out[b + __popc(grp & lt)] = (y << 16) | (p - y * W);   // packed (y<<16 | x)
+            out[b + __popc(grp & lt)] = (y << 16) | x;             // packed (y<<16 | x)
         }
         __syncwarp();
     }
@@ -576,6 +579,8 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[33], int& n, double
     return true;
 }
 
+// (Measured: two images per block with the registers capped at 48 / 40 to hold 40 / 48 warps per SM instead of 32 gives
+// the same images/s at a full wave and a slower single warp — the kernel is not occupancy-limited there.)
 template <bool REFINE>
 __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* rec, const int* n2map, const int* seeds,
                                                       const int* nSeeds, uint32_t* usedAll, int* reg, float* segs,
@@ -939,13 +944,13 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     lsd_grad_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_rec, c->d_n2, c->d_used, c->d_n2max, imgFirst);
     plf_mark(c, "lsd_order");
     {
-        const size_t smem = (size_t)32 * g.nBins * sizeof(int);
+        const size_t smem = (size_t)ORD_WARPS * g.nBins * sizeof(int);
         static size_t s_attr = 0;
         if (smem > 48 * 1024 && smem > s_attr) {
             cudaFuncSetAttribute(lsd_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             s_attr = smem;
         }
-        lsd_order_kernel<<<nImg, 1024, smem, s>>>(g, c->d_n2, c->d_n2max, c->d_seeds, c->d_nSeeds, imgFirst);
+        lsd_order_kernel<<<nImg, 32 * ORD_WARPS, smem, s>>>(g, c->d_n2, c->d_n2max, c->d_seeds, c->d_nSeeds, imgFirst);
     }
     plf_mark(c, "lsd_grow");
     {

@@ -99,10 +99,13 @@ __device__ __forceinline__ int fast_score16(const int* d, bool bright) {
 #define FS_TH 8
 #define FS_ROWW 36            // 32-bit words per staged row: (128 + 6 bytes -> 34 words) padded to a multiple of 4
 #define FS_IH (FS_TH + 6)
-// Packed FAST-9 corner test: every thread owns 4 horizontally adjacent pixels held as 4 bytes of one register, so the
-// 16 circle comparisons of the 4 pixels are done with byte-SIMD integer ops (VABSDIFF4 + carry-free byte compares)
-// and the "9 contiguous" test is a handful of 3-input ANDs over the 16 per-neighbour flag words — no divergence, the
-// cost does not depend on the image content.  Corners (a few per cent of the pixels) are queued and scored densely.
+// Packed FAST-9 candidate test: every thread owns 4 horizontally adjacent pixels held as 4 bytes of one register, so
+// the 16 circle comparisons of the 4 pixels are byte-SIMD integer ops (VABSDIFF4 + a carry-free byte compare) and the
+// "9 contiguous" test is a handful of 3-input ANDs over the 16 per-neighbour flag words — no divergence, the cost
+// does not depend on the image content.  The packed test is polarity-blind (|centre - ring| > minTh on 9 contiguous
+// ring pixels): a superset of the corners that costs half the instructions of two polarity masks.  Candidates (a few
+// per cent of the pixels) are queued and resolved densely: polarity by majority (a 9-arc needs >= 9 of the 16), exact
+// score, and the score decides (>= minTh <=> FAST-9 corner at minTh).
 __device__ __forceinline__ unsigned fast_gt_const4(unsigned x, unsigned k7f) {
     // per byte: x > t  (t < 128, k7f = (0x7F - t) * 0x01010101); result in bit 7 of every byte
     return (((x & 0x7F7F7F7Fu) + k7f) | x) & 0x80808080u;
@@ -138,39 +141,29 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
     };
     const unsigned C = nb(0, 0);
     const unsigned k7f = (unsigned)(0x7F - g.minTh) * 0x01010101u;
-    unsigned Fb[16], Fd[16];                       // bit 7 of byte j: neighbour k of pixel j is brighter / darker by > th
+    unsigned F[16];                                // bit 7 of byte j: |centre - neighbour k| of pixel j exceeds minTh
     const int cdx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
     const int cdy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const unsigned N = nb(cdx[k], cdy[k]);
-        const unsigned far = fast_gt_const4(__vabsdiffu4(C, N), k7f);   // |C - N| > th
-        const unsigned ngt = __vcmpgtu4(N, C);                          // 0xFF where N > C
-        Fd[k] = far & ~ngt;      // centre brighter than the circle pixel: d = C - N > th
-        Fb[k] = far & ngt;       // d < -th
-    }
+    for (int k = 0; k < 16; ++k) F[k] = fast_gt_const4(__vabsdiffu4(C, nb(cdx[k], cdy[k])), k7f);
     // 9 contiguous flags: T3[k] = F[k]&F[k+1]&F[k+2]; run[k] = T3[k]&T3[k+3]&T3[k+6]; any = OR run[k]
-    unsigned anyB = 0, anyD = 0;
+    unsigned any = 0;
     {
         unsigned T[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) T[k] = Fb[k] & Fb[(k + 1) & 15] & Fb[(k + 2) & 15];
+        for (int k = 0; k < 16; ++k) T[k] = F[k] & F[(k + 1) & 15] & F[(k + 2) & 15];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) anyB |= T[k] & T[(k + 3) & 15] & T[(k + 6) & 15];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) T[k] = Fd[k] & Fd[(k + 1) & 15] & Fd[(k + 2) & 15];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) anyD |= T[k] & T[(k + 3) & 15] & T[(k + 6) & 15];
+        for (int k = 0; k < 16; ++k) any |= T[k] & T[(k + 3) & 15] & T[(k + 6) & 15];
     }
     const int y = y0 + ty;
     const bool rowIn = y < lv.h - PLF_EDGE;
-    unsigned corner = (anyB | anyD) & 0x80808080u;
+    unsigned corner = any & 0x80808080u;
     // mask pixels right of the detection area
     const int xr = lv.w - PLF_EDGE - (x0 + 4 * tx);        // number of valid pixels from my first one
     if (!rowIn || xr <= 0) corner = 0;
     else if (xr < 4) corner &= (0xFFFFFFFFu >> (8 * (4 - xr)));
     if (rowIn && xr > 0) {
-        // non-corners score 0; corner bytes are overwritten by the scoring pass below (same block, after the barrier)
+        // non-candidates score 0; candidate bytes are overwritten by the scoring pass below (same block, after the barrier)
         unsigned* d4 = reinterpret_cast<unsigned*>(dst + (size_t)y * lv.pitch + x0 + 4 * tx);
         if (xr >= 4) *d4 = 0u;
         else for (int j = 0; j < xr; ++j) dst[(size_t)y * lv.pitch + x0 + 4 * tx + j] = 0;
@@ -178,7 +171,7 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         if (corner & (0x80u << (8 * j)))
-            s_queue[atomicAdd(&s_cnt, 1)] = (unsigned short)((ty << 7) | (4 * tx + j) | ((anyD & (0x80u << (8 * j))) ? 0x8000 : 0));
+            s_queue[atomicAdd(&s_cnt, 1)] = (unsigned short)((ty << 7) | (4 * tx + j));
     __syncthreads();
     const int nq = s_cnt;
     const uint8_t* sb = reinterpret_cast<const uint8_t*>(&s_w[0][0]);
@@ -189,10 +182,19 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
         const uint8_t* q = sb + (py + 3) * ST + px + 3;
         const int vq = *q;
         int d[16];
+        int nDark = 0, nBright = 0;                // ring pixels darker / brighter than the centre by more than minTh
 #pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = vq - (int)q[cdy[k] * ST + cdx[k]];
-        // polarity: 0x8000 = centre brighter (d > th)
-        dst[(size_t)(y0 + py) * lv.pitch + x0 + px] = (uint8_t)fast_score16(d, (e & 0x8000) != 0);   // >= minTh
+        for (int k = 0; k < 16; ++k) {
+            d[k] = vq - (int)q[cdy[k] * ST + cdx[k]];
+            nDark += d[k] > g.minTh;
+            nBright += d[k] < -g.minTh;
+        }
+        int sc = 0;
+        if (nDark >= 9 || nBright >= 9) {
+            sc = fast_score16(d, nDark >= 9);
+            if (sc < g.minTh) sc = 0;
+        }
+        dst[(size_t)(y0 + py) * lv.pitch + x0 + px] = (uint8_t)sc;
     }
 }
 

@@ -140,6 +140,7 @@ __device__ __forceinline__ double lsd_bin_coef(int n2max, int nBins) {
 // warp walk its segment again and place its pixels: lanes of one 32-pixel step that share a bin are ranked with
 // __match_any_sync, so the order inside a bin is raster order by construction and no warp waits for another.
 #define ORD_WARPS 16
+#define ORD_MLP 8
 __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, const int* n2map, const int* n2max, int* seeds,
                                                          int* nSeeds, int imgFirst) {
     extern __shared__ int s_cur[];          // [ORD_WARPS][nBins]
@@ -158,9 +159,15 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, co
     for (int i = tid; i < ORD_WARPS * nBins; i += 32 * ORD_WARPS) s_cur[i] = 0;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int p = p0 + lane; p < p1; p += 32) {
-        const int v = N2[p];
-        if (v) atomicAdd(&mine[lsd_bin(v, coef)], 1);
+    // both walks keep ORD_MLP independent loads in flight per lane (a single dependent load per step leaves the walk
+    // bound by memory latency)
+    for (int pb = p0 + lane; pb < p1; pb += 32 * ORD_MLP) {
+        int v[ORD_MLP];
+#pragma unroll
+        for (int u = 0; u < ORD_MLP; ++u) v[u] = (pb + 32 * u < p1) ? N2[pb + 32 * u] : 0;
+#pragma unroll
+        for (int u = 0; u < ORD_MLP; ++u)
+            if (v[u]) atomicAdd(&mine[lsd_bin(v[u], coef)], 1);
     }
     __syncthreads();
     // cursors: for bins in descending order, for warps in ascending order
@@ -196,21 +203,28 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, co
     const unsigned lt = (1u << lane) - 1u;
     const int W = g.Ps;                      // a multiple of 128 and segments start on multiples of 32: my (x, y) advances
     int y = (p0 + lane) / W, x = (p0 + lane) - y * W;     // by 32 columns per step with at most one row wrap
-    for (int pb = p0; pb < p1; pb += 32, x += 32) {
-        if (x >= W) { x -= W; ++y; }
-        const int p = pb + lane;
-        const int v = p < p1 ? N2[p] : 0;
-        const bool def = v != 0;
-        const int bin = def ? lsd_bin(v, coef) : 0;
-        const unsigned wm = __ballot_sync(0xffffffffu, def);
-        if (def) {
-            const unsigned grp = __match_any_sync(wm, bin);
-            const int b = mine[bin];
-            __syncwarp(wm);
-            if ((grp & lt) == 0) mine[bin] = b + __popc(grp);
-            out[b + __popc(grp & lt)] = (y << 16) | x;             // packed (y<<16 | x)
+    for (int pc = p0; pc < p1; pc += 32 * ORD_MLP) {
+        int vv[ORD_MLP];
+#pragma unroll
+        for (int u = 0; u < ORD_MLP; ++u) vv[u] = (pc + 32 * u + lane < p1) ? N2[pc + 32 * u + lane] : 0;
+#pragma unroll
+        for (int u = 0; u < ORD_MLP; ++u) {
+            if (pc + 32 * u >= p1) break;
+            if (x >= W) { x -= W; ++y; }
+            const int v = vv[u];
+            const bool def = v != 0;
+            const int bin = def ? lsd_bin(v, coef) : 0;
+            const unsigned wm = __ballot_sync(0xffffffffu, def);
+            if (def) {
+                const unsigned grp = __match_any_sync(wm, bin);
+                const int b = mine[bin];
+                __syncwarp(wm);
+                if ((grp & lt) == 0) mine[bin] = b + __popc(grp);
+                out[b + __popc(grp & lt)] = (y << 16) | x;             // packed (y<<16 | x)
+            }
+            __syncwarp();
+            x += 32;
         }
-        __syncwarp();
     }
 }
 

@@ -262,7 +262,7 @@ __device__ __forceinline__ void seq_sum3(double (*buf)[33], double a, double b, 
 struct GrowState {
     int n;            // region size
     float sumdx, sumdy;
-    double regAngle;  // exact angle of (sumdx, sumdy) unless `dirty`
+    float regDeg;     // exact region angle in degrees (fastAtan2 of the sums; the seed's angle for a fresh region) unless `dirty`
     bool dirty;
 };
 
@@ -282,12 +282,36 @@ __device__ __forceinline__ bool used_bit(const uint32_t* used, int q) {
     return (used[q >> 5] >> (q & 31)) & 1u;
 }
 
-// LSD isAligned(): |theta - a|, folded once around 2*pi, <= tolerance  (branch-free, same arithmetic)
-__device__ __forceinline__ bool lsd_aligned(double theta, double a, double tol) {
-    double nd = fabs(__dsub_rn(theta, a));
+// LSD isAligned(): |theta - a|, folded once around 2*pi, <= tolerance, on radians in double.  Both angles are float
+// degrees times one constant, so the decision is taken in float degrees whenever the float difference is farther than
+// `kAlignGuard` from the two thresholds (the tolerance and the 270-degree fold) — far more than the float rounding of the
+// difference (< 1e-4 below 360) and than the double roundings of the exact form; only the rare pixel inside a guard band
+// evaluates the exact double expression.
+constexpr float kAlignGuard = 4e-3f;
+struct AlignTol {
+    double tol;        // radians, the reference's tolerance
+    float lo, hi;      // degrees: tol - guard, tol + guard
+};
+__device__ __forceinline__ AlignTol make_align_tol(double tol) {
+    AlignTol t;
+    t.tol = tol;
+    const double deg = tol / kDegToRad;
+    t.lo = (float)(deg - (double)kAlignGuard);
+    t.hi = (float)(deg + (double)kAlignGuard);
+    return t;
+}
+__device__ __noinline__ bool lsd_aligned_exact(float thetaDeg, float aDeg, double tol) {
+    double nd = fabs(__dsub_rn((double)thetaDeg * kDegToRad, (double)aDeg * kDegToRad));
     const double nw = fabs(__dsub_rn(nd, 2 * kPi));
     nd = (nd > (3 * kPi) / 2) ? nw : nd;
     return nd <= tol;
+}
+__device__ __forceinline__ bool lsd_aligned(float thetaDeg, float aDeg, const AlignTol& t) {
+    float d = fabsf(__fsub_rn(thetaDeg, aDeg));
+    const bool nearFold = fabsf(__fsub_rn(d, 270.f)) < kAlignGuard;
+    if (d > 270.f) d = fabsf(__fsub_rn(d, 360.f));
+    if (nearFold || (d > t.lo && d < t.hi)) return lsd_aligned_exact(thetaDeg, aDeg, t.tol);
+    return d <= t.lo;
 }
 
 // Resolves one set of 32 candidates (lane order = processing order); `valid` lanes hold pixel q (packed pk) with
@@ -298,20 +322,19 @@ __device__ __forceinline__ bool lsd_aligned(double theta, double a, double tol) 
 // contradicts the prediction every lane has seen the true state, so those decisions are final; they are committed in
 // one SIMD step and the rest goes round again.  The angle drifts slowly, so one round usually settles a set:
 // ~100 + 9/accepted-pixel warp instructions per round instead of ~95 per accepted pixel.
-__device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int pk, const float4& r, double tol,
+__device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int pk, const float4& r, const AlignTol& tol,
                                            const GrowCtx& c) {
     unsigned pending = __ballot_sync(0xffffffffu, valid);
     if (!pending) return;
     const unsigned dup = __match_any_sync(0xffffffffu, valid ? q : -1 - c.lane);   // lanes holding my pixel
-    const double aRad = (double)r.x * kDegToRad;
     const unsigned myBit = 1u << c.lane, lt = myBit - 1u;
     while (pending) {
         if (st.dirty) {
-            st.regAngle = (double)fast_atan2_deg(st.sumdy, st.sumdx) * kDegToRad;
+            st.regDeg = fast_atan2_deg(st.sumdy, st.sumdx);
             st.dirty = false;
         }
         const bool mine = (pending & myBit) != 0u;
-        const unsigned am = __ballot_sync(0xffffffffu, mine && lsd_aligned(st.regAngle, aRad, tol));
+        const unsigned am = __ballot_sync(0xffffffffu, mine && lsd_aligned(st.regDeg, r.x, tol));
         if (!am) break;
         // prediction: the aligned lanes, first instance of every pixel only (a later instance finds it used)
         const bool pred = (am & myBit) && !(dup & lt & am);
@@ -331,8 +354,8 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
         }
         // lanes below the first A-lane still see the current state: its angle is st.regAngle (for a fresh region
         // that is the seed's angle, not the arctangent of the sums)
-        const double ang = ((A & lt) || c.lane == v) ? (double)fast_atan2_deg(sy, sx) * kDegToRad : st.regAngle;
-        const bool t = mine && !shadowed && lsd_aligned(ang, aRad, tol);
+        const float ang = ((A & lt) || c.lane == v) ? fast_atan2_deg(sy, sx) : st.regDeg;
+        const bool t = mine && !shadowed && lsd_aligned(ang, r.x, tol);
         const unsigned mm = __ballot_sync(0xffffffffu, mine && (t != pred));
         unsigned acc;
         int e;
@@ -359,7 +382,7 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
         st.sumdx = ex;
         st.sumdy = ey;
         if (mm == 0u) {
-            if (v >= 0) st.regAngle = __shfl_sync(0xffffffffu, ang, v); else st.dirty = true;
+            if (v >= 0) st.regDeg = __shfl_sync(0xffffffffu, ang, v); else st.dirty = true;
             break;
         }
         st.dirty = true;
@@ -370,18 +393,18 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
 
 // LSD region_grow from the seed (packed pk0, linear index p) with angle tolerance `tol`; returns the region size, the
 // pixel list is left in c.R[0..n)
-__device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, double tol, double& regAngleOut) {
+__device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, const AlignTol& tol, double& regAngleOut) {
     GrowState st;
     st.n = 1;
     if (c.lane == 0) {
         const int pb = (pk0 >> 16) * c.PB + (pk0 & 0xFFFF);
         c.ring[0] = pk0; c.R[0] = pk0; atomicOr(c.used + (pb >> 5), 1u << (pb & 31));
     }
-    st.regAngle = (double)c.REC[p].x * kDegToRad;
+    st.regDeg = c.REC[p].x;
     st.dirty = false;
     {
         double sn, cs;
-        sincos(st.regAngle, &sn, &cs);
+        sincos((double)st.regDeg * kDegToRad, &sn, &cs);
         st.sumdx = (float)cs;
         st.sumdy = (float)sn;
     }
@@ -423,7 +446,7 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, dou
         }
         i += nb;
     }
-    regAngleOut = st.dirty ? (double)fast_atan2_deg(st.sumdy, st.sumdx) * kDegToRad : st.regAngle;
+    regAngleOut = (double)(st.dirty ? fast_atan2_deg(st.sumdy, st.sumdx) : st.regDeg) * kDegToRad;
     return st.n;
 }
 
@@ -559,7 +582,7 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[33], int& n, double
                                                      __dmul_rn(mean, mean))));
     __syncwarp();
     __threadfence_block();
-    n = grow_region(c, pk0, p0, tau, regAngle);
+    n = grow_region(c, pk0, p0, make_align_tol(tau), regAngle);
     if (n < 2) return false;
     rect_fit<true>(c, s_sum, n, regAngle, prec, rf);
     density = (double)n / __dmul_rn(lsd_dist(rf.x1, rf.y1, rf.x2, rf.y2), rf.width);
@@ -617,6 +640,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
     float* out = segs + (size_t)img * g.segCap * 4;
     const int ns = nSeeds[img];
     const double prec = g.prec;
+    const AlignTol precTol = make_align_tol(prec);
     int nSeg = 0;
     for (int s0 = 0; s0 < ns; s0 += 32) {
         const int mySeed = (s0 + lane < ns) ? S[s0 + lane] : -1;       // packed (y<<16 | x)
@@ -630,7 +654,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
             const int p = __shfl_sync(0xffffffffu, myQ, si);
             if (used_bit(c.used, __shfl_sync(0xffffffffu, myB, si))) continue;   // claimed by a region grown earlier in this chunk
             double regAngle;
-            int n = grow_region(c, pk0, p, prec, regAngle);
+            int n = grow_region(c, pk0, p, precTol, regAngle);
             if (n < g.minRegSize) continue;
             RectFit rf;
             rect_fit<REFINE>(c, s_sum, n, regAngle, prec, rf);

@@ -323,7 +323,7 @@ __device__ __forceinline__ bool lsd_aligned(float thetaDeg, float aDeg, const Al
 // one SIMD step and the rest goes round again.  The angle drifts slowly, so one round usually settles a set:
 // ~100 + 9/accepted-pixel warp instructions per round instead of ~95 per accepted pixel.
 __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int pk, const float4& r, const AlignTol& tol,
-                                           const GrowCtx& c) {
+                                           const GrowCtx& c, unsigned& accepted) {
     unsigned pending = __ballot_sync(0xffffffffu, valid);
     if (!pending) return;
     const unsigned dup = __match_any_sync(0xffffffffu, valid ? q : -1 - c.lane);   // lanes holding my pixel
@@ -374,6 +374,7 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
             atomicOr(c.used + (q >> 5), 1u << (q & 31));
         }
         st.n += __popc(acc);
+        accepted |= acc;
         float ex = __shfl_sync(0xffffffffu, sx, e), ey = __shfl_sync(0xffffffffu, sy, e);
         if ((acc >> e) & 1u) {
             ex = __fadd_rn(ex, __shfl_sync(0xffffffffu, r.y, e));
@@ -429,19 +430,20 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
                 if (xx >= 0 && yy >= 0 && xx < c.W && yy < c.H) {
                     q[s] = yy * c.PB + xx;
                     pk[s] = (yy << 16) | xx;
-                    if (!used_bit(c.used, q[s])) {        // unused implies defined: undefined pixels start as used
-                        r[s] = c.REC[yy * c.W + xx];
-                        valid[s] = true;
-                    }
+                    r[s] = c.REC[yy * c.W + xx];          // issued together with the bitmap word: one round trip
+                    valid[s] = !used_bit(c.used, q[s]);   // unused implies defined: undefined pixels start as used
                 }
             }
         }
-        grow_chain(st, valid[0], q[0], pk[0], r[0], tol, c);
+        unsigned acc0 = 0u, acc1 = 0u;
+        grow_chain(st, valid[0], q[0], pk[0], r[0], tol, c, acc0);
         __syncwarp();
         if (nb > 4) {
-            // pixels accepted while resolving the first set are no longer available
-            if (valid[1] && used_bit(c.used, q[1])) valid[1] = false;
-            grow_chain(st, valid[1], q[1], pk[1], r[1], tol, c);
+            // pixels accepted while resolving the first set are no longer available: compare in registers (re-reading
+            // the bitmap would cost an L2 round trip, the atomics bypass L1)
+            for (unsigned m = acc0; m; m &= m - 1u)
+                if (q[1] == __shfl_sync(0xffffffffu, q[0], __ffs(m) - 1)) valid[1] = false;
+            grow_chain(st, valid[1], q[1], pk[1], r[1], tol, c, acc1);
             __syncwarp();
         }
         i += nb;

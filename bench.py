@@ -155,8 +155,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per camera stream per call (BASELINE config C2)")
-    ap.add_argument("--streams", type=int, default=16, help="independent camera streams served by one context")
-    ap.add_argument("--contexts", type=int, default=3, help="calls kept in flight per GPU (one CUDA stream each)")
+    ap.add_argument("--streams", type=int, default=8, help="independent camera streams served by one context")
+    ap.add_argument("--contexts", type=int, default=6, help="calls kept in flight per GPU (one CUDA stream each)")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic pairs generated per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

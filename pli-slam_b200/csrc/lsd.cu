@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, co
 // (A variant with four images per warp — 8 lanes per image, lock-step state machine — was measured: same instruction
 // count per image, 4x the latency; one warp per image is kept.)
 #define GROW_RING 512
+#define GROW_SETS 2
 
 // Sequential (scalar-loop order) accumulation of three quantities over the pixels of a region: the 32 lanes write
 // their three products to shared memory, then lanes 0..2 each own one accumulator and add the 32 values in order.
@@ -412,13 +413,16 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
     __syncwarp();
     int i = 0;
     while (i < st.n) {
-        const int nb = min(8, st.n - i);
+        // a batch: up to GROW_SETS sets of 4 list entries x 8 neighbours.  All loads of the batch (ring, bitmap word,
+        // record) are issued before the first set is resolved, so a wide frontier pays one memory round trip per
+        // 4 * GROW_SETS entries; the sets are then resolved in list order.
+        const int nb = min(4 * GROW_SETS, st.n - i);
         const bool inRing = (st.n - i) <= GROW_RING;
-        int q[2], pk[2];
-        float4 r[2];
-        bool valid[2];
+        int q[GROW_SETS], pk[GROW_SETS];
+        float4 r[GROW_SETS];
+        bool valid[GROW_SETS];
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < GROW_SETS; ++s) {
             const int e = s * 4 + (c.lane >> 3);
             q[s] = -1;
             pk[s] = 0;
@@ -435,16 +439,20 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
                 }
             }
         }
-        unsigned acc0 = 0u, acc1 = 0u;
-        grow_chain(st, valid[0], q[0], pk[0], r[0], tol, c, acc0);
-        __syncwarp();
-        if (nb > 4) {
-            // pixels accepted while resolving the first set are no longer available: compare in registers (re-reading
-            // the bitmap would cost an L2 round trip, the atomics bypass L1)
-            for (unsigned m = acc0; m; m &= m - 1u)
-                if (q[1] == __shfl_sync(0xffffffffu, q[0], __ffs(m) - 1)) valid[1] = false;
-            grow_chain(st, valid[1], q[1], pk[1], r[1], tol, c, acc1);
-            __syncwarp();
+        unsigned acc[GROW_SETS];
+#pragma unroll
+        for (int s = 0; s < GROW_SETS; ++s) {
+            acc[s] = 0u;
+            if (s * 4 < nb) {
+                // pixels accepted while resolving the earlier sets are no longer available: compare in registers
+                // (the bitmap words were read before those acceptances)
+#pragma unroll
+                for (int t = 0; t < s; ++t)
+                    for (unsigned m = acc[t]; m; m &= m - 1u)
+                        if (q[s] == __shfl_sync(0xffffffffu, q[t], __ffs(m) - 1)) valid[s] = false;
+                grow_chain(st, valid[s], q[s], pk[s], r[s], tol, c, acc[s]);
+                __syncwarp();
+            }
         }
         i += nb;
     }

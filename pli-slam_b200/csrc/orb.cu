@@ -72,27 +72,44 @@ __device__ __forceinline__ bool fast_run9(unsigned m) {
     r &= (m2 >> 8);
     return (r & 0xFFFFu) != 0u;
 }
-// Exact corner score of a pixel that IS a corner at some threshold >= 0, single polarity (a bright and a dark 9-arc
-// cannot coexist on a 16-pixel circle).  Bit-sliced bisection: B[b] holds bit b of e[k] = clamp(+-d[k], 0, 255) for the
-// 16 circle pixels; walking the bit planes from the top keeps the sets {e > prefix} and {e == prefix}, so each of the 8
-// steps costs a handful of logic ops plus one 9-run test.  Returns M-1 with M = max over 9-arcs of min(e).
-__device__ __forceinline__ int fast_score16(const int* d, bool bright) {
-    unsigned B[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+// Exact corner score from the 16 ring pixels packed four to a word (byte j of N[w] = ring pixel 4w+j), or 0 if the
+// pixel is not a FAST-9 corner at minTh.  Polarity by majority: a 9-arc needs >= 9 of the 16 ring pixels on one side.
+// With e[k] = the ring pixel's distance to the centre on that side (0 on the other side), the score is M-1 with
+// M = max over 9-arcs of min(e), found by bit-sliced bisection: plane b holds bit b of the 16 e[k] (gathered from the
+// packed bytes with one multiply per word); walking the planes from the top keeps the sets {e > prefix} and
+// {e == prefix}, so each of the 8 steps costs a handful of logic ops plus one 9-run test.
+__device__ __forceinline__ unsigned fast_gt_const4(unsigned x, unsigned k7f) {
+    // per byte: x > t  (t < 128, k7f = (0x7F - t) * 0x01010101); result in bit 7 of every byte
+    return (((x & 0x7F7F7F7Fu) + k7f) | x) & 0x80808080u;
+}
+__device__ __forceinline__ int fast_score_packed(const unsigned* N, unsigned centre, int minTh, unsigned k7f) {
+    const unsigned C4 = centre * 0x01010101u;
+    unsigned A[4], G[4];
+    int nDark = 0, nBright = 0;                    // ring pixels darker / brighter than the centre by more than minTh
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        int e = bright ? d[k] : -d[k];
-        e = e < 0 ? 0 : e;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) B[b] |= ((unsigned)(e >> b) & 1u) << k;
+    for (int w = 0; w < 4; ++w) {
+        A[w] = __vabsdiffu4(C4, N[w]);
+        G[w] = __vcmpgtu4(C4, N[w]);
+        const unsigned far = fast_gt_const4(A[w], k7f);
+        nDark += __popc(far & G[w]);
+        nBright += __popc(far & ~G[w]);
     }
+    if (nDark < 9 && nBright < 9) return 0;
+    const unsigned flip = nDark >= 9 ? 0u : 0xFFFFFFFFu;
+    unsigned E[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) E[w] = A[w] & (G[w] ^ flip);
     unsigned gt = 0u, eq = 0xFFFFu;
     int M = 0;
 #pragma unroll
     for (int b = 7; b >= 0; --b) {
-        if (fast_run9(gt | (eq & B[b]))) { M |= 1 << b; eq &= B[b]; }
-        else { gt |= eq & B[b]; eq &= ~B[b]; }
+        unsigned P = 0u;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) P |= ((((E[w] >> b) & 0x01010101u) * 0x01020408u) >> 24) << (4 * w);
+        if (fast_run9(gt | (eq & P))) { M |= 1 << b; eq &= P; }
+        else { gt |= eq & P; eq &= ~P; }
     }
-    return M - 1;
+    return M - 1 >= minTh ? M - 1 : 0;
 }
 
 #define FS_TW 128
@@ -106,10 +123,6 @@ __device__ __forceinline__ int fast_score16(const int* d, bool bright) {
 // ring pixels): a superset of the corners that costs half the instructions of two polarity masks.  Candidates (a few
 // per cent of the pixels) are queued and resolved densely: polarity by majority (a 9-arc needs >= 9 of the 16), exact
 // score, and the score decides (>= minTh <=> FAST-9 corner at minTh).
-__device__ __forceinline__ unsigned fast_gt_const4(unsigned x, unsigned k7f) {
-    // per byte: x > t  (t < 128, k7f = (0x7F - t) * 0x01010101); result in bit 7 of every byte
-    return (((x & 0x7F7F7F7Fu) + k7f) | x) & 0x80808080u;
-}
 
 __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_t* pyr, uint8_t* score,
                                                          const PlfTile* tiles, int imgFirst) {
@@ -168,10 +181,21 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
         if (xr >= 4) *d4 = 0u;
         else for (int j = 0; j < xr; ++j) dst[(size_t)y * lv.pitch + x0 + 4 * tx + j] = 0;
     }
+    {   // queue the candidates: one shared-memory atomic per warp (a warp is one row of the tile)
+        const int cnt = __popc(corner);
+        int inc = cnt;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (corner & (0x80u << (8 * j)))
-            s_queue[atomicAdd(&s_cnt, 1)] = (unsigned short)((ty << 7) | (4 * tx + j));
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tx >= o) inc += t;
+        }
+        int base = 0;
+        if (tx == 31 && inc) base = atomicAdd(&s_cnt, inc);
+        int pos = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (corner & (0x80u << (8 * j))) s_queue[pos++] = (unsigned short)((ty << 7) | (4 * tx + j));
+    }
     __syncthreads();
     const int nq = s_cnt;
     const uint8_t* sb = reinterpret_cast<const uint8_t*>(&s_w[0][0]);
@@ -180,20 +204,12 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
         const int e = s_queue[i];
         const int py = (e >> 7) & 0xFF, px = e & 0x7F;
         const uint8_t* q = sb + (py + 3) * ST + px + 3;
-        const int vq = *q;
-        int d[16];
-        int nDark = 0, nBright = 0;                // ring pixels darker / brighter than the centre by more than minTh
+        unsigned N[4];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            d[k] = vq - (int)q[cdy[k] * ST + cdx[k]];
-            nDark += d[k] > g.minTh;
-            nBright += d[k] < -g.minTh;
-        }
-        int sc = 0;
-        if (nDark >= 9 || nBright >= 9) {
-            sc = fast_score16(d, nDark >= 9);
-            if (sc < g.minTh) sc = 0;
-        }
+        for (int w = 0; w < 4; ++w)
+            N[w] = (unsigned)q[cdy[4 * w] * ST + cdx[4 * w]] | ((unsigned)q[cdy[4 * w + 1] * ST + cdx[4 * w + 1]] << 8) |
+                   ((unsigned)q[cdy[4 * w + 2] * ST + cdx[4 * w + 2]] << 16) | ((unsigned)q[cdy[4 * w + 3] * ST + cdx[4 * w + 3]] << 24);
+        const int sc = fast_score_packed(N, *q, g.minTh, k7f);
         dst[(size_t)(y0 + py) * lv.pitch + x0 + px] = (uint8_t)sc;
     }
 }

@@ -191,6 +191,8 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
     if (p->width < 64 || p->height < 64 || p->max_batch < 1 || p->n_levels < 1 || p->n_levels > PLF_MAX_LEVELS ||
         p->n_features < 1)
         return fail(PLF_ERR_INVALID, "bad image size / batch / levels / features");
+    if (!(p->scale_factor > 1.0f && p->scale_factor <= 2.0f) || (p->has_lines && !(p->lsd_scale >= 0.5)))
+        return fail(PLF_ERR_UNSUPPORTED, "scale_factor outside (1, 2] or lsd_scale < 0.5 (the resize kernels fetch the taps of 4 pixels from 12 source bytes)");
     if (p->lsd_refine < 0 || p->lsd_refine > 1) return fail(PLF_ERR_UNSUPPORTED, "lsd_refine = 2 (ADVANCED: NFA rectangle improvement) is not built");
     if (p->min_th_fast < 1 || p->min_th_fast > 126 || p->ini_th_fast < p->min_th_fast || p->ini_th_fast > 254)
         return fail(PLF_ERR_UNSUPPORTED, "FAST thresholds outside 1 <= minTh <= 126, minTh <= iniTh <= 254");
@@ -240,9 +242,14 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
                 lin.push_back(PlfLin{(unsigned short)sx, (short)std::nearbyintf((1.f - f) * 2048.f), (short)std::nearbyintf(f * 2048.f), 0});
             }
         };
+        // every table starts on a multiple of 4 entries and is followed by >= 4 padding entries: the resize kernels
+        // fetch the x-entries of 4 adjacent output pixels as two 16-byte loads
+        auto pad4 = [&] { for (int k = 0; k < 4; ++k) lin.push_back(PlfLin{0, 0, 0, 0}); while (lin.size() & 3) lin.push_back(PlfLin{0, 0, 0, 0}); };
         for (int l = 1; l < g.nLevels; ++l) {
+            pad4();
             c->g.lv[l].xTab = (int)lin.size();
             lin11(g.lv[l - 1].w, g.lv[l].w);
+            pad4();
             c->g.lv[l].yTab = (int)lin.size();
             lin11(g.lv[l - 1].h, g.lv[l].h);
         }
@@ -259,10 +266,13 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
                 lin.push_back(PlfLin{(unsigned short)o, (short)(256 - a), (short)a, 0});
             }
         };
+        pad4();
         c->linLsdX = (int)lin.size();
         lin8(g.W, g.Ws);
+        pad4();
         c->linLsdY = (int)lin.size();
         lin8(g.H, g.Hs);
+        pad4();
         c->nTilesBlur = (int)tb.size();
         c->nTilesFast = (int)tf.size();
         PLF_CUDA_OK(dalloc(&c->d_tilesBlur, tb.size()));
@@ -288,7 +298,7 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
     PLF_CUDA_OK(dalloc(&c->d_depth, nSlot * g.kpCap));
     PLF_CUDA_OK(dalloc(&c->d_sad, nSlot * g.kpCap));
     if (p->has_lines) {
-        PLF_CUDA_OK(dalloc(&c->d_lsdBlur, nImg * (size_t)g.lv[0].pitch * g.H));
+        PLF_CUDA_OK(dalloc(&c->d_lsdBlur, nImg * (size_t)g.lv[0].pitch * g.H + 64));   // +64: the upscale reads whole words
         PLF_CUDA_OK(dalloc(&c->d_lsdU, nImg * (size_t)g.Ps * g.Hs));
         PLF_CUDA_OK(dalloc(&c->d_rec, nImg * npx));
         PLF_CUDA_OK(dalloc(&c->d_n2max, nImg));

@@ -39,17 +39,16 @@ __global__ void __launch_bounds__(256) blur_image_kernel(const uint8_t* src, siz
 __global__ void __launch_bounds__(256) lsd_upscale_kernel(PlfGeom g, const uint8_t* src, size_t srcImgStride, int sp,
                                                           uint8_t* dst, const PlfLin* linX, const PlfLin* linY,
                                                           int imgFirst) {
-    const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
+    const int dx = blockIdx.x * 128 + threadIdx.x * 4, dy = blockIdx.y * 8 + threadIdx.y;
     if (dx >= g.Ws || dy >= g.Hs) return;
     const int img = imgFirst + blockIdx.z;
     const uint8_t* s = src + (size_t)img * srcImgStride;
-    const PlfLin cx = linX[dx], cy = linY[dy];      // Q8 weights built on the host (a0 = 256 - a1)
+    const PlfLin cy = linY[dy];                     // Q8 weights built on the host (a0 = 256 - a1)
     const uint8_t* r0 = s + (size_t)cy.ofs * sp;
-    const uint8_t* r1 = s + (size_t)min(cy.ofs + 1, g.H - 1) * sp;
-    const int x1 = min(cx.ofs + 1, g.W - 1);
-    const int h0 = r0[cx.ofs] * cx.a0 + r0[x1] * cx.a1;
-    const int h1 = r1[cx.ofs] * cx.a0 + r1[x1] * cx.a1;
-    dst[(size_t)img * g.Ps * g.Hs + (size_t)dy * g.Ps + dx] = (uint8_t)((h0 * cy.a0 + h1 * cy.a1 + 32768) >> 16);
+    const uint8_t* r1 = s + (size_t)min((int)cy.ofs + 1, g.H - 1) * sp;
+    // 4 pixels per thread; the row pitch Ps is a multiple of 128, so the store is always a whole aligned word
+    const unsigned v = resize_quad<true>(r0, r1, linX + dx, min(4, g.Ws - dx), cy.a0, cy.a1);
+    *reinterpret_cast<unsigned*>(dst + (size_t)img * g.Ps * g.Hs + (size_t)dy * g.Ps + dx) = v;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -986,7 +985,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         upStride = imgBytes;
         ++launches;
     }
-    lsd_upscale_kernel<<<dim3((g.Ws + 31) / 32, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, c->d_lin + c->linLsdX, c->d_lin + c->linLsdY, imgFirst);
+    lsd_upscale_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, c->d_lin + c->linLsdX, c->d_lin + c->linLsdY, imgFirst);
     plf_mark(c, "lsd_gradient");
     cudaMemsetAsync(c->d_n2max + imgFirst, 0, nImg * sizeof(int), s);
     lsd_grad_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_rec, c->d_n2, c->d_used, c->d_n2max, imgFirst);

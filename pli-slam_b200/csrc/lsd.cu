@@ -323,10 +323,10 @@ __device__ __forceinline__ bool lsd_aligned(float thetaDeg, float aDeg, const Al
 // one SIMD step and the rest goes round again.  The angle drifts slowly, so one round usually settles a set:
 // ~100 + 9/accepted-pixel warp instructions per round instead of ~95 per accepted pixel.
 __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int pk, const float4& r, const AlignTol& tol,
-                                           const GrowCtx& c, unsigned& accepted) {
+                                           const GrowCtx& c, unsigned dupAll, unsigned& accepted) {
     unsigned pending = __ballot_sync(0xffffffffu, valid);
     if (!pending) return;
-    const unsigned dup = __match_any_sync(0xffffffffu, valid ? q : -1 - c.lane);   // lanes holding my pixel
+    const unsigned dup = dupAll & pending;          // valid lanes holding my pixel (copies share the used bit)
     const unsigned myBit = 1u << c.lane, lt = myBit - 1u;
     while (pending) {
         if (st.dirty) {
@@ -423,7 +423,7 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
 #pragma unroll
         for (int s = 0; s < GROW_SETS; ++s) {
             const int e = s * 4 + (c.lane >> 3);
-            q[s] = -1;
+            q[s] = -1 - c.lane;
             pk[s] = 0;
             valid[s] = false;
             r[s] = make_float4(PLF_NOTDEF, 0.f, 0.f, 0.f);
@@ -438,6 +438,10 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
                 }
             }
         }
+        // which lanes of a set hold the same pixel: resolved while the loads are in flight
+        unsigned dupAll[GROW_SETS];
+#pragma unroll
+        for (int s = 0; s < GROW_SETS; ++s) dupAll[s] = (s * 4 < nb) ? __match_any_sync(0xffffffffu, q[s]) : 0u;
         unsigned acc[GROW_SETS];
 #pragma unroll
         for (int s = 0; s < GROW_SETS; ++s) {
@@ -449,7 +453,7 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
                 for (int t = 0; t < s; ++t)
                     for (unsigned m = acc[t]; m; m &= m - 1u)
                         if (q[s] == __shfl_sync(0xffffffffu, q[t], __ffs(m) - 1)) valid[s] = false;
-                grow_chain(st, valid[s], q[s], pk[s], r[s], tol, c, acc[s]);
+                grow_chain(st, valid[s], q[s], pk[s], r[s], tol, c, dupAll[s], acc[s]);
                 __syncwarp();
             }
         }

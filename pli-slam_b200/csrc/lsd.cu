@@ -328,6 +328,9 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
     if (!pending) return;
     const unsigned dup = dupAll & pending;          // valid lanes holding my pixel (copies share the used bit)
     const unsigned myBit = 1u << c.lane, lt = myBit - 1u;
+    // lanes that are a later copy of a pixel still pending in a lower lane (a copy is never predicted: if the first one
+    // is accepted the pixel is used, and copies share the angle); refreshed whenever `pending` shrinks
+    unsigned later = __ballot_sync(0xffffffffu, (dup & lt) != 0u);
     while (pending) {
         if (st.dirty) {
             st.regDeg = fast_atan2_deg(st.sumdy, st.sumdx);
@@ -337,8 +340,8 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
         const unsigned am = __ballot_sync(0xffffffffu, mine && lsd_aligned(st.regDeg, r.x, tol));
         if (!am) break;
         // prediction: the aligned lanes, first instance of every pixel only (a later instance finds it used)
-        const bool pred = (am & myBit) && !(dup & lt & am);
-        const unsigned A = __ballot_sync(0xffffffffu, pred);
+        const unsigned A = am & ~later;
+        const bool pred = (A & myBit) != 0u;
         const bool shadowed = (dup & lt & A) != 0u;
         // a lane outside the set (if any) accumulates all of A: the state after the set if the prediction holds
         const unsigned spare = ~pending;
@@ -375,6 +378,12 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
         }
         st.n += __popc(acc);
         accepted |= acc;
+        if (mm == 0u && v >= 0) {          // the spare lane holds the sums and the angle after all of A
+            st.sumdx = __shfl_sync(0xffffffffu, sx, v);
+            st.sumdy = __shfl_sync(0xffffffffu, sy, v);
+            st.regDeg = __shfl_sync(0xffffffffu, ang, v);
+            break;
+        }
         float ex = __shfl_sync(0xffffffffu, sx, e), ey = __shfl_sync(0xffffffffu, sy, e);
         if ((acc >> e) & 1u) {
             ex = __fadd_rn(ex, __shfl_sync(0xffffffffu, r.y, e));
@@ -382,13 +391,11 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
         }
         st.sumdx = ex;
         st.sumdy = ey;
-        if (mm == 0u) {
-            if (v >= 0) st.regDeg = __shfl_sync(0xffffffffu, ang, v); else st.dirty = true;
-            break;
-        }
         st.dirty = true;
+        if (mm == 0u) break;
         const unsigned dupAcc = __reduce_or_sync(0xffffffffu, (acc & myBit) ? dup : 0u);
         pending &= ~((2u << e) - 1u) & ~dupAcc;
+        later = __ballot_sync(0xffffffffu, (dup & lt & pending) != 0u);
     }
 }
 

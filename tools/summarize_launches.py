@@ -15,7 +15,7 @@ def main():
     for r in csv.DictReader(lines):
         if r.get("Metric Name") != "gpu__time_duration.sum":
             continue
-        name = re.sub(r"^<unnamed>::", "", r["Kernel Name"])
+        name = re.sub(r"^(void )?<unnamed>::", "", r["Kernel Name"])
         name = re.sub(r"\(.*$", "", name)
         scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r["Metric Unit"].strip(), 1e-6)
         rows.append((name, float(r["Metric Value"].replace(",", "")) * scale, r["Grid Size"], r["Block Size"]))

@@ -231,18 +231,21 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, co
 // K4c  region growing + rectangle fit (LSD region_grow / region2rect / get_theta / refine / reduce_region_radius).
 // One warp per image; seeds in order; every region is grown with the exact sequential rule: list entries are expanded
 // front to back, their 8 neighbours in raster order, a neighbour is accepted iff unused and aligned with the CURRENT
-// region angle, which is updated after every acceptance.  The kernel is bound by dependent-instruction latency (ncu:
-// ~200 warp instructions per accepted pixel at 0.14 IPC per warp, DRAM idle), so the design minimises instructions per
-// pixel and shared memory per block (many images in flight per SM), not bytes:
-//  * per-pixel data is one read-only 16-byte record (angle, cosf, sinf, |g|^2) -> one LDG.128 per neighbour;
-//  * the `used` map is a bitmap in global memory (64 KB per image, L2-resident), cleared by a memset node;
+// region angle, which is updated after every acceptance.  The kernel is bound by latency — of its own dependent
+// instruction chain and of L2/DRAM round trips (ncu: ~105 warp instructions per accepted pixel, one issue every ~12
+// cycles per warp, DRAM at a few per cent) — so the design shortens the critical path, not the byte count:
+//  * per-pixel data is one read-only 16-byte record (angle, cosf, sinf, |g|^2) -> one LDG.128 per neighbour, issued
+//    together with the bitmap word of that neighbour (one memory round trip per batch);
+//  * the `used` map is a bitmap in global memory (74 KB per image, rows of Ps bits); the gradient kernel writes it with
+//    the undefined pixels already set, so "unused" implies "defined" and undefined pixels never cost a record load;
 //  * list entries are packed (y<<16|x) so no integer division is ever needed; the BFS frontier lives in a small
 //    shared-memory ring, the full list also goes to global memory for the rectangle fit;
-//  * a batch covers 8 list entries x 8 neighbours = 2 candidates per lane in processing order; the loads of a batch are
-//    issued together and the acceptance chain is resolved with ballots, one fastAtan2 per accepted pixel;
+//  * a batch covers 8 list entries x 8 neighbours = 2 sets of 32 candidates in processing order; each set is resolved
+//    in speculative SIMD rounds (grow_chain), usually one round per set;
 //  * the rectangle sums keep the scalar loop's summation order (three lanes own one accumulator each).
-// (A variant with four images per warp — 8 lanes per image, lock-step state machine — was measured: same instruction
-// count per image, 4x the latency; one warp per image is kept.)
+// Measured and rejected (all parity-green): four images per warp (same instruction count, 4x the latency); 40 / 48
+// warps per SM through register caps (same images/s at a full wave); record prefetch at commit (slower: traffic);
+// 16 list entries per batch and software-pipelined sets of 4 (frontiers are mostly <= 4 pixels wide).
 #define GROW_RING 512
 #define GROW_SETS 2
 

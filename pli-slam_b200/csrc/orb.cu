@@ -54,9 +54,9 @@ __global__ void __launch_bounds__(256) blur_pyramid_kernel(PlfGeom g, const uint
 // empty, cv::FAST(window, minTh, nms) (src/ORBextractor.cc:787-854).  The corner score s = max{t : still a corner} does
 // not depend on the threshold, and for a pixel with s >= t strict 3x3 NMS against thresholded neighbours equals NMS
 // against raw scores, so ONE score map serves both thresholds.  Two kernels:
-//   fast_score_kernel : pixel-parallel score map of every level (32x8 tiles staged in shared memory, all levels in
-//                       one launch); scores below minTh are stored as 0.
-//   fast_cells_kernel : block per cell window: strict NMS restricted to the cell's detection area (neighbours outside
+//   fast_score_kernel : pixel-parallel score map of every level (128x8 tiles staged in shared memory as words, all
+//                       levels in one launch, 4 pixels per thread); scores below minTh are stored as 0.
+//   fast_cells_kernel : warp per cell window: strict NMS restricted to the cell's detection area (neighbours outside
 //                       count as 0, exactly like FAST on the sub-image), ini/min threshold choice, ordered compaction.
 //
 // Corner score by bisection on t with 16-bit arc masks — compare/logic ops only, on purpose: a min/max formulation

@@ -332,8 +332,8 @@ def main():
                        "distinct_pairs_per_rank": distinct,
                        "l2": "inputs larger than L2: %d contexts x %.0f MB of resident images" % (C, 2 * B * W * H / 1e6),
                        "parallelism": "replicas%d (streams sharded, no collective)" % world},
-            "e2e": {"value": e2e, "unit": "stereo pairs/s", "h2d_bytes_per_step": h2d * B * C,
-                    "d2h_bytes_per_step": d2h * B * C, "host_wall_s": round(t_e2e_wall, 4)},
+            "e2e": {"value": e2e, "unit": "stereo pairs/s", "h2d_bytes_per_step": h2d * B * C * world,
+                    "d2h_bytes_per_step": d2h * B * C * world, "host_wall_s": round(t_e2e_wall, 4)},
             "gpu_launches": launches,
             "ms_per_stage": {k: round(v, 4) for k, v in stage_acc.items()},
             "roofline": {"bound": "hbm", "kernel": "lsd_grow_kernel", "achieved": achieved, "peak": peak,

@@ -215,7 +215,7 @@ def main():
         for i, (f, l, r, out) in enumerate(zip(ctxs, hostL, hostR, results)):
             if pending[i]:
                 f.batch_download(B, out)      # D2H of every result array + stream sync
-            f.batch_upload_raw(l.data_ptr(), r.data_ptr(), B, W)
+            f.batch_upload_ptr(l.data_ptr(), r.data_ptr(), B, W)
             f.batch_run(B)
             pending[i] = True
 
@@ -250,7 +250,7 @@ def main():
 
     # inputs resident for the `value` leg
     for f, l, r in zip(ctxs, hostL, hostR):
-        f.batch_upload_raw(l.data_ptr(), r.data_ptr(), B, W)
+        f.batch_upload_ptr(l.data_ptr(), r.data_ptr(), B, W)
     for _ in range(max(args.warmup, 3)):
         step_resident()
     sampler = ClockSampler(local_rank)

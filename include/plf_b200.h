@@ -208,6 +208,25 @@ PLF_API int PLF_FN(get_stage_ms)(plf_ctx* ctx, const char* const** names, const 
 PLF_API void* PLF_FN(stream)(plf_ctx* ctx);
 
 /* ------------------------------------------------------------------------------------------------------ */
+/* The step immediately BEFORE the path: stereo rectification of the raw camera frames.  */
+
+/* Replaces: cv::remap(im, imRect, M1, M2, cv::INTER_LINEAR) (Examples/Stereo/stereo_euroc.cc:166-167; the ROS
+ * nodes do the same, Examples/ROS/PLI_SLAM2/src/ros_stereo_inertial.cc:275-276) with the CV_32F maps of
+ * cv::initUndistortRectifyMap (stereo_euroc.cc:117-118).  8-bit single channel, BORDER_CONSTANT 0, bit-exact
+ * to cv::remap's fixed-point path: source coordinate = cvRound(map * 32) (5 fractional bits), four taps weighted
+ * with 15-bit products of the two fractions, (sum + 2^14) >> 15.
+ * map_x / map_y: height x width floats (the context's image size), row-major, for images of src_w x src_h.   */
+PLF_API int PLF_FN(rectify_set_maps)(plf_ctx* ctx, int side, const float* map_x, const float* map_y,
+                                     int src_w, int src_h);
+/* One raw frame -> one rectified frame (host buffers). */
+PLF_API int PLF_FN(rectify)(plf_ctx* ctx, int side, const uint8_t* raw, int raw_stride, uint8_t* out,
+                            int out_stride);
+/* batch_upload for RAW frames ([batch][src_h][raw_stride]): H2D + rectification on the device, straight into the
+ * slots batch_run works on — the rectified image never exists on the host. */
+PLF_API int PLF_FN(batch_upload_raw)(plf_ctx* ctx, const uint8_t* left_raw, const uint8_t* right_raw, int batch,
+                                     int raw_stride);
+
+/* ------------------------------------------------------------------------------------------------------ */
 /* stage taps for parity tests (slot = batch index, side 0/1).  Not part of the reference interface.       */
 
 PLF_API int PLF_FN(tap_blurred_level)(plf_ctx* ctx, int slot, int side, int level, uint8_t* out, int out_stride);

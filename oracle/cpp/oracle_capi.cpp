@@ -34,6 +34,8 @@ struct plf_ctx {
     int kp_cap = 0, kl_cap = 0;
     int threads = 0;         // worker threads for batch calls (0 = hardware concurrency)
     int batch_resident = 0;
+    std::vector<float> mapx[2], mapy[2];   // rectification maps per camera (plf_cpu_rectify_set_maps)
+    int srcW[2] = {0, 0}, srcH[2] = {0, 0};
 };
 
 static thread_local std::string g_err;
@@ -275,6 +277,39 @@ PLF_API int plf_cpu_batch_upload(plf_ctx* c, const uint8_t* left, const uint8_t*
             const uint8_t* src = (s ? right : left) + (size_t)b * h * stride;
             for (int y = 0; y < h; ++y) std::memcpy(im.row(y), src + (size_t)y * stride, w);
         }
+    c->batch_resident = batch;
+    return PLF_OK;
+}
+
+// ---- rectification --------------------------------------------------------------------
+PLF_API int plf_cpu_rectify_set_maps(plf_ctx* c, int side, const float* mx, const float* my, int src_w, int src_h) {
+    if (!c || side < 0 || side > 1 || !mx || !my || src_w < 2 || src_h < 2) return fail(PLF_ERR_INVALID, "bad rectification maps");
+    const size_t n = (size_t)c->p.width * c->p.height;
+    c->mapx[side].assign(mx, mx + n);
+    c->mapy[side].assign(my, my + n);
+    c->srcW[side] = src_w; c->srcH[side] = src_h;
+    return PLF_OK;
+}
+static void rectify_one(plf_ctx* c, int side, const uint8_t* raw, int stride, Img8& dst) {
+    Img8 src(c->srcW[side], c->srcH[side]);
+    for (int y = 0; y < src.h; ++y) std::memcpy(src.row(y), raw + (size_t)y * stride, src.w);
+    remap_linear_u8(src, dst, c->mapx[side].data(), c->mapy[side].data(), c->p.width, c->p.height);
+}
+PLF_API int plf_cpu_rectify(plf_ctx* c, int side, const uint8_t* raw, int raw_stride, uint8_t* out, int out_stride) {
+    if (!c || side < 0 || side > 1 || !raw || !out) return fail(PLF_ERR_INVALID, "bad arguments");
+    if (c->mapx[side].empty()) return fail(PLF_ERR_STATE, "rectify before rectify_set_maps");
+    if (raw_stride < c->srcW[side] || out_stride < c->p.width) return fail(PLF_ERR_INVALID, "bad stride");
+    Img8 dst;
+    rectify_one(c, side, raw, raw_stride, dst);
+    for (int y = 0; y < dst.h; ++y) std::memcpy(out + (size_t)y * out_stride, dst.row(y), dst.w);
+    return PLF_OK;
+}
+PLF_API int plf_cpu_batch_upload_raw(plf_ctx* c, const uint8_t* left, const uint8_t* right, int batch, int stride) {
+    if (!c || !left || !right || batch < 1 || batch > (int)c->slots.size()) return fail(PLF_ERR_INVALID, "bad batch");
+    if (c->mapx[0].empty() || c->mapx[1].empty()) return fail(PLF_ERR_STATE, "batch_upload_raw before rectify_set_maps");
+    for (int b = 0; b < batch; ++b)
+        for (int s = 0; s < 2; ++s)
+            rectify_one(c, s, (s ? right : left) + (size_t)b * c->srcH[s] * stride, stride, c->slots[b].img[s]);
     c->batch_resident = batch;
     return PLF_OK;
 }

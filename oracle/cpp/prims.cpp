@@ -159,4 +159,34 @@ void sobel3_16s(const Img8& src, Img16& dx, Img16& dy) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// cv::remap, 8UC1, INTER_LINEAR, BORDER_CONSTANT(0), planar CV_32F maps (OpenCV imgproc remap: RemapInvoker +
+// remapBilinear<FixedPtCast<int, uchar, 15>>; call site Examples/Stereo/stereo_euroc.cc:166-167).
+//  * sx = cvRound(mapx * 32), sy = cvRound(mapy * 32) (round half to even); integer part = saturate_cast<short>(s >> 5),
+//    fraction index (sy & 31) * 32 + (sx & 31);
+//  * weights = saturate_cast<short>(wy * wx * 32768) with wx in {1 - fx/32, fx/32}; all are exact integers
+//    32 * (32 - fy or fy) * (32 - fx or fx); the only saturation is the (0, 0) entry, 32768 -> 32767, whose missing unit
+//    OpenCV's table fix-up adds to the LAST tap, giving {32767, 0, 0, 1};
+//  * out = (sum of tap * weight + 2^14) >> 15; a tap outside the source counts as 0.
+void remap_linear_u8(const Img8& src, Img8& dst, const float* mapx, const float* mapy, int dw, int dh) {
+    dst = Img8(dw, dh);
+    auto sat16 = [](int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); };
+    for (int y = 0; y < dh; ++y)
+        for (int x = 0; x < dw; ++x) {
+            const size_t i = (size_t)y * dw + x;
+            const int fxs = cv_roundf(mapx[i] * 32.f), fys = cv_roundf(mapy[i] * 32.f);
+            const int sx = sat16(fxs >> 5), sy = sat16(fys >> 5);
+            const int fx = fxs & 31, fy = fys & 31;
+            int w[4] = {32 * (32 - fy) * (32 - fx), 32 * (32 - fy) * fx, 32 * fy * (32 - fx), 32 * fy * fx};
+            if (fx == 0 && fy == 0) { w[0] = 32767; w[3] = 1; }
+            auto tap = [&](int yy, int xx) -> int {
+                return (xx >= 0 && yy >= 0 && xx < src.w && yy < src.h) ? src.at(yy, xx) : 0;
+            };
+            const int sum = tap(sy, sx) * w[0] + tap(sy, sx + 1) * w[1] + tap(sy + 1, sx) * w[2] + tap(sy + 1, sx + 1) * w[3];
+            const int v = (sum + (1 << 14)) >> 15;
+            dst.row(y)[x] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+}
+
 }  // namespace plfo

@@ -55,6 +55,9 @@ void resize_linear_exact_u8(const Img8& src, Img8& dst, double scale);
 void gaussian_blur_u8(const Img8& src, Img8& dst, const int* taps, int ksize);
 // cv::Sobel(8U -> 16S, ksize 3, REFLECT_101), call site binary_descriptor_custom.cpp:395-396.
 void sobel3_16s(const Img8& src, Img16& dx, Img16& dy);
+// cv::remap(src, dst, mapx, mapy, INTER_LINEAR, BORDER_CONSTANT, 0) for 8UC1 with CV_32FC1 maps (the call of
+// Examples/Stereo/stereo_euroc.cc:166-167), restated from OpenCV's fixed-point path; dst has the size of the maps.
+void remap_linear_u8(const Img8& src, Img8& dst, const float* mapx, const float* mapy, int dw, int dh);
 
 extern const int TAPS_ORB7[7];   // 7x7 sigma 2   : 18 34 48 56 48 34 18
 extern const int TAPS_LBD5[5];   // 5x5 sigma 1   : 14 62 104 62 14

@@ -66,6 +66,7 @@ ABI_SYMBOLS = [
     "match", "frontend_batch", "batch_upload", "batch_run", "batch_download", "sync", "batch_io_bytes",
     "last_launch_count", "set_stage_timing", "get_stage_ms", "stream", "tap_blurred_level", "tap_pyramid_level",
     "tap_fast_candidates", "tap_lsd_scaled", "tap_lsd_angles", "tap_lsd_segments", "tap_lbd_float",
+    "rectify_set_maps", "rectify", "batch_upload_raw",
 ]
 
 
@@ -317,9 +318,33 @@ class Frontend:
         self.lib.check(self.lib.fn("batch_upload")(self.ctx, _ptr(left), _ptr(right), left.shape[0],
                                                    left.strides[1]))
 
-    def batch_upload_raw(self, left_ptr, right_ptr, batch, stride):
+    def batch_upload_ptr(self, left_ptr, right_ptr, batch, stride):
+        """batch_upload from raw host addresses (pinned torch tensors in bench.py)."""
         self.lib.check(self.lib.fn("batch_upload")(self.ctx, C.c_void_p(left_ptr), C.c_void_p(right_ptr), batch,
                                                    stride))
+
+    # ---- rectification (SURVEY §8f rank 2: the cv::remap in front of the path) -------------------------------------
+    def rectify_set_maps(self, side, map_x, map_y, src_w=None, src_h=None):
+        """Maps of cv::initUndistortRectifyMap(..., CV_32F) for one camera: float32 arrays [H, W]."""
+        map_x = np.ascontiguousarray(map_x, np.float32)
+        map_y = np.ascontiguousarray(map_y, np.float32)
+        assert map_x.shape == map_y.shape == (self.params.height, self.params.width)
+        self.lib.check(self.lib.fn("rectify_set_maps")(self.ctx, side, _ptr(map_x), _ptr(map_y),
+                                                       int(src_w or self.params.width), int(src_h or self.params.height)))
+
+    def rectify(self, side, raw):
+        """cv::remap(raw, M1, M2, INTER_LINEAR) -> rectified uint8 [H, W]."""
+        raw = np.ascontiguousarray(raw, np.uint8)
+        out = np.zeros((self.params.height, self.params.width), np.uint8)
+        self.lib.check(self.lib.fn("rectify")(self.ctx, side, _ptr(raw), raw.strides[0], _ptr(out), out.strides[0]))
+        return out
+
+    def batch_upload_raw(self, left_raw, right_raw):
+        """Upload RAW frames [batch, src_h, src_w]; they are rectified on the way into the batch slots."""
+        left_raw = np.ascontiguousarray(left_raw, np.uint8)
+        right_raw = np.ascontiguousarray(right_raw, np.uint8)
+        self.lib.check(self.lib.fn("batch_upload_raw")(self.ctx, _ptr(left_raw), _ptr(right_raw), left_raw.shape[0],
+                                                       left_raw.strides[1]))
 
     def batch_run(self, batch):
         self.lib.check(self.lib.fn("batch_run")(self.ctx, batch))

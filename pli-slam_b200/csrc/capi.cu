@@ -342,7 +342,7 @@ PLF_API int plf_destroy(plf_ctx* c) {
                     c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_rec, c->d_n2max, c->d_seeds,
                     c->d_nSeeds, c->d_n2, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
                     c->d_sobel, c->d_lbd, c->d_ldesc, c->d_rowMask, c->d_dirR, c->d_dmat, c->d_m21, c->d_m12, c->d_disp,
-                    c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage};
+                    c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage, c->d_rmap[0], c->d_rmap[1]};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -643,12 +643,82 @@ PLF_API int plf_batch_upload(plf_ctx* c, const uint8_t* left, const uint8_t* rig
     return PLF_OK;
 }
 
+// ---- rectification: cv::remap in front of the path ------------------------------------------------
+static cudaError_t stage_reserve(plf_ctx* c, size_t bytes) {
+    if (c->stageCap >= bytes) return cudaSuccess;
+    if (c->d_stage) { cudaStreamSynchronize(c->stream); cudaFree(c->d_stage); }
+    c->d_stage = nullptr;
+    c->stageCap = 0;
+    cudaError_t e = cudaMalloc((void**)&c->d_stage, bytes);
+    if (e == cudaSuccess) c->stageCap = bytes;
+    return e;
+}
+
+PLF_API int plf_rectify_set_maps(plf_ctx* c, int side, const float* mx, const float* my, int src_w, int src_h) {
+    if (!c || side < 0 || side > 1 || !mx || !my || src_w < 2 || src_h < 2 || src_w > 32767 || src_h > 32767)
+        return fail(PLF_ERR_INVALID, "bad rectification maps");
+    PLF_CUDA_OK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->g.W * c->g.H;
+    // cv::remap's own conversion of the float maps: cvRound(map * 32) (round half to even), integer part saturated
+    // to int16, 5-bit fractions; done once here instead of once per frame
+    std::vector<uint2> t(n);
+    auto sat16 = [](int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); };
+    for (size_t i = 0; i < n; ++i) {
+        const int fxs = (int)std::nearbyintf(mx[i] * 32.f), fys = (int)std::nearbyintf(my[i] * 32.f);
+        const int sx = sat16(fxs >> 5), sy = sat16(fys >> 5);
+        t[i].x = (unsigned)(sx & 0xFFFF) | ((unsigned)(sy & 0xFFFF) << 16);
+        t[i].y = (unsigned)(((fys & 31) << 5) | (fxs & 31));
+    }
+    if (!c->d_rmap[side]) PLF_CUDA_OK(dalloc(&c->d_rmap[side], n));
+    PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
+    PLF_CUDA_OK(cudaMemcpy(c->d_rmap[side], t.data(), n * sizeof(uint2), cudaMemcpyHostToDevice));
+    c->srcW[side] = src_w; c->srcH[side] = src_h;
+    return PLF_OK;
+}
+
+PLF_API int plf_rectify(plf_ctx* c, int side, const uint8_t* raw, int raw_stride, uint8_t* out, int out_stride) {
+    if (!c || side < 0 || side > 1 || !raw || !out) return fail(PLF_ERR_INVALID, "bad arguments");
+    if (!c->d_rmap[side]) return fail(PLF_ERR_STATE, "rectify before rectify_set_maps");
+    if (raw_stride < c->srcW[side] || out_stride < c->g.W) return fail(PLF_ERR_INVALID, "bad stride");
+    PLF_CUDA_OK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->srcH[side] * raw_stride;
+    PLF_CUDA_OK(stage_reserve(c, bytes));
+    PLF_CUDA_OK(cudaMemcpyAsync(c->d_stage, raw, bytes, cudaMemcpyHostToDevice, c->stream));
+    plf_launch_rectify(c, c->d_stage, c->d_stage, raw_stride, side, 1);      // slot 0, image index = side
+    c->orbValid[side] = c->lineValid[side] = false;                         // level 0 of slot 0 was overwritten
+    const PlfLevel& l0 = c->g.lv[0];
+    PLF_CUDA_OK(cudaMemcpy2DAsync(out, out_stride, c->d_pyr + (size_t)side * c->g.pyrBytes + l0.off, l0.pitch, c->g.W, c->g.H,
+                                  cudaMemcpyDeviceToHost, c->stream));
+    PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
+    PLF_CUDA_OK(cudaGetLastError());
+    return PLF_OK;
+}
+
+PLF_API int plf_batch_upload_raw(plf_ctx* c, const uint8_t* left, const uint8_t* right, int batch, int raw_stride) {
+    if (!c || !left || !right || batch < 1 || batch > c->p.max_batch) return fail(PLF_ERR_INVALID, "bad batch");
+    if (!c->d_rmap[0] || !c->d_rmap[1]) return fail(PLF_ERR_STATE, "batch_upload_raw before rectify_set_maps");
+    if (raw_stride < c->srcW[0] || raw_stride < c->srcW[1]) return fail(PLF_ERR_INVALID, "bad stride");
+    PLF_CUDA_OK(cudaSetDevice(c->device));
+    c->nMarks = 0;
+    plf_mark(c, "h2d");
+    const size_t b0 = (size_t)batch * c->srcH[0] * raw_stride, b1 = (size_t)batch * c->srcH[1] * raw_stride;
+    const size_t off1 = (b0 + 255) & ~(size_t)255;
+    PLF_CUDA_OK(stage_reserve(c, (((size_t)c->p.max_batch * c->srcH[0] * raw_stride + 255) & ~(size_t)255) +
+                                     (size_t)c->p.max_batch * c->srcH[1] * raw_stride));
+    PLF_CUDA_OK(cudaMemcpyAsync(c->d_stage, left, b0, cudaMemcpyHostToDevice, c->stream));
+    PLF_CUDA_OK(cudaMemcpyAsync(c->d_stage + off1, right, b1, cudaMemcpyHostToDevice, c->stream));
+    plf_mark(c, "rectify");
+    plf_launch_rectify(c, c->d_stage, c->d_stage + off1, raw_stride, 0, 2 * batch);
+    c->batchResident = batch;
+    return PLF_OK;
+}
+
 PLF_API int plf_batch_run(plf_ctx* c, int batch) {
     if (!c || batch < 1 || batch > c->batchResident) return fail(PLF_ERR_INVALID, "bad batch (upload first)");
     PLF_CUDA_OK(cudaSetDevice(c->device));
     int n = 0;
     if (c->nMarks && strcmp(c->markNames[0], "h2d") != 0) c->nMarks = 0;   // run without a fresh upload: restart marks
-    if (c->nMarks > 1) c->nMarks = 0;
+    if (c->nMarks > 1 && !(c->nMarks == 2 && strcmp(c->markNames[1], "rectify") == 0)) c->nMarks = 0;
     n += plf_launch_orb(c, 0, 2 * batch, 0, 0);
     if (c->p.has_lines) n += plf_launch_lines(c, 0, 2 * batch);
     if (c->p.has_lines) n += plf_launch_stereo_lines(c, 0, batch);

@@ -126,6 +126,10 @@ struct plf_ctx {
     uint8_t* d_mA = nullptr; uint8_t* d_mB = nullptr; int* d_mOut = nullptr; int* d_mOut2 = nullptr; int mCap = 0;
     uint8_t* d_stage = nullptr;      // [2][batch][H][stride] bulk H2D landing zone of plf_batch_upload
     size_t stageCap = 0;
+    // rectification (cv::remap in front of the path): per camera, per output pixel {x | y << 16 (int16 source
+    // position), (fy << 5) | fx (5-bit fractions)} — cv::remap's fixed-point form of the float maps, built once
+    uint2* d_rmap[2] = {nullptr, nullptr};
+    int srcW[2] = {0, 0}, srcH[2] = {0, 0};
     // pinned host staging for small result reads
     int* h_counts = nullptr;         // pinned
     // state
@@ -147,6 +151,7 @@ void plf_mark(plf_ctx* c, const char* name);
 // --- stage launchers (each returns the number of kernel launches it issued) ---------------------------------------
 int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1);
 int plf_launch_unpack(plf_ctx* c, const uint8_t* stage, size_t sideBytes, int stride, int batch);
+int plf_launch_rectify(plf_ctx* c, const uint8_t* raw0, const uint8_t* raw1, int rawStride, int imgFirst, int nImg);
 int plf_launch_stereo_points(plf_ctx* c, int slotFirst, int nSlots);
 int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg);
 int plf_launch_stereo_lines(plf_ctx* c, int slotFirst, int nSlots);

@@ -91,3 +91,43 @@ def synth_batch(W, H, seeds):
     for i, s in enumerate(seeds):
         L[i], R[i] = synth_pair(W, H, int(s))
     return L, R
+
+
+# EuRoC MAV stereo calibration (Examples/Stereo/Config/EuRoC.yaml:42-84 of the reference: LEFT/RIGHT .K .D .R .P)
+EUROC_CALIB = {
+    0: dict(K=[458.654, 0.0, 367.215, 0.0, 457.296, 248.375, 0.0, 0.0, 1.0],
+            D=[-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0],
+            R=[0.999966347530033, -0.001422739138722922, 0.008079580483432283, 0.001365741834644127,
+               0.9999741760894847, 0.007055629199258132, -0.008089410156878961, -0.007044357138835809,
+               0.9999424675829176],
+            P=[435.2046959714599, 0, 367.4517211914062, 0, 0, 435.2046959714599, 252.2008514404297, 0, 0, 0, 1, 0]),
+    1: dict(K=[457.587, 0.0, 379.999, 0.0, 456.134, 255.238, 0.0, 0.0, 1],
+            D=[-0.28368365, 0.07451284, -0.00010473, -3.555907e-05, 0.0],
+            R=[0.9999633526194376, -0.003625811871560086, 0.007755443660172947, 0.003680398547259526,
+               0.9999684752771629, -0.007035845251224894, -0.007729688520722713, 0.007064130529506649,
+               0.999945173484644],
+            P=[435.2046959714599, 0, 367.4517211914062, -47.90639384423901, 0, 435.2046959714599,
+               252.2008514404297, 0, 0, 0, 1, 0]),
+}
+
+
+def rectify_maps(W=752, H=480, side=0):
+    """Undistort-rectify maps (float32 [H, W] x, y) of one EuRoC camera: the standard pinhole + radial/tangential model
+    that cv::initUndistortRectifyMap(K, D, R, P[:3,:3], size, CV_32F) evaluates (stereo_euroc.cc:117-118), in numpy
+    double precision.  Used to exercise the rectification kernel with realistic maps without needing cv2."""
+    c = EUROC_CALIB[side]
+    K = np.array(c["K"], np.float64).reshape(3, 3)
+    k1, k2, p1, p2, k3 = c["D"]
+    R = np.array(c["R"], np.float64).reshape(3, 3)
+    Pn = np.array(c["P"], np.float64).reshape(3, 4)[:3, :3]
+    iR = np.linalg.inv(Pn @ R)
+    u, v = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    X = iR[0, 0] * u + iR[0, 1] * v + iR[0, 2]
+    Y = iR[1, 0] * u + iR[1, 1] * v + iR[1, 2]
+    Wd = iR[2, 0] * u + iR[2, 1] * v + iR[2, 2]
+    x, y = X / Wd, Y / Wd
+    r2 = x * x + y * y
+    kr = 1 + ((k3 * r2 + k2) * r2 + k1) * r2
+    xd = x * kr + p1 * 2 * x * y + p2 * (r2 + 2 * x * x)
+    yd = y * kr + p1 * (r2 + 2 * y * y) + p2 * 2 * x * y
+    return (K[0, 0] * xd + K[0, 2]).astype(np.float32), (K[1, 1] * yd + K[1, 2]).astype(np.float32)

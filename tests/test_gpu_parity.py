@@ -257,3 +257,62 @@ def test_degenerate_images(plf, product, oracle):
     if n and nl:
         assert np.array_equal(rg.u_right[b, :n], ro.u_right[b, :n])
         assert np.array_equal(rg.line_match12[b, :nl], ro.line_match12[b, :nl])
+
+
+# ---- stereo rectification in front of the path ---------------------------------------------------
+def test_rectify_matches_oracle(plf, product, oracle):
+    """plf_rectify == the oracle's cv::remap restatement (itself pinned to cv2.remap) bit for bit: EuRoC maps of both
+    cameras, random maps with taps outside the source, integer positions and rounding ties, another source size."""
+    W, H = 752, 480
+    f, o = plf.Frontend(product, max_batch=1), plf.Frontend(oracle, max_batch=1)
+    L, R = plf.synth_pair(W, H, 11)
+    for side, raw in ((0, L), (1, R)):
+        mx, my = plf.rectify_maps(W, H, side)
+        f.rectify_set_maps(side, mx, my); o.rectify_set_maps(side, mx, my)
+        assert np.array_equal(f.rectify(side, raw), o.rectify(side, raw))
+    rng = np.random.default_rng(0)
+    raw = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    mx = rng.uniform(-20, W + 20, (H, W)).astype(np.float32)
+    my = rng.uniform(-20, H + 20, (H, W)).astype(np.float32)
+    mx[::7, ::5] = np.round(mx[::7, ::5]); my[::7, ::5] = np.round(my[::7, ::5])
+    mx[5, :64] = np.arange(64) + 0.5 / 32; my[5, :64] = 10 + 1.5 / 32
+    f.rectify_set_maps(0, mx, my); o.rectify_set_maps(0, mx, my)
+    assert np.array_equal(f.rectify(0, raw), o.rectify(0, raw))
+    small = rng.integers(0, 256, (300, 400), dtype=np.uint8)
+    mx = rng.uniform(-5, 405, (H, W)).astype(np.float32)
+    my = rng.uniform(-5, 305, (H, W)).astype(np.float32)
+    f.rectify_set_maps(1, mx, my, 400, 300); o.rectify_set_maps(1, mx, my, 400, 300)
+    assert np.array_equal(f.rectify(1, small), o.rectify(1, small))
+    # odd output width: the tail threads store single bytes
+    f2, o2 = plf.Frontend(product, width=641, height=479, max_batch=1), plf.Frontend(oracle, width=641, height=479, max_batch=1)
+    mx = rng.uniform(0, 640, (479, 641)).astype(np.float32); my = rng.uniform(0, 478, (479, 641)).astype(np.float32)
+    raw = rng.integers(0, 256, (479, 641), dtype=np.uint8)
+    f2.rectify_set_maps(0, mx, my); o2.rectify_set_maps(0, mx, my)
+    assert np.array_equal(f2.rectify(0, raw), o2.rectify(0, raw))
+
+
+def test_raw_upload_equals_rectified_upload(plf, product, oracle):
+    """batch_upload_raw (H2D + rectification on the device) + batch_run gives exactly the results of uploading the
+    rectified frames, and the oracle agrees; calling it before the maps are set is a state error."""
+    W, H = 752, 480
+    Lr, Rr = plf.synth_batch(W, H, [41, 42, 43])
+    f, o = plf.Frontend(product, max_batch=3), plf.Frontend(oracle, max_batch=3)
+    with pytest.raises(plf.PlfError):
+        f.batch_upload_raw(Lr, Rr)
+    for side in (0, 1):
+        mx, my = plf.rectify_maps(W, H, side)
+        f.rectify_set_maps(side, mx, my); o.rectify_set_maps(side, mx, my)
+    Lc = np.stack([o.rectify(0, im) for im in Lr]); Rc = np.stack([o.rectify(1, im) for im in Rr])
+    ref = f.frontend_batch(Lc, Rc)
+    out = f.new_result(3)
+    f.batch_upload_raw(Lr, Rr); f.batch_run(3); f.batch_download(3, out)
+    oo = o.new_result(3)
+    o.batch_upload_raw(Lr, Rr); o.batch_run(3); o.batch_download(3, oo)
+    for b in range(3):
+        n, nl = int(ref.n_kp_left[b]), int(ref.n_kl_left[b])
+        assert n > 500 and nl > 50
+        for r in (out, oo):
+            assert int(r.n_kp_left[b]) == n and int(r.n_kl_left[b]) == nl
+            assert np.array_equal(r.kp_left[b, :n], ref.kp_left[b, :n]) and np.array_equal(r.desc_left[b, :n], ref.desc_left[b, :n])
+            assert np.array_equal(r.kl_left[b, :nl], ref.kl_left[b, :nl]) and np.array_equal(r.ldesc_left[b, :nl], ref.ldesc_left[b, :nl])
+            assert np.array_equal(r.u_right[b, :n], ref.u_right[b, :n]) and np.array_equal(r.line_match12[b, :nl], ref.line_match12[b, :nl])

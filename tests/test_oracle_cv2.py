@@ -191,3 +191,45 @@ def test_lsd_refine_standard_vs_cv2(oracle, plf, w, h, seed):
         n = C.c_int(0)
         assert oracle.dll.plf_cpu_prim_lsd(_p(img), w, h, C.c_double(1.2), 1 | (1 << 4), _p(out), 20000, C.byref(n)) == 0
         assert n.value == len(ref) and np.array_equal(out[:n.value], ref)
+
+
+# ---- stereo rectification, cv::remap(INTER_LINEAR) with CV_32F maps -------------------------------
+def _euroc_maps_cv2(plf, side, w=752, h=480):
+    c = plf.EUROC_CALIB[side]
+    return cv2.initUndistortRectifyMap(np.array(c["K"], np.float64).reshape(3, 3), np.array(c["D"], np.float64),
+                                       np.array(c["R"], np.float64).reshape(3, 3),
+                                       np.array(c["P"], np.float64).reshape(3, 4)[:3, :3], (w, h), cv2.CV_32F)
+
+
+@pytest.mark.parametrize("side", [0, 1])
+def test_remap_euroc_vs_cv2(plf, oracle, side):
+    """The oracle's remap equals cv2.remap bit for bit on the EuRoC rectification maps (stereo_euroc.cc:117-118,166-167);
+    the numpy map generator used by the GPU tests equals cv2.initUndistortRectifyMap."""
+    m1, m2 = _euroc_maps_cv2(plf, side)
+    a, b = plf.rectify_maps(752, 480, side)
+    assert np.array_equal(a, m1) and np.array_equal(b, m2)
+    raw = plf.synth_pair(752, 480, 11)[side]
+    f = plf.Frontend(oracle, max_batch=1)
+    f.rectify_set_maps(side, m1, m2)
+    assert np.array_equal(f.rectify(side, raw), cv2.remap(raw, m1, m2, cv2.INTER_LINEAR))
+
+
+def test_remap_edge_cases_vs_cv2(plf, oracle):
+    """Taps outside the source (BORDER_CONSTANT 0), exact integer positions (the saturated 32767/1 table entry),
+    half-way roundings of map * 32, a source size different from the output size."""
+    rng = np.random.default_rng(0)
+    W, H = 752, 480
+    f = plf.Frontend(oracle, max_batch=1)
+    raw = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    mx = rng.uniform(-20, W + 20, (H, W)).astype(np.float32)
+    my = rng.uniform(-20, H + 20, (H, W)).astype(np.float32)
+    mx[::7, ::5] = np.round(mx[::7, ::5]); my[::7, ::5] = np.round(my[::7, ::5])
+    mx[5, :64] = np.arange(64) + 0.5 / 32; my[5, :64] = 10 + 1.5 / 32        # ties of cvRound(map * 32)
+    mx[6, :64] = -1 + np.arange(64) / 64.0; my[6, :64] = -1 + np.arange(64) / 64.0
+    f.rectify_set_maps(0, mx, my)
+    assert np.array_equal(f.rectify(0, raw), cv2.remap(raw, mx, my, cv2.INTER_LINEAR))
+    small = rng.integers(0, 256, (300, 400), dtype=np.uint8)
+    mx = rng.uniform(-5, 405, (H, W)).astype(np.float32)
+    my = rng.uniform(-5, 305, (H, W)).astype(np.float32)
+    f.rectify_set_maps(1, mx, my, 400, 300)
+    assert np.array_equal(f.rectify(1, small), cv2.remap(small, mx, my, cv2.INTER_LINEAR))

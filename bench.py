@@ -156,6 +156,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per camera stream per call (BASELINE config C2)")
     ap.add_argument("--streams", type=int, default=8, help="independent camera streams served by one context")
+    ap.add_argument("--rectify", action="store_true",
+                    help="e2e leg starts from RAW frames: upload + cv::remap rectification on the device (SURVEY 8f rank 2)")
     ap.add_argument("--contexts", type=int, default=6, help="calls kept in flight per GPU (one CUDA stream each)")
     ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic pairs generated per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -194,6 +196,9 @@ def main():
         idx = (np.arange(B) * 7 + ci * 11) % distinct
         l = torch.from_numpy(np.ascontiguousarray(Ld[idx])).pin_memory()
         r = torch.from_numpy(np.ascontiguousarray(Rd[idx])).pin_memory()
+        if args.rectify:
+            for side in (0, 1):
+                f.rectify_set_maps(side, *plf.rectify_maps(W, H, side))
         ctxs.append(f); hostL.append(l); hostR.append(r); results.append(f.new_result(B, pinned=True))
     ext = [torch.cuda.ExternalStream(f.stream(), device=local_rank) for f in ctxs]
     main_stream = torch.cuda.current_stream()
@@ -215,7 +220,10 @@ def main():
         for i, (f, l, r, out) in enumerate(zip(ctxs, hostL, hostR, results)):
             if pending[i]:
                 f.batch_download(B, out)      # D2H of every result array + stream sync
-            f.batch_upload_ptr(l.data_ptr(), r.data_ptr(), B, W)
+            if args.rectify:
+                f.batch_upload_raw_ptr(l.data_ptr(), r.data_ptr(), B, W)
+            else:
+                f.batch_upload_ptr(l.data_ptr(), r.data_ptr(), B, W)
             f.batch_run(B)
             pending[i] = True
 
@@ -295,6 +303,8 @@ def main():
     stage_acc = {}
     reps = 3
     for _ in range(reps):
+        if args.rectify:
+            f0.batch_upload_raw_ptr(hostL[0].data_ptr(), hostR[0].data_ptr(), B, W)
         f0.batch_run(B)
         f0.batch_download(B, results[0])
         for k, v in f0.stage_ms().items():
@@ -329,6 +339,7 @@ def main():
             "config": {"workload": "euroc_752x480_stereo_pointline_batch64", "width": W, "height": H, **WORKLOAD,
                        "frames_per_stream": args.batch, "streams_per_context": args.streams, "pairs_per_call": B,
                        "contexts_in_flight": C, "pairs_per_step": pairs_per_step,
+                       "e2e_input": "raw frames, rectified on the device" if args.rectify else "rectified frames",
                        "distinct_pairs_per_rank": distinct,
                        "l2": "inputs larger than L2: %d contexts x %.0f MB of resident images" % (C, 2 * B * W * H / 1e6),
                        "parallelism": "replicas%d (streams sharded, no collective)" % world},

@@ -339,6 +339,10 @@ class Frontend:
         self.lib.check(self.lib.fn("rectify")(self.ctx, side, _ptr(raw), raw.strides[0], _ptr(out), out.strides[0]))
         return out
 
+    def batch_upload_raw_ptr(self, left_ptr, right_ptr, batch, stride):
+        self.lib.check(self.lib.fn("batch_upload_raw")(self.ctx, C.c_void_p(left_ptr), C.c_void_p(right_ptr), batch,
+                                                       stride))
+
     def batch_upload_raw(self, left_raw, right_raw):
         """Upload RAW frames [batch, src_h, src_w]; they are rectified on the way into the batch slots."""
         left_raw = np.ascontiguousarray(left_raw, np.uint8)

@@ -180,4 +180,22 @@ private:
     std::shared_ptr<plf::Context> ctx_;
 };
 
+// The rectification in front of Frame (Examples/Stereo/stereo_euroc.cc:117-118,166-167):
+//   cv::initUndistortRectifyMap(K, D, R, P, size, CV_32F, M1, M2)  ->  Rectifier::setMaps(side, M1, M2, src size)
+//   cv::remap(im, imRect, M1, M2, cv::INTER_LINEAR)                ->  Rectifier::remap(side, im, imRect)
+class Rectifier {
+public:
+    explicit Rectifier(std::shared_ptr<plf::Context> ctx) : ctx_(ctx) {}
+    void setMaps(int side, const float* M1, const float* M2, int srcCols, int srcRows) {
+        plf::check(plf_rectify_set_maps(ctx_->get(), side, M1, M2, srcCols, srcRows), "plf_rectify_set_maps");
+    }
+    void remap(int side, const plf::Mat8& im, std::vector<uint8_t>& imRect) {
+        const int w = ctx_->params.width, h = ctx_->params.height;
+        imRect.resize((size_t)w * h);
+        plf::check(plf_rectify(ctx_->get(), side, im.data, im.step, imRect.data(), w), "plf_rectify");
+    }
+private:
+    std::shared_ptr<plf::Context> ctx_;
+};
+
 }  // namespace ORB_SLAM3

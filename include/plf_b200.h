@@ -15,6 +15,7 @@
 #ifndef PLF_B200_H
 #define PLF_B200_H
 
+#include <math.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -227,6 +228,19 @@ PLF_API int PLF_FN(batch_upload_raw)(plf_ctx* ctx, const uint8_t* left_raw, cons
                                      int raw_stride);
 
 /* ------------------------------------------------------------------------------------------------------ */
+/* The last step of Frame::Frame(stereo) and the lookup it serves (first half).           */
+
+#define PLF_GRID_COLS 64   /* FRAME_GRID_COLS, include/Frame.h:60 */
+#define PLF_GRID_ROWS 48   /* FRAME_GRID_ROWS, include/Frame.h:59 */
+/* Replaces: void Frame::AssignFeaturesToGrid() (src/Frame.cc:451-482, called at :204) with PosInGrid (:845-855) for
+ * the left keypoints of slots [first_slot, first_slot + n_slots) (undistorted = detected keypoints for rectified
+ * stereo; image bounds 0..width, 0..height as ComputeImageBounds sets them without distortion, :967-973).
+ * mGrid[x][y] becomes CSR: cell = x * PLF_GRID_ROWS + y, cell_start[n_slots][64*48+1], cell_idx[n_slots][idx_stride]
+ * (keypoint indices in ascending order inside a cell = push_back order). */
+PLF_API int PLF_FN(feature_grid)(plf_ctx* ctx, int first_slot, int n_slots, int32_t* cell_start, int32_t* cell_idx,
+                                 int idx_stride);
+
+/* ------------------------------------------------------------------------------------------------------ */
 /* stage taps for parity tests (slot = batch index, side 0/1).  Not part of the reference interface.       */
 
 PLF_API int PLF_FN(tap_blurred_level)(plf_ctx* ctx, int slot, int side, int level, uint8_t* out, int out_stride);
@@ -242,6 +256,49 @@ PLF_API int PLF_FN(tap_lsd_angles)(plf_ctx* ctx, int slot, int side, float* out,
 PLF_API int PLF_FN(tap_lsd_segments)(plf_ctx* ctx, int slot, int side, float* xyxy, int cap, int* n);
 /* LBD float descriptor (72 floats per line) before binarisation. */
 PLF_API int PLF_FN(tap_lbd_float)(plf_ctx* ctx, int slot, int side, float* out, int cap, int* n);
+
+/* Replaces: vector<size_t> Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel, bRight=false)
+ * (src/Frame.cc:774-843) on the CSR grid of plf_feature_grid: indices of the keypoints with |dx| < r and |dy| < r
+ * whose octave lies in [minLevel, maxLevel] (levels checked iff minLevel > 0 or maxLevel >= 0), in cell-column, cell-
+ * row, push_back order.  Pure host inline; returns the count (at most `cap` are written). */
+static inline int plf_features_in_area(const plf_keypoint* kps, const int32_t* cell_start, const int32_t* cell_idx,
+                                       int width, int height, float x, float y, float r, int min_level,
+                                       int max_level, int32_t* out, int cap) {
+    const float inv_w = (float)PLF_GRID_COLS / ((float)width - 0.0f), inv_h = (float)PLF_GRID_ROWS / ((float)height - 0.0f);
+    int x0 = (int)floorf((x - 0.0f - r) * inv_w), x1 = (int)ceilf((x - 0.0f + r) * inv_w);
+    int y0 = (int)floorf((y - 0.0f - r) * inv_h), y1 = (int)ceilf((y - 0.0f + r) * inv_h);
+    if (x0 < 0) x0 = 0;
+    if (x0 >= PLF_GRID_COLS) return 0;
+    if (x1 > PLF_GRID_COLS - 1) x1 = PLF_GRID_COLS - 1;
+    if (x1 < 0) return 0;
+    if (y0 < 0) y0 = 0;
+    if (y0 >= PLF_GRID_ROWS) return 0;
+    if (y1 > PLF_GRID_ROWS - 1) y1 = PLF_GRID_ROWS - 1;
+    if (y1 < 0) return 0;
+    const int check = (min_level > 0) || (max_level >= 0);
+    int n = 0;
+    for (int ix = x0; ix <= x1; ++ix)
+        for (int iy = y0; iy <= y1; ++iy) {
+            const int c = ix * PLF_GRID_ROWS + iy;
+            for (int j = cell_start[c]; j < cell_start[c + 1]; ++j) {
+                const plf_keypoint* k = kps + cell_idx[j];
+                if (check) {
+                    if (k->octave < min_level) continue;
+                    if (max_level >= 0 && k->octave > max_level) continue;
+                }
+                if (fabsf(k->x - x) < r && fabsf(k->y - y) < r) {
+                    if (n < cap) out[n] = cell_idx[j];
+                    ++n;
+                }
+            }
+        }
+    return n;
+}
+
+/* The same lookup as an exported symbol (for bindings that cannot use a C inline). */
+PLF_API int PLF_FN(get_features_in_area)(const plf_keypoint* kps, const int32_t* cell_start, const int32_t* cell_idx,
+                                         int width, int height, float x, float y, float r, int min_level,
+                                         int max_level, int32_t* out, int cap);
 
 /* Replaces: static int ORBmatcher::DescriptorDistance(const Mat&, const Mat&) (include/ORBmatcher.h:42,
  * src/ORBmatcher.cc:2495-2511) and int distance(const Mat&, const Mat&) (src/LineMatcher.cpp:231-247):

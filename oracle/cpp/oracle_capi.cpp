@@ -314,6 +314,38 @@ PLF_API int plf_cpu_batch_upload_raw(plf_ctx* c, const uint8_t* left, const uint
     return PLF_OK;
 }
 
+// ---- Frame::AssignFeaturesToGrid (src/Frame.cc:451-482) + PosInGrid (:845-855), left keypoints, no distortion --------
+PLF_API int plf_cpu_feature_grid(plf_ctx* c, int first_slot, int n_slots, int32_t* cell_start, int32_t* cell_idx, int idx_stride) {
+    if (!c || !cell_start || !cell_idx || first_slot < 0 || n_slots < 1 || first_slot + n_slots > (int)c->slots.size() ||
+        idx_stride < c->kp_cap)
+        return fail(PLF_ERR_INVALID, "bad slot range / idx_stride");
+    constexpr int NC = PLF_GRID_COLS * PLF_GRID_ROWS;
+    const float invW = (float)PLF_GRID_COLS / ((float)c->p.width - 0.0f), invH = (float)PLF_GRID_ROWS / ((float)c->p.height - 0.0f);
+    for (int s = 0; s < n_slots; ++s) {
+        const std::vector<plf_keypoint>& kps = c->slots[first_slot + s].orb[0].kps;
+        std::vector<std::vector<int>> grid(NC);
+        for (int i = 0; i < (int)kps.size(); ++i) {
+            const int px = (int)std::round((kps[i].x - 0.0f) * invW), py = (int)std::round((kps[i].y - 0.0f) * invH);
+            if (px < 0 || px >= PLF_GRID_COLS || py < 0 || py >= PLF_GRID_ROWS) continue;
+            grid[px * PLF_GRID_ROWS + py].push_back(i);
+        }
+        int32_t* st = cell_start + (size_t)s * (NC + 1);
+        int32_t* ix = cell_idx + (size_t)s * idx_stride;
+        int n = 0;
+        for (int cidx = 0; cidx < NC; ++cidx) {
+            st[cidx] = n;
+            for (int i : grid[cidx]) ix[n++] = i;
+        }
+        st[NC] = n;
+    }
+    return PLF_OK;
+}
+
+PLF_API int plf_cpu_get_features_in_area(const plf_keypoint* kps, const int32_t* cell_start, const int32_t* cell_idx, int width,
+                                         int height, float x, float y, float r, int min_level, int max_level, int32_t* out, int cap) {
+    return plf_features_in_area(kps, cell_start, cell_idx, width, height, x, y, r, min_level, max_level, out, cap);
+}
+
 static void run_pair(plf_ctx* c, int b) {
     Slot& s = c->slots[b];
     const int w = c->p.width, h = c->p.height;

@@ -60,13 +60,15 @@ KEYLINE_DT = np.dtype([("angle", "f4"), ("class_id", "i4"), ("octave", "i4"), ("
 assert KEYPOINT_DT.itemsize == 28 and KEYLINE_DT.itemsize == 68
 
 # every symbol include/plf_b200.h declares (without prefix)
+GRID_COLS, GRID_ROWS = 64, 48      # FRAME_GRID_COLS / FRAME_GRID_ROWS (include/Frame.h:59-60)
+
 ABI_SYMBOLS = [
     "default_params", "create", "destroy", "last_error", "keypoint_capacity", "keyline_capacity", "get_scale_tables",
     "orb_extract", "get_pyramid_level", "line_extract", "stereo_match_points", "stereo_match_lines", "match_nnr",
     "match", "frontend_batch", "batch_upload", "batch_run", "batch_download", "sync", "batch_io_bytes",
     "last_launch_count", "set_stage_timing", "get_stage_ms", "stream", "tap_blurred_level", "tap_pyramid_level",
     "tap_fast_candidates", "tap_lsd_scaled", "tap_lsd_angles", "tap_lsd_segments", "tap_lbd_float",
-    "rectify_set_maps", "rectify", "batch_upload_raw",
+    "rectify_set_maps", "rectify", "batch_upload_raw", "feature_grid", "get_features_in_area",
 ]
 
 
@@ -338,6 +340,22 @@ class Frontend:
         out = np.zeros((self.params.height, self.params.width), np.uint8)
         self.lib.check(self.lib.fn("rectify")(self.ctx, side, _ptr(raw), raw.strides[0], _ptr(out), out.strides[0]))
         return out
+
+    # ---- Frame::AssignFeaturesToGrid / GetFeaturesInArea (first half) -----------------------------
+    def feature_grid(self, first_slot=0, n_slots=1):
+        """CSR of Frame::mGrid for the left keypoints of the slots: (cell_start [n, 64*48+1], cell_idx [n, kp_cap])."""
+        st = np.zeros((n_slots, GRID_COLS * GRID_ROWS + 1), np.int32)
+        ix = np.full((n_slots, self.kp_cap), -1, np.int32)
+        self.lib.check(self.lib.fn("feature_grid")(self.ctx, first_slot, n_slots, _ptr(st), _ptr(ix), self.kp_cap))
+        return st, ix
+
+    def features_in_area(self, kps, cell_start, cell_idx, x, y, r, min_level=-1, max_level=-1):
+        """Frame::GetFeaturesInArea on the CSR grid of one slot -> int32 indices."""
+        out = np.zeros(len(kps) + 1, np.int32)
+        fn = self.lib.fn("get_features_in_area")
+        n = fn(_ptr(np.ascontiguousarray(kps)), _ptr(cell_start), _ptr(cell_idx), self.W, self.H, C.c_float(x), C.c_float(y),
+               C.c_float(r), int(min_level), int(max_level), _ptr(out), len(out))
+        return out[:n].copy()
 
     def batch_upload_raw_ptr(self, left_ptr, right_ptr, batch, stride):
         self.lib.check(self.lib.fn("batch_upload_raw")(self.ctx, C.c_void_p(left_ptr), C.c_void_p(right_ptr), batch,

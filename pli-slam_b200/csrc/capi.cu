@@ -342,7 +342,7 @@ PLF_API int plf_destroy(plf_ctx* c) {
                     c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_rec, c->d_n2max, c->d_seeds,
                     c->d_nSeeds, c->d_n2, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
                     c->d_sobel, c->d_lbd, c->d_ldesc, c->d_rowMask, c->d_dirR, c->d_dmat, c->d_m21, c->d_m12, c->d_disp,
-                    c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage, c->d_rmap[0], c->d_rmap[1]};
+                    c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage, c->d_rmap[0], c->d_rmap[1], c->d_gridStart, c->d_gridIdx};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -641,6 +641,32 @@ PLF_API int plf_batch_upload(plf_ctx* c, const uint8_t* left, const uint8_t* rig
     plf_launch_unpack(c, c->d_stage, sideBytes, stride, batch);
     c->batchResident = batch;
     return PLF_OK;
+}
+
+// ---- Frame::AssignFeaturesToGrid (first half) ---------------------------------------------------------
+PLF_API int plf_feature_grid(plf_ctx* c, int first_slot, int n_slots, int32_t* cell_start, int32_t* cell_idx, int idx_stride) {
+    if (!c || !cell_start || !cell_idx || first_slot < 0 || n_slots < 1 || first_slot + n_slots > c->p.max_batch ||
+        idx_stride < c->g.kpCap)
+        return fail(PLF_ERR_INVALID, "bad slot range / idx_stride smaller than plf_keypoint_capacity");
+    if (!c->orbValid[0]) return fail(PLF_ERR_STATE, "feature_grid before the left keypoints were extracted");
+    PLF_CUDA_OK(cudaSetDevice(c->device));
+    constexpr int NC1 = PLF_GRID_COLS * PLF_GRID_ROWS + 1;
+    if (!c->d_gridStart) {
+        PLF_CUDA_OK(dalloc(&c->d_gridStart, (size_t)c->p.max_batch * NC1));
+        PLF_CUDA_OK(dalloc(&c->d_gridIdx, (size_t)c->p.max_batch * c->g.kpCap));
+    }
+    plf_launch_feature_grid(c, first_slot, n_slots, c->d_gridStart, c->d_gridIdx);
+    PLF_CUDA_OK(cudaMemcpyAsync(cell_start, c->d_gridStart, (size_t)n_slots * NC1 * 4, cudaMemcpyDeviceToHost, c->stream));
+    PLF_CUDA_OK(cudaMemcpy2DAsync(cell_idx, (size_t)idx_stride * 4, c->d_gridIdx, (size_t)c->g.kpCap * 4, (size_t)c->g.kpCap * 4,
+                                  n_slots, cudaMemcpyDeviceToHost, c->stream));
+    PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
+    PLF_CUDA_OK(cudaGetLastError());
+    return PLF_OK;
+}
+
+PLF_API int plf_get_features_in_area(const plf_keypoint* kps, const int32_t* cell_start, const int32_t* cell_idx, int width,
+                                     int height, float x, float y, float r, int min_level, int max_level, int32_t* out, int cap) {
+    return plf_features_in_area(kps, cell_start, cell_idx, width, height, x, y, r, min_level, max_level, out, cap);
 }
 
 // ---- rectification: cv::remap in front of the path ------------------------------------------------

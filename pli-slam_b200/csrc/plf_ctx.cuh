@@ -129,6 +129,8 @@ struct plf_ctx {
     // rectification (cv::remap in front of the path): per camera, per output pixel {x | y << 16 (int16 source
     // position), (fy << 5) | fx (5-bit fractions)} — cv::remap's fixed-point form of the float maps, built once
     uint2* d_rmap[2] = {nullptr, nullptr};
+    int* d_gridStart = nullptr;      // [max_batch][64*48+1] CSR of Frame::mGrid (plf_feature_grid), allocated on first use
+    int* d_gridIdx = nullptr;        // [max_batch][kpCap]
     int srcW[2] = {0, 0}, srcH[2] = {0, 0};
     // pinned host staging for small result reads
     int* h_counts = nullptr;         // pinned
@@ -151,6 +153,7 @@ void plf_mark(plf_ctx* c, const char* name);
 // --- stage launchers (each returns the number of kernel launches it issued) ---------------------------------------
 int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1);
 int plf_launch_unpack(plf_ctx* c, const uint8_t* stage, size_t sideBytes, int stride, int batch);
+int plf_launch_feature_grid(plf_ctx* c, int slotFirst, int nSlots, int* cellStart, int* cellIdx);
 int plf_launch_rectify(plf_ctx* c, const uint8_t* raw0, const uint8_t* raw1, int rawStride, int imgFirst, int nImg);
 int plf_launch_stereo_points(plf_ctx* c, int slotFirst, int nSlots);
 int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg);

@@ -156,6 +156,78 @@ __global__ void __launch_bounds__(1024) stereo_cull_kernel(PlfGeom g, const int*
 
 }  // namespace
 
+namespace {
+// Frame::AssignFeaturesToGrid (src/Frame.cc:451-482) for the left keypoints of one slot per block: the 64 x 48 vectors
+// of keypoint indices become CSR (cell = x * 48 + y).  Histogram in shared memory, block scan, then one warp places the
+// indices in ascending order (lanes sharing a cell are ranked with __match_any_sync), which is the push_back order.
+__global__ void __launch_bounds__(256) feature_grid_kernel(PlfGeom g, const plf_keypoint* kp, const int* nKp, int* cellStart,
+                                                           int* cellIdx, float invW, float invH, int slotFirst) {
+    constexpr int NC = PLF_GRID_COLS * PLF_GRID_ROWS;
+    __shared__ int s_cnt[NC + 1];
+    __shared__ int s_part[256];
+    const int slot = slotFirst + blockIdx.x, img = slot * 2, tid = threadIdx.x;
+    const plf_keypoint* K = kp + (size_t)img * g.kpCap;
+    const int N = nKp[img];
+    int* outStart = cellStart + (size_t)blockIdx.x * (NC + 1);
+    int* outIdx = cellIdx + (size_t)blockIdx.x * g.kpCap;
+    auto cell_of = [&](int i) -> int {          // PosInGrid (src/Frame.cc:845-855): round() half away from zero
+        const int px = (int)roundf(__fmul_rn(__fsub_rn(K[i].x, 0.0f), invW)), py = (int)roundf(__fmul_rn(__fsub_rn(K[i].y, 0.0f), invH));
+        return (px < 0 || px >= PLF_GRID_COLS || py < 0 || py >= PLF_GRID_ROWS) ? -1 : px * PLF_GRID_ROWS + py;
+    };
+    for (int i = tid; i <= NC; i += 256) s_cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < N; i += 256) {
+        const int c = cell_of(i);
+        if (c >= 0) atomicAdd(&s_cnt[c], 1);
+    }
+    __syncthreads();
+    // exclusive scan: 12 consecutive cells per thread, then the 256 partial sums
+    constexpr int PER = NC / 256;
+    int loc[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { loc[k] = sum; sum += s_cnt[tid * PER + k]; }
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        const int v = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    const int base = s_part[tid] - sum;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        s_cnt[tid * PER + k] = base + loc[k];              // becomes the write cursor of the cell
+        outStart[tid * PER + k] = base + loc[k];
+    }
+    if (tid == 255) outStart[NC] = s_part[255];
+    __syncthreads();
+    if (tid < 32) {
+        const unsigned lt = (1u << tid) - 1u;
+        for (int b = 0; b < N; b += 32) {
+            const int i = b + tid;
+            const int c = i < N ? cell_of(i) : -1;
+            const unsigned grp = __match_any_sync(0xffffffffu, c >= 0 ? c : -1 - tid);
+            int at = 0;
+            if (c >= 0) at = s_cnt[c];
+            __syncwarp();
+            if (c >= 0) {
+                if ((grp & lt) == 0u) s_cnt[c] = at + __popc(grp);
+                outIdx[at + __popc(grp & lt)] = i;
+            }
+            __syncwarp();
+        }
+    }
+}
+}  // namespace
+
+int plf_launch_feature_grid(plf_ctx* c, int slotFirst, int nSlots, int* cellStart, int* cellIdx) {
+    const PlfGeom& g = c->g;
+    const float invW = (float)PLF_GRID_COLS / ((float)g.W - 0.0f), invH = (float)PLF_GRID_ROWS / ((float)g.H - 0.0f);
+    feature_grid_kernel<<<nSlots, 256, 0, c->stream>>>(g, c->d_kp, c->d_nKp, cellStart, cellIdx, invW, invH, slotFirst);
+    return 1;
+}
+
 int plf_launch_stereo_points(plf_ctx* c, int slotFirst, int nSlots) {
     const PlfGeom& g = c->g;
     plf_mark(c, "stereo_points");

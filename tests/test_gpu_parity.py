@@ -316,3 +316,28 @@ def test_raw_upload_equals_rectified_upload(plf, product, oracle):
             assert np.array_equal(r.kp_left[b, :n], ref.kp_left[b, :n]) and np.array_equal(r.desc_left[b, :n], ref.desc_left[b, :n])
             assert np.array_equal(r.kl_left[b, :nl], ref.kl_left[b, :nl]) and np.array_equal(r.ldesc_left[b, :nl], ref.ldesc_left[b, :nl])
             assert np.array_equal(r.u_right[b, :n], ref.u_right[b, :n]) and np.array_equal(r.line_match12[b, :nl], ref.line_match12[b, :nl])
+
+
+def test_feature_grid_matches_oracle(plf, product, oracle):
+    """plf_feature_grid (Frame::AssignFeaturesToGrid as CSR) for a batch: identical to the oracle, every keypoint listed
+    once in ascending order per cell, and the area lookup returns the same indices on both libraries."""
+    W, H = 752, 480
+    L, R = plf.synth_batch(W, H, [51, 52, 53, 54])
+    f, o = plf.Frontend(product, max_batch=4), plf.Frontend(oracle, max_batch=4)
+    rg, ro = f.frontend_batch(L, R), o.frontend_batch(L, R)
+    sg, ig = f.feature_grid(0, 4)
+    so, io = o.feature_grid(0, 4)
+    assert np.array_equal(sg, so)
+    for b in range(4):
+        n = int(ro.n_kp_left[b])
+        tot = int(so[b, -1])
+        assert n - 5 <= tot <= n
+        assert np.array_equal(ig[b, :tot], io[b, :tot])
+        assert len(np.unique(ig[b, :tot])) == tot
+        for c in np.nonzero(np.diff(so[b]) > 1)[0][:50]:
+            assert np.all(np.diff(ig[b, so[b, c]:so[b, c + 1]]) > 0)
+        got = f.features_in_area(rg.kp_left[b, :n], sg[b], ig[b], 300.5, 200.25, 25.0, 0, 3)
+        want = o.features_in_area(ro.kp_left[b, :n], so[b], io[b], 300.5, 200.25, 25.0, 0, 3)
+        assert np.array_equal(got, want) and len(want) > 0
+    s1, i1 = f.feature_grid(2, 2)           # a sub-range of slots
+    assert np.array_equal(s1, so[2:]) and np.array_equal(i1[0, :so[2, -1]], io[2, :so[2, -1]])

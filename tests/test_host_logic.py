@@ -127,3 +127,48 @@ def test_two_rank_gloo_sharding(tmp_path):
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     res = json.loads(line)
     assert res["pairs"] == 4 and res["tmax"] == 2.0 and res["streams"] == [0, 2] and res["kps"] > 4 * 250
+
+
+def test_feature_grid_and_area_lookup_oracle(plf, oracle):
+    """Frame::AssignFeaturesToGrid / GetFeaturesInArea (src/Frame.cc:451-482, 774-855): the oracle's CSR grid and the
+    header's lookup against a direct Python restatement of the reference loops."""
+    import math
+    W, H = 752, 480
+    L, R = plf.synth_pair(W, H, 3)
+    o = plf.Frontend(oracle, max_batch=1)
+    res = o.frontend_batch(L[None], R[None])
+    n = int(res.n_kp_left[0])
+    kps = res.kp_left[0, :n]
+    st, ix = o.feature_grid(0, 1)
+    st, ix = st[0], ix[0]
+    invw, invh = np.float32(64) / np.float32(W), np.float32(48) / np.float32(H)
+
+    def rnd(v):      # C round(): half away from zero
+        return int(math.floor(abs(v) + 0.5)) * (1 if v >= 0 else -1)
+    grid = {}
+    for i in range(n):
+        px, py = rnd(float(np.float32(kps["x"][i]) * invw)), rnd(float(np.float32(kps["y"][i]) * invh))
+        if 0 <= px < 64 and 0 <= py < 48:
+            grid.setdefault(px * 48 + py, []).append(i)
+    assert st[-1] == sum(len(v) for v in grid.values()) and st[-1] >= n - 5
+    for c in range(64 * 48):
+        assert list(ix[st[c]:st[c + 1]]) == grid.get(c, []), c
+    rng = np.random.default_rng(1)
+    for _ in range(60):
+        x, y = np.float32(rng.uniform(-30, W + 30)), np.float32(rng.uniform(-30, H + 30))
+        r = np.float32(rng.choice([3.0, 10.0, 17.5, 40.0]))
+        lo, hi = [(-1, -1), (0, 2), (1, -1), (3, 7)][int(rng.integers(0, 4))]
+        want = []
+        x0 = max(0, math.floor(float((x - r) * invw))); x1 = min(63, math.ceil(float((x + r) * invw)))
+        y0 = max(0, math.floor(float((y - r) * invh))); y1 = min(47, math.ceil(float((y + r) * invh)))
+        if x0 < 64 and x1 >= 0 and y0 < 48 and y1 >= 0:
+            for cx in range(x0, x1 + 1):
+                for cy in range(y0, y1 + 1):
+                    for i in grid.get(cx * 48 + cy, []):
+                        if lo > 0 or hi >= 0:
+                            if kps["octave"][i] < lo or (hi >= 0 and kps["octave"][i] > hi):
+                                continue
+                        if abs(np.float32(kps["x"][i]) - x) < r and abs(np.float32(kps["y"][i]) - y) < r:
+                            want.append(i)
+        got = o.features_in_area(kps, st, ix, x, y, r, lo, hi)
+        assert list(got) == want

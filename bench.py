@@ -354,7 +354,7 @@ def main():
                          "whole_path_frac": BYTES_PER_PAIR * value / world / (peak * 1e9)},
             "clocks": sampler.summary(),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
             cores = os.cpu_count() or 1
             sample = max(2 * cores, 8)
             v, dt = cpu_baseline(sample, cores, [1000 + i for i in range(sample)])

@@ -88,6 +88,14 @@ def test_state_errors(plf, product):
         f.stereo_match_points(10)          # before both extractions: PLF_ERR_STATE
     with pytest.raises(plf.PlfError):
         plf.Frontend(product, lsd_refine=2)
+    for bad in (dict(scale_factor=2.5), dict(scale_factor=1.0), dict(lsd_scale=0.4), dict(min_th_fast=0),
+                dict(ini_th_fast=5, min_th_fast=7), dict(width=32)):
+        with pytest.raises(plf.PlfError):                    # rejected loudly, never approximated
+            plf.Frontend(product, **bad)
+    with pytest.raises(plf.PlfError):
+        f.rectify(0, np.zeros((480, 752), np.uint8))          # before rectify_set_maps: PLF_ERR_STATE
+    with pytest.raises(plf.PlfError):
+        f.feature_grid(0, 1)                                  # before any extraction: PLF_ERR_STATE
 
 
 GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))

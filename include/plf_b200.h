@@ -241,6 +241,24 @@ PLF_API int PLF_FN(feature_grid)(plf_ctx* ctx, int first_slot, int n_slots, int3
                                  int idx_stride);
 
 /* ------------------------------------------------------------------------------------------------------ */
+/* Landmark back-projection: the epilogue that turns stereo matches into 3-D landmarks.   */
+
+/* Replaces: cv::Mat Frame::UnprojectStereo(const int& i) (src/Frame.cc:1332-1347; callers src/Tracking.cc:1977, 2866,
+ * 3651) for every left keypoint, and Eigen::Vector3d Frame::backProjection(u, v, disp) (src/Frame.cc:1349-1358;
+ * callers src/Tracking.cc:1992-1999, 2238-2247, 2904-2911, 3727-3734) for both end points of every left line, of the
+ * slots [first_slot, first_slot + n_slots) after batch_run / the stereo matchers.
+ *   Rwc: n_slots x 9 floats (row-major mRwc), Ow: n_slots x 3 floats (mOw); fx, bf from plf_params (mb = bf / fx),
+ *   fy / cx / cy as given (invfx = 1.0f / fx as in src/Frame.cc:190-191).
+ *   x3d: n_slots x x3d_rows x 3 floats; a row is (0,0,0) where mvDepth <= 0 (the reference returns an empty Mat).
+ *        Arithmetic of cv::Mat: x = (u-cx)*z*invfx in float; mRwc*x3Dc+mOw = cv::gemm's 3x3 path (float products summed
+ *        left to right, then (float)((double)t + (double)mOw)).
+ *   l3d: n_slots x l3d_rows x 6 doubles (start xyz, end xyz); zeros unless both disparities are > 0.  Arithmetic of
+ *        the Eigen expression in double: bd = mb/disp, P = (bd*(u-cx), bd*(v-cy), bd*fx), R*P+Ow summed left to right.
+ * Either output may be NULL. */
+PLF_API int PLF_FN(backproject)(plf_ctx* ctx, int first_slot, int n_slots, const float* Rwc, const float* Ow,
+                                float fy, float cx, float cy, float* x3d, int x3d_rows, double* l3d, int l3d_rows);
+
+/* ------------------------------------------------------------------------------------------------------ */
 /* stage taps for parity tests (slot = batch index, side 0/1).  Not part of the reference interface.       */
 
 PLF_API int PLF_FN(tap_blurred_level)(plf_ctx* ctx, int slot, int side, int level, uint8_t* out, int out_stride);

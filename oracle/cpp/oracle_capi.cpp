@@ -346,6 +346,52 @@ PLF_API int plf_cpu_get_features_in_area(const plf_keypoint* kps, const int32_t*
     return plf_features_in_area(kps, cell_start, cell_idx, width, height, x, y, r, min_level, max_level, out, cap);
 }
 
+// ---- Frame::UnprojectStereo (src/Frame.cc:1332-1347) and Frame::backProjection (:1349-1358) --------------------------
+// cv::Mat arithmetic of mRwc*x3Dc+mOw = cv::gemm's 3x3 path (pinned against cv2.gemm: float products summed left to
+// right, then (float)((double)t + (double)c)); the Eigen expression of backProjection is plain double arithmetic
+// (parity unpinned for that half: no Eigen in this container; evaluated as written, left to right, no contraction).
+PLF_API int plf_cpu_backproject(plf_ctx* c, int first_slot, int n_slots, const float* Rwc, const float* Ow, float fy, float cx,
+                                float cy, float* x3d, int x3d_rows, double* l3d, int l3d_rows) {
+    if (!c || !Rwc || !Ow || first_slot < 0 || n_slots < 1 || first_slot + n_slots > (int)c->slots.size() || (!x3d && !l3d))
+        return fail(PLF_ERR_INVALID, "bad arguments");
+    const float fx = c->p.fx, invfx = 1.0f / fx, invfy = 1.0f / fy, mb = c->p.bf / c->p.fx;
+    for (int s = 0; s < n_slots; ++s) {
+        const Slot& sl = c->slots[first_slot + s];
+        const float* R = Rwc + s * 9;
+        const float* O = Ow + s * 3;
+        if (x3d)
+            for (int i = 0; i < x3d_rows; ++i) {
+                float* d = x3d + ((size_t)s * x3d_rows + i) * 3;
+                d[0] = d[1] = d[2] = 0.f;
+                if (i >= (int)sl.orb[0].kps.size() || i >= (int)sl.depth.size()) continue;
+                const float z = sl.depth[i];
+                if (!(z > 0)) continue;
+                const float x = (sl.orb[0].kps[i].x - cx) * z * invfx, y = (sl.orb[0].kps[i].y - cy) * z * invfy;
+                for (int r = 0; r < 3; ++r) {
+                    const float t = R[3 * r] * x + R[3 * r + 1] * y + R[3 * r + 2] * z;
+                    d[r] = (float)((double)t + (double)O[r]);
+                }
+            }
+        if (l3d)
+            for (int i = 0; i < l3d_rows; ++i) {
+                double* d = l3d + ((size_t)s * l3d_rows + i) * 6;
+                for (int k = 0; k < 6; ++k) d[k] = 0;
+                if (i >= (int)sl.lsd[0].kls.size() || 2 * i + 1 >= (int)sl.disp.size()) continue;
+                const float dd[2] = {sl.disp[2 * i], sl.disp[2 * i + 1]};
+                if (!(dd[0] > 0 && dd[1] > 0)) continue;
+                const plf_keyline& k = sl.lsd[0].kls[i];
+                const float uv[4] = {k.startPointX, k.startPointY, k.endPointX, k.endPointY};
+                for (int e = 0; e < 2; ++e) {
+                    const double bd = (double)mb / (double)dd[e];
+                    const double P[3] = {bd * ((double)uv[2 * e] - (double)cx), bd * ((double)uv[2 * e + 1] - (double)cy), bd * (double)fx};
+                    for (int r = 0; r < 3; ++r)
+                        d[3 * e + r] = (((double)R[3 * r] * P[0] + (double)R[3 * r + 1] * P[1]) + (double)R[3 * r + 2] * P[2]) + (double)O[r];
+                }
+            }
+    }
+    return PLF_OK;
+}
+
 static void run_pair(plf_ctx* c, int b) {
     Slot& s = c->slots[b];
     const int w = c->p.width, h = c->p.height;

@@ -68,7 +68,7 @@ ABI_SYMBOLS = [
     "match", "frontend_batch", "batch_upload", "batch_run", "batch_download", "sync", "batch_io_bytes",
     "last_launch_count", "set_stage_timing", "get_stage_ms", "stream", "tap_blurred_level", "tap_pyramid_level",
     "tap_fast_candidates", "tap_lsd_scaled", "tap_lsd_angles", "tap_lsd_segments", "tap_lbd_float",
-    "rectify_set_maps", "rectify", "batch_upload_raw", "feature_grid", "get_features_in_area",
+    "rectify_set_maps", "rectify", "batch_upload_raw", "feature_grid", "get_features_in_area", "backproject",
 ]
 
 
@@ -348,6 +348,18 @@ class Frontend:
         ix = np.full((n_slots, self.kp_cap), -1, np.int32)
         self.lib.check(self.lib.fn("feature_grid")(self.ctx, first_slot, n_slots, _ptr(st), _ptr(ix), self.kp_cap))
         return st, ix
+
+    def backproject(self, Rwc, Ow, fy, cx, cy, first_slot=0, lines=True):
+        """Frame::UnprojectStereo for every left keypoint and Frame::backProjection for every line end point of the slots.
+        Rwc [n, 3, 3] float32, Ow [n, 3] float32 -> (x3d [n, kp_cap, 3] float32, l3d [n, kl_cap, 6] float64 or None)."""
+        Rwc = np.ascontiguousarray(Rwc, np.float32).reshape(-1, 9)
+        Ow = np.ascontiguousarray(Ow, np.float32).reshape(-1, 3)
+        n = Rwc.shape[0]
+        x3d = np.zeros((n, self.kp_cap, 3), np.float32)
+        l3d = np.zeros((n, self.kl_cap, 6), np.float64) if lines else None
+        self.lib.check(self.lib.fn("backproject")(self.ctx, first_slot, n, _ptr(Rwc), _ptr(Ow), C.c_float(fy), C.c_float(cx),
+                                                  C.c_float(cy), _ptr(x3d), self.kp_cap, _ptr(l3d), self.kl_cap if lines else 0))
+        return x3d, l3d
 
     def features_in_area(self, kps, cell_start, cell_idx, x, y, r, min_level=-1, max_level=-1):
         """Frame::GetFeaturesInArea on the CSR grid of one slot -> int32 indices."""

@@ -342,7 +342,7 @@ PLF_API int plf_destroy(plf_ctx* c) {
                     c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_rec, c->d_n2max, c->d_seeds,
                     c->d_nSeeds, c->d_n2, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
                     c->d_sobel, c->d_lbd, c->d_ldesc, c->d_rowMask, c->d_dirR, c->d_dmat, c->d_m21, c->d_m12, c->d_disp,
-                    c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage, c->d_rmap[0], c->d_rmap[1], c->d_gridStart, c->d_gridIdx};
+                    c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage, c->d_rmap[0], c->d_rmap[1], c->d_gridStart, c->d_gridIdx, c->d_bpPose, c->d_bpX, c->d_bpL};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -667,6 +667,32 @@ PLF_API int plf_feature_grid(plf_ctx* c, int first_slot, int n_slots, int32_t* c
 PLF_API int plf_get_features_in_area(const plf_keypoint* kps, const int32_t* cell_start, const int32_t* cell_idx, int width,
                                      int height, float x, float y, float r, int min_level, int max_level, int32_t* out, int cap) {
     return plf_features_in_area(kps, cell_start, cell_idx, width, height, x, y, r, min_level, max_level, out, cap);
+}
+
+// ---- landmark back-projection -------------------------------------------------------------------------
+PLF_API int plf_backproject(plf_ctx* c, int first_slot, int n_slots, const float* Rwc, const float* Ow, float fy, float cx,
+                            float cy, float* x3d, int x3d_rows, double* l3d, int l3d_rows) {
+    if (!c || !Rwc || !Ow || first_slot < 0 || n_slots < 1 || first_slot + n_slots > c->p.max_batch || (!x3d && !l3d) ||
+        (x3d && (x3d_rows < 1 || x3d_rows > c->g.kpCap)) || (l3d && (l3d_rows < 1 || l3d_rows > c->g.klCap)) || !(fy > 0))
+        return fail(PLF_ERR_INVALID, "bad slot range / rows beyond the keypoint or keyline capacity");
+    if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "backproject before the stereo matches exist");
+    if (l3d && !c->p.has_lines) return fail(PLF_ERR_STATE, "line back-projection on a context without lines");
+    PLF_CUDA_OK(cudaSetDevice(c->device));
+    if (!c->d_bpPose) {
+        PLF_CUDA_OK(dalloc(&c->d_bpPose, (size_t)c->p.max_batch * 12));
+        PLF_CUDA_OK(dalloc(&c->d_bpX, (size_t)c->p.max_batch * c->g.kpCap * 3));
+        PLF_CUDA_OK(dalloc(&c->d_bpL, (size_t)c->p.max_batch * c->g.klCap * 6));
+    }
+    cudaStream_t s = c->stream;
+    PLF_CUDA_OK(cudaMemcpyAsync(c->d_bpPose, Rwc, (size_t)n_slots * 36, cudaMemcpyHostToDevice, s));
+    PLF_CUDA_OK(cudaMemcpyAsync(c->d_bpPose + (size_t)c->p.max_batch * 9, Ow, (size_t)n_slots * 12, cudaMemcpyHostToDevice, s));
+    plf_launch_backproject(c, first_slot, n_slots, c->d_bpPose, c->d_bpPose + (size_t)c->p.max_batch * 9, fy, cx, cy,
+                           x3d ? c->d_bpX : nullptr, x3d_rows, l3d ? c->d_bpL : nullptr, l3d_rows);
+    if (x3d) PLF_CUDA_OK(cudaMemcpyAsync(x3d, c->d_bpX, (size_t)n_slots * x3d_rows * 12, cudaMemcpyDeviceToHost, s));
+    if (l3d) PLF_CUDA_OK(cudaMemcpyAsync(l3d, c->d_bpL, (size_t)n_slots * l3d_rows * 48, cudaMemcpyDeviceToHost, s));
+    PLF_CUDA_OK(cudaStreamSynchronize(s));
+    PLF_CUDA_OK(cudaGetLastError());
+    return PLF_OK;
 }
 
 // ---- rectification: cv::remap in front of the path ------------------------------------------------

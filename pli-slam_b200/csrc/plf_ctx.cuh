@@ -131,6 +131,9 @@ struct plf_ctx {
     uint2* d_rmap[2] = {nullptr, nullptr};
     int* d_gridStart = nullptr;      // [max_batch][64*48+1] CSR of Frame::mGrid (plf_feature_grid), allocated on first use
     int* d_gridIdx = nullptr;        // [max_batch][kpCap]
+    float* d_bpPose = nullptr;       // [max_batch][12] Rwc, Ow of plf_backproject
+    float* d_bpX = nullptr;          // [max_batch][kpCap][3]
+    double* d_bpL = nullptr;         // [max_batch][klCap][6]
     int srcW[2] = {0, 0}, srcH[2] = {0, 0};
     // pinned host staging for small result reads
     int* h_counts = nullptr;         // pinned
@@ -153,6 +156,8 @@ void plf_mark(plf_ctx* c, const char* name);
 // --- stage launchers (each returns the number of kernel launches it issued) ---------------------------------------
 int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1);
 int plf_launch_unpack(plf_ctx* c, const uint8_t* stage, size_t sideBytes, int stride, int batch);
+int plf_launch_backproject(plf_ctx* c, int slotFirst, int nSlots, const float* dRwc, const float* dOw, float fy, float cx,
+                           float cy, float* dX3d, int x3dRows, double* dL3d, int l3dRows);
 int plf_launch_feature_grid(plf_ctx* c, int slotFirst, int nSlots, int* cellStart, int* cellIdx);
 int plf_launch_rectify(plf_ctx* c, const uint8_t* raw0, const uint8_t* raw1, int rawStride, int imgFirst, int nImg);
 int plf_launch_stereo_points(plf_ctx* c, int slotFirst, int nSlots);

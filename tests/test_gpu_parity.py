@@ -349,3 +349,26 @@ def test_feature_grid_matches_oracle(plf, product, oracle):
         assert np.array_equal(got, want) and len(want) > 0
     s1, i1 = f.feature_grid(2, 2)           # a sub-range of slots
     assert np.array_equal(s1, so[2:]) and np.array_equal(i1[0, :so[2, -1]], io[2, :so[2, -1]])
+
+
+def test_backproject_matches_oracle(plf, product, oracle):
+    """plf_backproject (Frame::UnprojectStereo per keypoint, Frame::backProjection per line end point) for a batch with a
+    different pose per slot: bit-identical to the oracle, zeros exactly where the reference has no landmark."""
+    W, H = 752, 480
+    L, R = plf.synth_batch(W, H, [61, 62, 63])
+    f, o = plf.Frontend(product, max_batch=3), plf.Frontend(oracle, max_batch=3)
+    rg, ro = f.frontend_batch(L, R), o.frontend_batch(L, R)
+    rng = np.random.default_rng(4)
+    Rwc = np.stack([np.linalg.qr(rng.normal(size=(3, 3)))[0] for _ in range(3)]).astype(np.float32)
+    Ow = (rng.normal(size=(3, 3)) * 3).astype(np.float32)
+    xg, lg = f.backproject(Rwc, Ow, 435.2047, 367.4517, 252.2009)
+    xo, lo = o.backproject(Rwc, Ow, 435.2047, 367.4517, 252.2009)
+    assert np.array_equal(xg, xo) and np.array_equal(lg, lo)
+    for b in range(3):
+        n, nl = int(ro.n_kp_left[b]), int(ro.n_kl_left[b])
+        has = ro.depth[b, :n] > 0
+        assert has.sum() > 100 and np.all(np.any(xg[b, :n][has] != 0, axis=1)) and not xg[b, :n][~has].any() and not xg[b, n:].any()
+        st = (ro.disp_se[b, :nl] > 0).all(axis=1)
+        assert st.sum() > 20 and not lg[b, :nl][~st].any()
+    x1, _ = f.backproject(Rwc[1:2], Ow[1:2], 435.2047, 367.4517, 252.2009, first_slot=1, lines=False)
+    assert np.array_equal(x1[0], xo[1])

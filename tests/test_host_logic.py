@@ -172,3 +172,49 @@ def test_feature_grid_and_area_lookup_oracle(plf, oracle):
                             want.append(i)
         got = o.features_in_area(kps, st, ix, x, y, r, lo, hi)
         assert list(got) == want
+
+
+def test_backproject_oracle_against_cv2_gemm_and_numpy(plf, oracle):
+    """Frame::UnprojectStereo / Frame::backProjection (src/Frame.cc:1332-1358): the oracle against cv2.gemm (the cv::Mat
+    expression mRwc*x3Dc+mOw) for the points and against the double expression written out in numpy for the lines."""
+    cv2 = pytest.importorskip("cv2")
+    W, H = 752, 480
+    L, R = plf.synth_pair(W, H, 3)
+    o = plf.Frontend(oracle, max_batch=1)
+    res = o.frontend_batch(L[None], R[None])
+    n, nl = int(res.n_kp_left[0]), int(res.n_kl_left[0])
+    rng = np.random.default_rng(2)
+    A = rng.normal(size=(3, 3)); Q, _ = np.linalg.qr(A)
+    Rwc = Q.astype(np.float32); Ow = rng.normal(size=3).astype(np.float32) * 2
+    fx, fy, cx, cy = np.float32(o.params.fx), np.float32(435.2047), np.float32(367.4517), np.float32(252.2009)
+    x3d, l3d = o.backproject(Rwc[None], Ow[None], fy, cx, cy)
+    invfx, invfy = np.float32(1) / fx, np.float32(1) / fy
+    kps, depth = res.kp_left[0], res.depth[0]
+    hits = 0
+    for i in range(n):
+        z = np.float32(depth[i])
+        if not z > 0:
+            assert not x3d[0, i].any()
+            continue
+        x = np.float32(np.float32(np.float32(kps["x"][i]) - cx) * z) * invfx
+        y = np.float32(np.float32(np.float32(kps["y"][i]) - cy) * z) * invfy
+        want = cv2.gemm(Rwc, np.array([[x], [y], [z]], np.float32), 1.0, Ow.reshape(3, 1), 1.0).ravel()
+        assert np.array_equal(x3d[0, i], want), i
+        hits += 1
+    assert hits > 100 and not x3d[0, n:].any()
+    mb = np.float32(o.params.bf) / np.float32(o.params.fx)
+    kls, disp = res.kl_left[0], res.disp_se[0]
+    Rd, Od = Rwc.astype(np.float64), Ow.astype(np.float64)
+    hits = 0
+    for i in range(nl):
+        d0, d1 = disp[i]
+        if not (d0 > 0 and d1 > 0):
+            assert not l3d[0, i].any()
+            continue
+        for e, (u, v, d) in enumerate(((kls["startPointX"][i], kls["startPointY"][i], d0), (kls["endPointX"][i], kls["endPointY"][i], d1))):
+            bd = np.float64(mb) / np.float64(d)
+            P = np.array([bd * (np.float64(u) - np.float64(cx)), bd * (np.float64(v) - np.float64(cy)), bd * np.float64(fx)])
+            want = ((Rd[:, 0] * P[0] + Rd[:, 1] * P[1]) + Rd[:, 2] * P[2]) + Od
+            assert np.array_equal(l3d[0, i, 3 * e:3 * e + 3], want), (i, e)
+        hits += 1
+    assert hits > 20

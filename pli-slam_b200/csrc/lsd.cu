@@ -1006,11 +1006,9 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     plf_mark(c, "lsd_order");
     {
         const size_t smem = (size_t)ORD_WARPS * g.nBins * sizeof(int);
-        static size_t s_attr = 0;
-        if (smem > 48 * 1024 && smem > s_attr) {
+        static size_t s_granted[64] = {};
+        if (plf_raise_smem_optin(s_granted, c->device, smem))
             cudaFuncSetAttribute(lsd_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            s_attr = smem;
-        }
         lsd_order_kernel<<<nImg, 32 * ORD_WARPS, smem, s>>>(g, c->d_n2, c->d_n2max, c->d_seeds, c->d_nSeeds, imgFirst);
     }
     plf_mark(c, "lsd_grow");

@@ -843,11 +843,9 @@ int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1) {
     for (int l = 0; l < g.nLevels; ++l) maxQ = max(maxQ, max(g.lv[l].quota, 4 * g.lv[l].nIni));
     const int pool = maxQ + 16;
     const size_t smem = (size_t)pool * (sizeof(QNode) + 2 * sizeof(int));
-    static size_t s_attr = 0;
-    if (smem > 48 * 1024 && smem > s_attr) {
+    static size_t s_granted[64] = {};
+    if (plf_raise_smem_optin(s_granted, c->device, smem))
         cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        s_attr = smem;
-    }
     plf_mark(c, "orb_octree");
     octree_kernel<<<dim3(g.nLevels, nImg), 32, smem, s>>>(g, c->d_cells, c->d_cellCount, c->d_cand, c->d_scratch,
                                                          c->d_lvlKp, c->d_lvlN, c->d_err, imgFirst, pool);

@@ -155,6 +155,17 @@ void plf_mark(plf_ctx* c, const char* name);
 
 // --- stage launchers (each returns the number of kernel launches it issued) ---------------------------------------
 int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1);
+// Opt-in dynamic shared memory (> 48 KB) is an attribute of (function, device) and the last value set wins, so the
+// largest request per device is remembered process-wide and only ever raised.  Returns true if `smem` exceeds it.
+#include <mutex>
+inline bool plf_raise_smem_optin(size_t (&granted)[64], int device, size_t smem) {
+    static std::mutex m;
+    std::lock_guard<std::mutex> lock(m);
+    if (smem <= 48 * 1024 || device < 0 || device >= 64 || smem <= granted[device]) return device < 0 || device >= 64;
+    granted[device] = smem;
+    return true;
+}
+
 int plf_launch_unpack(plf_ctx* c, const uint8_t* stage, size_t sideBytes, int stride, int batch);
 int plf_launch_backproject(plf_ctx* c, int slotFirst, int nSlots, const float* dRwc, const float* dOw, float fy, float cx,
                            float cy, float* dX3d, int x3dRows, double* dL3d, int l3dRows);

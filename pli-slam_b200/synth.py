@@ -131,3 +131,47 @@ def rectify_maps(W=752, H=480, side=0):
     xd = x * kr + p1 * 2 * x * y + p2 * (r2 + 2 * x * x)
     yd = y * kr + p1 * (r2 + 2 * y * y) + p2 * 2 * x * y
     return (K[0, 0] * xd + K[0, 2]).astype(np.float32), (K[1, 1] * yd + K[1, 2]).astype(np.float32)
+
+
+def synth_curvy(W=752, H=480, seed=1):
+    """A second kind of test content (parity coverage beyond axis-aligned rectangles): smooth shading from a few random
+    sinusoids, 60 discs / rings / ellipses with soft and hard edges, 25 thick polylines, a mild vignette and noise in
+    [-3, 3].  Curved and slanted edges give region growing long chains of slowly turning angles, T-junctions and many
+    small rejected regions.  Pure numpy, deterministic in (W, H, seed); returns one uint8 image."""
+    rng = np.random.default_rng(seed)
+    ys, xs = np.mgrid[0:H, 0:W].astype(np.float64)
+    img = np.full((H, W), 110.0)
+    for _ in range(6):
+        fx, fy, ph, am = rng.uniform(0.002, 0.02), rng.uniform(0.002, 0.02), rng.uniform(0, 6.28), rng.uniform(5, 25)
+        img += am * np.sin(xs * fx * 6.28 + ys * fy * 6.28 + ph)
+    for i in range(60):
+        cx, cy = rng.uniform(0, W), rng.uniform(0, H)
+        a, b = rng.uniform(8, 90), rng.uniform(8, 90)
+        th = rng.uniform(0, 3.14159)
+        g = rng.uniform(20, 240)
+        u = (xs - cx) * np.cos(th) + (ys - cy) * np.sin(th)
+        v = -(xs - cx) * np.sin(th) + (ys - cy) * np.cos(th)
+        d = np.sqrt((u / a) ** 2 + (v / b) ** 2)
+        if i % 3 == 0:        # ring
+            m = np.clip(1.5 - np.abs(d - 1.0) * min(a, b) / 2.0, 0, 1)
+        elif i % 3 == 1:      # hard disc
+            m = (d <= 1.0).astype(np.float64)
+        else:                 # soft disc
+            m = np.clip((1.0 - d) * min(a, b) / 6.0, 0, 1)
+        img = img * (1 - m) + g * m
+    for _ in range(25):
+        n = int(rng.integers(2, 6))
+        pts = np.stack([rng.uniform(0, W, n), rng.uniform(0, H, n)], 1)
+        g, r = rng.uniform(10, 250), rng.uniform(0.8, 3.0)
+        for (x0, y0), (x1, y1) in zip(pts[:-1], pts[1:]):
+            dx, dy = x1 - x0, y1 - y0
+            L2 = dx * dx + dy * dy
+            if L2 < 1:
+                continue
+            t = np.clip(((xs - x0) * dx + (ys - y0) * dy) / L2, 0, 1)
+            dist = np.sqrt((xs - (x0 + t * dx)) ** 2 + (ys - (y0 + t * dy)) ** 2)
+            m = np.clip(r + 0.5 - dist, 0, 1)
+            img = img * (1 - m) + g * m
+    img *= 1.0 - 0.25 * (((xs - W / 2) / W) ** 2 + ((ys - H / 2) / H) ** 2)
+    img += rng.integers(-3, 4, (H, W))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)

@@ -372,3 +372,29 @@ def test_backproject_matches_oracle(plf, product, oracle):
         assert st.sum() > 20 and not lg[b, :nl][~st].any()
     x1, _ = f.backproject(Rwc[1:2], Ow[1:2], 435.2047, 367.4517, 252.2009, first_slot=1, lines=False)
     assert np.array_equal(x1[0], xo[1])
+
+
+@pytest.mark.parametrize("refine", [0, 1])
+def test_curved_content_matches_oracle(plf, product, oracle, refine):
+    """The whole path on the second content type (curved and slanted edges, smooth shading); right image = left shifted
+    by 14 px with its own noise.  Everything identical to the oracle."""
+    W, H = 752, 480
+    Ls = np.stack([plf.synth_curvy(W, H, s) for s in (5, 6)])
+    rng = np.random.default_rng(9)
+    Rs = np.clip(np.roll(Ls, -14, axis=2).astype(np.int16) + rng.integers(-2, 3, Ls.shape), 0, 255).astype(np.uint8)
+    kw = dict(lsd_refine=refine, lsd_nfeatures=0)
+    f, o = plf.Frontend(product, max_batch=2, **kw), plf.Frontend(oracle, max_batch=2, **kw)
+    rg, ro = f.frontend_batch(Ls, Rs), o.frontend_batch(Ls, Rs)
+    for b in range(2):
+        for side in ("left", "right"):
+            n, nl = int(getattr(ro, "n_kp_" + side)[b]), int(getattr(ro, "n_kl_" + side)[b])
+            assert n > 300 and nl > 200
+            assert int(getattr(rg, "n_kp_" + side)[b]) == n and int(getattr(rg, "n_kl_" + side)[b]) == nl
+            assert np.array_equal(getattr(rg, "kp_" + side)[b, :n], getattr(ro, "kp_" + side)[b, :n])
+            assert np.array_equal(getattr(rg, "desc_" + side)[b, :n], getattr(ro, "desc_" + side)[b, :n])
+            assert np.array_equal(getattr(rg, "kl_" + side)[b, :nl], getattr(ro, "kl_" + side)[b, :nl])
+            assert np.array_equal(getattr(rg, "ldesc_" + side)[b, :nl], getattr(ro, "ldesc_" + side)[b, :nl])
+        n, nl = int(ro.n_kp_left[b]), int(ro.n_kl_left[b])
+        assert (ro.u_right[b, :n] >= 0).sum() > 50
+        assert np.array_equal(rg.u_right[b, :n], ro.u_right[b, :n]) and np.array_equal(rg.depth[b, :n], ro.depth[b, :n])
+        assert np.array_equal(rg.line_match12[b, :nl], ro.line_match12[b, :nl]) and np.array_equal(rg.disp_se[b, :nl], ro.disp_se[b, :nl])

@@ -233,3 +233,15 @@ def test_remap_edge_cases_vs_cv2(plf, oracle):
     my = rng.uniform(-5, 305, (H, W)).astype(np.float32)
     f.rectify_set_maps(1, mx, my, 400, 300)
     assert np.array_equal(f.rectify(1, small), cv2.remap(small, mx, my, cv2.INTER_LINEAR))
+
+
+@pytest.mark.parametrize("w,h,seed,refine", [(752, 480, 1, 0), (752, 480, 2, 1), (640, 480, 3, 0)])
+def test_lsd_vs_cv2_curved_content(oracle, plf, w, h, seed, refine):
+    """Second content type (discs, rings, ellipses, polylines, smooth shading): long chains of slowly turning level-line
+    angles and many rejected regions.  The restatement still equals cv2's LSD bit for bit, order included."""
+    img = plf.synth_curvy(w, h, seed)
+    ref = cv2.createLineSegmentDetector(refine, 1.2, 0.6, 2.0, 22.5, 1.0, 0.6, 1024).detect(img)[0].reshape(-1, 4)
+    out = np.zeros((20000, 4), np.float32)
+    n = C.c_int(0)
+    assert oracle.dll.plf_cpu_prim_lsd(_p(img), w, h, C.c_double(1.2), 1 | (refine << 4), _p(out), 20000, C.byref(n)) == 0
+    assert len(ref) > 500 and n.value == len(ref) and np.array_equal(out[:n.value], ref)

@@ -1,0 +1,20 @@
+"""One small pass through every entry point of the C ABI (developer tool: run under compute-sanitizer on the GPU box)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, plf
+W, H, B = 752, 480, 2
+L, R = plf.synth_batch(W, H, [1, 2])
+f = plf.Frontend(plf.load_product(), max_batch=B, lsd_refine=int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+for side in (0, 1):
+    f.rectify_set_maps(side, *plf.rectify_maps(W, H, side))
+img = f.rectify(0, L[0])
+out = f.new_result(B)
+f.batch_upload_raw(L, R); f.batch_run(B); f.batch_download(B, out)
+res = f.frontend_batch(L, R)
+st, ix = f.feature_grid(0, B)
+x3d, l3d = f.backproject(np.tile(np.eye(3, dtype=np.float32), (B, 1, 1)), np.zeros((B, 3), np.float32), 435.2, 367.4, 252.2)
+m, k, d = f.orb_extract(0, L[0]); m2, k2, d2 = f.orb_extract(1, R[0])
+kl, ld = f.line_extract(0, L[0]); klr, ldr = f.line_extract(1, R[0])
+u, dep = f.stereo_match_points(len(k)); disp, le, m12 = f.stereo_match_lines(len(kl))
+n1, _ = f.match_nnr(ld, ldr, 0.9); n2, _ = f.match(ld, ldr, 0.9, 1)
+print("ok", int(res.n_kp_left[0]), int(res.n_kl_left[0]), int(st[0, -1]), int((x3d[0] != 0).any(axis=1).sum()), n1, n2, img.mean().round(1))

@@ -259,6 +259,23 @@ PLF_API int PLF_FN(backproject)(plf_ctx* ctx, int first_slot, int n_slots, const
                                 float fy, float cx, float cy, float* x3d, int x3d_rows, double* l3d, int l3d_rows);
 
 /* ------------------------------------------------------------------------------------------------------ */
+/* Bag-of-words transform: Frame::ComputeBoW (src/Frame.cc:858-870).                      */
+
+/* The DBoW2 vocabulary tree (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h, m_nodes; ORBvoc / the line vocabulary:
+ * k = 10, L = 6, TF_IDF weighting, L1_NORM scoring) as flat arrays.  Node 0 is the root; the children of node i are
+ * child[child_first[i] .. child_first[i] + child_count[i]) in the order of m_nodes[i].children; leaves have
+ * child_count 0 and carry word_id / weight.  `which`: 0 = ORB vocabulary, 1 = line (LBD) vocabulary. */
+PLF_API int PLF_FN(bow_set_vocabulary)(plf_ctx* ctx, int which, int n_nodes, int levels, const int32_t* child_first,
+                                       const int32_t* child_count, const int32_t* child, const uint8_t* desc,
+                                       const int32_t* word_id, const double* weight);
+/* Replaces the per-feature half of TemplatedVocabulary::transform(features, BowVector&, FeatureVector&, levelsup)
+ * (TemplatedVocabulary.h:1139-1205 -> :1230-1270): every left descriptor of the slots (which = 0: ORB rows, 1: LBD
+ * rows) is propagated down the tree by smallest Hamming distance (first child wins ties); outputs per feature the
+ * word id, the word weight and the node id at level L - levelsup (0 if that level is <= 0).  stride = rows per slot. */
+PLF_API int PLF_FN(bow_transform)(plf_ctx* ctx, int which, int first_slot, int n_slots, int levelsup,
+                                  int32_t* word_id, double* weight, int32_t* node_id, int stride);
+
+/* ------------------------------------------------------------------------------------------------------ */
 /* stage taps for parity tests (slot = batch index, side 0/1).  Not part of the reference interface.       */
 
 PLF_API int PLF_FN(tap_blurred_level)(plf_ctx* ctx, int slot, int side, int level, uint8_t* out, int out_stride);
@@ -317,6 +334,57 @@ static inline int plf_features_in_area(const plf_keypoint* kps, const int32_t* c
 PLF_API int PLF_FN(get_features_in_area)(const plf_keypoint* kps, const int32_t* cell_start, const int32_t* cell_idx,
                                          int width, int height, float x, float y, float r, int min_level,
                                          int max_level, int32_t* out, int cap);
+
+/* The other half of transform(): BowVector (TF_IDF: addWeight in feature order, then L1 normalisation in word order,
+ * BowVector.cpp:34-84) and FeatureVector (features grouped by node id, ascending feature index) from the per-feature
+ * outputs of plf_bow_transform.  Features with weight <= 0 are skipped ("stopped" words).  Pure host inline.
+ * bow_word / bow_value: >= n entries; fv_node / fv_start (>= n + 1) / fv_feat: >= n entries.  Returns the number of
+ * words; *n_nodes_out = number of FeatureVector nodes. */
+static inline int plf_bow_build(const int32_t* word_id, const double* weight, const int32_t* node_id, int n,
+                                int32_t* bow_word, double* bow_value, int32_t* fv_node, int32_t* fv_start,
+                                int32_t* fv_feat, int* n_nodes_out) {
+    int nw = 0, nn = 0, i, j;
+    /* insertion into sorted arrays keeps std::map order; n is ~1000 */
+    for (i = 0; i < n; ++i) {
+        if (!(weight[i] > 0)) continue;
+        for (j = 0; j < nw && bow_word[j] < word_id[i]; ++j) {}
+        if (j < nw && bow_word[j] == word_id[i]) bow_value[j] += weight[i];
+        else {
+            int m;
+            for (m = nw; m > j; --m) { bow_word[m] = bow_word[m - 1]; bow_value[m] = bow_value[m - 1]; }
+            bow_word[j] = word_id[i]; bow_value[j] = weight[i]; ++nw;
+        }
+    }
+    {
+        double norm = 0.0;
+        for (j = 0; j < nw; ++j) norm += fabs(bow_value[j]);
+        if (norm > 0.0) for (j = 0; j < nw; ++j) bow_value[j] /= norm;
+    }
+    /* FeatureVector: distinct node ids ascending, then the features of each node in ascending index */
+    for (i = 0; i < n; ++i) {
+        if (!(weight[i] > 0)) continue;
+        for (j = 0; j < nn && fv_node[j] < node_id[i]; ++j) {}
+        if (!(j < nn && fv_node[j] == node_id[i])) {
+            int m;
+            for (m = nn; m > j; --m) fv_node[m] = fv_node[m - 1];
+            fv_node[j] = node_id[i]; ++nn;
+        }
+    }
+    {
+        int pos = 0;
+        for (j = 0; j < nn; ++j) {
+            fv_start[j] = pos;
+            for (i = 0; i < n; ++i) if (weight[i] > 0 && node_id[i] == fv_node[j]) fv_feat[pos++] = i;
+        }
+        fv_start[nn] = pos;
+    }
+    if (n_nodes_out) *n_nodes_out = nn;
+    return nw;
+}
+/* The same as an exported symbol (for bindings that cannot use a C inline). */
+PLF_API int PLF_FN(bow_build_vectors)(const int32_t* word_id, const double* weight, const int32_t* node_id, int n,
+                              int32_t* bow_word, double* bow_value, int32_t* fv_node, int32_t* fv_start,
+                              int32_t* fv_feat, int* n_nodes_out);
 
 /* Replaces: static int ORBmatcher::DescriptorDistance(const Mat&, const Mat&) (include/ORBmatcher.h:42,
  * src/ORBmatcher.cc:2495-2511) and int distance(const Mat&, const Mat&) (src/LineMatcher.cpp:231-247):

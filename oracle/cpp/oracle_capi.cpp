@@ -34,6 +34,7 @@ struct plf_ctx {
     int kp_cap = 0, kl_cap = 0;
     int threads = 0;         // worker threads for batch calls (0 = hardware concurrency)
     int batch_resident = 0;
+    struct Vocab { int levels = 0; std::vector<int> first, count, child, word; std::vector<uint8_t> desc; std::vector<double> weight; } voc[2];
     std::vector<float> mapx[2], mapy[2];   // rectification maps per camera (plf_cpu_rectify_set_maps)
     int srcW[2] = {0, 0}, srcH[2] = {0, 0};
 };
@@ -390,6 +391,63 @@ PLF_API int plf_cpu_backproject(plf_ctx* c, int first_slot, int n_slots, const f
             }
     }
     return PLF_OK;
+}
+
+// ---- DBoW2 transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1139-1270), restated on flat node arrays ----------
+// parity unpinned: DBoW2 itself cannot be built here (needs OpenCV C++ headers) and the vocabulary files are not in the
+// reference tree; the descent and the vector construction follow the published algorithm and are cross-checked against
+// a direct Python restatement in tests/.
+PLF_API int plf_cpu_bow_set_vocabulary(plf_ctx* c, int which, int n_nodes, int levels, const int32_t* child_first,
+                                       const int32_t* child_count, const int32_t* child, const uint8_t* desc,
+                                       const int32_t* word_id, const double* weight) {
+    if (!c || which < 0 || which > 1 || n_nodes < 2 || levels < 1 || !child_first || !child_count || !child || !desc || !word_id || !weight)
+        return fail(PLF_ERR_INVALID, "bad vocabulary");
+    auto& v = c->voc[which];
+    v.levels = levels;
+    v.first.assign(child_first, child_first + n_nodes);
+    v.count.assign(child_count, child_count + n_nodes);
+    v.child.assign(child, child + (n_nodes - 1));
+    v.word.assign(word_id, word_id + n_nodes);
+    v.desc.assign(desc, desc + (size_t)n_nodes * 32);
+    v.weight.assign(weight, weight + n_nodes);
+    return PLF_OK;
+}
+PLF_API int plf_cpu_bow_transform(plf_ctx* c, int which, int first_slot, int n_slots, int levelsup, int32_t* word_id, double* weight,
+                                  int32_t* node_id, int stride) {
+    if (!c || which < 0 || which > 1 || !word_id || !weight || !node_id || first_slot < 0 || n_slots < 1 ||
+        first_slot + n_slots > (int)c->slots.size() || stride < 1)
+        return fail(PLF_ERR_INVALID, "bad arguments");
+    const auto& v = c->voc[which];
+    if (v.first.empty()) return fail(PLF_ERR_STATE, "bow_transform before bow_set_vocabulary");
+    for (int s = 0; s < n_slots; ++s) {
+        const Slot& sl = c->slots[first_slot + s];
+        const uint8_t* D = which ? sl.lsd[0].desc.data() : sl.orb[0].desc.data();
+        const int n = which ? (int)sl.lsd[0].kls.size() : (int)sl.orb[0].kps.size();
+        for (int i = 0; i < stride; ++i) {
+            const size_t o = (size_t)s * stride + i;
+            if (i >= n) { word_id[o] = -1; weight[o] = 0.0; node_id[o] = 0; continue; }
+            const uint8_t* f = D + (size_t)i * 32;
+            const int nidLevel = v.levels - levelsup;
+            int node = 0, level = 0, nid = 0;
+            do {
+                ++level;
+                int best = 0x7fffffff, bestId = node;
+                for (int k = 0; k < v.count[node]; ++k) {
+                    const int id = v.child[v.first[node] + k];
+                    const int d = plf_hamming256(f, v.desc.data() + (size_t)id * 32);
+                    if (d < best) { best = d; bestId = id; }
+                }
+                node = bestId;
+                if (level == nidLevel) nid = node;
+            } while (v.count[node] > 0);
+            word_id[o] = v.word[node]; weight[o] = v.weight[node]; node_id[o] = nid;
+        }
+    }
+    return PLF_OK;
+}
+PLF_API int plf_cpu_bow_build_vectors(const int32_t* word_id, const double* weight, const int32_t* node_id, int n, int32_t* bow_word,
+                                      double* bow_value, int32_t* fv_node, int32_t* fv_start, int32_t* fv_feat, int* n_nodes_out) {
+    return plf_bow_build(word_id, weight, node_id, n, bow_word, bow_value, fv_node, fv_start, fv_feat, n_nodes_out);
 }
 
 static void run_pair(plf_ctx* c, int b) {

@@ -68,7 +68,7 @@ ABI_SYMBOLS = [
     "match", "frontend_batch", "batch_upload", "batch_run", "batch_download", "sync", "batch_io_bytes",
     "last_launch_count", "set_stage_timing", "get_stage_ms", "stream", "tap_blurred_level", "tap_pyramid_level",
     "tap_fast_candidates", "tap_lsd_scaled", "tap_lsd_angles", "tap_lsd_segments", "tap_lbd_float",
-    "rectify_set_maps", "rectify", "batch_upload_raw", "feature_grid", "get_features_in_area", "backproject",
+    "rectify_set_maps", "rectify", "batch_upload_raw", "feature_grid", "get_features_in_area", "backproject", "bow_set_vocabulary", "bow_transform", "bow_build_vectors",
 ]
 
 
@@ -348,6 +348,35 @@ class Frontend:
         ix = np.full((n_slots, self.kp_cap), -1, np.int32)
         self.lib.check(self.lib.fn("feature_grid")(self.ctx, first_slot, n_slots, _ptr(st), _ptr(ix), self.kp_cap))
         return st, ix
+
+    # ---- bag of words ------------------------------------------------------------------------------
+    def bow_set_vocabulary(self, which, voc):
+        """voc: dict(levels, child_first, child_count, child, desc [n, 32] uint8, word_id, weight) — the DBoW2 tree, flat."""
+        cf = np.ascontiguousarray(voc["child_first"], np.int32); cc = np.ascontiguousarray(voc["child_count"], np.int32)
+        ch = np.ascontiguousarray(voc["child"], np.int32); de = np.ascontiguousarray(voc["desc"], np.uint8)
+        wi = np.ascontiguousarray(voc["word_id"], np.int32); we = np.ascontiguousarray(voc["weight"], np.float64)
+        self.lib.check(self.lib.fn("bow_set_vocabulary")(self.ctx, which, len(cf), int(voc["levels"]), _ptr(cf), _ptr(cc), _ptr(ch),
+                                                         _ptr(de), _ptr(wi), _ptr(we)))
+
+    def bow_transform(self, which, n_slots=1, first_slot=0, levelsup=4):
+        """Per-feature word id, weight and node id (level L - levelsup) for the left ORB (0) / LBD (1) descriptors."""
+        cap = self.kl_cap if which else self.kp_cap
+        w = np.zeros((n_slots, cap), np.int32); v = np.zeros((n_slots, cap), np.float64); nd = np.zeros((n_slots, cap), np.int32)
+        self.lib.check(self.lib.fn("bow_transform")(self.ctx, which, first_slot, n_slots, levelsup, _ptr(w), _ptr(v), _ptr(nd), cap))
+        return w, v, nd
+
+    def bow_build(self, word_id, weight, node_id):
+        """BowVector (sorted words, L1-normalised TF-IDF values) and FeatureVector (node -> feature indices)."""
+        n = len(word_id)
+        word_id = np.ascontiguousarray(word_id, np.int32); weight = np.ascontiguousarray(weight, np.float64)
+        node_id = np.ascontiguousarray(node_id, np.int32)
+        bw = np.zeros(n + 1, np.int32); bv = np.zeros(n + 1, np.float64)
+        fn_ = np.zeros(n + 1, np.int32); fs = np.zeros(n + 2, np.int32); ff = np.zeros(n + 1, np.int32)
+        nn = C.c_int(0)
+        nw = self.lib.fn("bow_build_vectors")(_ptr(word_id), _ptr(weight), _ptr(node_id), n, _ptr(bw), _ptr(bv), _ptr(fn_), _ptr(fs),
+                                              _ptr(ff), C.byref(nn))
+        fv = {int(fn_[j]): ff[fs[j]:fs[j + 1]].tolist() for j in range(nn.value)}
+        return bw[:nw].copy(), bv[:nw].copy(), fv
 
     def backproject(self, Rwc, Ow, fy, cx, cy, first_slot=0, lines=True):
         """Frame::UnprojectStereo for every left keypoint and Frame::backProjection for every line end point of the slots.

@@ -342,7 +342,9 @@ PLF_API int plf_destroy(plf_ctx* c) {
                     c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_rec, c->d_n2max, c->d_seeds,
                     c->d_nSeeds, c->d_n2, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
                     c->d_sobel, c->d_lbd, c->d_ldesc, c->d_rowMask, c->d_dirR, c->d_dmat, c->d_m21, c->d_m12, c->d_disp,
-                    c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage, c->d_rmap[0], c->d_rmap[1], c->d_gridStart, c->d_gridIdx, c->d_bpPose, c->d_bpX, c->d_bpL};
+                    c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage, c->d_rmap[0], c->d_rmap[1], c->d_gridStart, c->d_gridIdx, c->d_bpPose, c->d_bpX, c->d_bpL, c->d_bowWord, c->d_bowNode, c->d_bowWeight,
+                    c->voc[0].childFirst, c->voc[0].childCount, c->voc[0].child, c->voc[0].word, c->voc[0].desc, c->voc[0].weight,
+                    c->voc[1].childFirst, c->voc[1].childCount, c->voc[1].child, c->voc[1].word, c->voc[1].desc, c->voc[1].weight};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     for (auto& e : c->ev) cudaEventDestroy(e);
@@ -667,6 +669,89 @@ PLF_API int plf_feature_grid(plf_ctx* c, int first_slot, int n_slots, int32_t* c
 PLF_API int plf_get_features_in_area(const plf_keypoint* kps, const int32_t* cell_start, const int32_t* cell_idx, int width,
                                      int height, float x, float y, float r, int min_level, int max_level, int32_t* out, int cap) {
     return plf_features_in_area(kps, cell_start, cell_idx, width, height, x, y, r, min_level, max_level, out, cap);
+}
+
+// ---- bag-of-words transform -------------------------------------------------------------------------
+PLF_API int plf_bow_set_vocabulary(plf_ctx* c, int which, int n_nodes, int levels, const int32_t* child_first,
+                                   const int32_t* child_count, const int32_t* child, const uint8_t* desc, const int32_t* word_id,
+                                   const double* weight) {
+    if (!c || which < 0 || which > 1 || n_nodes < 2 || levels < 1 || !child_first || !child_count || !child || !desc || !word_id || !weight)
+        return fail(PLF_ERR_INVALID, "bad vocabulary");
+    // structural check on the host: children in range, every node but the root referenced once, depth <= levels
+    long long total = 0;
+    for (int i = 0; i < n_nodes; ++i) {
+        if (child_count[i] < 0 || child_first[i] < 0) return fail(PLF_ERR_INVALID, "bad vocabulary (child range)");
+        total += child_count[i];
+    }
+    if (total != n_nodes - 1 || child_count[0] == 0) return fail(PLF_ERR_INVALID, "bad vocabulary (not a tree rooted at node 0)");
+    for (int i = 0; i < n_nodes; ++i)
+        for (int k = 0; k < child_count[i]; ++k) {
+            if ((long long)child_first[i] + k >= total) return fail(PLF_ERR_INVALID, "bad vocabulary (child index)");
+            const int id = child[child_first[i] + k];
+            if (id <= 0 || id >= n_nodes) return fail(PLF_ERR_INVALID, "bad vocabulary (child id)");
+        }
+    {   // depth of every root-to-leaf path (also rejects cycles: a walk longer than `levels` fails)
+        std::vector<int> depth(n_nodes, -1), stack;
+        depth[0] = 0; stack.push_back(0);
+        while (!stack.empty()) {
+            const int i = stack.back(); stack.pop_back();
+            for (int k = 0; k < child_count[i]; ++k) {
+                const int id = child[child_first[i] + k];
+                if (depth[id] >= 0 || depth[i] + 1 > levels) return fail(PLF_ERR_INVALID, "bad vocabulary (cycle or deeper than levels)");
+                depth[id] = depth[i] + 1;
+                stack.push_back(id);
+            }
+        }
+    }
+    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
+    PlfVocab& v = c->voc[which];
+    void* old[] = {v.childFirst, v.childCount, v.child, v.word, v.desc, v.weight};
+    for (void* q : old) if (q) cudaFree(q);
+    v = PlfVocab();
+    PLF_CUDA_OK(dalloc(&v.childFirst, (size_t)n_nodes));
+    PLF_CUDA_OK(dalloc(&v.childCount, (size_t)n_nodes));
+    PLF_CUDA_OK(dalloc(&v.child, (size_t)n_nodes));
+    PLF_CUDA_OK(dalloc(&v.word, (size_t)n_nodes));
+    PLF_CUDA_OK(dalloc(&v.desc, (size_t)n_nodes * 32));
+    PLF_CUDA_OK(dalloc(&v.weight, (size_t)n_nodes));
+    PLF_CUDA_OK(cudaMemcpy(v.childFirst, child_first, (size_t)n_nodes * 4, cudaMemcpyHostToDevice));
+    PLF_CUDA_OK(cudaMemcpy(v.childCount, child_count, (size_t)n_nodes * 4, cudaMemcpyHostToDevice));
+    PLF_CUDA_OK(cudaMemcpy(v.child, child, (size_t)(n_nodes - 1) * 4, cudaMemcpyHostToDevice));
+    PLF_CUDA_OK(cudaMemcpy(v.word, word_id, (size_t)n_nodes * 4, cudaMemcpyHostToDevice));
+    PLF_CUDA_OK(cudaMemcpy(v.desc, desc, (size_t)n_nodes * 32, cudaMemcpyHostToDevice));
+    PLF_CUDA_OK(cudaMemcpy(v.weight, weight, (size_t)n_nodes * 8, cudaMemcpyHostToDevice));
+    v.nNodes = n_nodes; v.levels = levels;
+    return PLF_OK;
+}
+
+PLF_API int plf_bow_transform(plf_ctx* c, int which, int first_slot, int n_slots, int levelsup, int32_t* word_id, double* weight,
+                              int32_t* node_id, int stride) {
+    if (!c || which < 0 || which > 1 || !word_id || !weight || !node_id || first_slot < 0 || n_slots < 1 ||
+        first_slot + n_slots > c->p.max_batch || stride < 1 || stride > (which ? c->g.klCap : c->g.kpCap))
+        return fail(PLF_ERR_INVALID, "bad slot range / stride beyond the descriptor capacity");
+    if (!c->voc[which].nNodes) return fail(PLF_ERR_STATE, "bow_transform before bow_set_vocabulary");
+    if (which ? !(c->p.has_lines && c->lineValid[0]) : !c->orbValid[0]) return fail(PLF_ERR_STATE, "bow_transform before the descriptors exist");
+    PLF_CUDA_OK(cudaSetDevice(c->device));
+    const size_t cap = (size_t)std::max(c->g.kpCap, c->g.klCap);
+    if (!c->d_bowWord) {
+        PLF_CUDA_OK(dalloc(&c->d_bowWord, (size_t)c->p.max_batch * cap));
+        PLF_CUDA_OK(dalloc(&c->d_bowNode, (size_t)c->p.max_batch * cap));
+        PLF_CUDA_OK(dalloc(&c->d_bowWeight, (size_t)c->p.max_batch * cap));
+    }
+    plf_launch_bow(c, which, first_slot, n_slots, levelsup, c->d_bowWord, c->d_bowWeight, c->d_bowNode, stride);
+    cudaStream_t s = c->stream;
+    PLF_CUDA_OK(cudaMemcpyAsync(word_id, c->d_bowWord, (size_t)n_slots * stride * 4, cudaMemcpyDeviceToHost, s));
+    PLF_CUDA_OK(cudaMemcpyAsync(weight, c->d_bowWeight, (size_t)n_slots * stride * 8, cudaMemcpyDeviceToHost, s));
+    PLF_CUDA_OK(cudaMemcpyAsync(node_id, c->d_bowNode, (size_t)n_slots * stride * 4, cudaMemcpyDeviceToHost, s));
+    PLF_CUDA_OK(cudaStreamSynchronize(s));
+    PLF_CUDA_OK(cudaGetLastError());
+    return PLF_OK;
+}
+
+PLF_API int plf_bow_build_vectors(const int32_t* word_id, const double* weight, const int32_t* node_id, int n, int32_t* bow_word,
+                                  double* bow_value, int32_t* fv_node, int32_t* fv_start, int32_t* fv_feat, int* n_nodes_out) {
+    return plf_bow_build(word_id, weight, node_id, n, bow_word, bow_value, fv_node, fv_start, fv_feat, n_nodes_out);
 }
 
 // ---- landmark back-projection -------------------------------------------------------------------------

@@ -240,3 +240,55 @@ int plf_launch_stereo_lines(plf_ctx* c, int slotFirst, int nSlots) {
                                                      c->p.stereo_overlap_th, c->p.ls_min_disp_ratio, slotFirst); ++n;
     return n;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bag-of-words descent (DBoW2 TemplatedVocabulary::transform(feature, id, weight, nid, levelsup),
+// Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1230-1270): thread per descriptor; at every level the child with the
+// smallest Hamming distance is taken (strict <: the first child wins ties).  The tree is read-only and small next to
+// the frame data (ORBvoc: ~1.1 M nodes x 32 B), the features of a frame walk it independently.
+namespace {
+__global__ void __launch_bounds__(256) bow_kernel(const uint8_t* desc, const int* nFeat, int cap, int imgStride, const int* childFirst,
+                                                  const int* childCount, const int* child, const uint8_t* nodeDesc,
+                                                  const int* nodeWord, const double* nodeWeight, int levels, int levelsup,
+                                                  int* outWord, double* outWeight, int* outNode, int rows, int slotFirst) {
+    const int s = blockIdx.y, img = (slotFirst + s) * imgStride;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= rows) return;
+    const size_t o = (size_t)s * rows + i;
+    if (i >= nFeat[img]) { outWord[o] = -1; outWeight[o] = 0.0; outNode[o] = 0; return; }
+    const uint4* f4 = reinterpret_cast<const uint4*>(desc + ((size_t)img * cap + i) * 32);
+    const uint4 a = f4[0], b = f4[1];
+    const int nidLevel = levels - levelsup;
+    int node = 0, level = 0, nid = 0;
+    do {
+        ++level;
+        const int c0 = childFirst[node], nc = childCount[node];
+        int best = 0x7fffffff, bestId = node;
+        for (int k = 0; k < nc; ++k) {
+            const int id = child[c0 + k];
+            const uint4* n4 = reinterpret_cast<const uint4*>(nodeDesc + (size_t)id * 32);
+            const uint4 p = n4[0], q = n4[1];
+            const int d = __popc(a.x ^ p.x) + __popc(a.y ^ p.y) + __popc(a.z ^ p.z) + __popc(a.w ^ p.w) +
+                          __popc(b.x ^ q.x) + __popc(b.y ^ q.y) + __popc(b.z ^ q.z) + __popc(b.w ^ q.w);
+            if (d < best) { best = d; bestId = id; }
+        }
+        node = bestId;
+        if (level == nidLevel) nid = node;
+    } while (childCount[node] > 0);
+    outWord[o] = nodeWord[node];
+    outWeight[o] = nodeWeight[node];
+    outNode[o] = nid;
+}
+}  // namespace
+
+int plf_launch_bow(plf_ctx* c, int which, int slotFirst, int nSlots, int levelsup, int* dWord, double* dWeight, int* dNode, int rows) {
+    const PlfGeom& g = c->g;
+    const PlfVocab& v = c->voc[which];
+    const uint8_t* desc = which ? c->d_ldesc : c->d_desc;
+    const int* nFeat = which ? c->d_nKl : c->d_nKp;
+    const int cap = which ? g.klCap : g.kpCap;
+    bow_kernel<<<dim3((rows + 255) / 256, nSlots), 256, 0, c->stream>>>(desc, nFeat, cap, 2, v.childFirst, v.childCount, v.child, v.desc,
+                                                                       v.word, v.weight, v.levels, levelsup, dWord, dWeight, dNode,
+                                                                       rows, slotFirst);
+    return 1;
+}

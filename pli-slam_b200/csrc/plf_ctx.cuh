@@ -61,6 +61,13 @@ struct PlfGeom {          // passed by value to kernels (fits the 4 KB parameter
     int seedCap;
 };
 
+struct PlfVocab {           // DBoW2 vocabulary tree on the device (plf_bow_set_vocabulary)
+    int nNodes = 0, levels = 0;
+    int *childFirst = nullptr, *childCount = nullptr, *child = nullptr, *word = nullptr;
+    uint8_t* desc = nullptr;
+    double* weight = nullptr;
+};
+
 struct plf_ctx {
     plf_params p;
     PlfGeom g;
@@ -131,6 +138,10 @@ struct plf_ctx {
     uint2* d_rmap[2] = {nullptr, nullptr};
     int* d_gridStart = nullptr;      // [max_batch][64*48+1] CSR of Frame::mGrid (plf_feature_grid), allocated on first use
     int* d_gridIdx = nullptr;        // [max_batch][kpCap]
+    PlfVocab voc[2];                 // 0: ORB vocabulary, 1: line vocabulary
+    int* d_bowWord = nullptr;        // [max_batch][max(kpCap, klCap)] outputs of plf_bow_transform
+    int* d_bowNode = nullptr;
+    double* d_bowWeight = nullptr;
     float* d_bpPose = nullptr;       // [max_batch][12] Rwc, Ow of plf_backproject
     float* d_bpX = nullptr;          // [max_batch][kpCap][3]
     double* d_bpL = nullptr;         // [max_batch][klCap][6]
@@ -167,6 +178,7 @@ inline bool plf_raise_smem_optin(size_t (&granted)[64], int device, size_t smem)
 }
 
 int plf_launch_unpack(plf_ctx* c, const uint8_t* stage, size_t sideBytes, int stride, int batch);
+int plf_launch_bow(plf_ctx* c, int which, int slotFirst, int nSlots, int levelsup, int* dWord, double* dWeight, int* dNode, int rows);
 int plf_launch_backproject(plf_ctx* c, int slotFirst, int nSlots, const float* dRwc, const float* dOw, float fy, float cx,
                            float cy, float* dX3d, int x3dRows, double* dL3d, int l3dRows);
 int plf_launch_feature_grid(plf_ctx* c, int slotFirst, int nSlots, int* cellStart, int* cellIdx);

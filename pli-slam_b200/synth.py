@@ -175,3 +175,36 @@ def synth_curvy(W=752, H=480, seed=1):
     img *= 1.0 - 0.25 * (((xs - W / 2) / W) ** 2 + ((ys - H / 2) / H) ** 2)
     img += rng.integers(-3, 4, (H, W))
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def synth_vocabulary(k=10, L=4, seed=0, ragged=0.05, stop=0.02):
+    """A DBoW2-shaped vocabulary tree for tests (the real ORBvoc cannot travel): k children per inner node, at most L
+    levels below the root, node descriptors = the parent's with a level-dependent share of random bit flips (so the
+    descent is meaningful), a share `ragged` of the inner nodes cut short into leaves, a share `stop` of the words with
+    weight 0 (stopped words).  Returns the flat arrays plf_bow_set_vocabulary takes."""
+    rng = np.random.default_rng(seed)
+    desc = [rng.integers(0, 256, 32, dtype=np.uint8)]
+    first, count, child, level = [0], [0], [], [0]
+    queue = [0]
+    while queue:
+        i = queue.pop(0)
+        if level[i] == L or (level[i] > 0 and rng.random() < ragged):
+            continue
+        first[i], count[i] = len(child), k
+        for _ in range(k):
+            j = len(desc)
+            flips = rng.random(256) < (0.5 / (level[i] + 1))
+            d = np.unpackbits(desc[i]) ^ flips.astype(np.uint8)
+            desc.append(np.packbits(d))
+            first.append(0); count.append(0); level.append(level[i] + 1)
+            child.append(j)
+            queue.append(j)
+    n = len(desc)
+    word = np.full(n, -1, np.int32)
+    weight = np.zeros(n, np.float64)
+    leaves = [i for i in range(n) if count[i] == 0]
+    for w, i in enumerate(leaves):
+        word[i] = w
+        weight[i] = 0.0 if rng.random() < stop else float(rng.uniform(0.5, 9.0))
+    return dict(levels=L, child_first=np.array(first, np.int32), child_count=np.array(count, np.int32),
+                child=np.array(child, np.int32), desc=np.stack(desc), word_id=word, weight=weight)

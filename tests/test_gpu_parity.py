@@ -398,3 +398,28 @@ def test_curved_content_matches_oracle(plf, product, oracle, refine):
         assert (ro.u_right[b, :n] >= 0).sum() > 50
         assert np.array_equal(rg.u_right[b, :n], ro.u_right[b, :n]) and np.array_equal(rg.depth[b, :n], ro.depth[b, :n])
         assert np.array_equal(rg.line_match12[b, :nl], ro.line_match12[b, :nl]) and np.array_equal(rg.disp_se[b, :nl], ro.disp_se[b, :nl])
+
+
+def test_bow_transform_matches_oracle(plf, product, oracle):
+    """plf_bow_transform (DBoW2 descent of every left ORB / LBD descriptor) for a batch: word ids, weights and node ids
+    identical to the oracle; BowVector / FeatureVector built from them identical too; loud errors without a vocabulary."""
+    L, R = plf.synth_batch(752, 480, [71, 72, 73])
+    f, o = plf.Frontend(product, max_batch=3), plf.Frontend(oracle, max_batch=3)
+    rg, ro = f.frontend_batch(L, R), o.frontend_batch(L, R)
+    with pytest.raises(plf.PlfError):
+        f.bow_transform(0, 3)
+    for which, levelsup, voc in ((0, 4, plf.synth_vocabulary(10, 6, seed=1, ragged=0.3)), (1, 2, plf.synth_vocabulary(8, 4, seed=2))):
+        f.bow_set_vocabulary(which, voc); o.bow_set_vocabulary(which, voc)
+        wg, vg, ng = f.bow_transform(which, 3, 0, levelsup)
+        wo, vo, no = o.bow_transform(which, 3, 0, levelsup)
+        assert np.array_equal(wg, wo) and np.array_equal(vg, vo) and np.array_equal(ng, no)
+        n = int(ro.n_kl_left[1]) if which else int(ro.n_kp_left[1])
+        assert n > 100 and (wo[1, :n] >= 0).all()
+        bg, bo = f.bow_build(wg[1, :n], vg[1, :n], ng[1, :n]), o.bow_build(wo[1, :n], vo[1, :n], no[1, :n])
+        assert np.array_equal(bg[0], bo[0]) and np.array_equal(bg[1], bo[1]) and bg[2] == bo[2]
+    w1, v1, n1 = f.bow_transform(0, 1, 2, 4)
+    assert np.array_equal(w1[0], wo_first := f.bow_transform(0, 3, 0, 4)[0][2])
+    bad = plf.synth_vocabulary(4, 2, seed=5)
+    bad["child"] = bad["child"].copy(); bad["child"][0] = 0          # a child pointing back at the root
+    with pytest.raises(plf.PlfError):
+        f.bow_set_vocabulary(0, bad)

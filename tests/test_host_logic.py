@@ -218,3 +218,56 @@ def test_backproject_oracle_against_cv2_gemm_and_numpy(plf, oracle):
             assert np.array_equal(l3d[0, i, 3 * e:3 * e + 3], want), (i, e)
         hits += 1
     assert hits > 20
+
+
+def _bow_python(voc, descs, levelsup):
+    """DBoW2 transform(features, BowVector, FeatureVector, levelsup) restated directly (TemplatedVocabulary.h:1139-1270,
+    BowVector.cpp:34-84): TF_IDF weighting, L1 norm."""
+    cf, cc, ch = voc["child_first"], voc["child_count"], voc["child"]
+    nd = np.unpackbits(voc["desc"], axis=1)
+    words, weights, nodes = [], [], []
+    bow, fv = {}, {}
+    for i, f in enumerate(np.unpackbits(descs, axis=1)):
+        node, level, nid = 0, 0, 0
+        while True:
+            level += 1
+            kids = ch[cf[node]:cf[node] + cc[node]]
+            d = (nd[kids] ^ f).sum(axis=1)
+            node = int(kids[int(np.argmin(d))])          # argmin returns the first minimum = strict '<' scan
+            if level == voc["levels"] - levelsup:
+                nid = node
+            if cc[node] == 0:
+                break
+        w = float(voc["weight"][node])
+        words.append(int(voc["word_id"][node])); weights.append(w); nodes.append(nid)
+        if w > 0:
+            bow[words[-1]] = bow.get(words[-1], 0.0) + w
+            fv.setdefault(nid, []).append(i)
+    norm = 0.0
+    for k in sorted(bow):
+        norm += abs(bow[k])
+    if norm > 0:
+        bow = {k: v / norm for k, v in bow.items()}
+    return words, weights, nodes, bow, fv
+
+
+@pytest.mark.parametrize("which,levelsup", [(0, 2), (1, 4), (0, 0)])
+def test_bow_oracle_against_python(plf, oracle, which, levelsup):
+    """Frame::ComputeBoW's per-feature descent and the BowVector / FeatureVector construction on a synthetic DBoW2-shaped
+    vocabulary (ragged tree, some stopped words): oracle and header inline against the direct restatement."""
+    voc = plf.synth_vocabulary(k=10, L=4, seed=3 + which)
+    L, R = plf.synth_pair(752, 480, 5)
+    o = plf.Frontend(oracle, max_batch=1)
+    res = o.frontend_batch(L[None], R[None])
+    n = int(res.n_kl_left[0]) if which else int(res.n_kp_left[0])
+    descs = (res.ldesc_left if which else res.desc_left)[0, :n]
+    o.bow_set_vocabulary(which, voc)
+    w, v, nd = o.bow_transform(which, 1, 0, levelsup)
+    words, weights, nodes, bow, fv = _bow_python(voc, descs, levelsup)
+    assert list(w[0, :n]) == words and list(v[0, :n]) == weights and list(nd[0, :n]) == nodes
+    assert np.all(w[0, n:] == -1) and not v[0, n:].any()
+    bw, bv, fvec = o.bow_build(w[0, :n], v[0, :n], nd[0, :n])
+    assert list(bw) == sorted(bow) and [bow[k] for k in sorted(bow)] == list(bv)
+    assert fvec == fv and abs(bv.sum() - 1.0) < 1e-12 and len(bw) > 50
+    if voc["levels"] - levelsup <= 0:
+        assert set(fvec) == {0}

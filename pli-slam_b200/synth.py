@@ -183,6 +183,25 @@ def synth_vocabulary(k=10, L=4, seed=0, ragged=0.05, stop=0.02):
     descent is meaningful), a share `ragged` of the inner nodes cut short into leaves, a share `stop` of the words with
     weight 0 (stopped words).  Returns the flat arrays plf_bow_set_vocabulary takes."""
     rng = np.random.default_rng(seed)
+    if ragged == 0:          # complete tree, built level by level (fast enough for the 10^6-word shape of ORBvoc)
+        levels = [rng.integers(0, 256, (1, 32), dtype=np.uint8)]
+        for l in range(L):
+            par = np.repeat(levels[-1], k, axis=0)
+            flips = np.packbits(rng.random((par.shape[0], 256)) < (0.5 / (l + 1)), axis=1)
+            levels.append(par ^ flips)
+        desc = np.concatenate(levels)
+        n = desc.shape[0]
+        start = np.cumsum([0] + [k ** l for l in range(L + 1)])          # first node id of every level
+        first = np.zeros(n, np.int32); count = np.zeros(n, np.int32)
+        inner = start[L]                                                   # nodes of levels 0 .. L-1
+        count[:inner] = k
+        first[:inner] = np.arange(inner, dtype=np.int64) * k               # children lists are contiguous in BFS order
+        child = np.arange(1, n, dtype=np.int32)
+        word = np.full(n, -1, np.int32); weight = np.zeros(n, np.float64)
+        nw = n - inner
+        word[inner:] = np.arange(nw, dtype=np.int32)
+        weight[inner:] = np.where(rng.random(nw) < stop, 0.0, rng.uniform(0.5, 9.0, nw))
+        return dict(levels=L, child_first=first, child_count=count, child=child, desc=desc, word_id=word, weight=weight)
     desc = [rng.integers(0, 256, 32, dtype=np.uint8)]
     first, count, child, level = [0], [0], [], [0]
     queue = [0]

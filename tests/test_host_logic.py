@@ -255,7 +255,7 @@ def _bow_python(voc, descs, levelsup):
 def test_bow_oracle_against_python(plf, oracle, which, levelsup):
     """Frame::ComputeBoW's per-feature descent and the BowVector / FeatureVector construction on a synthetic DBoW2-shaped
     vocabulary (ragged tree, some stopped words): oracle and header inline against the direct restatement."""
-    voc = plf.synth_vocabulary(k=10, L=4, seed=3 + which)
+    voc = plf.synth_vocabulary(k=10, L=4, seed=3 + which) if levelsup else plf.synth_vocabulary(k=6, L=3, seed=9, ragged=0.0, stop=0.1)
     L, R = plf.synth_pair(752, 480, 5)
     o = plf.Frontend(oracle, max_batch=1)
     res = o.frontend_batch(L[None], R[None])

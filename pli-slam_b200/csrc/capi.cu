@@ -12,6 +12,7 @@ int plf_set_cuda_error(cudaError_t e, const char* what, const char* file, int li
     char buf[512];
     snprintf(buf, sizeof buf, "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
     g_err = buf;
+    cudaGetLastError();          // reported: do not let a non-sticky error (e.g. out of memory) poison the next call's check
     return PLF_ERR_CUDA;
 }
 static int fail(int code, const char* msg) { g_err = msg; return code; }
@@ -186,6 +187,9 @@ static int build_geometry(plf_ctx* c, std::vector<PlfCell>& cells) {
     return PLF_OK;
 }
 
+static int create_buffers(plf_ctx* c, const plf_params* p, std::vector<PlfCell>& cells);
+PLF_API int plf_destroy(plf_ctx* c);
+
 PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
     if (!p || !out) return fail(PLF_ERR_INVALID, "null argument");
     if (p->width < 64 || p->height < 64 || p->max_batch < 1 || p->n_levels < 1 || p->n_levels > PLF_MAX_LEVELS ||
@@ -208,7 +212,19 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
     c->device = device;
     std::vector<PlfCell> cells;
     int rc = build_geometry(c, cells);
-    if (rc) { delete c; return rc; }
+    if (!rc) rc = create_buffers(c, p, cells);
+    if (rc) {                       // nothing of a half-built context survives (device memory included)
+        const std::string why = g_err;
+        plf_destroy(c);
+        cudaGetLastError();
+        g_err = why;
+        return rc;
+    }
+    *out = c;
+    return PLF_OK;
+}
+
+static int create_buffers(plf_ctx* c, const plf_params* p, std::vector<PlfCell>& cells) {
     PlfGeom& g = c->g;
     const size_t nImg = (size_t)p->max_batch * 2, nSlot = p->max_batch;
     c->nImgMax = (int)nImg;
@@ -325,11 +341,10 @@ PLF_API int plf_create(const plf_params* p, int device, plf_ctx** out) {
     PLF_CUDA_OK(dalloc(&c->d_disp, nSlot * (size_t)g.klCap * 2));
     PLF_CUDA_OK(dalloc(&c->d_le, nSlot * (size_t)g.klCap * 3));
     PLF_CUDA_OK(cudaMallocHost((void**)&c->h_counts, (nImg * 4 + 16) * sizeof(int)));
-    c->ev.resize(PLF_MAX_MARKS);
+    c->ev.assign(PLF_MAX_MARKS, nullptr);
     for (auto& e : c->ev) PLF_CUDA_OK(cudaEventCreate(&e));
     c->markNames.assign(PLF_MAX_MARKS, "");
     c->stageMs.assign(PLF_MAX_MARKS, 0.f);
-    *out = c;
     return PLF_OK;
 }
 
@@ -347,8 +362,8 @@ PLF_API int plf_destroy(plf_ctx* c) {
                     c->voc[1].childFirst, c->voc[1].childCount, c->voc[1].child, c->voc[1].word, c->voc[1].desc, c->voc[1].weight};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (c->h_counts) cudaFreeHost(c->h_counts);
-    for (auto& e : c->ev) cudaEventDestroy(e);
-    cudaStreamDestroy(c->stream);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return PLF_OK;
 }

@@ -423,3 +423,19 @@ def test_bow_transform_matches_oracle(plf, product, oracle):
     bad["child"] = bad["child"].copy(); bad["child"][0] = 0          # a child pointing back at the root
     with pytest.raises(plf.PlfError):
         f.bow_set_vocabulary(0, bad)
+
+
+def test_failed_create_releases_device_memory(plf, product):
+    """A context that does not fit (cudaMalloc fails half-way through plf_create) reports PLF_ERR_CUDA and leaves no device
+    memory behind; the next context works."""
+    import torch
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    with pytest.raises(plf.PlfError) as e:
+        plf.Frontend(product, max_batch=12000)              # ~300 GB of buffers
+    assert e.value.code == 3                                # PLF_ERR_CUDA
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < (1 << 30)
+    f = plf.Frontend(product, max_batch=1)
+    L, R = plf.synth_pair(752, 480, 1)
+    assert int(f.frontend_batch(L[None], R[None]).n_kp_left[0]) > 1000

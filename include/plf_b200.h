@@ -241,6 +241,32 @@ PLF_API int PLF_FN(feature_grid)(plf_ctx* ctx, int first_slot, int n_slots, int3
                                  int idx_stride);
 
 /* ------------------------------------------------------------------------------------------------------ */
+/* Projection-window descriptor search (second half).                                     */
+
+/* One MapPoint of the local map as ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, ...) reads it
+ * (src/ORBmatcher.cc:44-130; rectified stereo, Nleft == -1).  56 bytes. */
+typedef struct plf_proj_query {
+    float proj_x, proj_y;       /* mTrackProjX, mTrackProjY                                                  */
+    float proj_xr;              /* mTrackProjXR (stereo consistency check against mvuRight)                  */
+    float view_cos;             /* mTrackViewCos -> RadiusByViewingCos (:216-222): > 0.998 ? 2.5 : 4.0       */
+    int32_t level;              /* mnTrackScaleLevel                                                         */
+    int32_t skip;               /* != 0: the `continue`s of :52-61 (not in view, too far, bad)               */
+    uint8_t desc[32];           /* pMP->GetDescriptor()                                                      */
+} plf_proj_query;
+
+/* Replaces: int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th, ...)
+ * (src/ORBmatcher.cc:44-130) for the left keypoints of one slot.  The window search, the level / stereo filters and
+ * every Hamming distance run on the device (a warp per map point, candidates in GetFeaturesInArea order); the
+ * order-dependent part — features already taken are skipped, best / second best with the reference's update rule, the
+ * TH_HIGH and mfNNratio tests, the assignment F.mvpMapPoints[bestIdx] = pMP — runs on the host in query order.
+ * occupied: one byte per keypoint, in/out: != 0 where F.mvpMapPoints[idx] has Observations() > 0; set for every feature
+ * assigned by this call (map points of the local map have observations).  match[i] = feature index given to query i
+ * or -1.  Returns the reference's nmatches in *n_matches. */
+PLF_API int PLF_FN(search_by_projection)(plf_ctx* ctx, int slot, const plf_proj_query* queries, int n_queries, float th,
+                                         float nn_ratio, int th_high, uint8_t* occupied, int32_t* match,
+                                         int* n_matches);
+
+/* ------------------------------------------------------------------------------------------------------ */
 /* Landmark back-projection: the epilogue that turns stereo matches into 3-D landmarks.   */
 
 /* Replaces: cv::Mat Frame::UnprojectStereo(const int& i) (src/Frame.cc:1332-1347; callers src/Tracking.cc:1977, 2866,

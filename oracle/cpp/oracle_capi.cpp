@@ -450,6 +450,81 @@ PLF_API int plf_cpu_bow_build_vectors(const int32_t* word_id, const double* weig
     return plf_bow_build(word_id, weight, node_id, n, bow_word, bow_value, fv_node, fv_start, fv_feat, n_nodes_out);
 }
 
+// ---- ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, ...) (src/ORBmatcher.cc:44-130), Nleft == -1 ----
+// parity unpinned (no runnable reference: MapPoint / Frame state); the loops follow the reference line by line.
+PLF_API int plf_cpu_search_by_projection(plf_ctx* c, int slot, const plf_proj_query* queries, int n_queries, float th, float nn_ratio,
+                                         int th_high, uint8_t* occupied, int32_t* match, int* n_matches) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || !queries || n_queries < 0 || !occupied || !match)
+        return fail(PLF_ERR_INVALID, "bad arguments");
+    const Slot& sl = c->slots[slot];
+    const std::vector<plf_keypoint>& kps = sl.orb[0].kps;
+    const uint8_t* D = sl.orb[0].desc.data();
+    const float invW = (float)PLF_GRID_COLS / ((float)c->p.width - 0.0f), invH = (float)PLF_GRID_ROWS / ((float)c->p.height - 0.0f);
+    std::vector<std::vector<int>> grid(PLF_GRID_COLS * PLF_GRID_ROWS);           // Frame::AssignFeaturesToGrid
+    for (int i = 0; i < (int)kps.size(); ++i) {
+        const int px = (int)std::round((kps[i].x - 0.0f) * invW), py = (int)std::round((kps[i].y - 0.0f) * invH);
+        if (px < 0 || px >= PLF_GRID_COLS || py < 0 || py >= PLF_GRID_ROWS) continue;
+        grid[px * PLF_GRID_ROWS + py].push_back(i);
+    }
+    const bool bFactor = th != 1.0f;
+    int nmatches = 0;
+    for (int iMP = 0; iMP < n_queries; ++iMP) {
+        const plf_proj_query& q = queries[iMP];
+        match[iMP] = -1;
+        if (q.skip || q.level < 0 || q.level >= (int)c->ot.scale.size()) continue;
+        float r = q.view_cos > 0.998f ? 2.5f : 4.0f;
+        if (bFactor) r *= th;
+        const float rad = r * c->ot.scale[q.level];
+        const int minLevel = q.level - 1, maxLevel = q.level;
+        // Frame::GetFeaturesInArea(x, y, rad, minLevel, maxLevel)
+        std::vector<int> vIndices;
+        {
+            const int x0 = std::max(0, (int)std::floor((q.proj_x - 0.0f - rad) * invW));
+            const int x1 = std::min(PLF_GRID_COLS - 1, (int)std::ceil((q.proj_x - 0.0f + rad) * invW));
+            const int y0 = std::max(0, (int)std::floor((q.proj_y - 0.0f - rad) * invH));
+            const int y1 = std::min(PLF_GRID_ROWS - 1, (int)std::ceil((q.proj_y - 0.0f + rad) * invH));
+            if (x0 < PLF_GRID_COLS && x1 >= 0 && y0 < PLF_GRID_ROWS && y1 >= 0) {
+                const bool check = minLevel > 0 || maxLevel >= 0;
+                for (int ix = x0; ix <= x1; ++ix)
+                    for (int iy = y0; iy <= y1; ++iy)
+                        for (int idx : grid[ix * PLF_GRID_ROWS + iy]) {
+                            const plf_keypoint& k = kps[idx];
+                            if (check) {
+                                if (k.octave < minLevel) continue;
+                                if (maxLevel >= 0 && k.octave > maxLevel) continue;
+                            }
+                            if (std::fabs(k.x - q.proj_x) < rad && std::fabs(k.y - q.proj_y) < rad) vIndices.push_back(idx);
+                        }
+            }
+        }
+        if (vIndices.empty()) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (occupied[idx]) continue;
+            if (idx < (int)sl.uRight.size() && sl.uRight[idx] > 0) {
+                const float er = std::fabs(q.proj_xr - sl.uRight[idx]);
+                if (er > rad) continue;
+            }
+            const int dist = plf_hamming256(q.desc, D + (size_t)idx * 32);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = kps[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = kps[idx].octave; bestDist2 = dist;
+            }
+        }
+        if (bestDist <= th_high) {
+            if (bestLevel == bestLevel2 && bestDist > nn_ratio * bestDist2) continue;
+            if (bestLevel != bestLevel2 || bestDist <= nn_ratio * bestDist2) {
+                match[iMP] = bestIdx;
+                occupied[bestIdx] = 1;
+                ++nmatches;
+            }
+        }
+    }
+    if (n_matches) *n_matches = nmatches;
+    return PLF_OK;
+}
+
 static void run_pair(plf_ctx* c, int b) {
     Slot& s = c->slots[b];
     const int w = c->p.width, h = c->p.height;

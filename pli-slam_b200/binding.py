@@ -60,6 +60,8 @@ KEYLINE_DT = np.dtype([("angle", "f4"), ("class_id", "i4"), ("octave", "i4"), ("
 assert KEYPOINT_DT.itemsize == 28 and KEYLINE_DT.itemsize == 68
 
 # every symbol include/plf_b200.h declares (without prefix)
+PROJ_QUERY_DT = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4"),
+                          ("skip", "<i4"), ("desc", "u1", (32,))])       # plf_proj_query, 56 bytes
 GRID_COLS, GRID_ROWS = 64, 48      # FRAME_GRID_COLS / FRAME_GRID_ROWS (include/Frame.h:59-60)
 
 ABI_SYMBOLS = [
@@ -68,7 +70,7 @@ ABI_SYMBOLS = [
     "match", "frontend_batch", "batch_upload", "batch_run", "batch_download", "sync", "batch_io_bytes",
     "last_launch_count", "set_stage_timing", "get_stage_ms", "stream", "tap_blurred_level", "tap_pyramid_level",
     "tap_fast_candidates", "tap_lsd_scaled", "tap_lsd_angles", "tap_lsd_segments", "tap_lbd_float",
-    "rectify_set_maps", "rectify", "batch_upload_raw", "feature_grid", "get_features_in_area", "backproject", "bow_set_vocabulary", "bow_transform", "bow_build_vectors",
+    "rectify_set_maps", "rectify", "batch_upload_raw", "feature_grid", "get_features_in_area", "backproject", "bow_set_vocabulary", "bow_transform", "bow_build_vectors", "search_by_projection",
 ]
 
 
@@ -348,6 +350,17 @@ class Frontend:
         ix = np.full((n_slots, self.kp_cap), -1, np.int32)
         self.lib.check(self.lib.fn("feature_grid")(self.ctx, first_slot, n_slots, _ptr(st), _ptr(ix), self.kp_cap))
         return st, ix
+
+    def search_by_projection(self, queries, occupied, th=1.0, nn_ratio=0.8, th_high=100, slot=0):
+        """ORBmatcher::SearchByProjection(F, vpMapPoints, th): queries = PROJ_QUERY_DT array, occupied = uint8 per keypoint
+        (updated in place) -> (match index per query, nmatches)."""
+        queries = np.ascontiguousarray(queries, PROJ_QUERY_DT)
+        assert occupied.dtype == np.uint8 and occupied.flags.c_contiguous
+        match = np.full(len(queries), -1, np.int32)
+        nm = C.c_int(0)
+        self.lib.check(self.lib.fn("search_by_projection")(self.ctx, slot, _ptr(queries), len(queries), C.c_float(th),
+                                                           C.c_float(nn_ratio), int(th_high), _ptr(occupied), _ptr(match), C.byref(nm)))
+        return match, nm.value
 
     # ---- bag of words (SURVEY §8f rank 3) ------------------------------------------------------------------------------
     def bow_set_vocabulary(self, which, voc):

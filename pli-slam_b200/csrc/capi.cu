@@ -357,7 +357,7 @@ PLF_API int plf_destroy(plf_ctx* c) {
                     c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_rec, c->d_n2max, c->d_seeds,
                     c->d_nSeeds, c->d_n2, c->d_used, c->d_reg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
                     c->d_sobel, c->d_lbd, c->d_ldesc, c->d_rowMask, c->d_dirR, c->d_dmat, c->d_m21, c->d_m12, c->d_disp,
-                    c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage, c->d_rmap[0], c->d_rmap[1], c->d_gridStart, c->d_gridIdx, c->d_bpPose, c->d_bpX, c->d_bpL, c->d_bowWord, c->d_bowNode, c->d_bowWeight,
+                    c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage, c->d_rmap[0], c->d_rmap[1], c->d_gridStart, c->d_gridIdx, c->d_bpPose, c->d_bpX, c->d_bpL, c->d_bowWord, c->d_bowNode, c->d_bowWeight, c->d_projQ, c->d_projCount, c->d_projStart, c->d_projPool,
                     c->voc[0].childFirst, c->voc[0].childCount, c->voc[0].child, c->voc[0].word, c->voc[0].desc, c->voc[0].weight,
                     c->voc[1].childFirst, c->voc[1].childCount, c->voc[1].child, c->voc[1].word, c->voc[1].desc, c->voc[1].weight};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -684,6 +684,78 @@ PLF_API int plf_feature_grid(plf_ctx* c, int first_slot, int n_slots, int32_t* c
 PLF_API int plf_get_features_in_area(const plf_keypoint* kps, const int32_t* cell_start, const int32_t* cell_idx, int width,
                                      int height, float x, float y, float r, int min_level, int max_level, int32_t* out, int cap) {
     return plf_features_in_area(kps, cell_start, cell_idx, width, height, x, y, r, min_level, max_level, out, cap);
+}
+
+// ---- projection-window search (second half) ----------------------------------------------------------
+PLF_API int plf_search_by_projection(plf_ctx* c, int slot, const plf_proj_query* queries, int n_queries, float th, float nn_ratio,
+                                     int th_high, uint8_t* occupied, int32_t* match, int* n_matches) {
+    if (!c || slot < 0 || slot >= c->p.max_batch || !queries || n_queries < 0 || !occupied || !match)
+        return fail(PLF_ERR_INVALID, "bad arguments");
+    if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "search_by_projection before the frame was extracted and stereo-matched");
+    if (n_matches) *n_matches = 0;
+    if (n_queries == 0) return PLF_OK;
+    PLF_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    constexpr int NC1 = PLF_GRID_COLS * PLF_GRID_ROWS + 1;
+    if (!c->d_gridStart) {
+        PLF_CUDA_OK(dalloc(&c->d_gridStart, (size_t)c->p.max_batch * NC1));
+        PLF_CUDA_OK(dalloc(&c->d_gridIdx, (size_t)c->p.max_batch * c->g.kpCap));
+    }
+    if (c->projQCap < (size_t)n_queries) {
+        PLF_CUDA_OK(cudaStreamSynchronize(s));
+        if (c->d_projQ) { cudaFree(c->d_projQ); cudaFree(c->d_projCount); cudaFree(c->d_projStart); }
+        c->d_projQ = nullptr; c->d_projCount = nullptr; c->d_projStart = nullptr; c->projQCap = 0;
+        PLF_CUDA_OK(dalloc(&c->d_projQ, (size_t)n_queries));
+        PLF_CUDA_OK(dalloc(&c->d_projCount, (size_t)n_queries));
+        PLF_CUDA_OK(dalloc(&c->d_projStart, (size_t)n_queries));
+        c->projQCap = n_queries;
+    }
+    // Frame::AssignFeaturesToGrid for this slot (slot-local CSR at the start of the grid buffers)
+    plf_launch_feature_grid(c, slot, 1, c->d_gridStart, c->d_gridIdx);
+    PLF_CUDA_OK(cudaMemcpyAsync(c->d_projQ, queries, (size_t)n_queries * sizeof(plf_proj_query), cudaMemcpyHostToDevice, s));
+    plf_launch_proj_candidates(c, slot, c->d_projQ, n_queries, th, c->d_gridStart, c->d_gridIdx, c->d_projCount, nullptr, nullptr, false);
+    std::vector<int> cnt(n_queries), start(n_queries + 1, 0);
+    PLF_CUDA_OK(cudaMemcpyAsync(cnt.data(), c->d_projCount, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, s));
+    PLF_CUDA_OK(cudaStreamSynchronize(s));
+    for (int i = 0; i < n_queries; ++i) start[i + 1] = start[i] + cnt[i];
+    const size_t total = (size_t)start[n_queries];
+    std::vector<int2> pool(total);
+    if (total) {
+        if (c->projPoolCap < total) {
+            if (c->d_projPool) cudaFree(c->d_projPool);
+            c->d_projPool = nullptr; c->projPoolCap = 0;
+            PLF_CUDA_OK(dalloc(&c->d_projPool, total * 2));
+            c->projPoolCap = total * 2;
+        }
+        PLF_CUDA_OK(cudaMemcpyAsync(c->d_projStart, start.data(), (size_t)n_queries * 4, cudaMemcpyHostToDevice, s));
+        plf_launch_proj_candidates(c, slot, c->d_projQ, n_queries, th, c->d_gridStart, c->d_gridIdx, c->d_projCount, c->d_projStart,
+                                   c->d_projPool, true);
+        PLF_CUDA_OK(cudaMemcpyAsync(pool.data(), c->d_projPool, total * sizeof(int2), cudaMemcpyDeviceToHost, s));
+        PLF_CUDA_OK(cudaStreamSynchronize(s));
+    }
+    PLF_CUDA_OK(cudaGetLastError());
+    // the order-dependent half, in query order (src/ORBmatcher.cc:84-129)
+    int nm = 0;
+    for (int i = 0; i < n_queries; ++i) {
+        match[i] = -1;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int j = start[i]; j < start[i + 1]; ++j) {
+            const int idx = pool[j].x, dist = pool[j].y & 0xFFFF, oct = pool[j].y >> 16;
+            if (occupied[idx]) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = idx; }
+            else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
+        }
+        if (bestDist <= th_high) {
+            if (bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) continue;
+            if (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2) {
+                match[i] = bestIdx;
+                occupied[bestIdx] = 1;
+                ++nm;
+            }
+        }
+    }
+    if (n_matches) *n_matches = nm;
+    return PLF_OK;
 }
 
 // ---- bag-of-words transform -------------------------------------------------------------------------

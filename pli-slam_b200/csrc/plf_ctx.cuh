@@ -142,6 +142,11 @@ struct plf_ctx {
     int* d_bowWord = nullptr;        // [max_batch][max(kpCap, klCap)] outputs of plf_bow_transform
     int* d_bowNode = nullptr;
     double* d_bowWeight = nullptr;
+    plf_proj_query* d_projQ = nullptr;   // plf_search_by_projection scratch: queries, counts, segment starts, candidate pool
+    int* d_projCount = nullptr;
+    int* d_projStart = nullptr;
+    int2* d_projPool = nullptr;
+    size_t projQCap = 0, projPoolCap = 0;
     float* d_bpPose = nullptr;       // [max_batch][12] Rwc, Ow of plf_backproject
     float* d_bpX = nullptr;          // [max_batch][kpCap][3]
     double* d_bpL = nullptr;         // [max_batch][klCap][6]
@@ -178,6 +183,8 @@ inline bool plf_raise_smem_optin(size_t (&granted)[64], int device, size_t smem)
 }
 
 int plf_launch_unpack(plf_ctx* c, const uint8_t* stage, size_t sideBytes, int stride, int batch);
+int plf_launch_proj_candidates(plf_ctx* c, int slot, const plf_proj_query* dQ, int nq, float th, const int* dCellStart,
+                               const int* dCellIdx, int* dCount, const int* dSegStart, int2* dPool, bool fill);
 int plf_launch_bow(plf_ctx* c, int which, int slotFirst, int nSlots, int levelsup, int* dWord, double* dWeight, int* dNode, int rows);
 int plf_launch_backproject(plf_ctx* c, int slotFirst, int nSlots, const float* dRwc, const float* dOw, float fy, float cx,
                            float cy, float* dX3d, int x3dRows, double* dL3d, int l3dRows);

@@ -439,3 +439,26 @@ def test_failed_create_releases_device_memory(plf, product):
     f = plf.Frontend(product, max_batch=1)
     L, R = plf.synth_pair(752, 480, 1)
     assert int(f.frontend_batch(L[None], R[None]).n_kp_left[0]) > 1000
+
+
+@pytest.mark.parametrize("th", [1.0, 3.0, 10.0])
+def test_search_by_projection_matches_oracle(plf, product, oracle, th):
+    """plf_search_by_projection (window search + Hamming on the device, order-dependent assignment on the host) against
+    the oracle: ~1350 map points against a frame with 10 % of its features already taken; matches, nmatches and the
+    updated occupancy identical; th = 10 gives windows of up to +-140 px (hundreds of candidates per map point)."""
+    from test_host_logic import _proj_queries
+    L, R = plf.synth_batch(752, 480, [81, 82])
+    f, o = plf.Frontend(product, max_batch=2), plf.Frontend(oracle, max_batch=2)
+    rg, ro = f.frontend_batch(L, R), o.frontend_batch(L, R)
+    for b in (1, 0):
+        n = int(ro.n_kp_left[b])
+        rng = np.random.default_rng(20 + b)
+        q = _proj_queries(plf, ro, b, rng)
+        occ0 = (rng.random(n) < 0.1).astype(np.uint8)
+        og, oo = occ0.copy(), occ0.copy()
+        mg, ng = f.search_by_projection(q, og, th=th, slot=b)
+        mo, no = o.search_by_projection(q, oo, th=th, slot=b)
+        assert ng == no and np.array_equal(mg, mo) and np.array_equal(og, oo)
+        assert no > 300
+    with pytest.raises(plf.PlfError):
+        plf.Frontend(product, max_batch=1).search_by_projection(q[:4], np.zeros(10, np.uint8))     # before extraction

@@ -271,3 +271,105 @@ def test_bow_oracle_against_python(plf, oracle, which, levelsup):
     assert fvec == fv and abs(bv.sum() - 1.0) < 1e-12 and len(bw) > 50
     if voc["levels"] - levelsup <= 0:
         assert set(fvec) == {0}
+
+
+def _proj_queries(plf, res, b, rng, n_extra=150):
+    """Map points as SearchByProjection sees them: every left keypoint of frame b re-observed with a small projection
+    error, a possibly different predicted level and a few flipped descriptor bits, plus some unrelated points; shuffled."""
+    n = int(res.n_kp_left[b])
+    kps, desc, ur = res.kp_left[b, :n], res.desc_left[b, :n], res.u_right[b, :n]
+    m = n + n_extra
+    q = np.zeros(m, plf.PROJ_QUERY_DT)
+    src = np.concatenate([np.arange(n), rng.integers(0, n, n_extra)])
+    q["proj_x"] = kps["x"][src] + rng.normal(0, 1.5, m).astype(np.float32)
+    q["proj_y"] = kps["y"][src] + rng.normal(0, 1.5, m).astype(np.float32)
+    q["proj_xr"] = np.where(ur[src] > 0, ur[src] + rng.normal(0, 1.0, m), -1).astype(np.float32)
+    q["view_cos"] = rng.choice(np.array([0.9995, 0.99, 0.7], np.float32), m)
+    q["level"] = np.clip(kps["octave"][src] + rng.integers(-1, 2, m), 0, 7)
+    q["skip"] = (rng.random(m) < 0.05).astype(np.int32)
+    d = desc[src].copy()
+    flips = rng.random((m, 256)) < 0.04
+    d ^= np.packbits(flips, axis=1)
+    d[n:] = rng.integers(0, 256, (n_extra, 32), dtype=np.uint8)
+    q["desc"] = d
+    q["proj_x"][n:] = rng.uniform(-20, 780, n_extra); q["proj_y"][n:] = rng.uniform(-20, 500, n_extra)
+    return q[rng.permutation(m)]
+
+
+def _search_by_projection_python(q, kps, desc, ur, scale, occupied, th, nn_ratio, th_high, W=752, H=480):
+    """ORBmatcher::SearchByProjection(F, vpMapPoints, th) restated loop for loop (src/ORBmatcher.cc:44-130, Nleft == -1)."""
+    import math
+    f32 = np.float32
+    invw, invh = f32(64) / f32(W), f32(48) / f32(H)
+
+    def rnd(v):
+        return int(math.floor(abs(v) + 0.5)) * (1 if v >= 0 else -1)
+    grid = {}
+    for i in range(len(kps)):
+        px, py = rnd(float(f32(kps["x"][i]) * invw)), rnd(float(f32(kps["y"][i]) * invh))
+        if 0 <= px < 64 and 0 <= py < 48:
+            grid.setdefault(px * 48 + py, []).append(i)
+    bits = np.unpackbits(desc, axis=1)
+    match = np.full(len(q), -1, np.int32)
+    nm = 0
+    for i, qq in enumerate(q):
+        if qq["skip"]:
+            continue
+        r = f32(2.5) if qq["view_cos"] > f32(0.998) else f32(4.0)
+        if th != 1.0:
+            r = f32(r * f32(th))
+        rad = f32(r * scale[qq["level"]])
+        lo, hi = qq["level"] - 1, qq["level"]
+        x, y = f32(qq["proj_x"]), f32(qq["proj_y"])
+        x0 = max(0, math.floor(float(f32(f32(x - rad) * invw)))); x1 = min(63, math.ceil(float(f32(f32(x + rad) * invw))))
+        y0 = max(0, math.floor(float(f32(f32(y - rad) * invh)))); y1 = min(47, math.ceil(float(f32(f32(y + rad) * invh))))
+        if not (x0 < 64 and x1 >= 0 and y0 < 48 and y1 >= 0):
+            continue
+        qb = np.unpackbits(qq["desc"])
+        best, bl, best2, bl2, bidx = 256, -1, 256, -1, -1
+        for cx in range(x0, x1 + 1):
+            for cy in range(y0, y1 + 1):
+                for idx in grid.get(cx * 48 + cy, []):
+                    o = int(kps["octave"][idx])
+                    if o < lo or o > hi:
+                        continue
+                    if not (abs(f32(kps["x"][idx]) - x) < rad and abs(f32(kps["y"][idx]) - y) < rad):
+                        continue
+                    if occupied[idx]:
+                        continue
+                    if ur[idx] > 0 and abs(f32(qq["proj_xr"]) - f32(ur[idx])) > rad:
+                        continue
+                    dist = int((bits[idx] ^ qb).sum())
+                    if dist < best:
+                        best2, best, bl2, bl, bidx = best, dist, bl, o, idx
+                    elif dist < best2:
+                        bl2, best2 = o, dist
+        if best <= th_high:
+            if bl == bl2 and f32(best) > f32(nn_ratio) * f32(best2):
+                continue
+            match[i] = bidx
+            occupied[bidx] = 1
+            nm += 1
+    return match, nm
+
+
+@pytest.mark.parametrize("th", [1.0, 3.0])
+def test_search_by_projection_oracle_against_python(plf, oracle, th):
+    """The oracle's SearchByProjection against the direct Python restatement, including pre-occupied features and the
+    order dependence (a feature taken by an earlier map point is skipped by the later ones)."""
+    L, R = plf.synth_pair(752, 480, 8)
+    o = plf.Frontend(oracle, max_batch=1)
+    res = o.frontend_batch(L[None], R[None])
+    n = int(res.n_kp_left[0])
+    rng = np.random.default_rng(11)
+    q = _proj_queries(plf, res, 0, rng, 60)[:500]
+    scale = o.scale_tables()[0] if hasattr(o, "scale_tables") else np.float32(1.2) ** np.arange(8, dtype=np.float32)
+    occ0 = (rng.random(n) < 0.1).astype(np.uint8)
+    occ_a, occ_b = occ0.copy(), occ0.copy()
+    got, nm = o.search_by_projection(q, occ_a, th=th)
+    sc = np.ones(8, np.float32)
+    for i in range(1, 8):
+        sc[i] = np.float32(sc[i - 1] * np.float32(1.2))
+    want, nm2 = _search_by_projection_python(q, res.kp_left[0, :n], res.desc_left[0, :n], res.u_right[0, :n], sc, occ_b, th, 0.8, 100)
+    assert nm == nm2 and np.array_equal(got, want) and np.array_equal(occ_a, occ_b)
+    assert nm > 100 and len(np.unique(got[got >= 0])) == nm          # a feature is given to one map point only

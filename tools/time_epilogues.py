@@ -29,6 +29,15 @@ timed("feature_grid", lambda: f.feature_grid(0, B))
 timed("backproject (points + lines)", lambda: f.backproject(Rwc, Ow, 435.2, 367.4, 252.2))
 timed("bow_transform ORB (k=10, L=6)", lambda: f.bow_transform(0, B, 0, 4))
 timed("bow_transform lines (k=10, L=5)", lambda: f.bow_transform(1, B, 0, 4))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from test_host_logic import _proj_queries
+q = _proj_queries(plf, out, 0, np.random.default_rng(1))
+occ = np.zeros(int(out.n_kp_left[0]), np.uint8)
+t = time.perf_counter()
+for _ in range(20):
+    occ[:] = 0
+    m, nm = f.search_by_projection(q, occ, th=1.0, slot=0)
+print("%-34s %8.2f ms per frame (%d map points, %d matches)" % ("search_by_projection th=1", (time.perf_counter() - t) / 20 * 1e3, len(q), nm))
 f.set_stage_timing(True)
 f.batch_upload_raw(L[idx], R[idx]); f.batch_run(B); f.batch_download(B, out)
 print("rectify kernel stage: %.2f ms per %d-pair batch" % (f.stage_ms().get("rectify", float("nan")), B))

@@ -1,0 +1,44 @@
+"""Exact comparison of the CUDA path with the CPU oracle over many synthetic pairs (GPU box; the oracle is the checker).
+
+  python tools/parity_sweep.py [n_pairs] [first_seed] [kind]     kind: rect (default) | curvy
+Prints, per output array, the number of pairs on which it differs from the oracle."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, plf
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+S0 = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
+KIND = sys.argv[3] if len(sys.argv) > 3 else "rect"
+W, H, B = 752, 480, 64
+f = plf.Frontend(plf.load_product(), max_batch=B, lsd_nfeatures=0)
+o = plf.Frontend(plf.load_oracle(), max_batch=B, lsd_nfeatures=0)
+fields = [("kp_left", "n_kp_left"), ("desc_left", "n_kp_left"), ("kp_right", "n_kp_right"), ("desc_right", "n_kp_right"),
+          ("kl_left", "n_kl_left"), ("ldesc_left", "n_kl_left"), ("kl_right", "n_kl_right"), ("ldesc_right", "n_kl_right"),
+          ("u_right", "n_kp_left"), ("depth", "n_kp_left"), ("disp_se", "n_kl_left"), ("line_match12", "n_kl_left")]
+bad = {k: 0 for k, _ in fields}
+bad.update(n_kp_left=0, n_kp_right=0, n_kl_left=0, n_kl_right=0)
+bad_pairs = set()
+tg = to = 0.0
+nkp = nkl = 0
+for c0 in range(0, N, B):
+    seeds = list(range(S0 + c0, S0 + min(c0 + B, N)))
+    if KIND == "curvy":
+        L = np.stack([plf.synth_curvy(W, H, s) for s in seeds])
+        rng = np.random.default_rng(S0 + c0)
+        R = np.clip(np.roll(L, -14, axis=2).astype(np.int16) + rng.integers(-2, 3, L.shape), 0, 255).astype(np.uint8)
+    else:
+        L, R = plf.synth_batch(W, H, seeds)
+    t = time.time(); rg = f.frontend_batch(L, R); tg += time.time() - t
+    t = time.time(); ro = o.frontend_batch(L, R); to += time.time() - t
+    for b in range(len(seeds)):
+        for cnt in ("n_kp_left", "n_kp_right", "n_kl_left", "n_kl_right"):
+            if int(getattr(rg, cnt)[b]) != int(getattr(ro, cnt)[b]):
+                bad[cnt] += 1; bad_pairs.add(seeds[b])
+        for name, cnt in fields:
+            n = int(getattr(ro, cnt)[b])
+            if not np.array_equal(getattr(rg, name)[b, :n], getattr(ro, name)[b, :n]):
+                bad[name] += 1; bad_pairs.add(seeds[b])
+        nkp += int(ro.n_kp_left[b]) + int(ro.n_kp_right[b]); nkl += int(ro.n_kl_left[b]) + int(ro.n_kl_right[b])
+print("%d pairs (%s, seeds %d..%d): %d keypoints, %d lines compared; GPU %.1f s, oracle %.1f s" % (N, KIND, S0, S0 + N - 1, nkp, nkl, tg, to))
+print("pairs with any difference:", len(bad_pairs), sorted(bad_pairs)[:20])
+print({k: v for k, v in bad.items() if v})

@@ -1,6 +1,6 @@
 """Exact comparison of the CUDA path with the CPU oracle over many synthetic pairs (GPU box; the oracle is the checker).
 
-  python tools/parity_sweep.py [n_pairs] [first_seed] [kind]     kind: rect (default) | curvy
+  python tools/parity_sweep.py [n_pairs] [first_seed] [kind] [lsd_refine] [W] [H]     kind: rect (default) | curvy
 Prints, per output array, the number of pairs on which it differs from the oracle."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,9 +9,13 @@ import numpy as np, plf
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 S0 = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
 KIND = sys.argv[3] if len(sys.argv) > 3 else "rect"
-W, H, B = 752, 480, 64
-f = plf.Frontend(plf.load_product(), max_batch=B, lsd_nfeatures=0)
-o = plf.Frontend(plf.load_oracle(), max_batch=B, lsd_nfeatures=0)
+REFINE = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+W = int(sys.argv[5]) if len(sys.argv) > 5 else 752
+H = int(sys.argv[6]) if len(sys.argv) > 6 else 480
+B = 64
+kw = dict(width=W, height=H, max_batch=B, lsd_nfeatures=0, lsd_refine=REFINE)
+f = plf.Frontend(plf.load_product(), **kw)
+o = plf.Frontend(plf.load_oracle(), **kw)
 fields = [("kp_left", "n_kp_left"), ("desc_left", "n_kp_left"), ("kp_right", "n_kp_right"), ("desc_right", "n_kp_right"),
           ("kl_left", "n_kl_left"), ("ldesc_left", "n_kl_left"), ("kl_right", "n_kl_right"), ("ldesc_right", "n_kl_right"),
           ("u_right", "n_kp_left"), ("depth", "n_kp_left"), ("disp_se", "n_kl_left"), ("line_match12", "n_kl_left")]
@@ -39,6 +43,7 @@ for c0 in range(0, N, B):
             if not np.array_equal(getattr(rg, name)[b, :n], getattr(ro, name)[b, :n]):
                 bad[name] += 1; bad_pairs.add(seeds[b])
         nkp += int(ro.n_kp_left[b]) + int(ro.n_kp_right[b]); nkl += int(ro.n_kl_left[b]) + int(ro.n_kl_right[b])
+print("%dx%d refine %d: " % (W, H, REFINE), end="")
 print("%d pairs (%s, seeds %d..%d): %d keypoints, %d lines compared; GPU %.1f s, oracle %.1f s" % (N, KIND, S0, S0 + N - 1, nkp, nkl, tg, to))
 print("pairs with any difference:", len(bad_pairs), sorted(bad_pairs)[:20])
 print({k: v for k, v in bad.items() if v})

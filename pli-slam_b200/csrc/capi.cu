@@ -15,7 +15,8 @@ int plf_set_cuda_error(cudaError_t e, const char* what, const char* file, int li
     cudaGetLastError();          // reported: do not let a non-sticky error (e.g. out of memory) poison the next call's check
     return PLF_ERR_CUDA;
 }
-static int fail(int code, const char* msg) { g_err = msg; return code; }
+int plf_fail(int code, const char* msg) { g_err = msg; return code; }
+static int fail(int code, const char* msg) { return plf_fail(code, msg); }
 
 #define PLF_MAX_MARKS 48
 void plf_mark(plf_ctx* c, const char* name) {
@@ -23,13 +24,6 @@ void plf_mark(plf_ctx* c, const char* name) {
     cudaEventRecord(c->ev[c->nMarks], c->stream);
     c->markNames[c->nMarks] = name;
     c->nMarks++;
-}
-
-template <typename T>
-static cudaError_t dalloc(T** p, size_t n) {
-    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
-    if (e == cudaSuccess) e = cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T));
-    return e;
 }
 
 extern "C" {
@@ -656,283 +650,6 @@ PLF_API int plf_batch_upload(plf_ctx* c, const uint8_t* left, const uint8_t* rig
     PLF_CUDA_OK(cudaMemcpyAsync(c->d_stage, left, sideBytes, cudaMemcpyHostToDevice, c->stream));
     PLF_CUDA_OK(cudaMemcpyAsync(c->d_stage + sideBytes, right, sideBytes, cudaMemcpyHostToDevice, c->stream));
     plf_launch_unpack(c, c->d_stage, sideBytes, stride, batch);
-    c->batchResident = batch;
-    return PLF_OK;
-}
-
-// ---- Frame::AssignFeaturesToGrid (first half) ---------------------------------------------------------
-PLF_API int plf_feature_grid(plf_ctx* c, int first_slot, int n_slots, int32_t* cell_start, int32_t* cell_idx, int idx_stride) {
-    if (!c || !cell_start || !cell_idx || first_slot < 0 || n_slots < 1 || first_slot + n_slots > c->p.max_batch ||
-        idx_stride < c->g.kpCap)
-        return fail(PLF_ERR_INVALID, "bad slot range / idx_stride smaller than plf_keypoint_capacity");
-    if (!c->orbValid[0]) return fail(PLF_ERR_STATE, "feature_grid before the left keypoints were extracted");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
-    constexpr int NC1 = PLF_GRID_COLS * PLF_GRID_ROWS + 1;
-    if (!c->d_gridStart) {
-        PLF_CUDA_OK(dalloc(&c->d_gridStart, (size_t)c->p.max_batch * NC1));
-        PLF_CUDA_OK(dalloc(&c->d_gridIdx, (size_t)c->p.max_batch * c->g.kpCap));
-    }
-    plf_launch_feature_grid(c, first_slot, n_slots, c->d_gridStart, c->d_gridIdx);
-    PLF_CUDA_OK(cudaMemcpyAsync(cell_start, c->d_gridStart, (size_t)n_slots * NC1 * 4, cudaMemcpyDeviceToHost, c->stream));
-    PLF_CUDA_OK(cudaMemcpy2DAsync(cell_idx, (size_t)idx_stride * 4, c->d_gridIdx, (size_t)c->g.kpCap * 4, (size_t)c->g.kpCap * 4,
-                                  n_slots, cudaMemcpyDeviceToHost, c->stream));
-    PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
-    PLF_CUDA_OK(cudaGetLastError());
-    return PLF_OK;
-}
-
-PLF_API int plf_get_features_in_area(const plf_keypoint* kps, const int32_t* cell_start, const int32_t* cell_idx, int width,
-                                     int height, float x, float y, float r, int min_level, int max_level, int32_t* out, int cap) {
-    return plf_features_in_area(kps, cell_start, cell_idx, width, height, x, y, r, min_level, max_level, out, cap);
-}
-
-// ---- projection-window search (second half) ----------------------------------------------------------
-PLF_API int plf_search_by_projection(plf_ctx* c, int slot, const plf_proj_query* queries, int n_queries, float th, float nn_ratio,
-                                     int th_high, uint8_t* occupied, int32_t* match, int* n_matches) {
-    if (!c || slot < 0 || slot >= c->p.max_batch || !queries || n_queries < 0 || !occupied || !match)
-        return fail(PLF_ERR_INVALID, "bad arguments");
-    if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "search_by_projection before the frame was extracted and stereo-matched");
-    if (n_matches) *n_matches = 0;
-    if (n_queries == 0) return PLF_OK;
-    PLF_CUDA_OK(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
-    constexpr int NC1 = PLF_GRID_COLS * PLF_GRID_ROWS + 1;
-    if (!c->d_gridStart) {
-        PLF_CUDA_OK(dalloc(&c->d_gridStart, (size_t)c->p.max_batch * NC1));
-        PLF_CUDA_OK(dalloc(&c->d_gridIdx, (size_t)c->p.max_batch * c->g.kpCap));
-    }
-    if (c->projQCap < (size_t)n_queries) {
-        PLF_CUDA_OK(cudaStreamSynchronize(s));
-        if (c->d_projQ) { cudaFree(c->d_projQ); cudaFree(c->d_projCount); cudaFree(c->d_projStart); }
-        c->d_projQ = nullptr; c->d_projCount = nullptr; c->d_projStart = nullptr; c->projQCap = 0;
-        PLF_CUDA_OK(dalloc(&c->d_projQ, (size_t)n_queries));
-        PLF_CUDA_OK(dalloc(&c->d_projCount, (size_t)n_queries));
-        PLF_CUDA_OK(dalloc(&c->d_projStart, (size_t)n_queries));
-        c->projQCap = n_queries;
-    }
-    // Frame::AssignFeaturesToGrid for this slot (slot-local CSR at the start of the grid buffers)
-    plf_launch_feature_grid(c, slot, 1, c->d_gridStart, c->d_gridIdx);
-    PLF_CUDA_OK(cudaMemcpyAsync(c->d_projQ, queries, (size_t)n_queries * sizeof(plf_proj_query), cudaMemcpyHostToDevice, s));
-    plf_launch_proj_candidates(c, slot, c->d_projQ, n_queries, th, c->d_gridStart, c->d_gridIdx, c->d_projCount, nullptr, nullptr, false);
-    std::vector<int> cnt(n_queries), start(n_queries + 1, 0);
-    PLF_CUDA_OK(cudaMemcpyAsync(cnt.data(), c->d_projCount, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, s));
-    PLF_CUDA_OK(cudaStreamSynchronize(s));
-    for (int i = 0; i < n_queries; ++i) start[i + 1] = start[i] + cnt[i];
-    const size_t total = (size_t)start[n_queries];
-    std::vector<int2> pool(total);
-    if (total) {
-        if (c->projPoolCap < total) {
-            if (c->d_projPool) cudaFree(c->d_projPool);
-            c->d_projPool = nullptr; c->projPoolCap = 0;
-            PLF_CUDA_OK(dalloc(&c->d_projPool, total * 2));
-            c->projPoolCap = total * 2;
-        }
-        PLF_CUDA_OK(cudaMemcpyAsync(c->d_projStart, start.data(), (size_t)n_queries * 4, cudaMemcpyHostToDevice, s));
-        plf_launch_proj_candidates(c, slot, c->d_projQ, n_queries, th, c->d_gridStart, c->d_gridIdx, c->d_projCount, c->d_projStart,
-                                   c->d_projPool, true);
-        PLF_CUDA_OK(cudaMemcpyAsync(pool.data(), c->d_projPool, total * sizeof(int2), cudaMemcpyDeviceToHost, s));
-        PLF_CUDA_OK(cudaStreamSynchronize(s));
-    }
-    PLF_CUDA_OK(cudaGetLastError());
-    // the order-dependent half, in query order (src/ORBmatcher.cc:84-129)
-    int nm = 0;
-    for (int i = 0; i < n_queries; ++i) {
-        match[i] = -1;
-        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
-        for (int j = start[i]; j < start[i + 1]; ++j) {
-            const int idx = pool[j].x, dist = pool[j].y & 0xFFFF, oct = pool[j].y >> 16;
-            if (occupied[idx]) continue;
-            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = oct; bestIdx = idx; }
-            else if (dist < bestDist2) { bestLevel2 = oct; bestDist2 = dist; }
-        }
-        if (bestDist <= th_high) {
-            if (bestLevel == bestLevel2 && (float)bestDist > nn_ratio * (float)bestDist2) continue;
-            if (bestLevel != bestLevel2 || (float)bestDist <= nn_ratio * (float)bestDist2) {
-                match[i] = bestIdx;
-                occupied[bestIdx] = 1;
-                ++nm;
-            }
-        }
-    }
-    if (n_matches) *n_matches = nm;
-    return PLF_OK;
-}
-
-// ---- bag-of-words transform -------------------------------------------------------------------------
-PLF_API int plf_bow_set_vocabulary(plf_ctx* c, int which, int n_nodes, int levels, const int32_t* child_first,
-                                   const int32_t* child_count, const int32_t* child, const uint8_t* desc, const int32_t* word_id,
-                                   const double* weight) {
-    if (!c || which < 0 || which > 1 || n_nodes < 2 || levels < 1 || !child_first || !child_count || !child || !desc || !word_id || !weight)
-        return fail(PLF_ERR_INVALID, "bad vocabulary");
-    // structural check on the host: children in range, every node but the root referenced once, depth <= levels
-    long long total = 0;
-    for (int i = 0; i < n_nodes; ++i) {
-        if (child_count[i] < 0 || child_first[i] < 0) return fail(PLF_ERR_INVALID, "bad vocabulary (child range)");
-        total += child_count[i];
-    }
-    if (total != n_nodes - 1 || child_count[0] == 0) return fail(PLF_ERR_INVALID, "bad vocabulary (not a tree rooted at node 0)");
-    for (int i = 0; i < n_nodes; ++i)
-        for (int k = 0; k < child_count[i]; ++k) {
-            if ((long long)child_first[i] + k >= total) return fail(PLF_ERR_INVALID, "bad vocabulary (child index)");
-            const int id = child[child_first[i] + k];
-            if (id <= 0 || id >= n_nodes) return fail(PLF_ERR_INVALID, "bad vocabulary (child id)");
-        }
-    {   // depth of every root-to-leaf path (also rejects cycles: a walk longer than `levels` fails)
-        std::vector<int> depth(n_nodes, -1), stack;
-        depth[0] = 0; stack.push_back(0);
-        while (!stack.empty()) {
-            const int i = stack.back(); stack.pop_back();
-            for (int k = 0; k < child_count[i]; ++k) {
-                const int id = child[child_first[i] + k];
-                if (depth[id] >= 0 || depth[i] + 1 > levels) return fail(PLF_ERR_INVALID, "bad vocabulary (cycle or deeper than levels)");
-                depth[id] = depth[i] + 1;
-                stack.push_back(id);
-            }
-        }
-    }
-    PLF_CUDA_OK(cudaSetDevice(c->device));
-    PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
-    PlfVocab& v = c->voc[which];
-    void* old[] = {v.childFirst, v.childCount, v.child, v.word, v.desc, v.weight};
-    for (void* q : old) if (q) cudaFree(q);
-    v = PlfVocab();
-    PLF_CUDA_OK(dalloc(&v.childFirst, (size_t)n_nodes));
-    PLF_CUDA_OK(dalloc(&v.childCount, (size_t)n_nodes));
-    PLF_CUDA_OK(dalloc(&v.child, (size_t)n_nodes));
-    PLF_CUDA_OK(dalloc(&v.word, (size_t)n_nodes));
-    PLF_CUDA_OK(dalloc(&v.desc, (size_t)n_nodes * 32));
-    PLF_CUDA_OK(dalloc(&v.weight, (size_t)n_nodes));
-    PLF_CUDA_OK(cudaMemcpy(v.childFirst, child_first, (size_t)n_nodes * 4, cudaMemcpyHostToDevice));
-    PLF_CUDA_OK(cudaMemcpy(v.childCount, child_count, (size_t)n_nodes * 4, cudaMemcpyHostToDevice));
-    PLF_CUDA_OK(cudaMemcpy(v.child, child, (size_t)(n_nodes - 1) * 4, cudaMemcpyHostToDevice));
-    PLF_CUDA_OK(cudaMemcpy(v.word, word_id, (size_t)n_nodes * 4, cudaMemcpyHostToDevice));
-    PLF_CUDA_OK(cudaMemcpy(v.desc, desc, (size_t)n_nodes * 32, cudaMemcpyHostToDevice));
-    PLF_CUDA_OK(cudaMemcpy(v.weight, weight, (size_t)n_nodes * 8, cudaMemcpyHostToDevice));
-    v.nNodes = n_nodes; v.levels = levels;
-    return PLF_OK;
-}
-
-PLF_API int plf_bow_transform(plf_ctx* c, int which, int first_slot, int n_slots, int levelsup, int32_t* word_id, double* weight,
-                              int32_t* node_id, int stride) {
-    if (!c || which < 0 || which > 1 || !word_id || !weight || !node_id || first_slot < 0 || n_slots < 1 ||
-        first_slot + n_slots > c->p.max_batch || stride < 1 || stride > (which ? c->g.klCap : c->g.kpCap))
-        return fail(PLF_ERR_INVALID, "bad slot range / stride beyond the descriptor capacity");
-    if (!c->voc[which].nNodes) return fail(PLF_ERR_STATE, "bow_transform before bow_set_vocabulary");
-    if (which ? !(c->p.has_lines && c->lineValid[0]) : !c->orbValid[0]) return fail(PLF_ERR_STATE, "bow_transform before the descriptors exist");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
-    const size_t cap = (size_t)std::max(c->g.kpCap, c->g.klCap);
-    if (!c->d_bowWord) {
-        PLF_CUDA_OK(dalloc(&c->d_bowWord, (size_t)c->p.max_batch * cap));
-        PLF_CUDA_OK(dalloc(&c->d_bowNode, (size_t)c->p.max_batch * cap));
-        PLF_CUDA_OK(dalloc(&c->d_bowWeight, (size_t)c->p.max_batch * cap));
-    }
-    plf_launch_bow(c, which, first_slot, n_slots, levelsup, c->d_bowWord, c->d_bowWeight, c->d_bowNode, stride);
-    cudaStream_t s = c->stream;
-    PLF_CUDA_OK(cudaMemcpyAsync(word_id, c->d_bowWord, (size_t)n_slots * stride * 4, cudaMemcpyDeviceToHost, s));
-    PLF_CUDA_OK(cudaMemcpyAsync(weight, c->d_bowWeight, (size_t)n_slots * stride * 8, cudaMemcpyDeviceToHost, s));
-    PLF_CUDA_OK(cudaMemcpyAsync(node_id, c->d_bowNode, (size_t)n_slots * stride * 4, cudaMemcpyDeviceToHost, s));
-    PLF_CUDA_OK(cudaStreamSynchronize(s));
-    PLF_CUDA_OK(cudaGetLastError());
-    return PLF_OK;
-}
-
-PLF_API int plf_bow_build_vectors(const int32_t* word_id, const double* weight, const int32_t* node_id, int n, int32_t* bow_word,
-                                  double* bow_value, int32_t* fv_node, int32_t* fv_start, int32_t* fv_feat, int* n_nodes_out) {
-    return plf_bow_build(word_id, weight, node_id, n, bow_word, bow_value, fv_node, fv_start, fv_feat, n_nodes_out);
-}
-
-// ---- landmark back-projection -------------------------------------------------------------------------
-PLF_API int plf_backproject(plf_ctx* c, int first_slot, int n_slots, const float* Rwc, const float* Ow, float fy, float cx,
-                            float cy, float* x3d, int x3d_rows, double* l3d, int l3d_rows) {
-    if (!c || !Rwc || !Ow || first_slot < 0 || n_slots < 1 || first_slot + n_slots > c->p.max_batch || (!x3d && !l3d) ||
-        (x3d && (x3d_rows < 1 || x3d_rows > c->g.kpCap)) || (l3d && (l3d_rows < 1 || l3d_rows > c->g.klCap)) || !(fy > 0))
-        return fail(PLF_ERR_INVALID, "bad slot range / rows beyond the keypoint or keyline capacity");
-    if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "backproject before the stereo matches exist");
-    if (l3d && !c->p.has_lines) return fail(PLF_ERR_STATE, "line back-projection on a context without lines");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
-    if (!c->d_bpPose) {
-        PLF_CUDA_OK(dalloc(&c->d_bpPose, (size_t)c->p.max_batch * 12));
-        PLF_CUDA_OK(dalloc(&c->d_bpX, (size_t)c->p.max_batch * c->g.kpCap * 3));
-        PLF_CUDA_OK(dalloc(&c->d_bpL, (size_t)c->p.max_batch * c->g.klCap * 6));
-    }
-    cudaStream_t s = c->stream;
-    PLF_CUDA_OK(cudaMemcpyAsync(c->d_bpPose, Rwc, (size_t)n_slots * 36, cudaMemcpyHostToDevice, s));
-    PLF_CUDA_OK(cudaMemcpyAsync(c->d_bpPose + (size_t)c->p.max_batch * 9, Ow, (size_t)n_slots * 12, cudaMemcpyHostToDevice, s));
-    plf_launch_backproject(c, first_slot, n_slots, c->d_bpPose, c->d_bpPose + (size_t)c->p.max_batch * 9, fy, cx, cy,
-                           x3d ? c->d_bpX : nullptr, x3d_rows, l3d ? c->d_bpL : nullptr, l3d_rows);
-    if (x3d) PLF_CUDA_OK(cudaMemcpyAsync(x3d, c->d_bpX, (size_t)n_slots * x3d_rows * 12, cudaMemcpyDeviceToHost, s));
-    if (l3d) PLF_CUDA_OK(cudaMemcpyAsync(l3d, c->d_bpL, (size_t)n_slots * l3d_rows * 48, cudaMemcpyDeviceToHost, s));
-    PLF_CUDA_OK(cudaStreamSynchronize(s));
-    PLF_CUDA_OK(cudaGetLastError());
-    return PLF_OK;
-}
-
-// ---- rectification: cv::remap in front of the path ------------------------------------------------
-static cudaError_t stage_reserve(plf_ctx* c, size_t bytes) {
-    if (c->stageCap >= bytes) return cudaSuccess;
-    if (c->d_stage) { cudaStreamSynchronize(c->stream); cudaFree(c->d_stage); }
-    c->d_stage = nullptr;
-    c->stageCap = 0;
-    cudaError_t e = cudaMalloc((void**)&c->d_stage, bytes);
-    if (e == cudaSuccess) c->stageCap = bytes;
-    return e;
-}
-
-PLF_API int plf_rectify_set_maps(plf_ctx* c, int side, const float* mx, const float* my, int src_w, int src_h) {
-    if (!c || side < 0 || side > 1 || !mx || !my || src_w < 2 || src_h < 2 || src_w > 32767 || src_h > 32767)
-        return fail(PLF_ERR_INVALID, "bad rectification maps");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
-    const size_t n = (size_t)c->g.W * c->g.H;
-    // cv::remap's own conversion of the float maps: cvRound(map * 32) (round half to even), integer part saturated
-    // to int16, 5-bit fractions; done once here instead of once per frame
-    std::vector<uint2> t(n);
-    auto sat16 = [](int v) { return v < -32768 ? -32768 : (v > 32767 ? 32767 : v); };
-    for (size_t i = 0; i < n; ++i) {
-        const int fxs = (int)std::nearbyintf(mx[i] * 32.f), fys = (int)std::nearbyintf(my[i] * 32.f);
-        const int sx = sat16(fxs >> 5), sy = sat16(fys >> 5);
-        t[i].x = (unsigned)(sx & 0xFFFF) | ((unsigned)(sy & 0xFFFF) << 16);
-        t[i].y = (unsigned)(((fys & 31) << 5) | (fxs & 31));
-    }
-    if (!c->d_rmap[side]) PLF_CUDA_OK(dalloc(&c->d_rmap[side], n));
-    PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
-    PLF_CUDA_OK(cudaMemcpy(c->d_rmap[side], t.data(), n * sizeof(uint2), cudaMemcpyHostToDevice));
-    c->srcW[side] = src_w; c->srcH[side] = src_h;
-    return PLF_OK;
-}
-
-PLF_API int plf_rectify(plf_ctx* c, int side, const uint8_t* raw, int raw_stride, uint8_t* out, int out_stride) {
-    if (!c || side < 0 || side > 1 || !raw || !out) return fail(PLF_ERR_INVALID, "bad arguments");
-    if (!c->d_rmap[side]) return fail(PLF_ERR_STATE, "rectify before rectify_set_maps");
-    if (raw_stride < c->srcW[side] || out_stride < c->g.W) return fail(PLF_ERR_INVALID, "bad stride");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
-    const size_t bytes = (size_t)c->srcH[side] * raw_stride;
-    PLF_CUDA_OK(stage_reserve(c, bytes));
-    PLF_CUDA_OK(cudaMemcpyAsync(c->d_stage, raw, bytes, cudaMemcpyHostToDevice, c->stream));
-    plf_launch_rectify(c, c->d_stage, c->d_stage, raw_stride, side, 1);      // slot 0, image index = side
-    c->orbValid[side] = c->lineValid[side] = false;                         // level 0 of slot 0 was overwritten
-    const PlfLevel& l0 = c->g.lv[0];
-    PLF_CUDA_OK(cudaMemcpy2DAsync(out, out_stride, c->d_pyr + (size_t)side * c->g.pyrBytes + l0.off, l0.pitch, c->g.W, c->g.H,
-                                  cudaMemcpyDeviceToHost, c->stream));
-    PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
-    PLF_CUDA_OK(cudaGetLastError());
-    return PLF_OK;
-}
-
-PLF_API int plf_batch_upload_raw(plf_ctx* c, const uint8_t* left, const uint8_t* right, int batch, int raw_stride) {
-    if (!c || !left || !right || batch < 1 || batch > c->p.max_batch) return fail(PLF_ERR_INVALID, "bad batch");
-    if (!c->d_rmap[0] || !c->d_rmap[1]) return fail(PLF_ERR_STATE, "batch_upload_raw before rectify_set_maps");
-    if (raw_stride < c->srcW[0] || raw_stride < c->srcW[1]) return fail(PLF_ERR_INVALID, "bad stride");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
-    c->nMarks = 0;
-    plf_mark(c, "h2d");
-    const size_t b0 = (size_t)batch * c->srcH[0] * raw_stride, b1 = (size_t)batch * c->srcH[1] * raw_stride;
-    const size_t off1 = (b0 + 255) & ~(size_t)255;
-    PLF_CUDA_OK(stage_reserve(c, (((size_t)c->p.max_batch * c->srcH[0] * raw_stride + 255) & ~(size_t)255) +
-                                     (size_t)c->p.max_batch * c->srcH[1] * raw_stride));
-    PLF_CUDA_OK(cudaMemcpyAsync(c->d_stage, left, b0, cudaMemcpyHostToDevice, c->stream));
-    PLF_CUDA_OK(cudaMemcpyAsync(c->d_stage + off1, right, b1, cudaMemcpyHostToDevice, c->stream));
-    plf_mark(c, "rectify");
-    plf_launch_rectify(c, c->d_stage, c->d_stage + off1, raw_stride, 0, 2 * batch);
     c->batchResident = batch;
     return PLF_OK;
 }

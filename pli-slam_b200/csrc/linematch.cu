@@ -241,139 +241,3 @@ int plf_launch_stereo_lines(plf_ctx* c, int slotFirst, int nSlots) {
     return n;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Bag-of-words descent (DBoW2 TemplatedVocabulary::transform(feature, id, weight, nid, levelsup),
-// Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1230-1270): thread per descriptor; at every level the child with the
-// smallest Hamming distance is taken (strict <: the first child wins ties).  The tree is read-only and small next to
-// the frame data (ORBvoc: ~1.1 M nodes x 32 B), the features of a frame walk it independently.
-namespace {
-__global__ void __launch_bounds__(256) bow_kernel(const uint8_t* desc, const int* nFeat, int cap, int imgStride, const int* childFirst,
-                                                  const int* childCount, const int* child, const uint8_t* nodeDesc,
-                                                  const int* nodeWord, const double* nodeWeight, int levels, int levelsup,
-                                                  int* outWord, double* outWeight, int* outNode, int rows, int slotFirst) {
-    const int s = blockIdx.y, img = (slotFirst + s) * imgStride;
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= rows) return;
-    const size_t o = (size_t)s * rows + i;
-    if (i >= nFeat[img]) { outWord[o] = -1; outWeight[o] = 0.0; outNode[o] = 0; return; }
-    const uint4* f4 = reinterpret_cast<const uint4*>(desc + ((size_t)img * cap + i) * 32);
-    const uint4 a = f4[0], b = f4[1];
-    const int nidLevel = levels - levelsup;
-    int node = 0, level = 0, nid = 0;
-    do {
-        ++level;
-        const int c0 = childFirst[node], nc = childCount[node];
-        int best = 0x7fffffff, bestId = node;
-        for (int k = 0; k < nc; ++k) {
-            const int id = child[c0 + k];
-            const uint4* n4 = reinterpret_cast<const uint4*>(nodeDesc + (size_t)id * 32);
-            const uint4 p = n4[0], q = n4[1];
-            const int d = __popc(a.x ^ p.x) + __popc(a.y ^ p.y) + __popc(a.z ^ p.z) + __popc(a.w ^ p.w) +
-                          __popc(b.x ^ q.x) + __popc(b.y ^ q.y) + __popc(b.z ^ q.z) + __popc(b.w ^ q.w);
-            if (d < best) { best = d; bestId = id; }
-        }
-        node = bestId;
-        if (level == nidLevel) nid = node;
-    } while (childCount[node] > 0);
-    outWord[o] = nodeWord[node];
-    outWeight[o] = nodeWeight[node];
-    outNode[o] = nid;
-}
-}  // namespace
-
-int plf_launch_bow(plf_ctx* c, int which, int slotFirst, int nSlots, int levelsup, int* dWord, double* dWeight, int* dNode, int rows) {
-    const PlfGeom& g = c->g;
-    const PlfVocab& v = c->voc[which];
-    const uint8_t* desc = which ? c->d_ldesc : c->d_desc;
-    const int* nFeat = which ? c->d_nKl : c->d_nKp;
-    const int cap = which ? g.klCap : g.kpCap;
-    bow_kernel<<<dim3((rows + 255) / 256, nSlots), 256, 0, c->stream>>>(desc, nFeat, cap, 2, v.childFirst, v.childCount, v.child, v.desc,
-                                                                       v.word, v.weight, v.levels, levelsup, dWord, dWeight, dNode,
-                                                                       rows, slotFirst);
-    return 1;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:44-130), device half: a warp per
-// map point walks the grid cells of its window in GetFeaturesInArea order (src/Frame.cc:774-843: cell columns, cell rows,
-// insertion order), lanes take the features of a cell 32 at a time, apply the level, window and stereo filters and
-// compute the Hamming distances; survivors are compacted in order.  FILL = false only counts (the host sizes the
-// candidate pool from the counts), FILL = true writes (feature index, distance | octave << 16).
-namespace {
-template <bool FILL>
-__global__ void __launch_bounds__(256) proj_candidates_kernel(PlfGeom g, const plf_proj_query* qs, int nq, float th, const plf_keypoint* kp,
-                                                              const uint8_t* desc, const float* uRight, const int* cellStart,
-                                                              const int* cellIdx, int* count, const int* segStart, int2* pool) {
-    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (qi >= nq) return;
-    const plf_proj_query q = qs[qi];
-    int total = 0;
-    if (!q.skip && q.level >= 0 && q.level < g.nLevels) {
-        float r = q.view_cos > 0.998f ? 2.5f : 4.0f;
-        if (th != 1.0f) r = __fmul_rn(r, th);
-        const float rad = __fmul_rn(r, g.lv[q.level].scale);
-        const float invW = (float)PLF_GRID_COLS / ((float)g.W - 0.0f), invH = (float)PLF_GRID_ROWS / ((float)g.H - 0.0f);
-        int x0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.proj_x, 0.0f), rad), invW));
-        int x1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.proj_x, 0.0f), rad), invW));
-        int y0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.proj_y, 0.0f), rad), invH));
-        int y1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.proj_y, 0.0f), rad), invH));
-        x0 = max(x0, 0); y0 = max(y0, 0);
-        x1 = min(x1, PLF_GRID_COLS - 1); y1 = min(y1, PLF_GRID_ROWS - 1);
-        const bool window = x0 < PLF_GRID_COLS && x1 >= 0 && y0 < PLF_GRID_ROWS && y1 >= 0;
-        const int minLevel = q.level - 1, maxLevel = q.level;
-        const bool check = minLevel > 0 || maxLevel >= 0;
-        uint4 a = make_uint4(0, 0, 0, 0), b = a;
-        if (FILL) {
-            const unsigned* w = reinterpret_cast<const unsigned*>(qs[qi].desc);      // 56-byte structs: 4-byte aligned rows
-            a = make_uint4(w[0], w[1], w[2], w[3]);
-            b = make_uint4(w[4], w[5], w[6], w[7]);
-        }
-        const unsigned lt = (1u << lane) - 1u;
-        int2* out = FILL ? pool + segStart[qi] : nullptr;
-        if (window)
-            for (int ix = x0; ix <= x1; ++ix)
-                for (int iy = y0; iy <= y1; ++iy) {
-                    const int c = ix * PLF_GRID_ROWS + iy;
-                    const int j0 = cellStart[c], j1 = cellStart[c + 1];
-                    for (int jb = j0; jb < j1; jb += 32) {
-                        const int j = jb + lane;
-                        bool ok = false;
-                        int idx = -1, oct = 0;
-                        if (j < j1) {
-                            idx = cellIdx[j];
-                            const plf_keypoint k = kp[idx];
-                            oct = k.octave;
-                            ok = !(check && (oct < minLevel || (maxLevel >= 0 && oct > maxLevel)));
-                            ok = ok && fabsf(__fsub_rn(k.x, q.proj_x)) < rad && fabsf(__fsub_rn(k.y, q.proj_y)) < rad;
-                            if (ok) {
-                                const float ur = uRight[idx];
-                                if (ur > 0 && fabsf(__fsub_rn(q.proj_xr, ur)) > rad) ok = false;
-                            }
-                        }
-                        const unsigned m = __ballot_sync(0xffffffffu, ok);
-                        if (FILL && ok) {
-                            const uint4* f4 = reinterpret_cast<const uint4*>(desc + (size_t)idx * 32);
-                            const uint4 p = f4[0], s2 = f4[1];
-                            const int d = __popc(a.x ^ p.x) + __popc(a.y ^ p.y) + __popc(a.z ^ p.z) + __popc(a.w ^ p.w) +
-                                          __popc(b.x ^ s2.x) + __popc(b.y ^ s2.y) + __popc(b.z ^ s2.z) + __popc(b.w ^ s2.w);
-                            out[total + __popc(m & lt)] = make_int2(idx, d | (oct << 16));
-                        }
-                        total += __popc(m);
-                    }
-                }
-    }
-    if (!FILL && lane == 0) count[qi] = total;
-}
-}  // namespace
-
-int plf_launch_proj_candidates(plf_ctx* c, int slot, const plf_proj_query* dQ, int nq, float th, const int* dCellStart,
-                               const int* dCellIdx, int* dCount, const int* dSegStart, int2* dPool, bool fill) {
-    const PlfGeom& g = c->g;
-    const plf_keypoint* kp = c->d_kp + (size_t)(slot * 2) * g.kpCap;
-    const uint8_t* desc = c->d_desc + (size_t)(slot * 2) * g.kpCap * 32;
-    const float* ur = c->d_uRight + (size_t)slot * g.kpCap;
-    const dim3 grid((nq + 7) / 8);
-    if (fill) proj_candidates_kernel<true><<<grid, 256, 0, c->stream>>>(g, dQ, nq, th, kp, desc, ur, dCellStart, dCellIdx, dCount, dSegStart, dPool);
-    else proj_candidates_kernel<false><<<grid, 256, 0, c->stream>>>(g, dQ, nq, th, kp, desc, ur, dCellStart, dCellIdx, dCount, dSegStart, dPool);
-    return 1;
-}

@@ -766,58 +766,6 @@ __global__ void __launch_bounds__(64) unpack_kernel(PlfGeom g, const uint8_t* st
 }
 }  // namespace
 
-namespace {
-// cv::remap(raw, M1, M2, INTER_LINEAR), BORDER_CONSTANT 0, from the fixed-point table built by plf_rectify_set_maps,
-// written straight into level 0 of the pyramid block (4 output pixels per thread, one 32-bit store).  The 15-bit
-// weights are products of the two 5-bit fractions, 32 * (32 - fy | fy) * (32 - fx | fx); only the (0, 0) entry
-// saturates in OpenCV's table (32768 -> 32767) and its missing unit goes to the last tap: {32767, 0, 0, 1}.
-__global__ void __launch_bounds__(256) rectify_kernel(PlfGeom g, const uint8_t* raw0, const uint8_t* raw1, int rawStride,
-                                                      const uint2* map0, const uint2* map1, int sw0, int sh0, int sw1,
-                                                      int sh1, uint8_t* pyr, int imgFirst) {
-    const int x = blockIdx.x * 128 + threadIdx.x * 4, y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= g.W || y >= g.H) return;
-    const int img = imgFirst + blockIdx.z, side = img & 1, frame = blockIdx.z >> 1;
-    const int sw = side ? sw1 : sw0, sh = side ? sh1 : sh0;
-    const uint8_t* src = (side ? raw1 : raw0) + (size_t)frame * sh * rawStride;
-    const uint2* map = (side ? map1 : map0) + (size_t)y * g.W + x;
-    uint8_t* dst = pyr + (size_t)img * g.pyrBytes + g.lv[0].off + (size_t)y * g.lv[0].pitch + x;
-    const int nValid = min(4, g.W - x);
-    unsigned out = 0u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (j >= nValid) break;
-        const uint2 m = map[j];
-        const int sx = (short)(m.x & 0xFFFFu), sy = (short)(m.x >> 16);
-        const int fx = (int)(m.y & 31u), fy = (int)(m.y >> 5);
-        int w00 = 32 * (32 - fy) * (32 - fx), w01 = 32 * (32 - fy) * fx, w10 = 32 * fy * (32 - fx), w11 = 32 * fy * fx;
-        if (m.y == 0u) { w00 = 32767; w11 = 1; }
-        int p00, p01, p10, p11;
-        const uint8_t* r0 = src + (size_t)sy * rawStride + sx;
-        if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
-            p00 = r0[0]; p01 = r0[1]; p10 = r0[rawStride]; p11 = r0[rawStride + 1];
-        } else {      // a tap outside the source image counts as 0 (BORDER_CONSTANT)
-            const bool x0 = sx >= 0 && sx < sw, x1 = sx + 1 >= 0 && sx + 1 < sw;
-            const bool y0 = sy >= 0 && sy < sh, y1 = sy + 1 >= 0 && sy + 1 < sh;
-            p00 = (x0 && y0) ? r0[0] : 0;
-            p01 = (x1 && y0) ? r0[1] : 0;
-            p10 = (x0 && y1) ? r0[rawStride] : 0;
-            p11 = (x1 && y1) ? r0[rawStride + 1] : 0;
-        }
-        const int v = (p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + (1 << 14)) >> 15;     // <= 255 by construction
-        out |= (unsigned)v << (8 * j);
-    }
-    if (nValid == 4) *reinterpret_cast<unsigned*>(dst) = out;
-    else for (int j = 0; j < nValid; ++j) dst[j] = (uint8_t)(out >> (8 * j));
-}
-}  // namespace
-
-int plf_launch_rectify(plf_ctx* c, const uint8_t* raw0, const uint8_t* raw1, int rawStride, int imgFirst, int nImg) {
-    const PlfGeom& g = c->g;
-    rectify_kernel<<<dim3((g.W + 127) / 128, (g.H + 7) / 8, nImg), dim3(32, 8), 0, c->stream>>>(
-        g, raw0, raw1, rawStride, c->d_rmap[0], c->d_rmap[1], c->srcW[0], c->srcH[0], c->srcW[1], c->srcH[1], c->d_pyr, imgFirst);
-    return 1;
-}
-
 int plf_launch_unpack(plf_ctx* c, const uint8_t* stage, size_t sideBytes, int stride, int batch) {
     unpack_kernel<<<dim3(1, c->g.H, 2 * batch), 64, 0, c->stream>>>(c->g, stage, sideBytes, stride, c->d_pyr);
     return 1;

@@ -201,3 +201,12 @@ int plf_launch_match_nnr(plf_ctx* c, const uint8_t* dA, int nA, const uint8_t* d
         if (_e != cudaSuccess) return plf_set_cuda_error(_e, #expr, __FILE__, __LINE__);        \
     } while (0)
 int plf_set_cuda_error(cudaError_t e, const char* what, const char* file, int line);
+int plf_fail(int code, const char* msg);          // sets plf_last_error() and returns `code`
+
+// zero-initialised device allocation of n elements (at least one)
+template <typename T>
+static inline cudaError_t dalloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, (n > 0 ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, (n > 0 ? n : 1) * sizeof(T));
+    return e;
+}

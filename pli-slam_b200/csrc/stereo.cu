@@ -156,152 +156,6 @@ __global__ void __launch_bounds__(1024) stereo_cull_kernel(PlfGeom g, const int*
 
 }  // namespace
 
-namespace {
-// Frame::AssignFeaturesToGrid (src/Frame.cc:451-482) for the left keypoints of one slot per block: the 64 x 48 vectors
-// of keypoint indices become CSR (cell = x * 48 + y).  Histogram in shared memory, block scan, then one warp places the
-// indices in ascending order (lanes sharing a cell are ranked with __match_any_sync), which is the push_back order.
-__global__ void __launch_bounds__(256) feature_grid_kernel(PlfGeom g, const plf_keypoint* kp, const int* nKp, int* cellStart,
-                                                           int* cellIdx, float invW, float invH, int slotFirst) {
-    constexpr int NC = PLF_GRID_COLS * PLF_GRID_ROWS;
-    __shared__ int s_cnt[NC + 1];
-    __shared__ int s_part[256];
-    const int slot = slotFirst + blockIdx.x, img = slot * 2, tid = threadIdx.x;
-    const plf_keypoint* K = kp + (size_t)img * g.kpCap;
-    const int N = nKp[img];
-    int* outStart = cellStart + (size_t)blockIdx.x * (NC + 1);
-    int* outIdx = cellIdx + (size_t)blockIdx.x * g.kpCap;
-    auto cell_of = [&](int i) -> int {          // PosInGrid (src/Frame.cc:845-855): round() half away from zero
-        const int px = (int)roundf(__fmul_rn(__fsub_rn(K[i].x, 0.0f), invW)), py = (int)roundf(__fmul_rn(__fsub_rn(K[i].y, 0.0f), invH));
-        return (px < 0 || px >= PLF_GRID_COLS || py < 0 || py >= PLF_GRID_ROWS) ? -1 : px * PLF_GRID_ROWS + py;
-    };
-    for (int i = tid; i <= NC; i += 256) s_cnt[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < N; i += 256) {
-        const int c = cell_of(i);
-        if (c >= 0) atomicAdd(&s_cnt[c], 1);
-    }
-    __syncthreads();
-    // exclusive scan: 12 consecutive cells per thread, then the 256 partial sums
-    constexpr int PER = NC / 256;
-    int loc[PER], sum = 0;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) { loc[k] = sum; sum += s_cnt[tid * PER + k]; }
-    s_part[tid] = sum;
-    __syncthreads();
-    for (int o = 1; o < 256; o <<= 1) {
-        const int v = tid >= o ? s_part[tid - o] : 0;
-        __syncthreads();
-        s_part[tid] += v;
-        __syncthreads();
-    }
-    const int base = s_part[tid] - sum;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        s_cnt[tid * PER + k] = base + loc[k];              // becomes the write cursor of the cell
-        outStart[tid * PER + k] = base + loc[k];
-    }
-    if (tid == 255) outStart[NC] = s_part[255];
-    __syncthreads();
-    if (tid < 32) {
-        const unsigned lt = (1u << tid) - 1u;
-        for (int b = 0; b < N; b += 32) {
-            const int i = b + tid;
-            const int c = i < N ? cell_of(i) : -1;
-            const unsigned grp = __match_any_sync(0xffffffffu, c >= 0 ? c : -1 - tid);
-            int at = 0;
-            if (c >= 0) at = s_cnt[c];
-            __syncwarp();
-            if (c >= 0) {
-                if ((grp & lt) == 0u) s_cnt[c] = at + __popc(grp);
-                outIdx[at + __popc(grp & lt)] = i;
-            }
-            __syncwarp();
-        }
-    }
-}
-}  // namespace
-
-namespace {
-struct BackprojArgs { float fx, fy, cx, cy, invfx, invfy, mb; };
-// Frame::UnprojectStereo (src/Frame.cc:1332-1347) per left keypoint and Frame::backProjection (:1349-1358) per line end
-// point; thread per keypoint / per line, slot = blockIdx.y.  Every operation is written out (no FMA contraction).
-__global__ void __launch_bounds__(256) backproject_kernel(PlfGeom g, const plf_keypoint* kp, const int* nKp, const float* depth,
-                                                          const plf_keyline* kl, const int* nKl, const float* disp,
-                                                          const float* Rwc, const float* Ow, BackprojArgs a, float* x3d,
-                                                          int x3dRows, double* l3d, int l3dRows, int slotFirst) {
-    const int s = blockIdx.y, slot = slotFirst + s, img = slot * 2;
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    const float* R = Rwc + s * 9;
-    const float* O = Ow + s * 3;
-    if (x3d && i < x3dRows) {
-        float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-        if (i < nKp[img]) {
-            const float z = depth[(size_t)slot * g.kpCap + i];
-            if (z > 0) {
-                const plf_keypoint k = kp[(size_t)img * g.kpCap + i];
-                const float x = __fmul_rn(__fmul_rn(__fsub_rn(k.x, a.cx), z), a.invfx);
-                const float y = __fmul_rn(__fmul_rn(__fsub_rn(k.y, a.cy), z), a.invfy);
-                const float t0 = __fadd_rn(__fadd_rn(__fmul_rn(R[0], x), __fmul_rn(R[1], y)), __fmul_rn(R[2], z));
-                const float t1 = __fadd_rn(__fadd_rn(__fmul_rn(R[3], x), __fmul_rn(R[4], y)), __fmul_rn(R[5], z));
-                const float t2 = __fadd_rn(__fadd_rn(__fmul_rn(R[6], x), __fmul_rn(R[7], y)), __fmul_rn(R[8], z));
-                o0 = (float)__dadd_rn((double)t0, (double)O[0]);
-                o1 = (float)__dadd_rn((double)t1, (double)O[1]);
-                o2 = (float)__dadd_rn((double)t2, (double)O[2]);
-            }
-        }
-        float* d = x3d + ((size_t)s * x3dRows + i) * 3;
-        d[0] = o0; d[1] = o1; d[2] = o2;
-    }
-    if (l3d && i < l3dRows) {
-        double o[6] = {0, 0, 0, 0, 0, 0};
-        if (nKl && i < nKl[img]) {
-            const float d0 = disp[((size_t)slot * g.klCap + i) * 2], d1 = disp[((size_t)slot * g.klCap + i) * 2 + 1];
-            if (d0 > 0 && d1 > 0) {
-                const plf_keyline k = kl[(size_t)img * g.klCap + i];
-                const float uv[4] = {k.startPointX, k.startPointY, k.endPointX, k.endPointY};
-                const float dd[2] = {d0, d1};
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const double bd = (double)a.mb / (double)dd[e];
-                    const double P0 = __dmul_rn(bd, __dsub_rn((double)uv[2 * e], (double)a.cx));
-                    const double P1 = __dmul_rn(bd, __dsub_rn((double)uv[2 * e + 1], (double)a.cy));
-                    const double P2 = __dmul_rn(bd, (double)a.fx);
-#pragma unroll
-                    for (int r = 0; r < 3; ++r)
-                        o[3 * e + r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn((double)R[3 * r], P0), __dmul_rn((double)R[3 * r + 1], P1)),
-                                                           __dmul_rn((double)R[3 * r + 2], P2)), (double)O[r]);
-                }
-            }
-        }
-        double* d = l3d + ((size_t)s * l3dRows + i) * 6;
-#pragma unroll
-        for (int k2 = 0; k2 < 6; ++k2) d[k2] = o[k2];
-    }
-}
-}  // namespace
-
-int plf_launch_backproject(plf_ctx* c, int slotFirst, int nSlots, const float* dRwc, const float* dOw, float fy, float cx,
-                           float cy, float* dX3d, int x3dRows, double* dL3d, int l3dRows) {
-    const PlfGeom& g = c->g;
-    BackprojArgs a;
-    a.fx = c->p.fx; a.fy = fy; a.cx = cx; a.cy = cy;
-    a.invfx = 1.0f / a.fx; a.invfy = 1.0f / fy;          // src/Frame.cc:190-191
-    a.mb = c->p.bf / c->p.fx;                             // src/Frame.cc:196 (the declared rule mb := mbf / fx)
-    const int rows = max(dX3d ? x3dRows : 0, dL3d ? l3dRows : 0);
-    if (rows <= 0) return 0;
-    backproject_kernel<<<dim3((rows + 255) / 256, nSlots), 256, 0, c->stream>>>(
-        g, c->d_kp, c->d_nKp, c->d_depth, c->d_kl, c->p.has_lines ? c->d_nKl : nullptr, c->d_disp, dRwc, dOw, a, dX3d, x3dRows,
-        dL3d, l3dRows, slotFirst);
-    return 1;
-}
-
-int plf_launch_feature_grid(plf_ctx* c, int slotFirst, int nSlots, int* cellStart, int* cellIdx) {
-    const PlfGeom& g = c->g;
-    const float invW = (float)PLF_GRID_COLS / ((float)g.W - 0.0f), invH = (float)PLF_GRID_ROWS / ((float)g.H - 0.0f);
-    feature_grid_kernel<<<nSlots, 256, 0, c->stream>>>(g, c->d_kp, c->d_nKp, cellStart, cellIdx, invW, invH, slotFirst);
-    return 1;
-}
-
 int plf_launch_stereo_points(plf_ctx* c, int slotFirst, int nSlots) {
     const PlfGeom& g = c->g;
     plf_mark(c, "stereo_points");

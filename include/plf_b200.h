@@ -266,6 +266,36 @@ PLF_API int PLF_FN(search_by_projection)(plf_ctx* ctx, int slot, const plf_proj_
                                          float nn_ratio, int th_high, uint8_t* occupied, int32_t* match,
                                          int* n_matches);
 
+/* One map point of LastFrame already projected into CurrentFrame, as the frame-to-frame overload
+ * ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono, match12)
+ * (src/ORBmatcher.cc:2179-2323, Tracking::TrackWithMotionModel) has it after :2205-2241.  The projection itself
+ * (a 3x4 transform per point) stays in the caller.  72 bytes. */
+typedef struct plf_frame_query {
+    float u, v;                 /* projection into CurrentFrame (:2217-2218)                                 */
+    float ur;                   /* u - mbf * invzc (:2262)                                                   */
+    float radius;               /* th * CurrentFrame.mvScaleFactors[nLastOctave] (:2229)                     */
+    int32_t min_level, max_level; /* GetFeaturesInArea level arguments picked by bForward / bBackward
+                                   * (:2233-2238): (oct, -1), (0, oct) or (oct - 1, oct + 1)                 */
+    int32_t skip;               /* != 0: no map point, outlier, invzc < 0 or outside the image bounds        */
+    int32_t has_observations;   /* pMP->Observations() > 0 (temporal points of UpdateLastFrame have none)    */
+    float angle;                /* LastFrame.mvKeysUn[i].angle                                               */
+    uint8_t desc[32];           /* pMP->GetDescriptor()                                                      */
+    int32_t pad;
+} plf_frame_query;
+
+/* Replaces the search loop, the rotation histogram and ComputeThreeMaxima (:2449-2490) of that overload for the left
+ * keypoints of one slot.  Device: window search, level / stereo filters, Hamming distances.  Host, in query order:
+ * best distance among the features not occupied, TH_HIGH, CurrentFrame.mvpMapPoints[best] = pMP (a later map point
+ * may overwrite an earlier one that has no observations, exactly as in the reference), match12.insert, the 30-bin
+ * rotation histogram and the removal of everything outside its three maxima.
+ * occupied  : in/out, one byte per keypoint: the feature holds a map point with Observations() > 0
+ * feat_query: out, per keypoint: index of the query whose map point it holds at the end, or -1
+ * match12   : out, per keypoint: the std::map<int,int> of the reference (first insertion wins), or -1; may be NULL
+ * Returns the reference's nmatches in *n_matches. */
+PLF_API int PLF_FN(search_by_projection_frame)(plf_ctx* ctx, int slot, const plf_frame_query* queries, int n_queries,
+                                               int th_high, int check_orientation, uint8_t* occupied,
+                                               int32_t* feat_query, int32_t* match12, int* n_matches);
+
 /* ------------------------------------------------------------------------------------------------------ */
 /* Landmark back-projection: the epilogue that turns stereo matches into 3-D landmarks.   */
 

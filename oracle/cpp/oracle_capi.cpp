@@ -525,6 +525,103 @@ PLF_API int plf_cpu_search_by_projection(plf_ctx* c, int slot, const plf_proj_qu
     return PLF_OK;
 }
 
+// ---- ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono, match12) (src/ORBmatcher.cc:2179-2323)
+// from the projected points on: window search, best distance, assignment, rotation histogram, ComputeThreeMaxima (:2449-2490).
+// parity unpinned, like the local-map overload above.
+PLF_API int plf_cpu_search_by_projection_frame(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, int th_high,
+                                               int check_orientation, uint8_t* occupied, int32_t* feat_query, int32_t* match12,
+                                               int* n_matches) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || !queries || n_queries < 0 || !occupied || !feat_query)
+        return fail(PLF_ERR_INVALID, "bad arguments");
+    const Slot& sl = c->slots[slot];
+    const std::vector<plf_keypoint>& kps = sl.orb[0].kps;
+    const uint8_t* D = sl.orb[0].desc.data();
+    const int N = (int)kps.size();
+    const float invW = (float)PLF_GRID_COLS / ((float)c->p.width - 0.0f), invH = (float)PLF_GRID_ROWS / ((float)c->p.height - 0.0f);
+    std::vector<std::vector<int>> grid(PLF_GRID_COLS * PLF_GRID_ROWS);
+    for (int i = 0; i < N; ++i) {
+        const int px = (int)std::round((kps[i].x - 0.0f) * invW), py = (int)std::round((kps[i].y - 0.0f) * invH);
+        if (px < 0 || px >= PLF_GRID_COLS || py < 0 || py >= PLF_GRID_ROWS) continue;
+        grid[px * PLF_GRID_ROWS + py].push_back(i);
+    }
+    for (int f = 0; f < N; ++f) { feat_query[f] = -1; if (match12) match12[f] = -1; }
+    const int HISTO = 30;
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / HISTO;
+    int nmatches = 0;
+    for (int i = 0; i < n_queries; ++i) {
+        const plf_frame_query& q = queries[i];
+        if (q.skip) continue;
+        const float u = q.u, v = q.v, radius = q.radius;
+        std::vector<int> vIndices2;                 // CurrentFrame.GetFeaturesInArea(u, v, radius, min_level, max_level)
+        {
+            const int x0 = std::max(0, (int)std::floor((u - 0.0f - radius) * invW));
+            const int x1 = std::min(PLF_GRID_COLS - 1, (int)std::ceil((u - 0.0f + radius) * invW));
+            const int y0 = std::max(0, (int)std::floor((v - 0.0f - radius) * invH));
+            const int y1 = std::min(PLF_GRID_ROWS - 1, (int)std::ceil((v - 0.0f + radius) * invH));
+            if (x0 < PLF_GRID_COLS && x1 >= 0 && y0 < PLF_GRID_ROWS && y1 >= 0) {
+                const bool check = q.min_level > 0 || q.max_level >= 0;
+                for (int ix = x0; ix <= x1; ++ix)
+                    for (int iy = y0; iy <= y1; ++iy)
+                        for (int idx : grid[ix * PLF_GRID_ROWS + iy]) {
+                            const plf_keypoint& k = kps[idx];
+                            if (check) {
+                                if (k.octave < q.min_level) continue;
+                                if (q.max_level >= 0 && k.octave > q.max_level) continue;
+                            }
+                            if (std::fabs(k.x - u) < radius && std::fabs(k.y - v) < radius) vIndices2.push_back(idx);
+                        }
+            }
+        }
+        if (vIndices2.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (occupied[i2]) continue;
+            if (i2 < (int)sl.uRight.size() && sl.uRight[i2] > 0) {
+                const float er = std::fabs(q.ur - sl.uRight[i2]);
+                if (er > radius) continue;
+            }
+            const int dist = plf_hamming256(q.desc, D + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestIdx2 >= 0 && bestDist <= th_high) {
+            feat_query[bestIdx2] = i;
+            occupied[bestIdx2] = q.has_observations ? 1 : 0;
+            ++nmatches;
+            if (match12 && match12[bestIdx2] < 0) match12[bestIdx2] = i;
+            if (check_orientation) {
+                float rot = q.angle - kps[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO) bin = 0;
+                if (bin >= 0 && bin < HISTO) rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;
+        for (int i = 0; i < HISTO; ++i) {
+            const int s = (int)rotHist[i].size();
+            if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+            else if (s > max3) { max3 = s; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+        for (int i = 0; i < HISTO; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); ++j) {
+                    const int f = rotHist[i][j];
+                    feat_query[f] = -1;
+                    occupied[f] = 0;
+                    --nmatches;
+                    if (match12) match12[f] = -1;
+                }
+    }
+    if (n_matches) *n_matches = nmatches;
+    return PLF_OK;
+}
+
 static void run_pair(plf_ctx* c, int b) {
     Slot& s = c->slots[b];
     const int w = c->p.width, h = c->p.height;

@@ -62,6 +62,8 @@ assert KEYPOINT_DT.itemsize == 28 and KEYLINE_DT.itemsize == 68
 # every symbol include/plf_b200.h declares (without prefix)
 PROJ_QUERY_DT = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("level", "<i4"),
                           ("skip", "<i4"), ("desc", "u1", (32,))])       # plf_proj_query, 56 bytes
+FRAME_QUERY_DT = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("radius", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"),
+                           ("skip", "<i4"), ("has_observations", "<i4"), ("angle", "<f4"), ("desc", "u1", (32,)), ("pad", "<i4")])
 GRID_COLS, GRID_ROWS = 64, 48      # FRAME_GRID_COLS / FRAME_GRID_ROWS (include/Frame.h:59-60)
 
 ABI_SYMBOLS = [
@@ -70,7 +72,7 @@ ABI_SYMBOLS = [
     "match", "frontend_batch", "batch_upload", "batch_run", "batch_download", "sync", "batch_io_bytes",
     "last_launch_count", "set_stage_timing", "get_stage_ms", "stream", "tap_blurred_level", "tap_pyramid_level",
     "tap_fast_candidates", "tap_lsd_scaled", "tap_lsd_angles", "tap_lsd_segments", "tap_lbd_float",
-    "rectify_set_maps", "rectify", "batch_upload_raw", "feature_grid", "get_features_in_area", "backproject", "bow_set_vocabulary", "bow_transform", "bow_build_vectors", "search_by_projection",
+    "rectify_set_maps", "rectify", "batch_upload_raw", "feature_grid", "get_features_in_area", "backproject", "bow_set_vocabulary", "bow_transform", "bow_build_vectors", "search_by_projection", "search_by_projection_frame",
 ]
 
 
@@ -361,6 +363,18 @@ class Frontend:
         self.lib.check(self.lib.fn("search_by_projection")(self.ctx, slot, _ptr(queries), len(queries), C.c_float(th),
                                                            C.c_float(nn_ratio), int(th_high), _ptr(occupied), _ptr(match), C.byref(nm)))
         return match, nm.value
+
+    def search_by_projection_frame(self, queries, occupied, th_high=100, check_orientation=True, slot=0):
+        """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, ...) from the projected points on: queries =
+        FRAME_QUERY_DT array, occupied = uint8 per keypoint (updated in place) -> (feat_query, match12, nmatches)."""
+        queries = np.ascontiguousarray(queries, FRAME_QUERY_DT)
+        assert occupied.dtype == np.uint8 and occupied.flags.c_contiguous
+        fq = np.full(len(occupied), -1, np.int32); m12 = np.full(len(occupied), -1, np.int32)
+        nm = C.c_int(0)
+        self.lib.check(self.lib.fn("search_by_projection_frame")(self.ctx, slot, _ptr(queries), len(queries), int(th_high),
+                                                                 int(bool(check_orientation)), _ptr(occupied), _ptr(fq), _ptr(m12),
+                                                                 C.byref(nm)))
+        return fq, m12, nm.value
 
     # ---- bag of words (SURVEY §8f rank 3) ------------------------------------------------------------------------------
     def bow_set_vocabulary(self, which, voc):

@@ -39,13 +39,9 @@ PLF_API int plf_get_features_in_area(const plf_keypoint* kps, const int32_t* cel
 }
 
 // ---- projection-window search (second half) ----------------------------------------------------------
-PLF_API int plf_search_by_projection(plf_ctx* c, int slot, const plf_proj_query* queries, int n_queries, float th, float nn_ratio,
-                                     int th_high, uint8_t* occupied, int32_t* match, int* n_matches) {
-    if (!c || slot < 0 || slot >= c->p.max_batch || !queries || n_queries < 0 || !occupied || !match)
-        return fail(PLF_ERR_INVALID, "bad arguments");
-    if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "search_by_projection before the frame was extracted and stereo-matched");
-    if (n_matches) *n_matches = 0;
-    if (n_queries == 0) return PLF_OK;
+// device half shared by the two overloads: feature grid of the slot, candidate counts, candidate pool (CSR by query)
+static int window_candidates(plf_ctx* c, int slot, const std::vector<PlfWinQ>& q, std::vector<int>& start, std::vector<int2>& pool) {
+    const int nq = (int)q.size();
     PLF_CUDA_OK(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     constexpr int NC1 = PLF_GRID_COLS * PLF_GRID_ROWS + 1;
@@ -53,25 +49,26 @@ PLF_API int plf_search_by_projection(plf_ctx* c, int slot, const plf_proj_query*
         PLF_CUDA_OK(dalloc(&c->d_gridStart, (size_t)c->p.max_batch * NC1));
         PLF_CUDA_OK(dalloc(&c->d_gridIdx, (size_t)c->p.max_batch * c->g.kpCap));
     }
-    if (c->projQCap < (size_t)n_queries) {
+    if (c->projQCap < (size_t)nq) {
         PLF_CUDA_OK(cudaStreamSynchronize(s));
         if (c->d_projQ) { cudaFree(c->d_projQ); cudaFree(c->d_projCount); cudaFree(c->d_projStart); }
         c->d_projQ = nullptr; c->d_projCount = nullptr; c->d_projStart = nullptr; c->projQCap = 0;
-        PLF_CUDA_OK(dalloc(&c->d_projQ, (size_t)n_queries));
-        PLF_CUDA_OK(dalloc(&c->d_projCount, (size_t)n_queries));
-        PLF_CUDA_OK(dalloc(&c->d_projStart, (size_t)n_queries));
-        c->projQCap = n_queries;
+        PLF_CUDA_OK(dalloc(&c->d_projQ, (size_t)nq));
+        PLF_CUDA_OK(dalloc(&c->d_projCount, (size_t)nq));
+        PLF_CUDA_OK(dalloc(&c->d_projStart, (size_t)nq));
+        c->projQCap = nq;
     }
     // Frame::AssignFeaturesToGrid for this slot (slot-local CSR at the start of the grid buffers)
     plf_launch_feature_grid(c, slot, 1, c->d_gridStart, c->d_gridIdx);
-    PLF_CUDA_OK(cudaMemcpyAsync(c->d_projQ, queries, (size_t)n_queries * sizeof(plf_proj_query), cudaMemcpyHostToDevice, s));
-    plf_launch_proj_candidates(c, slot, c->d_projQ, n_queries, th, c->d_gridStart, c->d_gridIdx, c->d_projCount, nullptr, nullptr, false);
-    std::vector<int> cnt(n_queries), start(n_queries + 1, 0);
-    PLF_CUDA_OK(cudaMemcpyAsync(cnt.data(), c->d_projCount, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, s));
+    PLF_CUDA_OK(cudaMemcpyAsync(c->d_projQ, q.data(), (size_t)nq * sizeof(PlfWinQ), cudaMemcpyHostToDevice, s));
+    plf_launch_proj_candidates(c, slot, c->d_projQ, nq, c->d_gridStart, c->d_gridIdx, c->d_projCount, nullptr, nullptr, false);
+    std::vector<int> cnt(nq);
+    start.assign(nq + 1, 0);
+    PLF_CUDA_OK(cudaMemcpyAsync(cnt.data(), c->d_projCount, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
     PLF_CUDA_OK(cudaStreamSynchronize(s));
-    for (int i = 0; i < n_queries; ++i) start[i + 1] = start[i] + cnt[i];
-    const size_t total = (size_t)start[n_queries];
-    std::vector<int2> pool(total);
+    for (int i = 0; i < nq; ++i) start[i + 1] = start[i] + cnt[i];
+    const size_t total = (size_t)start[nq];
+    pool.resize(total);
     if (total) {
         if (c->projPoolCap < total) {
             if (c->d_projPool) cudaFree(c->d_projPool);
@@ -79,13 +76,39 @@ PLF_API int plf_search_by_projection(plf_ctx* c, int slot, const plf_proj_query*
             PLF_CUDA_OK(dalloc(&c->d_projPool, total * 2));
             c->projPoolCap = total * 2;
         }
-        PLF_CUDA_OK(cudaMemcpyAsync(c->d_projStart, start.data(), (size_t)n_queries * 4, cudaMemcpyHostToDevice, s));
-        plf_launch_proj_candidates(c, slot, c->d_projQ, n_queries, th, c->d_gridStart, c->d_gridIdx, c->d_projCount, c->d_projStart,
+        PLF_CUDA_OK(cudaMemcpyAsync(c->d_projStart, start.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, s));
+        plf_launch_proj_candidates(c, slot, c->d_projQ, nq, c->d_gridStart, c->d_gridIdx, c->d_projCount, c->d_projStart,
                                    c->d_projPool, true);
         PLF_CUDA_OK(cudaMemcpyAsync(pool.data(), c->d_projPool, total * sizeof(int2), cudaMemcpyDeviceToHost, s));
         PLF_CUDA_OK(cudaStreamSynchronize(s));
     }
     PLF_CUDA_OK(cudaGetLastError());
+    return PLF_OK;
+}
+
+PLF_API int plf_search_by_projection(plf_ctx* c, int slot, const plf_proj_query* queries, int n_queries, float th, float nn_ratio,
+                                     int th_high, uint8_t* occupied, int32_t* match, int* n_matches) {
+    if (!c || slot < 0 || slot >= c->p.max_batch || !queries || n_queries < 0 || !occupied || !match)
+        return fail(PLF_ERR_INVALID, "bad arguments");
+    if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "search_by_projection before the frame was extracted and stereo-matched");
+    if (n_matches) *n_matches = 0;
+    if (n_queries == 0) return PLF_OK;
+    std::vector<PlfWinQ> q(n_queries);
+    for (int i = 0; i < n_queries; ++i) {
+        const plf_proj_query& m = queries[i];
+        PlfWinQ& w = q[i];
+        w.skip = m.skip || m.level < 0 || m.level >= c->g.nLevels;
+        float r = m.view_cos > 0.998f ? 2.5f : 4.0f;            // RadiusByViewingCos, src/ORBmatcher.cc:216-222
+        if (th != 1.0f) r *= th;
+        w.x = m.proj_x; w.y = m.proj_y; w.xr = m.proj_xr;
+        w.radius = w.skip ? 0.f : r * c->scale[m.level];
+        w.minLevel = m.level - 1; w.maxLevel = m.level; w.pad = 0;
+        memcpy(w.desc, m.desc, 32);
+    }
+    std::vector<int> start;
+    std::vector<int2> pool;
+    const int rc = window_candidates(c, slot, q, start, pool);
+    if (rc) return rc;
     // the order-dependent half, in query order (src/ORBmatcher.cc:84-129)
     int nm = 0;
     for (int i = 0; i < n_queries; ++i) {
@@ -105,6 +128,85 @@ PLF_API int plf_search_by_projection(plf_ctx* c, int slot, const plf_proj_query*
                 ++nm;
             }
         }
+    }
+    if (n_matches) *n_matches = nm;
+    return PLF_OK;
+}
+
+PLF_API int plf_search_by_projection_frame(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, int th_high,
+                                           int check_orientation, uint8_t* occupied, int32_t* feat_query, int32_t* match12,
+                                           int* n_matches) {
+    if (!c || slot < 0 || slot >= c->p.max_batch || !queries || n_queries < 0 || !occupied || !feat_query)
+        return fail(PLF_ERR_INVALID, "bad arguments");
+    if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "search_by_projection_frame before the frame was extracted and stereo-matched");
+    PLF_CUDA_OK(cudaSetDevice(c->device));
+    // the current frame's keypoint count and angles (rotation histogram)
+    const int img = slot * 2;
+    int N = 0;
+    PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
+    PLF_CUDA_OK(cudaMemcpy(&N, c->d_nKp + img, 4, cudaMemcpyDeviceToHost));
+    std::vector<plf_keypoint> kps((size_t)std::max(N, 1));
+    if (N > 0) PLF_CUDA_OK(cudaMemcpy(kps.data(), c->d_kp + (size_t)img * c->g.kpCap, (size_t)N * sizeof(plf_keypoint), cudaMemcpyDeviceToHost));
+    for (int f = 0; f < N; ++f) { feat_query[f] = -1; if (match12) match12[f] = -1; }
+    if (n_matches) *n_matches = 0;
+    if (n_queries == 0) return PLF_OK;
+    std::vector<PlfWinQ> q(n_queries);
+    for (int i = 0; i < n_queries; ++i) {
+        const plf_frame_query& m = queries[i];
+        PlfWinQ& w = q[i];
+        w.skip = m.skip; w.x = m.u; w.y = m.v; w.xr = m.ur; w.radius = m.radius;
+        w.minLevel = m.min_level; w.maxLevel = m.max_level; w.pad = 0;
+        memcpy(w.desc, m.desc, 32);
+    }
+    std::vector<int> start;
+    std::vector<int2> pool;
+    const int rc = window_candidates(c, slot, q, start, pool);
+    if (rc) return rc;
+    // src/ORBmatcher.cc:2246-2290 in query order, then the rotation consistency of :2293-2317
+    constexpr int HISTO = 30;
+    std::vector<int> rotHist[HISTO];
+    const float factor = 1.0f / HISTO;
+    int nm = 0;
+    for (int i = 0; i < n_queries; ++i) {
+        if (queries[i].skip) continue;
+        int bestDist = 256, bestIdx = -1;
+        for (int j = start[i]; j < start[i + 1]; ++j) {
+            const int idx = pool[j].x, dist = pool[j].y & 0xFFFF;
+            if (occupied[idx]) continue;
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestIdx >= 0 && bestDist <= th_high) {
+            feat_query[bestIdx] = i;
+            occupied[bestIdx] = queries[i].has_observations ? 1 : 0;     // the holder decides whether later points skip it
+            ++nm;
+            if (match12 && match12[bestIdx] < 0) match12[bestIdx] = i;    // std::map::insert keeps the first
+            if (check_orientation) {
+                float rot = queries[i].angle - kps[bestIdx].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)roundf(rot * factor);
+                if (bin == HISTO) bin = 0;
+                if (bin >= 0 && bin < HISTO) rotHist[bin].push_back(bestIdx);
+            }
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;          // ComputeThreeMaxima, :2449-2490
+        for (int i = 0; i < HISTO; ++i) {
+            const int sz = (int)rotHist[i].size();
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) ind3 = -1;
+        for (int i = 0; i < HISTO; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int f : rotHist[i]) {
+                    feat_query[f] = -1;
+                    occupied[f] = 0;
+                    --nm;
+                    if (match12) match12[f] = -1;
+                }
     }
     if (n_matches) *n_matches = nm;
     return PLF_OK;

@@ -260,40 +260,33 @@ int plf_launch_bow(plf_ctx* c, int which, int slotFirst, int nSlots, int levelsu
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/ORBmatcher.cc:44-130), device half: a warp per
-// map point walks the grid cells of its window in GetFeaturesInArea order (src/Frame.cc:774-843: cell columns, cell rows,
-// insertion order), lanes take the features of a cell 32 at a time, apply the level, window and stereo filters and
+// ORBmatcher::SearchByProjection, device half of both overloads built (src/ORBmatcher.cc:44-130 and :2179-2323): a warp
+// per map point walks the grid cells of its window in GetFeaturesInArea order (src/Frame.cc:774-843: cell columns, cell
+// rows, insertion order), lanes take the features of a cell 32 at a time, apply the level, window and stereo filters and
 // compute the Hamming distances; survivors are compacted in order.  FILL = false only counts (the host sizes the
 // candidate pool from the counts), FILL = true writes (feature index, distance | octave << 16).
 namespace {
 template <bool FILL>
-__global__ void __launch_bounds__(256) proj_candidates_kernel(PlfGeom g, const plf_proj_query* qs, int nq, float th, const plf_keypoint* kp,
+__global__ void __launch_bounds__(256) proj_candidates_kernel(PlfGeom g, const PlfWinQ* qs, int nq, const plf_keypoint* kp,
                                                               const uint8_t* desc, const float* uRight, const int* cellStart,
                                                               const int* cellIdx, int* count, const int* segStart, int2* pool) {
     const int qi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (qi >= nq) return;
-    const plf_proj_query q = qs[qi];
+    const PlfWinQ q = qs[qi];
     int total = 0;
-    if (!q.skip && q.level >= 0 && q.level < g.nLevels) {
-        float r = q.view_cos > 0.998f ? 2.5f : 4.0f;
-        if (th != 1.0f) r = __fmul_rn(r, th);
-        const float rad = __fmul_rn(r, g.lv[q.level].scale);
+    if (!q.skip) {
+        const float rad = q.radius;
         const float invW = (float)PLF_GRID_COLS / ((float)g.W - 0.0f), invH = (float)PLF_GRID_ROWS / ((float)g.H - 0.0f);
-        int x0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.proj_x, 0.0f), rad), invW));
-        int x1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.proj_x, 0.0f), rad), invW));
-        int y0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.proj_y, 0.0f), rad), invH));
-        int y1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.proj_y, 0.0f), rad), invH));
+        int x0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.x, 0.0f), rad), invW));
+        int x1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.x, 0.0f), rad), invW));
+        int y0 = (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(q.y, 0.0f), rad), invH));
+        int y1 = (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(q.y, 0.0f), rad), invH));
         x0 = max(x0, 0); y0 = max(y0, 0);
         x1 = min(x1, PLF_GRID_COLS - 1); y1 = min(y1, PLF_GRID_ROWS - 1);
         const bool window = x0 < PLF_GRID_COLS && x1 >= 0 && y0 < PLF_GRID_ROWS && y1 >= 0;
-        const int minLevel = q.level - 1, maxLevel = q.level;
+        const int minLevel = q.minLevel, maxLevel = q.maxLevel;
         const bool check = minLevel > 0 || maxLevel >= 0;
-        uint4 a = make_uint4(0, 0, 0, 0), b = a;
-        if (FILL) {
-            const unsigned* w = reinterpret_cast<const unsigned*>(qs[qi].desc);      // 56-byte structs: 4-byte aligned rows
-            a = make_uint4(w[0], w[1], w[2], w[3]);
-            b = make_uint4(w[4], w[5], w[6], w[7]);
-        }
+        const uint4 a = make_uint4(q.desc[0], q.desc[1], q.desc[2], q.desc[3]), b = make_uint4(q.desc[4], q.desc[5], q.desc[6], q.desc[7]);
         const unsigned lt = (1u << lane) - 1u;
         int2* out = FILL ? pool + segStart[qi] : nullptr;
         if (window)
@@ -310,10 +303,10 @@ __global__ void __launch_bounds__(256) proj_candidates_kernel(PlfGeom g, const p
                             const plf_keypoint k = kp[idx];
                             oct = k.octave;
                             ok = !(check && (oct < minLevel || (maxLevel >= 0 && oct > maxLevel)));
-                            ok = ok && fabsf(__fsub_rn(k.x, q.proj_x)) < rad && fabsf(__fsub_rn(k.y, q.proj_y)) < rad;
+                            ok = ok && fabsf(__fsub_rn(k.x, q.x)) < rad && fabsf(__fsub_rn(k.y, q.y)) < rad;
                             if (ok) {
                                 const float ur = uRight[idx];
-                                if (ur > 0 && fabsf(__fsub_rn(q.proj_xr, ur)) > rad) ok = false;
+                                if (ur > 0 && fabsf(__fsub_rn(q.xr, ur)) > rad) ok = false;
                             }
                         }
                         const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -332,14 +325,14 @@ __global__ void __launch_bounds__(256) proj_candidates_kernel(PlfGeom g, const p
 }
 }  // namespace
 
-int plf_launch_proj_candidates(plf_ctx* c, int slot, const plf_proj_query* dQ, int nq, float th, const int* dCellStart,
+int plf_launch_proj_candidates(plf_ctx* c, int slot, const PlfWinQ* dQ, int nq, const int* dCellStart,
                                const int* dCellIdx, int* dCount, const int* dSegStart, int2* dPool, bool fill) {
     const PlfGeom& g = c->g;
     const plf_keypoint* kp = c->d_kp + (size_t)(slot * 2) * g.kpCap;
     const uint8_t* desc = c->d_desc + (size_t)(slot * 2) * g.kpCap * 32;
     const float* ur = c->d_uRight + (size_t)slot * g.kpCap;
     const dim3 grid((nq + 7) / 8);
-    if (fill) proj_candidates_kernel<true><<<grid, 256, 0, c->stream>>>(g, dQ, nq, th, kp, desc, ur, dCellStart, dCellIdx, dCount, dSegStart, dPool);
-    else proj_candidates_kernel<false><<<grid, 256, 0, c->stream>>>(g, dQ, nq, th, kp, desc, ur, dCellStart, dCellIdx, dCount, dSegStart, dPool);
+    if (fill) proj_candidates_kernel<true><<<grid, 256, 0, c->stream>>>(g, dQ, nq, kp, desc, ur, dCellStart, dCellIdx, dCount, dSegStart, dPool);
+    else proj_candidates_kernel<false><<<grid, 256, 0, c->stream>>>(g, dQ, nq, kp, desc, ur, dCellStart, dCellIdx, dCount, dSegStart, dPool);
     return 1;
 }

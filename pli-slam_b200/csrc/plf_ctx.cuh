@@ -61,6 +61,12 @@ struct PlfGeom {          // passed by value to kernels (fits the 4 KB parameter
     int seedCap;
 };
 
+struct __align__(16) PlfWinQ {   // one window query of the projection searches, as the device sees it (64 bytes)
+    float x, y, xr, radius;      // window centre, right-image coordinate for the stereo check, half side
+    int minLevel, maxLevel, skip, pad;
+    unsigned desc[8];
+};
+
 struct PlfVocab {           // DBoW2 vocabulary tree on the device (plf_bow_set_vocabulary)
     int nNodes = 0, levels = 0;
     int *childFirst = nullptr, *childCount = nullptr, *child = nullptr, *word = nullptr;
@@ -142,7 +148,7 @@ struct plf_ctx {
     int* d_bowWord = nullptr;        // [max_batch][max(kpCap, klCap)] outputs of plf_bow_transform
     int* d_bowNode = nullptr;
     double* d_bowWeight = nullptr;
-    plf_proj_query* d_projQ = nullptr;   // plf_search_by_projection scratch: queries, counts, segment starts, candidate pool
+    PlfWinQ* d_projQ = nullptr;          // plf_search_by_projection scratch: queries, counts, segment starts, candidate pool
     int* d_projCount = nullptr;
     int* d_projStart = nullptr;
     int2* d_projPool = nullptr;
@@ -183,7 +189,7 @@ inline bool plf_raise_smem_optin(size_t (&granted)[64], int device, size_t smem)
 }
 
 int plf_launch_unpack(plf_ctx* c, const uint8_t* stage, size_t sideBytes, int stride, int batch);
-int plf_launch_proj_candidates(plf_ctx* c, int slot, const plf_proj_query* dQ, int nq, float th, const int* dCellStart,
+int plf_launch_proj_candidates(plf_ctx* c, int slot, const PlfWinQ* dQ, int nq, const int* dCellStart,
                                const int* dCellIdx, int* dCount, const int* dSegStart, int2* dPool, bool fill);
 int plf_launch_bow(plf_ctx* c, int which, int slotFirst, int nSlots, int levelsup, int* dWord, double* dWeight, int* dNode, int rows);
 int plf_launch_backproject(plf_ctx* c, int slotFirst, int nSlots, const float* dRwc, const float* dOw, float fy, float cx,

@@ -462,3 +462,23 @@ def test_search_by_projection_matches_oracle(plf, product, oracle, th):
         assert no > 300
     with pytest.raises(plf.PlfError):
         plf.Frontend(product, max_batch=1).search_by_projection(q[:4], np.zeros(10, np.uint8))     # before extraction
+
+
+@pytest.mark.parametrize("mode,check", [("around", True), ("forward", True), ("backward", False)])
+def test_search_by_projection_frame_matches_oracle(plf, product, oracle, mode, check):
+    """plf_search_by_projection_frame (TrackWithMotionModel's search: device candidates, in-order host resolve, rotation
+    histogram) against the oracle: final feature -> map point table, the match12 map, nmatches and occupancy identical."""
+    from test_host_logic import _frame_queries
+    L, R = plf.synth_batch(752, 480, [91, 92])
+    f, o = plf.Frontend(product, max_batch=2), plf.Frontend(oracle, max_batch=2)
+    rg, ro = f.frontend_batch(L, R), o.frontend_batch(L, R)
+    for b in (0, 1):
+        n = int(ro.n_kp_left[b])
+        rng = np.random.default_rng(30 + b)
+        q = _frame_queries(plf, ro, b, rng, mode)
+        occ0 = (rng.random(n) < 0.08).astype(np.uint8)
+        og, oo = occ0.copy(), occ0.copy()
+        fg, mg, ng = f.search_by_projection_frame(q, og, 100, check, slot=b)
+        fo, mo, no = o.search_by_projection_frame(q, oo, 100, check, slot=b)
+        assert ng == no and np.array_equal(fg, fo) and np.array_equal(mg, mo) and np.array_equal(og, oo)
+        assert no > 400

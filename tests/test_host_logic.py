@@ -373,3 +373,139 @@ def test_search_by_projection_oracle_against_python(plf, oracle, th):
     want, nm2 = _search_by_projection_python(q, res.kp_left[0, :n], res.desc_left[0, :n], res.u_right[0, :n], sc, occ_b, th, 0.8, 100)
     assert nm == nm2 and np.array_equal(got, want) and np.array_equal(occ_a, occ_b)
     assert nm > 100 and len(np.unique(got[got >= 0])) == nm          # a feature is given to one map point only
+
+
+def _frame_queries(plf, res, b, rng, mode="around"):
+    """LastFrame map points projected into the current frame b: every keypoint re-observed with a projection error, the
+    GetFeaturesInArea level arguments of one of the three motion cases, a rotated angle, some points without
+    observations (temporal points), some skipped, a block of unrelated points at the end; shuffled."""
+    n = int(res.n_kp_left[b])
+    kps, desc, ur = res.kp_left[b, :n], res.desc_left[b, :n], res.u_right[b, :n]
+    m = n + 120
+    q = np.zeros(m, plf.FRAME_QUERY_DT)
+    src = np.concatenate([np.arange(n), rng.integers(0, n, 120)])
+    q["u"] = kps["x"][src] + rng.normal(0, 2.0, m).astype(np.float32)
+    q["v"] = kps["y"][src] + rng.normal(0, 2.0, m).astype(np.float32)
+    q["ur"] = np.where(ur[src] > 0, ur[src] + rng.normal(0, 1.5, m), q["u"] - 20).astype(np.float32)
+    oct_ = kps["octave"][src].astype(np.int32)
+    sc = np.ones(8, np.float32)
+    for i in range(1, 8):
+        sc[i] = np.float32(sc[i - 1] * np.float32(1.2))
+    q["radius"] = np.float32(7.0) * sc[oct_]
+    if mode == "forward":
+        q["min_level"], q["max_level"] = oct_, -1
+    elif mode == "backward":
+        q["min_level"], q["max_level"] = 0, oct_
+    else:
+        q["min_level"], q["max_level"] = oct_ - 1, oct_ + 1
+    q["skip"] = (rng.random(m) < 0.05).astype(np.int32)
+    q["has_observations"] = (rng.random(m) < 0.7).astype(np.int32)
+    rot = rng.choice(np.array([3.0, 5.0, 8.0, 100.0, 200.0], np.float32), m, p=[0.45, 0.3, 0.15, 0.05, 0.05])
+    q["angle"] = np.mod(kps["angle"][src] + rot + rng.normal(0, 1.0, m), 360).astype(np.float32)
+    d = desc[src].copy()
+    d ^= np.packbits(rng.random((m, 256)) < 0.05, axis=1)
+    d[n:] = rng.integers(0, 256, (120, 32), dtype=np.uint8)
+    q["desc"] = d
+    return q[rng.permutation(m)]
+
+
+def _search_frame_python(q, kps, desc, ur, occupied, th_high, check, W=752, H=480):
+    """src/ORBmatcher.cc:2229-2317 restated loop for loop, incl. ComputeThreeMaxima (:2449-2490)."""
+    import math
+    f32 = np.float32
+    invw, invh = f32(64) / f32(W), f32(48) / f32(H)
+
+    def rnd(v):
+        return int(math.floor(abs(v) + 0.5)) * (1 if v >= 0 else -1)
+    grid = {}
+    for i in range(len(kps)):
+        px, py = rnd(float(f32(kps["x"][i]) * invw)), rnd(float(f32(kps["y"][i]) * invh))
+        if 0 <= px < 64 and 0 <= py < 48:
+            grid.setdefault(px * 48 + py, []).append(i)
+    bits = np.unpackbits(desc, axis=1)
+    N = len(kps)
+    fq, m12 = np.full(N, -1, np.int32), np.full(N, -1, np.int32)
+    hist = [[] for _ in range(30)]
+    factor = f32(1.0) / f32(30)
+    nm = 0
+    for i, qq in enumerate(q):
+        if qq["skip"]:
+            continue
+        u, v, rad = f32(qq["u"]), f32(qq["v"]), f32(qq["radius"])
+        lo, hi = int(qq["min_level"]), int(qq["max_level"])
+        x0 = max(0, math.floor(float(f32(f32(u - rad) * invw)))); x1 = min(63, math.ceil(float(f32(f32(u + rad) * invw))))
+        y0 = max(0, math.floor(float(f32(f32(v - rad) * invh)))); y1 = min(47, math.ceil(float(f32(f32(v + rad) * invh))))
+        if not (x0 < 64 and x1 >= 0 and y0 < 48 and y1 >= 0):
+            continue
+        qb = np.unpackbits(qq["desc"])
+        best, bidx = 256, -1
+        check_lv = lo > 0 or hi >= 0
+        for cx in range(x0, x1 + 1):
+            for cy in range(y0, y1 + 1):
+                for idx in grid.get(cx * 48 + cy, []):
+                    o = int(kps["octave"][idx])
+                    if check_lv and (o < lo or (hi >= 0 and o > hi)):
+                        continue
+                    if not (abs(f32(kps["x"][idx]) - u) < rad and abs(f32(kps["y"][idx]) - v) < rad):
+                        continue
+                    if occupied[idx]:
+                        continue
+                    if ur[idx] > 0 and abs(f32(qq["ur"]) - f32(ur[idx])) > rad:
+                        continue
+                    dist = int((bits[idx] ^ qb).sum())
+                    if dist < best:
+                        best, bidx = dist, idx
+        if bidx >= 0 and best <= th_high:
+            fq[bidx] = i
+            occupied[bidx] = 1 if qq["has_observations"] else 0
+            nm += 1
+            if m12[bidx] < 0:
+                m12[bidx] = i
+            if check:
+                rot = f32(f32(qq["angle"]) - f32(kps["angle"][bidx]))
+                if rot < 0:
+                    rot = f32(rot + f32(360))
+                b = rnd(float(f32(rot * factor)))
+                if b == 30:
+                    b = 0
+                hist[b].append(bidx)
+    if check:
+        i1 = i2 = i3 = -1
+        m1 = m2 = m3 = 0
+        for i in range(30):
+            s = len(hist[i])
+            if s > m1:
+                m3, m2, m1, i3, i2, i1 = m2, m1, s, i2, i1, i
+            elif s > m2:
+                m3, m2, i3, i2 = m2, s, i2, i
+            elif s > m3:
+                m3, i3 = s, i
+        if m2 < f32(0.1) * f32(m1):
+            i2 = i3 = -1
+        elif m3 < f32(0.1) * f32(m1):
+            i3 = -1
+        for i in range(30):
+            if i not in (i1, i2, i3):
+                for f in hist[i]:
+                    fq[f] = -1; occupied[f] = 0; nm -= 1; m12[f] = -1
+    return fq, m12, nm
+
+
+@pytest.mark.parametrize("mode,check", [("around", True), ("forward", True), ("backward", False)])
+def test_search_by_projection_frame_oracle_against_python(plf, oracle, mode, check):
+    """The frame-to-frame overload (window search, temporal points that do not block a feature, rotation histogram with
+    its three maxima) — oracle against the direct Python restatement."""
+    L, R = plf.synth_pair(752, 480, 8)
+    o = plf.Frontend(oracle, max_batch=1)
+    res = o.frontend_batch(L[None], R[None])
+    n = int(res.n_kp_left[0])
+    rng = np.random.default_rng(13)
+    q = _frame_queries(plf, res, 0, rng, mode)[:600]
+    occ0 = (rng.random(n) < 0.08).astype(np.uint8)
+    oa, ob = occ0.copy(), occ0.copy()
+    fq, m12, nm = o.search_by_projection_frame(q, oa, 100, check)
+    wfq, wm12, wnm = _search_frame_python(q, res.kp_left[0, :n], res.desc_left[0, :n], res.u_right[0, :n], ob, 100, check)
+    assert nm == wnm and np.array_equal(fq, wfq) and np.array_equal(m12, wm12) and np.array_equal(oa, ob)
+    assert nm > 150
+    if check:
+        assert (fq >= 0).sum() < 600 - 30          # the histogram removed the matches with the odd rotations

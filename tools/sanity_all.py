@@ -13,8 +13,16 @@ f.batch_upload_raw(L, R); f.batch_run(B); f.batch_download(B, out)
 res = f.frontend_batch(L, R)
 st, ix = f.feature_grid(0, B)
 x3d, l3d = f.backproject(np.tile(np.eye(3, dtype=np.float32), (B, 1, 1)), np.zeros((B, 3), np.float32), 435.2, 367.4, 252.2)
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from test_host_logic import _proj_queries, _frame_queries
+rng = np.random.default_rng(0)
+n0 = int(res.n_kp_left[0])
+mq, nmq = f.search_by_projection(_proj_queries(plf, res, 0, rng), np.zeros(n0, np.uint8), th=3.0)
+fq, m12, nfq = f.search_by_projection_frame(_frame_queries(plf, res, 0, rng), np.zeros(n0, np.uint8))
+f.bow_set_vocabulary(0, plf.synth_vocabulary(10, 4, seed=1)); f.bow_set_vocabulary(1, plf.synth_vocabulary(6, 3, seed=2, ragged=0.0))
+bw = f.bow_transform(0, B); bl = f.bow_transform(1, B)
 m, k, d = f.orb_extract(0, L[0]); m2, k2, d2 = f.orb_extract(1, R[0])
 kl, ld = f.line_extract(0, L[0]); klr, ldr = f.line_extract(1, R[0])
 u, dep = f.stereo_match_points(len(k)); disp, le, m12 = f.stereo_match_lines(len(kl))
 n1, _ = f.match_nnr(ld, ldr, 0.9); n2, _ = f.match(ld, ldr, 0.9, 1)
-print("ok", int(res.n_kp_left[0]), int(res.n_kl_left[0]), int(st[0, -1]), int((x3d[0] != 0).any(axis=1).sum()), n1, n2, img.mean().round(1))
+print("ok", nmq, nfq, int((bw[0] >= 0).sum()), int(res.n_kp_left[0]), int(res.n_kl_left[0]), int(st[0, -1]), int((x3d[0] != 0).any(axis=1).sum()), n1, n2, img.mean().round(1))

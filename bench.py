@@ -176,6 +176,10 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    # native libraries (NCCL's version banner, for one) printf to stdout: keep fd 1 for the one JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -371,7 +375,10 @@ def main():
             v, dt = cpu_baseline(sample, cores, [1000 + i for i in range(sample)])
             line["cpu_baseline"] = {"value": v, "unit": "stereo pairs/s", "cores": cores, "kind": "port",
                                     "sample": "%d pairs, %d worker threads over independent pairs, %.1f s" % (sample, cores, dt)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -267,6 +267,7 @@ struct GrowState {
     float sumdx, sumdy;
     float regDeg;     // exact region angle in degrees (fastAtan2 of the sums; the seed's angle for a fresh region) unless `dirty`
     bool dirty;
+    bool aborted;     // speculative mode only: a pixel of this region belongs to an earlier region of the wave
 };
 
 struct GrowCtx {
@@ -276,7 +277,12 @@ struct GrowCtx {
     int* R;
     int* ring;
     int W, H, PB, lane, ddx, ddy;   // PB: bits per bitmap row (= pitch of N2)
+    // speculative (several regions of one image in flight) mode only:
+    uint32_t* owner;    // per pixel: tag of the region that claims it in the current wave, PLF_FREE if none
+    uint32_t tag;       // my tag = slot + 1; a lower tag is an earlier seed
+    int* invalid;       // per slot: this region overlaps an earlier one of the wave and must be re-grown
 };
+#define PLF_FREE 0xFFFFFFFFu
 
 // q is a BIT index, y * PB + x
 __device__ __forceinline__ bool used_bit(const uint32_t* used, int q) {
@@ -325,6 +331,7 @@ __device__ __forceinline__ bool lsd_aligned(float thetaDeg, float aDeg, const Al
 // contradicts the prediction every lane has seen the true state, so those decisions are final; they are committed in
 // one SIMD step and the rest goes round again.  The angle drifts slowly, so one round usually settles a set:
 // ~100 + 9/accepted-pixel warp instructions per round instead of ~95 per accepted pixel.
+template <bool SPEC>
 __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int pk, const float4& r, const AlignTol& tol,
                                            const GrowCtx& c, unsigned dupAll, unsigned& accepted) {
     unsigned pending = __ballot_sync(0xffffffffu, valid);
@@ -377,8 +384,16 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
             const int at = st.n + __popc(acc & lt);
             c.ring[at & (GROW_RING - 1)] = pk;
             c.R[at] = pk;
-            atomicOr(c.used + (q >> 5), 1u << (q & 31));
+            if (!SPEC) {
+                atomicOr(c.used + (q >> 5), 1u << (q & 31));
+            } else {
+                // claim in the wave's owner map: the earlier seed (lower tag) wins a contested pixel, the loser is re-grown
+                const uint32_t old = atomicMin(c.owner + q, c.tag);
+                if (old < c.tag) c.invalid[c.tag - 1] = 1;
+                else if (old != PLF_FREE && old > c.tag) c.invalid[old - 1] = 1;
+            }
         }
+        if (SPEC && __any_sync(0xffffffffu, *(volatile int*)(c.invalid + (c.tag - 1)) != 0)) { st.aborted = true; st.n += __popc(acc); return; }
         st.n += __popc(acc);
         accepted |= acc;
         if (mm == 0u && v >= 0) {          // the spare lane holds the sums and the angle after all of A
@@ -404,12 +419,20 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
 
 // LSD region_grow from the seed (packed pk0, linear index p) with angle tolerance `tol`; returns the region size, the
 // pixel list is left in c.R[0..n)
+template <bool SPEC>
 __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, const AlignTol& tol, double& regAngleOut) {
     GrowState st;
     st.n = 1;
+    st.aborted = false;
     if (c.lane == 0) {
         const int pb = (pk0 >> 16) * c.PB + (pk0 & 0xFFFF);
-        c.ring[0] = pk0; c.R[0] = pk0; atomicOr(c.used + (pb >> 5), 1u << (pb & 31));
+        c.ring[0] = pk0; c.R[0] = pk0;
+        if (!SPEC) atomicOr(c.used + (pb >> 5), 1u << (pb & 31));
+        else {
+            const uint32_t old = atomicMin(c.owner + pb, c.tag);
+            if (old < c.tag) c.invalid[c.tag - 1] = 1;
+            else if (old != PLF_FREE && old > c.tag) c.invalid[old - 1] = 1;
+        }
     }
     st.regDeg = c.REC[p].x;
     st.dirty = false;
@@ -421,7 +444,7 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
     }
     __syncwarp();
     int i = 0;
-    while (i < st.n) {
+    while (i < st.n && !(SPEC && st.aborted)) {
         // a batch: up to GROW_SETS sets of 4 list entries x 8 neighbours.  All loads of the batch (ring, bitmap word,
         // record) are issued before the first set is resolved, so a wide frontier pays one memory round trip per
         // 4 * GROW_SETS entries; the sets are then resolved in list order.
@@ -445,6 +468,7 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
                     pk[s] = (yy << 16) | xx;
                     r[s] = c.REC[yy * c.W + xx];          // issued together with the bitmap word: one round trip
                     valid[s] = !used_bit(c.used, q[s]);   // unused implies defined: undefined pixels start as used
+                    if (SPEC && valid[s] && c.owner[q[s]] == c.tag) valid[s] = false;     // my own pixels count as used
                 }
             }
         }
@@ -463,7 +487,7 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
                 for (int t = 0; t < s; ++t)
                     for (unsigned m = acc[t]; m; m &= m - 1u)
                         if (q[s] == __shfl_sync(0xffffffffu, q[t], __ffs(m) - 1)) valid[s] = false;
-                grow_chain(st, valid[s], q[s], pk[s], r[s], tol, c, dupAll[s], acc[s]);
+                grow_chain<SPEC>(st, valid[s], q[s], pk[s], r[s], tol, c, dupAll[s], acc[s]);
                 __syncwarp();
             }
         }
@@ -605,7 +629,7 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[33], int& n, double
                                                      __dmul_rn(mean, mean))));
     __syncwarp();
     __threadfence_block();
-    n = grow_region(c, pk0, p0, make_align_tol(tau), regAngle);
+    n = grow_region<false>(c, pk0, p0, make_align_tol(tau), regAngle);
     if (n < 2) return false;
     rect_fit<true>(c, s_sum, n, regAngle, prec, rf);
     density = (double)n / __dmul_rn(lsd_dist(rf.x1, rf.y1, rf.x2, rf.y2), rf.width);
@@ -677,7 +701,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
             const int p = __shfl_sync(0xffffffffu, myQ, si);
             if (used_bit(c.used, __shfl_sync(0xffffffffu, myB, si))) continue;   // claimed by a region grown earlier in this chunk
             double regAngle;
-            int n = grow_region(c, pk0, p, precTol, regAngle);
+            int n = grow_region<false>(c, pk0, p, precTol, regAngle);
             if (n < g.minRegSize) continue;
             RectFit rf;
             rect_fit<REFINE>(c, s_sum, n, regAngle, prec, rf);
@@ -699,6 +723,162 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
         }
     }
     if (lane == 0) nSegsOut[img] = nSeg;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4c'  the same region growing for SMALL batches: several regions of ONE image in flight (a block of MW warps per
+// image) with the sequential result.  A region only depends on the `used` state of the pixels it examines, so the next
+// few unused seeds (picked at least MW_DIST pixels apart; seeds on the same edge would only collide) are grown
+// speculatively against the committed bitmap, each claiming its pixels in a per-wave owner map with atomicMin(tag):
+// the earlier seed wins a contested pixel and the loser is marked invalid.  Then one warp walks the seed list in order
+// and commits regions (bitmap bits, segment) until it meets an invalid region or a seed that was skipped for distance
+// and that no committed region swallowed; everything after that point is discarded and grown again in the next wave.
+// The first unused seed of a wave is always picked and can never lose, so every wave commits at least one region.
+// Exactness: a committed region saw exactly the used pixels the sequential order gives it — pixels of earlier regions
+// it merely examined and rejected do not matter, pixels it accepted are contested through the owner map.
+#define MW 8
+#define MW_SCAN 256
+#define MW_DIST 12
+__global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const float4* rec, const int* n2map, const int* seeds,
+                                                            const int* nSeeds, uint32_t* usedAll, uint32_t* ownerAll, int* regAll,
+                                                            float* segs, int* nSegsOut, int* err, int imgFirst) {
+    __shared__ int ring[MW][GROW_RING];
+    __shared__ double s_sum[MW][3][33];
+    __shared__ double s_seg[MW][4];
+    __shared__ int s_pickPos[MW], s_pickPk[MW], s_n[MW], s_inv[MW], s_hasSeg[MW];
+    __shared__ int s_nPick, s_pos, s_scanEnd, s_nSeg;
+    const int img = imgFirst + blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t npx = (size_t)g.Ws * g.Hs, npb = (size_t)g.Ps * g.Hs;
+    GrowCtx c;
+    c.W = g.Ws; c.H = g.Hs; c.PB = g.Ps; c.lane = lane;
+    c.REC = rec + (size_t)img * npx;
+    c.N2 = n2map + (size_t)img * npb;
+    c.used = usedAll + (size_t)img * (g.Ps >> 5) * g.Hs;
+    c.owner = ownerAll + (size_t)blockIdx.x * npb;
+    c.R = regAll + ((size_t)blockIdx.x * MW + w) * npx;
+    c.ring = ring[w];
+    c.tag = (uint32_t)w + 1u;
+    c.invalid = s_inv;
+    {
+        const int k = lane & 7;
+        c.ddx = (k < 3) ? k - 1 : (k == 3 ? -1 : (k == 4 ? 1 : k - 6));
+        c.ddy = (k < 3) ? -1 : (k < 5 ? 0 : 1);
+    }
+    const int* S = seeds + (size_t)img * g.seedCap;
+    float* out = segs + (size_t)img * g.segCap * 4;
+    const int ns = nSeeds[img];
+    const double prec = g.prec;
+    const AlignTol precTol = make_align_tol(prec);
+    if (threadIdx.x == 0) { s_pos = 0; s_nSeg = 0; }
+    __syncthreads();
+    while (s_pos < ns) {
+        // ---- 1. pick the seeds of the wave (warp 0) ----
+        if (w == 0) {
+            int nPick = 0, pos = s_pos, scanned = 0, lastPick = -1;
+            int myX = -100000, myY = -100000;                       // lane j < nPick holds pick j
+            while (nPick < MW && pos < ns && scanned < MW_SCAN) {
+                const int p = pos + lane;
+                const int seed = p < ns ? S[p] : -1;
+                const bool unused = seed >= 0 && !used_bit(c.used, (seed >> 16) * c.PB + (seed & 0xFFFF));
+                unsigned um = __ballot_sync(0xffffffffu, unused);
+                while (um && nPick < MW) {
+                    const int l = __ffs(um) - 1;
+                    um &= um - 1u;
+                    const int sd = __shfl_sync(0xffffffffu, seed, l);
+                    const int sx = sd & 0xFFFF, sy = sd >> 16;
+                    const bool nearPick = lane < nPick && max(abs(sx - myX), abs(sy - myY)) < MW_DIST;
+                    if (!__any_sync(0xffffffffu, nearPick)) {
+                        if (lane == nPick) { myX = sx; myY = sy; }
+                        if (lane == 0) { s_pickPos[nPick] = pos + l; s_pickPk[nPick] = sd; }
+                        lastPick = pos + l;
+                        ++nPick;
+                    }
+                }
+                pos += 32;
+                scanned += 32;
+            }
+            if (lane < MW) s_inv[lane] = 0;
+            if (lane == 0) {
+                s_nPick = nPick;
+                s_scanEnd = nPick == MW ? lastPick + 1 : min(pos, ns);      // every seed below scanEnd was examined
+            }
+        }
+        __syncthreads();
+        // ---- 2. grow the picked regions concurrently ----
+        if (w < s_nPick) {
+            const int pk0 = s_pickPk[w];
+            double regAngle;
+            const int n = grow_region<true>(c, pk0, (pk0 >> 16) * c.W + (pk0 & 0xFFFF), precTol, regAngle);
+            int hasSeg = 0;
+            if (!*(volatile int*)(s_inv + w) && n >= g.minRegSize) {
+                RectFit rf;
+                rect_fit<false>(c, s_sum[w], n, regAngle, prec, rf);
+                if (lane == 0) { s_seg[w][0] = rf.x1; s_seg[w][1] = rf.y1; s_seg[w][2] = rf.x2; s_seg[w][3] = rf.y2; }
+                hasSeg = 1;
+            }
+            if (lane == 0) { s_n[w] = n; s_hasSeg[w] = hasSeg; }
+        }
+        __syncthreads();
+        // ---- 3. commit in seed order (warp 0) ----
+        if (w == 0) {
+            const int nPick = s_nPick, scanEnd = s_scanEnd;
+            int pos = s_pos, nSeg = s_nSeg, stopPos = -1;
+            while (pos < scanEnd && stopPos < 0) {
+                const int p = pos + lane;
+                const bool inRange = p < scanEnd;
+                const int seed = inRange ? S[p] : -1;
+                const int bidx = inRange ? (seed >> 16) * c.PB + (seed & 0xFFFF) : 0;
+                int pickIdx = -1;
+                for (int k = 0; k < nPick; ++k) if (p == s_pickPos[k]) pickIdx = k;
+                unsigned done = 0u;
+                while (true) {
+                    const bool unused = inRange && !((done >> lane) & 1u) && !used_bit(c.used, bidx);
+                    const unsigned ev = __ballot_sync(0xffffffffu, unused);
+                    if (!ev) break;
+                    const int l = __ffs(ev) - 1;
+                    const int k = __shfl_sync(0xffffffffu, pickIdx, l);
+                    if (k < 0 || *(volatile int*)(s_inv + k)) { stopPos = pos + l; break; }     // skipped seed nobody swallowed / invalid region
+                    const int n = s_n[k];
+                    const int* Rk = regAll + ((size_t)blockIdx.x * MW + k) * npx;
+                    for (int i = lane; i < n; i += 32) {
+                        const int pk = Rk[i];
+                        const int qb = (pk >> 16) * c.PB + (pk & 0xFFFF);
+                        atomicOr(c.used + (qb >> 5), 1u << (qb & 31));
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                    if (s_hasSeg[k]) {
+                        if (lane == 0) {
+                            if (nSeg < g.segCap) {
+                                for (int q4 = 0; q4 < 4; ++q4) {
+                                    double v = s_seg[k][q4] + 0.5;
+                                    if (g.lsdScale != 1) v /= g.lsdScale;
+                                    out[nSeg * 4 + q4] = (float)v;
+                                }
+                            } else {
+                                atomicOr(err, 2);
+                            }
+                        }
+                        if (nSeg < g.segCap) ++nSeg;
+                    }
+                    done |= (2u << l) - 1u;
+                }
+                if (stopPos < 0) pos += 32;
+            }
+            if (lane == 0) { s_pos = stopPos >= 0 ? stopPos : scanEnd; s_nSeg = nSeg; }
+        }
+        __syncthreads();
+        // ---- 4. every region of the wave withdraws its claims (committed ones are in the bitmap now) ----
+        if (w < s_nPick) {
+            const int n = s_n[w];
+            for (int i = lane; i < n; i += 32) {
+                const int pk = c.R[i];
+                atomicCAS(c.owner + (pk >> 16) * c.PB + (pk & 0xFFFF), c.tag, PLF_FREE);
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) nSegsOut[img] = s_nSeg;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1016,6 +1196,10 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         if (g.refine >= 1)
             lsd_grow_kernel<true><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                       c->d_nSegs, c->d_err, imgFirst);
+        else if (nImg <= PLF_MW_MAX_IMG && c->d_owner)
+            // few images: several regions of each image in flight (a block of 8 warps per image)
+            lsd_grow_mw_kernel<<<nImg, 32 * MW, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_owner, c->d_regMW,
+                                                        c->d_segs, c->d_nSegs, c->d_err, imgFirst);
         else
             lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                        c->d_nSegs, c->d_err, imgFirst);

@@ -12,6 +12,7 @@
 #define PLF_EDGE 19               // EDGE_THRESHOLD, src/ORBextractor.cc:72
 #define PLF_MINB 16               // minBorder = EDGE_THRESHOLD-3, src/ORBextractor.cc:771
 #define PLF_NOTDEF (-1024.0f)
+#define PLF_MW_MAX_IMG 8          // launches of at most this many images use the multi-warp (several regions in flight) grower
 #define PLF_GRID_COLS 64          // FRAME_GRID_COLS, include/Frame.h:60
 #define PLF_GRID_ROWS 48          // FRAME_GRID_ROWS, include/Frame.h:59
 
@@ -118,6 +119,8 @@ struct plf_ctx {
     int* d_n2 = nullptr;             // [nImg][Hs][Ps] |g|^2 of defined pixels, 0 where undefined (seed ordering, rectangle weights)
     uint32_t* d_used = nullptr;      // [nImg][Hs][Ps/32] used bitmap of the region grower; undefined pixels start as used
     int* d_reg = nullptr;            // [nImg][Hs*Ws] region pixel list, packed y<<16|x (reused per region)
+    uint32_t* d_owner = nullptr;     // small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][Hs][Ps] owner tags of the current wave (PLF_FREE = none)
+    int* d_regMW = nullptr;          // small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][8][Hs*Ws] region lists, one per wave slot
     float* d_segs = nullptr;         // [nImg][segCap][4]
     int* d_nSegs = nullptr;          // [nImg]
     plf_keyline* d_kl = nullptr;     // [nImg][klCap]

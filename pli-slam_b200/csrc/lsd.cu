@@ -746,7 +746,8 @@ __global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const f
     __shared__ double s_sum[MW][3][33];
     __shared__ double s_seg[MW][4];
     __shared__ int s_pickPos[MW], s_pickPk[MW], s_n[MW], s_inv[MW], s_hasSeg[MW];
-    __shared__ int s_nPick, s_pos, s_scanEnd, s_nSeg;
+    __shared__ int s_nPick, s_pos, s_scanEnd, s_nSeg, s_segIdx[MW];
+    __shared__ unsigned s_committed;
     const int img = imgFirst + blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t npx = (size_t)g.Ws * g.Hs, npb = (size_t)g.Ps * g.Hs;
     GrowCtx c;
@@ -819,66 +820,77 @@ __global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const f
             if (lane == 0) { s_n[w] = n; s_hasSeg[w] = hasSeg; }
         }
         __syncthreads();
-        // ---- 3. commit in seed order (warp 0) ----
+        // ---- 3. decide, in seed order, which regions of the wave are committed (warp 0; registers only after the loads) ----
+        // A seed below scanEnd is skipped if it was used before the wave or lies in a region committed earlier in this
+        // wave (its owner tag is that region's: claims are still in place); a picked seed commits its region unless the
+        // region is invalid; anything else — a seed skipped for distance that nobody swallowed, an invalid region — ends
+        // the wave there.
         if (w == 0) {
             const int nPick = s_nPick, scanEnd = s_scanEnd;
             int pos = s_pos, nSeg = s_nSeg, stopPos = -1;
+            unsigned committed = 0u;                 // slots committed so far in this wave
             while (pos < scanEnd && stopPos < 0) {
                 const int p = pos + lane;
                 const bool inRange = p < scanEnd;
                 const int seed = inRange ? S[p] : -1;
                 const int bidx = inRange ? (seed >> 16) * c.PB + (seed & 0xFFFF) : 0;
+                const bool usedBefore = !inRange || used_bit(c.used, bidx);
+                const uint32_t tag = inRange ? c.owner[bidx] : PLF_FREE;
                 int pickIdx = -1;
                 for (int k = 0; k < nPick; ++k) if (p == s_pickPos[k]) pickIdx = k;
-                unsigned done = 0u;
-                while (true) {
-                    const bool unused = inRange && !((done >> lane) & 1u) && !used_bit(c.used, bidx);
-                    const unsigned ev = __ballot_sync(0xffffffffu, unused);
-                    if (!ev) break;
-                    const int l = __ffs(ev) - 1;
+                unsigned open = __ballot_sync(0xffffffffu, !usedBefore);
+                while (open) {
+                    const int l = __ffs(open) - 1;
+                    open &= open - 1u;
+                    const uint32_t tl = __shfl_sync(0xffffffffu, tag, l);
                     const int k = __shfl_sync(0xffffffffu, pickIdx, l);
-                    if (k < 0 || *(volatile int*)(s_inv + k)) { stopPos = pos + l; break; }     // skipped seed nobody swallowed / invalid region
-                    const int n = s_n[k];
-                    const int* Rk = regAll + ((size_t)blockIdx.x * MW + k) * npx;
-                    for (int i = lane; i < n; i += 32) {
-                        const int pk = Rk[i];
-                        const int qb = (pk >> 16) * c.PB + (pk & 0xFFFF);
-                        atomicOr(c.used + (qb >> 5), 1u << (qb & 31));
-                    }
-                    __threadfence_block();
-                    __syncwarp();
-                    if (s_hasSeg[k]) {
-                        if (lane == 0) {
-                            if (nSeg < g.segCap) {
-                                for (int q4 = 0; q4 < 4; ++q4) {
-                                    double v = s_seg[k][q4] + 0.5;
-                                    if (g.lsdScale != 1) v /= g.lsdScale;
-                                    out[nSeg * 4 + q4] = (float)v;
-                                }
-                            } else {
-                                atomicOr(err, 2);
-                            }
+                    if (k >= 0) {
+                        // (a pick whose seed was swallowed by an earlier committed region lost that pixel: it is invalid)
+                        if (*(volatile int*)(s_inv + k)) {
+                            if (tl != PLF_FREE && tl != (uint32_t)k + 1u && ((committed >> (tl - 1u)) & 1u)) continue;   // swallowed
+                            stopPos = pos + l;
+                            break;
                         }
-                        if (nSeg < g.segCap) ++nSeg;
+                        committed |= 1u << k;
+                        if (lane == 0) s_segIdx[k] = s_hasSeg[k] ? nSeg : -1;
+                        if (s_hasSeg[k]) ++nSeg;
+                    } else {
+                        if (tl != PLF_FREE && ((committed >> (tl - 1u)) & 1u)) continue;     // swallowed by a committed region
+                        stopPos = pos + l;                                                    // would have started its own region here
+                        break;
                     }
-                    done |= (2u << l) - 1u;
                 }
                 if (stopPos < 0) pos += 32;
             }
-            if (lane == 0) { s_pos = stopPos >= 0 ? stopPos : scanEnd; s_nSeg = nSeg; }
+            if (lane == 0) { s_pos = stopPos >= 0 ? stopPos : scanEnd; s_nSeg = nSeg; s_committed = committed; }
         }
         __syncthreads();
-        // ---- 4. every region of the wave withdraws its claims (committed ones are in the bitmap now) ----
+        // ---- 4. committed regions enter the bitmap and write their segment; every region withdraws its claims ----
         if (w < s_nPick) {
             const int n = s_n[w];
+            const bool commit = (s_committed >> w) & 1u;
             for (int i = lane; i < n; i += 32) {
                 const int pk = c.R[i];
-                atomicCAS(c.owner + (pk >> 16) * c.PB + (pk & 0xFFFF), c.tag, PLF_FREE);
+                const int qb = (pk >> 16) * c.PB + (pk & 0xFFFF);
+                if (commit) atomicOr(c.used + (qb >> 5), 1u << (qb & 31));
+                atomicCAS(c.owner + qb, c.tag, PLF_FREE);
+            }
+            if (commit && lane == 0 && s_segIdx[w] >= 0) {
+                const int si = s_segIdx[w];
+                if (si < g.segCap) {
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        double v = s_seg[w][q4] + 0.5;
+                        if (g.lsdScale != 1) v /= g.lsdScale;
+                        out[si * 4 + q4] = (float)v;
+                    }
+                } else {
+                    atomicOr(err, 2);
+                }
             }
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) nSegsOut[img] = s_nSeg;
+    if (threadIdx.x == 0) nSegsOut[img] = min(s_nSeg, g.segCap);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -212,10 +212,13 @@ int plf_launch_match_nnr(plf_ctx* c, const uint8_t* dA, int nA, const uint8_t* d
 int plf_set_cuda_error(cudaError_t e, const char* what, const char* file, int line);
 int plf_fail(int code, const char* msg);          // sets plf_last_error() and returns `code`
 
-// zero-initialised device allocation of n elements (at least one)
+// zero-initialised device allocation of n elements (at least one).  The memset runs on the legacy default stream, which
+// does not order with the contexts' non-blocking streams: it is waited for here, otherwise a kernel launched on the
+// context stream right after a lazy allocation can be overtaken by the memset and lose what it wrote.
 template <typename T>
 static inline cudaError_t dalloc(T** p, size_t n) {
     cudaError_t e = cudaMalloc((void**)p, (n > 0 ? n : 1) * sizeof(T));
     if (e == cudaSuccess) e = cudaMemset(*p, 0, (n > 0 ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
     return e;
 }

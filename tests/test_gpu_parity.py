@@ -480,5 +480,8 @@ def test_search_by_projection_frame_matches_oracle(plf, product, oracle, mode, c
         og, oo = occ0.copy(), occ0.copy()
         fg, mg, ng = f.search_by_projection_frame(q, og, 100, check, slot=b)
         fo, mo, no = o.search_by_projection_frame(q, oo, 100, check, slot=b)
-        assert ng == no and np.array_equal(fg, fo) and np.array_equal(mg, mo) and np.array_equal(og, oo)
+        assert np.array_equal(rg.kp_left[b, :n], ro.kp_left[b, :n]) and np.array_equal(rg.u_right[b, :n], ro.u_right[b, :n])
+        assert ng == no, (ng, no)
+        assert np.array_equal(fg, fo), np.nonzero(fg != fo)[0][:10]
+        assert np.array_equal(mg, mo) and np.array_equal(og, oo)
         assert no > 400

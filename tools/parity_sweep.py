@@ -1,6 +1,6 @@
 """Exact comparison of the CUDA path with the CPU oracle over many synthetic pairs (GPU box; the oracle is the checker).
 
-  python tools/parity_sweep.py [n_pairs] [first_seed] [kind] [lsd_refine] [W] [H]     kind: rect (default) | curvy
+  python tools/parity_sweep.py [n_pairs] [first_seed] [kind] [lsd_refine] [W] [H] [batch]     kind: rect (default) | curvy; batch <= 4 exercises the small-batch grower
 Prints, per output array, the number of pairs on which it differs from the oracle."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,7 +12,7 @@ KIND = sys.argv[3] if len(sys.argv) > 3 else "rect"
 REFINE = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 W = int(sys.argv[5]) if len(sys.argv) > 5 else 752
 H = int(sys.argv[6]) if len(sys.argv) > 6 else 480
-B = 64
+B = int(sys.argv[7]) if len(sys.argv) > 7 else 64
 kw = dict(width=W, height=H, max_batch=B, lsd_nfeatures=0, lsd_refine=REFINE)
 f = plf.Frontend(plf.load_product(), **kw)
 o = plf.Frontend(plf.load_oracle(), **kw)

@@ -322,7 +322,7 @@ static int create_buffers(plf_ctx* c, const plf_params* p, std::vector<PlfCell>&
             PLF_CUDA_OK(dalloc(&c->d_owner, nLat * (size_t)g.Ps * g.Hs));
             PLF_CUDA_OK(cudaMemset(c->d_owner, 0xFF, nLat * (size_t)g.Ps * g.Hs * sizeof(uint32_t)));
             PLF_CUDA_OK(cudaStreamSynchronize(0));
-            PLF_CUDA_OK(dalloc(&c->d_regMW, nLat * 8 * npx));
+            PLF_CUDA_OK(dalloc(&c->d_regMW, nLat * PLF_MW_WARPS * npx));
         }
         PLF_CUDA_OK(dalloc(&c->d_segs, nImg * (size_t)g.segCap * 4));
         PLF_CUDA_OK(dalloc(&c->d_nSegs, nImg));

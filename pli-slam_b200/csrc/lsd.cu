@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
 // The first unused seed of a wave is always picked and can never lose, so every wave commits at least one region.
 // Exactness: a committed region saw exactly the used pixels the sequential order gives it — pixels of earlier regions
 // it merely examined and rejected do not matter, pixels it accepted are contested through the owner map.
-#define MW 8
+#define MW PLF_MW_WARPS
 #define MW_SCAN 256
 #define MW_DIST 12
 __global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const float4* rec, const int* n2map, const int* seeds,

@@ -317,13 +317,6 @@ static int create_buffers(plf_ctx* c, const plf_params* p, std::vector<PlfCell>&
         PLF_CUDA_OK(dalloc(&c->d_n2, nImg * (size_t)g.Ps * g.Hs));
         PLF_CUDA_OK(dalloc(&c->d_used, nImg * (size_t)(g.Ps / 32) * g.Hs));
         PLF_CUDA_OK(dalloc(&c->d_reg, nImg * npx));
-        if (p->lsd_refine == 0) {          // the small-batch grower's owner map (all PLF_FREE) and per-slot region lists
-            const size_t nLat = std::min<size_t>(nImg, PLF_MW_MAX_IMG);
-            PLF_CUDA_OK(dalloc(&c->d_owner, nLat * (size_t)g.Ps * g.Hs));
-            PLF_CUDA_OK(cudaMemset(c->d_owner, 0xFF, nLat * (size_t)g.Ps * g.Hs * sizeof(uint32_t)));
-            PLF_CUDA_OK(cudaStreamSynchronize(0));
-            PLF_CUDA_OK(dalloc(&c->d_regMW, nLat * PLF_MW_WARPS * npx));
-        }
         PLF_CUDA_OK(dalloc(&c->d_segs, nImg * (size_t)g.segCap * 4));
         PLF_CUDA_OK(dalloc(&c->d_nSegs, nImg));
         PLF_CUDA_OK(dalloc(&c->d_klAll, nImg * (size_t)g.segCap));

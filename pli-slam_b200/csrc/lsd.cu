@@ -9,6 +9,7 @@
 // region is grown with the exact sequential acceptance rule, one warp per image.
 #include "plf_ctx.cuh"
 #include "blur.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -1168,6 +1169,21 @@ static void upload_lbd_tables(int device) {
     if (device < 64) s_tablesReady[device] = true;
 }
 
+// scratch of the small-batch grower, allocated the first time a small launch happens (a context that only ever runs large
+// batches never pays for it): owner map (all PLF_FREE) and one region list per wave slot, for up to PLF_MW_MAX_IMG images
+static int plf_ensure_mw_buffers(plf_ctx* c) {
+    if (c->d_owner && c->d_regMW) return 0;
+    const PlfGeom& g = c->g;
+    const size_t nLat = std::min<size_t>((size_t)c->nImgMax, PLF_MW_MAX_IMG);
+    const size_t npb = (size_t)g.Ps * g.Hs, npx = (size_t)g.Ws * g.Hs;
+    if (cudaMalloc((void**)&c->d_owner, nLat * npb * sizeof(uint32_t)) != cudaSuccess) { c->d_owner = nullptr; cudaGetLastError(); return 1; }
+    if (cudaMalloc((void**)&c->d_regMW, nLat * PLF_MW_WARPS * npx * sizeof(int)) != cudaSuccess) {
+        cudaFree(c->d_owner); c->d_owner = nullptr; c->d_regMW = nullptr; cudaGetLastError(); return 1;      // fall back to the sequential kernel
+    }
+    cudaMemsetAsync(c->d_owner, 0xFF, nLat * npb * sizeof(uint32_t), c->stream);
+    return 0;
+}
+
 int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     const PlfGeom& g = c->g;
     cudaStream_t s = c->stream;
@@ -1208,7 +1224,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         if (g.refine >= 1)
             lsd_grow_kernel<true><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                       c->d_nSegs, c->d_err, imgFirst);
-        else if (nImg <= PLF_MW_MAX_IMG && c->d_owner)
+        else if (nImg <= PLF_MW_MAX_IMG && plf_ensure_mw_buffers(c) == 0)
             // few images: several regions of each image in flight (a block of 8 warps per image)
             lsd_grow_mw_kernel<<<nImg, 32 * MW, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_owner, c->d_regMW,
                                                         c->d_segs, c->d_nSegs, c->d_err, imgFirst);

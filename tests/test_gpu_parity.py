@@ -485,3 +485,28 @@ def test_search_by_projection_frame_matches_oracle(plf, product, oracle, mode, c
         assert np.array_equal(fg, fo), np.nonzero(fg != fo)[0][:10]
         assert np.array_equal(mg, mo) and np.array_equal(og, oo)
         assert no > 400
+
+
+def test_large_batch_sequential_grower_matches_oracle(plf, product, oracle):
+    """Launches of more than 128 images use the one-warp-per-image region grower (the kernel the benchmark runs); smaller
+    ones use the multi-region grower.  72 pairs (144 images, 8 distinct pairs repeated) against the oracle, exactly, and
+    against the same pairs sent through a small batch."""
+    W, H = 752, 480
+    L8, R8 = plf.synth_batch(W, H, [101, 102, 103, 104, 105, 106, 107, 108])
+    idx = np.arange(72) % 8
+    f = plf.Frontend(product, max_batch=72, lsd_nfeatures=0)
+    o = plf.Frontend(oracle, max_batch=8, lsd_nfeatures=0)
+    rg, ro = f.frontend_batch(L8[idx], R8[idx]), o.frontend_batch(L8, R8)
+    small = plf.Frontend(product, max_batch=8, lsd_nfeatures=0).frontend_batch(L8, R8)
+    for b in range(72):
+        r = b % 8
+        for side in ("left", "right"):
+            nl = int(getattr(ro, "n_kl_" + side)[r])
+            assert int(getattr(rg, "n_kl_" + side)[b]) == nl and nl > 300
+            assert np.array_equal(getattr(rg, "kl_" + side)[b, :nl], getattr(ro, "kl_" + side)[r, :nl])
+            assert np.array_equal(getattr(rg, "ldesc_" + side)[b, :nl], getattr(ro, "ldesc_" + side)[r, :nl])
+            if b < 8:
+                assert np.array_equal(getattr(small, "kl_" + side)[b, :nl], getattr(ro, "kl_" + side)[r, :nl])
+        n, nl = int(ro.n_kp_left[r]), int(ro.n_kl_left[r])
+        assert np.array_equal(rg.kp_left[b, :n], ro.kp_left[r, :n]) and np.array_equal(rg.u_right[b, :n], ro.u_right[r, :n])
+        assert np.array_equal(rg.line_match12[b, :nl], ro.line_match12[r, :nl])

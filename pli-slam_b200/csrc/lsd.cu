@@ -332,6 +332,14 @@ __device__ __forceinline__ bool lsd_aligned(float thetaDeg, float aDeg, const Al
 // contradicts the prediction every lane has seen the true state, so those decisions are final; they are committed in
 // one SIMD step and the rest goes round again.  The angle drifts slowly, so one round usually settles a set:
 // ~100 + 9/accepted-pixel warp instructions per round instead of ~95 per accepted pixel.
+// speculative mode: has an earlier region of the wave taken one of my pixels?  The flags only ever go 0 -> 1 and are written
+// and polled with shared-memory atomics while the regions grow; the authoritative read is after the wave's barrier.
+__device__ __forceinline__ bool grow_is_invalid(const GrowCtx& c) {
+    int f = 0;
+    if (c.lane == 0) f = atomicOr(c.invalid + (c.tag - 1), 0);
+    return __shfl_sync(0xffffffffu, f, 0) != 0;
+}
+
 template <bool SPEC>
 __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int pk, const float4& r, const AlignTol& tol,
                                            const GrowCtx& c, unsigned dupAll, unsigned& accepted) {
@@ -390,11 +398,11 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
             } else {
                 // claim in the wave's owner map: the earlier seed (lower tag) wins a contested pixel, the loser is re-grown
                 const uint32_t old = atomicMin(c.owner + q, c.tag);
-                if (old < c.tag) c.invalid[c.tag - 1] = 1;
-                else if (old != PLF_FREE && old > c.tag) c.invalid[old - 1] = 1;
+                if (old < c.tag) atomicOr(c.invalid + (c.tag - 1), 1);
+                else if (old != PLF_FREE && old > c.tag) atomicOr(c.invalid + (old - 1), 1);
             }
         }
-        if (SPEC && __any_sync(0xffffffffu, *(volatile int*)(c.invalid + (c.tag - 1)) != 0)) { st.aborted = true; st.n += __popc(acc); return; }
+        if (SPEC && grow_is_invalid(c)) { st.aborted = true; st.n += __popc(acc); return; }
         st.n += __popc(acc);
         accepted |= acc;
         if (mm == 0u && v >= 0) {          // the spare lane holds the sums and the angle after all of A
@@ -431,8 +439,8 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
         if (!SPEC) atomicOr(c.used + (pb >> 5), 1u << (pb & 31));
         else {
             const uint32_t old = atomicMin(c.owner + pb, c.tag);
-            if (old < c.tag) c.invalid[c.tag - 1] = 1;
-            else if (old != PLF_FREE && old > c.tag) c.invalid[old - 1] = 1;
+            if (old < c.tag) atomicOr(c.invalid + (c.tag - 1), 1);
+            else if (old != PLF_FREE && old > c.tag) atomicOr(c.invalid + (old - 1), 1);
         }
     }
     st.regDeg = c.REC[p].x;
@@ -812,7 +820,7 @@ __global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const f
             double regAngle;
             const int n = grow_region<true>(c, pk0, (pk0 >> 16) * c.W + (pk0 & 0xFFFF), precTol, regAngle);
             int hasSeg = 0;
-            if (!*(volatile int*)(s_inv + w) && n >= g.minRegSize) {
+            if (!grow_is_invalid(c) && n >= g.minRegSize) {
                 RectFit rf;
                 rect_fit<false>(c, s_sum[w], n, regAngle, prec, rf);
                 if (lane == 0) { s_seg[w][0] = rf.x1; s_seg[w][1] = rf.y1; s_seg[w][2] = rf.x2; s_seg[w][3] = rf.y2; }

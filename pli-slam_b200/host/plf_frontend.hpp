@@ -13,6 +13,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/plf_b200.h"
 
@@ -196,6 +197,74 @@ public:
     }
 private:
     std::shared_ptr<plf::Context> ctx_;
+};
+
+// The frame-level pieces after the stereo matchers: Frame::AssignFeaturesToGrid / GetFeaturesInArea
+// (src/Frame.cc:451-482, 774-843), Frame::UnprojectStereo / backProjection (:1332-1358), Frame::ComputeBoW (:858-870) and the
+// two ORBmatcher::SearchByProjection overloads of the tracking thread (src/ORBmatcher.cc:44-130, 2179-2323).
+class FrameTail {
+public:
+    explicit FrameTail(std::shared_ptr<plf::Context> ctx, int slot = 0) : ctx_(ctx), slot_(slot) {}
+    // void Frame::AssignFeaturesToGrid(): keeps mGrid[64][48] as CSR
+    void AssignFeaturesToGrid() {
+        cellStart_.assign(PLF_GRID_COLS * PLF_GRID_ROWS + 1, 0);
+        cellIdx_.assign((size_t)plf_keypoint_capacity(ctx_->get()), -1);
+        plf::check(plf_feature_grid(ctx_->get(), slot_, 1, cellStart_.data(), cellIdx_.data(), (int)cellIdx_.size()), "plf_feature_grid");
+    }
+    // vector<size_t> Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel)
+    std::vector<size_t> GetFeaturesInArea(const std::vector<KeyPoint>& mvKeysUn, float x, float y, float r, int minLevel = -1,
+                                          int maxLevel = -1) const {
+        std::vector<int32_t> idx(mvKeysUn.size() + 1);
+        const int n = plf_features_in_area(mvKeysUn.data(), cellStart_.data(), cellIdx_.data(), ctx_->params.width, ctx_->params.height,
+                                           x, y, r, minLevel, maxLevel, idx.data(), (int)idx.size());
+        return std::vector<size_t>(idx.begin(), idx.begin() + n);
+    }
+    // cv::Mat Frame::UnprojectStereo(i) for every keypoint and Frame::backProjection for both ends of every line
+    void BackProject(const float Rwc[9], const float Ow[3], float fy, float cx, float cy, int N, int N_l, std::vector<float>& x3D,
+                     std::vector<double>& lines3D) {
+        x3D.assign((size_t)3 * N, 0.f);
+        lines3D.assign((size_t)6 * N_l, 0.0);
+        plf::check(plf_backproject(ctx_->get(), slot_, 1, Rwc, Ow, fy, cx, cy, N ? x3D.data() : nullptr, N, N_l ? lines3D.data() : nullptr, N_l),
+                   "plf_backproject");
+    }
+    // mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4) / the line vocabulary (which = 1)
+    void ComputeBoW(int which, int nFeatures, std::vector<std::pair<int32_t, double>>& bowVec,
+                    std::vector<std::pair<int32_t, std::vector<int32_t>>>& featVec, int levelsup = 4) {
+        const int n = nFeatures;
+        std::vector<int32_t> w((size_t)n + 1), nid((size_t)n + 1), bw((size_t)n + 1), fn((size_t)n + 1), fs((size_t)n + 2), ff((size_t)n + 1);
+        std::vector<double> v((size_t)n + 1), bv((size_t)n + 1);
+        bowVec.clear(); featVec.clear();
+        if (n <= 0) return;
+        plf::check(plf_bow_transform(ctx_->get(), which, slot_, 1, levelsup, w.data(), v.data(), nid.data(), n), "plf_bow_transform");
+        int nNodes = 0;
+        const int nWords = plf_bow_build(w.data(), v.data(), nid.data(), n, bw.data(), bv.data(), fn.data(), fs.data(), ff.data(), &nNodes);
+        for (int j = 0; j < nWords; ++j) bowVec.emplace_back(bw[j], bv[j]);
+        for (int j = 0; j < nNodes; ++j) featVec.emplace_back(fn[j], std::vector<int32_t>(ff.begin() + fs[j], ff.begin() + fs[j + 1]));
+    }
+    // int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th): match[i] = feature given to map point i or -1
+    int SearchByProjection(const std::vector<plf_proj_query>& mapPoints, float th, float mfNNratio, std::vector<uint8_t>& occupied,
+                           std::vector<int32_t>& match, int TH_HIGH = 100) {
+        match.assign(mapPoints.size(), -1);
+        int n = 0;
+        plf::check(plf_search_by_projection(ctx_->get(), slot_, mapPoints.data(), (int)mapPoints.size(), th, mfNNratio, TH_HIGH,
+                                            occupied.data(), match.data(), &n), "plf_search_by_projection");
+        return n;
+    }
+    // int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono, match12), projection done by the caller
+    int SearchByProjection(const std::vector<plf_frame_query>& lastFramePoints, bool mbCheckOrientation, std::vector<uint8_t>& occupied,
+                           std::vector<int32_t>& featQuery, std::vector<int32_t>& match12, int TH_HIGH = 100) {
+        featQuery.assign(occupied.size(), -1);
+        match12.assign(occupied.size(), -1);
+        int n = 0;
+        plf::check(plf_search_by_projection_frame(ctx_->get(), slot_, lastFramePoints.data(), (int)lastFramePoints.size(), TH_HIGH,
+                                                  mbCheckOrientation ? 1 : 0, occupied.data(), featQuery.data(), match12.data(), &n),
+                   "plf_search_by_projection_frame");
+        return n;
+    }
+private:
+    std::shared_ptr<plf::Context> ctx_;
+    int slot_;
+    std::vector<int32_t> cellStart_, cellIdx_;
 };
 
 }  // namespace ORB_SLAM3

@@ -509,3 +509,26 @@ def test_search_by_projection_frame_oracle_against_python(plf, oracle, mode, che
     assert nm > 150
     if check:
         assert (fq >= 0).sum() < 600 - 30          # the histogram removed the matches with the odd rotations
+
+
+def test_header_inlines_edge_cases(plf, oracle):
+    """The host inlines of include/plf_b200.h on their edges: a bag of words with nothing but stopped words or no
+    features at all, an area lookup whose window misses the image or covers all of it."""
+    o = plf.Frontend(oracle, max_batch=1)
+    bw, bv, fv = o.bow_build(np.array([3, 1, 3], np.int32), np.zeros(3), np.array([7, 7, 9], np.int32))
+    assert len(bw) == 0 and len(bv) == 0 and fv == {}
+    bw, bv, fv = o.bow_build(np.zeros(0, np.int32), np.zeros(0), np.zeros(0, np.int32))
+    assert len(bw) == 0 and fv == {}
+    bw, bv, fv = o.bow_build(np.array([5, 2, 5, 9], np.int32), np.array([1.0, 3.0, 0.5, 0.0]), np.array([40, 41, 40, 42], np.int32))
+    assert list(bw) == [2, 5] and list(bv) == [3.0 / 4.5, 1.5 / 4.5] and fv == {40: [0, 2], 41: [1]}
+    L, R = plf.synth_pair(752, 480, 4)
+    res = o.frontend_batch(L[None], R[None])
+    n = int(res.n_kp_left[0])
+    st, ix = o.feature_grid(0, 1)
+    kps = res.kp_left[0, :n]
+    assert len(o.features_in_area(kps, st[0], ix[0], -500.0, 100.0, 20.0)) == 0
+    assert len(o.features_in_area(kps, st[0], ix[0], 100.0, 5000.0, 20.0)) == 0
+    everything = o.features_in_area(kps, st[0], ix[0], 376.0, 240.0, 2000.0)
+    assert sorted(everything) == sorted(ix[0, :st[0, -1]].tolist()) and len(everything) >= n - 5
+    lvl = o.features_in_area(kps, st[0], ix[0], 376.0, 240.0, 2000.0, 2, 3)
+    assert len(lvl) > 0 and set(kps["octave"][lvl]) <= {2, 3}

@@ -1,0 +1,112 @@
+#!/usr/bin/env python3
+"""TEST INFRASTRUCTURE ONLY — builds oracle/_ref/libplf_ref.so from the REFERENCE'S OWN SOURCES where they lie under
+/root/reference (nothing of them is copied into this repository; oracle/_ref/ is git-ignored).
+
+What is compiled, unmodified:
+  whole files  src/ORBextractor.cc  src/LineExtractor.cc  src/LineMatcher.cpp  src/gridStructure.cpp
+               src/LineIterator.cpp  src/Config.cpp  Thirdparty/line_descriptor/src/LSDDetector_custom.cpp
+  line ranges  (written at build time to oracle/_ref/gen/, never committed)
+               src/Frame.cc:976-1307          ComputeStereoMatches, ComputeStereoMatches_Lines,
+                                              lineSegmentOverlapStereo, filterLineSegmentDisparity
+               src/ORBmatcher.cc:36-42,2495-2511   TH_HIGH / TH_LOW, DescriptorDistance
+               Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp:42-687,1026-1372
+                                              LBD: parameters, computeSobel, binaryConversion, computeImpl, computeLBD
+                                              (the rest of that file is the EDLine detector, dead on this path)
+against oracle/refshim/: a stand-in for the OpenCV / Eigen headers (neither is installed here) whose arithmetic
+primitives forward to the cv2-pinned restatements of oracle/cpp (prims.cpp, orb.cpp fast_window, lsd.cpp lsd_detect).
+The reference's own build system (cmake + OpenCV 3 + Eigen + Pangolin + DBoW2 + g2o) is not run.
+
+Flags follow the oracle: -O2 -ffp-contract=off (float expressions evaluated as written).
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("PLF_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+GEN = os.path.join(OUT, "gen")
+LIB = os.path.join(OUT, "libplf_ref.so")
+SHIM = os.path.join(HERE, "refshim")
+LD = os.path.join(REF, "Thirdparty", "line_descriptor")
+
+WHOLE = ["src/ORBextractor.cc", "src/LineExtractor.cc", "src/LineMatcher.cpp", "src/gridStructure.cpp",
+         "src/LineIterator.cpp", "src/Config.cpp", "Thirdparty/line_descriptor/src/LSDDetector_custom.cpp"]
+ORACLE_PRIMS = ["cpp/prims.cpp", "cpp/orb.cpp", "cpp/lsd.cpp"]   # pinned OpenCV primitives (orb/lsd also carry oracle logic, unused here)
+
+CXX = os.environ.get("CXX", "g++")
+BASE = ["-O2", "-std=c++14", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-fvisibility=hidden"]
+INC = ["-I", SHIM, "-I", os.path.join(REF, "include"), "-I", os.path.join(LD, "include"), "-I", os.path.join(LD, "src")]
+# src/ files that reach include/Frame.h in the reference see ref_types.h instead (Frame / ORBmatcher / MapLine stand-ins);
+# the line_descriptor library is compiled exactly as its own CMakeLists does: its own precomp header, nothing else
+# (no using-directives leak in - that decides e.g. which atan2 overload LSDDetector_custom.cpp:297 binds to).
+FRAME_SIDE = ["-DFRAME_H", "-DORBMATCHER_H", "-DMAPPOINT_H", "-DMAPLINE_H", "-DKEYFRAME_H",
+              "-include", os.path.join(SHIM, "ref_types.h")]
+
+
+def lines(path, a, b):
+    with open(os.path.join(REF, path), encoding="utf-8", errors="replace") as f:
+        ls = f.readlines()
+    return "".join(ls[a - 1:b])
+
+
+def generate():
+    os.makedirs(GEN, exist_ok=True)
+    frame = ("// GENERATED at build time from %s/src/Frame.cc:976-1307 and src/ORBmatcher.cc:36-42,2495-2511 - do not commit\n"
+             "namespace ORB_SLAM3 {\n" % REF
+             + lines("src/ORBmatcher.cc", 36, 42) + lines("src/ORBmatcher.cc", 2495, 2511)
+             + lines("src/Frame.cc", 976, 1307) + "\n}\n")
+    lbd = ("// GENERATED at build time from %s/Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp:42-687,1026-1372 - do not commit\n" % REF
+           + lines("Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp", 42, 687)
+           + lines("Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp", 1026, 1372)
+           + "\n// members of the EDLine half of the file, named by the ranges above but never reached on this path\n"
+           "int BinaryDescriptor::OctaveKeyLines( cv::Mat&, ScaleLines& ) { throw std::runtime_error(\"EDLine is not built\"); }\n"
+           "BinaryDescriptor::EDLineDetector::EDLineDetector() {}\n"
+           "BinaryDescriptor::EDLineDetector::~EDLineDetector() {}\n"
+           "}\n}\n")
+    for name, text in (("frame_ranges.cpp", frame), ("lbd_ranges.cpp", lbd)):
+        p = os.path.join(GEN, name)
+        if not os.path.exists(p) or open(p).read() != text:
+            with open(p, "w") as f:
+                f.write(text)
+    return [os.path.join(GEN, "frame_ranges.cpp"), os.path.join(GEN, "lbd_ranges.cpp")]
+
+
+def build(force=False):
+    if not os.path.isdir(os.path.join(REF, "src")):
+        if os.path.exists(LIB):
+            return LIB            # GPU box: the prebuilt library travelled with the snapshot
+        raise RuntimeError("reference tree not found at %s and no prebuilt %s" % (REF, LIB))
+    gen = generate()
+    srcs = [os.path.join(REF, s) for s in WHOLE] + gen + \
+           [os.path.join(SHIM, "cvshim.cpp"), os.path.join(SHIM, "ref_capi.cpp")] + \
+           [os.path.join(HERE, s) for s in ORACLE_PRIMS]
+    deps = srcs + [os.path.join(dp, f) for dp, _, fs in os.walk(SHIM) for f in fs] + \
+           [os.path.join(HERE, "cpp", f) for f in os.listdir(os.path.join(HERE, "cpp")) if f.endswith(".h")] + [__file__]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+        return LIB
+    objdir = os.path.join(OUT, "obj")
+    os.makedirs(objdir, exist_ok=True)
+
+    def cc(src):
+        obj = os.path.join(objdir, os.path.basename(src) + ".o")
+        if src.startswith(HERE + os.sep + "cpp"):      # the oracle's own files: no reference headers, C++17
+            flags = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-fvisibility=hidden",
+                     "-DPLF_ORACLE_BUILD"]
+        elif "line_descriptor" in src or src.endswith("lbd_ranges.cpp") or src.endswith("cvshim.cpp") \
+                or os.path.basename(src) in ("gridStructure.cpp", "LineIterator.cpp", "Config.cpp"):
+            flags = BASE + INC
+        else:
+            flags = BASE + INC + FRAME_SIDE
+        subprocess.check_call([CXX] + flags + ["-c", src, "-o", obj])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(cc, srcs))
+    subprocess.check_call([CXX, "-shared", "-o", LIB] + objs + ["-Wl,-Bsymbolic", "-lpthread"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

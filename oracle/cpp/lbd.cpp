@@ -45,8 +45,8 @@ void lbd_compute(const Img8& img, const std::vector<plf_keyline>& kls, std::vect
         const float midX = (float)(0.5 * (kl.sPointInOctaveX + kl.ePointInOctaveX));
         const float midY = (float)(0.5 * (kl.sPointInOctaveY + kl.ePointInOctaveY));
         float dL[2], dO[2];
-        dL[0] = (float)std::cos((double)kl.angle);
-        dL[1] = (float)std::sin((double)kl.angle);
+        dL[0] = ref_cosf(kl.angle);   // cos( pSingleLine->direction ) on a float, :1134
+        dL[1] = ref_sinf(kl.angle);
         dO[0] = -dL[1];
         dO[1] = dL[0];
         float sCorX0 = -dL[0] * halfWidth + dL[1] * halfHeight + midX;

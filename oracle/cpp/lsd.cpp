@@ -291,9 +291,54 @@ void lsd_detect(const LsdConfig& c, const Img8& img, LsdState& st) {
 }
 
 // cv::LineIterator(img, Point2f, Point2f).count for endpoints inside the image.
-int line_iterator_count(float x1, float y1, float x2, float y2) {
-    int ax = cv_roundf(x1), ay = cv_roundf(y1), bx = cv_roundf(x2), by = cv_roundf(y2);
-    return std::max(std::abs(bx - ax), std::abs(by - ay)) + 1;
+// cv::clipLine(Size(W, H), pt1, pt2) (OpenCV imgproc/drawing.cpp; restated from the published algorithm and pinned to
+// cv2.clipLine in tests/test_oracle_cv2.py): Cohen-Sutherland on 64-bit integers, the intersection offsets truncated
+// toward zero, the second end point clipped against the ALREADY MOVED first one.
+bool clip_line(int W, int H, long long& x1, long long& y1, long long& x2, long long& y2) {
+    const long long right = W - 1, bottom = H - 1;
+    if (W <= 0 || H <= 0) return false;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        long long a;
+        if (c1 & 12) {
+            a = c1 < 8 ? 0 : bottom;
+            x1 += (long long)((double)(a - y1) * (double)(x2 - x1) / (double)(y2 - y1));
+            y1 = a;
+            c1 = (x1 < 0) + (x1 > right) * 2;
+        }
+        if (c2 & 12) {
+            a = c2 < 8 ? 0 : bottom;
+            x2 += (long long)((double)(a - y2) * (double)(x2 - x1) / (double)(y2 - y1));
+            y2 = a;
+            c2 = (x2 < 0) + (x2 > right) * 2;
+        }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) {
+                a = c1 == 1 ? 0 : right;
+                y1 += (long long)((double)(a - x1) * (double)(y2 - y1) / (double)(x2 - x1));
+                x1 = a;
+                c1 = 0;
+            }
+            if (c2) {
+                a = c2 == 1 ? 0 : right;
+                y2 += (long long)((double)(a - x2) * (double)(y2 - y1) / (double)(x2 - x1));
+                x2 = a;
+                c2 = 0;
+            }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+
+// cv::LineIterator(img, Point2f p1, Point2f p2).count, 8-connected (LSDDetector_custom.cpp:295-296): end points rounded
+// half-to-even (Point2f -> Point saturate_cast), clipped to the image when one lies outside - which happens: the clamp
+// of checkLineExtremes leaves x in [W-0.5, W) and that rounds to W - and 0 when the clipped line is empty.
+int line_iterator_count(float x1, float y1, float x2, float y2, int W, int H) {
+    long long ax = cv_roundf(x1), ay = cv_roundf(y1), bx = cv_roundf(x2), by = cv_roundf(y2);
+    if (ax < 0 || ax >= W || bx < 0 || bx >= W || ay < 0 || ay >= H || by < 0 || by >= H)
+        if (!clip_line(W, H, ax, ay, bx, by)) return 0;
+    return (int)std::max(std::llabs(bx - ax), std::llabs(by - ay)) + 1;
 }
 
 // LSDDetector_custom.cpp:76-102,268-308 then src/LineExtractor.cc:56-65
@@ -315,8 +360,8 @@ void lines_to_keylines(const std::vector<float>& segs, int w, int h, double min_
         kl.startPointX = e[0]; kl.startPointY = e[1]; kl.endPointX = e[2]; kl.endPointY = e[3];
         kl.sPointInOctaveX = e[0]; kl.sPointInOctaveY = e[1]; kl.ePointInOctaveX = e[2]; kl.ePointInOctaveY = e[3];
         kl.lineLength = (float)length;
-        kl.numOfPixels = line_iterator_count(e[0], e[1], e[2], e[3]);
-        kl.angle = (float)std::atan2((double)(kl.endPointY - kl.startPointY), (double)(kl.endPointX - kl.startPointX));
+        kl.numOfPixels = line_iterator_count(e[0], e[1], e[2], e[3], w, h);
+        kl.angle = ref_atan2f(kl.endPointY - kl.startPointY, kl.endPointX - kl.startPointX);   // atan2 on floats, :297
         kl.class_id = ++class_counter;
         kl.octave = 0;
         kl.size = (kl.endPointX - kl.startPointX) * (kl.endPointY - kl.startPointY);

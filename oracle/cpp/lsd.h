@@ -37,6 +37,7 @@ void lines_to_keylines(const std::vector<float>& segs, int w, int h, double min_
                        std::vector<plf_keyline>& kls);
 void lbd_compute(const Img8& img, const std::vector<plf_keyline>& kls, std::vector<float>& lbd72,
                  std::vector<uint8_t>& desc);
-int line_iterator_count(float x1, float y1, float x2, float y2);
+bool clip_line(int W, int H, long long& x1, long long& y1, long long& x2, long long& y2);
+int line_iterator_count(float x1, float y1, float x2, float y2, int W, int H);
 
 }  // namespace plfo

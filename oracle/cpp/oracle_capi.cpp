@@ -772,6 +772,54 @@ PLF_API int plf_cpu_prim_lsd(const uint8_t* src, int w, int h, double scale, int
     return PLF_OK;
 }
 
+// function-level entry points used by tests/test_oracle_ref.py to pin the restated reference-owned logic against the
+// reference's own code (oracle/_ref)
+PLF_API int plf_cpu_prim_octree(const float* xyr, int n, int minX, int maxX, int minY, int maxY, int N, float* out, int cap, int* nout) {
+    std::vector<Cand> in(n), res;
+    for (int i = 0; i < n; ++i) in[i] = Cand{xyr[3 * i], xyr[3 * i + 1], xyr[3 * i + 2]};
+    distribute_octree(in, minX, maxX, minY, maxY, N, res);
+    if (nout) *nout = (int)res.size();
+    if ((int)res.size() > cap) return PLF_ERR_INVALID;
+    for (size_t i = 0; i < res.size(); ++i) { out[3 * i] = res[i].x; out[3 * i + 1] = res[i].y; out[3 * i + 2] = res[i].resp; }
+    return PLF_OK;
+}
+PLF_API int plf_cpu_prim_lbd(const uint8_t* src, int w, int h, const plf_keyline* kls, int n, float* lbd72, uint8_t* desc) {
+    Img8 s(w, h);
+    std::memcpy(s.d.data(), src, (size_t)w * h);
+    std::vector<plf_keyline> v(kls, kls + n);
+    std::vector<float> f;
+    std::vector<uint8_t> d;
+    lbd_compute(s, v, f, d);
+    if (lbd72) std::memcpy(lbd72, f.data(), f.size() * 4);
+    if (desc) std::memcpy(desc, d.data(), d.size());
+    return PLF_OK;
+}
+PLF_API int plf_cpu_prim_stereo_lines(const plf_params* p, int W, int H, const plf_keyline* klL, int nL, const uint8_t* dL,
+                                      const plf_keyline* klR, int nR, const uint8_t* dR, float* disp_se, double* le, int32_t* m12) {
+    LineMatchConfig mc;
+    mc.best_lr_matches = p->best_lr_matches; mc.matching_s_ws = p->matching_s_ws; mc.min_ratio_12_l = p->min_ratio_12_l;
+    mc.line_sim_th = p->line_sim_th; mc.min_disp = p->min_disp; mc.line_horiz_th = p->line_horiz_th;
+    mc.stereo_overlap_th = p->stereo_overlap_th; mc.ls_min_disp_ratio = p->ls_min_disp_ratio;
+    std::vector<plf_keyline> a(klL, klL + nL), b(klR, klR + nR);
+    std::vector<uint8_t> da(dL, dL + (size_t)nL * 32), db(dR, dR + (size_t)nR * 32);
+    std::vector<float> disp;
+    std::vector<double> l;
+    std::vector<int> m;
+    stereo_match_lines(mc, W, H, a, da, b, db, disp, l, m);
+    std::memcpy(disp_se, disp.data(), disp.size() * 4);
+    std::memcpy(le, l.data(), l.size() * 8);
+    for (int i = 0; i < nL; ++i) m12[i] = m[i];
+    return PLF_OK;
+}
+PLF_API int plf_cpu_set_float_libm(int on) { int old = g_float_libm; g_float_libm = on != 0; return old; }
+PLF_API int plf_cpu_prim_clip_line(int W, int H, long long* pts4) {
+    return clip_line(W, H, pts4[0], pts4[1], pts4[2], pts4[3]) ? 1 : 0;
+}
+PLF_API int plf_cpu_prim_line_iterator_count(float x1, float y1, float x2, float y2, int W, int H) {
+    return line_iterator_count(x1, y1, x2, y2, W, H);
+}
+PLF_API int plf_cpu_prim_hamming(const uint8_t* a, const uint8_t* b) { return hamming256(a, b); }
+
 }  // extern "C"
 
 namespace plfo { void lsd_stats(const LsdConfig& c, const Img8& img, long long out[8]); }

@@ -80,12 +80,28 @@ void fast_window(const Img8& img, int x0, int y0, int x1, int y1, int th, std::v
     const int cols = x1 - x0, rows = y1 - y0;
     if (cols < 7 || rows < 7) return;
     const int aw = cols - 6, ah = rows - 6;          // detection area
-    std::vector<int> sc((size_t)aw * ah);
-    for (int i = 0; i < ah; ++i)
+    std::vector<int> sc((size_t)aw * ah, 0);
+    for (int i = 0; i < ah; ++i) {
+        const uint8_t* r0 = img.row(y0 + 3 + i);
         for (int j = 0; j < aw; ++j) {
-            int s = fast_score(img, x0 + 3 + j, y0 + 3 + i);
+            // Early reject (the high-speed test every FAST implementation starts with): a 9-arc of the 16-ring holds
+            // at least one pixel of each opposite pair (k, k+8), so a corner at threshold th needs, in EVERY pair, a
+            // pixel brighter than p+th (bright corner) or in every pair one darker than p-th (dark corner).  A
+            // necessary condition only: survivors get the full score and the `>= th` test, so the list is unchanged.
+            const int x = x0 + 3 + j, y = y0 + 3 + i;
+            const int p = r0[x], hi = p + th, lo = p - th;
+            bool bright = true, dark = true;
+            for (int k = 0; k < 8 && (bright || dark); ++k) {
+                const int a = img.at(y + kCircle[k][1], x + kCircle[k][0]);
+                const int b = img.at(y + kCircle[k + 8][1], x + kCircle[k + 8][0]);
+                bright = bright && (a > hi || b > hi);
+                dark = dark && (a < lo || b < lo);
+            }
+            if (!bright && !dark) continue;
+            int s = fast_score(img, x, y);
             sc[(size_t)i * aw + j] = (s >= th) ? s : 0;   // non-corners at this threshold score 0
         }
+    }
     for (int i = 0; i < ah; ++i)
         for (int j = 0; j < aw; ++j) {
             int s = sc[(size_t)i * aw + j];
@@ -272,7 +288,7 @@ void orb_descriptor(const Img8& blur, int x, int y, float angleDeg, uint8_t* des
     // Declared oracle rule: cosf/sinf are taken as correctly rounded, i.e. the double libm result rounded to float.
     // glibc's cosf differs from that by 1 ulp for ~0.9 % of arguments and its ifunc variant depends on the host CPU,
     // which would make the oracle machine-dependent.
-    float a = (float)std::cos((double)angle), b = (float)std::sin((double)angle);
+    float a = ref_cosf(angle), b = ref_sinf(angle);   // (float)cos(angle) on a float under `using namespace std`, :112
     const int* pat = kPattern;
     for (int i = 0; i < 32; ++i, pat += 32) {
         int val = 0;

@@ -5,6 +5,12 @@
 
 namespace plfo {
 
+int g_float_libm = 0;
+float ref_cosf(float x) { return g_float_libm ? ::cosf(x) : (float)std::cos((double)x); }
+float ref_sinf(float x) { return g_float_libm ? ::sinf(x) : (float)std::sin((double)x); }
+float ref_atan2f(float y, float x) { return g_float_libm ? ::atan2f(y, x) : (float)std::atan2((double)y, (double)x); }
+
+
 const int TAPS_ORB7[7] = {18, 34, 48, 56, 48, 34, 18};
 const int TAPS_LBD5[5] = {14, 62, 104, 62, 14};
 const int TAPS_LSD7[7] = {0, 1, 42, 170, 42, 1, 0};

@@ -59,6 +59,18 @@ void sobel3_16s(const Img8& src, Img16& dx, Img16& dy);
 // Examples/Stereo/stereo_euroc.cc:166-167), restated from OpenCV's fixed-point path; dst has the size of the maps.
 void remap_linear_u8(const Img8& src, Img8& dst, const float* mapx, const float* mapy, int dw, int dh);
 
+// The reference calls cos / sin / atan2 on FLOAT operands at three places of its own code (src/ORBextractor.cc:112,
+// LSDDetector_custom.cpp:297, binary_descriptor_custom.cpp:1134-1135); with GCC >= 6 these bind to the float overloads,
+// i.e. to the cosf / sinf / atan2f of whatever libm the binary meets at run time — not correctly rounded before glibc
+// 2.41, and CPU-dependent through ifunc variants.  The oracle DECLARES the correctly rounded value (double libm rounded
+// to float; what glibc >= 2.41 returns) — mode 0, the only mode the product is compared with.  Mode 1 calls this
+// machine's float libm instead: "the reference as built here", which tests/test_oracle_ref.py uses to show that the
+// libm rounding is the ONLY difference between the oracle and the reference's own object code.
+extern int g_float_libm;
+float ref_cosf(float x);
+float ref_sinf(float x);
+float ref_atan2f(float y, float x);
+
 extern const int TAPS_ORB7[7];   // 7x7 sigma 2   : 18 34 48 56 48 34 18
 extern const int TAPS_LBD5[5];   // 5x5 sigma 1   : 14 62 104 62 14
 extern const int TAPS_LSD7[7];   // 7x7 sigma 0.6 : 0 1 42 170 42 1 0

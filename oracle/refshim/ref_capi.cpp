@@ -1,0 +1,293 @@
+// TEST INFRASTRUCTURE ONLY — C entry points of oracle/_ref/libplf_ref.so: the REFERENCE'S OWN frontend code (compiled
+// from /root/reference by oracle/build_ref.py, nothing of it copied into this repository) behind plain-C calls, so that
+// tests/test_oracle_ref.py can pin the restated oracle (oracle/cpp) to it.  This file only marshals arrays in and
+// out of the reference's classes; it contains no frontend logic of its own.
+//
+// Heap addresses: DistributeOctTree breaks size ties by ExtractorNode* (src/ORBextractor.cc:682), i.e. by where the
+// std::list nodes happen to live.  ref_arena(1) serves exactly the list-node allocations of a call from a bump arena
+// (monotonically increasing addresses, the "most recently created node first" rule the oracle declares); ref_arena(0)
+// leaves them to malloc (whatever glibc does on this machine).
+#include "ref_types.h"
+#include <cstdlib>
+#include <new>
+#include <string>
+
+using namespace ORB_SLAM3;
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+// ---------------------------------------------------------------------------------------------------------------
+// bump arena for std::list<ExtractorNode> nodes
+namespace {
+struct ListNodeProbe { void* a; void* b; ExtractorNode n; };   // layout of std::_List_node<ExtractorNode>
+const size_t kNodeSize = sizeof(ListNodeProbe);
+const size_t kArenaCap = (size_t)256 << 20;
+char* g_arena = nullptr;
+size_t g_off = 0;
+bool g_arena_enabled = true;
+thread_local bool g_in_call = false;
+std::string g_err;
+
+struct CallScope {
+    CallScope() { g_off = 0; g_in_call = true; }
+    ~CallScope() { g_in_call = false; }
+};
+inline bool in_arena(void* p) { return g_arena && (char*)p >= g_arena && (char*)p < g_arena + kArenaCap; }
+}  // namespace
+
+void* operator new(size_t n) {
+    if (g_in_call && g_arena_enabled && n == kNodeSize) {
+        if (!g_arena) g_arena = (char*)std::malloc(kArenaCap);
+        size_t a = (g_off + 15) & ~(size_t)15;
+        if (g_arena && a + n <= kArenaCap) { g_off = a + n; return g_arena + a; }
+    }
+    void* p = std::malloc(n ? n : 1);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+void operator delete(void* p) noexcept { if (p && !in_arena(p)) std::free(p); }
+void operator delete(void* p, size_t) noexcept { if (p && !in_arena(p)) std::free(p); }
+
+namespace {
+
+struct OrbPeek : public ORBextractor {
+    using ORBextractor::ORBextractor;
+    std::vector<cv::KeyPoint> octree(const std::vector<cv::KeyPoint>& v, int minX, int maxX, int minY, int maxY, int N) {
+        return DistributeOctTree(v, minX, maxX, minY, maxY, N, 0);
+    }
+    const std::vector<int>& quotas() const { return mnFeaturesPerLevel; }
+    const std::vector<int>& umaxTable() const { return umax; }
+};
+
+OrbPeek* g_orb[2] = {nullptr, nullptr};
+Frame g_frame;
+
+cv::Mat wrap_u8(const uint8_t* p, int w, int h, int stride) { return cv::Mat(h, w, CV_8UC1, (void*)p, (size_t)stride); }
+cv::Mat wrap_desc(const uint8_t* p, int n) { return cv::Mat(n, 32, CV_8UC1, (void*)p, 32); }
+
+template <typename F> int guarded(F f) {
+    try { return f(); }
+    catch (const std::exception& e) { g_err = e.what(); return -1000; }
+    catch (...) { g_err = "unknown exception"; return -1001; }
+}
+
+}  // namespace
+
+REF_API const char* ref_last_error() { return g_err.c_str(); }
+REF_API int ref_arena(int on) { g_arena_enabled = on != 0; return (int)kNodeSize; }
+
+// Config singleton of the reference (include/Config.h, src/Config.cpp): v[] = hasLines, bestLRMatches, matchingSWs,
+// minRatio12L, lineSimTh, minDisp, lineHorizTh, stereoOverlapTh, lsMinDispRatio, minRatio12P, lrInParallel,
+// lsdNFeatures, lsdRefine, lsdScale, lsdSigmaScale, lsdQuant, lsdAngTh, lsdLogEps, lsdDensityTh, lsdNBins, minLineLength
+static void config_read(double* v) {
+    v[0] = Config::hasLines(); v[1] = Config::bestLRMatches(); v[2] = Config::matchingSWs(); v[3] = Config::minRatio12L();
+    v[4] = Config::lineSimTh(); v[5] = Config::minDisp(); v[6] = Config::lineHorizTh(); v[7] = Config::stereoOverlapTh();
+    v[8] = Config::lsMinDispRatio(); v[9] = Config::minRatio12P(); v[10] = Config::lrInParallel();
+    v[11] = Config::lsdNFeatures(); v[12] = Config::lsdRefine(); v[13] = Config::lsdScale(); v[14] = Config::lsdSigmaScale();
+    v[15] = Config::lsdQuant(); v[16] = Config::lsdAngTh(); v[17] = Config::lsdLogEps(); v[18] = Config::lsdDensityTh();
+    v[19] = Config::lsdNBins(); v[20] = Config::minLineLength();
+}
+REF_API int ref_config_get(double* v21) { return guarded([&] { config_read(v21); return 0; }); }
+REF_API int ref_config_load(const char* yaml, double* v21) {
+    return guarded([&] { Config::loadFromFile(yaml); config_read(v21); return 0; });
+}
+REF_API int ref_config_set(const double* v) {
+    return guarded([&] {
+        Config::hasLines() = v[0] != 0; Config::bestLRMatches() = v[1] != 0; Config::matchingSWs() = (int)v[2];
+        Config::minRatio12L() = v[3]; Config::lineSimTh() = v[4]; Config::minDisp() = v[5]; Config::lineHorizTh() = v[6];
+        Config::stereoOverlapTh() = v[7]; Config::lsMinDispRatio() = v[8]; Config::minRatio12P() = v[9];
+        Config::lrInParallel() = v[10] != 0;
+        return 0;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ORBextractor (src/ORBextractor.cc, whole file)
+REF_API int ref_orb_create(int side, int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
+    return guarded([&] {
+        delete g_orb[side];
+        g_orb[side] = new OrbPeek(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+        return 0;
+    });
+}
+REF_API int ref_orb_tables(int side, float* scale, float* invScale, float* sigma2, float* invSigma2, int* quotas, int* umax16) {
+    return guarded([&] {
+        OrbPeek* e = g_orb[side];
+        int n = e->GetLevels();
+        std::vector<float> a = e->GetScaleFactors(), b = e->GetInverseScaleFactors(), c = e->GetScaleSigmaSquares(),
+                           d = e->GetInverseScaleSigmaSquares();
+        for (int i = 0; i < n; i++) { scale[i] = a[i]; invScale[i] = b[i]; sigma2[i] = c[i]; invSigma2[i] = d[i];
+                                      quotas[i] = e->quotas()[i]; }
+        for (int i = 0; i < 16; i++) umax16[i] = e->umaxTable()[i];
+        return n;
+    });
+}
+// ORBextractor::operator(): returns monoIndex (or -1 for an empty image); *n = keypoints written.
+REF_API int ref_orb_extract(int side, const uint8_t* img, int w, int h, int stride, int lap0, int lap1,
+                            cv::KeyPoint* kp_out, uint8_t* desc_out, int cap, int* n) {
+    return guarded([&] {
+        CallScope scope;
+        cv::Mat im = (img && w > 0 && h > 0) ? wrap_u8(img, w, h, stride) : cv::Mat();
+        std::vector<cv::KeyPoint> kps;
+        cv::Mat desc;
+        std::vector<int> lap = {lap0, lap1};
+        int mono = (*g_orb[side])(im, cv::Mat(), kps, desc, lap);
+        *n = (int)kps.size();
+        if (*n > cap) throw std::runtime_error("ref_orb_extract: capacity");
+        for (int i = 0; i < *n; i++) { kp_out[i] = kps[i]; memcpy(desc_out + 32 * i, desc.ptr(i), 32); }
+        return mono;
+    });
+}
+REF_API int ref_orb_level(int side, int level, uint8_t* out, int cap, int* w, int* h) {
+    return guarded([&] {
+        const cv::Mat& m = g_orb[side]->mvImagePyramid[level];
+        *w = m.cols; *h = m.rows;
+        if (m.cols * m.rows > cap) throw std::runtime_error("ref_orb_level: capacity");
+        for (int y = 0; y < m.rows; y++) memcpy(out + (size_t)y * m.cols, m.ptr(y), (size_t)m.cols);
+        return 0;
+    });
+}
+// ORBextractor::DistributeOctTree on a caller-supplied candidate list (x, y, response triples).
+REF_API int ref_octree(int side, const float* xyr, int n, int minX, int maxX, int minY, int maxY, int N, float* out, int cap) {
+    return guarded([&] {
+        CallScope scope;
+        std::vector<cv::KeyPoint> v(n);
+        for (int i = 0; i < n; i++) v[i] = cv::KeyPoint(xyr[3 * i], xyr[3 * i + 1], 7.f, -1.f, xyr[3 * i + 2]);
+        std::vector<cv::KeyPoint> r = g_orb[side]->octree(v, minX, maxX, minY, maxY, N);
+        if ((int)r.size() > cap) throw std::runtime_error("ref_octree: capacity");
+        for (size_t i = 0; i < r.size(); i++) { out[3 * i] = r[i].pt.x; out[3 * i + 1] = r[i].pt.y; out[3 * i + 2] = r[i].response; }
+        return (int)r.size();
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Lineextractor::operator() (src/LineExtractor.cc whole file -> LSDDetector_custom.cpp whole file -> LBD ranges)
+REF_API int ref_line_extract(const uint8_t* img, int w, int h, int stride, int nfeatures, double min_line_length, int refine,
+                             double scale, double sigma_scale, double quant, double ang_th, double log_eps,
+                             double density_th, int n_bins, KeyLine* kl_out, uint8_t* desc_out, int cap) {
+    return guarded([&] {
+        Lineextractor ex(nfeatures, min_line_length, refine, scale, sigma_scale, quant, ang_th, log_eps, density_th, n_bins);
+        std::vector<KeyLine> kls;
+        cv::Mat desc;
+        ex(wrap_u8(img, w, h, stride), cv::Mat(), kls, desc);
+        if ((int)kls.size() > cap) throw std::runtime_error("ref_line_extract: capacity");
+        for (size_t i = 0; i < kls.size(); i++) { kl_out[i] = kls[i]; memcpy(desc_out + 32 * i, desc.ptr((int)i), 32); }
+        return (int)kls.size();
+    });
+}
+// BinaryDescriptor::compute on caller-supplied KeyLines: 72-float LBD (returnFloatDescr) and the 32-byte binary form.
+REF_API int ref_lbd(const uint8_t* img, int w, int h, int stride, const KeyLine* kls, int n, float* lbd72, uint8_t* desc) {
+    return guarded([&] {
+        cv::Ptr<BinaryDescriptor> lbd = BinaryDescriptor::createBinaryDescriptor();
+        std::vector<KeyLine> v(kls, kls + n);
+        cv::Mat im = wrap_u8(img, w, h, stride), d, f;
+        if (desc) { lbd->compute(im, v, d, false); for (int i = 0; i < n; i++) memcpy(desc + 32 * i, d.ptr(i), 32); }
+        if (lbd72) { lbd->compute(im, v, f, true); for (int i = 0; i < n; i++) memcpy(lbd72 + 72 * i, f.ptr(i), 72 * 4); }
+        return n;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Frame::ComputeStereoMatches (src/Frame.cc:976-1154) on the pyramids the two extractors hold from their last call.
+REF_API int ref_stereo_points(float bf, float fx, const cv::KeyPoint* kpL, int nL, const uint8_t* dL, const cv::KeyPoint* kpR,
+                              int nR, const uint8_t* dR, float* uRight, float* depth) {
+    return guarded([&] {
+        if (nL == 0) return 0;
+        Frame& F = g_frame;
+        F.mpORBextractorLeft = g_orb[0]; F.mpORBextractorRight = g_orb[1];
+        F.mvScaleFactors = g_orb[0]->GetScaleFactors(); F.mvInvScaleFactors = g_orb[0]->GetInverseScaleFactors();
+        F.mbf = bf; F.mb = bf / fx;        // src/Frame.cc:1006 reads mb before :197 sets it; declared rule mb := mbf/fx
+        F.N = nL;
+        F.mvKeys.assign(kpL, kpL + nL); F.mvKeysRight.assign(kpR, kpR + nR);
+        F.mDescriptors = wrap_desc(dL, nL).clone(); F.mDescriptorsRight = wrap_desc(dR, nR).clone();
+        F.ComputeStereoMatches();
+        for (int i = 0; i < nL; i++) { uRight[i] = F.mvuRight[i]; depth[i] = F.mvDepth[i]; }
+        return 0;
+    });
+}
+
+// Frame::ComputeStereoMatches_Lines (src/Frame.cc:1156-1307) -> matchGrid (src/LineMatcher.cpp, whole file) ->
+// GridStructure / LineIterator (src/gridStructure.cpp, src/LineIterator.cpp, whole files).  matchGrid's matches_12 is
+// a local of the reference function; it is recovered by a second, direct call with the same inputs.
+REF_API int ref_stereo_lines(int W, int H, const KeyLine* klL, int nL, const uint8_t* dL, const KeyLine* klR, int nR,
+                             const uint8_t* dR, float* disp_se, double* le) {
+    return guarded([&] {
+        Frame& F = g_frame;
+        F.inv_width = FRAME_GRID_COLS / static_cast<double>(W);     // src/Frame.cc:109-110
+        F.inv_height = FRAME_GRID_ROWS / static_cast<double>(H);
+        F.mvKeys_Line.assign(klL, klL + nL); F.mvKeysRight_Line.assign(klR, klR + nR);
+        F.mDescriptors_Line = nL ? wrap_desc(dL, nL).clone() : cv::Mat();
+        F.mDescriptorsRight_Line = nR ? wrap_desc(dR, nR).clone() : cv::Mat();
+        F.N_l = nL;
+        F.ComputeStereoMatches_Lines();
+        for (int i = 0; i < nL; i++) {
+            disp_se[2 * i] = F.mvDisparity_l[i].first; disp_se[2 * i + 1] = F.mvDisparity_l[i].second;
+            for (int k = 0; k < 3; k++) le[3 * i + k] = F.mvle_l[i](k);
+        }
+        return 0;
+    });
+}
+// matchGrid(lines) called the way src/Frame.cc:1178-1205 calls it (grid of the right lines, endpoint cells of the left).
+REF_API int ref_match_grid_lines(int W, int H, const KeyLine* klL, int nL, const uint8_t* dL, const KeyLine* klR, int nR,
+                                 const uint8_t* dR, int* m12) {
+    return guarded([&] {
+        const double inv_width = FRAME_GRID_COLS / static_cast<double>(W), inv_height = FRAME_GRID_ROWS / static_cast<double>(H);
+        std::vector<line_2d> coords;
+        for (int i = 0; i < nL; i++)
+            coords.push_back(std::make_pair(std::make_pair(klL[i].startPointX * inv_width, klL[i].startPointY * inv_height),
+                                            std::make_pair(klL[i].endPointX * inv_width, klL[i].endPointY * inv_height)));
+        std::list<std::pair<int, int>> line_coords;
+        GridStructure grid(FRAME_GRID_ROWS, FRAME_GRID_COLS);
+        std::vector<std::pair<double, double>> directions(nR);
+        for (int idx = 0; idx < nR; ++idx) {
+            const KeyLine& kl = klR[idx];
+            directions[idx] = std::make_pair((kl.endPointX - kl.startPointX) * inv_width, (kl.endPointY - kl.startPointY) * inv_height);
+            normalize(directions[idx]);
+            getLineCoords(kl.startPointX * inv_width, kl.startPointY * inv_height, kl.endPointX * inv_width,
+                          kl.endPointY * inv_height, line_coords);
+            for (const std::pair<int, int>& p : line_coords) grid.at(p.first, p.second).push_back(idx);
+        }
+        GridWindow w;
+        w.width = std::make_pair(Config::matchingSWs(), 0);
+        w.height = std::make_pair(0, 0);
+        std::vector<int> matches_12;
+        int r = matchGrid(coords, wrap_desc(dL, nL), grid, wrap_desc(dR, nR), directions, w, matches_12);
+        for (int i = 0; i < nL; i++) m12[i] = matches_12[i];
+        return r;
+    });
+}
+// getLineCoords (src/gridStructure.cpp:33-41 over src/LineIterator.cpp): cells as x,y pairs; returns the count.
+REF_API int ref_line_coords(double x1, double y1, double x2, double y2, int* xy, int cap) {
+    return guarded([&] {
+        std::list<std::pair<int, int>> lc;
+        getLineCoords(x1, y1, x2, y2, lc);
+        int k = 0;
+        for (const auto& p : lc) { if (k < cap) { xy[2 * k] = p.first; xy[2 * k + 1] = p.second; } k++; }
+        return k;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// matchNNR / match / distance (src/LineMatcher.cpp:139-159,201-247), ORBmatcher::DescriptorDistance (:2495-2511)
+REF_API int ref_match_nnr(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int* m12) {
+    return guarded([&] {
+        if (n2 < 2) throw std::runtime_error("undefined in the reference: matches_[idx][1] with fewer than 2 train rows");
+        std::vector<int> m;
+        int r = matchNNR(wrap_desc(d1, n1), wrap_desc(d2, n2), nnr, m);
+        for (int i = 0; i < n1; i++) m12[i] = m[i];
+        return r;
+    });
+}
+REF_API int ref_match(const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int* m12) {
+    return guarded([&] {
+        if (n2 < 2 || (Config::bestLRMatches() && n1 < 2)) throw std::runtime_error("undefined in the reference: fewer than 2 train rows");
+        std::vector<int> m;
+        int r = match(wrap_desc(d1, n1), wrap_desc(d2, n2), nnr, m);
+        for (int i = 0; i < n1; i++) m12[i] = m[i];
+        return r;
+    });
+}
+REF_API int ref_distance(const uint8_t* a, const uint8_t* b) { return ORB_SLAM3::distance(wrap_desc(a, 1), wrap_desc(b, 1)); }
+REF_API int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    return ORBmatcher::DescriptorDistance(wrap_desc(a, 1), wrap_desc(b, 1));
+}

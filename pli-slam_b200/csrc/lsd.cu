@@ -902,6 +902,49 @@ __global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const f
     if (threadIdx.x == 0) nSegsOut[img] = min(s_nSeg, g.segCap);
 }
 
+// cv::LineIterator(img, Point2f, Point2f).count of LSDDetector_custom.cpp:295-296, 8-connected: end points rounded half to
+// even, clipped with cv::clipLine when one lies outside the image (the clamp of checkLineExtremes leaves x in
+// [W-0.5, W), which rounds to W), count = max(|dx|, |dy|) + 1, 0 when nothing is left.  clipLine is OpenCV's integer
+// Cohen-Sutherland: offsets through double, truncated toward zero, the second point clipped against the moved first.
+__device__ __forceinline__ int line_iterator_count(float fx1, float fy1, float fx2, float fy2, int W, int H) {
+    long long x1 = __float2int_rn(fx1), y1 = __float2int_rn(fy1), x2 = __float2int_rn(fx2), y2 = __float2int_rn(fy2);
+    const long long right = W - 1, bottom = H - 1;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        long long a;
+        if (c1 & 12) {
+            a = c1 < 8 ? 0 : bottom;
+            x1 += (long long)__ddiv_rn(__dmul_rn((double)(a - y1), (double)(x2 - x1)), (double)(y2 - y1));
+            y1 = a;
+            c1 = (x1 < 0) + (x1 > right) * 2;
+        }
+        if (c2 & 12) {
+            a = c2 < 8 ? 0 : bottom;
+            x2 += (long long)__ddiv_rn(__dmul_rn((double)(a - y2), (double)(x2 - x1)), (double)(y2 - y1));
+            y2 = a;
+            c2 = (x2 < 0) + (x2 > right) * 2;
+        }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) {
+                a = c1 == 1 ? 0 : right;
+                y1 += (long long)__ddiv_rn(__dmul_rn((double)(a - x1), (double)(y2 - y1)), (double)(x2 - x1));
+                x1 = a;
+                c1 = 0;
+            }
+            if (c2) {
+                a = c2 == 1 ? 0 : right;
+                y2 += (long long)__ddiv_rn(__dmul_rn((double)(a - x2), (double)(y2 - y1)), (double)(x2 - x1));
+                x2 = a;
+                c2 = 0;
+            }
+        }
+    }
+    if ((c1 | c2) != 0) return 0;
+    const long long dx = x2 > x1 ? x2 - x1 : x1 - x2, dy = y2 > y1 ? y2 - y1 : y1 - y2;
+    return (int)(dx > dy ? dx : dy) + 1;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // K4d  KeyLine construction (LSDDetector_custom.cpp:268-308) and top-N by response (src/LineExtractor.cc:56-65;
 // declared rule: stable order, response descending then detection index ascending).  One block per image.
@@ -939,8 +982,7 @@ __global__ void __launch_bounds__(256) keylines_kernel(PlfGeom g, const float* s
             kl.startPointX = ex[0]; kl.startPointY = ex[1]; kl.endPointX = ex[2]; kl.endPointY = ex[3];
             kl.sPointInOctaveX = ex[0]; kl.sPointInOctaveY = ex[1]; kl.ePointInOctaveX = ex[2]; kl.ePointInOctaveY = ex[3];
             kl.lineLength = (float)length;
-            const int ax = __float2int_rn(ex[0]), ay = __float2int_rn(ex[1]), bx = __float2int_rn(ex[2]), by = __float2int_rn(ex[3]);
-            kl.numOfPixels = max(abs(bx - ax), abs(by - ay)) + 1;   // cv::LineIterator(...).count, 8-connected
+            kl.numOfPixels = line_iterator_count(ex[0], ex[1], ex[2], ex[3], W, H);
             kl.angle = (float)atan2((double)__fsub_rn(ex[3], ex[1]), (double)__fsub_rn(ex[2], ex[0]));
             kl.octave = 0;
             kl.size = __fmul_rn(__fsub_rn(ex[2], ex[0]), __fsub_rn(ex[3], ex[1]));

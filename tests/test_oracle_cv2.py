@@ -245,3 +245,31 @@ def test_lsd_vs_cv2_curved_content(oracle, plf, w, h, seed, refine):
     n = C.c_int(0)
     assert oracle.dll.plf_cpu_prim_lsd(_p(img), w, h, C.c_double(1.2), 1 | (refine << 4), _p(out), 20000, C.byref(n)) == 0
     assert len(ref) > 500 and n.value == len(ref) and np.array_equal(out[:n.value], ref)
+
+
+def test_clip_line_and_line_iterator_count_vs_cv2(oracle):
+    """cv::LineIterator(img, p1, p2).count of LSDDetector_custom.cpp:295-296 = max(|dx|, |dy|) + 1 after cv::clipLine.
+    cv2 exposes clipLine; 20 000 random segments around / across / outside several image rectangles, plus the case that
+    occurs on the path (an end point clamped into [W-0.5, W) rounds to W)."""
+    rng = np.random.default_rng(4)
+    pts = np.zeros(4, np.int64)
+    for k in range(20000):
+        W, H = [(752, 480), (376, 240), (1280, 720), (7, 5)][k % 4]
+        if k % 3 == 0:      # just outside on the right / bottom, as the path produces
+            p = [int(rng.integers(0, W + 1)), int(rng.integers(0, H + 1)), int(rng.integers(0, W + 1)), int(rng.integers(0, H + 1))]
+        else:
+            p = [int(v) for v in rng.integers(-2 * max(W, H), 3 * max(W, H), 4)]
+        ok, a, b = cv2.clipLine((0, 0, W, H), (p[0], p[1]), (p[2], p[3]))
+        pts[:] = p
+        got = oracle.dll.plf_cpu_prim_clip_line(W, H, _p(pts))
+        assert bool(got) == bool(ok), (W, H, p)
+        if ok:
+            assert (int(pts[0]), int(pts[1])) == tuple(a) and (int(pts[2]), int(pts[3])) == tuple(b), (W, H, p)
+            want = max(abs(b[0] - a[0]), abs(b[1] - a[1])) + 1
+        else:
+            want = 0
+        fn = oracle.dll.plf_cpu_prim_line_iterator_count
+        fn.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int]
+        assert fn(p[0], p[1], p[2], p[3], W, H) == want
+    assert fn(375.6, 10.0, 300.0, 50.0, 376, 240) == 76        # (376,10) is clipped to (375,10)
+    assert fn(375.6, 10.0, 375.7, 50.0, 376, 240) == 0         # both ends round to x = W: nothing left

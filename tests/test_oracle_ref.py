@@ -1,0 +1,540 @@
+"""The restated oracle (oracle/cpp) pinned to the REFERENCE'S OWN CODE (oracle/_ref/libplf_ref.so).
+
+oracle/build_ref.py compiles the reference's frontend sources from /root/reference, unmodified — whole files
+(src/ORBextractor.cc, LineExtractor.cc, LineMatcher.cpp, gridStructure.cpp, LineIterator.cpp, Config.cpp,
+LSDDetector_custom.cpp) and, where a file drags the whole SLAM system in, line ranges extracted at build time
+(src/Frame.cc:976-1307, src/ORBmatcher.cc:36-42,2495-2511, binary_descriptor_custom.cpp:42-687,1026-1372) — against a
+stand-in for the OpenCV headers whose arithmetic primitives are the cv2-pinned ones of tests/test_oracle_cv2.py.
+Everything the reference owns (quadtree, orientation, rBRIEF, row placement, KeyLine construction, LBD, both stereo
+matchers, matchGrid / grid / line iterator, matchNNR / match, both Hamming distances, the Config defaults) is therefore
+checked here against the reference's own object code.  Equality is demanded; the two places where the reference's
+result depends on the machine it runs on are asserted as such (see test_keyline_angle_*, test_octree_address_*).
+
+No GPU involved; the library travels prebuilt (oracle/_ref is git-ignored, not gpurun-ignored).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libplf_ref.so")
+REF_TREE = "/root/reference"
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="session")
+def ref():
+    if not os.path.exists(REF_LIB):
+        if not os.path.isdir(REF_TREE):
+            pytest.skip("oracle/_ref is not built and the reference tree is absent")
+        import subprocess
+        import sys
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "oracle", "build_ref.py")])
+    lib = C.CDLL(REF_LIB)
+    lib.ref_last_error.restype = C.c_char_p
+    lib.ref_arena(1)
+    return lib
+
+
+@pytest.fixture(scope="session")
+def bind(plf):
+    return plf            # KEYPOINT_DT / KEYLINE_DT record layouts (== cv::KeyPoint / KeyLine)
+
+
+def synth(plf, W, H, seed, curved=False):
+    """(left, right): rectangle/segment content, or the curved-edge content (one image, used for both sides)."""
+    if curved:
+        im = plf.synth_curvy(W, H, seed)
+        return im, im
+    return plf.synth_pair(W, H, seed)
+
+
+def ref_orb(ref, bind, side, img, nfeat=1200, lap=(0, 0), scale=1.2, levels=8, ini=20, mn=7):
+    assert ref.ref_orb_create(side, nfeat, C.c_float(scale), levels, ini, mn) == 0
+    img = np.ascontiguousarray(img)
+    h, w = img.shape
+    cap = 4 * nfeat + 64
+    kp = np.zeros(cap, bind.KEYPOINT_DT)
+    d = np.zeros((cap, 32), np.uint8)
+    n = C.c_int(0)
+    mono = ref.ref_orb_extract(side, P(img), w, h, img.strides[0], lap[0], lap[1], P(kp), P(d), cap, C.byref(n))
+    assert mono > -1000, ref.ref_last_error()
+    return mono, kp[:n.value].copy(), d[:n.value].copy()
+
+
+def ref_lines(ref, bind, img, p):
+    img = np.ascontiguousarray(img)
+    h, w = img.shape
+    kl = np.zeros(20000, bind.KEYLINE_DT)
+    d = np.zeros((20000, 32), np.uint8)
+    n = ref.ref_line_extract(P(img), w, h, img.strides[0], p.lsd_nfeatures, C.c_double(p.min_line_length), p.lsd_refine,
+                             C.c_double(p.lsd_scale), C.c_double(p.lsd_sigma_scale), C.c_double(p.lsd_quant),
+                             C.c_double(p.lsd_ang_th), C.c_double(p.lsd_log_eps), C.c_double(p.lsd_density_th),
+                             p.lsd_n_bins, P(kl), P(d), 20000)
+    assert n >= 0, ref.ref_last_error()
+    return kl[:n].copy(), d[:n].copy()
+
+
+def ulp_diff(a, b):
+    def mono(x):    # sign-magnitude float bits -> integers that are monotone in the float value
+        i = x.view(np.int32).astype(np.int64)
+        return np.where(i < 0, -(i & 0x7FFFFFFF), i)
+    return np.abs(mono(a) - mono(b))
+
+
+class float_libm:
+    """Oracle test hook: 1 = call this machine's cosf / sinf / atan2f where the reference does ("as built here"),
+    0 = the declared, correctly rounded values (what every other test and the product use)."""
+
+    def __init__(self, oracle, on):
+        self.oracle, self.on = oracle, on
+
+    def __enter__(self):
+        self.old = self.oracle.dll.plf_cpu_set_float_libm(int(self.on))
+
+    def __exit__(self, *a):
+        self.oracle.dll.plf_cpu_set_float_libm(self.old)
+
+
+GEOM = ["octave", "pt_x", "pt_y", "response", "size", "startPointX", "startPointY", "endPointX", "endPointY",
+        "sPointInOctaveX", "sPointInOctaveY", "ePointInOctaveX", "ePointInOctaveY", "lineLength", "numOfPixels"]
+
+
+def assert_keylines_equal(okl, od, rkl, rd, full=None, img=None, oracle=None, as_built=False):
+    """Reference rows == oracle rows.  Two things are not bit-for-bit by construction and are asserted as what they are:
+    * `angle`: the reference calls the float atan2 of whatever libm it is linked to (test_keyline_angle_is_libm_atan2f);
+      at most 1 ulp from the oracle's correctly rounded value;
+    * rows of EQUAL response: src/LineExtractor.cc:59 orders them with the unstable std::sort (introsort), the oracle
+      declares (response desc, detection index asc).  So: the response column is identical, every row whose response
+      is unique sits at the same index with identical fields, and every reference row — tie or not — is a row of the
+      oracle's untruncated detection list (`full`) with the same 15 geometry fields and the same 32 descriptor bytes.
+    With `as_built` (oracle in float-libm mode) angle and descriptor must be IDENTICAL.  In the declared mode a
+    descriptor may differ from the reference's by at most the north star's 2 bits, and only through the libm rounding of
+    atan2f / cosf / sinf (shown by the as-built run of the same inputs being identical)."""
+    assert len(okl) == len(rkl)
+    assert np.array_equal(okl["response"], rkl["response"])
+    fk, fd = (okl, od) if full is None else full
+    geom = lambda a: np.ascontiguousarray(np.stack([a[f].astype(np.float64) for f in GEOM], 1))   # exact for f32 / i32
+    gf, go, gr = geom(fk), geom(okl), geom(rkl)
+    table = {gf[i].tobytes(): i for i in range(len(fk))}
+    resp, counts = np.unique(okl["response"], return_counts=True)
+    unique = np.isin(okl["response"], resp[counts == 1])
+    ties = 0
+    for i in range(len(rkl)):
+        j = table.get(gr[i].tobytes())
+        assert j is not None, "reference row %d is not an oracle line" % i
+        assert ulp_diff(rkl["angle"][i:i + 1], fk["angle"][j:j + 1])[0] <= (0 if as_built else 1)
+        if not np.array_equal(rd[i], fd[j]):
+            assert not as_built
+            assert np.unpackbits(rd[i] ^ fd[j]).sum() <= 2
+        if unique[i]:
+            assert np.array_equal(gr[i], go[i]) and rkl["class_id"][i] == okl["class_id"][i], i
+        else:
+            ties += 1
+    assert np.array_equal(rkl["class_id"], okl["class_id"])
+    return ties
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_config_defaults_and_euroc_yaml(ref, oracle):
+    """src/Config.cpp:26-160 (the reference's own constructor) and Config::loadFromFile on the reference's EuRoC.yaml
+    give the values plf_default_params carries."""
+    v = (C.c_double * 21)()
+    assert ref.ref_config_get(v) == 0
+    p = oracle.default_params()
+    names = ["has_lines", "best_lr_matches", "matching_s_ws", "min_ratio_12_l", "line_sim_th", "min_disp", "line_horiz_th",
+             "stereo_overlap_th", "ls_min_disp_ratio"]
+    for i, nme in enumerate(names):
+        assert float(getattr(p, nme)) == v[i], nme
+    lsd = {12: "lsd_refine", 13: "lsd_scale", 14: "lsd_sigma_scale", 15: "lsd_quant", 16: "lsd_ang_th", 17: "lsd_log_eps",
+           18: "lsd_density_th", 19: "lsd_n_bins", 20: "min_line_length"}
+    for i, nme in lsd.items():
+        assert float(getattr(p, nme)) == v[i], nme
+    assert v[11] == 300                       # Config default lsd_nfeatures (src/Config.cpp:100)
+    yaml = os.path.join(REF_TREE, "Examples/Stereo/Config/EuRoC.yaml")
+    if os.path.exists(yaml):
+        assert ref.ref_config_load(yaml.encode(), v) == 0
+        assert v[11] == 500 == p.lsd_nfeatures    # EuRoC.yaml:156
+        for i, nme in list(enumerate(names)) + list(lsd.items()):
+            assert float(getattr(p, nme)) == v[i], nme
+
+
+def test_scale_tables_quotas_umax(ref, oracle, plf):
+    for nfeat, sf, nl in ((1200, 1.2, 8), (2000, 1.2, 8), (1000, 1.2, 8), (500, 1.5, 5), (3000, 1.1, 10)):
+        assert ref.ref_orb_create(0, nfeat, C.c_float(sf), nl, 20, 7) == 0
+        a = [np.zeros(16, np.float32) for _ in range(4)]
+        q = np.zeros(16, np.int32)
+        um = np.zeros(16, np.int32)
+        assert ref.ref_orb_tables(0, P(a[0]), P(a[1]), P(a[2]), P(a[3]), P(q), P(um)) == nl
+        f = plf.Frontend(oracle, width=160, height=120, n_features=nfeat, scale_factor=sf, n_levels=nl, max_batch=1)
+        s, inv, s2, inv2, quota = f.scale_tables()
+        assert np.array_equal(s, a[0][:nl]) and np.array_equal(inv, a[1][:nl])
+        assert np.array_equal(s2, a[2][:nl]) and np.array_equal(inv2, a[3][:nl])
+        assert np.array_equal(quota, q[:nl])
+        assert list(um) == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+
+
+CASES = [  # name, W, H, seed, nfeatures   (C1, C3, C4 of BASELINE.json, the KITTI shape with 4 root nodes, a small frame)
+    ("c1", 752, 480, 1, 1200), ("c3", 752, 480, 1000, 2000), ("c4", 1280, 720, 2000, 1200),
+    ("kitti", 1241, 376, 77, 2000), ("small", 320, 240, 5, 500)]
+
+
+@pytest.mark.parametrize("name,W,H,seed,nfeat", CASES)
+def test_orb_extractor_whole_operator(ref, bind, oracle, plf, name, W, H, seed, nfeat):
+    """ORBextractor::operator() — the reference's src/ORBextractor.cc, whole file — equals the oracle: row count, every
+    KeyPoint field, every descriptor byte, monoIndex, and the pyramid it leaves behind."""
+    L, R = plf.synth_pair(W, H, seed)
+    f = plf.Frontend(oracle, width=W, height=H, n_features=nfeat, max_batch=1)
+    for side, img in ((0, L), (1, R)):
+        mono, kp, d = f.orb_extract(side, img)
+        rmono, rkp, rd = ref_orb(ref, bind, side, img, nfeat)
+        assert (mono, len(kp)) == (rmono, len(rkp))
+        assert np.array_equal(kp, rkp) and np.array_equal(d, rd)
+        for lvl in range(8):
+            o_l = f.pyramid_level(side, lvl)
+            buf = np.zeros(o_l.size, np.uint8)
+            w, h = C.c_int(0), C.c_int(0)
+            assert ref.ref_orb_level(side, lvl, P(buf), buf.size, C.byref(w), C.byref(h)) == 0
+            assert (h.value, w.value) == o_l.shape and np.array_equal(buf.reshape(o_l.shape), o_l)
+
+
+@pytest.mark.parametrize("lap", [(0, 1000), (300, 500), (0, 0), (751, 751)])
+def test_orb_extractor_lapping_area(ref, bind, oracle, plf, lap):
+    """Back-to-front placement of the rows inside vLappingArea and the returned monoIndex (src/ORBextractor.cc:1135-1146)."""
+    L, _ = plf.synth_pair(752, 480, 3)
+    f = plf.Frontend(oracle, max_batch=1)
+    mono, kp, d = f.orb_extract(0, L, lapping=lap)
+    rmono, rkp, rd = ref_orb(ref, bind, 0, L, 1200, lap)
+    assert mono == rmono and np.array_equal(kp, rkp) and np.array_equal(d, rd)
+    if lap == (0, 1000):
+        assert mono == 0
+
+
+def test_orb_extractor_fifty_seeds(ref, bind, oracle, plf):
+    """50 more images (several sizes and feature budgets): 0 differing rows."""
+    total = 0
+    for k in range(50):
+        W, H, nfeat = [(376, 240, 500), (480, 360, 800), (641, 479, 1000), (752, 480, 1200), (320, 200, 300)][k % 5]
+        L, _ = synth(plf, W, H, 40000 + k, curved=(k % 7 == 3))
+        f = plf.Frontend(oracle, width=W, height=H, n_features=nfeat, max_batch=1, has_lines=0)
+        rmono, rkp, rd = ref_orb(ref, bind, 0, L, nfeat)
+        for as_built in ((False, True) if k % 5 == 0 else (False,)):
+            with float_libm(oracle, as_built):
+                mono, kp, d = f.orb_extract(0, L)
+            assert mono == rmono and np.array_equal(kp, rkp) and np.array_equal(d, rd), k
+        total += len(kp)
+    assert total > 20000
+
+
+def test_empty_image_returns_minus_one(ref, bind):
+    assert ref.ref_orb_create(0, 1200, C.c_float(1.2), 8, 20, 7) == 0
+    n = C.c_int(0)
+    kp = np.zeros(8, bind.KEYPOINT_DT)
+    d = np.zeros((8, 32), np.uint8)
+    assert ref.ref_orb_extract(0, None, 0, 0, 0, 0, 0, P(kp), P(d), 8, C.byref(n)) == -1   # src/ORBextractor.cc:1072
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _octree(oracle, ref, xyr, box, N):
+    out = np.zeros((len(xyr) + 8, 3), np.float32)
+    n = C.c_int(0)
+    assert oracle.dll.plf_cpu_prim_octree(P(xyr), len(xyr), *box, N, P(out), len(out), C.byref(n)) == 0
+    rout = np.zeros((len(xyr) + 8, 3), np.float32)
+    rn = ref.ref_octree(0, P(xyr), len(xyr), *box, N, P(rout), len(rout))
+    assert rn >= 0, ref.ref_last_error()
+    return out[:n.value], rout[:rn]
+
+
+def _random_candidates(rng, n, w, h, ties):
+    xy = rng.permutation(w * h)[:n]
+    xyr = np.zeros((n, 3), np.float32)
+    xyr[:, 0], xyr[:, 1] = xy % w, xy // w
+    xyr[:, 2] = rng.integers(7, 12 if ties else 200, n)      # few distinct responses -> many response ties
+    order = np.lexsort((xyr[:, 0], xyr[:, 1]))
+    return np.ascontiguousarray(xyr[order])
+
+
+def test_octree_random_candidates(ref, oracle):
+    """DistributeOctTree alone on 60 random candidate sets (clustered and uniform, with response ties, 1 to 6 root
+    nodes, quota from 1 to more than the candidates): the retained points AND their order equal the reference's with
+    list nodes at monotonically increasing addresses — the oracle's declared tie rule (most recent node first)."""
+    rng = np.random.default_rng(7)
+    assert ref.ref_orb_create(0, 1200, C.c_float(1.2), 8, 20, 7) == 0
+    ref.ref_arena(1)
+    for k in range(60):
+        w, h = [(720, 448), (1209, 344), (200, 180), (300, 90), (200, 300)][k % 5]   # (W' < H'/2 gives nIni = 0: division by zero in the reference)
+        n = int(rng.integers(1, 3000))
+        xyr = _random_candidates(rng, min(n, w * h // 2), w, h, ties=(k % 2 == 0))
+        if k % 3 == 0:                                         # clustered: deep subdivision, many equal-size nodes
+            xyr[:, 0] = np.minimum(w - 1, (xyr[:, 0] * 0.2).astype(np.int32) + (k % 4) * w // 5)
+            xyr = np.unique(xyr, axis=0)
+            xyr = np.ascontiguousarray(xyr[np.lexsort((xyr[:, 0], xyr[:, 1]))])
+        N = int(rng.integers(1, max(2, 2 * len(xyr))))
+        o, r = _octree(oracle, ref, xyr, (16, 16 + w, 16, 16 + h), N)
+        assert np.array_equal(o, r), (k, len(xyr), N)
+
+
+def test_octree_depends_on_heap_addresses_in_the_reference(ref, oracle):
+    """The same kind of sets with the list nodes left to malloc: src/ORBextractor.cc:682 sorts (size, ExtractorNode*), so
+    equal-size nodes are expanded in heap-address order and the reference's own output — even the number of retained
+    points — changes with the allocator (observed here: different results for most sets).  With nodes at monotonically
+    increasing addresses it is reproducible and equals the oracle; that is the declared rule."""
+    rng = np.random.default_rng(11)
+    assert ref.ref_orb_create(0, 1200, C.c_float(1.2), 8, 20, 7) == 0
+    differ = 0
+    try:
+        for k in range(20):
+            xyr = _random_candidates(rng, 1500, 720, 448, ties=True)
+            ref.ref_arena(0)
+            _, r_malloc = _octree(oracle, ref, xyr, (16, 736, 16, 464), 261)
+            ref.ref_arena(1)
+            o, r_arena = _octree(oracle, ref, xyr, (16, 736, 16, 464), 261)
+            assert np.array_equal(o, r_arena)
+            assert 261 <= len(r_malloc) <= 264 and 261 <= len(r_arena) <= 264
+            differ += int(not np.array_equal(r_malloc, r_arena))
+    finally:
+        ref.ref_arena(1)
+    print("reference octree with malloc addresses differs from monotonic addresses on %d of 20 sets" % differ)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+LINE_CASES = [("c1", 752, 480, 1, 500, 0), ("c2", 752, 480, 1001, 300, 0), ("c4", 1280, 720, 2000, 500, 0),
+              ("all", 752, 480, 9, 0, 0), ("refine1", 641, 479, 21, 300, 1)]
+
+
+@pytest.mark.parametrize("name,W,H,seed,nl,refine", LINE_CASES)
+def test_line_extractor_whole_operator(ref, bind, oracle, plf, name, W, H, seed, nl, refine):
+    """Lineextractor::operator() = the reference's LineExtractor.cc + LSDDetector_custom.cpp (whole files) + the LBD ranges
+    of binary_descriptor_custom.cpp: KeyLines (all 17 fields) and descriptors."""
+    L, R = plf.synth_pair(W, H, seed)
+    f = plf.Frontend(oracle, width=W, height=H, lsd_nfeatures=nl, lsd_refine=refine, max_batch=1)
+    fall = plf.Frontend(oracle, width=W, height=H, lsd_nfeatures=0, lsd_refine=refine, max_batch=1)
+    for side, img in ((0, L), (1, R)):
+        rkl, rd = ref_lines(ref, bind, img, f.params)
+        for as_built in (True, False):
+            with float_libm(oracle, as_built):
+                okl, od = f.line_extract(side, img)
+                full = fall.line_extract(side, img)
+            assert len(okl) > 100
+            ties = assert_keylines_equal(okl, od, rkl, rd, full=full, as_built=as_built)
+            if nl == 0:
+                assert ties == 0      # no sort at all: identical row for row
+                if as_built:
+                    assert np.array_equal(okl, rkl) and np.array_equal(od, rd)
+
+
+def test_keyline_angle_is_libm_atan2f(ref, bind, oracle, plf):
+    """LSDDetector_custom.cpp:297 calls atan2 on float operands; bitarray_custom.hpp includes <math.h>, so with GCC >= 6
+    the call binds to the FLOAT overload and the value is whatever the linked libm's atan2f returns (glibc < 2.41: not
+    correctly rounded).  The oracle declares the correctly rounded value.  Shown here: the reference's angle is exactly
+    this machine's atan2f, and never more than 1 ulp from the oracle."""
+    L, _ = plf.synth_pair(752, 480, 1)
+    f = plf.Frontend(oracle, max_batch=1)
+    okl, _ = f.line_extract(0, L)
+    rkl, _ = ref_lines(ref, bind, L, f.params)
+    libm = C.CDLL("libm.so.6")
+    libm.atan2f.restype = C.c_float
+    libm.atan2f.argtypes = [C.c_float, C.c_float]
+    dy = okl["endPointY"] - okl["startPointY"]
+    dx = okl["endPointX"] - okl["startPointX"]
+    mine = np.array([libm.atan2f(a, b) for a, b in zip(dy, dx)], np.float32)
+    assert np.array_equal(mine, rkl["angle"])
+    exact = np.arctan2(dy.astype(np.float64), dx.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(exact, okl["angle"])
+    assert ulp_diff(okl["angle"], rkl["angle"]).max() <= 1
+
+
+def test_line_extractor_thirty_seeds(ref, bind, oracle, plf):
+    n_lines = 0
+    for k in range(30):
+        W, H = [(376, 240), (480, 360), (641, 479)][k % 3]
+        L, _ = synth(plf, W, H, 50000 + k, curved=(k % 5 == 2))
+        f = plf.Frontend(oracle, width=W, height=H, lsd_nfeatures=(0 if k % 2 else 150), max_batch=1)
+        fall = plf.Frontend(oracle, width=W, height=H, lsd_nfeatures=0, max_batch=1)
+        rkl, rd = ref_lines(ref, bind, L, f.params)
+        for as_built in (True, False):
+            with float_libm(oracle, as_built):
+                okl, od = f.line_extract(0, L)
+                full = fall.line_extract(0, L)
+            assert_keylines_equal(okl, od, rkl, rd, full=full, as_built=as_built)
+        n_lines += len(okl)
+    assert n_lines > 3000
+
+
+def test_lbd_float_and_binary_on_given_keylines(ref, bind, oracle, plf):
+    """BinaryDescriptor::compute on identical KeyLines: the 72 floats per line (returnFloatDescr) and the 32 bytes are
+    IDENTICAL - not merely within the north star's 2 bits - including lines that leave the image, very short ones and one
+    whose LineIterator count is 0."""
+    rng = np.random.default_rng(5)
+    libm = C.CDLL("libm.so.6")
+    for fn in (libm.cosf, libm.sinf):
+        fn.restype, fn.argtypes = C.c_float, [C.c_float]
+    for seed, (W, H) in ((1, (752, 480)), (2000, (1280, 720)), (31, (320, 240))):
+        L, _ = plf.synth_pair(W, H, seed)
+        f = plf.Frontend(oracle, width=W, height=H, lsd_nfeatures=0, max_batch=1)
+        okl, _ = f.line_extract(0, L)
+        kls = okl.copy()
+        extra = kls[:40].copy()                               # synthetic lines: random placement incl. the borders
+        for i in range(len(extra)):
+            x1, y1, x2, y2 = rng.uniform(0, W - 1), rng.uniform(0, H - 1), rng.uniform(0, W - 1), rng.uniform(0, H - 1)
+            if i % 4 == 0:
+                x2, y2 = min(W - 1, x1 + 3), y1                # 4-pixel line
+            e = extra[i]
+            e["startPointX"], e["startPointY"], e["endPointX"], e["endPointY"] = x1, y1, x2, y2
+            e["sPointInOctaveX"], e["sPointInOctaveY"], e["ePointInOctaveX"], e["ePointInOctaveY"] = x1, y1, x2, y2
+            e["lineLength"] = np.hypot(x2 - x1, y2 - y1)
+            e["numOfPixels"] = int(max(abs(round(x2) - round(x1)), abs(round(y2) - round(y1))) + 1)
+            e["angle"] = np.arctan2(np.float32(y2) - np.float32(y1), np.float32(x2) - np.float32(x1))
+            if i == 7:
+                e["numOfPixels"] = 0        # cv::LineIterator count of a segment that rounds out of the image
+        kls = np.concatenate([kls, extra])
+        kls["class_id"] = np.arange(len(kls))
+        n = len(kls)
+        of, ob = np.zeros((n, 72), np.float32), np.zeros((n, 32), np.uint8)
+        rf, rb = np.zeros((n, 72), np.float32), np.zeros((n, 32), np.uint8)
+        img = np.ascontiguousarray(L)
+        assert ref.ref_lbd(P(img), W, H, W, P(kls), n, P(rf), P(rb)) == n, ref.ref_last_error()
+        with float_libm(oracle, True):          # as built here: every float and every byte identical
+            assert oracle.dll.plf_cpu_prim_lbd(P(img), W, H, P(kls), n, P(of), P(ob)) == 0
+        assert np.array_equal(of.view(np.int32), rf.view(np.int32))
+        assert np.array_equal(ob, rb)
+        # declared mode: a row may differ only if this machine's cosf / sinf of its angle is not the correctly rounded
+        # value (the reference calls cos / sin on a float, binary_descriptor_custom.cpp:1134-1135), and by <= 2 bits
+        assert oracle.dll.plf_cpu_prim_lbd(P(img), W, H, P(kls), n, P(of), P(ob)) == 0
+        differs = (of.view(np.int32) != rf.view(np.int32)).any(1)
+        a64 = kls["angle"].astype(np.float64)
+        libm_off = np.array([(libm.cosf(a) != np.float32(np.cos(b))) or (libm.sinf(a) != np.float32(np.sin(b)))
+                             for a, b in zip(kls["angle"], a64)])
+        assert not (differs & ~libm_off).any()
+        assert np.unpackbits(ob ^ rb, axis=1).sum(1).max() <= 2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,W,H,seed,nfeat", CASES[:4])
+def test_stereo_matches_points_and_lines(ref, bind, oracle, plf, name, W, H, seed, nfeat):
+    """Frame::ComputeStereoMatches and Frame::ComputeStereoMatches_Lines — the reference's own function bodies
+    (src/Frame.cc:976-1307) over matchGrid / GridStructure / LineIterator / DescriptorDistance — against the oracle:
+    mvuRight, mvDepth, matches_12, mvDisparity_l, mvle_l."""
+    L, R = plf.synth_pair(W, H, seed)
+    f = plf.Frontend(oracle, width=W, height=H, n_features=nfeat, max_batch=1)
+    _, kL, dL = f.orb_extract(0, L)
+    _, kR, dR = f.orb_extract(1, R)
+    klL, ldL = f.line_extract(0, L)
+    klR, ldR = f.line_extract(1, R)
+    u, dep = f.stereo_match_points(len(kL))
+    ref_orb(ref, bind, 0, L, nfeat)
+    ref_orb(ref, bind, 1, R, nfeat)             # leaves both pyramids in the reference extractors
+    ru, rd = np.zeros(len(kL), np.float32), np.zeros(len(kL), np.float32)
+    assert ref.ref_stereo_points(C.c_float(f.params.bf), C.c_float(f.params.fx), P(kL), len(kL), P(dL), P(kR), len(kR),
+                                 P(dR), P(ru), P(rd)) == 0, ref.ref_last_error()
+    assert (u >= 0).sum() > 100
+    assert np.array_equal(u, ru) and np.array_equal(dep, rd)
+    disp, le, m12 = f.stereo_match_lines(len(klL))
+    rdisp, rle, rm = np.zeros((len(klL), 2), np.float32), np.zeros((len(klL), 3)), np.zeros(len(klL), np.int32)
+    assert ref.ref_stereo_lines(W, H, P(klL), len(klL), P(ldL), P(klR), len(klR), P(ldR), P(rdisp), P(rle)) == 0
+    assert ref.ref_match_grid_lines(W, H, P(klL), len(klL), P(ldL), P(klR), len(klR), P(ldR), P(rm)) >= 0
+    assert (m12 >= 0).sum() > 50
+    assert np.array_equal(m12, rm) and np.array_equal(disp, rdisp) and np.array_equal(le, rle)
+
+
+def _random_keylines(rng, bind, n, W, H):
+    kl = np.zeros(n, bind.KEYLINE_DT)
+    x1, y1 = rng.uniform(0, W - 1, n), rng.uniform(0, H - 1, n)
+    ang = rng.uniform(-np.pi, np.pi, n)
+    ln = rng.uniform(12, 200, n)
+    x2, y2 = np.clip(x1 + ln * np.cos(ang), 0, W - 1), np.clip(y1 + ln * np.sin(ang), 0, H - 1)
+    horiz = rng.random(n) < 0.1
+    y2 = np.where(horiz, y1 + rng.uniform(-0.15, 0.15, n), y2)      # near-horizontal lines around lineHorizTh
+    kl["startPointX"], kl["startPointY"], kl["endPointX"], kl["endPointY"] = x1, y1, x2, np.clip(y2, 0, H - 1)
+    return kl
+
+
+def test_stereo_lines_random_sets(ref, bind, oracle):
+    """50 random left/right KeyLine + descriptor sets through ComputeStereoMatches_Lines, with every Config switch the
+    function reads varied (bestLRMatches, matchingSWs, ratios, thresholds): identical outputs, doubles included."""
+    rng = np.random.default_rng(3)
+    v0 = (C.c_double * 21)()
+    assert ref.ref_config_get(v0) == 0
+    try:
+        for k in range(50):
+            W, H = [(752, 480), (1280, 720), (1241, 376)][k % 3]
+            nL, nR = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+            klL = _random_keylines(rng, bind, nL, W, H)
+            klR = klL[rng.integers(0, nL, nR)].copy() if k % 2 else _random_keylines(rng, bind, nR, W, H)
+            shift = rng.uniform(0.5, 40, nR).astype(np.float32)
+            klR["startPointX"] -= shift * rng.uniform(0.6, 1.0, nR).astype(np.float32)
+            klR["endPointX"] -= shift
+            klR["startPointY"] += rng.uniform(-2, 2, nR).astype(np.float32)
+            base = rng.integers(0, 256, (8, 32), dtype=np.uint8)       # few prototypes -> close distances and exact ties
+            dL = base[rng.integers(0, 8, nL)] ^ (rng.random((nL, 32)) < 0.05).astype(np.uint8)
+            dR = base[rng.integers(0, 8, nR)] ^ (rng.random((nR, 32)) < 0.05).astype(np.uint8)
+            dL, dR = np.ascontiguousarray(dL), np.ascontiguousarray(dR)
+            p = oracle.default_params(best_lr_matches=int(k % 4 != 3), matching_s_ws=int(rng.integers(0, 20)),
+                                      min_ratio_12_l=float(rng.choice([0.9, 0.75, 1.0])),
+                                      line_sim_th=float(rng.choice([0.75, 0.0, 0.95])), min_disp=float(rng.choice([1.0, 0.0])),
+                                      stereo_overlap_th=float(rng.choice([0.75, 0.3])),
+                                      ls_min_disp_ratio=float(rng.choice([0.7, 0.2])))
+            v = (C.c_double * 21)(*v0)
+            v[1], v[2], v[3], v[4], v[5], v[7], v[8] = (p.best_lr_matches, p.matching_s_ws, p.min_ratio_12_l, p.line_sim_th,
+                                                        p.min_disp, p.stereo_overlap_th, p.ls_min_disp_ratio)
+            assert ref.ref_config_set(v) == 0
+            od, ol, om = np.zeros((nL, 2), np.float32), np.zeros((nL, 3)), np.zeros(nL, np.int32)
+            rd, rl, rm = np.zeros((nL, 2), np.float32), np.zeros((nL, 3)), np.zeros(nL, np.int32)
+            assert oracle.dll.plf_cpu_prim_stereo_lines(C.byref(p), W, H, P(klL), nL, P(dL), P(klR), nR, P(dR), P(od),
+                                                        P(ol), P(om)) == 0
+            assert ref.ref_stereo_lines(W, H, P(klL), nL, P(dL), P(klR), nR, P(dR), P(rd), P(rl)) == 0, ref.ref_last_error()
+            assert ref.ref_match_grid_lines(W, H, P(klL), nL, P(dL), P(klR), nR, P(dR), P(rm)) >= 0
+            assert np.array_equal(om, rm), k
+            assert np.array_equal(od, rd) and np.array_equal(ol, rl), k
+    finally:
+        ref.ref_config_set(v0)
+
+
+def test_matchnnr_match_and_distances_random(ref, oracle, plf):
+    """matchNNR / match (both Config::bestLRMatches settings) / distance / DescriptorDistance on 50 random descriptor
+    sets with exact distance ties."""
+    rng = np.random.default_rng(17)
+    f = plf.Frontend(oracle, width=160, height=120, max_batch=1)
+    v0 = (C.c_double * 21)()
+    assert ref.ref_config_get(v0) == 0
+    try:
+        for k in range(50):
+            n1, n2 = int(rng.integers(1, 300)), int(rng.integers(2, 300))
+            base = rng.integers(0, 256, (6, 32), dtype=np.uint8)
+            d1 = np.ascontiguousarray(base[rng.integers(0, 6, n1)] ^ (rng.random((n1, 32)) < 0.03).astype(np.uint8))
+            d2 = np.ascontiguousarray(base[rng.integers(0, 6, n2)] ^ (rng.random((n2, 32)) < 0.03).astype(np.uint8))
+            nnr = float(rng.choice([0.9, 0.75, 1.0, 0.5]))
+            m = np.zeros(n1, np.int32)
+            cnt, om = f.match_nnr(d1, d2, nnr)
+            assert ref.ref_match_nnr(P(d1), n1, P(d2), n2, C.c_float(nnr), P(m)) == cnt
+            assert np.array_equal(om, m)
+            for best in (1, 0):
+                if best and n1 < 2:
+                    continue
+                v = (C.c_double * 21)(*v0)
+                v[1] = best
+                assert ref.ref_config_set(v) == 0
+                cnt, om = f.match(d1, d2, nnr, best_lr=bool(best))
+                assert ref.ref_match(P(d1), n1, P(d2), n2, C.c_float(nnr), P(m)) == cnt
+                assert np.array_equal(om, m)
+            for i in range(10):
+                a, b = d1[rng.integers(0, n1)], d2[rng.integers(0, n2)]
+                want = int(np.unpackbits(a ^ b).sum())
+                assert ref.ref_distance(P(a), P(b)) == want == ref.ref_descriptor_distance(P(a), P(b))
+                assert oracle.dll.plf_cpu_prim_hamming(P(a), P(b)) == want
+    finally:
+        ref.ref_config_set(v0)
+
+
+def test_matchnnr_with_one_train_row_is_undefined_in_the_reference(ref):
+    """src/LineMatcher.cpp:152 reads matches_[idx][1] although knnMatch returned one neighbour: out of range.  The
+    binding refuses to run it; the oracle/product rule (no matches) is a declared rule, not a measured one."""
+    d = np.zeros((3, 32), np.uint8)
+    m = np.zeros(3, np.int32)
+    assert ref.ref_match_nnr(P(d), 3, P(d), 1, C.c_float(0.9), P(m)) == -1000
+    assert b"undefined" in ref.ref_last_error()

@@ -40,7 +40,7 @@ typedef enum plf_status {
     PLF_ERR_EMPTY_IMAGE = 2,  /* ORBextractor::operator() returns -1 on an empty image (ORBextractor.cc:1072) */
     PLF_ERR_CUDA = 3,         /* a CUDA call failed; plf_last_error() has the text                         */
     PLF_ERR_NO_DEVICE = 4,    /* no usable sm_100 device: the product path never falls back to the CPU     */
-    PLF_ERR_UNSUPPORTED = 5,  /* parameter combination not built (e.g. lsd_refine != 0)                    */
+    PLF_ERR_UNSUPPORTED = 5,  /* parameter combination not built (e.g. lsd_refine == 2, n_features too large) */
     PLF_ERR_SIZE_MISMATCH = 6,/* std::runtime_error sites of LineMatcher.cpp:148-149,322-323                */
     PLF_ERR_STATE = 7         /* call order violated (e.g. stereo match before both extractions)           */
 } plf_status;
@@ -260,11 +260,12 @@ typedef struct plf_proj_query {
  * order-dependent part — features already taken are skipped, best / second best with the reference's update rule, the
  * TH_HIGH and mfNNratio tests, the assignment F.mvpMapPoints[bestIdx] = pMP — runs on the host in query order.
  * occupied: one byte per keypoint, in/out: != 0 where F.mvpMapPoints[idx] has Observations() > 0; set for every feature
- * assigned by this call (map points of the local map have observations).  match[i] = feature index given to query i
- * or -1.  Returns the reference's nmatches in *n_matches. */
+ * assigned by this call (map points of the local map have observations).  n_features = entries of occupied[]; fewer than
+ * the slot's left keypoint count (Frame::N) -> PLF_ERR_INVALID.  match[i] = feature index given to query i or -1.
+ * Returns the reference's nmatches in *n_matches. */
 PLF_API int PLF_FN(search_by_projection)(plf_ctx* ctx, int slot, const plf_proj_query* queries, int n_queries, float th,
-                                         float nn_ratio, int th_high, uint8_t* occupied, int32_t* match,
-                                         int* n_matches);
+                                         float nn_ratio, int th_high, uint8_t* occupied, int n_features,
+                                         int32_t* match, int* n_matches);
 
 /* One map point of LastFrame already projected into CurrentFrame, as the frame-to-frame overload
  * ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono, match12)
@@ -291,9 +292,10 @@ typedef struct plf_frame_query {
  * occupied  : in/out, one byte per keypoint: the feature holds a map point with Observations() > 0
  * feat_query: out, per keypoint: index of the query whose map point it holds at the end, or -1
  * match12   : out, per keypoint: the std::map<int,int> of the reference (first insertion wins), or -1; may be NULL
+ * n_features: entries of occupied[] / feat_query[] / match12[]; fewer than Frame::N of the slot -> PLF_ERR_INVALID
  * Returns the reference's nmatches in *n_matches. */
 PLF_API int PLF_FN(search_by_projection_frame)(plf_ctx* ctx, int slot, const plf_frame_query* queries, int n_queries,
-                                               int th_high, int check_orientation, uint8_t* occupied,
+                                               int th_high, int check_orientation, uint8_t* occupied, int n_features,
                                                int32_t* feat_query, int32_t* match12, int* n_matches);
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -455,6 +457,19 @@ static inline int plf_hamming256(const uint8_t* a, const uint8_t* b) {
     }
     return d;
 }
+
+/* Layout contracts of the PODs that cross the boundary (cv::KeyPoint 28 B, KeyLine 68 B, query records 56 / 72 B). */
+#if defined(__cplusplus)
+static_assert(sizeof(plf_keypoint) == 28, "plf_keypoint must be layout-identical to cv::KeyPoint");
+static_assert(sizeof(plf_keyline) == 68, "plf_keyline must be layout-identical to cv::line_descriptor::KeyLine");
+static_assert(sizeof(plf_proj_query) == 56, "plf_proj_query is 56 bytes");
+static_assert(sizeof(plf_frame_query) == 72, "plf_frame_query is 72 bytes");
+#elif defined(__STDC_VERSION__) && __STDC_VERSION__ >= 201112L
+_Static_assert(sizeof(plf_keypoint) == 28, "plf_keypoint must be layout-identical to cv::KeyPoint");
+_Static_assert(sizeof(plf_keyline) == 68, "plf_keyline must be layout-identical to cv::line_descriptor::KeyLine");
+_Static_assert(sizeof(plf_proj_query) == 56, "plf_proj_query is 56 bytes");
+_Static_assert(sizeof(plf_frame_query) == 72, "plf_frame_query is 72 bytes");
+#endif
 
 #ifdef __cplusplus
 }

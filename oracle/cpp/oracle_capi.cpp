@@ -453,11 +453,12 @@ PLF_API int plf_cpu_bow_build_vectors(const int32_t* word_id, const double* weig
 // ---- ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, ...) (src/ORBmatcher.cc:44-130), Nleft == -1 ----
 // parity unpinned (no runnable reference: MapPoint / Frame state); the loops follow the reference line by line.
 PLF_API int plf_cpu_search_by_projection(plf_ctx* c, int slot, const plf_proj_query* queries, int n_queries, float th, float nn_ratio,
-                                         int th_high, uint8_t* occupied, int32_t* match, int* n_matches) {
+                                         int th_high, uint8_t* occupied, int n_features, int32_t* match, int* n_matches) {
     if (!c || slot < 0 || slot >= (int)c->slots.size() || !queries || n_queries < 0 || !occupied || !match)
         return fail(PLF_ERR_INVALID, "bad arguments");
     const Slot& sl = c->slots[slot];
     const std::vector<plf_keypoint>& kps = sl.orb[0].kps;
+    if (n_features < (int)kps.size()) return fail(PLF_ERR_INVALID, "occupied[] is shorter than the slot's keypoint count");
     const uint8_t* D = sl.orb[0].desc.data();
     const float invW = (float)PLF_GRID_COLS / ((float)c->p.width - 0.0f), invH = (float)PLF_GRID_ROWS / ((float)c->p.height - 0.0f);
     std::vector<std::vector<int>> grid(PLF_GRID_COLS * PLF_GRID_ROWS);           // Frame::AssignFeaturesToGrid
@@ -529,14 +530,15 @@ PLF_API int plf_cpu_search_by_projection(plf_ctx* c, int slot, const plf_proj_qu
 // from the projected points on: window search, best distance, assignment, rotation histogram, ComputeThreeMaxima (:2449-2490).
 // parity unpinned, like the local-map overload above.
 PLF_API int plf_cpu_search_by_projection_frame(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, int th_high,
-                                               int check_orientation, uint8_t* occupied, int32_t* feat_query, int32_t* match12,
-                                               int* n_matches) {
+                                               int check_orientation, uint8_t* occupied, int n_features, int32_t* feat_query,
+                                               int32_t* match12, int* n_matches) {
     if (!c || slot < 0 || slot >= (int)c->slots.size() || !queries || n_queries < 0 || !occupied || !feat_query)
         return fail(PLF_ERR_INVALID, "bad arguments");
     const Slot& sl = c->slots[slot];
     const std::vector<plf_keypoint>& kps = sl.orb[0].kps;
     const uint8_t* D = sl.orb[0].desc.data();
     const int N = (int)kps.size();
+    if (n_features < N) return fail(PLF_ERR_INVALID, "occupied[] / feat_query[] are shorter than the slot's keypoint count");
     const float invW = (float)PLF_GRID_COLS / ((float)c->p.width - 0.0f), invH = (float)PLF_GRID_ROWS / ((float)c->p.height - 0.0f);
     std::vector<std::vector<int>> grid(PLF_GRID_COLS * PLF_GRID_ROWS);
     for (int i = 0; i < N; ++i) {

@@ -80,6 +80,23 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _image(img):
+    """uint8 [H, W] whose rows may be padded (strides (stride, 1)): passed through with its row stride, like a cv::Mat
+    ROI; anything else is copied to a dense array."""
+    if not (isinstance(img, np.ndarray) and img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+            and img.strides[0] >= img.shape[1]):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+    return img
+
+
+def _image_batch(a):
+    """uint8 [B, H, W] with padded rows allowed (strides (H * stride, stride, 1)), as the ABI's [batch][h][stride]."""
+    if not (isinstance(a, np.ndarray) and a.dtype == np.uint8 and a.ndim == 3 and a.strides[2] == 1
+            and a.strides[1] >= a.shape[2] and a.strides[0] == a.shape[1] * a.strides[1]):
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a
+
+
 class Library:
     """One loaded ABI library (product or oracle)."""
 
@@ -195,7 +212,7 @@ class Frontend:
     # --- reference-shaped single-frame calls ---------------------------------------------------------------
     def orb_extract(self, side, img, lapping=(0, 0)):
         """ORBextractor::operator()(im, mask, kps, desc, vLappingArea) -> (monoIndex, keypoints, descriptors)."""
-        img = np.ascontiguousarray(img, dtype=np.uint8)
+        img = _image(img)
         h, w = img.shape
         kps = np.zeros(self.kp_cap, KEYPOINT_DT)
         desc = np.zeros((self.kp_cap, 32), np.uint8)
@@ -207,7 +224,7 @@ class Frontend:
 
     def line_extract(self, side, img):
         """Lineextractor::operator()(im, mask, keylines, desc) -> (keylines, descriptors)."""
-        img = np.ascontiguousarray(img, dtype=np.uint8)
+        img = _image(img)
         h, w = img.shape
         kls = np.zeros(self.kl_cap, KEYLINE_DT)
         desc = np.zeros((self.kl_cap, 32), np.uint8)
@@ -312,8 +329,9 @@ class Frontend:
 
     def frontend_batch(self, left, right, out=None):
         """Frame::Frame(stereo) extraction + matching for left/right arrays of shape [batch, H, W]."""
-        left = np.ascontiguousarray(left, np.uint8)
-        right = np.ascontiguousarray(right, np.uint8)
+        left, right = _image_batch(left), _image_batch(right)
+        if left.strides != right.strides:
+            left, right = np.ascontiguousarray(left), np.ascontiguousarray(right)
         b = left.shape[0]
         out = out or self.new_result(b)
         self.lib.check(self.lib.fn("frontend_batch")(self.ctx, _ptr(left), _ptr(right), b, left.strides[1],
@@ -361,7 +379,8 @@ class Frontend:
         match = np.full(len(queries), -1, np.int32)
         nm = C.c_int(0)
         self.lib.check(self.lib.fn("search_by_projection")(self.ctx, slot, _ptr(queries), len(queries), C.c_float(th),
-                                                           C.c_float(nn_ratio), int(th_high), _ptr(occupied), _ptr(match), C.byref(nm)))
+                                                           C.c_float(nn_ratio), int(th_high), _ptr(occupied), len(occupied),
+                                                           _ptr(match), C.byref(nm)))
         return match, nm.value
 
     def search_by_projection_frame(self, queries, occupied, th_high=100, check_orientation=True, slot=0):
@@ -372,8 +391,8 @@ class Frontend:
         fq = np.full(len(occupied), -1, np.int32); m12 = np.full(len(occupied), -1, np.int32)
         nm = C.c_int(0)
         self.lib.check(self.lib.fn("search_by_projection_frame")(self.ctx, slot, _ptr(queries), len(queries), int(th_high),
-                                                                 int(bool(check_orientation)), _ptr(occupied), _ptr(fq), _ptr(m12),
-                                                                 C.byref(nm)))
+                                                                 int(bool(check_orientation)), _ptr(occupied), len(occupied),
+                                                                 _ptr(fq), _ptr(m12), C.byref(nm)))
         return fq, m12, nm.value
 
     # ---- bag of words ------------------------------------------------------------------------------

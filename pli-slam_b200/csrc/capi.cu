@@ -146,6 +146,17 @@ static int build_geometry(plf_ctx* c, std::vector<PlfCell>& cells) {
     g.kpCap = ((p.n_features + 3 * L + 31) / 32) * 32;
     if (g.kpCap < kpOff) g.kpCap = ((kpOff + 31) / 32) * 32;
     g.klCap = p.lsd_nfeatures > 0 ? p.lsd_nfeatures : 4096;
+    // shared-memory bounds of the kernels that keep a whole list on chip: refuse loudly here instead of failing at launch
+    {
+        int maxQ = 0;
+        for (int l = 0; l < L; ++l) maxQ = std::max(maxQ, std::max(g.lv[l].quota, 4 * g.lv[l].nIni));
+        const size_t octree = (size_t)(maxQ + 16) * 36;      // octree_kernel: QNode (28 B) + two ints per pool entry, 16-bit links
+        if (maxQ + 16 > 32000 || octree > 200 * 1024)
+            return fail(PLF_ERR_UNSUPPORTED, "n_features too large: the quadtree node pool of one level exceeds shared memory (about 5800 features per level)");
+        if ((size_t)g.kpCap * sizeof(int) > 200 * 1024)
+            return fail(PLF_ERR_UNSUPPORTED, "n_features too large: the stereo cull keeps one SAD value per keypoint in shared memory (about 51000 features)");
+        if (g.klCap > 8192) return fail(PLF_ERR_UNSUPPORTED, "lsd_nfeatures above 8192");
+    }
     // LSD constants (OpenCV LineSegmentDetectorImpl::flsd)
     const double kPi = 3.14159265358979323846;
     g.lsdScale = p.lsd_scale;
@@ -532,7 +543,12 @@ PLF_API int plf_stereo_match_lines(plf_ctx* c, float* disp_se, double* le, int32
 
 static int ensure_match_scratch(plf_ctx* c, int n) {
     if (n <= c->mCap) return PLF_OK;
-    if (c->d_mA) { cudaFree(c->d_mA); cudaFree(c->d_mB); cudaFree(c->d_mOut); cudaFree(c->d_mOut2); }
+    if (c->d_mA) cudaFree(c->d_mA);
+    if (c->d_mB) cudaFree(c->d_mB);
+    if (c->d_mOut) cudaFree(c->d_mOut);
+    if (c->d_mOut2) cudaFree(c->d_mOut2);
+    c->d_mA = nullptr; c->d_mB = nullptr; c->d_mOut = nullptr; c->d_mOut2 = nullptr;   // a failed allocation below leaves no stale pointer
+    c->mCap = 0;
     const int cap = std::max(n, 1024);
     PLF_CUDA_OK(dalloc(&c->d_mA, (size_t)cap * 32));
     PLF_CUDA_OK(dalloc(&c->d_mB, (size_t)cap * 32));

@@ -87,11 +87,18 @@ static int window_candidates(plf_ctx* c, int slot, const std::vector<PlfWinQ>& q
 }
 
 PLF_API int plf_search_by_projection(plf_ctx* c, int slot, const plf_proj_query* queries, int n_queries, float th, float nn_ratio,
-                                     int th_high, uint8_t* occupied, int32_t* match, int* n_matches) {
-    if (!c || slot < 0 || slot >= c->p.max_batch || !queries || n_queries < 0 || !occupied || !match)
+                                     int th_high, uint8_t* occupied, int n_features, int32_t* match, int* n_matches) {
+    if (!c || slot < 0 || slot >= c->p.max_batch || !queries || n_queries < 0 || !occupied || !match || n_features < 0)
         return fail(PLF_ERR_INVALID, "bad arguments");
     if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "search_by_projection before the frame was extracted and stereo-matched");
     if (n_matches) *n_matches = 0;
+    {   // occupied[] is indexed by feature: it must cover the slot's left keypoints
+        int N = 0;
+        PLF_CUDA_OK(cudaSetDevice(c->device));
+        PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
+        PLF_CUDA_OK(cudaMemcpy(&N, c->d_nKp + slot * 2, 4, cudaMemcpyDeviceToHost));
+        if (n_features < N) return fail(PLF_ERR_INVALID, "occupied[] is shorter than the slot's keypoint count");
+    }
     if (n_queries == 0) return PLF_OK;
     std::vector<PlfWinQ> q(n_queries);
     for (int i = 0; i < n_queries; ++i) {
@@ -134,9 +141,9 @@ PLF_API int plf_search_by_projection(plf_ctx* c, int slot, const plf_proj_query*
 }
 
 PLF_API int plf_search_by_projection_frame(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, int th_high,
-                                           int check_orientation, uint8_t* occupied, int32_t* feat_query, int32_t* match12,
-                                           int* n_matches) {
-    if (!c || slot < 0 || slot >= c->p.max_batch || !queries || n_queries < 0 || !occupied || !feat_query)
+                                           int check_orientation, uint8_t* occupied, int n_features, int32_t* feat_query,
+                                           int32_t* match12, int* n_matches) {
+    if (!c || slot < 0 || slot >= c->p.max_batch || !queries || n_queries < 0 || !occupied || !feat_query || n_features < 0)
         return fail(PLF_ERR_INVALID, "bad arguments");
     if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "search_by_projection_frame before the frame was extracted and stereo-matched");
     PLF_CUDA_OK(cudaSetDevice(c->device));
@@ -145,6 +152,7 @@ PLF_API int plf_search_by_projection_frame(plf_ctx* c, int slot, const plf_frame
     int N = 0;
     PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
     PLF_CUDA_OK(cudaMemcpy(&N, c->d_nKp + img, 4, cudaMemcpyDeviceToHost));
+    if (n_features < N) return fail(PLF_ERR_INVALID, "occupied[] / feat_query[] are shorter than the slot's keypoint count");
     std::vector<plf_keypoint> kps((size_t)std::max(N, 1));
     if (N > 0) PLF_CUDA_OK(cudaMemcpy(kps.data(), c->d_kp + (size_t)img * c->g.kpCap, (size_t)N * sizeof(plf_keypoint), cudaMemcpyDeviceToHost));
     for (int f = 0; f < N; ++f) { feat_query[f] = -1; if (match12) match12[f] = -1; }

@@ -161,7 +161,11 @@ int plf_launch_stereo_points(plf_ctx* c, int slotFirst, int nSlots) {
     plf_mark(c, "stereo_points");
     stereo_points_kernel<<<dim3((g.kpCap + 7) / 8, nSlots), 256, 0, c->stream>>>(
         g, c->d_pyr, c->d_kp, c->d_desc, c->d_nKp, c->d_uRight, c->d_depth, c->d_sad, c->p.bf, c->p.fx, slotFirst);
-    stereo_cull_kernel<<<nSlots, 1024, g.kpCap * sizeof(int), c->stream>>>(g, c->d_nKp, c->d_uRight, c->d_depth,
+    const size_t smem = g.kpCap * sizeof(int);          // bounded by build_geometry (<= 200 KB)
+    static size_t s_granted[64] = {};
+    if (plf_raise_smem_optin(s_granted, c->device, smem))
+        cudaFuncSetAttribute(stereo_cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    stereo_cull_kernel<<<nSlots, 1024, smem, c->stream>>>(g, c->d_nKp, c->d_uRight, c->d_depth,
                                                                           c->d_sad, slotFirst);
     return 2;
 }

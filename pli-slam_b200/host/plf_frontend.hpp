@@ -9,6 +9,7 @@
 // (and include <opencv2/core.hpp> first) to get cv::Mat / cv::KeyPoint / KeyLine overloads — the PODs are layout
 // identical, so the conversion is a reinterpret_cast.
 #pragma once
+#include <array>
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
@@ -247,7 +248,7 @@ public:
         match.assign(mapPoints.size(), -1);
         int n = 0;
         plf::check(plf_search_by_projection(ctx_->get(), slot_, mapPoints.data(), (int)mapPoints.size(), th, mfNNratio, TH_HIGH,
-                                            occupied.data(), match.data(), &n), "plf_search_by_projection");
+                                            occupied.data(), (int)occupied.size(), match.data(), &n), "plf_search_by_projection");
         return n;
     }
     // int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono, match12), projection done by the caller
@@ -257,7 +258,8 @@ public:
         match12.assign(occupied.size(), -1);
         int n = 0;
         plf::check(plf_search_by_projection_frame(ctx_->get(), slot_, lastFramePoints.data(), (int)lastFramePoints.size(), TH_HIGH,
-                                                  mbCheckOrientation ? 1 : 0, occupied.data(), featQuery.data(), match12.data(), &n),
+                                                  mbCheckOrientation ? 1 : 0, occupied.data(), (int)occupied.size(), featQuery.data(),
+                                                  match12.data(), &n),
                    "plf_search_by_projection_frame");
         return n;
     }

@@ -1,6 +1,5 @@
 // Drives the C++ host mirror (pli-slam_b200/host/plf_frontend.hpp) the way Frame::Frame(stereo) drives the reference
 // classes (src/Frame.cc:128-163) and prints a few counters; tests/test_host_shim.py compares them with the oracle.
-#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -12,7 +11,7 @@ static std::vector<uint8_t> read_file(const char* p) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 5) { fprintf(stderr, "usage: %s left.raw right.raw W H\n", argv[0]); return 2; }
+    if (argc < 5) { fprintf(stderr, "usage: %s left.raw right.raw W H [mapx.f32 mapy.f32]\n", argv[0]); return 2; }
     const int W = atoi(argv[3]), H = atoi(argv[4]);
     std::vector<uint8_t> L = read_file(argv[1]), R = read_file(argv[2]);
     if ((int)L.size() != W * H || (int)R.size() != W * H) { fprintf(stderr, "bad raw size\n"); return 2; }
@@ -46,10 +45,50 @@ int main(int argc, char** argv) {
         for (auto& d : mvDisparity_l) stereoLines += d.first >= 0;
         unsigned long long h = 1469598103934665603ull;
         for (uint8_t b : mDescriptors.bytes) h = (h ^ b) * 1099511628211ull;
+        // --- the frame-level tail: grid, area lookup, back-projection (FrameTail), on the state of the frame above
+        ORB_SLAM3::FrameTail tail(ctx);
+        tail.AssignFeaturesToGrid();
+        std::vector<size_t> area = tail.GetFeaturesInArea(mvKeys, 376.f, 240.f, 60.f, 0, 3);
+        unsigned long long hArea = 1469598103934665603ull;
+        for (size_t i : area) hArea = (hArea ^ (unsigned long long)i) * 1099511628211ull;
+        const float Rwc[9] = {0.96f, -0.28f, 0.f, 0.28f, 0.96f, 0.f, 0.f, 0.f, 1.f}, Ow[3] = {0.5f, -1.25f, 2.f};
+        std::vector<float> x3D;
+        std::vector<double> lines3D;
+        tail.BackProject(Rwc, Ow, 435.2047f, 367.4517f, 252.2008f, (int)mvKeys.size(), (int)mvKeys_Line.size(), x3D, lines3D);
+        double sumX = 0, sumL = 0;
+        for (float v : x3D) sumX += v;
+        for (double v : lines3D) sumL += v;
+        // --- lapping area {0, 1000} (the monocular constructor, src/Frame.cc:360-361) and a padded-row view of the same image
+        std::vector<ORB_SLAM3::KeyPoint> kLap, kPad;
+        plf::Desc dLap, dPad;
+        std::vector<int> lapMono = {0, 1000};
+        const int monoLap = orbL(imL, none, kLap, dLap, lapMono);
+        const int S = W + 40;
+        std::vector<uint8_t> padded((size_t)S * H, 0x5A);
+        for (int y = 0; y < H; ++y) std::copy(L.begin() + (size_t)y * W, L.begin() + (size_t)(y + 1) * W, padded.begin() + (size_t)y * S);
+        orbL(plf::Mat8(padded.data(), H, W, S), none, kPad, dPad, lap);
+        const int padSame = kPad.size() == mvKeys.size() && dPad.bytes == mDescriptors.bytes;
+        const int lapReversed = kLap.size() == mvKeys.size() && !kLap.empty() && kLap.back().x == mvKeys.front().x &&
+                                kLap.back().y == mvKeys.front().y && kLap.front().x == mvKeys.back().x;
+        // --- rectification in front of the path (Rectifier), when maps are given
+        unsigned long long hRect = 0;
+        if (argc >= 7) {
+            std::vector<uint8_t> mx = read_file(argv[5]), my = read_file(argv[6]);
+            if ((int)mx.size() != W * H * 4 || (int)my.size() != W * H * 4) { fprintf(stderr, "bad map size\n"); return 2; }
+            ORB_SLAM3::Rectifier rect(ctx);
+            rect.setMaps(0, reinterpret_cast<const float*>(mx.data()), reinterpret_cast<const float*>(my.data()), W, H);
+            std::vector<uint8_t> imRect;
+            rect.remap(0, imL, imRect);
+            hRect = 1469598103934665603ull;
+            for (uint8_t b : imRect) hRect = (hRect ^ b) * 1099511628211ull;
+        }
         printf("{\"N\": %zu, \"Nr\": %zu, \"mono\": [%d, %d], \"Nl\": %zu, \"Nlr\": %zu, \"stereo_pts\": %d, \"sum_u\": %.4f, "
-               "\"stereo_lines\": %d, \"nnr\": %d, \"desc_fnv\": %llu, \"hamming01\": %d, \"empty\": %d}\n",
+               "\"stereo_lines\": %d, \"nnr\": %d, \"desc_fnv\": %llu, \"hamming01\": %d, \"area_n\": %zu, \"area_fnv\": %llu, "
+               "\"sum_x3d\": %.6f, \"sum_l3d\": %.9f, \"mono_lap\": %d, \"lap_reversed\": %d, \"pad_same\": %d, \"rect_fnv\": %llu, "
+               "\"empty\": %d}\n",
                mvKeys.size(), mvKeysRight.size(), monoLeft, monoRight, mvKeys_Line.size(), mvKeysRight_Line.size(), stereoPts,
                sumU, stereoLines, nnr, h, ORB_SLAM3::ORBmatcher::DescriptorDistance(mDescriptors.row(0), mDescriptors.row(1)),
+               area.size(), hArea, sumX, sumL, monoLap, lapReversed, padSame, hRect,
                orbL(none, none, mvKeys, mDescriptors, lap));
     } catch (const std::exception& e) {
         fprintf(stderr, "error: %s\n", e.what());

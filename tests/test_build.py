@@ -64,3 +64,17 @@ def test_sass_has_no_vimnmx3(built):
     sass = subprocess.run([cuobjdump, "-sass", built], capture_output=True, text=True).stdout
     assert "sm_100a" in sass or "SM100a" in sass.upper() or "EF_CUDA_SM100" in sass
     assert "VIMNMX3" not in sass
+
+
+def test_headers_are_self_contained_and_assert_their_layouts(tmp_path):
+    """A translation unit that includes ONLY the host mirror (C++) or ONLY the C header (C11) compiles; the headers carry
+    static assertions on the 28 / 68 / 56 / 72-byte records that cross the boundary."""
+    cpp = tmp_path / "only_hpp.cpp"
+    cpp.write_text('#include "%s"\nint main() { return 0; }\n' % os.path.join(ROOT, "pli-slam_b200", "host", "plf_frontend.hpp"))
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", str(cpp)])
+    c = tmp_path / "only_h.c"
+    c.write_text('#include "%s"\nint main(void) { return (int)sizeof(plf_keyline) - 68; }\n' % os.path.join(ROOT, "include", "plf_b200.h"))
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-fsyntax-only", str(c)])
+    hdr = open(os.path.join(ROOT, "include", "plf_b200.h")).read()
+    for rec, size in (("plf_keypoint", 28), ("plf_keyline", 68), ("plf_proj_query", 56), ("plf_frame_query", 72)):
+        assert "static_assert(sizeof(%s) == %d" % (rec, size) in hdr

@@ -217,6 +217,8 @@ def test_batch64_full_size_properties(plf, product, oracle):
     (752, 480, dict(best_lr_matches=0, matching_s_ws=20, min_ratio_12_l=0.8, line_sim_th=0.5)),
     (752, 480, dict(lsd_refine=1)),                               # LSD_REFINE_STD: re-grow + radius reduction
     (1280, 720, dict(lsd_refine=1, lsd_density_th=0.8, lsd_nfeatures=0)),
+    (1241, 376, dict(n_features=2000)),                            # Examples/Stereo/Config/KITTI00-02.yaml: 4 quadtree roots
+    (1241, 376, dict(n_features=2000, ini_th_fast=12)),            # KITTI04-12.yaml (iniThFAST 12)
 ])
 def test_shapes_and_parameters(plf, product, oracle, W, H, kw):
     """Geometry and parameter sweep (batch of 2 pairs): every output array identical to the oracle."""
@@ -239,6 +241,67 @@ def test_shapes_and_parameters(plf, product, oracle, W, H, kw):
         assert np.array_equal(rg.line_match12[b, :nl], ro.line_match12[b, :nl])
         assert np.array_equal(rg.disp_se[b, :nl], ro.disp_se[b, :nl])
         assert np.allclose(rg.le[b, :nl], ro.le[b, :nl], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("lap", [(0, 1000), (300, 500), (100, 101), (-5, -1)])
+def test_lapping_area_on_device(plf, product, oracle, lap):
+    """vLappingArea of ORBextractor::operator() (src/ORBextractor.cc:1135-1146; the monocular constructor passes {0, 1000},
+    src/Frame.cc:360-361): rows inside the interval are written back to front, the rest front to back, the return value is
+    the number of the rest.  3000 features so that more than 1024 rows fall inside (the placement kernel carries its
+    running counts across 1024-thread chunks).  Row order, every field, every descriptor byte, monoIndex: identical."""
+    L, R = plf.synth_pair(752, 480, 3)
+    f = plf.Frontend(product, n_features=3000, has_lines=0, max_batch=1)
+    o = plf.Frontend(oracle, n_features=3000, has_lines=0, max_batch=1)
+    for side, img in ((0, L), (1, R)):
+        mg, kg, dg = f.orb_extract(side, img, lapping=lap)
+        mo, ko, do = o.orb_extract(side, img, lapping=lap)
+        assert mg == mo and np.array_equal(kg, ko) and np.array_equal(dg, do)
+        inside = int(((ko["x"] >= lap[0]) & (ko["x"] <= lap[1])).sum())
+        assert mo == len(ko) - inside
+        if lap == (0, 1000):
+            assert mo == 0 and inside > 2048
+        if lap == (300, 500):
+            assert 256 < inside < len(ko)
+
+
+def test_row_stride_larger_than_width(plf, product, oracle):
+    """Images whose rows are padded (stride = width + 40, cv::Mat ROIs): the single-frame calls and the batched upload
+    read only the first `width` bytes of each row."""
+    W, H, S = 752, 480, 752 + 40
+    L, R = plf.synth_batch(W, H, [61, 62, 63])
+    rng = np.random.default_rng(9)
+    padL = rng.integers(0, 256, (3, H, S), dtype=np.uint8)
+    padR = rng.integers(0, 256, (3, H, S), dtype=np.uint8)
+    padL[:, :, :W], padR[:, :, :W] = L, R
+    vL, vR = padL[:, :, :W], padR[:, :, :W]
+    assert vL.strides == (H * S, S, 1)
+    f, o = plf.Frontend(product, max_batch=3), plf.Frontend(oracle, max_batch=3)
+    for side, view, dense in ((0, vL[1], L[1]), (1, vR[1], R[1])):
+        mg, kg, dg = f.orb_extract(side, view)
+        mo, ko, do = o.orb_extract(side, dense)
+        assert mg == mo and np.array_equal(kg, ko) and np.array_equal(dg, do)
+        klg, ldg = f.line_extract(side, view)
+        klo, ldo = o.line_extract(side, dense)
+        assert np.array_equal(klg, klo) and np.array_equal(ldg, ldo)
+    rg, ro = f.frontend_batch(vL, vR), o.frontend_batch(L, R)
+    for b in range(3):
+        n, nl = int(ro.n_kp_left[b]), int(ro.n_kl_left[b])
+        assert int(rg.n_kp_left[b]) == n and int(rg.n_kl_left[b]) == nl
+        assert np.array_equal(rg.kp_left[b, :n], ro.kp_left[b, :n]) and np.array_equal(rg.desc_left[b, :n], ro.desc_left[b, :n])
+        assert np.array_equal(rg.u_right[b, :n], ro.u_right[b, :n])
+        assert np.array_equal(rg.kl_left[b, :nl], ro.kl_left[b, :nl]) and np.array_equal(rg.disp_se[b, :nl], ro.disp_se[b, :nl])
+
+
+def test_limits_are_refused_at_create(plf, product):
+    """Feature budgets whose on-chip lists would not fit are refused by plf_create (PLF_ERR_UNSUPPORTED), not at launch."""
+    for kw in (dict(n_features=60000), dict(n_features=40000, n_levels=2), dict(lsd_nfeatures=9000)):
+        with pytest.raises(plf.PlfError) as e:
+            plf.Frontend(product, max_batch=1, **kw)
+        assert e.value.code == 5
+    f = plf.Frontend(product, n_features=15000, has_lines=0, max_batch=1)      # above the old 12 k stereo-cull limit: works
+    L, R = plf.synth_pair(752, 480, 2)
+    r = f.frontend_batch(L[None], R[None])
+    assert int(r.n_kp_left[0]) > 3000 and int((r.u_right[0] >= 0).sum()) > 300
 
 
 def test_degenerate_images(plf, product, oracle):
@@ -462,6 +525,13 @@ def test_search_by_projection_matches_oracle(plf, product, oracle, th):
         assert no > 300
     with pytest.raises(plf.PlfError):
         plf.Frontend(product, max_batch=1).search_by_projection(q[:4], np.zeros(10, np.uint8))     # before extraction
+    for fe in (f, o):                                                                               # occupied[] shorter than Frame::N
+        with pytest.raises(plf.PlfError) as e:
+            fe.search_by_projection(q[:4], np.zeros(10, np.uint8), slot=0)
+        assert e.value.code == 1
+        with pytest.raises(plf.PlfError) as e:
+            fe.search_by_projection_frame(np.zeros(2, plf.FRAME_QUERY_DT), np.zeros(10, np.uint8), slot=0)
+        assert e.value.code == 1
 
 
 @pytest.mark.parametrize("mode,check", [("around", True), ("forward", True), ("backward", False)])

@@ -36,7 +36,10 @@ def test_shim_matches_oracle(tmp_path, plf, oracle, pair1):
     exe = _build(tmp_path)
     L, R = pair1
     L.tofile(tmp_path / "l.raw"); R.tofile(tmp_path / "r.raw")
-    out = subprocess.run([exe, str(tmp_path / "l.raw"), str(tmp_path / "r.raw"), "752", "480"], capture_output=True, text=True)
+    mx, my = plf.rectify_maps(752, 480, 0)
+    mx.tofile(tmp_path / "mx.f32"); my.tofile(tmp_path / "my.f32")
+    out = subprocess.run([exe, str(tmp_path / "l.raw"), str(tmp_path / "r.raw"), "752", "480", str(tmp_path / "mx.f32"),
+                          str(tmp_path / "my.f32")], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     got = json.loads(out.stdout.strip().splitlines()[-1])
     o = plf.Frontend(oracle)
@@ -56,3 +59,23 @@ def test_shim_matches_oracle(tmp_path, plf, oracle, pair1):
     assert got["stereo_lines"] == int((disp[:, 0] >= 0).sum()) and got["nnr"] == nnr
     assert got["desc_fnv"] == h
     assert got["hamming01"] == int(np.unpackbits(d[0] ^ d[1]).sum()) and got["empty"] == -1
+
+    def fnv(values):
+        x = 1469598103934665603
+        for v in values:
+            x = ((x ^ int(v)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return x
+    # FrameTail: grid + area lookup + back-projection against the oracle
+    st, ix = o.feature_grid(0, 1)
+    area = o.features_in_area(k, st[0], ix[0], 376.0, 240.0, 60.0, 0, 3)
+    assert got["area_n"] == len(area) > 5 and got["area_fnv"] == fnv(area)
+    Rwc = np.array([0.96, -0.28, 0, 0.28, 0.96, 0, 0, 0, 1], np.float32).reshape(1, 3, 3)
+    x3d, l3d = o.backproject(Rwc, np.array([[0.5, -1.25, 2.0]], np.float32), 435.2047, 367.4517, 252.2008)
+    assert abs(got["sum_x3d"] - float(x3d[0, :len(k)].astype(np.float64).sum())) < 1e-3 * max(1.0, abs(got["sum_x3d"]))
+    assert abs(got["sum_l3d"] - float(l3d[0, :len(kl)].sum())) < 1e-6 * max(1.0, abs(got["sum_l3d"]))
+    # lapping area {0, 1000}: every row back to front, monoIndex 0; padded rows give the dense result
+    assert got["mono_lap"] == o.orb_extract(0, L, lapping=(0, 1000))[0] == 0 and got["lap_reversed"] == 1
+    assert got["pad_same"] == 1
+    # Rectifier
+    o.rectify_set_maps(0, mx, my)
+    assert got["rect_fnv"] == fnv(o.rectify(0, L).tobytes())

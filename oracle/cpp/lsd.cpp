@@ -1,5 +1,9 @@
 // TEST INFRASTRUCTURE ONLY — CPU oracle, LSD + KeyLine construction.  See lsd.h for provenance.
 #include "lsd.h"
+#include <array>
+#include <map>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -412,5 +416,269 @@ void lsd_stats(const LsdConfig& c, const Img8& img, long long out[8]) {
         else if (reg.size() < 16) out[5]++;
         else { out[6]++; out[7] += (long long)reg.size(); }
     }
+}
+}  // namespace plfo
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Design aid for the CUDA region grower (TEST INFRASTRUCTURE, like everything here): a lock-step emulation of the
+// "one lane per region" streaming scheme of csrc/lsd_stream.cu — up to 32 regions of ONE image in flight in the lanes of
+// a warp, every lane running the scalar region_grow state machine (one list entry = 8 neighbours per step) against an
+// owner map; tickets = seed positions (earlier position = higher priority); in-order commit.  Returns the segments
+// (which must equal lsd_detect's: the protocol is exact whatever the heuristics do) and the step /
+// occupancy / kill counters the design was tuned with.
+//
+// Protocol.  O[q]: 0 free, 0xFFFFFFFF committed (or undefined pixel), else tag = seed position + 1 of the in-flight
+// region that claims q.  A region with tag T visiting q: committed or mine -> skip; free -> claim if aligned; claimed by a
+// LATER ticket -> steal if aligned (the victim is killed); claimed by an EARLIER in-flight ticket E -> skip, and if it
+// would have been aligned remember "T depends on E".  Killing a ticket withdraws its claims and kills every ticket that
+// depends on it.  A finished region waits; the commit pointer walks the candidate list in order and commits the
+// region of each candidate whose pixel is still uncommitted when its turn comes (growing it first if nobody has).
+namespace plfo {
+struct StreamSimParams { int window; int fifo; double dperp; int heuristic; int lanes; };
+void lsd_stream_sim(const LsdConfig& c, const Img8& img, const StreamSimParams& sp, std::vector<float>& segs, long long st[16]) {
+    const double prec = kPi * c.ang_th / 180, p = c.ang_th / 180;
+    const double rho = c.quant / std::sin(prec);
+    Lsd L(c);
+    LsdState stt;
+    if (c.scale != 1) {
+        const double sigma = (c.scale < 1) ? (c.sigma_scale / c.scale) : c.sigma_scale;
+        const unsigned h = (unsigned)std::ceil(sigma * std::sqrt(2 * 3.0 * std::log(10.0)));
+        std::vector<int> taps;
+        gaussian_taps_fixed(1 + 2 * (int)h, sigma, taps);
+        Img8 g;
+        gaussian_blur_u8(img, g, taps.data(), 1 + 2 * (int)h);
+        resize_linear_exact_u8(g, stt.scaled, c.scale);
+    } else stt.scaled = img;
+    L.ll_angle(stt.scaled, rho, stt.angleDeg);
+    const int W = L.W, H = L.H;
+    const double logNT = 5 * (std::log10((double)W) + std::log10((double)H)) / 2 + std::log10(11.0);
+    const int minReg = (int)(size_t)(-logNT / std::log10(p));
+    for (int k = 0; k < 16; ++k) st[k] = 0;
+    segs.clear();
+    const uint32_t FREE = 0u, COMMITTED = 0xFFFFFFFFu;
+    std::vector<uint32_t> O((size_t)W * H, COMMITTED);
+    std::vector<int> S;
+    for (const auto& op : L.ordered) {
+        const size_t idx = (size_t)op.y * W + op.x;
+        if (L.angles[idx] == kNotDef) continue;
+        O[idx] = FREE;
+        S.push_back((int)idx);
+    }
+    const int ns = (int)S.size();
+    const int NL = sp.lanes;
+    enum { GROW = 1, DONE = 2 };
+    struct Ticket {
+        int state = GROW, lane = -1, i = 0; float sumdx = 0, sumdy = 0; double angle = 0; int sx = 0, sy = 0;
+        std::vector<int> list; std::vector<uint32_t> deps; bool depAll = false;   // depAll: more than 4 dependencies -> on every earlier ticket
+        long long epoch = 0;          // kill counter when the ticket started
+    };
+    long long killEpoch = 0;
+    std::vector<long long> killStamp(4096, -1);     // hashed by tag: epoch of the last kill that hashes there (collisions only invalidate more)
+    auto dep_broken = [&](const Ticket& t) {
+        if (t.depAll) return killEpoch > t.epoch;
+        for (uint32_t d : t.deps) if (killStamp[d & 4095] >= t.epoch) return true;
+        return false;
+    };
+    std::map<uint32_t, Ticket> T;                 // live tickets by tag
+    std::vector<uint32_t> laneTag(NL, 0);         // tag growing in each lane (0 = idle)
+    std::vector<int> laneDone(NL, 0);             // finished, uncommitted tickets per lane
+    std::vector<std::pair<int, uint32_t>> blocked;   // (candidate position, blocker tag): not picked while the blocker grows
+    std::vector<int> ready;                          // candidate positions released by a finished / killed blocker or a killed ticket
+    const size_t BLOCKED_CAP = 1024, READY_CAP = 1024, TICKET_CAP = 2048;
+    int cp = 0, scanPos = 0;
+    static const int ddx[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, ddy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+    std::vector<uint32_t> killQueue;
+    auto start_ticket = [&](int l, int pos) {
+        Ticket t;
+        const int q = S[pos];
+        t.lane = l; t.sx = q % W; t.sy = q / W; t.angle = L.angles[q];
+        t.sumdx = (float)std::cos(t.angle); t.sumdy = (float)std::sin(t.angle);
+        t.list.push_back(q);
+        const uint32_t tag = (uint32_t)pos + 1u, o = O[q];
+        if (o != FREE && o != COMMITTED && o > tag) killQueue.push_back(o);     // a forced ticket steals its seed
+        O[q] = tag;
+        laneTag[l] = tag;
+        t.epoch = killEpoch;
+        T[tag] = t;
+    };
+    auto kill_all = [&]() {          // kill the queued victims and, transitively, every ticket that depends on one
+        while (!killQueue.empty()) {
+            const uint32_t v = killQueue.back();
+            killQueue.pop_back();
+            auto it = T.find(v);
+            if (it == T.end()) continue;
+            Ticket& t = it->second;
+            for (int q : t.list) if (O[q] == v) O[q] = FREE;
+            st[12] += (long long)t.list.size();
+            st[3] += ((long long)t.list.size() + 31) / 32;            // cooperative withdrawal steps
+            if (t.state == GROW) laneTag[t.lane] = 0; else laneDone[t.lane]--;
+            T.erase(it);
+            st[11]++;
+            if (ready.size() < READY_CAP) ready.push_back((int)v - 1); else scanPos = std::min(scanPos, (int)v - 1);
+            killStamp[v & 4095] = killEpoch++;          // dependents find out lazily: while growing, or at their commit
+        }
+    };
+    long guard = 0;
+    while (true) {
+        if (++guard > 2000000) { st[15] = -1; break; }
+        // ---- 1. commit walk ----
+        {
+            int walked = 0;
+            while (cp < ns) {
+                const int q = S[cp];
+                const uint32_t o = O[q], tag = (uint32_t)cp + 1u;
+                if (o == COMMITTED) { ++cp; ++walked; continue; }
+                if (o == tag) {
+                    auto it = T.find(tag);
+                    if (it == T.end()) { st[15] = -4; break; }
+                    if (it->second.state != DONE) break;               // still growing
+                    if (dep_broken(it->second)) { killQueue.push_back(tag); kill_all(); st[10]++; continue; }   // a ticket it relied on was killed: grow again
+                    Ticket& t = it->second;
+                    for (int qq : t.list) O[qq] = COMMITTED;
+                    st[3] += ((long long)t.list.size() + 31) / 32;
+                    if ((int)t.list.size() >= minReg) {
+                        std::vector<RegPt> reg(t.list.size());
+                        for (size_t j = 0; j < t.list.size(); ++j) reg[j] = {t.list[j] % W, t.list[j] / W};
+                        Lsd::Rect rec;
+                        L.region2rect(reg, t.angle, prec, p, rec);
+                        double r[4] = {rec.x1, rec.y1, rec.x2, rec.y2};
+                        for (int k = 0; k < 4; ++k) { r[k] += 0.5; if (c.scale != 1) r[k] /= c.scale; segs.push_back((float)r[k]); }
+                    }
+                    laneDone[t.lane]--;
+                    if (t.lane == 0) st[2] += 0, st[12] += 0;
+                    if ((long long)t.list.size() > st[14]) st[14] = (long long)t.list.size();
+                    if (t.lane == 0) st[13] += (long long)t.list.size();
+                    T.erase(it);
+                    st[4]++;
+                    ++cp; ++walked;
+                    continue;
+                }
+                // free, or claimed by a later ticket: this candidate starts its own region now on the reserved lane 0
+                if (laneTag[0] == 0) { start_ticket(0, cp); st[5]++; kill_all(); }
+                break;
+            }
+            st[2] += (walked + 31) / 32;
+        }
+        if (cp >= ns && T.empty()) break;
+        // ---- 2. pick ----
+        {
+            auto lane_free = [&](int l) { return laneTag[l] == 0 && laneDone[l] < sp.fifo; };
+            int nIdle = 0;
+            for (int l = 1; l < NL; ++l) nIdle += lane_free(l);
+            if (scanPos < cp) scanPos = cp;
+            auto find_blocker = [&](int q) -> uint32_t {
+                if (!sp.heuristic) return 0u;
+                const int x = q % W, y = q / W;
+                const double a = L.angles[q];
+                for (int l = 0; l < NL; ++l) {
+                    if (!laneTag[l]) continue;
+                    const Ticket& t = T[laneTag[l]];
+                    double d = std::fabs(a - t.angle);
+                    if (d > 1.5 * kPi) d = std::fabs(d - 2 * kPi);
+                    if (d > prec) continue;
+                    const double perp = std::fabs(-(x - t.sx) * std::sin(t.angle) + (y - t.sy) * std::cos(t.angle));
+                    if (perp <= sp.dperp) return laneTag[l];
+                }
+                return 0u;
+            };
+            // released candidates first
+            for (size_t r = 0; r < ready.size() && nIdle > 0 && T.size() < TICKET_CAP;) {
+                const int pos = ready[r];
+                {
+                    const uint32_t o = O[S[pos]];
+                    if (pos < cp || o == COMMITTED || (o != FREE && o <= (uint32_t)pos + 1u)) { ready[r] = ready.back(); ready.pop_back(); continue; }
+                }
+                if (pos == cp) { ++r; continue; }
+                const uint32_t blocker = find_blocker(S[pos]);
+                if (blocker) {
+                    if (blocked.size() < BLOCKED_CAP) { blocked.push_back({pos, blocker}); st[6]++; ready[r] = ready.back(); ready.pop_back(); }
+                    else ++r;
+                    continue;
+                }
+                for (int l = 1; l < NL; ++l) if (lane_free(l)) { start_ticket(l, pos); --nIdle; st[7]++; break; }
+                ready[r] = ready.back(); ready.pop_back();
+            }
+            int scans = 0;
+            while (nIdle > 0 && scanPos < ns && scanPos < cp + sp.window && scans < 2 && blocked.size() + 32 <= BLOCKED_CAP && T.size() + 32 <= TICKET_CAP) {
+                ++scans; st[1]++;
+                const int end = std::min(ns, scanPos + 32);
+                int pos = scanPos;
+                for (; pos < end && nIdle > 0; ++pos) {
+                    const int q = S[pos];
+                    if (O[q] != FREE || pos == cp) continue;
+                    const uint32_t blocker = find_blocker(q);
+                    if (blocker) { blocked.push_back({pos, blocker}); st[6]++; continue; }
+                    for (int l = 1; l < NL; ++l) if (lane_free(l)) { start_ticket(l, pos); --nIdle; st[7]++; break; }
+                }
+                scanPos = pos;
+            }
+            kill_all();
+        }
+        // ---- 3. one lock-step grow step ----
+        int active = 0;
+        std::vector<std::array<uint32_t, 8>> snap(NL);
+        for (int l = 0; l < NL; ++l) {
+            if (!laneTag[l]) continue;
+            ++active;
+            Ticket& t = T[laneTag[l]];
+            const int e = t.list[t.i], ex = e % W, ey = e / W;
+            for (int k = 0; k < 8; ++k) {
+                const int xx = ex + ddx[k], yy = ey + ddy[k];
+                snap[l][k] = (xx < 0 || yy < 0 || xx >= W || yy >= H) ? COMMITTED : O[(size_t)yy * W + xx];
+            }
+        }
+        for (int k = 0; k < 8; ++k)
+            for (int l = 0; l < NL; ++l) {
+                const uint32_t tag = laneTag[l];
+                if (!tag) continue;
+                Ticket& t = T[tag];
+                const uint32_t o = snap[l][k];
+                if (o == COMMITTED || o == tag) continue;
+                const int e = t.list[t.i];
+                const int xx = e % W + ddx[k], yy = e / W + ddy[k];
+                if (!L.is_aligned(xx, yy, t.angle, prec)) continue;
+                const size_t q = (size_t)yy * W + xx;
+                const uint32_t o2 = O[q];                                   // fresh read before the claim
+                if (o2 == COMMITTED || o2 == tag) continue;
+                if (o2 != FREE && o2 < tag) {                               // an earlier in-flight ticket has it: I depend on that ticket
+                    if (!t.depAll && std::find(t.deps.begin(), t.deps.end(), o2) == t.deps.end()) {
+                        if (t.deps.size() < 4) t.deps.push_back(o2); else t.depAll = true;
+                    }
+                    continue;
+                }
+                if (o2 != FREE) { killQueue.push_back(o2); st[8]++; }       // steal from a later ticket
+                O[q] = tag;
+                t.list.push_back((int)q);
+                const double ang = L.angles[q];
+                t.sumdx += (float)std::cos((double)(float)ang);
+                t.sumdy += (float)std::sin((double)(float)ang);
+                t.angle = fast_atan2(t.sumdy, t.sumdx) * kDegToRad;
+            }
+        for (int l = 0; l < NL; ++l) {
+            const uint32_t tag = laneTag[l];
+            if (!tag) continue;
+            Ticket& t = T[tag];
+            if (++t.i >= (int)t.list.size()) {
+                t.state = DONE; laneTag[l] = 0; laneDone[l]++;
+                for (size_t b = 0; b < blocked.size();)                     // candidates held back for this region may go now
+                    if (blocked[b].second == tag) {
+                        if (ready.size() < READY_CAP) ready.push_back(blocked[b].first); else scanPos = std::min(scanPos, blocked[b].first);
+                        blocked[b] = blocked.back(); blocked.pop_back();
+                    } else ++b;
+            }
+        }
+        st[0]++;
+        st[9] += active;
+        for (int l = 0; l < NL; ++l) if (laneTag[l] && dep_broken(T[laneTag[l]])) killQueue.push_back(laneTag[l]);
+        kill_all();
+        // blockers that died release their candidates as well
+        for (size_t b = 0; b < blocked.size();)
+            if (T.find(blocked[b].second) == T.end()) {
+                if (ready.size() < READY_CAP) ready.push_back(blocked[b].first); else scanPos = std::min(scanPos, blocked[b].first);
+                blocked[b] = blocked.back(); blocked.pop_back();
+            } else ++b;
+        st[6] = std::max<long long>(st[6], (long long)T.size());
+    }
+    (void)minReg;
 }
 }  // namespace plfo

@@ -832,3 +832,19 @@ extern "C" PLF_API int plf_cpu_prim_lsd_stats(const uint8_t* src, int w, int h, 
     plfo::lsd_stats(c, s, out);
     return PLF_OK;
 }
+
+namespace plfo { struct StreamSimParams { int window; int fifo; double dperp; int heuristic; int lanes; };
+void lsd_stream_sim(const LsdConfig& c, const Img8& img, const StreamSimParams& sp, std::vector<float>& segs, long long st[16]); }
+extern "C" PLF_API int plf_cpu_prim_lsd_stream_sim(const uint8_t* src, int w, int h, int window, int fifo, double dperp, int heuristic, int lanes,
+                                                   float* xyxy, int cap, int* n, long long* st16) {
+    Img8 s(w, h);
+    std::memcpy(s.d.data(), src, (size_t)w * h);
+    LsdConfig c;
+    plfo::StreamSimParams sp{window, fifo, dperp, heuristic, lanes};
+    std::vector<float> segs;
+    plfo::lsd_stream_sim(c, s, sp, segs, st16);
+    if (n) *n = (int)segs.size() / 4;
+    if ((int)segs.size() / 4 > cap) return PLF_ERR_INVALID;
+    std::memcpy(xyxy, segs.data(), segs.size() * 4);
+    return PLF_OK;
+}

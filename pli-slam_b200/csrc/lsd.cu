@@ -10,6 +10,8 @@
 #include "plf_ctx.cuh"
 #include "blur.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -902,6 +904,8 @@ __global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const f
     if (threadIdx.x == 0) nSegsOut[img] = min(s_nSeg, g.segCap);
 }
 
+#include "lsd_stream.cuh"
+
 // cv::LineIterator(img, Point2f, Point2f).count of LSDDetector_custom.cpp:295-296, 8-connected: end points rounded half to
 // even, clipped with cv::clipLine when one lies outside the image (the clamp of checkLineExtremes leaves x in
 // [W-0.5, W), which rounds to W), count = max(|dx|, |dy|) + 1, 0 when nothing is left.  clipLine is OpenCV's integer
@@ -1221,6 +1225,14 @@ static void upload_lbd_tables(int device) {
 
 // scratch of the small-batch grower, allocated the first time a small launch happens (a context that only ever runs large
 // batches never pays for it): owner map (all PLF_FREE) and one region list per wave slot, for up to PLF_MW_MAX_IMG images
+static int plf_ensure_stream_buffers(plf_ctx* c) {
+    if (c->d_stream) return 0;
+    const StreamLayout L = stream_layout(c->g.Ps, c->g.Ws, c->g.Hs, c->g.segCap);
+    const size_t nImg = (size_t)c->p.max_batch * 2;
+    if (dalloc(&c->d_stream, nImg * (size_t)L.total) != cudaSuccess) { cudaGetLastError(); c->d_stream = nullptr; return 1; }
+    return 0;
+}
+
 static int plf_ensure_mw_buffers(plf_ctx* c) {
     if (c->d_owner && c->d_regMW) return 0;
     const PlfGeom& g = c->g;
@@ -1271,9 +1283,24 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     }
     plf_mark(c, "lsd_grow");
     {
+        // seq (one warp per image) for wide launches and mw (16 warps per image) for <= 128 images are the product path;
+        // PLF_LSD_GROWER=stream selects the one-lane-per-region grower (exact, measured slower: profiles/r02_stream_grower.md)
+        static const char* s_mode = getenv("PLF_LSD_GROWER");
+        const bool wantStream = s_mode && !strcmp(s_mode, "stream");
         if (g.refine >= 1)
             lsd_grow_kernel<true><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                       c->d_nSegs, c->d_err, imgFirst);
+        else if (wantStream && plf_ensure_stream_buffers(c) == 0) {
+            // one lane per region: up to 32 regions of each image in flight in its warp, rectangles fitted afterwards
+            const StreamLayout L = stream_layout(g.Ps, g.Ws, g.Hs, g.segCap);
+            int* scr = c->d_stream + (size_t)imgFirst * L.total;
+            lsd_stream_init_kernel<<<dim3(32, nImg), 256, 0, s>>>(g, c->d_n2, scr, L, imgFirst);
+            lsd_stream_kernel<<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_seeds, c->d_nSeeds, scr, L, c->d_reg, c->d_nReg, c->d_err, imgFirst);
+            lsd_rect_kernel<<<dim3(64, nImg), 128, 0, s>>>(g, c->d_n2, scr, L, c->d_reg, c->d_nReg, c->d_segs, c->d_nSegs, imgFirst);
+            launches += 2;
+        } else if (s_mode && !strcmp(s_mode, "seq"))
+            lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
+                                                       c->d_nSegs, c->d_err, imgFirst);
         else if (nImg <= PLF_MW_MAX_IMG && plf_ensure_mw_buffers(c) == 0)
             // few images: several regions of each image in flight (a block of 8 warps per image)
             lsd_grow_mw_kernel<<<nImg, 32 * MW, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_owner, c->d_regMW,

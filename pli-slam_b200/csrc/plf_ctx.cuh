@@ -122,6 +122,8 @@ struct plf_ctx {
     int* d_reg = nullptr;            // [nImg][Hs*Ws] region pixel list, packed y<<16|x (reused per region)
     uint32_t* d_owner = nullptr;     // small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][Hs][Ps] owner tags of the current wave (PLF_FREE = none)
     int* d_regMW = nullptr;          // small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][8][Hs*Ws] region lists, one per wave slot
+    int* d_stream = nullptr;         // streaming grower: [nImg][StreamLayout.total] owner map, list chunks, ticket table, region table (lazy)
+    int* d_nReg = nullptr;           // [nImg] regions committed by the streaming grower
     float* d_segs = nullptr;         // [nImg][segCap][4]
     int* d_nSegs = nullptr;          // [nImg]
     plf_keyline* d_kl = nullptr;     // [nImg][klCap]

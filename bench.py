@@ -34,10 +34,19 @@ sys.path.insert(0, ROOT)
 
 W, H = 752, 480
 WORKLOAD = dict(n_features=1200, n_levels=8, lsd_nfeatures=300)
-# algorithmic bytes of one stereo pair through the whole path (752x480, 1200 kp, 300 lines)
-BYTES_PER_PAIR = 50_661_326
-S_PIXELS = 902 * 576                 # scaled LSD image
-GROW_BYTES_PER_IMAGE = 9 * S_PIXELS  # region growing reads angle + modgrad (2 x f32) and the u8 used map once
+# BASELINE.json configs that are bench lines (the others are parity-test cases).  bytes_per_pair = SURVEY.md 8d's algorithmic
+# bytes of one stereo pair through the configured path; dominant = the kernel the roofline object describes, with its own
+# algorithmic bytes per image (8d) - region growing reads angle + modgrad (2 x f32) and the u8 used map once: 9 S.
+CONFIGS = {
+    "c2": dict(name="euroc_752x480_stereo_pointline_batch64", W=752, H=480, params=dict(n_features=1200, n_levels=8, lsd_nfeatures=300),
+               bytes_per_pair=50_661_326, dominant=("lsd_grow_kernel", "lsd_grow", 9 * 902 * 576), seed0=10_000),
+    "c3": dict(name="orb_only_752x480_2000feat", W=752, H=480, params=dict(n_features=2000, n_levels=8, has_lines=0),
+               bytes_per_pair=18_551_470, dominant=("fast_score_kernel+fast_cells_kernel", "orb_fast", 2 * 1_117_367), seed0=1000),
+    "c4": dict(name="line_path_1280x720_lsd_lbd_matchnnr", W=1280, H=720, params=dict(n_features=1200, n_levels=8, lsd_nfeatures=500, has_points=0),
+               bytes_per_pair=82_240_000, dominant=("lsd_grow_kernel", "lsd_grow", 9 * 1536 * 864), seed0=2000),
+}
+CONFIGS["c5"] = dict(CONFIGS["c2"], name="euroc_752x480_512_streams_sharded")
+BYTES_PER_PAIR = CONFIGS["c2"]["bytes_per_pair"]
 
 
 def shard_streams(n_streams, world_size, rank):
@@ -50,24 +59,26 @@ def stream_seed(stream, frame):
     return 10_000 * (stream + 1) + frame
 
 
-def _gen_pair(seed):
+def _gen_pair(args):
     import plf
-    return plf.synth_pair(W, H, seed)
+    seed, w, h = args
+    return plf.synth_pair(w, h, seed)
 
 
-def make_inputs(seeds):
+def make_inputs(seeds, W=752, H=480):
     """Distinct synthetic pairs, generated on the host cores in parallel (pure numpy, deterministic per seed)."""
     from concurrent.futures import ProcessPoolExecutor
     L = np.empty((len(seeds), H, W), np.uint8)
     R = np.empty((len(seeds), H, W), np.uint8)
+    seeds = [(s, W, H) for s in seeds]
     workers = max(1, min(len(seeds), (os.cpu_count() or 2)))
     try:
         with ProcessPoolExecutor(max_workers=workers) as ex:
             for i, (l, r) in enumerate(ex.map(_gen_pair, seeds, chunksize=2)):
                 L[i], R[i] = l, r
     except Exception:
-        for i, s in enumerate(seeds):
-            L[i], R[i] = _gen_pair(s)
+        for i, s_ in enumerate(seeds):
+            L[i], R[i] = _gen_pair(s_)
     return L, R
 
 
@@ -102,47 +113,154 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def cpu_baseline(sample_pairs, threads, seeds):
-    """The CPU port of the reference path (oracle/) on the host cores, `threads` workers over independent pairs."""
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libplf_ref_o3.so")
+
+
+def _ref_lib():
+    """oracle/_ref: the reference's OWN frontend sources (ORBextractor.cc, LineExtractor.cc, the line_descriptor library,
+    the stereo matchers of Frame.cc, LineMatcher.cpp ...) compiled where they lie by oracle/build_ref.py, -O3
+    -march=x86-64-v3, over the cv2-pinned restatements of the OpenCV primitives.  Returns None when it did not travel."""
+    import ctypes as C
+    if not os.path.exists(REF_LIB):
+        return None
+    lib = C.CDLL(REF_LIB)
+    lib.ref_frame_create.restype = C.c_void_p
+    return lib
+
+
+def reference_cpu(cfg, L, R, workers, pairs_per_worker):
+    """The reference's stereo Frame constructor on the host: `workers` pairs in flight, each with the reference's own
+    four extraction threads (src/Frame.cc:128-135) followed by the two stereo matchers.  Returns (pairs/s, seconds)."""
+    import ctypes as C
+    lib = _ref_lib()
+    p = dict(n_features=1200, scale_factor=1.2, n_levels=8, ini=20, mn=7, lsd_nfeatures=500, has_lines=1, has_points=1)
+    p.update(cfg["params"])
+    w, h = cfg["W"], cfg["H"]
+    use_threads = 1 | (0 if p["has_points"] else 2) | (0 if p["has_lines"] else 4)
+
+    def make():
+        return C.c_void_p(lib.ref_frame_create(p["n_features"], C.c_float(1.2), p["n_levels"], 20, 7, p["lsd_nfeatures"], C.c_double(0.025), 0,
+                                               C.c_double(1.2), C.c_double(0.6), C.c_double(2.0), C.c_double(22.5), C.c_double(1.0),
+                                               C.c_double(0.6), 1024, C.c_float(47.90639), C.c_float(435.2047)))
+    handles = [make() for _ in range(workers)]
+    done = [0.0] * workers
+
+    def work(k):
+        cnt = (C.c_int * 6)()
+        for i in range(pairs_per_worker):
+            j = (k * pairs_per_worker + i) % len(L)
+            lib.ref_frame_run(handles[k], L[j].ctypes.data_as(C.c_void_p), R[j].ctypes.data_as(C.c_void_p), w, h, w, use_threads, cnt)
+        done[k] = time.perf_counter()
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(workers)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    for hnd in handles:
+        lib.ref_frame_destroy(hnd)
+    return workers * pairs_per_worker / dt, dt
+
+
+def port_cpu(cfg, L, R, threads):
+    """Fallback when oracle/_ref did not travel: the restated oracle (kind "port"), `threads` workers over independent pairs."""
     import plf
-    orc = plf.load_oracle()     # bench.py's cpu_baseline / --impl reference legs are allowed to execute oracle/
-    f = plf.Frontend(orc, width=W, height=H, max_batch=sample_pairs, **WORKLOAD)
+    orc = plf.load_oracle()
+    n = len(L)
+    f = plf.Frontend(orc, width=cfg["W"], height=cfg["H"], max_batch=n, **cfg["params"])
     orc.dll.plf_cpu_set_threads(f.ctx, threads)
-    L, R = make_inputs(seeds[:sample_pairs])
-    out = f.new_result(sample_pairs)
+    out = f.new_result(n)
     f.batch_upload(L, R)
     t0 = time.perf_counter()
-    f.batch_run(sample_pairs)
+    f.batch_run(n)
     dt = time.perf_counter() - t0
-    f.batch_download(sample_pairs, out)
-    return sample_pairs / dt, dt
+    f.batch_download(n, out)
+    return n / dt, dt
+
+
+def cpu_cross_checks(cfg, img):
+    """Single-thread times of the dominant CPU stage beside real OpenCV (cv2 wheel of this image), ms per image."""
+    out = {}
+    try:
+        import ctypes as C
+        import plf
+        o = plf.load_oracle().dll
+        h, w = img.shape
+        seg = np.zeros((20000, 4), np.float32)
+        n = C.c_int(0)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        t = time.perf_counter()
+        for _ in range(3):
+            o.plf_cpu_prim_lsd(P(img), w, h, C.c_double(1.2), 1, P(seg), 20000, C.byref(n))
+        out["port_lsd_ms"] = round((time.perf_counter() - t) / 3 * 1e3, 1)
+        import cv2
+        cv2.setNumThreads(1)
+        lsd = cv2.createLineSegmentDetector(0, 1.2, 0.6, 2.0, 22.5, 1.0, 0.6, 1024)
+        lsd.detect(img)
+        t = time.perf_counter()
+        for _ in range(3):
+            lsd.detect(img)
+        out["cv2_lsd_ms"] = round((time.perf_counter() - t) / 3 * 1e3, 1)
+    except Exception as e:          # cv2 missing on the box: the cross-check is optional
+        out["cross_check_error"] = str(e)[:80]
+    return out
+
+
+def cpu_baseline(cfg, budget_s=12.0):
+    """Reference CPU leg on a bounded sample: throughput-saturated (cores/2 pairs in flight x the reference's 4 threads) and
+    the reference's own shape (one pair at a time, 4 threads).  Returns the cpu_baseline object of the JSON line."""
+    cores = os.cpu_count() or 1
+    workers = max(1, cores // 2)
+    seeds = [cfg["seed0"] + i for i in range(max(workers, 4))]
+    L, R = make_inputs(seeds, cfg["W"], cfg["H"])
+    if _ref_lib() is None:
+        v, dt = port_cpu(cfg, L, R, cores)
+        return {"value": v, "unit": "stereo pairs/s", "cores": cores, "kind": "port",
+                "sample": "%d pairs, %d worker threads over independent pairs, %.1f s (oracle/_ref absent)" % (len(L), cores, dt)}
+    _, d1 = reference_cpu(cfg, L, R, 1, 2)                              # warm-up + latency of the reference's own shape
+    lat_ms = d1 / 2 * 1e3
+    per_worker = max(2, int(budget_s / max(d1 / 2, 1e-3) / 2))
+    per_worker = min(per_worker, 16)
+    v, dt = reference_cpu(cfg, L, R, workers, per_worker)
+    out = {"value": v, "unit": "stereo pairs/s", "cores": cores, "kind": "reference",
+           "sample": "%d pairs: %d pairs in flight x the reference's 4 extraction threads, %.1f s; reference sources compiled by "
+                     "oracle/build_ref.py (-O3 -march=x86-64-v3) over cv2-pinned OpenCV primitives" % (workers * per_worker, workers, dt),
+           "latency_ms_one_pair_4_threads": round(lat_ms, 1), "pairs_in_flight": workers}
+    out.update(cpu_cross_checks(cfg, L[0]))
+    return out
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path.  Its own sources cannot be built here (they
-    need OpenCV 3 / Eigen / Pangolin headers, none present), so the timed code is the CPU port in oracle/ with every
-    host thread, on the same workload, each step a bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref) with every host thread it can use,
+    on the configured workload, each step a bounded sample.  Rank 0 alone runs it."""
     if rank != 0:
         return
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
-    sample = max(2 * cores, 8)
-    seeds = [1000 + i for i in range(sample)]
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_baseline(min(sample, cores), cores, seeds)
-    vals = []
+    workers = max(1, cores // 2)
+    have_ref = _ref_lib() is not None
+    seeds = [cfg["seed0"] + i for i in range(max(workers * 2, 8))]
+    L, R = make_inputs(seeds, cfg["W"], cfg["H"])
+    per_worker = 2
+    run = (lambda: reference_cpu(cfg, L, R, workers, per_worker)) if have_ref else (lambda: port_cpu(cfg, L, R, cores))
+    for _ in range(min(args.warmup, 1)):
+        run()
+    pairs = 0
     t_all = 0.0
     for _ in range(args.steps):
-        v, dt = cpu_baseline(sample, cores, seeds)
-        vals.append(v)
+        v, dt = run()
+        pairs += v * dt
         t_all += dt
-    value = sample * args.steps / t_all
+    value = pairs / t_all
+    base = cpu_baseline(cfg, budget_s=4.0) if have_ref else {"kind": "port", "cores": cores, "sample": "oracle port, all cores"}
+    base["value"] = value
     line = {"impl": "reference", "metric": "stereo_frames_per_sec", "value": value, "unit": "stereo pairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "euroc_752x480_stereo_pointline_batch64", "width": W, "height": H, **WORKLOAD,
-                       "timing": "host wall clock, inputs in host memory"},
-            "cpu_baseline": {"value": value, "unit": "stereo pairs/s", "cores": cores, "kind": "port",
-                             "sample": "%d pairs per step, %d worker threads over independent pairs" % (sample, cores)},
+            "config": {"workload": cfg["name"], "width": cfg["W"], "height": cfg["H"], **cfg["params"],
+                       "pairs_per_step": int(round(pairs / args.steps)), "timing": "host wall clock, inputs in host memory"},
+            "cpu_baseline": base,
             "e2e": {"value": value, "unit": "stereo pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -159,7 +277,8 @@ def main():
     ap.add_argument("--rectify", action="store_true",
                     help="e2e leg starts from RAW frames: upload + cv::remap rectification on the device (SURVEY 8f rank 2)")
     ap.add_argument("--contexts", type=int, default=6, help="calls kept in flight per GPU (one CUDA stream each)")
-    ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic pairs generated per rank")
+    ap.add_argument("--distinct", type=int, default=512, help="distinct synthetic pairs generated per rank (every launch sees pairs_per_call distinct pairs)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config: c2 headline, c3 ORB only, c4 1280x720 line path, c5 512 streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -185,19 +304,27 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     prod = plf.load_product()
+    cfg = CONFIGS[args.config]
+    global W, H, WORKLOAD
+    W, H, WORKLOAD = cfg["W"], cfg["H"], dict(cfg["params"])
+    if args.config == "c4" and args.streams == 8 and args.contexts == 6:
+        args.streams, args.contexts = 2, 4                # 1280x720: 2.6x the pixels and device memory per pair
     B, C = args.batch * args.streams, args.contexts       # pairs per call, calls in flight
-    if os.environ.get("PLF_BENCH_NO_LINES"):      # developer switch: ORB + stereo points only
-        WORKLOAD["has_lines"] = 0
-    # this rank's camera streams (global ids), args.streams of them per context
-    my_streams = shard_streams(C * args.streams * world, world, rank)
+    # this rank's camera streams (global ids), args.streams of them per context: stream s -> rank s mod world
+    n_streams_total = 512 if args.config == "c5" else C * args.streams * world
+    my_streams = shard_streams(max(n_streams_total, C * args.streams * world), world, rank)
     distinct = min(args.distinct, B)
-    seeds = [stream_seed(my_streams[0], f) for f in range(distinct)]
-    Ld, Rd = make_inputs(seeds)
+    # distinct pairs of this rank: frames f of its first streams, seed convention of SURVEY 8d (c2/c5) or the config's own
+    if args.config in ("c2", "c5"):
+        seeds = [stream_seed(my_streams[(i // args.batch) % len(my_streams)], i % args.batch) for i in range(distinct)]
+    else:
+        seeds = [cfg["seed0"] + rank * distinct + i for i in range(distinct)]
+    Ld, Rd = make_inputs(seeds, W, H)
     ctxs, hostL, hostR, results = [], [], [], []
     for ci in range(C):
         f = plf.Frontend(prod, device=local_rank, width=W, height=H, max_batch=B, **WORKLOAD)
-        # every context gets its own rotation of the distinct pairs (own device copy: C x 46 MB of inputs > L2)
-        idx = (np.arange(B) * 7 + ci * 11) % distinct
+        # every call covers `distinct` different pairs (all of them when distinct == pairs_per_call); the contexts rotate them
+        idx = (np.arange(B) + ci * (distinct // max(C, 1) + 1)) % distinct
         l = torch.from_numpy(np.ascontiguousarray(Ld[idx])).pin_memory()
         r = torch.from_numpy(np.ascontiguousarray(Rd[idx])).pin_memory()
         if args.rectify:
@@ -322,6 +449,22 @@ def main():
     f0.set_stage_timing(False)
     barrier()
 
+    # latency of ONE pair through the batched call on an otherwise idle GPU (host buffers in, results out)
+    lat_ms = None
+    try:
+        f1 = plf.Frontend(prod, device=local_rank, width=W, height=H, max_batch=1, **WORKLOAD)
+        o1 = f1.new_result(1, pinned=True)
+        for _ in range(3):
+            f1.frontend_batch(Ld[:1], Rd[:1], o1)
+        t1 = time.perf_counter()
+        for k in range(5):
+            f1.frontend_batch(Ld[k % distinct:k % distinct + 1], Rd[k % distinct:k % distinct + 1], o1)
+        lat_ms = (time.perf_counter() - t1) / 5 * 1e3
+        f1.close()
+    except Exception:
+        pass
+    barrier()
+
     pairs_per_step = B * C * world
     value = pairs_per_step * args.steps / t_res
     e2e = pairs_per_step * args.steps / t_e2e
@@ -331,15 +474,16 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    grow_alone_ms = stage_acc.get("lsd_grow", 0.0)
-    grow_ms = live_ms.get("lsd_grow", 0.0) or grow_alone_ms
-    achieved = (GROW_BYTES_PER_IMAGE * 2 * B / (grow_ms * 1e-3) / 1e9) if grow_ms > 0 else 0.0
-    achieved_alone = (GROW_BYTES_PER_IMAGE * 2 * B / (grow_alone_ms * 1e-3) / 1e9) if grow_alone_ms > 0 else 0.0
+    dom_kernel, dom_stage, dom_bytes = cfg["dominant"]
+    dom_alone_ms = stage_acc.get(dom_stage, 0.0)
+    dom_ms = live_ms.get(dom_stage, 0.0) or dom_alone_ms
+    achieved = (dom_bytes * 2 * B / (dom_ms * 1e-3) / 1e9) if dom_ms > 0 else 0.0
+    achieved_alone = (dom_bytes * 2 * B / (dom_alone_ms * 1e-3) / 1e9) if dom_alone_ms > 0 else 0.0
     live_total = sum(v for k, v in live_ms.items() if k not in ("h2d", "d2h")) or 1.0
     h2d, d2h = f0.io_bytes()
     traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of one lsd_grow_kernel launch (ncu --set full, profiles/)
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_lsd_grow_traffic.json")))
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel (ncu --set full, profiles/)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_dominant_traffic.json")))[args.config]
         if prof.get("images_per_launch") == 2 * B:
             traffic = prof["dram_bytes_per_launch"]
     except Exception:
@@ -349,32 +493,29 @@ def main():
             "metric": "stereo_frames_per_sec", "value": value, "unit": "stereo pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "euroc_752x480_stereo_pointline_batch64", "width": W, "height": H, **WORKLOAD,
+            "config": {"workload": cfg["name"], "baseline_config": args.config, "width": W, "height": H, **WORKLOAD,
                        "frames_per_stream": args.batch, "streams_per_context": args.streams, "pairs_per_call": B,
                        "contexts_in_flight": C, "pairs_per_step": pairs_per_step,
                        "e2e_input": "raw frames, rectified on the device" if args.rectify else "rectified frames",
-                       "distinct_pairs_per_rank": distinct,
+                       "distinct_pairs_per_rank": distinct, "distinct_images_per_launch": 2 * min(distinct, B),
                        "l2": "inputs larger than L2: %d contexts x %.0f MB of resident images" % (C, 2 * B * W * H / 1e6),
                        "parallelism": "replicas%d (streams sharded, no collective)" % world},
             "e2e": {"value": e2e, "unit": "stereo pairs/s", "h2d_bytes_per_step": h2d * B * C * world,
                     "d2h_bytes_per_step": d2h * B * C * world, "host_wall_s": round(t_e2e_wall, 4)},
             "gpu_launches": launches,
+            "latency_ms_single_pair": None if lat_ms is None else round(lat_ms, 2),
             "ms_per_stage": {k: round(v, 4) for k, v in stage_acc.items()},
-            "roofline": {"bound": "hbm", "kernel": "lsd_grow_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                         "algorithmic_bytes_per_launch": GROW_BYTES_PER_IMAGE * 2 * B,
-                         "launch_ms_live": round(grow_ms, 3), "launch_ms_alone": round(grow_alone_ms, 3),
-                         "achieved_alone": achieved_alone, "share_of_step_live": round(grow_ms / live_total, 4),
-                         "whole_path_frac": BYTES_PER_PAIR * value / world / (peak * 1e9)},
+                         "algorithmic_bytes_per_launch": dom_bytes * 2 * B,
+                         "launch_ms_live": round(dom_ms, 3), "launch_ms_alone": round(dom_alone_ms, 3),
+                         "achieved_alone": achieved_alone, "share_of_step_live": round(dom_ms / live_total, 4),
+                         "whole_path_frac": cfg["bytes_per_pair"] * value / world / (peak * 1e9)},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
-            cores = os.cpu_count() or 1
-            sample = max(2 * cores, 8)
-            v, dt = cpu_baseline(sample, cores, [1000 + i for i in range(sample)])
-            line["cpu_baseline"] = {"value": v, "unit": "stereo pairs/s", "cores": cores, "kind": "port",
-                                    "sample": "%d pairs, %d worker threads over independent pairs, %.1f s" % (sample, cores, dt)}
+            line["cpu_baseline"] = cpu_baseline(cfg)
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

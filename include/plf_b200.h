@@ -107,6 +107,10 @@ typedef struct plf_params {
     double  line_horiz_th;        /* 0.1  */
     double  stereo_overlap_th;    /* 0.75 */
     double  ls_min_disp_ratio;    /* 0.7  */
+    /* Isolation switch for the line-only configuration of BASELINE.json (C4): 0 skips the ORB extractors and the stereo
+     * point matcher in the BATCHED calls (keypoint counts come back 0; lines and line matching still run).  1 = the
+     * reference's path.  Not a reference behaviour: Frame::Frame(stereo) always extracts points. */
+    int32_t has_points;           /* 1    */
 } plf_params;
 
 typedef struct plf_ctx plf_ctx;

@@ -27,7 +27,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("PLF_REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
 GEN = os.path.join(OUT, "gen")
-LIB = os.path.join(OUT, "libplf_ref.so")
+LIB = os.path.join(OUT, "libplf_ref.so")          # the pin: -O2 -ffp-contract=off, float expressions as written
+LIB_O3 = os.path.join(OUT, "libplf_ref_o3.so")    # the timed build: -O3 -march=x86-64-v3 (the reference's CMake uses -O3 -march=native)
 SHIM = os.path.join(HERE, "refshim")
 LD = os.path.join(REF, "Thirdparty", "line_descriptor")
 
@@ -74,6 +75,12 @@ def generate():
 
 
 def build(force=False):
+    a = build_one(LIB, ["-O2", "-ffp-contract=off", "-fno-fast-math"], "obj", force)
+    build_one(LIB_O3, ["-O3", "-march=x86-64-v3"], "obj_o3", force)
+    return a
+
+
+def build_one(LIB, OPT, objname, force=False):
     if not os.path.isdir(os.path.join(REF, "src")):
         if os.path.exists(LIB):
             return LIB            # GPU box: the prebuilt library travelled with the snapshot
@@ -86,14 +93,14 @@ def build(force=False):
            [os.path.join(HERE, "cpp", f) for f in os.listdir(os.path.join(HERE, "cpp")) if f.endswith(".h")] + [__file__]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
-    objdir = os.path.join(OUT, "obj")
+    objdir = os.path.join(OUT, objname)
+    BASE = OPT + ["-std=c++14", "-fPIC", "-w", "-fvisibility=hidden"]
     os.makedirs(objdir, exist_ok=True)
 
     def cc(src):
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
         if src.startswith(HERE + os.sep + "cpp"):      # the oracle's own files: no reference headers, C++17
-            flags = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-fvisibility=hidden",
-                     "-DPLF_ORACLE_BUILD"]
+            flags = OPT + ["-std=c++17", "-fPIC", "-w", "-fvisibility=hidden", "-DPLF_ORACLE_BUILD"]
         elif "line_descriptor" in src or src.endswith("lbd_ranges.cpp") or src.endswith("cvshim.cpp") \
                 or os.path.basename(src) in ("gridStructure.cpp", "LineIterator.cpp", "Config.cpp"):
             flags = BASE + INC

@@ -51,6 +51,7 @@ PLF_API int plf_cpu_default_params(plf_params* p) {
     std::memset(p, 0, sizeof(*p));
     p->width = 752; p->height = 480; p->max_batch = 1;
     p->n_features = 1200; p->scale_factor = 1.2f; p->n_levels = 8; p->ini_th_fast = 20; p->min_th_fast = 7;
+    p->has_points = 1;
     p->has_lines = 1; p->lsd_nfeatures = 500; p->lsd_refine = 0; p->lsd_n_bins = 1024;
     p->min_line_length = 0.025; p->lsd_scale = 1.2; p->lsd_sigma_scale = 0.6; p->lsd_quant = 2.0;
     p->lsd_ang_th = 22.5; p->lsd_log_eps = 1.0; p->lsd_density_th = 0.6;
@@ -628,7 +629,8 @@ static void run_pair(plf_ctx* c, int b) {
     Slot& s = c->slots[b];
     const int w = c->p.width, h = c->p.height;
     for (int side = 0; side < 2; ++side) {
-        orb_slot(c, b, side, s.img[side].d.data(), w, h, w, 0, 0);
+        if (c->p.has_points) orb_slot(c, b, side, s.img[side].d.data(), w, h, w, 0, 0);
+        else { s.orb[side].kps.clear(); s.orb[side].desc.clear(); s.orb[side].valid = true; }   // line-only isolation (plf_params.has_points)
         line_slot(c, b, side, s.img[side].d.data(), w, h, w);
     }
     // Frame.cc:146-149: both matchers are skipped when there are no keypoints or no lines
@@ -637,10 +639,10 @@ static void run_pair(plf_ctx* c, int b) {
     s.disp.assign(s.lsd[0].kls.size() * 2, -1.f);
     s.le.assign(s.lsd[0].kls.size() * 3, 0.0);
     s.m12.assign(s.lsd[0].kls.size(), -1);
-    if (s.orb[0].kps.empty()) return;
+    if (c->p.has_points && s.orb[0].kps.empty()) return;
     if (c->p.has_lines && s.lsd[0].kls.empty()) return;
     if (c->p.has_lines) match_lines_slot(c, b);
-    match_points_slot(c, b);
+    if (c->p.has_points) match_points_slot(c, b);
 }
 
 PLF_API int plf_cpu_batch_run(plf_ctx* c, int batch) {

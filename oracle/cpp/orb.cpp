@@ -80,28 +80,38 @@ void fast_window(const Img8& img, int x0, int y0, int x1, int y1, int th, std::v
     const int cols = x1 - x0, rows = y1 - y0;
     if (cols < 7 || rows < 7) return;
     const int aw = cols - 6, ah = rows - 6;          // detection area
-    std::vector<int> sc((size_t)aw * ah, 0);
+    static thread_local std::vector<int> sc;
+    sc.assign((size_t)aw * ah, 0);
+    int off[16];
+    for (int k = 0; k < 16; ++k) off[k] = kCircle[k][1] * img.w + kCircle[k][0];
+    bool any = false;
     for (int i = 0; i < ah; ++i) {
-        const uint8_t* r0 = img.row(y0 + 3 + i);
+        const uint8_t* r0 = img.row(y0 + 3 + i) + x0 + 3;
         for (int j = 0; j < aw; ++j) {
             // Early reject (the high-speed test every FAST implementation starts with): a 9-arc of the 16-ring holds
             // at least one pixel of each opposite pair (k, k+8), so a corner at threshold th needs, in EVERY pair, a
             // pixel brighter than p+th (bright corner) or in every pair one darker than p-th (dark corner).  A
             // necessary condition only: survivors get the full score and the `>= th` test, so the list is unchanged.
-            const int x = x0 + 3 + j, y = y0 + 3 + i;
-            const int p = r0[x], hi = p + th, lo = p - th;
-            bool bright = true, dark = true;
-            for (int k = 0; k < 8 && (bright || dark); ++k) {
-                const int a = img.at(y + kCircle[k][1], x + kCircle[k][0]);
-                const int b = img.at(y + kCircle[k + 8][1], x + kCircle[k + 8][0]);
+            const uint8_t* c = r0 + j;
+            const int p = c[0], hi = p + th, lo = p - th;
+            int a = c[off[0]], b = c[off[8]];
+            bool bright = a > hi || b > hi, dark = a < lo || b < lo;
+            if (!bright && !dark) continue;
+            a = c[off[4]]; b = c[off[12]];
+            bright = bright && (a > hi || b > hi); dark = dark && (a < lo || b < lo);
+            if (!bright && !dark) continue;
+            for (int k = 1; k < 8 && (bright || dark); ++k) {
+                if (k == 4) continue;
+                a = c[off[k]]; b = c[off[k + 8]];
                 bright = bright && (a > hi || b > hi);
                 dark = dark && (a < lo || b < lo);
             }
             if (!bright && !dark) continue;
-            int s = fast_score(img, x, y);
-            sc[(size_t)i * aw + j] = (s >= th) ? s : 0;   // non-corners at this threshold score 0
+            const int s = fast_score(img, x0 + 3 + j, y0 + 3 + i);
+            if (s >= th) { sc[(size_t)i * aw + j] = s; any = true; }   // non-corners at this threshold score 0
         }
     }
+    if (!any) return;
     for (int i = 0; i < ah; ++i)
         for (int j = 0; j < aw; ++j) {
             int s = sc[(size_t)i * aw + j];

@@ -291,3 +291,82 @@ REF_API int ref_distance(const uint8_t* a, const uint8_t* b) { return ORB_SLAM3:
 REF_API int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
     return ORBmatcher::DescriptorDistance(wrap_desc(a, 1), wrap_desc(b, 1));
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The stereo Frame constructor of the reference as a timed unit (bench.py --impl reference / cpu_baseline): four
+// threads per pair — ExtractORB(left), ExtractORB(right), ExtractLine(left), ExtractLine(right), src/Frame.cc:128-135 —
+// join, ComputeStereoMatches_Lines, ComputeStereoMatches (:160-163).  One handle per worker; handles share nothing but
+// the read-only Config singleton, so several pairs can be in flight on a many-core host.
+namespace {
+struct RefPipeline {
+    OrbPeek* orb[2];
+    Lineextractor* line[2];
+    Frame frame;
+    float bf, fx;
+};
+}  // namespace
+
+REF_API void* ref_frame_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, int lsd_nfeatures,
+                               double min_line_length, int refine, double scale, double sigma_scale, double quant, double ang_th,
+                               double log_eps, double density_th, int n_bins, float bf, float fx) {
+    RefPipeline* p = new RefPipeline();
+    for (int s = 0; s < 2; ++s) {
+        p->orb[s] = new OrbPeek(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+        p->line[s] = new Lineextractor(lsd_nfeatures, min_line_length, refine, scale, sigma_scale, quant, ang_th, log_eps, density_th, n_bins);
+    }
+    p->bf = bf; p->fx = fx;
+    return p;
+}
+REF_API void ref_frame_destroy(void* h) {
+    RefPipeline* p = (RefPipeline*)h;
+    if (!p) return;
+    for (int s = 0; s < 2; ++s) { delete p->orb[s]; delete p->line[s]; }
+    delete p;
+}
+// counts[0..5] = N, Nr, N_l, Nr_l, stereo points, stereo lines.  mode bit 0: the reference's four extraction threads;
+// bit 1: no ORB extractors / point matcher (line-only isolation, BASELINE config 4: matchNNR on the line descriptors instead);
+// bit 2: no line extractors / line matcher (ORB-only isolation, config 3).
+REF_API int ref_frame_run(void* h, const uint8_t* left, const uint8_t* right, int w, int hgt, int stride, int mode, int* counts) {
+    return guarded([&] {
+        const bool use_threads = mode & 1, noPoints = mode & 2, noLines = mode & 4;
+        RefPipeline* p = (RefPipeline*)h;
+        Frame& F = p->frame;
+        cv::Mat im[2] = {wrap_u8(left, w, hgt, stride), wrap_u8(right, w, hgt, stride)};
+        std::vector<int> lap = {0, 0};
+        cv::Mat none;
+        auto orbL = [&] { if (noPoints) { F.mvKeys.clear(); return; } (*p->orb[0])(im[0], none, F.mvKeys, F.mDescriptors, lap); };
+        auto orbR = [&] { if (noPoints) { F.mvKeysRight.clear(); return; } (*p->orb[1])(im[1], none, F.mvKeysRight, F.mDescriptorsRight, lap); };
+        auto lineL = [&] { if (noLines) { F.mvKeys_Line.clear(); return; } (*p->line[0])(im[0], none, F.mvKeys_Line, F.mDescriptors_Line); };
+        auto lineR = [&] { if (noLines) { F.mvKeysRight_Line.clear(); return; } (*p->line[1])(im[1], none, F.mvKeysRight_Line, F.mDescriptorsRight_Line); };
+        if (use_threads) {
+            std::thread t0(orbL), t1(orbR), t2(lineL), t3(lineR);
+            t0.join(); t1.join(); t2.join(); t3.join();
+        } else { orbL(); orbR(); lineL(); lineR(); }
+        F.N = (int)F.mvKeys.size(); F.N_l = (int)F.mvKeys_Line.size();
+        F.mpORBextractorLeft = p->orb[0]; F.mpORBextractorRight = p->orb[1];
+        F.mvScaleFactors = p->orb[0]->GetScaleFactors(); F.mvInvScaleFactors = p->orb[0]->GetInverseScaleFactors();
+        F.mbf = p->bf; F.mb = p->bf / p->fx;
+        F.inv_width = FRAME_GRID_COLS / static_cast<double>(w);
+        F.inv_height = FRAME_GRID_ROWS / static_cast<double>(hgt);
+        int sp = 0, sl = 0;
+        if (noPoints || noLines) {
+            if (!noLines && !F.mvKeys_Line.empty()) {
+                F.ComputeStereoMatches_Lines();
+                for (auto& d : F.mvDisparity_l) sl += d.first >= 0;
+                if (F.mDescriptorsRight_Line.rows >= 2) {            // config 4 names matchNNR on the stereo descriptor sets
+                    std::vector<int> m12;
+                    matchNNR(F.mDescriptors_Line, F.mDescriptorsRight_Line, (float)Config::minRatio12L(), m12);
+                }
+            }
+            if (!noPoints && !F.mvKeys.empty()) { F.ComputeStereoMatches(); for (float u : F.mvuRight) sp += u >= 0; }
+        } else if (!F.mvKeys.empty() && !F.mvKeys_Line.empty()) {  // src/Frame.cc:146-149
+            F.ComputeStereoMatches_Lines();
+            F.ComputeStereoMatches();
+            for (float u : F.mvuRight) sp += u >= 0;
+            for (auto& d : F.mvDisparity_l) sl += d.first >= 0;
+        }
+        counts[0] = F.N; counts[1] = (int)F.mvKeysRight.size(); counts[2] = F.N_l; counts[3] = (int)F.mvKeysRight_Line.size();
+        counts[4] = sp; counts[5] = sl;
+        return 0;
+    });
+}

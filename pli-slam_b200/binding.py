@@ -36,6 +36,7 @@ class Params(C.Structure):
         ("best_lr_matches", C.c_int32), ("matching_s_ws", C.c_int32),
         ("min_ratio_12_l", C.c_double), ("line_sim_th", C.c_double), ("min_disp", C.c_double),
         ("line_horiz_th", C.c_double), ("stereo_overlap_th", C.c_double), ("ls_min_disp_ratio", C.c_double),
+        ("has_points", C.c_int32),
     ]
 
 

@@ -35,6 +35,7 @@ PLF_API int plf_default_params(plf_params* p) {
     memset(p, 0, sizeof(*p));
     p->width = 752; p->height = 480; p->max_batch = 1;
     p->n_features = 1200; p->scale_factor = 1.2f; p->n_levels = 8; p->ini_th_fast = 20; p->min_th_fast = 7;
+    p->has_points = 1;
     p->has_lines = 1; p->lsd_nfeatures = 500; p->lsd_refine = 0; p->lsd_n_bins = 1024;
     p->min_line_length = 0.025; p->lsd_scale = 1.2; p->lsd_sigma_scale = 0.6; p->lsd_quant = 2.0;
     p->lsd_ang_th = 22.5; p->lsd_log_eps = 1.0; p->lsd_density_th = 0.6;
@@ -677,10 +678,11 @@ PLF_API int plf_batch_run(plf_ctx* c, int batch) {
     int n = 0;
     if (c->nMarks && strcmp(c->markNames[0], "h2d") != 0) c->nMarks = 0;   // run without a fresh upload: restart marks
     if (c->nMarks > 1 && !(c->nMarks == 2 && strcmp(c->markNames[1], "rectify") == 0)) c->nMarks = 0;
-    n += plf_launch_orb(c, 0, 2 * batch, 0, 0);
+    if (c->p.has_points) n += plf_launch_orb(c, 0, 2 * batch, 0, 0);
+    else PLF_CUDA_OK(cudaMemsetAsync(c->d_nKp, 0, (size_t)2 * batch * sizeof(int), c->stream));
     if (c->p.has_lines) n += plf_launch_lines(c, 0, 2 * batch);
     if (c->p.has_lines) n += plf_launch_stereo_lines(c, 0, batch);
-    n += plf_launch_stereo_points(c, 0, batch);
+    if (c->p.has_points) n += plf_launch_stereo_points(c, 0, batch);
     plf_mark(c, "d2h");
     PLF_CUDA_OK(cudaGetLastError());
     c->launches = n;

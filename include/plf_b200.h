@@ -302,6 +302,76 @@ PLF_API int PLF_FN(search_by_projection_frame)(plf_ctx* ctx, int slot, const plf
                                                int th_high, int check_orientation, uint8_t* occupied, int n_features,
                                                int32_t* feat_query, int32_t* match12, int* n_matches);
 
+/* Replaces: int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound,
+ * const float th, const int ORBdist) (src/ORBmatcher.cc:2325-2447, Tracking::Relocalization) from the projected points
+ * on, for the left keypoints of one slot (= CurrentFrame).  One plf_frame_query per keyframe map point i: u, v
+ * (:2354), radius = th * mvScaleFactors[nPredictedLevel] (:2377), min_level / max_level = nPredictedLevel -/+ 1 (:2379),
+ * angle = pKF->mvKeysUn[i].angle (:2410), desc, skip != 0 for the `continue`s of :2346-2372 (no map point, bad, already
+ * found, outside the image bounds or the scale-invariance distances).  `ur` and `has_observations` are not read: this
+ * overload has no stereo check and ANY map point held by a feature blocks it (:2393).  Device: window search, level
+ * filter, Hamming distances.  Host, in query order: best distance among free features, bestDist <= orb_dist, assignment,
+ * the 30-bin rotation histogram and ComputeThreeMaxima.
+ * occupied  : in/out, one byte per keypoint: CurrentFrame.mvpMapPoints[idx] != NULL
+ * feat_query: out, per keypoint: the query whose map point it received, or -1.  Returns nmatches in *n_matches. */
+PLF_API int PLF_FN(search_by_projection_reloc)(plf_ctx* ctx, int slot, const plf_frame_query* queries, int n_queries,
+                                               int orb_dist, int check_orientation, uint8_t* occupied, int n_features,
+                                               int32_t* feat_query, int* n_matches);
+
+/* Replaces: int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints,
+ * vector<MapPoint*>& vpMatched, int th, float ratioHamming) (src/ORBmatcher.cc:473-580) and its vpPointsKFs /
+ * vpMatchedKF variant (:582-704; the search is identical, feat_query tells the caller which pKFi to record), the loop
+ * closing / place recognition searches, from the projected points on; the slot plays the keyframe.  One plf_frame_query
+ * per candidate map point: u, v (:519 / :631-635), radius = th * mvScaleFactors[nPredictedLevel] (:545), min_level /
+ * max_level = nPredictedLevel - 1 / nPredictedLevel (the filter of :566), desc, skip != 0 for the `continue`s of
+ * :502-541.  No stereo check, no rotation histogram.  Host, in query order: best distance among the features with
+ * vpMatched[idx] == NULL, accepted iff (float)bestDist <= (float)th_low * ratio_hamming (:574).
+ * occupied: in/out, vpMatched[idx] != NULL.  feat_query: out, query index per keypoint or -1. */
+PLF_API int PLF_FN(search_by_projection_loop)(plf_ctx* ctx, int slot, const plf_frame_query* queries, int n_queries,
+                                              int th_low, float ratio_hamming, uint8_t* occupied, int n_features,
+                                              int32_t* feat_query, int* n_matches);
+
+/* Replaces: int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches)
+ * (src/ORBmatcher.cc:269-471; Tracking::TrackReferenceKeyFrame, Relocalization) for rectified stereo (F.Nleft == -1);
+ * the slot plays F.  Keyframe side, per keyframe feature: descriptor row, keypoint angle (mvKeysUn), the key of its
+ * FeatureVector entry (kf_node: node id at level L - levelsup as plf_bow_transform returns it, < 0 if the feature is in
+ * no entry: stopped word) and kf_valid != 0 where vpMapPointsKF[i] is a good map point (:300-306).  Frame side:
+ * f_node[n_features] likewise for the slot's left keypoints.  Device: every Hamming distance between a valid keyframe
+ * feature and the frame features of the same node (a warp per keyframe feature).  Host, in the reference's order
+ * (nodes ascending = std::map order, keyframe features of a node ascending, frame features ascending): features already
+ * matched are skipped (:325), best / second best, best <= th_low and (float)best < nn_ratio * (float)second (:388-391),
+ * rotation histogram with factor 1/HISTO_LENGTH and ComputeThreeMaxima.
+ * match[f]: keyframe feature whose map point frame feature f received, or -1 (vpMapPointMatches); returns nmatches. */
+PLF_API int PLF_FN(search_by_bow)(plf_ctx* ctx, int slot, const uint8_t* kf_desc, const float* kf_angle,
+                                  const int32_t* kf_node, const uint8_t* kf_valid, int n_kf, const int32_t* f_node,
+                                  int n_features, int th_low, float nn_ratio, int check_orientation, int32_t* match,
+                                  int* n_matches);
+
+/* One line of the "first" set of the tracking thread's line matching: a keyline of LastFrame (frame-to-frame) or the
+ * projection of a local-map line (mTrackProjsX/sY/eX/eY).  24 bytes. */
+typedef struct plf_track_line {
+    float sx, sy, ex, ey;       /* start / end point in the current image                                    */
+    float angle;                /* mvKeysUn_Line[i1].angle (frame-to-frame gate only)                        */
+    int32_t eligible;           /* frame-to-frame: LastFrame.mvpMapLines[i1] != NULL (:3064); local map: 1   */
+} plf_track_line;
+
+/* Replaces the line half of Tracking::TrackWithMotionModel (src/Tracking.cc:3055-3099; mode 0) and of
+ * Tracking::SearchLocalLines (src/Tracking.cc:3879-3917; mode 1): match(desc1, desc2, nnr, matches_12)
+ * (src/LineMatcher.cpp:201-229, mutual best) followed by the gates the tracker applies to every match, fused into one
+ * device pass (2-NN both ways, mutual-best filter and gates; one D2H of the two result arrays).
+ *   lines1[n1]: the first set; kl2[n2]: mCurrentFrame.mvKeysUn_Line; disp2[n2][2]: mCurrentFrame.mvDisparity_l
+ *   held2[n2] (mode 1, may be NULL): mCurrentFrame.mvpMapLines[i2] has Observations() > 0 (:3892-3894)
+ *   min_x .. max_y: Frame::mnMinX/mnMaxX/mnMinY/mnMaxY (deltaWidth/Height = (max - min) * 0.1, :3060-3061)
+ * For every i1 with a match i2: not eligible, a negative disparity (:3067) or (mode 1) a held line -> the match is kept
+ * but nothing is assigned; mode 0: |angle2 - angle1| folded to (-pi, pi] > pi/8 -> matches12[i1] = -1 (:3072-3079);
+ * both modes: an end point farther than deltaWidth / deltaHeight from its counterpart -> matches12[i1] = -1
+ * (:3080-3093, :3901-3914); otherwise assign12[i1] = i2 (mCurrentFrame.mvpMapLines[i2] = the line of i1).
+ *   matches12[n1], assign12[n1]: out.  *n_assigned = the reference's n_inliers_ls of mode 0 / the number of map lines
+ *   attached in mode 1. */
+PLF_API int PLF_FN(match_lines_tracked)(plf_ctx* ctx, int mode, const uint8_t* desc1, const plf_track_line* lines1, int n1,
+                                        const uint8_t* desc2, const plf_keyline* kl2, const float* disp2,
+                                        const uint8_t* held2, int n2, float nnr, float min_x, float max_x, float min_y,
+                                        float max_y, int32_t* matches12, int32_t* assign12, int* n_assigned);
+
 /* ------------------------------------------------------------------------------------------------------ */
 /* Landmark back-projection: the epilogue that turns stereo matches into 3-D landmarks.   */
 
@@ -468,11 +538,13 @@ static_assert(sizeof(plf_keypoint) == 28, "plf_keypoint must be layout-identical
 static_assert(sizeof(plf_keyline) == 68, "plf_keyline must be layout-identical to cv::line_descriptor::KeyLine");
 static_assert(sizeof(plf_proj_query) == 56, "plf_proj_query is 56 bytes");
 static_assert(sizeof(plf_frame_query) == 72, "plf_frame_query is 72 bytes");
+static_assert(sizeof(plf_track_line) == 24, "plf_track_line is 24 bytes");
 #elif defined(__STDC_VERSION__) && __STDC_VERSION__ >= 201112L
 _Static_assert(sizeof(plf_keypoint) == 28, "plf_keypoint must be layout-identical to cv::KeyPoint");
 _Static_assert(sizeof(plf_keyline) == 68, "plf_keyline must be layout-identical to cv::line_descriptor::KeyLine");
 _Static_assert(sizeof(plf_proj_query) == 56, "plf_proj_query is 56 bytes");
 _Static_assert(sizeof(plf_frame_query) == 72, "plf_frame_query is 72 bytes");
+_Static_assert(sizeof(plf_track_line) == 24, "plf_track_line is 24 bytes");
 #endif
 
 #ifdef __cplusplus

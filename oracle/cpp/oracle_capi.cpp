@@ -10,6 +10,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstring>
+#include <map>
 #include <string>
 #include <thread>
 
@@ -622,6 +623,278 @@ PLF_API int plf_cpu_search_by_projection_frame(plf_ctx* c, int slot, const plf_f
                 }
     }
     if (n_matches) *n_matches = nmatches;
+    return PLF_OK;
+}
+
+// ---- the remaining descriptor searches of SURVEY §8(f) rank 1 and the line-match gates ---------------------------------
+namespace {
+// Frame::GetFeaturesInArea / KeyFrame::GetFeaturesInArea (src/Frame.cc:774-843, src/KeyFrame.cc:881-925) over mGrid of the slot
+struct SlotGrid {
+    std::vector<std::vector<int>> cell;
+    float invW, invH;
+    const std::vector<plf_keypoint>* kps;
+    SlotGrid(const plf_ctx* c, const std::vector<plf_keypoint>& k) : cell(PLF_GRID_COLS * PLF_GRID_ROWS), kps(&k) {
+        invW = (float)PLF_GRID_COLS / ((float)c->p.width - 0.0f);
+        invH = (float)PLF_GRID_ROWS / ((float)c->p.height - 0.0f);
+        for (int i = 0; i < (int)k.size(); ++i) {       // AssignFeaturesToGrid + PosInGrid (src/Frame.cc:451-482, :845-855)
+            const int px = (int)std::round((k[i].x - 0.0f) * invW), py = (int)std::round((k[i].y - 0.0f) * invH);
+            if (px < 0 || px >= PLF_GRID_COLS || py < 0 || py >= PLF_GRID_ROWS) continue;
+            cell[px * PLF_GRID_ROWS + py].push_back(i);
+        }
+    }
+    void area(float x, float y, float r, int minLevel, int maxLevel, std::vector<int>& out) const {
+        out.clear();
+        const int nMinCellX = std::max(0, (int)std::floor((x - 0.0f - r) * invW));
+        if (nMinCellX >= PLF_GRID_COLS) return;
+        const int nMaxCellX = std::min(PLF_GRID_COLS - 1, (int)std::ceil((x - 0.0f + r) * invW));
+        if (nMaxCellX < 0) return;
+        const int nMinCellY = std::max(0, (int)std::floor((y - 0.0f - r) * invH));
+        if (nMinCellY >= PLF_GRID_ROWS) return;
+        const int nMaxCellY = std::min(PLF_GRID_ROWS - 1, (int)std::ceil((y - 0.0f + r) * invH));
+        if (nMaxCellY < 0) return;
+        const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+        for (int ix = nMinCellX; ix <= nMaxCellX; ++ix)
+            for (int iy = nMinCellY; iy <= nMaxCellY; ++iy)
+                for (int idx : cell[ix * PLF_GRID_ROWS + iy]) {
+                    const plf_keypoint& kp = (*kps)[idx];
+                    if (bCheckLevels) {
+                        if (kp.octave < minLevel) continue;
+                        if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                    }
+                    const float distx = kp.x - x, disty = kp.y - y;
+                    if (std::fabs(distx) < r && std::fabs(disty) < r) out.push_back(idx);
+                }
+    }
+};
+
+// ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:2449-2490)
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+}  // namespace
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:2325-2447,
+// from the projected points on.  parity unpinned (needs MapPoint / KeyFrame state); cross-checked by a Python restatement.
+PLF_API int plf_cpu_search_by_projection_reloc(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, int orb_dist,
+                                               int check_orientation, uint8_t* occupied, int n_features, int32_t* feat_query,
+                                               int* n_matches) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || !queries || n_queries < 0 || !occupied || !feat_query)
+        return fail(PLF_ERR_INVALID, "bad arguments");
+    const Slot& sl = c->slots[slot];
+    const std::vector<plf_keypoint>& kps = sl.orb[0].kps;
+    const uint8_t* D = sl.orb[0].desc.data();
+    const int N = (int)kps.size();
+    if (n_features < N) return fail(PLF_ERR_INVALID, "occupied[] / feat_query[] are shorter than the slot's keypoint count");
+    const SlotGrid grid(c, kps);
+    for (int f = 0; f < N; ++f) feat_query[f] = -1;
+    const int HISTO_LENGTH = 30;
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / HISTO_LENGTH;
+    int nmatches = 0;
+    std::vector<int> vIndices2;
+    for (int i = 0; i < n_queries; ++i) {
+        const plf_frame_query& q = queries[i];
+        if (q.skip) continue;
+        grid.area(q.u, q.v, q.radius, q.min_level, q.max_level, vIndices2);
+        if (vIndices2.empty()) continue;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (occupied[i2]) continue;                       // CurrentFrame.mvpMapPoints[i2]
+            const int dist = plf_hamming256(q.desc, D + (size_t)i2 * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestIdx2 >= 0 && bestDist <= orb_dist) {
+            occupied[bestIdx2] = 1;
+            feat_query[bestIdx2] = i;
+            nmatches++;
+            if (check_orientation) {
+                float rot = q.angle - kps[bestIdx2].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)std::round(rot * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                if (bin >= 0 && bin < HISTO_LENGTH) rotHist[bin].push_back(bestIdx2);
+            }
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (size_t j = 0; j < rotHist[i].size(); j++) {
+                    occupied[rotHist[i][j]] = 0;              // CurrentFrame.mvpMapPoints[...] = NULL
+                    feat_query[rotHist[i][j]] = -1;
+                    nmatches--;
+                }
+    }
+    if (n_matches) *n_matches = nmatches;
+    return PLF_OK;
+}
+
+// ORBmatcher::SearchByProjection(KeyFrame* pKF, Scw, vpPoints, vpMatched, th, ratioHamming), src/ORBmatcher.cc:473-580 (and
+// :582-704), from the projected points on.  parity unpinned, as above.
+PLF_API int plf_cpu_search_by_projection_loop(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, int th_low,
+                                              float ratio_hamming, uint8_t* occupied, int n_features, int32_t* feat_query,
+                                              int* n_matches) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || !queries || n_queries < 0 || !occupied || !feat_query)
+        return fail(PLF_ERR_INVALID, "bad arguments");
+    const Slot& sl = c->slots[slot];
+    const std::vector<plf_keypoint>& kps = sl.orb[0].kps;
+    const uint8_t* D = sl.orb[0].desc.data();
+    const int N = (int)kps.size();
+    if (n_features < N) return fail(PLF_ERR_INVALID, "occupied[] / feat_query[] are shorter than the slot's keypoint count");
+    const SlotGrid grid(c, kps);
+    for (int f = 0; f < N; ++f) feat_query[f] = -1;
+    int nmatches = 0;
+    std::vector<int> vIndices;
+    for (int iMP = 0; iMP < n_queries; ++iMP) {
+        const plf_frame_query& q = queries[iMP];
+        if (q.skip) continue;
+        grid.area(q.u, q.v, q.radius, -1, -1, vIndices);      // pKF->GetFeaturesInArea(u, v, radius): no level filter
+        if (vIndices.empty()) continue;
+        const int nPredictedLevel = q.max_level;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (occupied[idx]) continue;                      // vpMatched[idx]
+            const int kpLevel = kps[idx].octave;
+            if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+            const int dist = plf_hamming256(q.desc, D + (size_t)idx * 32);
+            if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+        }
+        if (bestIdx >= 0 && bestDist <= th_low * ratio_hamming) {
+            occupied[bestIdx] = 1;
+            feat_query[bestIdx] = iMP;
+            nmatches++;
+        }
+    }
+    if (n_matches) *n_matches = nmatches;
+    return PLF_OK;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches), src/ORBmatcher.cc:269-471, F.Nleft == -1.
+// The two FeatureVectors are std::map<NodeId, vector<unsigned>>: rebuilt here from the per-feature node ids.
+PLF_API int plf_cpu_search_by_bow(plf_ctx* c, int slot, const uint8_t* kf_desc, const float* kf_angle, const int32_t* kf_node,
+                                  const uint8_t* kf_valid, int n_kf, const int32_t* f_node, int n_features, int th_low,
+                                  float nn_ratio, int check_orientation, int32_t* match, int* n_matches) {
+    if (!c || slot < 0 || slot >= (int)c->slots.size() || n_kf < 0 || n_features < 0 ||
+        (n_kf && (!kf_desc || !kf_angle || !kf_node || !kf_valid)) || (n_features && (!f_node || !match)))
+        return fail(PLF_ERR_INVALID, "bad arguments");
+    const Slot& sl = c->slots[slot];
+    const std::vector<plf_keypoint>& kps = sl.orb[0].kps;
+    const uint8_t* D = sl.orb[0].desc.data();
+    const int N = (int)kps.size();
+    if (n_features < N) return fail(PLF_ERR_INVALID, "f_node[] / match[] are shorter than the slot's keypoint count");
+    std::map<int, std::vector<unsigned>> vFeatVecKF, vFeatVecF;
+    for (int i = 0; i < n_kf; ++i) if (kf_node[i] >= 0) vFeatVecKF[kf_node[i]].push_back((unsigned)i);
+    for (int i = 0; i < N; ++i) if (f_node[i] >= 0) vFeatVecF[f_node[i]].push_back((unsigned)i);
+    for (int f = 0; f < n_features; ++f) match[f] = -1;       // vpMapPointMatches = vector<MapPoint*>(F.N, NULL)
+    int nmatches = 0;
+    const int HISTO_LENGTH = 30, TH_LOW = th_low;
+    std::vector<int> rotHist[30];
+    const float factor = 1.0f / HISTO_LENGTH;
+    auto KFit = vFeatVecKF.begin(), KFend = vFeatVecKF.end();
+    auto Fit = vFeatVecF.begin(), Fend = vFeatVecF.end();
+    while (KFit != KFend && Fit != Fend) {
+        if (KFit->first == Fit->first) {
+            const std::vector<unsigned>& vIndicesKF = KFit->second;
+            const std::vector<unsigned>& vIndicesF = Fit->second;
+            for (size_t iKF = 0; iKF < vIndicesKF.size(); iKF++) {
+                const unsigned realIdxKF = vIndicesKF[iKF];
+                if (!kf_valid[realIdxKF]) continue;           // no map point, or a bad one
+                const uint8_t* dKF = kf_desc + (size_t)realIdxKF * 32;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (size_t iF = 0; iF < vIndicesF.size(); iF++) {
+                    const unsigned realIdxF = vIndicesF[iF];
+                    if (match[realIdxF] >= 0) continue;
+                    const int dist = plf_hamming256(dKF, D + (size_t)realIdxF * 32);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = (int)realIdxF; }
+                    else if (dist < bestDist2) { bestDist2 = dist; }
+                }
+                if (bestDist1 <= TH_LOW) {
+                    if (static_cast<float>(bestDist1) < nn_ratio * static_cast<float>(bestDist2)) {
+                        match[bestIdxF] = (int)realIdxKF;
+                        if (check_orientation) {
+                            float rot = kf_angle[realIdxKF] - kps[bestIdxF].angle;
+                            if (rot < 0.0) rot += 360.0f;
+                            int bin = (int)std::round(rot * factor);
+                            if (bin == HISTO_LENGTH) bin = 0;
+                            if (bin >= 0 && bin < HISTO_LENGTH) rotHist[bin].push_back(bestIdxF);
+                        }
+                        nmatches++;
+                    }
+                }
+            }
+            KFit++;
+            Fit++;
+        } else if (KFit->first < Fit->first) {
+            KFit = vFeatVecKF.lower_bound(Fit->first);
+        } else {
+            Fit = vFeatVecF.lower_bound(KFit->first);
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (size_t j = 0; j < rotHist[i].size(); j++) { match[rotHist[i][j]] = -1; nmatches--; }
+        }
+    }
+    if (n_matches) *n_matches = nmatches;
+    return PLF_OK;
+}
+
+// match() + the gates of Tracking::TrackWithMotionModel (src/Tracking.cc:3055-3099, mode 0) and Tracking::SearchLocalLines
+// (src/Tracking.cc:3879-3917, mode 1), restated loop by loop.
+PLF_API int plf_cpu_match_lines_tracked(plf_ctx*, int mode, const uint8_t* desc1, const plf_track_line* lines1, int n1,
+                                        const uint8_t* desc2, const plf_keyline* kl2, const float* disp2, const uint8_t* held2,
+                                        int n2, float nnr, float min_x, float max_x, float min_y, float max_y, int32_t* matches12,
+                                        int32_t* assign12, int* n_assigned) {
+    if (mode < 0 || mode > 1 || n1 < 0 || n2 < 0 || (n1 && (!desc1 || !lines1 || !matches12 || !assign12)) ||
+        (n2 && (!desc2 || !kl2 || !disp2)))
+        return fail(PLF_ERR_INVALID, "bad arguments");
+    if (n_assigned) *n_assigned = 0;
+    if (n1 == 0) return PLF_OK;
+    match_lr(desc1, n1, desc2, n2, nnr, 1, matches12);
+    const double kPiD = 3.14159265358979323846;
+    const double deltaAngle = kPiD / 8.0;
+    const double deltaWidth = (max_x - min_x) * 0.1;
+    const double deltaHeight = (max_y - min_y) * 0.1;
+    int n_inliers_ls = 0;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        assign12[i1] = -1;
+        if (!lines1[i1].eligible) continue;
+        const int i2 = matches12[i1];
+        if (i2 < 0) continue;
+        if (disp2[i2 * 2] < 0 || disp2[i2 * 2 + 1] < 0) continue;
+        if (mode == 1 && held2 && held2[i2]) continue;
+        if (mode == 0) {
+            double theta = kl2[i2].angle - lines1[i1].angle;
+            if (theta < -kPiD) theta += 2 * kPiD;
+            else if (theta > kPiD) theta -= 2 * kPiD;
+            if (std::fabs(theta) > deltaAngle) { matches12[i1] = -1; continue; }
+        }
+        const float sX_curr = kl2[i2].startPointX, sX_last = lines1[i1].sx;
+        const float sY_curr = kl2[i2].startPointY, sY_last = lines1[i1].sy;
+        const float eX_curr = kl2[i2].endPointX, eX_last = lines1[i1].ex;
+        const float eY_curr = kl2[i2].endPointY, eY_last = lines1[i1].ey;
+        if (std::fabs(sX_curr - sX_last) > deltaWidth || std::fabs(eX_curr - eX_last) > deltaWidth ||
+            std::fabs(sY_curr - sY_last) > deltaHeight || std::fabs(eY_curr - eY_last) > deltaHeight) {
+            matches12[i1] = -1;
+            continue;
+        }
+        assign12[i1] = i2;
+        ++n_inliers_ls;
+    }
+    if (n_assigned) *n_assigned = n_inliers_ls;
     return PLF_OK;
 }
 

@@ -5,5 +5,5 @@ the thin Python host mirror used by tests and bench.py; the C++ host mirror of t
 `pli-slam_b200/host/`.  There is no CPU fallback: `load_product()` raises when the CUDA library is absent.
 """
 from .binding import (Frontend, Library, Params, PlfError, BatchResult, load_product, load_oracle, KEYPOINT_DT,
-                      KEYLINE_DT, PROJ_QUERY_DT, FRAME_QUERY_DT, ABI_SYMBOLS, PRODUCT_LIB, ORACLE_LIB)
+                      KEYLINE_DT, PROJ_QUERY_DT, FRAME_QUERY_DT, TRACK_LINE_DT, ABI_SYMBOLS, PRODUCT_LIB, ORACLE_LIB)
 from .synth import synth_pair, synth_batch, synth_curvy, synth_vocabulary, rectify_maps, EUROC_CALIB

@@ -65,6 +65,8 @@ PROJ_QUERY_DT = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4
                           ("skip", "<i4"), ("desc", "u1", (32,))])       # plf_proj_query, 56 bytes
 FRAME_QUERY_DT = np.dtype([("u", "<f4"), ("v", "<f4"), ("ur", "<f4"), ("radius", "<f4"), ("min_level", "<i4"), ("max_level", "<i4"),
                            ("skip", "<i4"), ("has_observations", "<i4"), ("angle", "<f4"), ("desc", "u1", (32,)), ("pad", "<i4")])
+TRACK_LINE_DT = np.dtype([("sx", "<f4"), ("sy", "<f4"), ("ex", "<f4"), ("ey", "<f4"), ("angle", "<f4"), ("eligible", "<i4")])   # plf_track_line
+assert PROJ_QUERY_DT.itemsize == 56 and FRAME_QUERY_DT.itemsize == 72 and TRACK_LINE_DT.itemsize == 24
 GRID_COLS, GRID_ROWS = 64, 48      # FRAME_GRID_COLS / FRAME_GRID_ROWS (include/Frame.h:59-60)
 
 ABI_SYMBOLS = [
@@ -74,6 +76,7 @@ ABI_SYMBOLS = [
     "last_launch_count", "set_stage_timing", "get_stage_ms", "stream", "tap_blurred_level", "tap_pyramid_level",
     "tap_fast_candidates", "tap_lsd_scaled", "tap_lsd_angles", "tap_lsd_segments", "tap_lbd_float",
     "rectify_set_maps", "rectify", "batch_upload_raw", "feature_grid", "get_features_in_area", "backproject", "bow_set_vocabulary", "bow_transform", "bow_build_vectors", "search_by_projection", "search_by_projection_frame",
+    "search_by_projection_reloc", "search_by_projection_loop", "search_by_bow", "match_lines_tracked",
 ]
 
 
@@ -395,6 +398,60 @@ class Frontend:
                                                                  int(bool(check_orientation)), _ptr(occupied), len(occupied),
                                                                  _ptr(fq), _ptr(m12), C.byref(nm)))
         return fq, m12, nm.value
+
+    def search_by_projection_reloc(self, queries, occupied, orb_dist=100, check_orientation=True, slot=0):
+        """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) from the projected points on
+        -> (feat_query, nmatches); occupied (uint8 per keypoint) is updated in place."""
+        queries = np.ascontiguousarray(queries, FRAME_QUERY_DT)
+        assert occupied.dtype == np.uint8 and occupied.flags.c_contiguous
+        fq = np.full(len(occupied), -1, np.int32)
+        nm = C.c_int(0)
+        self.lib.check(self.lib.fn("search_by_projection_reloc")(self.ctx, slot, _ptr(queries), len(queries), int(orb_dist),
+                                                                 int(bool(check_orientation)), _ptr(occupied), len(occupied),
+                                                                 _ptr(fq), C.byref(nm)))
+        return fq, nm.value
+
+    def search_by_projection_loop(self, queries, occupied, th_low=50, ratio_hamming=1.0, slot=0):
+        """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) from the projected points on
+        -> (feat_query, nmatches); occupied = vpMatched != NULL, updated in place."""
+        queries = np.ascontiguousarray(queries, FRAME_QUERY_DT)
+        assert occupied.dtype == np.uint8 and occupied.flags.c_contiguous
+        fq = np.full(len(occupied), -1, np.int32)
+        nm = C.c_int(0)
+        self.lib.check(self.lib.fn("search_by_projection_loop")(self.ctx, slot, _ptr(queries), len(queries), int(th_low),
+                                                                C.c_float(ratio_hamming), _ptr(occupied), len(occupied),
+                                                                _ptr(fq), C.byref(nm)))
+        return fq, nm.value
+
+    def search_by_bow(self, kf_desc, kf_angle, kf_node, kf_valid, f_node, th_low=50, nn_ratio=0.7, check_orientation=True, slot=0):
+        """ORBmatcher::SearchByBoW(pKF, F, vpMapPointMatches) -> (match [len(f_node)]: keyframe feature per frame feature
+        or -1, nmatches)."""
+        kf_desc = np.ascontiguousarray(kf_desc, np.uint8).reshape(-1, 32)
+        kf_angle = np.ascontiguousarray(kf_angle, np.float32); kf_node = np.ascontiguousarray(kf_node, np.int32)
+        kf_valid = np.ascontiguousarray(kf_valid, np.uint8); f_node = np.ascontiguousarray(f_node, np.int32)
+        m = np.full(max(len(f_node), 1), -1, np.int32)
+        nm = C.c_int(0)
+        self.lib.check(self.lib.fn("search_by_bow")(self.ctx, slot, _ptr(kf_desc), _ptr(kf_angle), _ptr(kf_node), _ptr(kf_valid),
+                                                    len(kf_desc), _ptr(f_node), len(f_node), int(th_low), C.c_float(nn_ratio),
+                                                    int(bool(check_orientation)), _ptr(m), C.byref(nm)))
+        return m[:len(f_node)], nm.value
+
+    def match_lines_tracked(self, mode, desc1, lines1, desc2, kl2, disp2, held2, nnr, bounds):
+        """match() + the tracking gates (mode 0: Tracking::TrackWithMotionModel, 1: SearchLocalLines) ->
+        (matches12, assign12, n_assigned).  bounds = (mnMinX, mnMaxX, mnMinY, mnMaxY)."""
+        desc1 = np.ascontiguousarray(desc1, np.uint8).reshape(-1, 32); desc2 = np.ascontiguousarray(desc2, np.uint8).reshape(-1, 32)
+        lines1 = np.ascontiguousarray(lines1, TRACK_LINE_DT); kl2 = np.ascontiguousarray(kl2, KEYLINE_DT)
+        disp2 = np.ascontiguousarray(disp2, np.float32).reshape(-1, 2)
+        held2 = None if held2 is None else np.ascontiguousarray(held2, np.uint8)
+        n1, n2 = len(desc1), len(desc2)
+        assert len(lines1) == n1 and len(kl2) == n2 and len(disp2) == n2
+        m = np.full(max(n1, 1), -1, np.int32); a = np.full(max(n1, 1), -1, np.int32)
+        na = C.c_int(0)
+        self.lib.check(self.lib.fn("match_lines_tracked")(self.ctx, int(mode), _ptr(desc1), _ptr(lines1), n1, _ptr(desc2), _ptr(kl2),
+                                                          _ptr(disp2), _ptr(held2), n2, C.c_float(nnr), C.c_float(bounds[0]),
+                                                          C.c_float(bounds[1]), C.c_float(bounds[2]), C.c_float(bounds[3]),
+                                                          _ptr(m), _ptr(a), C.byref(na)))
+        return m[:n1], a[:n1], na.value
 
     # ---- bag of words (SURVEY §8f rank 3) ------------------------------------------------------------------------------
     def bow_set_vocabulary(self, which, voc):

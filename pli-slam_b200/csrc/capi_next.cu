@@ -140,12 +140,23 @@ PLF_API int plf_search_by_projection(plf_ctx* c, int slot, const plf_proj_query*
     return PLF_OK;
 }
 
-PLF_API int plf_search_by_projection_frame(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, int th_high,
-                                           int check_orientation, uint8_t* occupied, int n_features, int32_t* feat_query,
-                                           int32_t* match12, int* n_matches) {
+}  // extern "C"
+
+// The three overloads that take already projected points (frame-to-frame :2179-2323, relocalisation :2325-2447, loop
+// closing :473-704) share everything but four switches.
+struct ProjSearchRule {
+    bool stereo;          // |ur - mvuRight| <= radius for features with a right match (frame-to-frame only, :2262-2267)
+    bool holderByObs;     // a feature is blocked iff its holder has observations (frame-to-frame); else any holder blocks
+    bool orientation;     // rotation histogram + ComputeThreeMaxima
+    float maxDist;        // accepted iff (float)bestDist <= maxDist (TH_HIGH, ORBdist, or TH_LOW * ratioHamming in float)
+};
+
+static int search_projected(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, const ProjSearchRule& rule,
+                            uint8_t* occupied, int n_features, int32_t* feat_query, int32_t* match12, int* n_matches) {
     if (!c || slot < 0 || slot >= c->p.max_batch || !queries || n_queries < 0 || !occupied || !feat_query || n_features < 0)
         return fail(PLF_ERR_INVALID, "bad arguments");
-    if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "search_by_projection_frame before the frame was extracted and stereo-matched");
+    const int check_orientation = rule.orientation;
+    if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "search_by_projection before the frame was extracted and stereo-matched");
     PLF_CUDA_OK(cudaSetDevice(c->device));
     // the current frame's keypoint count and angles (rotation histogram)
     const int img = slot * 2;
@@ -163,7 +174,7 @@ PLF_API int plf_search_by_projection_frame(plf_ctx* c, int slot, const plf_frame
         const plf_frame_query& m = queries[i];
         PlfWinQ& w = q[i];
         w.skip = m.skip; w.x = m.u; w.y = m.v; w.xr = m.ur; w.radius = m.radius;
-        w.minLevel = m.min_level; w.maxLevel = m.max_level; w.pad = 0;
+        w.minLevel = m.min_level; w.maxLevel = m.max_level; w.pad = rule.stereo ? 0 : 1;      // bit 0: no stereo check
         memcpy(w.desc, m.desc, 32);
     }
     std::vector<int> start;
@@ -183,9 +194,9 @@ PLF_API int plf_search_by_projection_frame(plf_ctx* c, int slot, const plf_frame
             if (occupied[idx]) continue;
             if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
         }
-        if (bestIdx >= 0 && bestDist <= th_high) {
+        if (bestIdx >= 0 && (float)bestDist <= rule.maxDist) {
             feat_query[bestIdx] = i;
-            occupied[bestIdx] = queries[i].has_observations ? 1 : 0;     // the holder decides whether later points skip it
+            occupied[bestIdx] = (!rule.holderByObs || queries[i].has_observations) ? 1 : 0;     // the holder decides whether later points skip it
             ++nm;
             if (match12 && match12[bestIdx] < 0) match12[bestIdx] = i;    // std::map::insert keeps the first
             if (check_orientation) {
@@ -217,6 +228,189 @@ PLF_API int plf_search_by_projection_frame(plf_ctx* c, int slot, const plf_frame
                 }
     }
     if (n_matches) *n_matches = nm;
+    return PLF_OK;
+}
+
+extern "C" {
+
+PLF_API int plf_search_by_projection_frame(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, int th_high,
+                                           int check_orientation, uint8_t* occupied, int n_features, int32_t* feat_query,
+                                           int32_t* match12, int* n_matches) {
+    const ProjSearchRule rule = {true, true, check_orientation != 0, (float)th_high};
+    return search_projected(c, slot, queries, n_queries, rule, occupied, n_features, feat_query, match12, n_matches);
+}
+
+PLF_API int plf_search_by_projection_reloc(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, int orb_dist,
+                                           int check_orientation, uint8_t* occupied, int n_features, int32_t* feat_query,
+                                           int* n_matches) {
+    const ProjSearchRule rule = {false, false, check_orientation != 0, (float)orb_dist};
+    return search_projected(c, slot, queries, n_queries, rule, occupied, n_features, feat_query, nullptr, n_matches);
+}
+
+PLF_API int plf_search_by_projection_loop(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, int th_low,
+                                          float ratio_hamming, uint8_t* occupied, int n_features, int32_t* feat_query,
+                                          int* n_matches) {
+    const ProjSearchRule rule = {false, false, false, (float)th_low * ratio_hamming};
+    return search_projected(c, slot, queries, n_queries, rule, occupied, n_features, feat_query, nullptr, n_matches);
+}
+
+// grow-only device scratch for the small per-frame searches below
+static cudaError_t scratch_reserve(plf_ctx* c, size_t bytes) {
+    if (c->scrCap >= bytes) return cudaSuccess;
+    cudaStreamSynchronize(c->stream);
+    if (c->d_scr) cudaFree(c->d_scr);
+    c->d_scr = nullptr;
+    c->scrCap = 0;
+    const size_t want = std::max(bytes * 2, (size_t)1 << 20);
+    cudaError_t e = cudaMalloc((void**)&c->d_scr, want);
+    if (e == cudaSuccess) c->scrCap = want;
+    return e;
+}
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// ---- ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (src/ORBmatcher.cc:269-471) ---------------------------------------
+PLF_API int plf_search_by_bow(plf_ctx* c, int slot, const uint8_t* kf_desc, const float* kf_angle, const int32_t* kf_node,
+                              const uint8_t* kf_valid, int n_kf, const int32_t* f_node, int n_features, int th_low,
+                              float nn_ratio, int check_orientation, int32_t* match, int* n_matches) {
+    if (!c || slot < 0 || slot >= c->p.max_batch || n_kf < 0 || n_features < 0 || (n_kf && (!kf_desc || !kf_angle || !kf_node || !kf_valid)) ||
+        (n_features && (!f_node || !match)))
+        return fail(PLF_ERR_INVALID, "bad arguments");
+    if (!c->orbValid[0]) return fail(PLF_ERR_STATE, "search_by_bow before the frame was extracted");
+    PLF_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int img = slot * 2;
+    int N = 0;
+    PLF_CUDA_OK(cudaStreamSynchronize(s));
+    PLF_CUDA_OK(cudaMemcpy(&N, c->d_nKp + img, 4, cudaMemcpyDeviceToHost));
+    if (n_features < N) return fail(PLF_ERR_INVALID, "f_node[] / match[] are shorter than the slot's keypoint count");
+    for (int f = 0; f < n_features; ++f) match[f] = -1;
+    if (n_matches) *n_matches = 0;
+    if (n_kf == 0 || N == 0) return PLF_OK;
+    // F.mFeatVec as CSR: nodes ascending (std::map order), features of a node ascending (addFeature in feature order)
+    std::vector<int> order;
+    order.reserve(N);
+    for (int f = 0; f < N; ++f) if (f_node[f] >= 0) order.push_back(f);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return f_node[a] < f_node[b]; });
+    std::vector<int> kfOrder;
+    for (int i = 0; i < n_kf; ++i) if (kf_node[i] >= 0) kfOrder.push_back(i);
+    std::stable_sort(kfOrder.begin(), kfOrder.end(), [&](int a, int b) { return kf_node[a] < kf_node[b]; });
+    // per valid keyframe feature (in the reference's visiting order): its frame range and its slice of the distance pool
+    struct Job { int kf, begin, end, pool; };
+    std::vector<Job> jobs;
+    size_t pool = 0;
+    {
+        size_t a = 0, b = 0;
+        while (a < kfOrder.size() && b < order.size()) {
+            const int na = kf_node[kfOrder[a]], nb = f_node[order[b]];
+            if (na < nb) { ++a; continue; }
+            if (nb < na) { ++b; continue; }
+            size_t b1 = b;
+            while (b1 < order.size() && f_node[order[b1]] == na) ++b1;
+            for (; a < kfOrder.size() && kf_node[kfOrder[a]] == na; ++a)
+                if (kf_valid[kfOrder[a]]) { jobs.push_back({kfOrder[a], (int)b, (int)b1, (int)pool}); pool += b1 - b; }
+            b = b1;
+        }
+    }
+    if (jobs.empty()) return PLF_OK;
+    const size_t oDesc = 0, oJobs = align256((size_t)n_kf * 32), oOrder = oJobs + align256(jobs.size() * sizeof(Job));
+    const size_t oPool = oOrder + align256(order.size() * 4), total = oPool + align256(pool * 4);
+    PLF_CUDA_OK(scratch_reserve(c, total));
+    PLF_CUDA_OK(cudaMemcpyAsync(c->d_scr + oDesc, kf_desc, (size_t)n_kf * 32, cudaMemcpyHostToDevice, s));
+    PLF_CUDA_OK(cudaMemcpyAsync(c->d_scr + oJobs, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice, s));
+    PLF_CUDA_OK(cudaMemcpyAsync(c->d_scr + oOrder, order.data(), order.size() * 4, cudaMemcpyHostToDevice, s));
+    c->launches = plf_launch_bow_pairs(c, slot, c->d_scr + oDesc, reinterpret_cast<const int4*>(c->d_scr + oJobs), (int)jobs.size(),
+                                       reinterpret_cast<const int*>(c->d_scr + oOrder), reinterpret_cast<int*>(c->d_scr + oPool));
+    std::vector<int> dist(pool);
+    std::vector<plf_keypoint> kps((size_t)N);
+    PLF_CUDA_OK(cudaMemcpyAsync(dist.data(), c->d_scr + oPool, pool * 4, cudaMemcpyDeviceToHost, s));
+    PLF_CUDA_OK(cudaMemcpyAsync(kps.data(), c->d_kp + (size_t)img * c->g.kpCap, (size_t)N * sizeof(plf_keypoint), cudaMemcpyDeviceToHost, s));
+    PLF_CUDA_OK(cudaStreamSynchronize(s));
+    PLF_CUDA_OK(cudaGetLastError());
+    // the order-dependent half (src/ORBmatcher.cc:296-402 for F.Nleft == -1, then :447-467)
+    constexpr int HISTO = 30;
+    std::vector<int> rotHist[HISTO];
+    const float factor = 1.0f / HISTO;
+    int nm = 0;
+    for (const Job& j : jobs) {
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int k = j.begin; k < j.end; ++k) {
+            const int f = order[k];
+            if (match[f] >= 0) continue;
+            const int d = dist[j.pool + (k - j.begin)];
+            if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdxF = f; }
+            else if (d < bestDist2) bestDist2 = d;
+        }
+        if (bestDist1 <= th_low && (float)bestDist1 < nn_ratio * (float)bestDist2) {
+            match[bestIdxF] = j.kf;
+            if (check_orientation) {
+                float rot = kf_angle[j.kf] - kps[bestIdxF].angle;
+                if (rot < 0.0) rot += 360.0f;
+                int bin = (int)roundf(rot * factor);
+                if (bin == HISTO) bin = 0;
+                if (bin >= 0 && bin < HISTO) rotHist[bin].push_back(bestIdxF);
+            }
+            ++nm;
+        }
+    }
+    if (check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1, max1 = 0, max2 = 0, max3 = 0;          // ComputeThreeMaxima, :2449-2490
+        for (int i = 0; i < HISTO; ++i) {
+            const int sz = (int)rotHist[i].size();
+            if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+            else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+            else if (sz > max3) { max3 = sz; ind3 = i; }
+        }
+        if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+        else if (max3 < 0.1f * (float)max1) ind3 = -1;
+        for (int i = 0; i < HISTO; ++i)
+            if (i != ind1 && i != ind2 && i != ind3)
+                for (int f : rotHist[i]) { match[f] = -1; --nm; }
+    }
+    if (n_matches) *n_matches = nm;
+    return PLF_OK;
+}
+
+// ---- match() + the tracking thread's gates (src/Tracking.cc:3055-3099, :3879-3917) -------------------------------------
+PLF_API int plf_match_lines_tracked(plf_ctx* c, int mode, const uint8_t* desc1, const plf_track_line* lines1, int n1,
+                                    const uint8_t* desc2, const plf_keyline* kl2, const float* disp2, const uint8_t* held2, int n2,
+                                    float nnr, float min_x, float max_x, float min_y, float max_y, int32_t* matches12,
+                                    int32_t* assign12, int* n_assigned) {
+    if (!c || mode < 0 || mode > 1 || n1 < 0 || n2 < 0 || (n1 && (!desc1 || !lines1 || !matches12 || !assign12)) ||
+        (n2 && (!desc2 || !kl2 || !disp2)))
+        return fail(PLF_ERR_INVALID, "bad arguments");
+    if (n_assigned) *n_assigned = 0;
+    if (n1 == 0) return PLF_OK;
+    PLF_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const size_t oD1 = 0, oD2 = oD1 + align256((size_t)n1 * 32), oL1 = oD2 + align256((size_t)n2 * 32);
+    const size_t oK2 = oL1 + align256((size_t)n1 * sizeof(plf_track_line)), oDisp = oK2 + align256((size_t)n2 * sizeof(plf_keyline));
+    const size_t oHeld = oDisp + align256((size_t)n2 * 8), oM12 = oHeld + align256((size_t)n2);
+    const size_t oM21 = oM12 + align256((size_t)n1 * 4), oAsg = oM21 + align256((size_t)n2 * 4), total = oAsg + align256((size_t)n1 * 4);
+    PLF_CUDA_OK(scratch_reserve(c, total));
+    uint8_t* b = c->d_scr;
+    PLF_CUDA_OK(cudaMemcpyAsync(b + oD1, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+    PLF_CUDA_OK(cudaMemcpyAsync(b + oL1, lines1, (size_t)n1 * sizeof(plf_track_line), cudaMemcpyHostToDevice, s));
+    if (n2) {
+        PLF_CUDA_OK(cudaMemcpyAsync(b + oD2, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+        PLF_CUDA_OK(cudaMemcpyAsync(b + oK2, kl2, (size_t)n2 * sizeof(plf_keyline), cudaMemcpyHostToDevice, s));
+        PLF_CUDA_OK(cudaMemcpyAsync(b + oDisp, disp2, (size_t)n2 * 8, cudaMemcpyHostToDevice, s));
+        if (held2) PLF_CUDA_OK(cudaMemcpyAsync(b + oHeld, held2, (size_t)n2, cudaMemcpyHostToDevice, s));
+    }
+    int* dM12 = reinterpret_cast<int*>(b + oM12);
+    int* dM21 = reinterpret_cast<int*>(b + oM21);
+    int* dAsg = reinterpret_cast<int*>(b + oAsg);
+    c->launches = plf_launch_match_nnr(c, b + oD1, n1, b + oD2, n2, nnr, dM12);
+    c->launches += plf_launch_match_nnr(c, b + oD2, n2, b + oD1, n1, nnr, dM21);
+    c->launches += plf_launch_line_gates(c, mode, reinterpret_cast<const plf_track_line*>(b + oL1), n1,
+                                         reinterpret_cast<const plf_keyline*>(b + oK2), reinterpret_cast<const float2*>(b + oDisp),
+                                         (mode == 1 && held2) ? b + oHeld : nullptr, n2, min_x, max_x, min_y, max_y, dM12, dM21, dAsg);
+    PLF_CUDA_OK(cudaMemcpyAsync(matches12, dM12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    PLF_CUDA_OK(cudaMemcpyAsync(assign12, dAsg, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    PLF_CUDA_OK(cudaStreamSynchronize(s));
+    PLF_CUDA_OK(cudaGetLastError());
+    int cnt = 0;
+    for (int i = 0; i < n1; ++i) cnt += assign12[i] >= 0;
+    if (n_assigned) *n_assigned = cnt;
     return PLF_OK;
 }
 

@@ -905,6 +905,7 @@ __global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const f
 }
 
 #include "lsd_stream.cuh"
+#include "lsd_lane.cuh"
 
 // cv::LineIterator(img, Point2f, Point2f).count of LSDDetector_custom.cpp:295-296, 8-connected: end points rounded half to
 // even, clipped with cv::clipLine when one lies outside the image (the clamp of checkLineExtremes leaves x in
@@ -1233,6 +1234,12 @@ static int plf_ensure_stream_buffers(plf_ctx* c) {
     return 0;
 }
 
+static int plf_ensure_lane_buffers(plf_ctx* c) {
+    if (c->d_laneRT) return 0;
+    if (dalloc(&c->d_laneRT, (size_t)c->nImgMax * c->g.segCap) != cudaSuccess) { cudaGetLastError(); c->d_laneRT = nullptr; return 1; }
+    return 0;
+}
+
 static int plf_ensure_mw_buffers(plf_ctx* c) {
     if (c->d_owner && c->d_regMW) return 0;
     const PlfGeom& g = c->g;
@@ -1287,6 +1294,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         // PLF_LSD_GROWER=stream selects the one-lane-per-region grower (exact, measured slower: profiles/r02_stream_grower.md)
         static const char* s_mode = getenv("PLF_LSD_GROWER");
         const bool wantStream = s_mode && !strcmp(s_mode, "stream");
+        const bool wantLane = s_mode && !strcmp(s_mode, "lane");
         if (g.refine >= 1)
             lsd_grow_kernel<true><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                       c->d_nSegs, c->d_err, imgFirst);
@@ -1296,8 +1304,16 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
             int* scr = c->d_stream + (size_t)imgFirst * L.total;
             lsd_stream_init_kernel<<<dim3(32, nImg), 256, 0, s>>>(g, c->d_n2, scr, L, imgFirst);
             lsd_stream_kernel<<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_seeds, c->d_nSeeds, scr, L, c->d_reg, c->d_nReg, c->d_err, imgFirst);
-            lsd_rect_kernel<<<dim3(64, nImg), 128, 0, s>>>(g, c->d_n2, scr, L, c->d_reg, c->d_nReg, c->d_segs, c->d_nSegs, imgFirst);
+            lsd_rect_kernel<<<dim3(64, nImg), 128, 0, s>>>(g, c->d_n2, reinterpret_cast<const int4*>(scr + L.RT), (size_t)L.total / 4, c->d_reg,
+                                                           c->d_nReg, c->d_segs, c->d_nSegs, imgFirst);
             launches += 2;
+        } else if (wantLane && plf_ensure_lane_buffers(c) == 0) {
+            // one lane per image: 32 images per warp, the plain scalar loop; rectangles fitted afterwards
+            lsd_grow_lane_kernel<<<(nImg + 31) / 32, 32, 0, s>>>(g, c->d_rec, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_laneRT, c->d_nReg,
+                                                                 c->d_err, imgFirst, nImg);
+            lsd_rect_kernel<<<dim3(16, nImg), 128, 0, s>>>(g, c->d_n2, c->d_laneRT + (size_t)imgFirst * g.segCap, (size_t)g.segCap, c->d_reg,
+                                                           c->d_nReg, c->d_segs, c->d_nSegs, imgFirst);
+            launches += 1;
         } else if (s_mode && !strcmp(s_mode, "seq"))
             lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                        c->d_nSegs, c->d_err, imgFirst);

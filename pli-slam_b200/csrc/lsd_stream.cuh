@@ -669,14 +669,15 @@ __global__ void __launch_bounds__(32) lsd_stream_kernel(PlfGeom g, const float4*
 }
 
 // rectangle of every committed region (LSD region2rect), one warp per region; the segments come out in commit order
-__global__ void __launch_bounds__(128) lsd_rect_kernel(PlfGeom g, const int* n2map, const int* scratch, StreamLayout L, int* regAll,
+// (region table: rtBase + blockIdx.y * rtStride, entries {offset in the image's list arena, size, region angle in degrees as float bits, -})
+__global__ void __launch_bounds__(128) lsd_rect_kernel(PlfGeom g, const int* n2map, const int4* rtBase, size_t rtStride, int* regAll,
                                                       const int* nRegAll, float* segs, int* nSegsOut, int imgFirst) {
     __shared__ double s_sum[4][3][33];
     const int img = imgFirst + blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nReg = min(nRegAll[img], g.segCap);
     if (blockIdx.x == 0 && threadIdx.x == 0) nSegsOut[img] = nReg;
     for (int ri = blockIdx.x * 4 + w; ri < nReg; ri += gridDim.x * 4) {
-        const int4 rt = reinterpret_cast<const int4*>(scratch + (size_t)blockIdx.y * L.total + L.RT)[ri];
+        const int4 rt = rtBase[(size_t)blockIdx.y * rtStride + ri];
         GrowCtx c;
         c.W = g.Ws; c.H = g.Hs; c.PB = g.Ps; c.lane = lane;
         c.N2 = n2map + (size_t)img * g.Ps * g.Hs;

@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256) proj_candidates_kernel(PlfGeom g, const P
                             oct = k.octave;
                             ok = !(check && (oct < minLevel || (maxLevel >= 0 && oct > maxLevel)));
                             ok = ok && fabsf(__fsub_rn(k.x, q.x)) < rad && fabsf(__fsub_rn(k.y, q.y)) < rad;
-                            if (ok) {
+                            if (ok && !(q.pad & 1)) {          // pad bit 0: the overload has no stereo check
                                 const float ur = uRight[idx];
                                 if (ur > 0 && fabsf(__fsub_rn(q.xr, ur)) > rad) ok = false;
                             }
@@ -334,5 +334,74 @@ int plf_launch_proj_candidates(plf_ctx* c, int slot, const PlfWinQ* dQ, int nq, 
     const dim3 grid((nq + 7) / 8);
     if (fill) proj_candidates_kernel<true><<<grid, 256, 0, c->stream>>>(g, dQ, nq, kp, desc, ur, dCellStart, dCellIdx, dCount, dSegStart, dPool);
     else proj_candidates_kernel<false><<<grid, 256, 0, c->stream>>>(g, dQ, nq, kp, desc, ur, dCellStart, dCellIdx, dCount, dSegStart, dPool);
+    return 1;
+}
+
+// ---- SearchByBoW, device half: a warp per valid keyframe feature; its descriptor against the frame features of the same
+// vocabulary node (job = {keyframe feature, begin, end in the node-sorted frame order, first slot of the distance pool})
+namespace {
+__global__ void __launch_bounds__(256) bow_pairs_kernel(const uint8_t* kfDesc, const int4* jobs, int nJobs, const int* order,
+                                                        const uint8_t* desc, int* pool) {
+    const int ji = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (ji >= nJobs) return;
+    const int4 j = jobs[ji];
+    const uint4* a4 = reinterpret_cast<const uint4*>(kfDesc + (size_t)j.x * 32);
+    const uint4 a = a4[0], b = a4[1];
+    for (int k = j.y + lane; k < j.z; k += 32) {
+        const uint4* f4 = reinterpret_cast<const uint4*>(desc + (size_t)order[k] * 32);
+        const uint4 p = f4[0], s2 = f4[1];
+        pool[j.w + (k - j.y)] = __popc(a.x ^ p.x) + __popc(a.y ^ p.y) + __popc(a.z ^ p.z) + __popc(a.w ^ p.w) +
+                                __popc(b.x ^ s2.x) + __popc(b.y ^ s2.y) + __popc(b.z ^ s2.z) + __popc(b.w ^ s2.w);
+    }
+}
+
+// ---- match() epilogue of the tracking thread: mutual-best filter (src/LineMatcher.cpp:218-224) and the gates of
+// src/Tracking.cc:3062-3098 (mode 0) / :3888-3917 (mode 1), a thread per line of the first set
+__global__ void __launch_bounds__(128) line_gates_kernel(int mode, const plf_track_line* l1, int n1, const plf_keyline* k2,
+                                                         const float2* disp2, const uint8_t* held2, double deltaW, double deltaH,
+                                                         int* m12, const int* m21, int* assign) {
+    const int i1 = blockIdx.x * 128 + threadIdx.x;
+    if (i1 >= n1) return;
+    int i2 = m12[i1];
+    if (i2 >= 0 && m21[i2] != i1) i2 = -1;
+    int as = -1;
+    const plf_track_line a = l1[i1];
+    if (i2 >= 0 && a.eligible) {
+        const float2 d = disp2[i2];
+        if (!(d.x < 0 || d.y < 0) && !(held2 && held2[i2])) {
+            const plf_keyline b = k2[i2];
+            const double kPiD = 3.14159265358979323846;
+            bool ok = true;
+            if (mode == 0) {
+                double theta = (double)__fsub_rn(b.angle, a.angle);
+                if (theta < -kPiD) theta += 2 * kPiD;
+                else if (theta > kPiD) theta -= 2 * kPiD;
+                if (fabs(theta) > kPiD / 8.0) ok = false;
+            }
+            if (ok && ((double)fabsf(__fsub_rn(b.startPointX, a.sx)) > deltaW || (double)fabsf(__fsub_rn(b.endPointX, a.ex)) > deltaW ||
+                       (double)fabsf(__fsub_rn(b.startPointY, a.sy)) > deltaH || (double)fabsf(__fsub_rn(b.endPointY, a.ey)) > deltaH))
+                ok = false;
+            if (ok) as = i2; else i2 = -1;
+        }
+    }
+    m12[i1] = i2;
+    assign[i1] = as;
+}
+}  // namespace
+
+int plf_launch_bow_pairs(plf_ctx* c, int slot, const uint8_t* dKfDesc, const int4* dJobs, int nJobs, const int* dOrder, int* dPool) {
+    if (nJobs <= 0) return 0;
+    const uint8_t* desc = c->d_desc + (size_t)(slot * 2) * c->g.kpCap * 32;
+    bow_pairs_kernel<<<(nJobs + 7) / 8, 256, 0, c->stream>>>(dKfDesc, dJobs, nJobs, dOrder, desc, dPool);
+    return 1;
+}
+
+int plf_launch_line_gates(plf_ctx* c, int mode, const plf_track_line* dL1, int n1, const plf_keyline* dK2, const float2* dDisp2,
+                          const uint8_t* dHeld2, int n2, float minX, float maxX, float minY, float maxY, int* dM12, const int* dM21,
+                          int* dAssign) {
+    (void)n2;
+    if (n1 <= 0) return 0;
+    const double deltaW = (double)(maxX - minX) * 0.1, deltaH = (double)(maxY - minY) * 0.1;     // float difference times the double 0.1
+    line_gates_kernel<<<(n1 + 127) / 128, 128, 0, c->stream>>>(mode, dL1, n1, dK2, dDisp2, dHeld2, deltaW, deltaH, dM12, dM21, dAssign);
     return 1;
 }

@@ -123,7 +123,8 @@ struct plf_ctx {
     uint32_t* d_owner = nullptr;     // small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][Hs][Ps] owner tags of the current wave (PLF_FREE = none)
     int* d_regMW = nullptr;          // small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][8][Hs*Ws] region lists, one per wave slot
     int* d_stream = nullptr;         // streaming grower: [nImg][StreamLayout.total] owner map, list chunks, ticket table, region table (lazy)
-    int* d_nReg = nullptr;           // [nImg] regions committed by the streaming grower
+    int4* d_laneRT = nullptr;        // lane-per-image grower: [nImg][segCap] region table {arena offset, size, angle bits, -} (lazy)
+    int* d_nReg = nullptr;           // [nImg] regions entered in the table by the streaming / lane-per-image grower
     float* d_segs = nullptr;         // [nImg][segCap][4]
     int* d_nSegs = nullptr;          // [nImg]
     plf_keyline* d_kl = nullptr;     // [nImg][klCap]
@@ -159,6 +160,8 @@ struct plf_ctx {
     int* d_projStart = nullptr;
     int2* d_projPool = nullptr;
     size_t projQCap = 0, projPoolCap = 0;
+    uint8_t* d_scr = nullptr;        // grow-only scratch of the per-frame searches (plf_search_by_bow, plf_match_lines_tracked)
+    size_t scrCap = 0;
     float* d_bpPose = nullptr;       // [max_batch][12] Rwc, Ow of plf_backproject
     float* d_bpX = nullptr;          // [max_batch][kpCap][3]
     double* d_bpL = nullptr;         // [max_batch][klCap][6]
@@ -198,6 +201,10 @@ int plf_launch_unpack(plf_ctx* c, const uint8_t* stage, size_t sideBytes, int st
 int plf_launch_proj_candidates(plf_ctx* c, int slot, const PlfWinQ* dQ, int nq, const int* dCellStart,
                                const int* dCellIdx, int* dCount, const int* dSegStart, int2* dPool, bool fill);
 int plf_launch_bow(plf_ctx* c, int which, int slotFirst, int nSlots, int levelsup, int* dWord, double* dWeight, int* dNode, int rows);
+int plf_launch_bow_pairs(plf_ctx* c, int slot, const uint8_t* dKfDesc, const int4* dJobs, int nJobs, const int* dOrder, int* dPool);
+int plf_launch_line_gates(plf_ctx* c, int mode, const plf_track_line* dL1, int n1, const plf_keyline* dK2, const float2* dDisp2,
+                          const uint8_t* dHeld2, int n2, float minX, float maxX, float minY, float maxY, int* dM12, const int* dM21,
+                          int* dAssign);
 int plf_launch_backproject(plf_ctx* c, int slotFirst, int nSlots, const float* dRwc, const float* dOw, float fy, float cx,
                            float cy, float* dX3d, int x3dRows, double* dL3d, int l3dRows);
 int plf_launch_feature_grid(plf_ctx* c, int slotFirst, int nSlots, int* cellStart, int* cellIdx);

@@ -202,7 +202,8 @@ private:
 
 // The frame-level pieces after the stereo matchers: Frame::AssignFeaturesToGrid / GetFeaturesInArea
 // (src/Frame.cc:451-482, 774-843), Frame::UnprojectStereo / backProjection (:1332-1358), Frame::ComputeBoW (:858-870) and the
-// two ORBmatcher::SearchByProjection overloads of the tracking thread (src/ORBmatcher.cc:44-130, 2179-2323).
+// ORBmatcher searches of the tracking / relocalisation / loop-closing threads (src/ORBmatcher.cc:44-130, 2179-2323, 2325-2447,
+// 473-704, SearchByBoW 269-471) and the gated line matching of the tracking thread (src/Tracking.cc:3055-3099, 3879-3917).
 class FrameTail {
 public:
     explicit FrameTail(std::shared_ptr<plf::Context> ctx, int slot = 0) : ctx_(ctx), slot_(slot) {}
@@ -261,6 +262,59 @@ public:
                                                   mbCheckOrientation ? 1 : 0, occupied.data(), (int)occupied.size(), featQuery.data(),
                                                   match12.data(), &n),
                    "plf_search_by_projection_frame");
+        return n;
+    }
+    // int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist)
+    // (relocalisation, src/ORBmatcher.cc:2325-2447), projection done by the caller
+    int SearchByProjectionReloc(const std::vector<plf_frame_query>& keyFramePoints, int ORBdist, bool mbCheckOrientation,
+                                std::vector<uint8_t>& occupied, std::vector<int32_t>& featQuery) {
+        featQuery.assign(occupied.size(), -1);
+        int n = 0;
+        plf::check(plf_search_by_projection_reloc(ctx_->get(), slot_, keyFramePoints.data(), (int)keyFramePoints.size(), ORBdist,
+                                                  mbCheckOrientation ? 1 : 0, occupied.data(), (int)occupied.size(), featQuery.data(), &n),
+                   "plf_search_by_projection_reloc");
+        return n;
+    }
+    // int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, vpPoints, vpMatched, th, ratioHamming) and its vpMatchedKF
+    // variant (loop closing, src/ORBmatcher.cc:473-704); the slot plays pKF
+    int SearchByProjectionLoop(const std::vector<plf_frame_query>& candidatePoints, float ratioHamming, std::vector<uint8_t>& vpMatchedSet,
+                               std::vector<int32_t>& featQuery, int TH_LOW = 50) {
+        featQuery.assign(vpMatchedSet.size(), -1);
+        int n = 0;
+        plf::check(plf_search_by_projection_loop(ctx_->get(), slot_, candidatePoints.data(), (int)candidatePoints.size(), TH_LOW,
+                                                 ratioHamming, vpMatchedSet.data(), (int)vpMatchedSet.size(), featQuery.data(), &n),
+                   "plf_search_by_projection_loop");
+        return n;
+    }
+    // int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (src/ORBmatcher.cc:269-471):
+    // vpMapPointMatches[f] = index of the keyframe feature whose map point frame feature f received, or -1
+    int SearchByBoW(const plf::Mat8& kfDescriptors, const std::vector<float>& kfAngles, const std::vector<int32_t>& kfNodes,
+                    const std::vector<uint8_t>& kfHasGoodMapPoint, const std::vector<int32_t>& frameNodes, float mfNNratio,
+                    bool mbCheckOrientation, std::vector<int32_t>& vpMapPointMatches, int TH_LOW = 50) {
+        vpMapPointMatches.assign(frameNodes.size(), -1);
+        int n = 0;
+        plf::check(plf_search_by_bow(ctx_->get(), slot_, kfDescriptors.data, kfAngles.data(), kfNodes.data(), kfHasGoodMapPoint.data(),
+                                     kfDescriptors.rows, frameNodes.data(), (int)frameNodes.size(), TH_LOW, mfNNratio,
+                                     mbCheckOrientation ? 1 : 0, vpMapPointMatches.data(), &n),
+                   "plf_search_by_bow");
+        return n;
+    }
+    // match(mLastFrame.mDescriptors_Line, mCurrentFrame.mDescriptors_Line, minRatio12L, matches_12) + the gates of
+    // Tracking::TrackWithMotionModel (src/Tracking.cc:3055-3099; mode 0) / match(mvpLocalMapLines_InFrustum, mCurrentFrame, ...) +
+    // the gates of Tracking::SearchLocalLines (:3879-3917; mode 1).  Returns the number of map lines attached.
+    int MatchLinesTracked(int mode, const plf::Mat8& desc1, const std::vector<plf_track_line>& lines1, const plf::Mat8& desc2,
+                          const std::vector<KeyLine>& mvKeysUn_Line, const std::vector<std::pair<float, float>>& mvDisparity_l,
+                          const std::vector<uint8_t>* held2, float nnr, float mnMinX, float mnMaxX, float mnMinY, float mnMaxY,
+                          std::vector<int>& matches_12, std::vector<int>& assign_12) {
+        matches_12.assign(lines1.size(), -1);
+        assign_12.assign(lines1.size(), -1);
+        int n = 0;
+        static_assert(sizeof(std::pair<float, float>) == 8, "mvDisparity_l is passed as float pairs");
+        plf::check(plf_match_lines_tracked(ctx_->get(), mode, desc1.data, lines1.data(), (int)lines1.size(), desc2.data, mvKeysUn_Line.data(),
+                                           reinterpret_cast<const float*>(mvDisparity_l.data()), held2 ? held2->data() : nullptr,
+                                           (int)mvKeysUn_Line.size(), nnr, mnMinX, mnMaxX, mnMinY, mnMaxY, matches_12.data(),
+                                           assign_12.data(), &n),
+                   "plf_match_lines_tracked");
         return n;
     }
 private:

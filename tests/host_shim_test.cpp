@@ -58,6 +58,24 @@ int main(int argc, char** argv) {
         double sumX = 0, sumL = 0;
         for (float v : x3D) sumX += v;
         for (double v : lines3D) sumL += v;
+        // --- the gated line matching of the tracking thread (FrameTail::MatchLinesTracked): the frame against a copy of itself
+        // shifted by 4 px, every line eligible -> a line is attached iff it has stereo disparities and is its own mutual best
+        std::vector<plf_track_line> last(mvKeys_Line.size());
+        for (size_t i = 0; i < last.size(); ++i)
+            last[i] = {mvKeys_Line[i].startPointX + 4.f, mvKeys_Line[i].startPointY, mvKeys_Line[i].endPointX + 4.f,
+                       mvKeys_Line[i].endPointY, mvKeys_Line[i].angle, 1};
+        std::vector<int> m12t, a12t;
+        const int tracked = tail.MatchLinesTracked(0, mDescriptors_Line.view(), last, mDescriptors_Line.view(), mvKeys_Line, mvDisparity_l,
+                                                   nullptr, 0.9f, 0.f, (float)W, 0.f, (float)H, m12t, a12t);
+        // --- SearchByBoW of the frame against itself with every feature in one of 8 nodes: each feature finds itself
+        std::vector<float> ang(mvKeys.size());
+        std::vector<int32_t> nodes(mvKeys.size());
+        std::vector<uint8_t> good(mvKeys.size(), 1);
+        for (size_t i = 0; i < mvKeys.size(); ++i) { ang[i] = mvKeys[i].angle; nodes[i] = (int32_t)(i % 8); }
+        std::vector<int32_t> bowMatches;
+        const int nBow = tail.SearchByBoW(mDescriptors.view(), ang, nodes, good, nodes, 0.7f, true, bowMatches);
+        int bowSelf = 0;
+        for (size_t i = 0; i < bowMatches.size(); ++i) bowSelf += bowMatches[i] == (int32_t)i;
         // --- lapping area {0, 1000} (the monocular constructor, src/Frame.cc:360-361) and a padded-row view of the same image
         std::vector<ORB_SLAM3::KeyPoint> kLap, kPad;
         plf::Desc dLap, dPad;
@@ -85,10 +103,10 @@ int main(int argc, char** argv) {
         printf("{\"N\": %zu, \"Nr\": %zu, \"mono\": [%d, %d], \"Nl\": %zu, \"Nlr\": %zu, \"stereo_pts\": %d, \"sum_u\": %.4f, "
                "\"stereo_lines\": %d, \"nnr\": %d, \"desc_fnv\": %llu, \"hamming01\": %d, \"area_n\": %zu, \"area_fnv\": %llu, "
                "\"sum_x3d\": %.6f, \"sum_l3d\": %.9f, \"mono_lap\": %d, \"lap_reversed\": %d, \"pad_same\": %d, \"rect_fnv\": %llu, "
-               "\"empty\": %d}\n",
+               "\"tracked\": %d, \"bow\": [%d, %d], \"empty\": %d}\n",
                mvKeys.size(), mvKeysRight.size(), monoLeft, monoRight, mvKeys_Line.size(), mvKeysRight_Line.size(), stereoPts,
                sumU, stereoLines, nnr, h, ORB_SLAM3::ORBmatcher::DescriptorDistance(mDescriptors.row(0), mDescriptors.row(1)),
-               area.size(), hArea, sumX, sumL, monoLap, lapReversed, padSame, hRect,
+               area.size(), hArea, sumX, sumL, monoLap, lapReversed, padSame, hRect, tracked, nBow, bowSelf,
                orbL(none, none, mvKeys, mDescriptors, lap));
     } catch (const std::exception& e) {
         fprintf(stderr, "error: %s\n", e.what());

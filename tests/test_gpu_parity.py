@@ -557,6 +557,67 @@ def test_search_by_projection_frame_matches_oracle(plf, product, oracle, mode, c
         assert no > 400
 
 
+def test_keyframe_searches_match_oracle(plf, product, oracle):
+    """The remaining SearchByProjection overloads (relocalisation src/ORBmatcher.cc:2325-2447, loop closing :473-704) and
+    SearchByBoW (:269-471) through the C ABI against the oracle: assignment tables, nmatches and occupancy identical."""
+    from test_host_logic import _frame_queries, _bow_case
+    L, R = plf.synth_batch(752, 480, [93, 94])
+    f, o = plf.Frontend(product, max_batch=2), plf.Frontend(oracle, max_batch=2)
+    rg, ro = f.frontend_batch(L, R), o.frontend_batch(L, R)
+    for b in (1, 0):
+        n = int(ro.n_kp_left[b])
+        assert np.array_equal(rg.kp_left[b, :n], ro.kp_left[b, :n])
+        rng = np.random.default_rng(50 + b)
+        q = _frame_queries(plf, ro, b, rng, "around")
+        occ0 = (rng.random(n) < 0.1).astype(np.uint8)
+        for check in (True, False):
+            og, oo = occ0.copy(), occ0.copy()
+            fg, ng = f.search_by_projection_reloc(q, og, 64, check, slot=b)
+            fo, no = o.search_by_projection_reloc(q, oo, 64, check, slot=b)
+            assert ng == no and np.array_equal(fg, fo) and np.array_equal(og, oo) and no > 300
+        q2 = _frame_queries(plf, ro, b, rng, "backward")
+        q2["min_level"] = q2["max_level"] - 1
+        for ratio in (1.0, 0.64):
+            og, oo = occ0.copy(), occ0.copy()
+            fg, ng = f.search_by_projection_loop(q2, og, 50, ratio, slot=b)
+            fo, no = o.search_by_projection_loop(q2, oo, 50, ratio, slot=b)
+            assert ng == no and np.array_equal(fg, fo) and np.array_equal(og, oo) and no > 150
+        case = _bow_case(plf, ro, rng)
+        for check, ratio in ((True, 0.7), (False, 0.9)):
+            mg, ng = f.search_by_bow(*case, 50, ratio, check, slot=b)
+            mo, no = o.search_by_bow(*case, 50, ratio, check, slot=b)
+            assert ng == no and np.array_equal(mg, mo) and no > 200
+        e, en = f.search_by_bow(case[0][:0], case[1][:0], case[2][:0], case[3][:0], case[4], slot=b)
+        assert en == 0 and np.all(e == -1)
+    with pytest.raises(plf.PlfError):
+        f.search_by_bow(*case[:4], case[4][:10], slot=0)                 # f_node[] shorter than Frame::N
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_match_lines_tracked_matches_oracle(plf, product, oracle, mode):
+    """match() + the tracking thread's orientation / position gates (src/Tracking.cc:3055-3099, :3879-3917), fused on the
+    device, against the oracle: matches_12, the assignment list and the inlier count identical."""
+    from test_host_logic import _track_lines_case
+    L, R = plf.synth_batch(752, 480, [95, 96])
+    f, o = plf.Frontend(product, max_batch=2, lsd_nfeatures=0), plf.Frontend(oracle, max_batch=2, lsd_nfeatures=0)
+    ro = o.frontend_batch(L, R)
+    f.frontend_batch(L, R)
+    for b in (0, 1):
+        sub = type("R", (), {})()
+        sub.n_kl_left = ro.n_kl_left[b:b + 1]; sub.kl_left = ro.kl_left[b:b + 1]; sub.ldesc_left = ro.ldesc_left[b:b + 1]
+        sub.disp_se = ro.disp_se[b:b + 1]
+        case = _track_lines_case(plf, sub, np.random.default_rng(60 + b + 2 * mode), mode)
+        for bounds in ((0.0, 752.0, 0.0, 480.0), (0.0, 300.0, 0.0, 200.0)):
+            mg, ag, ng = f.match_lines_tracked(mode, *case, 0.9, bounds)
+            mo, ao, no = o.match_lines_tracked(mode, *case, 0.9, bounds)
+            assert ng == no and np.array_equal(mg, mo) and np.array_equal(ag, ao)
+        assert no > 20
+    mg, ag, ng = f.match_lines_tracked(mode, case[0][:0], case[1][:0], case[2], case[3], case[4], case[5], 0.9, bounds)
+    assert ng == 0 and len(mg) == 0
+    mg, ag, ng = f.match_lines_tracked(mode, case[0], case[1], case[2][:1], case[3][:1], case[4][:1], None, 0.9, bounds)
+    assert ng == 0 and np.all(mg == -1)                                   # fewer than two train rows: no matches (declared rule)
+
+
 def test_large_batch_sequential_grower_matches_oracle(plf, product, oracle):
     """Launches of more than 128 images use the one-warp-per-image region grower (the kernel the benchmark runs); smaller
     ones use the multi-region grower.  72 pairs (144 images, 8 distinct pairs repeated) against the oracle, exactly, and

@@ -409,7 +409,7 @@ def _frame_queries(plf, res, b, rng, mode="around"):
     return q[rng.permutation(m)]
 
 
-def _search_frame_python(q, kps, desc, ur, occupied, th_high, check, W=752, H=480):
+def _search_frame_python(q, kps, desc, ur, occupied, th_high, check, W=752, H=480, stereo=True, holder_by_obs=True):
     """src/ORBmatcher.cc:2229-2317 restated loop for loop, incl. ComputeThreeMaxima (:2449-2490)."""
     import math
     f32 = np.float32
@@ -450,14 +450,14 @@ def _search_frame_python(q, kps, desc, ur, occupied, th_high, check, W=752, H=48
                         continue
                     if occupied[idx]:
                         continue
-                    if ur[idx] > 0 and abs(f32(qq["ur"]) - f32(ur[idx])) > rad:
+                    if stereo and ur[idx] > 0 and abs(f32(qq["ur"]) - f32(ur[idx])) > rad:
                         continue
                     dist = int((bits[idx] ^ qb).sum())
                     if dist < best:
                         best, bidx = dist, idx
         if bidx >= 0 and best <= th_high:
             fq[bidx] = i
-            occupied[bidx] = 1 if qq["has_observations"] else 0
+            occupied[bidx] = 1 if (qq["has_observations"] or not holder_by_obs) else 0
             nm += 1
             if m12[bidx] < 0:
                 m12[bidx] = i
@@ -509,6 +509,222 @@ def test_search_by_projection_frame_oracle_against_python(plf, oracle, mode, che
     assert nm > 150
     if check:
         assert (fq >= 0).sum() < 600 - 30          # the histogram removed the matches with the odd rotations
+
+
+@pytest.mark.parametrize("check", [True, False])
+def test_search_by_projection_reloc_oracle_against_python(plf, oracle, check):
+    """The relocalisation overload (src/ORBmatcher.cc:2325-2447): no stereo check, any holder blocks a feature."""
+    L, R = plf.synth_pair(752, 480, 9)
+    o = plf.Frontend(oracle, max_batch=1)
+    res = o.frontend_batch(L[None], R[None])
+    n = int(res.n_kp_left[0])
+    rng = np.random.default_rng(21)
+    q = _frame_queries(plf, res, 0, rng, "around")[:700]
+    q["has_observations"] = 0                      # must not matter for this overload
+    occ0 = (rng.random(n) < 0.1).astype(np.uint8)
+    oa, ob = occ0.copy(), occ0.copy()
+    fq, nm = o.search_by_projection_reloc(q, oa, 64, check)
+    wfq, _, wnm = _search_frame_python(q, res.kp_left[0, :n], res.desc_left[0, :n], res.u_right[0, :n], ob, 64, check,
+                                       stereo=False, holder_by_obs=False)
+    assert nm == wnm and np.array_equal(fq, wfq) and np.array_equal(oa, ob)
+    assert nm > 150 and not np.any((fq >= 0) & (occ0 != 0))
+
+
+@pytest.mark.parametrize("ratio", [1.0, 0.64])
+def test_search_by_projection_loop_oracle_against_python(plf, oracle, ratio):
+    """The loop-closing overloads (src/ORBmatcher.cc:473-704): levels [pred - 1, pred], float threshold TH_LOW * ratio."""
+    L, R = plf.synth_pair(752, 480, 10)
+    o = plf.Frontend(oracle, max_batch=1)
+    res = o.frontend_batch(L[None], R[None])
+    n = int(res.n_kp_left[0])
+    rng = np.random.default_rng(22)
+    q = _frame_queries(plf, res, 0, rng, "backward")[:700]
+    q["min_level"] = q["max_level"] - 1
+    occ0 = (rng.random(n) < 0.1).astype(np.uint8)
+    oa, ob = occ0.copy(), occ0.copy()
+    fq, nm = o.search_by_projection_loop(q, oa, 50, ratio)
+    wfq, _, wnm = _search_frame_python(q, res.kp_left[0, :n], res.desc_left[0, :n], res.u_right[0, :n], ob,
+                                       np.float32(50) * np.float32(ratio), False, stereo=False, holder_by_obs=False)
+    assert nm == wnm and np.array_equal(fq, wfq) and np.array_equal(oa, ob)
+    assert nm > 100
+
+
+def _bow_case(plf, res, rng, n_nodes=60):
+    """A keyframe made of the frame's own features (noisy descriptors, rotated angles) plus strangers, with DBoW2-like
+    node ids on both sides (some features in no node: stopped words)."""
+    n = int(res.n_kp_left[0])
+    kps, desc = res.kp_left[0, :n], res.desc_left[0, :n]
+    m = 900
+    src = rng.integers(0, n, m)
+    kf_desc = desc[src].copy()
+    kf_desc ^= np.packbits(rng.random((m, 256)) < 0.04, axis=1)
+    kf_desc[-100:] = rng.integers(0, 256, (100, 32), dtype=np.uint8)
+    f_node = rng.integers(0, n_nodes, n).astype(np.int32) * 7 + 100
+    kf_node = f_node[src].copy()
+    kf_node[rng.random(m) < 0.1] = rng.integers(0, n_nodes, int((rng.random(m) < 0.1).sum()) or 1)[0] * 7 + 100
+    f_node[rng.random(n) < 0.05] = -1
+    kf_node[rng.random(m) < 0.05] = -1
+    rot = rng.choice(np.array([4.0, 9.0, 150.0], np.float32), m, p=[0.6, 0.3, 0.1])
+    kf_angle = np.mod(kps["angle"][src] + rot + rng.normal(0, 1.0, m), 360).astype(np.float32)
+    kf_valid = (rng.random(m) < 0.85).astype(np.uint8)
+    return kf_desc, kf_angle, kf_node.astype(np.int32), kf_valid, f_node
+
+
+def _search_bow_python(kf_desc, kf_angle, kf_node, kf_valid, f_node, kps, desc, th_low, nn_ratio, check):
+    """src/ORBmatcher.cc:269-471 (F.Nleft == -1) restated: merge join of the two FeatureVectors, best / second best,
+    TH_LOW and mfNNratio, rotation histogram."""
+    import math
+    f32 = np.float32
+
+    def rnd(v):
+        return int(math.floor(abs(v) + 0.5)) * (1 if v >= 0 else -1)
+    fv_kf, fv_f = {}, {}
+    for i, nd in enumerate(kf_node):
+        if nd >= 0:
+            fv_kf.setdefault(int(nd), []).append(i)
+    for i, nd in enumerate(f_node[:len(kps)]):
+        if nd >= 0:
+            fv_f.setdefault(int(nd), []).append(i)
+    bits_f = np.unpackbits(desc, axis=1)
+    bits_kf = np.unpackbits(kf_desc, axis=1)
+    match = np.full(len(f_node), -1, np.int32)
+    hist = [[] for _ in range(30)]
+    factor = f32(1.0) / f32(30)
+    nm = 0
+    for nd in sorted(set(fv_kf) & set(fv_f)):
+        for ikf in fv_kf[nd]:
+            if not kf_valid[ikf]:
+                continue
+            b1, b2, bidx = 256, 256, -1
+            for f in fv_f[nd]:
+                if match[f] >= 0:
+                    continue
+                d = int((bits_kf[ikf] ^ bits_f[f]).sum())
+                if d < b1:
+                    b2, b1, bidx = b1, d, f
+                elif d < b2:
+                    b2 = d
+            if b1 <= th_low and f32(b1) < f32(nn_ratio) * f32(b2):
+                match[bidx] = ikf
+                nm += 1
+                if check:
+                    rot = f32(f32(kf_angle[ikf]) - f32(kps["angle"][bidx]))
+                    if rot < 0:
+                        rot = f32(rot + f32(360))
+                    b = rnd(float(f32(rot * factor)))
+                    if b == 30:
+                        b = 0
+                    hist[b].append(bidx)
+    if check:
+        i1 = i2 = i3 = -1
+        m1 = m2 = m3 = 0
+        for i in range(30):
+            s = len(hist[i])
+            if s > m1:
+                m3, m2, m1, i3, i2, i1 = m2, m1, s, i2, i1, i
+            elif s > m2:
+                m3, m2, i3, i2 = m2, s, i2, i
+            elif s > m3:
+                m3, i3 = s, i
+        if m2 < f32(0.1) * f32(m1):
+            i2 = i3 = -1
+        elif m3 < f32(0.1) * f32(m1):
+            i3 = -1
+        for i in range(30):
+            if i not in (i1, i2, i3):
+                for f in hist[i]:
+                    match[f] = -1; nm -= 1
+    return match, nm
+
+
+@pytest.mark.parametrize("check,ratio", [(True, 0.7), (False, 0.9)])
+def test_search_by_bow_oracle_against_python(plf, oracle, check, ratio):
+    L, R = plf.synth_pair(752, 480, 11)
+    o = plf.Frontend(oracle, max_batch=1)
+    res = o.frontend_batch(L[None], R[None])
+    n = int(res.n_kp_left[0])
+    kf_desc, kf_angle, kf_node, kf_valid, f_node = _bow_case(plf, res, np.random.default_rng(31))
+    m, nm = o.search_by_bow(kf_desc, kf_angle, kf_node, kf_valid, f_node, 50, ratio, check)
+    wm, wnm = _search_bow_python(kf_desc, kf_angle, kf_node, kf_valid, f_node, res.kp_left[0, :n], res.desc_left[0, :n], 50, ratio, check)
+    assert nm == wnm and np.array_equal(m, wm)
+    assert nm > 200
+    e, enm = o.search_by_bow(kf_desc[:0], kf_angle[:0], kf_node[:0], kf_valid[:0], f_node)
+    assert enm == 0 and np.all(e == -1)
+
+
+def _track_lines_case(plf, res, rng, mode):
+    """Current frame = the slot's left lines; first set = the same lines moved / rotated a little (some a lot), plus
+    strangers; some without map line, some current lines without stereo or already held."""
+    nl = int(res.n_kl_left[0])
+    kl2 = res.kl_left[0, :nl].copy()
+    desc2 = res.ldesc_left[0, :nl].copy()
+    disp2 = res.disp_se[0, :nl].copy()
+    m = nl + 40
+    src = np.concatenate([rng.permutation(nl), rng.integers(0, nl, 40)])
+    lines1 = np.zeros(m, plf.TRACK_LINE_DT)
+    big = rng.random(m) < 0.15
+    shift = np.where(big[:, None], rng.normal(0, 60.0, (m, 4)), rng.normal(0, 6.0, (m, 4))).astype(np.float32)
+    lines1["sx"] = kl2["startPointX"][src] + shift[:, 0]; lines1["sy"] = kl2["startPointY"][src] + shift[:, 1]
+    lines1["ex"] = kl2["endPointX"][src] + shift[:, 2]; lines1["ey"] = kl2["endPointY"][src] + shift[:, 3]
+    dang = np.where(rng.random(m) < 0.15, rng.uniform(-3.2, 3.2, m), rng.normal(0, 0.1, m))
+    lines1["angle"] = (kl2["angle"][src] + dang).astype(np.float32)
+    lines1["eligible"] = 1 if mode == 1 else (rng.random(m) < 0.85).astype(np.int32)
+    desc1 = desc2[src].copy()
+    desc1 ^= np.packbits(rng.random((m, 256)) < 0.03, axis=1)
+    desc1[-40:] = rng.integers(0, 256, (40, 32), dtype=np.uint8)
+    held2 = (rng.random(nl) < 0.1).astype(np.uint8) if mode == 1 else None
+    return desc1, lines1, desc2, kl2, disp2, held2
+
+
+def _match_lines_tracked_python(oracle_front, mode, desc1, lines1, desc2, kl2, disp2, held2, nnr, bounds):
+    """src/Tracking.cc:3055-3099 / :3879-3917 restated on top of match() (itself tested above)."""
+    import math
+    f32 = np.float32
+    _, m12 = oracle_front.match(desc1, desc2, nnr, True)
+    m12 = m12.copy()
+    asg = np.full(len(desc1), -1, np.int32)
+    dw = float(f32(bounds[1]) - f32(bounds[0])) * 0.1
+    dh = float(f32(bounds[3]) - f32(bounds[2])) * 0.1
+    for i1 in range(len(desc1)):
+        if not lines1["eligible"][i1]:
+            continue
+        i2 = int(m12[i1])
+        if i2 < 0:
+            continue
+        if disp2[i2, 0] < 0 or disp2[i2, 1] < 0:
+            continue
+        if mode == 1 and held2 is not None and held2[i2]:
+            continue
+        if mode == 0:
+            th = float(f32(kl2["angle"][i2]) - f32(lines1["angle"][i1]))
+            if th < -math.pi:
+                th += 2 * math.pi
+            elif th > math.pi:
+                th -= 2 * math.pi
+            if abs(th) > math.pi / 8.0:
+                m12[i1] = -1
+                continue
+        if (abs(float(f32(kl2["startPointX"][i2]) - f32(lines1["sx"][i1]))) > dw or abs(float(f32(kl2["endPointX"][i2]) - f32(lines1["ex"][i1]))) > dw or
+                abs(float(f32(kl2["startPointY"][i2]) - f32(lines1["sy"][i1]))) > dh or abs(float(f32(kl2["endPointY"][i2]) - f32(lines1["ey"][i1]))) > dh):
+            m12[i1] = -1
+            continue
+        asg[i1] = i2
+    return m12, asg, int((asg >= 0).sum())
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_match_lines_tracked_oracle_against_python(plf, oracle, mode):
+    L, R = plf.synth_pair(752, 480, 12)
+    o = plf.Frontend(oracle, max_batch=1)
+    res = o.frontend_batch(L[None], R[None])
+    case = _track_lines_case(plf, res, np.random.default_rng(41 + mode), mode)
+    bounds = (0.0, 752.0, 0.0, 480.0)
+    m12, asg, na = o.match_lines_tracked(mode, *case, 0.9, bounds)
+    wm, wa, wna = _match_lines_tracked_python(o, mode, *case, 0.9, bounds)
+    assert na == wna and np.array_equal(m12, wm) and np.array_equal(asg, wa)
+    assert na > 40 and (m12 >= 0).sum() > na            # some matches pass without an assignment (no stereo / not eligible / held)
+    nm0, plain = o.match(case[0], case[2], 0.9, True)
+    assert (plain >= 0).sum() > (m12 >= 0).sum()        # and the gates removed some
 
 
 def test_header_inlines_edge_cases(plf, oracle):

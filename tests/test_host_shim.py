@@ -79,3 +79,13 @@ def test_shim_matches_oracle(tmp_path, plf, oracle, pair1):
     # Rectifier
     o.rectify_set_maps(0, mx, my)
     assert got["rect_fnv"] == fnv(o.rectify(0, L).tobytes())
+    # gated line matching and SearchByBoW through the shim, against the oracle's entry points
+    lines1 = np.zeros(len(kl), plf.TRACK_LINE_DT)
+    lines1["sx"] = kl["startPointX"] + np.float32(4); lines1["sy"] = kl["startPointY"]
+    lines1["ex"] = kl["endPointX"] + np.float32(4); lines1["ey"] = kl["endPointY"]
+    lines1["angle"] = kl["angle"]; lines1["eligible"] = 1
+    _, _, na = o.match_lines_tracked(0, ld, lines1, ld, kl, disp, None, 0.9, (0.0, 752.0, 0.0, 480.0))
+    assert got["tracked"] == na > 20
+    nodes = (np.arange(len(k)) % 8).astype(np.int32)
+    m, nb = o.search_by_bow(d, k["angle"], nodes, np.ones(len(k), np.uint8), nodes, 50, 0.7, True)
+    assert got["bow"] == [nb, int((m == np.arange(len(k))).sum())] and nb > 500

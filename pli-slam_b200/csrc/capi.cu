@@ -324,6 +324,8 @@ static int create_buffers(plf_ctx* c, const plf_params* p, std::vector<PlfCell>&
         PLF_CUDA_OK(dalloc(&c->d_lsdU, nImg * (size_t)g.Ps * g.Hs));
         PLF_CUDA_OK(dalloc(&c->d_rec, nImg * npx));
         PLF_CUDA_OK(dalloc(&c->d_n2max, nImg));
+        c->d_gradLut = plf_grad_lut(c);
+        if (!c->d_gradLut) return fail(PLF_ERR_CUDA, "cannot allocate the LSD gradient record table");
         PLF_CUDA_OK(dalloc(&c->d_seeds, nImg * (size_t)g.seedCap + 8));      // + 8: the lane-per-image grower reads whole 16-byte groups
         PLF_CUDA_OK(dalloc(&c->d_nSeeds, nImg));
         PLF_CUDA_OK(dalloc(&c->d_n2, nImg * (size_t)g.Ps * g.Hs));

@@ -57,14 +57,31 @@ __global__ void __launch_bounds__(256) lsd_upscale_kernel(PlfGeom g, const uint8
 // ---------------------------------------------------------------------------------------------------------------
 // K4b  level-line field (LSD ll_angle): 2x2 gradient, squared norm, fastAtan2 angle (degrees), cosf/sinf of the angle,
 // per-image max of the squared norm over defined pixels.
-__global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, float4* rec, int* n2map, uint32_t* used,
-                                                       int* n2max, int imgFirst) {
+// The record of a defined pixel — angle, cosf, sinf, |g|^2 — is a pure function of the integer gradient (gx, gy), each in
+// [-510, 510]: one table per device (1021^2 x 16 B = 16.7 MB, L2-resident; typical gradients touch a few hundred KB of
+// it), filled once by the very expression the per-pixel code used, so the records are unchanged bit for bit.
+#define LSD_LUT_R 510
+#define LSD_LUT_W (2 * LSD_LUT_R + 1)
+__global__ void __launch_bounds__(256) lsd_lut_kernel(float4* lut) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= LSD_LUT_W * LSD_LUT_W) return;
+    const int gy = i / LSD_LUT_W - LSD_LUT_R, gx = i % LSD_LUT_W - LSD_LUT_R;
+    const float a = fast_atan2_deg((float)gx, (float)-gy);
+    const float af = (float)((double)a * kDegToRad);
+    // cosf/sinf taken as correctly rounded (double result rounded to float), the declared oracle rule
+    double sn, cs;
+    sincos((double)af, &sn, &cs);
+    lut[i] = make_float4(a, (float)cs, (float)sn, __int_as_float(gx * gx + gy * gy));
+}
+
+__global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, const float4* __restrict__ lut, float4* rec,
+                                                       int* n2map, uint32_t* used, int* n2max, int imgFirst) {
     // Two phases per 128x8 tile, 4 horizontally adjacent pixels per thread (aligned 32-bit loads of the u8 image, one
     // 16-byte store of the |g|^2 map per thread, one bitmap word per 8 threads):
     // (1) 2x2 gradient and |g|^2; a pixel is defined iff |g|^2 > n2Thresh, the integer image of LSD's "norm > rho" test
     //     (exact: host-searched with the same IEEE sqrt).  Undefined pixels get no record; defined ones are queued.
-    // (2) the queue is processed densely, one defined pixel per thread, so the expensive part (fastAtan2 + double
-    //     sincos) costs in proportion to the defined pixels, not to the warps that happen to contain one.
+    // (2) the queue is processed densely, one defined pixel per thread: the record is copied from the per-device table
+    //     of all (gx, gy) (see lsd_lut_kernel), so the fastAtan2 + double sincos of the first version is paid once per device.
     __shared__ int s_cnt;
     __shared__ int s_q[1024];          // (ty<<7 | column) | (gx+1024)<<10 | (gy+1024)<<21
     const int x = blockIdx.x * 128 + threadIdx.x * 4, y = blockIdx.y * 8 + threadIdx.y;
@@ -120,12 +137,7 @@ __global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t*
         const int e = s_q[i];
         const int col = e & 0x7F, row = (e >> 7) & 0x7, gx = ((e >> 10) & 0x7FF) - 1024, gy = ((e >> 21) & 0x7FF) - 1024;
         const int px = blockIdx.x * 128 + col, py = blockIdx.y * 8 + row;
-        const float a = fast_atan2_deg((float)gx, (float)-gy);
-        const float af = (float)((double)a * kDegToRad);
-        // cosf/sinf taken as correctly rounded (double result rounded to float), the declared oracle rule
-        double sn, cs;
-        sincos((double)af, &sn, &cs);
-        rec[base + (size_t)py * g.Ws + px] = make_float4(a, (float)cs, (float)sn, __int_as_float(gx * gx + gy * gy));
+        rec[base + (size_t)py * g.Ws + px] = lut[(gy + LSD_LUT_R) * LSD_LUT_W + gx + LSD_LUT_R];
     }
 }
 
@@ -1226,6 +1238,23 @@ static void upload_lbd_tables(int device) {
 
 // scratch of the small-batch grower, allocated the first time a small launch happens (a context that only ever runs large
 // batches never pays for it): owner map (all PLF_FREE) and one region list per wave slot, for up to PLF_MW_MAX_IMG images
+// per-device record table of lsd_grad_kernel (process lifetime, like the constant tables)
+static float4* s_gradLut[64] = {};
+const float4* plf_grad_lut(plf_ctx* c) {
+    static std::mutex m;
+    std::lock_guard<std::mutex> lock(m);
+    const int dev = c->device;
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (!s_gradLut[dev]) {
+        float4* p = nullptr;
+        if (cudaMalloc((void**)&p, (size_t)LSD_LUT_W * LSD_LUT_W * sizeof(float4)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        lsd_lut_kernel<<<(LSD_LUT_W * LSD_LUT_W + 255) / 256, 256, 0, c->stream>>>(p);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaFree(p); return nullptr; }
+        s_gradLut[dev] = p;
+    }
+    return s_gradLut[dev];
+}
+
 static int plf_ensure_stream_buffers(plf_ctx* c) {
     if (c->d_stream) return 0;
     const StreamLayout L = stream_layout(c->g.Ps, c->g.Ws, c->g.Hs, c->g.segCap);
@@ -1257,6 +1286,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     const PlfGeom& g = c->g;
     cudaStream_t s = c->stream;
     upload_lbd_tables(c->device);
+    const float4* lut = c->d_gradLut;               // per-device table, fetched by plf_create
     const uint8_t* in = c->d_pyr + g.lv[0].off;      // level 0 of the pyramid block is the input image
     const size_t inStride = (size_t)g.pyrBytes;
     const int ip = g.lv[0].pitch;
@@ -1279,7 +1309,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     lsd_upscale_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, c->d_lin + c->linLsdX, c->d_lin + c->linLsdY, imgFirst);
     plf_mark(c, "lsd_gradient");
     cudaMemsetAsync(c->d_n2max + imgFirst, 0, nImg * sizeof(int), s);
-    lsd_grad_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_rec, c->d_n2, c->d_used, c->d_n2max, imgFirst);
+    lsd_grad_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, lut, c->d_rec, c->d_n2, c->d_used, c->d_n2max, imgFirst);
     plf_mark(c, "lsd_order");
     {
         const size_t smem = (size_t)ORD_WARPS * g.nBins * sizeof(int);

@@ -121,13 +121,15 @@ __device__ __forceinline__ int fast_score_packed(const unsigned* N, unsigned cen
 // does not depend on the image content.  The packed test is polarity-blind (|centre - ring| > minTh on 9 contiguous
 // ring pixels): a superset of the corners that costs half the instructions of two polarity masks.  Candidates (a few
 // per cent of the pixels) are queued and resolved densely: polarity by majority (a 9-arc needs >= 9 of the 16), exact
-// score, and the score decides (>= minTh <=> FAST-9 corner at minTh).
+// score, and the score decides (>= minTh <=> FAST-9 corner at minTh).  In front of it, a four-point compass test
+// discards most quads with a quarter of the comparisons; only the survivors (queued, processed densely) run the 16-point test.
 
 __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_t* pyr, uint8_t* score,
                                                          const PlfTile* tiles, int imgFirst) {
     __shared__ __align__(16) unsigned s_w[FS_IH][FS_ROWW];
-    __shared__ int s_cnt;
-    __shared__ unsigned short s_queue[FS_TW * FS_TH];
+    __shared__ int s_cnt1, s_cnt2;
+    __shared__ unsigned short s_quads[256];                // phase-1 survivors: thread id | valid-pixel mask << 8
+    __shared__ unsigned short s_queue[FS_TW * FS_TH];      // phase-2 survivors: (row << 7) | column
     // tiles cover [19, w-19) x [19, h-19) of every level: the union of all cell detection areas
     const PlfTile t = tiles[blockIdx.x];
     const PlfLevel& lv = g.lv[t.level];
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
     uint8_t* dst = score + (size_t)img * g.pyrBytes + lv.off + 1;      // score(x,y) lives at byte x+1: word-aligned rows of 4
     const int x0 = t.x0, y0 = t.y0;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
-    if (tid == 0) s_cnt = 0;
+    if (tid == 0) { s_cnt1 = 0; s_cnt2 = 0; }
     // the window starts at x0-3 = 16 (mod 128) and level rows are 64-byte aligned: aligned 32-bit loads (the row pitch
     // is padded to 64 B and the pyramid allocation has slack, so the last words never leave the allocation)
     for (int i = tid; i < FS_IH * 34; i += 256) {
@@ -145,58 +147,78 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
         s_w[iy][wx] = *reinterpret_cast<const unsigned*>(row + wx * 4);
     }
     __syncthreads();
-    // neighbour bytes of my 4 pixels at circle offset (dx, dy): bytes [4tx+3+dx, +4) of staged row ty+3+dy
-    auto nb = [&](int dx, int dy) -> unsigned {
+    // neighbour bytes of the 4 pixels of quad (qx, qy) at circle offset (dx, dy): bytes [4qx+3+dx, +4) of staged row qy+3+dy
+    auto nb = [&](int qx, int qy, int dx, int dy) -> unsigned {
         const int b = 3 + dx;                      // 0..6, compile-time after unrolling
-        const unsigned* r = &s_w[ty + 3 + dy][tx + (b >> 2)];
+        const unsigned* r = &s_w[qy + 3 + dy][qx + (b >> 2)];
         return (b & 3) ? __funnelshift_r(r[0], r[1], (b & 3) * 8) : r[0];
     };
-    const unsigned C = nb(0, 0);
     const unsigned k7f = (unsigned)(0x7F - g.minTh) * 0x01010101u;
-    unsigned F[16];                                // bit 7 of byte j: |centre - neighbour k| of pixel j exceeds minTh
     const int cdx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
     const int cdy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
-#pragma unroll
-    for (int k = 0; k < 16; ++k) F[k] = fast_gt_const4(__vabsdiffu4(C, nb(cdx[k], cdy[k])), k7f);
-    // 9 contiguous flags: T3[k] = F[k]&F[k+1]&F[k+2]; run[k] = T3[k]&T3[k+3]&T3[k+6]; any = OR run[k]
-    unsigned any = 0;
+    // ---- phase 1, every thread: the four compass points.  Nine contiguous ring pixels always contain two compass points
+    // that are neighbours on the compass, so a pixel without such a pair (polarity-blind, like the full test below) cannot
+    // be a corner; most quads of a frame end here.
     {
-        unsigned T[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) T[k] = F[k] & F[(k + 1) & 15] & F[(k + 2) & 15];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) any |= T[k] & T[(k + 3) & 15] & T[(k + 6) & 15];
-    }
-    const int y = y0 + ty;
-    const bool rowIn = y < lv.h - PLF_EDGE;
-    unsigned corner = any & 0x80808080u;
-    // mask pixels right of the detection area
-    const int xr = lv.w - PLF_EDGE - (x0 + 4 * tx);        // number of valid pixels from my first one
-    if (!rowIn || xr <= 0) corner = 0;
-    else if (xr < 4) corner &= (0xFFFFFFFFu >> (8 * (4 - xr)));
-    if (rowIn && xr > 0) {
-        // non-candidates score 0; candidate bytes are overwritten by the scoring pass below (same block, after the barrier)
-        unsigned* d4 = reinterpret_cast<unsigned*>(dst + (size_t)y * lv.pitch + x0 + 4 * tx);
-        if (xr >= 4) *d4 = 0u;
-        else for (int j = 0; j < xr; ++j) dst[(size_t)y * lv.pitch + x0 + 4 * tx + j] = 0;
-    }
-    {   // queue the candidates: one shared-memory atomic per warp (a warp is one row of the tile)
-        const int cnt = __popc(corner);
-        int inc = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (tx >= o) inc += t;
+        const unsigned C = nb(tx, ty, 0, 0);
+        const unsigned f0 = fast_gt_const4(__vabsdiffu4(C, nb(tx, ty, 0, 3)), k7f), f4 = fast_gt_const4(__vabsdiffu4(C, nb(tx, ty, 3, 0)), k7f);
+        const unsigned f8 = fast_gt_const4(__vabsdiffu4(C, nb(tx, ty, 0, -3)), k7f), f12 = fast_gt_const4(__vabsdiffu4(C, nb(tx, ty, -3, 0)), k7f);
+        unsigned quick = ((f0 | f8) & (f4 | f12)) & 0x80808080u;          // = (f0&f4)|(f4&f8)|(f8&f12)|(f12&f0)
+        const int y = y0 + ty;
+        const bool rowIn = y < lv.h - PLF_EDGE;
+        const int xr = lv.w - PLF_EDGE - (x0 + 4 * tx);        // number of valid pixels from my first one
+        if (!rowIn || xr <= 0) quick = 0;
+        else if (xr < 4) quick &= (0xFFFFFFFFu >> (8 * (4 - xr)));
+        if (rowIn && xr > 0) {
+            // everything scores 0 unless the scoring pass below (same block, after the barriers) says otherwise
+            unsigned* d4 = reinterpret_cast<unsigned*>(dst + (size_t)y * lv.pitch + x0 + 4 * tx);
+            if (xr >= 4) *d4 = 0u;
+            else for (int j = 0; j < xr; ++j) dst[(size_t)y * lv.pitch + x0 + 4 * tx + j] = 0;
         }
-        int base = 0;
-        if (tx == 31 && inc) base = atomicAdd(&s_cnt, inc);
-        int pos = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (corner & (0x80u << (8 * j))) s_queue[pos++] = (unsigned short)((ty << 7) | (4 * tx + j));
+        const unsigned vote = __ballot_sync(0xffffffffu, quick != 0u);
+        if (vote) {                                            // one shared-memory atomic per warp
+            int base = 0;
+            if (tx == 0) base = atomicAdd(&s_cnt1, __popc(vote));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (quick) {
+                const unsigned m4 = ((quick >> 7) & 1u) | ((quick >> 14) & 2u) | ((quick >> 21) & 4u) | ((quick >> 28) & 8u);
+                s_quads[base + __popc(vote & ((1u << tx) - 1u))] = (unsigned short)(tid | (m4 << 8));
+            }
+        }
     }
     __syncthreads();
-    const int nq = s_cnt;
+    // ---- phase 2, dense over the surviving quads: the packed, polarity-blind 16-point test
+    const int n1 = s_cnt1;
+    for (int i = tid; i < n1; i += 256) {
+        const int e = s_quads[i];
+        const int qx = e & 31, qy = (e >> 5) & 7;
+        const unsigned m4 = (unsigned)e >> 8;
+        const unsigned C = nb(qx, qy, 0, 0);
+        unsigned F[16];                                // bit 7 of byte j: |centre - neighbour k| of pixel j exceeds minTh
+#pragma unroll
+        for (int k = 0; k < 16; ++k) F[k] = fast_gt_const4(__vabsdiffu4(C, nb(qx, qy, cdx[k], cdy[k])), k7f);
+        // 9 contiguous flags: T3[k] = F[k]&F[k+1]&F[k+2]; run[k] = T3[k]&T3[k+3]&T3[k+6]; any = OR run[k]
+        unsigned any = 0;
+        {
+            unsigned T[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) T[k] = F[k] & F[(k + 1) & 15] & F[(k + 2) & 15];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) any |= T[k] & T[(k + 3) & 15] & T[(k + 6) & 15];
+        }
+        const unsigned valid = ((m4 & 1u) << 7) | ((m4 & 2u) << 14) | ((m4 & 4u) << 21) | ((m4 & 8u) << 28);
+        const unsigned corner = any & valid;
+        const int cnt = __popc(corner);
+        if (cnt) {
+            int pos = atomicAdd(&s_cnt2, cnt);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (corner & (0x80u << (8 * j))) s_queue[pos++] = (unsigned short)((qy << 7) | (4 * qx + j));
+        }
+    }
+    __syncthreads();
+    // ---- phase 3, dense over the candidates: polarity by majority, exact score; the score decides
+    const int nq = s_cnt2;
     const uint8_t* sb = reinterpret_cast<const uint8_t*>(&s_w[0][0]);
     constexpr int ST = FS_ROWW * 4;
     for (int i = tid; i < nq; i += 256) {
@@ -209,7 +231,7 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
             N[w] = (unsigned)q[cdy[4 * w] * ST + cdx[4 * w]] | ((unsigned)q[cdy[4 * w + 1] * ST + cdx[4 * w + 1]] << 8) |
                    ((unsigned)q[cdy[4 * w + 2] * ST + cdx[4 * w + 2]] << 16) | ((unsigned)q[cdy[4 * w + 3] * ST + cdx[4 * w + 3]] << 24);
         const int sc = fast_score_packed(N, *q, g.minTh, k7f);
-        dst[(size_t)(y0 + py) * lv.pitch + x0 + px] = (uint8_t)sc;
+        if (sc) dst[(size_t)(y0 + py) * lv.pitch + x0 + px] = (uint8_t)sc;
     }
 }
 

@@ -113,6 +113,7 @@ struct plf_ctx {
     // LSD / LBD
     uint8_t* d_lsdBlur = nullptr;    // [nImg][H][pitch0]
     uint8_t* d_lsdU = nullptr;       // [nImg][Hs][Ps]
+    const float4* d_gradLut = nullptr; // per-DEVICE table (gx, gy) -> record, shared by every context of the device, never freed
     float4* d_rec = nullptr;         // [nImg][Hs*Ws] per-pixel record of the region grower: angle, cosf, sinf, |g|^2 (as int bits)
     int* d_n2max = nullptr;          // [nImg]
     int* d_seeds = nullptr;          // [nImg][seedCap] seed pixels (packed y<<16|x) in processing order
@@ -211,6 +212,7 @@ int plf_launch_feature_grid(plf_ctx* c, int slotFirst, int nSlots, int* cellStar
 int plf_launch_rectify(plf_ctx* c, const uint8_t* raw0, const uint8_t* raw1, int rawStride, int imgFirst, int nImg);
 int plf_launch_stereo_points(plf_ctx* c, int slotFirst, int nSlots);
 int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg);
+const float4* plf_grad_lut(plf_ctx* c);          // builds the device's gradient record table on first use; nullptr on failure
 int plf_launch_stereo_lines(plf_ctx* c, int slotFirst, int nSlots);
 int plf_launch_match_nnr(plf_ctx* c, const uint8_t* dA, int nA, const uint8_t* dB, int nB, float nnr, int* dOut);
 

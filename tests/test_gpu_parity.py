@@ -582,7 +582,7 @@ def test_keyframe_searches_match_oracle(plf, product, oracle):
             fg, ng = f.search_by_projection_loop(q2, og, 50, ratio, slot=b)
             fo, no = o.search_by_projection_loop(q2, oo, 50, ratio, slot=b)
             assert ng == no and np.array_equal(fg, fo) and np.array_equal(og, oo) and no > 150
-        case = _bow_case(plf, ro, rng)
+        case = _bow_case(plf, ro, rng, b)
         for check, ratio in ((True, 0.7), (False, 0.9)):
             mg, ng = f.search_by_bow(*case, 50, ratio, check, slot=b)
             mo, no = o.search_by_bow(*case, 50, ratio, check, slot=b)

@@ -549,11 +549,11 @@ def test_search_by_projection_loop_oracle_against_python(plf, oracle, ratio):
     assert nm > 100
 
 
-def _bow_case(plf, res, rng, n_nodes=60):
+def _bow_case(plf, res, rng, b=0, n_nodes=60):
     """A keyframe made of the frame's own features (noisy descriptors, rotated angles) plus strangers, with DBoW2-like
     node ids on both sides (some features in no node: stopped words)."""
-    n = int(res.n_kp_left[0])
-    kps, desc = res.kp_left[0, :n], res.desc_left[0, :n]
+    n = int(res.n_kp_left[b])
+    kps, desc = res.kp_left[b, :n], res.desc_left[b, :n]
     m = 900
     src = rng.integers(0, n, m)
     kf_desc = desc[src].copy()

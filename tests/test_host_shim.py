@@ -73,12 +73,6 @@ def test_shim_matches_oracle(tmp_path, plf, oracle, pair1):
     x3d, l3d = o.backproject(Rwc, np.array([[0.5, -1.25, 2.0]], np.float32), 435.2047, 367.4517, 252.2008)
     assert abs(got["sum_x3d"] - float(x3d[0, :len(k)].astype(np.float64).sum())) < 1e-3 * max(1.0, abs(got["sum_x3d"]))
     assert abs(got["sum_l3d"] - float(l3d[0, :len(kl)].sum())) < 1e-6 * max(1.0, abs(got["sum_l3d"]))
-    # lapping area {0, 1000}: every row back to front, monoIndex 0; padded rows give the dense result
-    assert got["mono_lap"] == o.orb_extract(0, L, lapping=(0, 1000))[0] == 0 and got["lap_reversed"] == 1
-    assert got["pad_same"] == 1
-    # Rectifier
-    o.rectify_set_maps(0, mx, my)
-    assert got["rect_fnv"] == fnv(o.rectify(0, L).tobytes())
     # gated line matching and SearchByBoW through the shim, against the oracle's entry points
     lines1 = np.zeros(len(kl), plf.TRACK_LINE_DT)
     lines1["sx"] = kl["startPointX"] + np.float32(4); lines1["sy"] = kl["startPointY"]
@@ -89,3 +83,9 @@ def test_shim_matches_oracle(tmp_path, plf, oracle, pair1):
     nodes = (np.arange(len(k)) % 8).astype(np.int32)
     m, nb = o.search_by_bow(d, k["angle"], nodes, np.ones(len(k), np.uint8), nodes, 50, 0.7, True)
     assert got["bow"] == [nb, int((m == np.arange(len(k))).sum())] and nb > 500
+    # lapping area {0, 1000}: every row back to front, monoIndex 0; padded rows give the dense result
+    assert got["mono_lap"] == o.orb_extract(0, L, lapping=(0, 1000))[0] == 0 and got["lap_reversed"] == 1
+    assert got["pad_same"] == 1
+    # Rectifier
+    o.rectify_set_maps(0, mx, my)
+    assert got["rect_fnv"] == fnv(o.rectify(0, L).tobytes())

@@ -3,6 +3,7 @@
 #include "plf_ctx.cuh"
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 
@@ -322,7 +323,6 @@ static int create_buffers(plf_ctx* c, const plf_params* p, std::vector<PlfCell>&
     if (p->has_lines) {
         PLF_CUDA_OK(dalloc(&c->d_lsdBlur, nImg * (size_t)g.lv[0].pitch * g.H + 64));   // +64: the upscale reads whole words
         PLF_CUDA_OK(dalloc(&c->d_lsdU, nImg * (size_t)g.Ps * g.Hs));
-        PLF_CUDA_OK(dalloc(&c->d_rec, nImg * npx));
         PLF_CUDA_OK(dalloc(&c->d_n2max, nImg));
         c->d_gradLut = plf_grad_lut(c);
         if (!c->d_gradLut) return fail(PLF_ERR_CUDA, "cannot allocate the LSD gradient record table");
@@ -363,13 +363,14 @@ PLF_API int plf_destroy(plf_ctx* c) {
     cudaStreamSynchronize(c->stream);
     void* ptrs[] = {c->d_pyr, c->d_blur, c->d_score, c->d_tilesBlur, c->d_tilesFast, c->d_lin, c->d_cells, c->d_cellCount, c->d_cand, c->d_scratch, c->d_lvlKp, c->d_lvlN,
                     c->d_kpTmp, c->d_descTmp, c->d_kp, c->d_desc, c->d_nKp, c->d_mono, c->d_err, c->d_uRight, c->d_depth,
-                    c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_rec, c->d_n2max, c->d_seeds,
+                    c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_n2max, c->d_seeds,
                     c->d_nSeeds, c->d_n2, c->d_used, c->d_reg, c->d_owner, c->d_regMW, c->d_stream, c->d_laneRT, c->d_scr, c->d_nReg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
                     c->d_sobel, c->d_lbd, c->d_ldesc, c->d_rowMask, c->d_dirR, c->d_dmat, c->d_m21, c->d_m12, c->d_disp,
                     c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage, c->d_rmap[0], c->d_rmap[1], c->d_gridStart, c->d_gridIdx, c->d_bpPose, c->d_bpX, c->d_bpL, c->d_bowWord, c->d_bowNode, c->d_bowWeight, c->d_projQ, c->d_projCount, c->d_projStart, c->d_projPool,
                     c->voc[0].childFirst, c->voc[0].childCount, c->voc[0].child, c->voc[0].word, c->voc[0].desc, c->voc[0].weight,
                     c->voc[1].childFirst, c->voc[1].childCount, c->voc[1].child, c->voc[1].word, c->voc[1].desc, c->voc[1].weight};
     for (void* q : ptrs) if (q) cudaFree(q);
+    if (c->graphExec) cudaGraphExecDestroy(c->graphExec);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -616,13 +617,14 @@ PLF_API int plf_tap_lsd_angles(plf_ctx* c, int slot, int side, float* out, int* 
     if (!out) return PLF_OK;
     PLF_CUDA_OK(cudaSetDevice(c->device));
     const size_t npx = (size_t)c->g.Ws * c->g.Hs;
-    PLF_CUDA_OK(cudaMemcpy2DAsync(out, 4, c->d_rec + (size_t)(slot * 2 + side) * npx, 16, 4, npx, cudaMemcpyDeviceToHost, c->stream));
-    // records exist only for defined pixels; the |g|^2 map (0 = undefined) says which ones those are
-    std::vector<int> n2(npx);
-    PLF_CUDA_OK(cudaMemcpy2DAsync(n2.data(), (size_t)c->g.Ws * 4, c->d_n2 + (size_t)(slot * 2 + side) * c->g.Ps * c->g.Hs, (size_t)c->g.Ps * 4,
+    // the angle of a defined pixel is the .x of its record in the per-device table, indexed by the pixel's gradient code
+    std::vector<int> code(npx);
+    std::vector<float> ang((size_t)1 << 20);
+    PLF_CUDA_OK(cudaMemcpy2DAsync(code.data(), (size_t)c->g.Ws * 4, c->d_n2 + (size_t)(slot * 2 + side) * c->g.Ps * c->g.Hs, (size_t)c->g.Ps * 4,
                                   (size_t)c->g.Ws * 4, c->g.Hs, cudaMemcpyDeviceToHost, c->stream));
+    PLF_CUDA_OK(cudaMemcpy2DAsync(ang.data(), 4, c->d_gradLut, 16, 4, ang.size(), cudaMemcpyDeviceToHost, c->stream));
     PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
-    for (size_t i = 0; i < npx; ++i) if (n2[i] == 0) out[i] = PLF_NOTDEF;
+    for (size_t i = 0; i < npx; ++i) out[i] = code[i] ? ang[code[i]] : PLF_NOTDEF;
     return PLF_OK;
 }
 PLF_API int plf_tap_lsd_segments(plf_ctx* c, int slot, int side, float* xyxy, int cap, int* n) {
@@ -680,13 +682,38 @@ PLF_API int plf_batch_run(plf_ctx* c, int batch) {
     int n = 0;
     if (c->nMarks && strcmp(c->markNames[0], "h2d") != 0) c->nMarks = 0;   // run without a fresh upload: restart marks
     if (c->nMarks > 1 && !(c->nMarks == 2 && strcmp(c->markNames[1], "rectify") == 0)) c->nMarks = 0;
+    // The whole pass is a fixed sequence of ~30 launches and memsets on the context stream with no host round trip, so
+    // from the second call with the same batch size on it is replayed as ONE CUDA graph launch (the first call runs
+    // eagerly: it performs the lazy allocations and the one-time function attributes that must not happen under capture).
+    // Stage timing needs the events between the stages and keeps the eager path; PLF_NO_GRAPH=1 disables the graph.
+    static const bool s_noGraph = getenv("PLF_NO_GRAPH") != nullptr;
+    const bool wantGraph = !s_noGraph && !c->stageTiming && c->warmBatch == batch;
+    if (wantGraph && c->graphExec && c->graphBatch == batch) {
+        PLF_CUDA_OK(cudaGraphLaunch(c->graphExec, c->stream));
+        c->launches = c->graphLaunches;
+        c->orbValid[0] = c->orbValid[1] = c->lineValid[0] = c->lineValid[1] = true;
+        return PLF_OK;
+    }
+    const bool capture = wantGraph && cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (c->p.has_points) n += plf_launch_orb(c, 0, 2 * batch, 0, 0);
-    else PLF_CUDA_OK(cudaMemsetAsync(c->d_nKp, 0, (size_t)2 * batch * sizeof(int), c->stream));
+    else cudaMemsetAsync(c->d_nKp, 0, (size_t)2 * batch * sizeof(int), c->stream);
     if (c->p.has_lines) n += plf_launch_lines(c, 0, 2 * batch);
     if (c->p.has_lines) n += plf_launch_stereo_lines(c, 0, batch);
     if (c->p.has_points) n += plf_launch_stereo_points(c, 0, batch);
     plf_mark(c, "d2h");
+    if (capture) {
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        if (c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&c->graphExec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { c->graphExec = nullptr; return plf_set_cuda_error(e, "graph capture of plf_batch_run", __FILE__, __LINE__); }
+        c->graphBatch = batch;
+        c->graphLaunches = n;
+        PLF_CUDA_OK(cudaGraphLaunch(c->graphExec, c->stream));
+    }
     PLF_CUDA_OK(cudaGetLastError());
+    c->warmBatch = batch;
     c->launches = n;
     c->orbValid[0] = c->orbValid[1] = c->lineValid[0] = c->lineValid[1] = true;
     return PLF_OK;

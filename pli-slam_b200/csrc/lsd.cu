@@ -58,14 +58,22 @@ __global__ void __launch_bounds__(256) lsd_upscale_kernel(PlfGeom g, const uint8
 // K4b  level-line field (LSD ll_angle): 2x2 gradient, squared norm, fastAtan2 angle (degrees), cosf/sinf of the angle,
 // per-image max of the squared norm over defined pixels.
 // The record of a defined pixel — angle, cosf, sinf, |g|^2 — is a pure function of the integer gradient (gx, gy), each in
-// [-510, 510]: one table per device (1021^2 x 16 B = 16.7 MB, L2-resident; typical gradients touch a few hundred KB of
-// it), filled once by the very expression the per-pixel code used, so the records are unchanged bit for bit.
-#define LSD_LUT_R 510
-#define LSD_LUT_W (2 * LSD_LUT_R + 1)
+// [-510, 510].  A pixel therefore carries only its 20-bit GRADIENT CODE (gx + 512) | (gy + 512) << 10 (0 = undefined:
+// a real code has both fields >= 2) in a 4-byte map, and the records live in one table per device indexed by that code
+// (2^20 x 16 B = 16.8 MB, L2-resident; the gradients of a frame touch a few hundred KB of it), filled once by the very
+// expression the per-pixel code of the first version used, so every record is unchanged bit for bit.  Against a
+// 16-byte record per pixel this takes 8.3 MB per image out of HBM (and out of the gradient kernel's writes and the
+// grower's reads) for one dependent, cache-resident load per candidate pixel.
+#define LSD_LUT_N (1 << 20)
+__device__ __forceinline__ int lsd_code(int gx, int gy) { return (gx + 512) | ((gy + 512) << 10); }
+__device__ __forceinline__ int lsd_n2(int code) {          // |g|^2 (x4, as LSD's 2x2 operator gives it) of a DEFINED pixel
+    const int gx = (code & 1023) - 512, gy = (code >> 10) - 512;
+    return gx * gx + gy * gy;
+}
 __global__ void __launch_bounds__(256) lsd_lut_kernel(float4* lut) {
     const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= LSD_LUT_W * LSD_LUT_W) return;
-    const int gy = i / LSD_LUT_W - LSD_LUT_R, gx = i % LSD_LUT_W - LSD_LUT_R;
+    if (i >= LSD_LUT_N) return;
+    const int gy = (i >> 10) - 512, gx = (i & 1023) - 512;
     const float a = fast_atan2_deg((float)gx, (float)-gy);
     const float af = (float)((double)a * kDegToRad);
     // cosf/sinf taken as correctly rounded (double result rounded to float), the declared oracle rule
@@ -74,25 +82,15 @@ __global__ void __launch_bounds__(256) lsd_lut_kernel(float4* lut) {
     lut[i] = make_float4(a, (float)cs, (float)sn, __int_as_float(gx * gx + gy * gy));
 }
 
-__global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, const float4* __restrict__ lut, float4* rec,
-                                                       int* n2map, uint32_t* used, int* n2max, int imgFirst) {
-    // Two phases per 128x8 tile, 4 horizontally adjacent pixels per thread (aligned 32-bit loads of the u8 image, one
-    // 16-byte store of the |g|^2 map per thread, one bitmap word per 8 threads):
-    // (1) 2x2 gradient and |g|^2; a pixel is defined iff |g|^2 > n2Thresh, the integer image of LSD's "norm > rho" test
-    //     (exact: host-searched with the same IEEE sqrt).  Undefined pixels get no record; defined ones are queued.
-    // (2) the queue is processed densely, one defined pixel per thread: the record is copied from the per-device table
-    //     of all (gx, gy) (see lsd_lut_kernel), so the fastAtan2 + double sincos of the first version is paid once per device.
-    __shared__ int s_cnt;
-    __shared__ int s_q[1024];          // (ty<<7 | column) | (gx+1024)<<10 | (gy+1024)<<21
+__global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, int* gmap, uint32_t* used, int* n2max, int imgFirst) {
+    // 128x8 tiles, 4 horizontally adjacent pixels per thread (aligned 32-bit loads of the u8 image, one 16-byte store of
+    // the gradient-code map per thread, one bitmap word per 8 threads): 2x2 gradient and |g|^2; a pixel is defined iff
+    // |g|^2 > n2Thresh, the integer image of LSD's "norm > rho" test (exact: host-searched with the same IEEE sqrt).
     const int x = blockIdx.x * 128 + threadIdx.x * 4, y = blockIdx.y * 8 + threadIdx.y;
     const int img = imgFirst + blockIdx.z;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    const size_t base = (size_t)img * g.Ws * g.Hs;
     int best = 0;
     if (y < g.Hs) {                                    // warp-uniform: a warp is one row of the tile
-        int n2v[4] = {0, 0, 0, 0};
+        int gv[4] = {0, 0, 0, 0};
         if (x < g.Ws) {
             const uint8_t* r0 = U + (size_t)img * g.Ps * g.Hs + (size_t)y * g.Ps + x;
             const uint8_t* r1 = r0 + (y + 1 < g.Hs ? g.Ps : 0);
@@ -111,34 +109,32 @@ __global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t*
                     const int gx = DA + BC, gy = DA - BC;
                     const int n2 = gx * gx + gy * gy;
                     if (n2 > g.n2Thresh) {
-                        s_q[atomicAdd(&s_cnt, 1)] = (threadIdx.y << 7) | (threadIdx.x * 4 + j) | ((gx + 1024) << 10) | ((gy + 1024) << 21);
                         best = max(best, n2);
-                        n2v[j] = n2;
+                        gv[j] = lsd_code(gx, gy);
                     }
                 }
             }
         }
-        // |g|^2 map (0 = undefined) and the grower's bitmap with the undefined pixels pre-marked as used: undefined
-        // pixels need no record at all, and the grower never loads one for them
-        *reinterpret_cast<int4*>(n2map + (size_t)img * g.Ps * g.Hs + (size_t)y * g.Ps + x) = make_int4(n2v[0], n2v[1], n2v[2], n2v[3]);
-        unsigned w = ((n2v[0] == 0) | ((n2v[1] == 0) << 1) | ((n2v[2] == 0) << 2) | ((n2v[3] == 0) << 3)) << (4 * (threadIdx.x & 7));
+        // gradient-code map (0 = undefined) and the grower's bitmap with the undefined pixels pre-marked as used: the
+        // grower never looks at the record of an undefined pixel
+        *reinterpret_cast<int4*>(gmap + (size_t)img * g.Ps * g.Hs + (size_t)y * g.Ps + x) = make_int4(gv[0], gv[1], gv[2], gv[3]);
+        unsigned w = ((gv[0] == 0) | ((gv[1] == 0) << 1) | ((gv[2] == 0) << 2) | ((gv[3] == 0) << 3)) << (4 * (threadIdx.x & 7));
         w |= __shfl_xor_sync(0xffffffffu, w, 1);
         w |= __shfl_xor_sync(0xffffffffu, w, 2);
         w |= __shfl_xor_sync(0xffffffffu, w, 4);
         if ((threadIdx.x & 7) == 0)
             used[((size_t)img * g.Hs + y) * (g.Ps >> 5) + blockIdx.x * 4 + (threadIdx.x >> 3)] = w;
     }
+    // per-image maximum: one atomic per block at most, and none when the image's maximum already covers the block's (a
+    // same-address atomic per warp made this reduction the kernel's bottleneck)
+    __shared__ int s_best;
+    if (threadIdx.x == 0 && threadIdx.y == 0) s_best = 0;
+    __syncthreads();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(n2max + img, best);
+    if (threadIdx.x == 0 && best > 0) atomicMax(&s_best, best);
     __syncthreads();
-    const int nq = s_cnt;
-    for (int i = tid; i < nq; i += 256) {
-        const int e = s_q[i];
-        const int col = e & 0x7F, row = (e >> 7) & 0x7, gx = ((e >> 10) & 0x7FF) - 1024, gy = ((e >> 21) & 0x7FF) - 1024;
-        const int px = blockIdx.x * 128 + col, py = blockIdx.y * 8 + row;
-        rec[base + (size_t)py * g.Ws + px] = lut[(gy + LSD_LUT_R) * LSD_LUT_W + gx + LSD_LUT_R];
-    }
+    if (threadIdx.x == 0 && threadIdx.y == 0 && s_best > 0 && s_best > *reinterpret_cast<volatile int*>(n2max + img)) atomicMax(n2max + img, s_best);
 }
 
 __device__ __forceinline__ int lsd_bin(int n2, double binCoef) { return (int)(sqrt((double)n2 / 4.0) * binCoef); }
@@ -155,7 +151,7 @@ __device__ __forceinline__ double lsd_bin_coef(int n2max, int nBins) {
 // __match_any_sync, so the order inside a bin is raster order by construction and no warp waits for another.
 #define ORD_WARPS 16
 #define ORD_MLP 8
-__global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, const int* n2map, const int* n2max, int* seeds,
+__global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, const int* gmap, const int* n2max, int* seeds,
                                                          int* nSeeds, int imgFirst) {
     extern __shared__ int s_cur[];          // [ORD_WARPS][nBins]
     __shared__ int s_scan[ORD_WARPS];
@@ -164,11 +160,11 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nBins = g.nBins;
     const double coef = lsd_bin_coef(n2max[img], nBins);
-    // raster walk over the pitched |g|^2 map: the padding columns hold 0 (undefined) and cost one compare
+    // raster walk over the pitched gradient-code map: the padding columns hold 0 (undefined) and cost one compare
     const int npx = g.Ps * g.Hs;
     const int segLen = ((npx + ORD_WARPS - 1) / ORD_WARPS + 31) & ~31;
     const int p0 = warp * segLen, p1 = min(p0 + segLen, npx);
-    const int* N2 = n2map + (size_t)img * npx;
+    const int* N2 = gmap + (size_t)img * npx;
     int* mine = s_cur + warp * nBins;
     for (int i = tid; i < ORD_WARPS * nBins; i += 32 * ORD_WARPS) s_cur[i] = 0;
     if (tid == 0) s_carry = 0;
@@ -181,7 +177,7 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, co
         for (int u = 0; u < ORD_MLP; ++u) v[u] = (pb + 32 * u < p1) ? N2[pb + 32 * u] : 0;
 #pragma unroll
         for (int u = 0; u < ORD_MLP; ++u)
-            if (v[u]) atomicAdd(&mine[lsd_bin(v[u], coef)], 1);
+            if (v[u]) atomicAdd(&mine[lsd_bin(lsd_n2(v[u]), coef)], 1);
     }
     __syncthreads();
     // cursors: for bins in descending order, for warps in ascending order
@@ -227,7 +223,7 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, co
             if (x >= W) { x -= W; ++y; }
             const int v = vv[u];
             const bool def = v != 0;
-            const int bin = def ? lsd_bin(v, coef) : 0;
+            const int bin = def ? lsd_bin(lsd_n2(v), coef) : 0;
             const unsigned wm = __ballot_sync(0xffffffffu, def);
             if (def) {
                 const unsigned grp = __match_any_sync(wm, bin);
@@ -286,12 +282,12 @@ struct GrowState {
 };
 
 struct GrowCtx {
-    const float4* REC;
+    const float4* LUT;   // per-device record table, indexed by gradient code
     uint32_t* used;
-    const int* N2;   // pitched |g|^2 map
+    const int* G;    // pitched gradient-code map (0 = undefined)
     int* R;
     int* ring;
-    int W, H, PB, lane, ddx, ddy;   // PB: bits per bitmap row (= pitch of N2)
+    int W, H, PB, lane, ddx, ddy;   // PB: bits per bitmap row (= pitch of G)
     // speculative (several regions of one image in flight) mode only:
     uint32_t* owner;    // per pixel: tag of the region that claims it in the current wave, PLF_FREE if none
     uint32_t tag;       // my tag = slot + 1; a lower tag is an earlier seed
@@ -457,7 +453,7 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
             else if (old != PLF_FREE && old > c.tag) atomicOr(c.invalid + (old - 1), 1);
         }
     }
-    st.regDeg = c.REC[p].x;
+    st.regDeg = c.LUT[c.G[(pk0 >> 16) * c.PB + (pk0 & 0xFFFF)]].x;
     st.dirty = false;
     {
         double sn, cs;
@@ -473,7 +469,7 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
         // 4 * GROW_SETS entries; the sets are then resolved in list order.
         const int nb = min(4 * GROW_SETS, st.n - i);
         const bool inRing = (st.n - i) <= GROW_RING;
-        int q[GROW_SETS], pk[GROW_SETS];
+        int q[GROW_SETS], pk[GROW_SETS], code[GROW_SETS];
         float4 r[GROW_SETS];
         bool valid[GROW_SETS];
 #pragma unroll
@@ -482,14 +478,14 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
             q[s] = -1 - c.lane;
             pk[s] = 0;
             valid[s] = false;
-            r[s] = make_float4(PLF_NOTDEF, 0.f, 0.f, 0.f);
+            code[s] = 0;
             if (e < nb) {
                 const int rp = inRing ? c.ring[(i + e) & (GROW_RING - 1)] : c.R[i + e];
                 const int xx = (rp & 0xFFFF) + c.ddx, yy = (rp >> 16) + c.ddy;
                 if (xx >= 0 && yy >= 0 && xx < c.W && yy < c.H) {
                     q[s] = yy * c.PB + xx;
                     pk[s] = (yy << 16) | xx;
-                    r[s] = c.REC[yy * c.W + xx];          // issued together with the bitmap word: one round trip
+                    code[s] = c.G[q[s]];                  // issued together with the bitmap word: one round trip
                     valid[s] = !used_bit(c.used, q[s]);   // unused implies defined: undefined pixels start as used
                     if (SPEC && valid[s] && c.owner[q[s]] == c.tag) valid[s] = false;     // my own pixels count as used
                 }
@@ -499,6 +495,9 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
         unsigned dupAll[GROW_SETS];
 #pragma unroll
         for (int s = 0; s < GROW_SETS; ++s) dupAll[s] = (s * 4 < nb) ? __match_any_sync(0xffffffffu, q[s]) : 0u;
+        // the records of the unused candidates only (a cache-resident table; most candidates are used and load nothing)
+#pragma unroll
+        for (int s = 0; s < GROW_SETS; ++s) r[s] = valid[s] ? c.LUT[code[s]] : make_float4(PLF_NOTDEF, 0.f, 0.f, 0.f);
         unsigned acc[GROW_SETS];
 #pragma unroll
         for (int s = 0; s < GROW_SETS; ++s) {
@@ -533,7 +532,7 @@ __device__ __forceinline__ void rect_fit(const GrowCtx& c, double (*s_sum)[33], 
         if (lane < cnt) {
             const int rp = c.R[i0 + lane];
             const int ry = rp >> 16, rx = rp & 0xFFFF;
-            wv = sqrt((double)c.N2[ry * c.PB + rx] / 4.0);
+            wv = sqrt((double)lsd_n2(c.G[ry * c.PB + rx]) / 4.0);
             xw = __dmul_rn((double)rx, wv);
             yw = __dmul_rn((double)ry, wv);
         }
@@ -548,7 +547,7 @@ __device__ __forceinline__ void rect_fit(const GrowCtx& c, double (*s_sum)[33], 
         if (lane < cnt) {
             const int rp = c.R[i0 + lane];
             const int ry = rp >> 16, rx = rp & 0xFFFF;
-            const double wv = sqrt((double)c.N2[ry * c.PB + rx] / 4.0);
+            const double wv = sqrt((double)lsd_n2(c.G[ry * c.PB + rx]) / 4.0);
             const double dx = __dsub_rn((double)rx, cxm), dy = __dsub_rn((double)ry, cym);
             vxx = __dmul_rn(__dmul_rn(dy, dy), wv);
             vyy = __dmul_rn(__dmul_rn(dx, dx), wv);
@@ -623,7 +622,7 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[33], int& n, double
     const int pk0 = c.R[0];
     const int sy = pk0 >> 16, sx = pk0 & 0xFFFF, p0 = sy * W + sx;
     const double xc = (double)sx, yc = (double)sy;
-    const double angC = (double)c.REC[p0].x * kDegToRad;
+    const double angC = (double)c.LUT[c.G[sy * c.PB + sx]].x * kDegToRad;
     double acc3 = 0;      // lane 0: sum of signed angle differences, lane 1: sum of their squares
     int cntIn = 0;
     for (int i0 = 0; i0 < n; i0 += 32) {
@@ -632,10 +631,10 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[33], int& n, double
         bool in = false;
         if (lane < cnt) {
             const int rp = c.R[i0 + lane];
-            const int ry = rp >> 16, rx = rp & 0xFFFF, q = ry * W + rx, qb = ry * c.PB + rx;
+            const int ry = rp >> 16, rx = rp & 0xFFFF, qb = ry * c.PB + rx;
             atomicAnd(c.used + (qb >> 5), ~(1u << (qb & 31)));                    // *(reg[i].used) = NOTUSED
             if (lsd_dist(xc, yc, (double)rx, (double)ry) < rf.width) {
-                double d = __dsub_rn((double)c.REC[q].x * kDegToRad, angC);         // angle_diff_signed
+                double d = __dsub_rn((double)c.LUT[c.G[qb]].x * kDegToRad, angC);         // angle_diff_signed
                 while (d <= -kPi) d += 2 * kPi;
                 while (d > kPi) d -= 2 * kPi;
                 v0 = d;
@@ -689,7 +688,7 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[33], int& n, double
 // (Measured: two images per block with the registers capped at 48 / 40 to hold 40 / 48 warps per SM instead of 32 gives
 // the same images/s at a full wave and a slower single warp — the kernel is not occupancy-limited there.)
 template <bool REFINE>
-__global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* rec, const int* n2map, const int* seeds,
+__global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* lut, const int* gmap, const int* seeds,
                                                       const int* nSeeds, uint32_t* usedAll, int* reg, float* segs,
                                                       int* nSegsOut, int* err, int imgFirst) {
     __shared__ int ring[GROW_RING];
@@ -698,8 +697,8 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
     GrowCtx c;
     c.W = g.Ws; c.H = g.Hs; c.PB = g.Ps; c.lane = lane;
     const size_t base = (size_t)img * c.W * c.H;
-    c.REC = rec + base;
-    c.N2 = n2map + (size_t)img * g.Ps * g.Hs;
+    c.LUT = lut;
+    c.G = gmap + (size_t)img * g.Ps * g.Hs;
     c.used = usedAll + (size_t)img * (g.Ps >> 5) * g.Hs;
     c.R = reg + base;
     c.ring = ring;
@@ -762,7 +761,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* r
 #define MW PLF_MW_WARPS
 #define MW_SCAN 256
 #define MW_DIST 12
-__global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const float4* rec, const int* n2map, const int* seeds,
+__global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const float4* lut, const int* gmap, const int* seeds,
                                                             const int* nSeeds, uint32_t* usedAll, uint32_t* ownerAll, int* regAll,
                                                             float* segs, int* nSegsOut, int* err, int imgFirst) {
     __shared__ int ring[MW][GROW_RING];
@@ -775,8 +774,8 @@ __global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const f
     const size_t npx = (size_t)g.Ws * g.Hs, npb = (size_t)g.Ps * g.Hs;
     GrowCtx c;
     c.W = g.Ws; c.H = g.Hs; c.PB = g.Ps; c.lane = lane;
-    c.REC = rec + (size_t)img * npx;
-    c.N2 = n2map + (size_t)img * npb;
+    c.LUT = lut;
+    c.G = gmap + (size_t)img * npb;
     c.used = usedAll + (size_t)img * (g.Ps >> 5) * g.Hs;
     c.owner = ownerAll + (size_t)blockIdx.x * npb;
     c.R = regAll + ((size_t)blockIdx.x * MW + w) * npx;
@@ -1247,8 +1246,8 @@ const float4* plf_grad_lut(plf_ctx* c) {
     if (dev < 0 || dev >= 64) return nullptr;
     if (!s_gradLut[dev]) {
         float4* p = nullptr;
-        if (cudaMalloc((void**)&p, (size_t)LSD_LUT_W * LSD_LUT_W * sizeof(float4)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        lsd_lut_kernel<<<(LSD_LUT_W * LSD_LUT_W + 255) / 256, 256, 0, c->stream>>>(p);
+        if (cudaMalloc((void**)&p, (size_t)LSD_LUT_N * sizeof(float4)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        lsd_lut_kernel<<<LSD_LUT_N / 256, 256, 0, c->stream>>>(p);
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cudaFree(p); return nullptr; }
         s_gradLut[dev] = p;
     }
@@ -1309,7 +1308,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     lsd_upscale_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, c->d_lin + c->linLsdX, c->d_lin + c->linLsdY, imgFirst);
     plf_mark(c, "lsd_gradient");
     cudaMemsetAsync(c->d_n2max + imgFirst, 0, nImg * sizeof(int), s);
-    lsd_grad_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, lut, c->d_rec, c->d_n2, c->d_used, c->d_n2max, imgFirst);
+    lsd_grad_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_n2, c->d_used, c->d_n2max, imgFirst);
     plf_mark(c, "lsd_order");
     {
         const size_t smem = (size_t)ORD_WARPS * g.nBins * sizeof(int);
@@ -1326,33 +1325,33 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         const bool wantStream = s_mode && !strcmp(s_mode, "stream");
         const bool wantLane = s_mode && !strcmp(s_mode, "lane");
         if (g.refine >= 1)
-            lsd_grow_kernel<true><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
+            lsd_grow_kernel<true><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                       c->d_nSegs, c->d_err, imgFirst);
         else if (wantStream && plf_ensure_stream_buffers(c) == 0) {
             // one lane per region: up to 32 regions of each image in flight in its warp, rectangles fitted afterwards
             const StreamLayout L = stream_layout(g.Ps, g.Ws, g.Hs, g.segCap);
             int* scr = c->d_stream + (size_t)imgFirst * L.total;
             lsd_stream_init_kernel<<<dim3(32, nImg), 256, 0, s>>>(g, c->d_n2, scr, L, imgFirst);
-            lsd_stream_kernel<<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_seeds, c->d_nSeeds, scr, L, c->d_reg, c->d_nReg, c->d_err, imgFirst);
+            lsd_stream_kernel<<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, scr, L, c->d_reg, c->d_nReg, c->d_err, imgFirst);
             lsd_rect_kernel<<<dim3(64, nImg), 128, 0, s>>>(g, c->d_n2, reinterpret_cast<const int4*>(scr + L.RT), (size_t)L.total / 4, c->d_reg,
                                                            c->d_nReg, c->d_segs, c->d_nSegs, imgFirst);
             launches += 2;
         } else if (wantLane && plf_ensure_lane_buffers(c) == 0) {
             // one lane per image: 32 images per warp, the plain scalar loop; rectangles fitted afterwards
-            lsd_grow_lane_kernel<<<(nImg + 31) / 32, 32, 0, s>>>(g, c->d_rec, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_laneRT, c->d_nReg,
+            lsd_grow_lane_kernel<<<(nImg + 31) / 32, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_laneRT, c->d_nReg,
                                                                  c->d_err, imgFirst, nImg);
             lsd_rect_kernel<<<dim3(16, nImg), 128, 0, s>>>(g, c->d_n2, c->d_laneRT + (size_t)imgFirst * g.segCap, (size_t)g.segCap, c->d_reg,
                                                            c->d_nReg, c->d_segs, c->d_nSegs, imgFirst);
             launches += 1;
         } else if (s_mode && !strcmp(s_mode, "seq"))
-            lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
+            lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                        c->d_nSegs, c->d_err, imgFirst);
         else if (nImg <= PLF_MW_MAX_IMG && plf_ensure_mw_buffers(c) == 0)
             // few images: several regions of each image in flight (a block of 8 warps per image)
-            lsd_grow_mw_kernel<<<nImg, 32 * MW, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_owner, c->d_regMW,
+            lsd_grow_mw_kernel<<<nImg, 32 * MW, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_owner, c->d_regMW,
                                                         c->d_segs, c->d_nSegs, c->d_err, imgFirst);
         else
-            lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, c->d_rec, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
+            lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                        c->d_nSegs, c->d_err, imgFirst);
     }
     plf_mark(c, "line_keylines");

@@ -19,7 +19,7 @@
 __device__ __forceinline__ int ln_dx(int k) { return (int)((0x9224u >> (2 * k)) & 3u) - 1; }   // 0 1 2 0 2 0 1 2 (2 bits each) - 1
 __device__ __forceinline__ int ln_dy(int k) { return (int)((0xA940u >> (2 * k)) & 3u) - 1; }   // 0 0 0 1 1 2 2 2
 
-__global__ void __launch_bounds__(32) lsd_grow_lane_kernel(PlfGeom g, const float4* rec, const int* seeds, const int* nSeeds,
+__global__ void __launch_bounds__(32) lsd_grow_lane_kernel(PlfGeom g, const float4* lut, const int* gmap, const int* seeds, const int* nSeeds,
                                                            uint32_t* usedAll, int* regAll, int4* rtAll, int* nRegAll, int* err,
                                                            int imgFirst, int nImg) {
     __shared__ int ring[LN_RING][32];
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(32) lsd_grow_lane_kernel(PlfGeom g, const floa
     const bool live = li < nImg;
     const int img = imgFirst + (live ? li : nImg - 1);
     const int W = g.Ws, H = g.Hs, PBW = g.Ps >> 5;
-    const float4* REC = rec + (size_t)img * W * H;
+    const int* G = gmap + (size_t)img * g.Ps * H;
     uint32_t* used = usedAll + (size_t)img * PBW * H;
     int* R = regAll + (size_t)img * W * H;
     const int* S = seeds + (size_t)img * g.seedCap;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(32) lsd_grow_lane_kernel(PlfGeom g, const floa
                     const int k = __ffs(m) - 1;
                     m &= m - 1;
                     const int xx = x + ln_dx(k), yy = y + ln_dy(k);
-                    const float4 r = REC[yy * W + xx];
+                    const float4 r = lut[G[yy * (PBW << 5) + xx]];
                     if (lsd_aligned(regDeg, r.x, tol)) {
                         if (fresh) {          // the seed enters the sums as (float)cos / sin of its double angle
                             double sn, cs;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(32) lsd_grow_lane_kernel(PlfGeom g, const floa
                     R[base] = pk0;
                     ring[0][lane] = pk0;
                     n = 1;
-                    regDeg = REC[y * W + x].x;
+                    regDeg = lut[G[qb]].x;
                     fresh = true;
                 } else {
                     sPos = s0 + 8;

@@ -97,7 +97,7 @@ struct StreamShared {
 
 struct StreamCtx {                  // per-image pointers and the warp-uniform bookkeeping
     uint32_t* O; int* CH; int* FS; int* TK; int4* RT; int* RF;
-    const float4* REC; const int* S;
+    const float4* LUT; const int* G; const int* S;
     StreamShared* sh;
     int W, H, PB, ns, nChunks, minReg, segCap, lane;
     int cp, scanPos, nBlocked, nReady, bump, stackTop, nFreeC, killEpoch, live, nReg, rfPos, err, nKill, nRel;
@@ -229,7 +229,7 @@ __device__ __forceinline__ bool st_dep_broken(const StreamCtx& c, int ndep, uint
     return b;
 }
 
-__global__ void __launch_bounds__(32) lsd_stream_kernel(PlfGeom g, const float4* rec, const int* seeds, const int* nSeeds, int* scratch,
+__global__ void __launch_bounds__(32) lsd_stream_kernel(PlfGeom g, const float4* lut, const int* gmap, const int* seeds, const int* nSeeds, int* scratch,
                                                        StreamLayout L, int* regAll, int* nRegOut, int* err, int imgFirst) {
     __shared__ StreamShared sh;
     const int img = imgFirst + blockIdx.x, lane = threadIdx.x;
@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(32) lsd_stream_kernel(PlfGeom g, const float4*
     c.O = reinterpret_cast<uint32_t*>(base + L.O); c.CH = base + L.CH; c.FS = base + L.FS; c.TK = base + L.TK;
     c.RT = reinterpret_cast<int4*>(base + L.RT);
     c.RF = regAll + (size_t)img * g.Ws * g.Hs;
-    c.REC = rec + (size_t)img * g.Ws * g.Hs;
+    c.LUT = lut;
+    c.G = gmap + (size_t)img * g.Ps * g.Hs;
     c.S = seeds + (size_t)img * g.seedCap;
     c.W = g.Ws; c.H = g.Hs; c.PB = g.Ps; c.ns = nSeeds[img]; c.nChunks = L.nChunks; c.minReg = g.minRegSize; c.segCap = g.segCap; c.lane = lane;
     c.cp = 0; c.scanPos = 0; c.nBlocked = 0; c.nReady = 0; c.bump = 0; c.stackTop = 0; c.nFreeC = 0; c.killEpoch = 0; c.live = 0; c.nReg = 0;
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(32) lsd_stream_kernel(PlfGeom g, const float4*
         uint32_t oc = ST_COMMITTED, os = ST_COMMITTED;
         float ds = 0.f;
         if (cpPk >= 0) oc = c.O[(cpPk >> 16) * c.PB + (cpPk & 0xFFFF)];
-        if (scPk >= 0) { os = c.O[(scPk >> 16) * c.PB + (scPk & 0xFFFF)]; ds = c.REC[(scPk >> 16) * c.W + (scPk & 0xFFFF)].x; }
+        if (scPk >= 0) { os = c.O[(scPk >> 16) * c.PB + (scPk & 0xFFFF)]; ds = c.LUT[c.G[(scPk >> 16) * c.PB + (scPk & 0xFFFF)]].x; }
         // released candidates: one per lane from the top of the ready list
         int rdPos = -1, rdPk = 0;
         uint32_t rdO = ST_COMMITTED;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(32) lsd_stream_kernel(PlfGeom g, const float4*
             rdPos = sh.ready[c.nReady - 1 - lane];
             rdPk = c.S[rdPos];
             rdO = c.O[(rdPk >> 16) * c.PB + (rdPk & 0xFFFF)];
-            rdDeg = c.REC[(rdPk >> 16) * c.W + (rdPk & 0xFFFF)].x;
+            rdDeg = c.LUT[c.G[(rdPk >> 16) * c.PB + (rdPk & 0xFFFF)]].x;
         }
         // the pixels claimed in the previous step, the neighbours of the entry to expand, the entry after it
         const bool growing = a.tag != 0u && a.i < a.n;
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(32) lsd_stream_kernel(PlfGeom g, const float4*
             const int xx = ex + st_dx(k), yy = ey + st_dy(k);
             o[k] = ST_COMMITTED;
             r[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (growing && xx >= 0 && yy >= 0 && xx < c.W && yy < c.H) { o[k] = c.O[yy * c.PB + xx]; r[k] = c.REC[yy * c.W + xx]; }
+            if (growing && xx >= 0 && yy >= 0 && xx < c.W && yy < c.H) { o[k] = c.O[yy * c.PB + xx]; r[k] = c.LUT[c.G[yy * c.PB + xx]]; }
         }
         int nxPk = 0;
         bool nxLoaded = false;
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(32) lsd_stream_kernel(PlfGeom g, const float4*
                     if (stall) {
                         // no lane / no room earlier in this source: keep the candidate
                     } else if (src == 0) {
-                        dj = c.REC[y * c.W + x].x;
+                        dj = c.LUT[c.G[y * c.PB + x]].x;
                         target = 0;
                     } else if (__ballot_sync(0xffffffffu, a.tag == tag)) {
                         handled = true;                                                  // already in a lane (queued twice)
@@ -680,7 +681,7 @@ __global__ void __launch_bounds__(128) lsd_rect_kernel(PlfGeom g, const int* n2m
         const int4 rt = rtBase[(size_t)blockIdx.y * rtStride + ri];
         GrowCtx c;
         c.W = g.Ws; c.H = g.Hs; c.PB = g.Ps; c.lane = lane;
-        c.N2 = n2map + (size_t)img * g.Ps * g.Hs;
+        c.G = n2map + (size_t)img * g.Ps * g.Hs;
         c.R = regAll + (size_t)img * g.Ws * g.Hs + rt.x;
         RectFit rf;
         rect_fit<false>(c, s_sum[w], rt.y, (double)__int_as_float(rt.z) * kDegToRad, g.prec, rf);

@@ -113,12 +113,12 @@ struct plf_ctx {
     // LSD / LBD
     uint8_t* d_lsdBlur = nullptr;    // [nImg][H][pitch0]
     uint8_t* d_lsdU = nullptr;       // [nImg][Hs][Ps]
-    const float4* d_gradLut = nullptr; // per-DEVICE table (gx, gy) -> record, shared by every context of the device, never freed
-    float4* d_rec = nullptr;         // [nImg][Hs*Ws] per-pixel record of the region grower: angle, cosf, sinf, |g|^2 (as int bits)
+    const float4* d_gradLut = nullptr; // per-DEVICE table gradient code -> record (angle in degrees, cosf, sinf, |g|^2 as int bits), shared by every context of the device, never freed
     int* d_n2max = nullptr;          // [nImg]
     int* d_seeds = nullptr;          // [nImg][seedCap] seed pixels (packed y<<16|x) in processing order
     int* d_nSeeds = nullptr;         // [nImg]
-    int* d_n2 = nullptr;             // [nImg][Hs][Ps] |g|^2 of defined pixels, 0 where undefined (seed ordering, rectangle weights)
+    int* d_n2 = nullptr;             // [nImg][Hs][Ps] gradient code (gx + 512) | (gy + 512) << 10 of defined pixels, 0 where undefined:
+                                     // index of the pixel's record in d_gradLut; |g|^2 for the seed order and the rectangle weights
     uint32_t* d_used = nullptr;      // [nImg][Hs][Ps/32] used bitmap of the region grower; undefined pixels start as used
     int* d_reg = nullptr;            // [nImg][Hs*Ws] region pixel list, packed y<<16|x (reused per region)
     uint32_t* d_owner = nullptr;     // small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][Hs][Ps] owner tags of the current wave (PLF_FREE = none)
@@ -174,6 +174,8 @@ struct plf_ctx {
     bool orbValid[2] = {false, false};
     bool lineValid[2] = {false, false};
     int launches = 0;
+    cudaGraphExec_t graphExec = nullptr;  // plf_batch_run of `graphBatch` pairs as one graph (captured on the second call with that size)
+    int graphBatch = 0, graphLaunches = 0, warmBatch = 0;
     bool stageTiming = false;
     std::vector<cudaEvent_t> ev;          // pool of timing events (marks)
     std::vector<const char*> markNames;   // name of the stage that STARTS at mark i

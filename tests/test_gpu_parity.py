@@ -618,6 +618,26 @@ def test_match_lines_tracked_matches_oracle(plf, product, oracle, mode):
     assert ng == 0 and np.all(mg == -1)                                   # fewer than two train rows: no matches (declared rule)
 
 
+def test_repeated_calls_replay_the_graph(plf, product, oracle):
+    """From the second call with one batch size on, plf_batch_run replays a captured CUDA graph: four calls on one context
+    with different frames (and a change of batch size in between, which re-captures) against the oracle, every array."""
+    W, H = 752, 480
+    f = plf.Frontend(product, max_batch=3, lsd_nfeatures=0)
+    o = plf.Frontend(oracle, max_batch=3, lsd_nfeatures=0)
+    fields = [("kp_left", "n_kp_left"), ("desc_left", "n_kp_left"), ("kp_right", "n_kp_right"), ("desc_right", "n_kp_right"),
+              ("kl_left", "n_kl_left"), ("ldesc_left", "n_kl_left"), ("kl_right", "n_kl_right"), ("ldesc_right", "n_kl_right"),
+              ("u_right", "n_kp_left"), ("depth", "n_kp_left"), ("disp_se", "n_kl_left"), ("line_match12", "n_kl_left")]
+    for call, seeds in enumerate(([201, 202, 203], [204, 205, 206], [207, 208, 209], [210, 211], [212, 213], [214, 215, 216])):
+        L, R = plf.synth_batch(W, H, seeds)
+        rg, ro = f.frontend_batch(L, R), o.frontend_batch(L, R)
+        for b in range(len(seeds)):
+            for name, cnt in fields:
+                n = int(getattr(ro, cnt)[b])
+                assert int(getattr(rg, cnt)[b]) == n, (call, b, cnt)
+                assert np.array_equal(getattr(rg, name)[b, :n], getattr(ro, name)[b, :n]), (call, b, name)
+        assert f.launch_count() > 20
+
+
 def test_large_batch_sequential_grower_matches_oracle(plf, product, oracle):
     """Launches of more than 128 images use the one-warp-per-image region grower (the kernel the benchmark runs); smaller
     ones use the multi-region grower.  72 pairs (144 images, 8 distinct pairs repeated) against the oracle, exactly, and

@@ -351,22 +351,27 @@ PLF_API int PLF_FN(search_by_bow)(plf_ctx* ctx, int slot, const uint8_t* kf_desc
 typedef struct plf_track_line {
     float sx, sy, ex, ey;       /* start / end point in the current image                                    */
     float angle;                /* mvKeysUn_Line[i1].angle (frame-to-frame gate only)                        */
-    int32_t eligible;           /* frame-to-frame: LastFrame.mvpMapLines[i1] != NULL (:3064); local map: 1   */
+    int32_t eligible;           /* mode 0: LastFrame.mvpMapLines[i1] != NULL (:3064)
+                                 * mode 1: pML->Observations() > 0 (decides whether a line attached by this very
+                                 *         loop blocks the later ones that matched the same keyline, :3892-3894) */
 } plf_track_line;
 
-/* Replaces the line half of Tracking::TrackWithMotionModel (src/Tracking.cc:3055-3099; mode 0) and of
- * Tracking::SearchLocalLines (src/Tracking.cc:3879-3917; mode 1): match(desc1, desc2, nnr, matches_12)
- * (src/LineMatcher.cpp:201-229, mutual best) followed by the gates the tracker applies to every match, fused into one
- * device pass (2-NN both ways, mutual-best filter and gates; one D2H of the two result arrays).
+/* Replaces the line half of Tracking::TrackWithMotionModel (src/Tracking.cc:3055-3099; mode 0) and the matching half of
+ * Tracking::SearchLocalLines (src/Tracking.cc:3879-3919; mode 1): the descriptor matching followed by the gates the
+ * tracker applies to every match, in one device pass (2-NN, gates, one D2H of the two result arrays).
+ *   mode 0 matches with match(desc1, desc2, nnr, matches_12) (src/LineMatcher.cpp:201-229: both directions, mutual best);
+ *   mode 1 with match(vpLocalMapLines, CurrentFrame, nnr, matches_12), which RETURNS AFTER matchNNR(desc1, desc2)
+ *   (src/LineMatcher.cpp:161-170; the mutual-best code behind the return is dead), so several lines may match one keyline
+ *   and the loop is order-dependent: reproduced exactly (the first passing line that has observations keeps the keyline).
  *   lines1[n1]: the first set; kl2[n2]: mCurrentFrame.mvKeysUn_Line; disp2[n2][2]: mCurrentFrame.mvDisparity_l
  *   held2[n2] (mode 1, may be NULL): mCurrentFrame.mvpMapLines[i2] has Observations() > 0 (:3892-3894)
  *   min_x .. max_y: Frame::mnMinX/mnMaxX/mnMinY/mnMaxY (deltaWidth/Height = (max - min) * 0.1, :3060-3061)
- * For every i1 with a match i2: not eligible, a negative disparity (:3067) or (mode 1) a held line -> the match is kept
- * but nothing is assigned; mode 0: |angle2 - angle1| folded to (-pi, pi] > pi/8 -> matches12[i1] = -1 (:3072-3079);
- * both modes: an end point farther than deltaWidth / deltaHeight from its counterpart -> matches12[i1] = -1
- * (:3080-3093, :3901-3914); otherwise assign12[i1] = i2 (mCurrentFrame.mvpMapLines[i2] = the line of i1).
- *   matches12[n1], assign12[n1]: out.  *n_assigned = the reference's n_inliers_ls of mode 0 / the number of map lines
- *   attached in mode 1. */
+ * For every i1 with a match i2: (mode 0) not eligible, a negative disparity (:3067) or (mode 1) a keyline whose current
+ * holder has observations -> the match is kept but nothing is assigned; mode 0: |angle2 - angle1| folded to (-pi, pi] >
+ * pi/8 -> matches12[i1] = -1 (:3072-3079); both modes: an end point farther than deltaWidth / deltaHeight from its
+ * counterpart -> matches12[i1] = -1 (:3080-3093, :3901-3914); otherwise the line is attached to the keyline.
+ *   matches12[n1]: out.  assign12[n1]: out, the i2 with mCurrentFrame.mvpMapLines[i2] == line i1 when the loop ends, else -1.
+ *   *n_assigned = the reference's n_inliers_ls of mode 0 / the number of keylines that received a line in mode 1. */
 PLF_API int PLF_FN(match_lines_tracked)(plf_ctx* ctx, int mode, const uint8_t* desc1, const plf_track_line* lines1, int n1,
                                         const uint8_t* desc2, const plf_keyline* kl2, const float* disp2,
                                         const uint8_t* held2, int n2, float nnr, float min_x, float max_x, float min_y,

@@ -9,6 +9,9 @@ What is compiled, unmodified:
                src/Frame.cc:976-1307          ComputeStereoMatches, ComputeStereoMatches_Lines,
                                               lineSegmentOverlapStereo, filterLineSegmentDisparity
                src/ORBmatcher.cc:36-42,2495-2511   TH_HIGH / TH_LOW, DescriptorDistance
+               src/ORBmatcher.cc:269-471,2449-2490 SearchByBoW(KeyFrame*, Frame&, ...), ComputeThreeMaxima
+               src/Tracking.cc:3055-3099,3879-3919 match() + the orientation / position gates of TrackWithMotionModel
+                                              and SearchLocalLines (loop bodies wrapped in two functions)
                Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp:42-687,1026-1372
                                               LBD: parameters, computeSobel, binaryConversion, computeImpl, computeLBD
                                               (the rest of that file is the EDLine detector, dead on this path)
@@ -47,9 +50,10 @@ FRAME_SIDE = ["-DFRAME_H", "-DORBMATCHER_H", "-DMAPPOINT_H", "-DMAPLINE_H", "-DK
 
 
 def lines(path, a, b):
-    with open(os.path.join(REF, path), encoding="utf-8", errors="replace") as f:
+    # newline="\n": line numbers as grep / sed / an editor count them (a lone CR inside a line is not a line break)
+    with open(os.path.join(REF, path), encoding="utf-8", errors="replace", newline="\n") as f:
         ls = f.readlines()
-    return "".join(ls[a - 1:b])
+    return "".join(ls[a - 1:b]).replace("\r", "")
 
 
 def generate():
@@ -57,7 +61,19 @@ def generate():
     frame = ("// GENERATED at build time from %s/src/Frame.cc:976-1307 and src/ORBmatcher.cc:36-42,2495-2511 - do not commit\n"
              "namespace ORB_SLAM3 {\n" % REF
              + lines("src/ORBmatcher.cc", 36, 42) + lines("src/ORBmatcher.cc", 2495, 2511)
-             + lines("src/Frame.cc", 976, 1307) + "\n}\n")
+             + lines("src/Frame.cc", 976, 1307)
+             + "\n// ORBmatcher::SearchByBoW (src/ORBmatcher.cc:269-471) and ComputeThreeMaxima (:2449-2490)\n"
+             + lines("src/ORBmatcher.cc", 269, 471) + lines("src/ORBmatcher.cc", 2449, 2490)
+             + "\nfloat Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;\n"
+             "// Tracking::TrackWithMotionModel, line half: src/Tracking.cc:3055-3099\n"
+             "int ref_track_gate_f2f(Frame& mCurrentFrame, Frame& mLastFrame, std::vector<int>& matches_out) {\n"
+             + lines("src/Tracking.cc", 3055, 3099)
+             + "    matches_out = matches_12;\n    return mCurrentFrame.n_inliers_ls;\n}\n"
+             "// Tracking::SearchLocalLines, matching half: src/Tracking.cc:3879-3919\n"
+             "void ref_track_gate_local(Frame& mCurrentFrame, std::vector<MapLine*>& mvpLocalMapLines_InFrustum, int nToMatch, std::vector<int>& matches_out) {\n"
+             + lines("src/Tracking.cc", 3879, 3919)
+             + "    matches_out = matches_12;\n}\n"
+             + "\n}\n")
     lbd = ("// GENERATED at build time from %s/Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp:42-687,1026-1372 - do not commit\n" % REF
            + lines("Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp", 42, 687)
            + lines("Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp", 1026, 1372)

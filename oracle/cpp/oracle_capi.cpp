@@ -863,19 +863,29 @@ PLF_API int plf_cpu_match_lines_tracked(plf_ctx*, int mode, const uint8_t* desc1
         return fail(PLF_ERR_INVALID, "bad arguments");
     if (n_assigned) *n_assigned = 0;
     if (n1 == 0) return PLF_OK;
-    match_lr(desc1, n1, desc2, n2, nnr, 1, matches12);
+    // mode 0: match(desc1, desc2, ...) = both directions + mutual best (src/LineMatcher.cpp:201-229).  mode 1:
+    // match(vpLocalMapLines, CurrentFrame, ...) returns right after matchNNR(desc1, desc2) (src/LineMatcher.cpp:161-170).
+    if (mode == 0) match_lr(desc1, n1, desc2, n2, nnr, 1, matches12);
+    else match_nnr(desc1, n1, desc2, n2, nnr, matches12);
     const double kPiD = 3.14159265358979323846;
     const double deltaAngle = kPiD / 8.0;
     const double deltaWidth = (max_x - min_x) * 0.1;
     const double deltaHeight = (max_y - min_y) * 0.1;
     int n_inliers_ls = 0;
+    // mCurrentFrame.mvpMapLines as the loop sees it: -2 = a line from before the loop with observations, -3 = none,
+    // >= 0 = the line of that i1 (attached by this loop)
+    std::vector<int> holder(n2 > 0 ? n2 : 1, -3);
+    if (mode == 1 && held2) for (int i2 = 0; i2 < n2; ++i2) if (held2[i2]) holder[i2] = -2;
+    for (int i1 = 0; i1 < n1; ++i1) assign12[i1] = -1;
     for (int i1 = 0; i1 < n1; ++i1) {
-        assign12[i1] = -1;
-        if (!lines1[i1].eligible) continue;
+        if (mode == 0 && !lines1[i1].eligible) continue;
         const int i2 = matches12[i1];
         if (i2 < 0) continue;
         if (disp2[i2 * 2] < 0 || disp2[i2 * 2 + 1] < 0) continue;
-        if (mode == 1 && held2 && held2[i2]) continue;
+        if (mode == 1) {                                      // if(mvpMapLines[i2]) if(mvpMapLines[i2]->Observations()>0) continue;
+            const int h = holder[i2];
+            if (h == -2 || (h >= 0 && lines1[h].eligible)) continue;
+        }
         if (mode == 0) {
             double theta = kl2[i2].angle - lines1[i1].angle;
             if (theta < -kPiD) theta += 2 * kPiD;
@@ -891,9 +901,12 @@ PLF_API int plf_cpu_match_lines_tracked(plf_ctx*, int mode, const uint8_t* desc1
             matches12[i1] = -1;
             continue;
         }
+        if (holder[i2] >= 0) assign12[holder[i2]] = -1;      // mvpMapLines[i2] is overwritten
+        holder[i2] = i1;
         assign12[i1] = i2;
-        ++n_inliers_ls;
+        if (mode == 0) ++n_inliers_ls;
     }
+    if (mode == 1) for (int i1 = 0; i1 < n1; ++i1) n_inliers_ls += assign12[i1] >= 0;
     if (n_assigned) *n_assigned = n_inliers_ls;
     return PLF_OK;
 }

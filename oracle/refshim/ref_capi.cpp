@@ -293,6 +293,109 @@ REF_API int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (src/ORBmatcher.cc:269-471): the two FeatureVectors are
+// built from per-feature node ids (< 0: the feature is in no entry); kf_valid 0 = no map point, 2 = a bad one.
+// match[f] = index of the keyframe feature whose map point frame feature f received, or -1.
+REF_API int ref_search_by_bow(const uint8_t* kfDesc, const float* kfAngle, const int* kfNode, const uint8_t* kfValid, int nKF,
+                              const uint8_t* fDesc, const float* fAngle, const int* fNode, int nF, float nnratio, int checkOri,
+                              int* match) {
+    return guarded([&] {
+        std::vector<MapPoint> pts(nKF);
+        KeyFrame kf;
+        kf.mvpMapPoints.assign(nKF, nullptr);
+        kf.mvKeysUn.resize(nKF);
+        for (int i = 0; i < nKF; i++) {
+            kf.mvKeysUn[i].angle = kfAngle[i];
+            if (kfValid[i]) { kf.mvpMapPoints[i] = &pts[i]; pts[i].mbBad = kfValid[i] == 2; }
+            if (kfNode[i] >= 0) kf.mFeatVec[(DBoW2::NodeId)kfNode[i]].push_back((unsigned)i);
+        }
+        kf.mDescriptors = wrap_desc(kfDesc, nKF);
+        Frame F;
+        F.N = nF;
+        F.mvKeys.resize(nF);
+        for (int i = 0; i < nF; i++) {
+            F.mvKeys[i].angle = fAngle[i];
+            if (fNode[i] >= 0) F.mFeatVec[(DBoW2::NodeId)fNode[i]].push_back((unsigned)i);
+        }
+        F.mDescriptors = wrap_desc(fDesc, nF);
+        std::vector<MapPoint*> out;
+        ORBmatcher matcher(nnratio, checkOri != 0);
+        const int n = matcher.SearchByBoW(&kf, F, out);
+        for (int f = 0; f < nF; f++) match[f] = out[f] ? (int)(out[f] - pts.data()) : -1;
+        return n;
+    });
+}
+
+// The line half of Tracking::TrackWithMotionModel (src/Tracking.cc:3055-3099): match() with Config::minRatio12L() and the
+// orientation / position gates.  has1[i1]: LastFrame.mvpMapLines[i1] != NULL.  assign[i1] = the i2 whose mvpMapLines slot
+// received the line of i1, or -1; returns n_inliers_ls; *nnr = the ratio the reference used.
+REF_API int ref_track_lines_f2f(const uint8_t* d1, const KeyLine* kl1, const uint8_t* has1, int n1, const uint8_t* d2,
+                                const KeyLine* kl2, const float* disp2, int n2, float minX, float maxX, float minY, float maxY,
+                                int* matches12, int* assign12, float* nnr) {
+    return guarded([&] {
+        if (n2 < 2 || n1 < 2) throw std::runtime_error("undefined in the reference: fewer than 2 rows");
+        std::vector<MapLine> lines(n1);
+        Frame last, cur;
+        last.mvpMapLines.assign(n1, nullptr);
+        for (int i = 0; i < n1; i++) if (has1[i]) last.mvpMapLines[i] = &lines[i];
+        last.mDescriptors_Line = wrap_desc(d1, n1);
+        last.mvKeysUn_Line.assign(kl1, kl1 + n1);
+        cur.mDescriptors_Line = wrap_desc(d2, n2);
+        cur.mvKeysUn_Line.assign(kl2, kl2 + n2);
+        cur.mvpMapLines.assign(n2, nullptr);
+        cur.mvDisparity_l.resize(n2);
+        for (int i = 0; i < n2; i++) cur.mvDisparity_l[i] = std::make_pair(disp2[2 * i], disp2[2 * i + 1]);
+        Frame::mnMinX = minX; Frame::mnMaxX = maxX; Frame::mnMinY = minY; Frame::mnMaxY = maxY;
+        std::vector<int> m;
+        const int n = ref_track_gate_f2f(cur, last, m);
+        for (int i = 0; i < n1; i++) { matches12[i] = m[i]; assign12[i] = -1; }
+        for (int i2 = 0; i2 < n2; i2++) if (cur.mvpMapLines[i2]) assign12[cur.mvpMapLines[i2] - lines.data()] = i2;
+        if (nnr) *nnr = (float)Config::minRatio12L();
+        return n;
+    });
+}
+
+// The matching half of Tracking::SearchLocalLines (src/Tracking.cc:3879-3919): match(local map lines, frame) and the
+// position gate against the projections mTrackProjsX .. mTrackProjeY.  obs1[i1]: the local map line has observations;
+// held2[i2]: mCurrentFrame.mvpMapLines[i2] is a line with Observations() > 0 (1) or without (2) before the loop.
+REF_API int ref_track_lines_local(const uint8_t* d1, const float* proj1 /* n1 x 4: sX sY eX eY */, const uint8_t* obs1, int n1, const uint8_t* d2,
+                                  const KeyLine* kl2, const float* disp2, const uint8_t* held2, int n2, float minX, float maxX,
+                                  float minY, float maxY, int* matches12, int* assign12, float* nnr) {
+    return guarded([&] {
+        if (n2 < 2 || n1 < 2) throw std::runtime_error("undefined in the reference: fewer than 2 rows");
+        std::vector<MapLine> lines(n1), holders(n2);
+        std::vector<MapLine*> local(n1);
+        for (int i = 0; i < n1; i++) {
+            lines[i].mLDescriptor = wrap_desc(d1 + (size_t)i * 32, 1);
+            lines[i].mTrackProjsX = proj1[4 * i]; lines[i].mTrackProjsY = proj1[4 * i + 1];
+            lines[i].mTrackProjeX = proj1[4 * i + 2]; lines[i].mTrackProjeY = proj1[4 * i + 3];
+            lines[i].nObs = obs1[i] ? 2 : 0;                  // pML->Observations()
+            local[i] = &lines[i];
+        }
+        Frame cur;
+        cur.mDescriptors_Line = wrap_desc(d2, n2);
+        cur.mvKeysUn_Line.assign(kl2, kl2 + n2);
+        cur.mvpMapLines.assign(n2, nullptr);
+        cur.mvDisparity_l.resize(n2);
+        for (int i = 0; i < n2; i++) {
+            cur.mvDisparity_l[i] = std::make_pair(disp2[2 * i], disp2[2 * i + 1]);
+            if (held2 && held2[i]) { holders[i].nObs = held2[i] == 1 ? 3 : 0; cur.mvpMapLines[i] = &holders[i]; }
+        }
+        Frame::mnMinX = minX; Frame::mnMaxX = maxX; Frame::mnMinY = minY; Frame::mnMaxY = maxY;
+        std::vector<int> m;
+        ref_track_gate_local(cur, local, n1, m);
+        int cnt = 0;
+        for (int i = 0; i < n1; i++) { matches12[i] = m[i]; assign12[i] = -1; }
+        for (int i2 = 0; i2 < n2; i2++) {
+            MapLine* q = cur.mvpMapLines[i2];
+            if (q && q >= lines.data() && q < lines.data() + n1) { assign12[q - lines.data()] = i2; ++cnt; }
+        }
+        if (nnr) *nnr = (float)Config::minRatio12L();
+        return cnt;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // The stereo Frame constructor of the reference as a timed unit (bench.py --impl reference / cpu_baseline): four
 // threads per pair — ExtractORB(left), ExtractORB(right), ExtractLine(left), ExtractLine(right), src/Frame.cc:128-135 —
 // join, ComputeStereoMatches_Lines, ComputeStereoMatches (:160-163).  One handle per worker; handles share nothing but

@@ -3,10 +3,15 @@
 // (oracle/build_ref.py passes -DFRAME_H -DORBMATCHER_H -DMAPPOINT_H -DMAPLINE_H -DKEYFRAME_H and force-includes this
 // file).  Those headers drag in DBoW2, g2o, Pangolin-era types and the whole map; the frontend FUNCTION BODIES taken
 // from src/Frame.cc:976-1307 and src/ORBmatcher.cc:36-42,2495-2511 only need the members declared here, under the
-// reference's own names (include/Frame.h:152-154,218-252,316,373-374; include/ORBmatcher.h:36-42,102-104).
+// reference's own names (include/Frame.h:152-154,218-252,316,373-374; include/ORBmatcher.h:36-42,102-104).  The bodies of
+// ORBmatcher::SearchByBoW / ComputeThreeMaxima (src/ORBmatcher.cc:269-471,2449-2490) and the line-match gates of the
+// tracking thread (src/Tracking.cc:3055-3099,3879-3919) additionally need the KeyFrame / MapPoint / MapLine members and
+// the DBoW2::FeatureVector declared below (include/KeyFrame.h, include/MapPoint.h, include/MapLine.h,
+// Thirdparty/DBoW2/DBoW2/FeatureVector.h:24-27: a std::map<NodeId, std::vector<unsigned int>>).
 #pragma once
 #include <climits>
 #include <list>
+#include <map>
 #include <thread>
 #include <vector>
 #include "Auxiliar.h"        // the reference's own header (using-directives for cv / line_descriptor / std / Eigen)
@@ -20,18 +25,45 @@
 
 namespace ORB_SLAM3 {
 
-class MapPoint {};
-class KeyFrame {};
+}  // namespace ORB_SLAM3
+namespace DBoW2 {
+typedef unsigned int NodeId;
+class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
+}
+namespace ORB_SLAM3 {
+
+class GeometricCamera {};
+class MapPoint {
+public:
+    bool isBad() { return mbBad; }
+    bool mbBad = false;
+};
+class KeyFrame {
+public:
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    std::vector<MapPoint*> mvpMapPoints;
+    DBoW2::FeatureVector mFeatVec;
+    cv::Mat mDescriptors;
+    std::vector<cv::KeyPoint> mvKeysUn, mvKeys, mvKeysRight;
+    GeometricCamera* mpCamera2 = nullptr;
+    int NLeft = -1;
+};
 class MapLine {
 public:
     cv::Mat GetDescriptor() { return mLDescriptor.clone(); }
+    int Observations() { return nObs; }
     cv::Mat mLDescriptor;
+    float mTrackProjsX = 0, mTrackProjsY = 0, mTrackProjeX = 0, mTrackProjeY = 0;
+    int nObs = 0;
 };
+class Frame;
 
 class ORBmatcher {
 public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true);
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
     static const int TH_LOW;
     static const int TH_HIGH;
     static const int HISTO_LENGTH;
@@ -66,6 +98,21 @@ public:
     std::vector<Vector3d> mvle_l;
     std::vector<float> mvScaleFactors, mvInvScaleFactors;
     double inv_width = 0, inv_height = 0;
+    // members read by SearchByBoW and by the tracking thread's line gates
+    DBoW2::FeatureVector mFeatVec;
+    int Nleft = -1;
+    GeometricCamera* mpCamera2 = nullptr;
+    std::vector<cv::KeyPoint> mvKeysUn;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<MapLine*> mvpMapLines;
+    std::vector<KeyLine> mvKeysUn_Line;
+    int n_inliers_ls = 0;
+    static float mnMinX, mnMaxX, mnMinY, mnMaxY;
 };
+
+// the two loops of the tracking thread, generated from src/Tracking.cc by oracle/build_ref.py
+int ref_track_gate_f2f(Frame& mCurrentFrame, Frame& mLastFrame, std::vector<int>& matches_out);
+void ref_track_gate_local(Frame& mCurrentFrame, std::vector<MapLine*>& mvpLocalMapLines_InFrustum, int nToMatch,
+                          std::vector<int>& matches_out);
 
 }  // namespace ORB_SLAM3

@@ -385,7 +385,8 @@ PLF_API int plf_match_lines_tracked(plf_ctx* c, int mode, const uint8_t* desc1, 
     const size_t oD1 = 0, oD2 = oD1 + align256((size_t)n1 * 32), oL1 = oD2 + align256((size_t)n2 * 32);
     const size_t oK2 = oL1 + align256((size_t)n1 * sizeof(plf_track_line)), oDisp = oK2 + align256((size_t)n2 * sizeof(plf_keyline));
     const size_t oHeld = oDisp + align256((size_t)n2 * 8), oM12 = oHeld + align256((size_t)n2);
-    const size_t oM21 = oM12 + align256((size_t)n1 * 4), oAsg = oM21 + align256((size_t)n2 * 4), total = oAsg + align256((size_t)n1 * 4);
+    const size_t oM21 = oM12 + align256((size_t)n1 * 4), oAsg = oM21 + align256((size_t)n2 * 4), oState = oAsg + align256((size_t)n1 * 4);
+    const size_t oBlk = oState + align256((size_t)n1 * 4), oLast = oBlk + align256((size_t)n2 * 4 + 4), total = oLast + align256((size_t)n2 * 4 + 4);
     PLF_CUDA_OK(scratch_reserve(c, total));
     uint8_t* b = c->d_scr;
     PLF_CUDA_OK(cudaMemcpyAsync(b + oD1, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
@@ -399,11 +400,13 @@ PLF_API int plf_match_lines_tracked(plf_ctx* c, int mode, const uint8_t* desc1, 
     int* dM12 = reinterpret_cast<int*>(b + oM12);
     int* dM21 = reinterpret_cast<int*>(b + oM21);
     int* dAsg = reinterpret_cast<int*>(b + oAsg);
+    // mode 0: match() = both directions + mutual best; mode 1: the MapLine overload returns after the one-way matchNNR
     c->launches = plf_launch_match_nnr(c, b + oD1, n1, b + oD2, n2, nnr, dM12);
-    c->launches += plf_launch_match_nnr(c, b + oD2, n2, b + oD1, n1, nnr, dM21);
+    if (mode == 0) c->launches += plf_launch_match_nnr(c, b + oD2, n2, b + oD1, n1, nnr, dM21);
     c->launches += plf_launch_line_gates(c, mode, reinterpret_cast<const plf_track_line*>(b + oL1), n1,
                                          reinterpret_cast<const plf_keyline*>(b + oK2), reinterpret_cast<const float2*>(b + oDisp),
-                                         (mode == 1 && held2) ? b + oHeld : nullptr, n2, min_x, max_x, min_y, max_y, dM12, dM21, dAsg);
+                                         (mode == 1 && held2) ? b + oHeld : nullptr, n2, min_x, max_x, min_y, max_y, dM12, dM21, dAsg,
+                                         reinterpret_cast<int*>(b + oState), reinterpret_cast<int*>(b + oBlk), reinterpret_cast<int*>(b + oLast));
     PLF_CUDA_OK(cudaMemcpyAsync(matches12, dM12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
     PLF_CUDA_OK(cudaMemcpyAsync(assign12, dAsg, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
     PLF_CUDA_OK(cudaStreamSynchronize(s));

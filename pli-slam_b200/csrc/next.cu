@@ -1,6 +1,7 @@
 // Kernels of the rows SURVEY.md §8(f) marks "next" (see capi_next.cu for the entry points): rectification, feature grid,
 // projection-window candidates, bag-of-words descent, landmark back-projection.  Small next to the frontend itself.
 #include "plf_ctx.cuh"
+#include <algorithm>
 #include <cstdint>
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -355,37 +356,69 @@ __global__ void __launch_bounds__(256) bow_pairs_kernel(const uint8_t* kfDesc, c
     }
 }
 
-// ---- match() epilogue of the tracking thread: mutual-best filter (src/LineMatcher.cpp:218-224) and the gates of
-// src/Tracking.cc:3062-3098 (mode 0) / :3888-3917 (mode 1), a thread per line of the first set
+// ---- epilogue of the tracking thread's line matching: mutual-best filter of match() (src/LineMatcher.cpp:218-224, mode 0
+// only: the MapLine overload of mode 1 returns after the one-way matchNNR, :161-170) and the gates of
+// src/Tracking.cc:3062-3098 (mode 0) / :3888-3919 (mode 1), a thread per line of the first set.
+// Mode 0 is order-free (a mutual-best i2 belongs to one i1).  In mode 1 several lines may hold the same keyline i2 and the
+// reference loop is sequential: a line is looked at only while the keyline's holder has no observations.  With
+// pass(i1) = "disparities >= 0 and inside the position gate", the first i1 (in order) of a keyline that passes AND has
+// observations blocks everything after it, every earlier one is looked at, and the keyline ends up with the last passing
+// line at or before the blocker: an atomicMin, an atomicMax and three small passes instead of a serial loop.
+__device__ __forceinline__ bool line_gate_pass(int mode, const plf_track_line& a, const plf_keyline& b, double deltaW, double deltaH) {
+    const double kPiD = 3.14159265358979323846;
+    if (mode == 0) {
+        double theta = (double)__fsub_rn(b.angle, a.angle);
+        if (theta < -kPiD) theta += 2 * kPiD;
+        else if (theta > kPiD) theta -= 2 * kPiD;
+        if (fabs(theta) > kPiD / 8.0) return false;
+    }
+    return !((double)fabsf(__fsub_rn(b.startPointX, a.sx)) > deltaW || (double)fabsf(__fsub_rn(b.endPointX, a.ex)) > deltaW ||
+             (double)fabsf(__fsub_rn(b.startPointY, a.sy)) > deltaH || (double)fabsf(__fsub_rn(b.endPointY, a.ey)) > deltaH);
+}
+
+// pass 1.  state[i1]: 0 = not looked at by the gates (no match / not eligible / negative disparity), 1 = fails, 2 = passes.
+// Mode 0 finishes here; mode 1 records the blocker of every keyline.
 __global__ void __launch_bounds__(128) line_gates_kernel(int mode, const plf_track_line* l1, int n1, const plf_keyline* k2,
-                                                         const float2* disp2, const uint8_t* held2, double deltaW, double deltaH,
-                                                         int* m12, const int* m21, int* assign) {
+                                                         const float2* disp2, double deltaW, double deltaH, int* m12,
+                                                         const int* m21, int* assign, int* state, int* blocker) {
     const int i1 = blockIdx.x * 128 + threadIdx.x;
     if (i1 >= n1) return;
     int i2 = m12[i1];
-    if (i2 >= 0 && m21[i2] != i1) i2 = -1;
-    int as = -1;
+    if (mode == 0 && i2 >= 0 && m21[i2] != i1) i2 = -1;
+    int as = -1, st = 0;
     const plf_track_line a = l1[i1];
-    if (i2 >= 0 && a.eligible) {
+    if (i2 >= 0 && (mode == 1 || a.eligible)) {
         const float2 d = disp2[i2];
-        if (!(d.x < 0 || d.y < 0) && !(held2 && held2[i2])) {
-            const plf_keyline b = k2[i2];
-            const double kPiD = 3.14159265358979323846;
-            bool ok = true;
-            if (mode == 0) {
-                double theta = (double)__fsub_rn(b.angle, a.angle);
-                if (theta < -kPiD) theta += 2 * kPiD;
-                else if (theta > kPiD) theta -= 2 * kPiD;
-                if (fabs(theta) > kPiD / 8.0) ok = false;
-            }
-            if (ok && ((double)fabsf(__fsub_rn(b.startPointX, a.sx)) > deltaW || (double)fabsf(__fsub_rn(b.endPointX, a.ex)) > deltaW ||
-                       (double)fabsf(__fsub_rn(b.startPointY, a.sy)) > deltaH || (double)fabsf(__fsub_rn(b.endPointY, a.ey)) > deltaH))
-                ok = false;
-            if (ok) as = i2; else i2 = -1;
+        if (!(d.x < 0 || d.y < 0)) {
+            const bool ok = line_gate_pass(mode, a, k2[i2], deltaW, deltaH);
+            st = ok ? 2 : 1;
+            if (mode == 0) { if (ok) as = i2; else i2 = -1; }
+            else if (ok && a.eligible) atomicMin(blocker + i2, i1);
         }
     }
     m12[i1] = i2;
     assign[i1] = as;
+    if (mode == 1) state[i1] = st;
+}
+// pass 2 (mode 1): lines at or before their keyline's blocker are looked at: a failing one loses its match, the last
+// passing one is the keyline's final holder
+__global__ void __launch_bounds__(128) line_gates_resolve_kernel(int n1, const uint8_t* held2, int* m12, const int* state,
+                                                                 const int* blocker, int* last) {
+    const int i1 = blockIdx.x * 128 + threadIdx.x;
+    if (i1 >= n1) return;
+    const int st = state[i1];
+    if (st == 0) return;
+    const int i2 = m12[i1];
+    if ((held2 && held2[i2]) || i1 > blocker[i2]) return;           // the holder has observations: `continue`
+    if (st == 1) m12[i1] = -1;
+    else atomicMax(last + i2, i1);
+}
+// pass 3 (mode 1): mCurrentFrame.mvpMapLines[i2] when the loop ends
+__global__ void __launch_bounds__(128) line_gates_assign_kernel(int n1, const int* m12, const int* state, const int* last, int* assign) {
+    const int i1 = blockIdx.x * 128 + threadIdx.x;
+    if (i1 >= n1) return;
+    const int i2 = m12[i1];
+    assign[i1] = (state[i1] == 2 && i2 >= 0 && last[i2] == i1) ? i2 : -1;
 }
 }  // namespace
 
@@ -398,10 +431,18 @@ int plf_launch_bow_pairs(plf_ctx* c, int slot, const uint8_t* dKfDesc, const int
 
 int plf_launch_line_gates(plf_ctx* c, int mode, const plf_track_line* dL1, int n1, const plf_keyline* dK2, const float2* dDisp2,
                           const uint8_t* dHeld2, int n2, float minX, float maxX, float minY, float maxY, int* dM12, const int* dM21,
-                          int* dAssign) {
-    (void)n2;
+                          int* dAssign, int* dState, int* dBlocker, int* dLast) {
     if (n1 <= 0) return 0;
     const double deltaW = (double)(maxX - minX) * 0.1, deltaH = (double)(maxY - minY) * 0.1;     // float difference times the double 0.1
-    line_gates_kernel<<<(n1 + 127) / 128, 128, 0, c->stream>>>(mode, dL1, n1, dK2, dDisp2, dHeld2, deltaW, deltaH, dM12, dM21, dAssign);
-    return 1;
+    const int nb = (n1 + 127) / 128;
+    if (mode == 0) {
+        line_gates_kernel<<<nb, 128, 0, c->stream>>>(0, dL1, n1, dK2, dDisp2, deltaW, deltaH, dM12, dM21, dAssign, nullptr, nullptr);
+        return 1;
+    }
+    cudaMemsetAsync(dBlocker, 0x7F, (size_t)std::max(n2, 1) * sizeof(int), c->stream);          // "no blocker": larger than any i1
+    cudaMemsetAsync(dLast, 0xFF, (size_t)std::max(n2, 1) * sizeof(int), c->stream);             // -1
+    line_gates_kernel<<<nb, 128, 0, c->stream>>>(1, dL1, n1, dK2, dDisp2, deltaW, deltaH, dM12, dM21, dAssign, dState, dBlocker);
+    line_gates_resolve_kernel<<<nb, 128, 0, c->stream>>>(n1, dHeld2, dM12, dState, dBlocker, dLast);
+    line_gates_assign_kernel<<<nb, 128, 0, c->stream>>>(n1, dM12, dState, dLast, dAssign);
+    return 3;
 }

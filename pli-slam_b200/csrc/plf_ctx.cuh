@@ -207,7 +207,7 @@ int plf_launch_bow(plf_ctx* c, int which, int slotFirst, int nSlots, int levelsu
 int plf_launch_bow_pairs(plf_ctx* c, int slot, const uint8_t* dKfDesc, const int4* dJobs, int nJobs, const int* dOrder, int* dPool);
 int plf_launch_line_gates(plf_ctx* c, int mode, const plf_track_line* dL1, int n1, const plf_keyline* dK2, const float2* dDisp2,
                           const uint8_t* dHeld2, int n2, float minX, float maxX, float minY, float maxY, int* dM12, const int* dM21,
-                          int* dAssign);
+                          int* dAssign, int* dState, int* dBlocker, int* dLast);
 int plf_launch_backproject(plf_ctx* c, int slotFirst, int nSlots, const float* dRwc, const float* dOw, float fy, float cx,
                            float cy, float* dX3d, int x3dRows, double* dL3d, int l3dRows);
 int plf_launch_feature_grid(plf_ctx* c, int slotFirst, int nSlots, int* cellStart, int* cellIdx);

@@ -668,7 +668,7 @@ def _track_lines_case(plf, res, rng, mode):
     lines1["ex"] = kl2["endPointX"][src] + shift[:, 2]; lines1["ey"] = kl2["endPointY"][src] + shift[:, 3]
     dang = np.where(rng.random(m) < 0.15, rng.uniform(-3.2, 3.2, m), rng.normal(0, 0.1, m))
     lines1["angle"] = (kl2["angle"][src] + dang).astype(np.float32)
-    lines1["eligible"] = 1 if mode == 1 else (rng.random(m) < 0.85).astype(np.int32)
+    lines1["eligible"] = (rng.random(m) < 0.85).astype(np.int32)      # mode 0: has a map line; mode 1: the map line has observations
     desc1 = desc2[src].copy()
     desc1 ^= np.packbits(rng.random((m, 256)) < 0.03, axis=1)
     desc1[-40:] = rng.integers(0, 256, (40, 32), dtype=np.uint8)
@@ -677,24 +677,34 @@ def _track_lines_case(plf, res, rng, mode):
 
 
 def _match_lines_tracked_python(oracle_front, mode, desc1, lines1, desc2, kl2, disp2, held2, nnr, bounds):
-    """src/Tracking.cc:3055-3099 / :3879-3917 restated on top of match() (itself tested above)."""
+    """src/Tracking.cc:3055-3099 / :3879-3919 restated on top of match() / matchNNR() (themselves tested above): mode 1
+    matches one way only (src/LineMatcher.cpp:161-170 returns after matchNNR), so the loop is order-dependent."""
     import math
     f32 = np.float32
-    _, m12 = oracle_front.match(desc1, desc2, nnr, True)
+    if mode == 0:
+        _, m12 = oracle_front.match(desc1, desc2, nnr, True)
+    else:
+        _, m12 = oracle_front.match_nnr(desc1, desc2, nnr)
     m12 = m12.copy()
     asg = np.full(len(desc1), -1, np.int32)
+    holder = {}                                     # i2 -> ("old", has_obs) | ("new", i1)
+    if mode == 1 and held2 is not None:
+        for i2 in np.nonzero(held2)[0]:
+            holder[int(i2)] = ("old", True)
     dw = float(f32(bounds[1]) - f32(bounds[0])) * 0.1
     dh = float(f32(bounds[3]) - f32(bounds[2])) * 0.1
     for i1 in range(len(desc1)):
-        if not lines1["eligible"][i1]:
+        if mode == 0 and not lines1["eligible"][i1]:
             continue
         i2 = int(m12[i1])
         if i2 < 0:
             continue
         if disp2[i2, 0] < 0 or disp2[i2, 1] < 0:
             continue
-        if mode == 1 and held2 is not None and held2[i2]:
-            continue
+        if mode == 1 and i2 in holder:
+            kind, v = holder[i2]
+            if (kind == "old" and v) or (kind == "new" and lines1["eligible"][v]):
+                continue
         if mode == 0:
             th = float(f32(kl2["angle"][i2]) - f32(lines1["angle"][i1]))
             if th < -math.pi:
@@ -708,6 +718,9 @@ def _match_lines_tracked_python(oracle_front, mode, desc1, lines1, desc2, kl2, d
                 abs(float(f32(kl2["startPointY"][i2]) - f32(lines1["sy"][i1]))) > dh or abs(float(f32(kl2["endPointY"][i2]) - f32(lines1["ey"][i1]))) > dh):
             m12[i1] = -1
             continue
+        if i2 in holder and holder[i2][0] == "new":
+            asg[holder[i2][1]] = -1
+        holder[i2] = ("new", i1)
         asg[i1] = i2
     return m12, asg, int((asg >= 0).sum())
 
@@ -723,7 +736,7 @@ def test_match_lines_tracked_oracle_against_python(plf, oracle, mode):
     wm, wa, wna = _match_lines_tracked_python(o, mode, *case, 0.9, bounds)
     assert na == wna and np.array_equal(m12, wm) and np.array_equal(asg, wa)
     assert na > 40 and (m12 >= 0).sum() > na            # some matches pass without an assignment (no stereo / not eligible / held)
-    nm0, plain = o.match(case[0], case[2], 0.9, True)
+    nm0, plain = o.match(case[0], case[2], 0.9, True) if mode == 0 else o.match_nnr(case[0], case[2], 0.9)
     assert (plain >= 0).sum() > (m12 >= 0).sum()        # and the gates removed some
 
 

@@ -538,3 +538,72 @@ def test_matchnnr_with_one_train_row_is_undefined_in_the_reference(ref):
     m = np.zeros(3, np.int32)
     assert ref.ref_match_nnr(P(d), 3, P(d), 1, C.c_float(0.9), P(m)) == -1000
     assert b"undefined" in ref.ref_last_error()
+
+
+# ---- SearchByBoW and the tracking thread's line gates against the reference's own function bodies -------
+def test_search_by_bow_equals_reference(ref, oracle, plf):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (src/ORBmatcher.cc:269-471 + ComputeThreeMaxima :2449-2490, compiled
+    from the reference) against plf_cpu_search_by_bow on 40 random keyframe / frame pairs: vpMapPointMatches and nmatches
+    equal, with and without the rotation check, for three ratios; keyframe features without a map point and with a bad one."""
+    from test_host_logic import _bow_case
+    f = plf.Frontend(oracle, max_batch=1)
+    for seed in range(8):
+        L, R = plf.synth_pair(752, 480, 500 + seed)
+        res = f.frontend_batch(L[None], R[None])
+        n = int(res.n_kp_left[0])
+        kps, desc = res.kp_left[0, :n], res.desc_left[0, :n]
+        for rep in range(5):
+            rng = np.random.default_rng(1000 * seed + rep)
+            kf_desc, kf_angle, kf_node, kf_valid, f_node = _bow_case(plf, res, rng, 0, n_nodes=int(rng.choice([8, 60, 400])))
+            valid_ref = kf_valid.copy()
+            valid_ref[(kf_valid == 0) & (rng.random(len(kf_valid)) < 0.5)] = 2      # a bad map point instead of none
+            for check, ratio in ((1, 0.7), (0, 0.9), (1, 0.6)):
+                want = np.full(n, -7, np.int32)
+                nref = ref.ref_search_by_bow(P(kf_desc), P(kf_angle), P(kf_node), P(valid_ref), len(kf_desc), P(desc),
+                                             P(np.ascontiguousarray(kps["angle"])), P(f_node), n, C.c_float(ratio), check, P(want))
+                assert nref >= 0, ref.ref_last_error()
+                got, ngot = f.search_by_bow(kf_desc, kf_angle, kf_node, kf_valid, f_node, 50, ratio, bool(check))
+                assert ngot == nref and np.array_equal(got, want), (seed, rep, check, ratio)
+            assert nref > 50
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_tracking_line_gates_equal_reference(ref, oracle, plf, mode):
+    """match() + the orientation / position gates of Tracking::TrackWithMotionModel (src/Tracking.cc:3055-3099, mode 0) and
+    Tracking::SearchLocalLines (:3879-3919, mode 1), loop bodies compiled from the reference, against
+    plf_cpu_match_lines_tracked on 30 random cases and two image-bound settings: matches_12, the map lines attached and
+    the inlier count equal."""
+    from test_host_logic import _track_lines_case
+    f = plf.Frontend(oracle, max_batch=1, lsd_nfeatures=0)
+    total = 0
+    for seed in range(6):
+        L, R = plf.synth_pair(752, 480, 600 + seed)
+        res = f.frontend_batch(L[None], R[None])
+        for rep in range(5):
+            rng = np.random.default_rng(77 * seed + rep + 1000 * mode)
+            desc1, lines1, desc2, kl2, disp2, held2 = _track_lines_case(plf, res, rng, mode)
+            n1, n2 = len(desc1), len(desc2)
+            for bounds in ((0.0, 752.0, 0.0, 480.0), (-3.5, 420.25, 2.0, 150.0)):
+                m = np.zeros(n1, np.int32); a = np.zeros(n1, np.int32); nnr = C.c_float(0)
+                args = [C.c_float(v) for v in bounds]
+                if mode == 0:
+                    kl1 = np.zeros(n1, plf.KEYLINE_DT)
+                    kl1["startPointX"], kl1["startPointY"] = lines1["sx"], lines1["sy"]
+                    kl1["endPointX"], kl1["endPointY"], kl1["angle"] = lines1["ex"], lines1["ey"], lines1["angle"]
+                    has1 = np.ascontiguousarray(lines1["eligible"].astype(np.uint8))
+                    nref = ref.ref_track_lines_f2f(P(desc1), P(kl1), P(has1), n1, P(desc2), P(kl2), P(disp2), n2, *args, P(m), P(a),
+                                                   C.byref(nnr))
+                    held = None
+                else:
+                    proj = np.ascontiguousarray(np.stack([lines1["sx"], lines1["sy"], lines1["ex"], lines1["ey"]], 1), np.float32)
+                    held_ref = held2.copy()
+                    held_ref[(held2 == 0) & (rng.random(n2) < 0.2)] = 2         # held by a line without observations: not a holder
+                    obs1 = np.ascontiguousarray(lines1["eligible"].astype(np.uint8))
+                    nref = ref.ref_track_lines_local(P(desc1), P(proj), P(obs1), n1, P(desc2), P(kl2), P(disp2), P(held_ref), n2, *args,
+                                                     P(m), P(a), C.byref(nnr))
+                    held = held2
+                assert nref >= 0, ref.ref_last_error()
+                gm, ga, gn = f.match_lines_tracked(mode, desc1, lines1, desc2, kl2, disp2, held, nnr.value, bounds)
+                assert gn == nref and np.array_equal(gm, m) and np.array_equal(ga, a), (seed, rep, bounds)
+                total += nref
+    assert total > 1000

@@ -318,8 +318,8 @@ PLF_API int PLF_FN(search_by_projection_reloc)(plf_ctx* ctx, int slot, const plf
                                                int32_t* feat_query, int* n_matches);
 
 /* Replaces: int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints,
- * vector<MapPoint*>& vpMatched, int th, float ratioHamming) (src/ORBmatcher.cc:473-580) and its vpPointsKFs /
- * vpMatchedKF variant (:582-704; the search is identical, feat_query tells the caller which pKFi to record), the loop
+ * vector<MapPoint*>& vpMatched, int th, float ratioHamming) (src/ORBmatcher.cc:473-586) and its vpPointsKFs /
+ * vpMatchedKF variant (:588-704; the search is identical, feat_query tells the caller which pKFi to record), the loop
  * closing / place recognition searches, from the projected points on; the slot plays the keyframe.  One plf_frame_query
  * per candidate map point: u, v (:519 / :631-635), radius = th * mvScaleFactors[nPredictedLevel] (:545), min_level /
  * max_level = nPredictedLevel - 1 / nPredictedLevel (the filter of :566), desc, skip != 0 for the `continue`s of

@@ -10,6 +10,9 @@ What is compiled, unmodified:
                                               lineSegmentOverlapStereo, filterLineSegmentDisparity
                src/ORBmatcher.cc:36-42,2495-2511   TH_HIGH / TH_LOW, DescriptorDistance
                src/ORBmatcher.cc:269-471,2449-2490 SearchByBoW(KeyFrame*, Frame&, ...), ComputeThreeMaxima
+               src/ORBmatcher.cc:44-222,473-586,2179-2447  the four SearchByProjection overloads + RadiusByViewingCos
+               src/Frame.cc:451-482,774-855   AssignFeaturesToGrid, GetFeaturesInArea, PosInGrid
+               src/KeyFrame.cc:881-930        KeyFrame::GetFeaturesInArea, IsInImage
                src/Tracking.cc:3055-3099,3879-3919 match() + the orientation / position gates of TrackWithMotionModel
                                               and SearchLocalLines (loop bodies wrapped in two functions)
                Thirdparty/line_descriptor/src/binary_descriptor_custom.cpp:42-687,1026-1372
@@ -64,7 +67,14 @@ def generate():
              + lines("src/Frame.cc", 976, 1307)
              + "\n// ORBmatcher::SearchByBoW (src/ORBmatcher.cc:269-471) and ComputeThreeMaxima (:2449-2490)\n"
              + lines("src/ORBmatcher.cc", 269, 471) + lines("src/ORBmatcher.cc", 2449, 2490)
+             + "\n// the SearchByProjection overloads: local map (:44-214 with RadiusByViewingCos :216-222), loop closing (:473-586),\n"
+             "// frame to frame (:2179-2323), relocalisation (:2325-2447)\n"
+             + lines("src/ORBmatcher.cc", 44, 222) + lines("src/ORBmatcher.cc", 473, 586) + lines("src/ORBmatcher.cc", 2179, 2447)
+             + "\n// Frame::AssignFeaturesToGrid (src/Frame.cc:451-482), GetFeaturesInArea (:774-843), PosInGrid (:845-855);\n"
+             "// KeyFrame::GetFeaturesInArea, IsInImage (src/KeyFrame.cc:881-930)\n"
+             + lines("src/Frame.cc", 451, 482) + lines("src/Frame.cc", 774, 855) + lines("src/KeyFrame.cc", 881, 930)
              + "\nfloat Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;\n"
+             "float Frame::fx, Frame::fy, Frame::cx, Frame::cy, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;\n"
              "// Tracking::TrackWithMotionModel, line half: src/Tracking.cc:3055-3099\n"
              "int ref_track_gate_f2f(Frame& mCurrentFrame, Frame& mLastFrame, std::vector<int>& matches_out) {\n"
              + lines("src/Tracking.cc", 3055, 3099)

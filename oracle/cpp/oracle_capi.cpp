@@ -453,7 +453,8 @@ PLF_API int plf_cpu_bow_build_vectors(const int32_t* word_id, const double* weig
 }
 
 // ---- ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, ...) (src/ORBmatcher.cc:44-130), Nleft == -1 ----
-// parity unpinned (no runnable reference: MapPoint / Frame state); the loops follow the reference line by line.
+// pinned: tests/test_oracle_ref.py runs the reference's own function (oracle/_ref, src/ORBmatcher.cc:44-214 on a grid filled by
+// its AssignFeaturesToGrid) on the same map points and demands equality; the loops follow the reference line by line.
 PLF_API int plf_cpu_search_by_projection(plf_ctx* c, int slot, const plf_proj_query* queries, int n_queries, float th, float nn_ratio,
                                          int th_high, uint8_t* occupied, int n_features, int32_t* match, int* n_matches) {
     if (!c || slot < 0 || slot >= (int)c->slots.size() || !queries || n_queries < 0 || !occupied || !match)
@@ -530,7 +531,7 @@ PLF_API int plf_cpu_search_by_projection(plf_ctx* c, int slot, const plf_proj_qu
 
 // ---- ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono, match12) (src/ORBmatcher.cc:2179-2323)
 // from the projected points on: window search, best distance, assignment, rotation histogram, ComputeThreeMaxima (:2449-2490).
-// parity unpinned, like the local-map overload above.
+// pinned like the local-map overload above (oracle/_ref runs src/ORBmatcher.cc:2179-2323 itself, all three motion cases).
 PLF_API int plf_cpu_search_by_projection_frame(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, int th_high,
                                                int check_orientation, uint8_t* occupied, int n_features, int32_t* feat_query,
                                                int32_t* match12, int* n_matches) {
@@ -682,7 +683,7 @@ void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, in
 }  // namespace
 
 // ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:2325-2447,
-// from the projected points on.  parity unpinned (needs MapPoint / KeyFrame state); cross-checked by a Python restatement.
+// from the projected points on.  Pinned to the reference's own function in tests/test_oracle_ref.py (oracle/_ref).
 PLF_API int plf_cpu_search_by_projection_reloc(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, int orb_dist,
                                                int check_orientation, uint8_t* occupied, int n_features, int32_t* feat_query,
                                                int* n_matches) {
@@ -739,8 +740,8 @@ PLF_API int plf_cpu_search_by_projection_reloc(plf_ctx* c, int slot, const plf_f
     return PLF_OK;
 }
 
-// ORBmatcher::SearchByProjection(KeyFrame* pKF, Scw, vpPoints, vpMatched, th, ratioHamming), src/ORBmatcher.cc:473-580 (and
-// :582-704), from the projected points on.  parity unpinned, as above.
+// ORBmatcher::SearchByProjection(KeyFrame* pKF, Scw, vpPoints, vpMatched, th, ratioHamming), src/ORBmatcher.cc:473-586 (and
+// :588-704), from the projected points on.  Pinned to the reference's own function (:473-586) in tests/test_oracle_ref.py.
 PLF_API int plf_cpu_search_by_projection_loop(plf_ctx* c, int slot, const plf_frame_query* queries, int n_queries, int th_low,
                                               float ratio_hamming, uint8_t* occupied, int n_features, int32_t* feat_query,
                                               int* n_matches) {

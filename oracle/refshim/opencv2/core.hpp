@@ -85,6 +85,12 @@ typedef Point_<int> Point2i;
 typedef Point_<int> Point;
 typedef Point_<float> Point2f;
 typedef Point_<double> Point2d;
+template <typename T> struct Point3_ {
+    T x, y, z;
+    Point3_() : x(0), y(0), z(0) {}
+    Point3_(T x_, T y_, T z_) : x(x_), y(y_), z(z_) {}
+};
+typedef Point3_<float> Point3f;
 
 template <typename T> struct Size_ {
     T width, height;
@@ -175,6 +181,21 @@ public:
     Mat rowRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * step; m.rows = b - a; return m; }
     Mat colRange(int a, int b) const { Mat m(*this); m.data = data + (size_t)a * elemSize(); m.cols = b - a; return m; }
     Mat row(int i) const { return rowRange(i, i + 1); }
+    Mat col(int i) const { return colRange(i, i + 1); }
+    // CV_32F small-matrix algebra of the pose code in src/ORBmatcher.cc (3x3 / 3x1 / 4x4): plain float loops.  The pins
+    // that go through it use identity rotations and exactly representable operands, so no rounding rule is at stake.
+    Mat t() const {
+        Mat m(cols, rows, type_);
+        for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) m.at<float>(x, y) = at<float>(y, x);
+        return m;
+    }
+    double dot(const Mat& o) const {
+        double acc = 0;
+        for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) acc += (double)at<float>(y, x) * (double)o.at<float>(y, x);
+        return acc;
+    }
+    template <typename T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+    template <typename T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
     Mat operator()(const Rect& r) const { return rowRange(r.y, r.y + r.height).colRange(r.x, r.x + r.width); }
     uchar* ptr(int i = 0) { return data + (size_t)i * step; }
     const uchar* ptr(int i = 0) const { return data + (size_t)i * step; }
@@ -245,6 +266,36 @@ static inline Mat operator-(const Mat& a, double s) {
     }
     return out;
 }
+
+static inline Mat operator*(const Mat& a, const Mat& b) {
+    if (a.cols != b.rows || a.depth() != CV_32F || b.depth() != CV_32F) throw std::runtime_error("cvshim: Mat * Mat shape / depth");
+    Mat out(a.rows, b.cols, CV_32F);
+    for (int y = 0; y < a.rows; y++) for (int x = 0; x < b.cols; x++) {
+        float acc = 0.f;
+        for (int k = 0; k < a.cols; k++) acc += a.at<float>(y, k) * b.at<float>(k, x);
+        out.at<float>(y, x) = acc;
+    }
+    return out;
+}
+static inline Mat cvshim_zip(const Mat& a, const Mat& b, float sa, float sb) {
+    if (a.rows != b.rows || a.cols != b.cols || a.depth() != CV_32F || b.depth() != CV_32F) throw std::runtime_error("cvshim: Mat +- Mat shape / depth");
+    Mat out(a.rows, a.cols, CV_32F);
+    for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) out.at<float>(y, x) = sa * a.at<float>(y, x) + sb * b.at<float>(y, x);
+    return out;
+}
+static inline Mat operator+(const Mat& a, const Mat& b) { return cvshim_zip(a, b, 1.f, 1.f); }
+static inline Mat operator-(const Mat& a, const Mat& b) { return cvshim_zip(a, b, 1.f, -1.f); }
+static inline Mat operator-(const Mat& a) {
+    Mat out(a.rows, a.cols, CV_32F);
+    for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) out.at<float>(y, x) = -a.at<float>(y, x);
+    return out;
+}
+static inline Mat operator/(const Mat& a, double s) {
+    Mat out(a.rows, a.cols, CV_32F);
+    for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) out.at<float>(y, x) = (float)(a.at<float>(y, x) / s);
+    return out;
+}
+static inline double norm(const Mat& a) { return std::sqrt(a.dot(a)); }
 
 // cv::norm(a, b, NORM_L1) for CV_16S / CV_8U / CV_32F (src/Frame.cc:1098).
 static inline double norm(const Mat& a, const Mat& b, int normType) {

@@ -396,6 +396,224 @@ REF_API int ref_track_lines_local(const uint8_t* d1, const float* proj1 /* n1 x 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The four ORBmatcher::SearchByProjection overloads (src/ORBmatcher.cc:44-214, 473-586, 2179-2323, 2325-2447) on a Frame /
+// KeyFrame whose grid was filled by the reference's own AssignFeaturesToGrid.  A query is a plf_frame_query-shaped record
+// (u, v, ur, radius, min_level, max_level, skip, has_observations, angle, desc[32], pad) = 18 ints; the map point behind
+// it is placed at (u z, v z, z) with z a power of two and the camera is the unit pinhole, poses are identities, so the
+// reference's own projection code yields exactly (u, v).
+namespace {
+struct RefQuery { float u, v, ur, radius; int min_level, max_level, skip, has_observations; float angle; uint8_t desc[32]; int pad; };
+static_assert(sizeof(RefQuery) == 72, "same layout as plf_frame_query");
+
+struct RefScene {
+    Frame F;
+    GeometricCamera cam;
+    std::vector<MapPoint> holders;      // what F.mvpMapPoints points at before the call (one per feature)
+    void build(const cv::KeyPoint* kp, const uint8_t* desc, const float* uRight, int N, int W, int H, const float* scale, int nLevels,
+               const uint8_t* occupied /* 0 none, 1 holder with observations, 2 holder without */) {
+        Frame::mnMinX = 0; Frame::mnMaxX = (float)W; Frame::mnMinY = 0; Frame::mnMaxY = (float)H;
+        Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);   // src/Frame.cc:183-184
+        Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(Frame::mnMaxY - Frame::mnMinY);
+        Frame::fx = 1; Frame::fy = 1; Frame::cx = 0; Frame::cy = 0;
+        F.N = N;
+        F.Nleft = -1;
+        F.mvKeys.assign(kp, kp + N);
+        F.mvKeysUn = F.mvKeys;
+        F.mvuRight.assign(uRight, uRight + N);
+        F.mDescriptors = wrap_desc(desc, N);
+        F.mvScaleFactors.assign(scale, scale + nLevels);
+        F.mpCamera = &cam;
+        F.mTcw = cv::Mat::zeros(4, 4, CV_32F);
+        for (int i = 0; i < 4; i++) F.mTcw.at<float>(i, i) = 1.f;
+        holders.assign(N, MapPoint());
+        F.mvpMapPoints.assign(N, nullptr);
+        for (int i = 0; i < N; i++) if (occupied && occupied[i]) { holders[i].nObs = occupied[i] == 1 ? 1 : 0; F.mvpMapPoints[i] = &holders[i]; }
+        F.AssignFeaturesToGrid();
+    }
+};
+MapPoint make_point(const RefQuery& q, float z) {
+    MapPoint p;
+    p.mWorldPos = cv::Mat(3, 1, CV_32F);
+    p.mWorldPos.at<float>(0) = q.u * z; p.mWorldPos.at<float>(1) = q.v * z; p.mWorldPos.at<float>(2) = z;
+    p.mNormalVector = p.mWorldPos.clone();      // PO.dot(Pn) = |PO|^2 >= 0.5 |PO|
+    p.mDescriptor = cv::Mat(1, 32, CV_8UC1);
+    memcpy(p.mDescriptor.data, q.desc, 32);
+    p.nObs = q.has_observations ? 1 : 0;
+    return p;
+}
+}  // namespace
+
+// mGrid as CSR (cell = ix * 48 + iy) and one GetFeaturesInArea lookup, for the pin of plf_feature_grid / plf_features_in_area
+REF_API int ref_feature_grid(const cv::KeyPoint* kp, int N, int W, int H, int* cellStart /* 64*48+1 */, int* cellIdx /* N */,
+                             float x, float y, float r, int minLevel, int maxLevel, int* area, int areaCap) {
+    return guarded([&] {
+        RefScene sc;
+        std::vector<uint8_t> d((size_t)std::max(N, 1) * 32, 0);
+        std::vector<float> ur((size_t)std::max(N, 1), -1.f), scale(8, 1.f);
+        sc.build(kp, d.data(), ur.data(), N, W, H, scale.data(), 8, nullptr);
+        int n = 0;
+        for (int ix = 0; ix < FRAME_GRID_COLS; ix++) for (int iy = 0; iy < FRAME_GRID_ROWS; iy++) {
+            cellStart[ix * FRAME_GRID_ROWS + iy] = n;
+            for (size_t v : sc.F.mGrid[ix][iy]) cellIdx[n++] = (int)v;
+        }
+        cellStart[FRAME_GRID_COLS * FRAME_GRID_ROWS] = n;
+        const std::vector<size_t> a = sc.F.GetFeaturesInArea(x, y, r, minLevel, maxLevel);
+        for (size_t i = 0; i < a.size() && (int)i < areaCap; i++) area[i] = (int)a[i];
+        return (int)a.size();
+    });
+}
+
+// SearchByProjection(Frame& F, const vector<MapPoint*>&, th, bFarPoints = false) — the local-map search (:44-214).
+// q: level = max_level, view cosine in `angle`, projection (u, v, ur); skip = not in view.  occupied in/out as in the product.
+REF_API int ref_sbp_local(const cv::KeyPoint* kp, const uint8_t* desc, const float* uRight, int N, int W, int H, const float* scale,
+                          int nLevels, const RefQuery* q, int nq, float th, float nnratio, uint8_t* occupied, int* match) {
+    return guarded([&] {
+        RefScene sc;
+        sc.build(kp, desc, uRight, N, W, H, scale, nLevels, occupied);
+        std::vector<MapPoint> pts(nq);
+        std::vector<MapPoint*> vp(nq);
+        for (int i = 0; i < nq; i++) {
+            pts[i] = make_point(q[i], 1.f);
+            pts[i].mbTrackInView = !q[i].skip;
+            pts[i].mnTrackScaleLevel = q[i].max_level;
+            pts[i].mTrackViewCos = q[i].angle;
+            pts[i].mTrackProjX = q[i].u; pts[i].mTrackProjY = q[i].v; pts[i].mTrackProjXR = q[i].ur;
+            pts[i].nObs = 1;                                   // map points of the local map have observations
+            vp[i] = &pts[i];
+        }
+        ORBmatcher matcher(nnratio, true);
+        const int n = matcher.SearchByProjection(sc.F, vp, th);
+        for (int i = 0; i < nq; i++) match[i] = -1;
+        for (int f = 0; f < N; f++) {
+            MapPoint* h = sc.F.mvpMapPoints[f];
+            const bool mine = h && h >= pts.data() && h < pts.data() + nq;
+            if (mine) match[h - pts.data()] = f;
+            occupied[f] = h ? (h->Observations() > 0 ? 1 : 0) : 0;
+        }
+        return n;
+    });
+}
+
+// SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono, match12) — TrackWithMotionModel (:2179-2323).
+// The last frame carries one map point per query; radius = th * scale[octave] is formed by the reference from
+// q.max_level (octave) — direction: 0 around, 1 forward (LastFrame.mTcw z-translation > mb), 2 backward.
+REF_API int ref_sbp_frame(const cv::KeyPoint* kp, const uint8_t* desc, const float* uRight, int N, int W, int H, const float* scale,
+                          int nLevels, const RefQuery* q, const int* octave, const float* zs, int nq, float th, int direction, float mbf,
+                          int checkOri, uint8_t* occupied, int* featQuery, int* match12) {
+    return guarded([&] {
+        RefScene sc;
+        sc.build(kp, desc, uRight, N, W, H, scale, nLevels, occupied);
+        sc.F.mb = 0.5f; sc.F.mbf = mbf;
+        Frame last;
+        last.N = nq;
+        last.mTcw = cv::Mat::zeros(4, 4, CV_32F);
+        for (int i = 0; i < 4; i++) last.mTcw.at<float>(i, i) = 1.f;
+        last.mTcw.at<float>(2, 3) = direction == 1 ? 1.f : (direction == 2 ? -1.f : 0.f);
+        std::vector<MapPoint> pts(nq);
+        last.mvpMapPoints.assign(nq, nullptr);
+        last.mvbOutlier.assign(nq, false);
+        last.mvKeys.resize(nq);
+        last.mvKeysUn.resize(nq);
+        for (int i = 0; i < nq; i++) {
+            pts[i] = make_point(q[i], zs[i]);
+            if (!q[i].skip) last.mvpMapPoints[i] = &pts[i];
+            last.mvKeys[i].octave = octave[i];
+            last.mvKeysUn[i].angle = q[i].angle;
+        }
+        std::map<int, int> m12;
+        ORBmatcher matcher(0.9f, checkOri != 0);
+        const int n = matcher.SearchByProjection(sc.F, last, th, false, m12);
+        for (int f = 0; f < N; f++) {
+            MapPoint* h = sc.F.mvpMapPoints[f];
+            const bool mine = h && h >= pts.data() && h < pts.data() + nq;
+            featQuery[f] = mine ? (int)(h - pts.data()) : -1;
+            occupied[f] = h ? (h->Observations() > 0 ? 1 : 0) : 0;
+            match12[f] = -1;
+        }
+        for (auto& kv : m12) match12[kv.first] = kv.second;
+        return n;
+    });
+}
+
+// SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist) — relocalisation (:2325-2447).
+// q.max_level - 1 = the predicted level (the window is [pred - 1, pred + 1]); skip 1 = no map point, 2 = already found.
+REF_API int ref_sbp_reloc(const cv::KeyPoint* kp, const uint8_t* desc, const float* uRight, int N, int W, int H, const float* scale,
+                          int nLevels, const RefQuery* q, const float* zs, int nq, float th, int orbDist, int checkOri, uint8_t* occupied,
+                          int* featQuery) {
+    return guarded([&] {
+        RefScene sc;
+        sc.build(kp, desc, uRight, N, W, H, scale, nLevels, occupied);
+        KeyFrame kf;
+        std::vector<MapPoint> pts(nq);
+        kf.mvpMapPoints.assign(nq, nullptr);
+        kf.mvKeysUn.resize(nq);
+        std::set<MapPoint*> found;
+        for (int i = 0; i < nq; i++) {
+            pts[i] = make_point(q[i], zs[i]);
+            pts[i].mnPredictedLevel = q[i].max_level - 1;
+            if (q[i].skip != 1) kf.mvpMapPoints[i] = &pts[i];
+            if (q[i].skip == 2) found.insert(&pts[i]);
+            if (q[i].skip == 3) pts[i].mbBad = true;
+            kf.mvKeysUn[i].angle = q[i].angle;
+        }
+        ORBmatcher matcher(0.9f, checkOri != 0);
+        const int n = matcher.SearchByProjection(sc.F, &kf, found, th, orbDist);
+        for (int f = 0; f < N; f++) {
+            MapPoint* h = sc.F.mvpMapPoints[f];
+            const bool mine = h && h >= pts.data() && h < pts.data() + nq;
+            featQuery[f] = mine ? (int)(h - pts.data()) : -1;
+            occupied[f] = h ? 1 : 0;
+        }
+        return n;
+    });
+}
+
+// SearchByProjection(KeyFrame* pKF, cv::Mat Scw, vpPoints, vpMatched, th, ratioHamming) — loop closing (:473-586); the
+// frame's features play the keyframe.  q.max_level = the predicted level; skip 1 = bad point, 2 = already in vpMatched.
+REF_API int ref_sbp_loop(const cv::KeyPoint* kp, const uint8_t* desc, int N, int W, int H, const float* scale, int nLevels,
+                         const RefQuery* q, const float* zs, int nq, int th, float ratioHamming, uint8_t* occupied, int* featQuery) {
+    return guarded([&] {
+        RefScene sc;
+        std::vector<float> ur((size_t)std::max(N, 1), -1.f);
+        sc.build(kp, desc, ur.data(), N, W, H, scale, nLevels, nullptr);
+        KeyFrame kf;
+        GeometricCamera cam;
+        kf.mpCamera = &cam;
+        kf.N = N;
+        kf.mvKeysUn = sc.F.mvKeysUn;
+        kf.mDescriptors = sc.F.mDescriptors;
+        kf.mvScaleFactors = sc.F.mvScaleFactors;
+        kf.mnMinX = 0; kf.mnMinY = 0; kf.mnMaxX = W; kf.mnMaxY = H;
+        kf.mfGridElementWidthInv = Frame::mfGridElementWidthInv; kf.mfGridElementHeightInv = Frame::mfGridElementHeightInv;
+        kf.mGrid.assign(FRAME_GRID_COLS, std::vector<std::vector<size_t> >(FRAME_GRID_ROWS));       // KeyFrame::KeyFrame copies F.mGrid
+        for (int i = 0; i < FRAME_GRID_COLS; i++) for (int j = 0; j < FRAME_GRID_ROWS; j++) kf.mGrid[i][j] = sc.F.mGrid[i][j];
+        std::vector<MapPoint> pts(nq), old(N);
+        std::vector<MapPoint*> vp(nq), matched(N, nullptr);
+        for (int f = 0; f < N; f++) if (occupied[f]) matched[f] = &old[f];
+        for (int i = 0; i < nq; i++) {
+            pts[i] = make_point(q[i], zs[i]);
+            pts[i].mnPredictedLevel = q[i].max_level;
+            pts[i].mbBad = q[i].skip == 1;
+            vp[i] = &pts[i];
+        }
+        // "already found": such a point sits in vpMatched before the call
+        int slot = 0;
+        for (int i = 0; i < nq; i++) if (q[i].skip == 2) { while (slot < N && !occupied[slot]) ++slot; if (slot < N) matched[slot++] = &pts[i]; }
+        cv::Mat Scw = cv::Mat::zeros(4, 4, CV_32F);
+        for (int i = 0; i < 4; i++) Scw.at<float>(i, i) = 1.f;
+        ORBmatcher matcher(0.75f, true);
+        const int n = matcher.SearchByProjection(&kf, Scw, vp, matched, th, ratioHamming);
+        for (int f = 0; f < N; f++) {
+            MapPoint* h = matched[f];
+            const bool mine = h && h >= pts.data() && h < pts.data() + nq && q[h - pts.data()].skip != 2;
+            featQuery[f] = mine ? (int)(h - pts.data()) : -1;
+            occupied[f] = h ? 1 : 0;
+        }
+        return n;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // The stereo Frame constructor of the reference as a timed unit (bench.py --impl reference / cpu_baseline): four
 // threads per pair — ExtractORB(left), ExtractORB(right), ExtractLine(left), ExtractLine(right), src/Frame.cc:128-135 —
 // join, ComputeStereoMatches_Lines, ComputeStereoMatches (:160-163).  One handle per worker; handles share nothing but

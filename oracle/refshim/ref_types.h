@@ -12,6 +12,7 @@
 #include <climits>
 #include <list>
 #include <map>
+#include <set>
 #include <thread>
 #include <vector>
 #include "Auxiliar.h"        // the reference's own header (using-directives for cv / line_descriptor / std / Eigen)
@@ -32,21 +33,49 @@ class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
 }
 namespace ORB_SLAM3 {
 
-class GeometricCamera {};
+// a pinhole with fx = fy = 1, cx = cy = 0: the pins choose world points (u z, v z, z) with z a power of two, so the
+// projection is exactly the (u, v) the test prescribes
+class GeometricCamera {
+public:
+    cv::Point2f project(const cv::Mat& m) { return cv::Point2f(m.at<float>(0) / m.at<float>(2), m.at<float>(1) / m.at<float>(2)); }
+    cv::Point2f project(const cv::Point3f& p) { return cv::Point2f(p.x / p.z, p.y / p.z); }
+};
+class Frame;
+class KeyFrame;
 class MapPoint {
 public:
     bool isBad() { return mbBad; }
-    bool mbBad = false;
+    int Observations() { return nObs; }
+    cv::Mat GetDescriptor() { return mDescriptor.clone(); }
+    cv::Mat GetWorldPos() { return mWorldPos.clone(); }
+    cv::Mat GetNormal() { return mNormalVector.clone(); }
+    float GetMinDistanceInvariance() { return mfMinDistance; }
+    float GetMaxDistanceInvariance() { return mfMaxDistance; }
+    int PredictScale(const float&, Frame*) { return mnPredictedLevel; }      // the level the test prescribes
+    int PredictScale(const float&, KeyFrame*) { return mnPredictedLevel; }
+    bool mbBad = false, mbTrackInView = false, mbTrackInViewR = false;
+    int nObs = 0, mnTrackScaleLevel = 0, mnTrackScaleLevelR = 0, mnPredictedLevel = 0;
+    float mTrackDepth = 0, mTrackViewCos = 0, mTrackViewCosR = 0, mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackProjYR = 0;
+    float mfMinDistance = 0.f, mfMaxDistance = 3.0e38f;
+    cv::Mat mDescriptor, mWorldPos, mNormalVector;
 };
 class KeyFrame {
 public:
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;
+    bool IsInImage(const float& x, const float& y) const;
     std::vector<MapPoint*> mvpMapPoints;
     DBoW2::FeatureVector mFeatVec;
     cv::Mat mDescriptors;
     std::vector<cv::KeyPoint> mvKeysUn, mvKeys, mvKeysRight;
-    GeometricCamera* mpCamera2 = nullptr;
-    int NLeft = -1;
+    GeometricCamera *mpCamera = nullptr, *mpCamera2 = nullptr;
+    int NLeft = -1, N = 0;
+    float fx = 1, fy = 1, cx = 0, cy = 0;
+    int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
+    float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;                 // include/KeyFrame.h: const int
+    std::vector<std::vector<std::vector<size_t> > > mGrid, mGridRight;
+    std::vector<float> mvScaleFactors;
 };
 class MapLine {
 public:
@@ -63,6 +92,13 @@ public:
     ORBmatcher(float nnratio = 0.6, bool checkOri = true);
     static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
     int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches);
+    int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3, const bool bFarPoints = false,
+                           const float thFarPoints = 50.0f);
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono, std::map<int, int>& match12);
+    int SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist);
+    int SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th,
+                           float ratioHamming = 1.0);
+    float RadiusByViewingCos(const float& viewCos);
     void ComputeThreeMaxima(std::vector<int>* histo, const int L, int& ind1, int& ind2, int& ind3);
     static const int TH_LOW;
     static const int TH_HIGH;
@@ -108,6 +144,17 @@ public:
     std::vector<KeyLine> mvKeysUn_Line;
     int n_inliers_ls = 0;
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+    // members read by the SearchByProjection overloads and the feature grid (include/Frame.h:196-264)
+    void AssignFeaturesToGrid();
+    bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
+    std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1, const int maxLevel = -1,
+                                          const bool bRight = false) const;
+    cv::Mat mTcw;
+    static float fx, fy, cx, cy, mfGridElementWidthInv, mfGridElementHeightInv;
+    std::vector<bool> mvbOutlier;
+    std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
+    GeometricCamera* mpCamera = nullptr;
+    std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS], mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
 };
 
 // the two loops of the tracking thread, generated from src/Tracking.cc by oracle/build_ref.py

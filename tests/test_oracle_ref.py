@@ -607,3 +607,145 @@ def test_tracking_line_gates_equal_reference(ref, oracle, plf, mode):
                 assert gn == nref and np.array_equal(gm, m) and np.array_equal(ga, a), (seed, rep, bounds)
                 total += nref
     assert total > 1000
+
+
+# ---- the four SearchByProjection overloads and the feature grid against the reference's own function bodies -----------
+def _scene(plf, oracle, seed):
+    f = plf.Frontend(oracle, max_batch=1)
+    L, R = plf.synth_pair(752, 480, seed)
+    res = f.frontend_batch(L[None], R[None])
+    n = int(res.n_kp_left[0])
+    kps = np.ascontiguousarray(res.kp_left[0, :n]); desc = np.ascontiguousarray(res.desc_left[0, :n])
+    ur = np.ascontiguousarray(res.u_right[0, :n])
+    scale = f.scale_tables()[0]
+    return f, res, n, kps, desc, ur, np.ascontiguousarray(scale)
+
+
+def test_feature_grid_and_area_lookup_equal_reference(ref, oracle, plf):
+    """Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea (src/Frame.cc:451-482,774-855, compiled from the
+    reference): mGrid as CSR and 200 window lookups equal plf_cpu_feature_grid / plf_features_in_area."""
+    for seed in (700, 701, 702):
+        f, res, n, kps, desc, ur, scale = _scene(plf, oracle, seed)
+        st, ix = f.feature_grid(0, 1)
+        rng = np.random.default_rng(seed)
+        cs = np.zeros(64 * 48 + 1, np.int32); ci = np.zeros(n, np.int32); area = np.zeros(n + 1, np.int32)
+        for k in range(200):
+            x, y, r = float(rng.uniform(-30, 790)), float(rng.uniform(-30, 510)), float(rng.choice([3.0, 12.5, 40.0, 300.0]))
+            lo, hi = [(-1, -1), (0, 3), (2, -1), (1, 1), (-1, 0)][k % 5]
+            na = ref.ref_feature_grid(P(kps), n, 752, 480, P(cs), P(ci), C.c_float(x), C.c_float(y), C.c_float(r), lo, hi, P(area), n + 1)
+            assert na >= 0, ref.ref_last_error()
+            got = f.features_in_area(kps, st[0], ix[0], x, y, r, lo, hi)
+            assert list(got) == list(area[:na]), (seed, k)
+        assert np.array_equal(cs, st[0]) and np.array_equal(ci[:cs[-1]], ix[0, :cs[-1]])
+
+
+def _inside(q, fx="u", fy="v"):
+    """The reference drops projections outside the image bounds itself; the C ABI leaves that to the caller (skip)."""
+    return (q[fx] > 1) & (q[fx] < 751) & (q[fy] > 1) & (q[fy] < 479)
+
+
+@pytest.mark.parametrize("th", [1.0, 3.0])
+def test_search_by_projection_local_map_equals_reference(ref, oracle, plf, th):
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:44-214, compiled from the
+    reference, on a grid filled by the reference's AssignFeaturesToGrid) against plf_cpu_search_by_projection."""
+    from test_host_logic import _proj_queries
+    for seed in (710, 711, 712, 713):
+        f, res, n, kps, desc, ur, scale = _scene(plf, oracle, seed)
+        rng = np.random.default_rng(seed)
+        q = _proj_queries(plf, res, 0, rng)
+        occ0 = (rng.random(n) < 0.1).astype(np.uint8)
+        rq = np.zeros(len(q), plf.FRAME_QUERY_DT)
+        rq["u"], rq["v"], rq["ur"], rq["angle"] = q["proj_x"], q["proj_y"], q["proj_xr"], q["view_cos"]
+        rq["max_level"], rq["skip"], rq["desc"] = q["level"], q["skip"], q["desc"]
+        oa, ob = occ0.copy(), occ0.copy()
+        want = np.zeros(len(q), np.int32)
+        nref = ref.ref_sbp_local(P(kps), P(desc), P(ur), n, 752, 480, P(scale), 8, P(rq), len(q), C.c_float(th), C.c_float(0.8), P(oa), P(want))
+        assert nref >= 0, ref.ref_last_error()
+        got, ngot = f.search_by_projection(q, ob, th=th, nn_ratio=0.8)
+        assert ngot == nref and np.array_equal(got, want) and np.array_equal(oa, ob), seed
+        assert nref > 300
+
+
+@pytest.mark.parametrize("direction,check", [(0, 1), (1, 1), (2, 0)])
+def test_search_by_projection_frame_equals_reference(ref, oracle, plf, direction, check):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono, match12) (src/ORBmatcher.cc:2179-2323) run by the
+    reference's own code — projection through identity poses and the unit pinhole, forward / backward decided by its own
+    tlc test — against plf_cpu_search_by_projection_frame on the same projected points."""
+    from test_host_logic import _frame_queries
+    f32 = np.float32
+    for seed in (720, 721, 722):
+        f, res, n, kps, desc, ur, scale = _scene(plf, oracle, seed)
+        rng = np.random.default_rng(seed + direction)
+        q = _frame_queries(plf, res, 0, rng, ["around", "forward", "backward"][direction])
+        q = q[_inside(q)]
+        octave = (q["min_level"] if direction == 1 else q["max_level"] if direction == 2 else q["min_level"] + 1).astype(np.int32)
+        th, mbf = f32(7.0), f32(47.9)
+        zs = rng.choice(np.array([0.5, 1.0, 2.0, 4.0], f32), len(q))
+        q["radius"] = th * scale[octave]
+        q["ur"] = q["u"] - mbf * (f32(1.0) / zs)
+        occ0 = rng.choice(np.array([0, 0, 0, 0, 0, 0, 0, 0, 1, 2], np.uint8), n)      # 2: a holder without observations does not block
+        oa = occ0.copy(); ob = (occ0 == 1).astype(np.uint8)
+        fq_ref = np.zeros(n, np.int32); m12_ref = np.zeros(n, np.int32)
+        nref = ref.ref_sbp_frame(P(kps), P(desc), P(ur), n, 752, 480, P(scale), 8, P(q), P(octave), P(zs), len(q), C.c_float(th), direction,
+                                 C.c_float(mbf), check, P(oa), P(fq_ref), P(m12_ref))
+        assert nref >= 0, ref.ref_last_error()
+        fq, m12, ngot = f.search_by_projection_frame(q, ob, 100, bool(check))
+        # features that held a map point without observations before the call and were not re-assigned still hold it in the
+        # reference (featQuery -1 there too); nmatches counts assignments, so it is compared directly
+        assert ngot == nref and np.array_equal(fq, fq_ref) and np.array_equal(m12, m12_ref) and np.array_equal(oa, ob), seed
+        assert nref > 300
+
+
+@pytest.mark.parametrize("check", [1, 0])
+def test_search_by_projection_reloc_equals_reference(ref, oracle, plf, check):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:2325-2447)."""
+    from test_host_logic import _frame_queries
+    f32 = np.float32
+    for seed in (730, 731, 732):
+        f, res, n, kps, desc, ur, scale = _scene(plf, oracle, seed)
+        rng = np.random.default_rng(seed)
+        q = _frame_queries(plf, res, 0, rng, "around")
+        q = q[_inside(q)]
+        pred = (q["min_level"] + 1).astype(np.int32)
+        th = f32(10.0)
+        zs = rng.choice(np.array([0.5, 1.0, 2.0, 4.0], f32), len(q))
+        q["radius"] = th * scale[pred]
+        rq = q.copy()
+        rq["skip"] = np.where(q["skip"] != 0, rng.integers(1, 4, len(q)), 0)          # no map point / already found / bad
+        occ0 = (rng.random(n) < 0.1).astype(np.uint8)
+        oa, ob = occ0.copy(), occ0.copy()
+        fq_ref = np.zeros(n, np.int32)
+        nref = ref.ref_sbp_reloc(P(kps), P(desc), P(ur), n, 752, 480, P(scale), 8, P(rq), P(zs), len(q), C.c_float(th), 64, check, P(oa), P(fq_ref))
+        assert nref >= 0, ref.ref_last_error()
+        fq, ngot = f.search_by_projection_reloc(q, ob, 64, bool(check))
+        assert ngot == nref and np.array_equal(fq, fq_ref) and np.array_equal(oa, ob), seed
+        assert nref > 200
+
+
+@pytest.mark.parametrize("ratio", [1.0, 0.64])
+def test_search_by_projection_loop_equals_reference(ref, oracle, plf, ratio):
+    """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th, ratioHamming) (src/ORBmatcher.cc:473-586) with
+    KeyFrame::GetFeaturesInArea / IsInImage (src/KeyFrame.cc:881-930), all compiled from the reference."""
+    from test_host_logic import _frame_queries
+    f32 = np.float32
+    for seed in (740, 741, 742):
+        f, res, n, kps, desc, ur, scale = _scene(plf, oracle, seed)
+        rng = np.random.default_rng(seed)
+        q = _frame_queries(plf, res, 0, rng, "backward")
+        q = q[_inside(q)]
+        pred = q["max_level"].astype(np.int32)
+        q["min_level"] = pred - 1
+        th = 4
+        zs = rng.choice(np.array([0.5, 1.0, 2.0, 4.0], f32), len(q))
+        q["radius"] = f32(th) * scale[pred]
+        occ0 = (rng.random(n) < 0.1).astype(np.uint8)
+        rq = q.copy()
+        rq["skip"] = np.where(q["skip"] != 0, rng.integers(1, 3, len(q)), 0)          # bad / already found
+        assert int((rq["skip"] == 2).sum()) <= int(occ0.sum())
+        oa, ob = occ0.copy(), occ0.copy()
+        fq_ref = np.zeros(n, np.int32)
+        nref = ref.ref_sbp_loop(P(kps), P(desc), n, 752, 480, P(scale), 8, P(rq), P(zs), len(q), th, C.c_float(ratio), P(oa), P(fq_ref))
+        assert nref >= 0, ref.ref_last_error()
+        fq, ngot = f.search_by_projection_loop(q, ob, 50, ratio)
+        assert ngot == nref and np.array_equal(fq, fq_ref) and np.array_equal(oa, ob), seed
+        assert nref > 100

@@ -5,6 +5,8 @@
 What is compiled, unmodified:
   whole files  src/ORBextractor.cc  src/LineExtractor.cc  src/LineMatcher.cpp  src/gridStructure.cpp
                src/LineIterator.cpp  src/Config.cpp  Thirdparty/line_descriptor/src/LSDDetector_custom.cpp
+               Thirdparty/DBoW2/DBoW2/{FORB,BowVector,FeatureVector,ScoringObject}.cpp  Thirdparty/DBoW2/DUtils/*.cpp
+               (+ the header-only TemplatedVocabulary.h, instantiated for FORB in refshim/ref_capi.cpp)
   line ranges  (written at build time to oracle/_ref/gen/, never committed)
                src/Frame.cc:976-1307          ComputeStereoMatches, ComputeStereoMatches_Lines,
                                               lineSegmentOverlapStereo, filterLineSegmentDisparity
@@ -39,12 +41,19 @@ SHIM = os.path.join(HERE, "refshim")
 LD = os.path.join(REF, "Thirdparty", "line_descriptor")
 
 WHOLE = ["src/ORBextractor.cc", "src/LineExtractor.cc", "src/LineMatcher.cpp", "src/gridStructure.cpp",
-         "src/LineIterator.cpp", "src/Config.cpp", "Thirdparty/line_descriptor/src/LSDDetector_custom.cpp"]
+         "src/LineIterator.cpp", "src/Config.cpp", "Thirdparty/line_descriptor/src/LSDDetector_custom.cpp",
+         # DBoW2 as vendored by the reference (bag-of-words transform of Frame::ComputeBoW): the whole library
+         "Thirdparty/DBoW2/DBoW2/FORB.cpp", "Thirdparty/DBoW2/DBoW2/BowVector.cpp", "Thirdparty/DBoW2/DBoW2/FeatureVector.cpp",
+         "Thirdparty/DBoW2/DBoW2/ScoringObject.cpp", "Thirdparty/DBoW2/DUtils/Random.cpp", "Thirdparty/DBoW2/DUtils/Timestamp.cpp"]
 ORACLE_PRIMS = ["cpp/prims.cpp", "cpp/orb.cpp", "cpp/lsd.cpp"]   # pinned OpenCV primitives (orb/lsd also carry oracle logic, unused here)
 
-CXX = os.environ.get("CXX", "g++")
+# The system compiler when it is there: this image's $CXX is a wrapper that links libstdc++ STATICALLY, and a second copy
+# of libstdc++ inside a dlopen'ed library breaks iostream extraction (locale facet ids are GNU-unique symbols shared with
+# the process's libstdc++.so.6) - DBoW2's loadFromTextFile parses with operator>>.
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else os.environ.get("CXX", "g++")
 BASE = ["-O2", "-std=c++14", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w", "-fvisibility=hidden"]
-INC = ["-I", SHIM, "-I", os.path.join(REF, "include"), "-I", os.path.join(LD, "include"), "-I", os.path.join(LD, "src")]
+INC = ["-I", SHIM, "-I", os.path.join(REF, "include"), "-I", os.path.join(LD, "include"), "-I", os.path.join(LD, "src"),
+       "-I", os.path.join(REF, "Thirdparty", "DBoW2"), "-I", os.path.join(REF, "Thirdparty", "DBoW2", "DBoW2")]
 # src/ files that reach include/Frame.h in the reference see ref_types.h instead (Frame / ORBmatcher / MapLine stand-ins);
 # the line_descriptor library is compiled exactly as its own CMakeLists does: its own precomp header, nothing else
 # (no using-directives leak in - that decides e.g. which atan2 overload LSDDetector_custom.cpp:297 binds to).
@@ -127,7 +136,7 @@ def build_one(LIB, OPT, objname, force=False):
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
         if src.startswith(HERE + os.sep + "cpp"):      # the oracle's own files: no reference headers, C++17
             flags = OPT + ["-std=c++17", "-fPIC", "-w", "-fvisibility=hidden", "-DPLF_ORACLE_BUILD"]
-        elif "line_descriptor" in src or src.endswith("lbd_ranges.cpp") or src.endswith("cvshim.cpp") \
+        elif "line_descriptor" in src or "DBoW2" in src or src.endswith("lbd_ranges.cpp") or src.endswith("cvshim.cpp") \
                 or os.path.basename(src) in ("gridStructure.cpp", "LineIterator.cpp", "Config.cpp"):
             flags = BASE + INC
         else:

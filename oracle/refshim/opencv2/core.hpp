@@ -15,6 +15,7 @@
 #include <memory>
 #include <vector>
 #include <string>
+#include <sstream>
 #include <map>
 #include <stdexcept>
 #include <algorithm>
@@ -353,6 +354,10 @@ public:
     bool empty() const { return type_ == NONE; }
     FileNode operator[](const char*) const { return FileNode(); }
     FileNode operator[](const std::string&) const { return FileNode(); }
+    // sequence access: named by DBoW2's YAML load() (TemplatedVocabulary.h:1660-1720), which oracle/_ref never calls
+    size_t size() const { return 0; }
+    FileNode operator[](unsigned int) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
     operator int() const { return type_ == NONE ? 0 : (int)std::lround(std::atof(s_.c_str())); }
     operator float() const { return type_ == NONE ? 0.f : (float)std::atof(s_.c_str()); }
     operator double() const { return type_ == NONE ? 0.0 : std::atof(s_.c_str()); }

@@ -8,6 +8,8 @@
 // (monotonically increasing addresses, the "most recently created node first" rule the oracle declares); ref_arena(0)
 // leaves them to malloc (whatever glibc does on this machine).
 #include "ref_types.h"
+#include "DBoW2/FORB.h"                  // the reference's own vendored DBoW2 (Thirdparty/DBoW2)
+#include "DBoW2/TemplatedVocabulary.h"
 #include <cstdlib>
 #include <new>
 #include <string>
@@ -392,6 +394,36 @@ REF_API int ref_track_lines_local(const uint8_t* d1, const float* proj1 /* n1 x 
         }
         if (nnr) *nnr = (float)Config::minRatio12L();
         return cnt;
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Frame::ComputeBoW (src/Frame.cc:858-870): mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4) by the reference's
+// own DBoW2 (TemplatedVocabulary<FORB::TDescriptor, FORB>, include/ORBVocabulary.h) on a vocabulary loaded with its own
+// loadFromTextFile (the ORBvoc.txt format).  Outputs: BowVector (word id ascending, value) and FeatureVector as CSR.
+REF_API int ref_bow_transform(const char* vocText, const uint8_t* desc, int n, int levelsup, int* bowWord, double* bowValue,
+                              int* fvNode, int* fvStart, int* fvFeat, int* nNodes) {
+    return guarded([&] {
+        typedef DBoW2::TemplatedVocabulary<DBoW2::FORB::TDescriptor, DBoW2::FORB> Vocabulary;
+        Vocabulary voc;
+        if (!voc.loadFromTextFile(vocText)) throw std::runtime_error("loadFromTextFile failed");
+        std::vector<cv::Mat> vCurrentDesc;
+        vCurrentDesc.reserve(n);
+        for (int i = 0; i < n; i++) vCurrentDesc.push_back(wrap_desc(desc + (size_t)i * 32, 1));   // Converter::toDescriptorVector
+        DBoW2::BowVector bv;
+        ::DBoW2::FeatureVector fv;
+        voc.transform(vCurrentDesc, bv, fv, levelsup);
+        int nw = 0;
+        for (auto& kv : bv) { bowWord[nw] = (int)kv.first; bowValue[nw] = kv.second; ++nw; }
+        int nn = 0, pos = 0;
+        for (auto& kv : fv) {
+            fvNode[nn] = (int)kv.first; fvStart[nn] = pos;
+            for (unsigned f : kv.second) fvFeat[pos++] = (int)f;
+            ++nn;
+        }
+        fvStart[nn] = pos;
+        *nNodes = nn;
+        return nw;
     });
 }
 

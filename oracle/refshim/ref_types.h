@@ -6,8 +6,8 @@
 // reference's own names (include/Frame.h:152-154,218-252,316,373-374; include/ORBmatcher.h:36-42,102-104).  The bodies of
 // ORBmatcher::SearchByBoW / ComputeThreeMaxima (src/ORBmatcher.cc:269-471,2449-2490) and the line-match gates of the
 // tracking thread (src/Tracking.cc:3055-3099,3879-3919) additionally need the KeyFrame / MapPoint / MapLine members and
-// the DBoW2::FeatureVector declared below (include/KeyFrame.h, include/MapPoint.h, include/MapLine.h,
-// Thirdparty/DBoW2/DBoW2/FeatureVector.h:24-27: a std::map<NodeId, std::vector<unsigned int>>).
+// DBoW2::FeatureVector (the reference's own header, Thirdparty/DBoW2/DBoW2/FeatureVector.h) declared below
+// (include/KeyFrame.h, include/MapPoint.h, include/MapLine.h).
 #pragma once
 #include <climits>
 #include <list>
@@ -27,10 +27,8 @@
 namespace ORB_SLAM3 {
 
 }  // namespace ORB_SLAM3
-namespace DBoW2 {
-typedef unsigned int NodeId;
-class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
-}
+#include "DBoW2/BowVector.h"      // the reference's own vendored DBoW2 (Thirdparty/DBoW2/DBoW2; boost::serialization is a stub)
+#include "DBoW2/FeatureVector.h"
 namespace ORB_SLAM3 {
 
 // a pinhole with fx = fy = 1, cx = cy = 0: the pins choose world points (u z, v z, z) with z a power of two, so the

@@ -749,3 +749,56 @@ def test_search_by_projection_loop_equals_reference(ref, oracle, plf, ratio):
         fq, ngot = f.search_by_projection_loop(q, ob, 50, ratio)
         assert ngot == nref and np.array_equal(fq, fq_ref) and np.array_equal(oa, ob), seed
         assert nref > 100
+
+
+# ---- bag of words against the reference's own DBoW2 ------------------------------------------------------------------
+def _write_vocabulary_text(path, voc, k):
+    """The ORBvoc.txt format of TemplatedVocabulary::loadFromTextFile (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1350-1433):
+    `k L scoring weighting`, then one line per node in id order: parent, is-leaf, 32 descriptor bytes, weight."""
+    n = len(voc["child_count"])
+    parent = np.zeros(n, np.int64)
+    for i in range(n):
+        for c in voc["child"][voc["child_first"][i]:voc["child_first"][i] + voc["child_count"][i]]:
+            parent[c] = i
+    with open(path, "w") as f:
+        f.write("%d %d 0 0" % (k, voc["levels"]))                  # L1_NORM, TF_IDF; no trailing newline after the last node either
+        for i in range(1, n):
+            f.write("\n%d %d %s %s" % (parent[i], int(voc["child_count"][i] == 0), " ".join(str(int(b)) for b in voc["desc"][i]),
+                                      repr(float(voc["weight"][i]))))
+
+
+@pytest.mark.parametrize("k,L,levelsup,ragged", [(10, 4, 2, 0.05), (6, 3, 0, 0.0), (10, 5, 4, 0.0), (4, 6, 3, 0.1)])
+def test_bow_transform_equals_reference_dbow2(ref, oracle, plf, tmp_path, k, L, levelsup, ragged):
+    """TemplatedVocabulary<FORB>::transform(features, BowVector&, FeatureVector&, levelsup) of the reference's vendored DBoW2
+    (compiled whole into oracle/_ref), on a vocabulary it loads itself from the ORBvoc.txt text format, against
+    plf_cpu_bow_transform + the plf_bow_build inline: word ids, L1-normalised TF-IDF values (bit for bit) and the
+    node -> feature lists equal; ragged trees and stopped words included."""
+    voc = plf.synth_vocabulary(k=k, L=L, seed=11 * k + L, ragged=ragged, stop=0.05)
+    path = str(tmp_path / "voc.txt")
+    _write_vocabulary_text(path, voc, k)
+    f = plf.Frontend(oracle, max_batch=1)
+    f.bow_set_vocabulary(0, voc)
+    for seed in (750, 751):
+        Lm, Rm = plf.synth_pair(752, 480, seed)
+        res = f.frontend_batch(Lm[None], Rm[None])
+        n = int(res.n_kp_left[0])
+        desc = np.ascontiguousarray(res.desc_left[0, :n])
+        bw = np.zeros(n + 1, np.int32); bv = np.zeros(n + 1, np.float64)
+        fn = np.zeros(n + 1, np.int32); fs = np.zeros(n + 2, np.int32); ff = np.zeros(n + 1, np.int32); nn = C.c_int(0)
+        nw = ref.ref_bow_transform(path.encode(), P(desc), n, levelsup, P(bw), P(bv), P(fn), P(fs), P(ff), C.byref(nn))
+        assert nw >= 0, ref.ref_last_error()
+        w, v, nd = f.bow_transform(0, levelsup=levelsup)
+        gw, gv, gfv = f.bow_build(w[0, :n], v[0, :n], nd[0, :n])
+        assert list(gw) == list(bw[:nw]) and np.array_equal(np.asarray(gv), bv[:nw]), seed
+        want_fv = {int(fn[j]): [int(x) for x in ff[fs[j]:fs[j + 1]]] for j in range(nn.value)}
+        if ragged == 0.0:
+            assert gfv == want_fv, seed
+        else:
+            # a leaf above level L - levelsup: DBoW2 leaves *nid unwritten there (TemplatedVocabulary.h:1230-1270 sets it only when
+            # the walk REACHES that level; the caller's `NodeId nid` is an uninitialised local) - undefined in the reference,
+            # never the case for ORBvoc (complete tree).  The oracle's rule is node 0; every other feature must agree.
+            short = set(gfv.get(0, []))
+            assert short, "the ragged vocabulary must exercise the case"
+            strip = lambda fv: {k: [x for x in v if x not in short] for k, v in fv.items() if [x for x in v if x not in short]}
+            assert strip(gfv) == strip(want_fv), seed
+        assert nw > 50

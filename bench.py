@@ -276,7 +276,7 @@ def main():
     ap.add_argument("--streams", type=int, default=8, help="independent camera streams served by one context")
     ap.add_argument("--rectify", action="store_true",
                     help="e2e leg starts from RAW frames: upload + cv::remap rectification on the device (SURVEY 8f rank 2)")
-    ap.add_argument("--contexts", type=int, default=6, help="calls kept in flight per GPU (one CUDA stream each)")
+    ap.add_argument("--contexts", type=int, default=8, help="calls kept in flight per GPU (one CUDA stream each; 8 x 16.5 GB of buffers for 512-pair calls)")
     ap.add_argument("--distinct", type=int, default=512, help="distinct synthetic pairs generated per rank (every launch sees pairs_per_call distinct pairs)")
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json config: c2 headline, c3 ORB only, c4 1280x720 line path, c5 512 streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -307,7 +307,7 @@ def main():
     cfg = CONFIGS[args.config]
     global W, H, WORKLOAD
     W, H, WORKLOAD = cfg["W"], cfg["H"], dict(cfg["params"])
-    if args.config == "c4" and args.streams == 8 and args.contexts == 6:
+    if args.config == "c4" and args.streams == 8 and args.contexts == 8:
         args.streams, args.contexts = 2, 4                # 1280x720: 2.6x the pixels and device memory per pair
     B, C = args.batch * args.streams, args.contexts       # pairs per call, calls in flight
     # this rank's camera streams (global ids), args.streams of them per context: stream s -> rank s mod world

@@ -426,6 +426,9 @@ PLF_API int PLF_FN(tap_fast_candidates)(plf_ctx* ctx, int slot, int side, int le
 PLF_API int PLF_FN(tap_lsd_scaled)(plf_ctx* ctx, int slot, int side, uint8_t* out, int out_stride, int* w, int* h);
 PLF_API int PLF_FN(tap_lsd_angles)(plf_ctx* ctx, int slot, int side, float* out, int* w, int* h);
 PLF_API int PLF_FN(tap_lsd_segments)(plf_ctx* ctx, int slot, int side, float* xyxy, int cap, int* n);
+/* Nanoseconds every image spent in the one-warp-per-image region grower during the last pass run with stage timing on
+ * (image index = slot * 2 + side; zeros for launches that used another grower). */
+PLF_API int PLF_FN(tap_grow_ns)(plf_ctx* ctx, unsigned long long* out, int n_images);
 /* LBD float descriptor (72 floats per line) before binarisation. */
 PLF_API int PLF_FN(tap_lbd_float)(plf_ctx* ctx, int slot, int side, float* out, int cap, int* n);
 

@@ -208,6 +208,10 @@ PLF_API int plf_cpu_tap_lsd_segments(plf_ctx* c, int slot, int side, float* xyxy
     if (xyxy) std::memcpy(xyxy, st.segs.data(), st.segs.size() * 4);
     return PLF_OK;
 }
+PLF_API int plf_cpu_tap_grow_ns(plf_ctx*, unsigned long long* out, int n_images) {      // no such kernel on the CPU: zeros
+    for (int i = 0; i < n_images; ++i) out[i] = 0;
+    return PLF_OK;
+}
 PLF_API int plf_cpu_tap_lbd_float(plf_ctx* c, int slot, int side, float* out, int cap, int* n) {
     if (!c || slot < 0 || slot >= (int)c->slots.size() || side < 0 || side > 1) return PLF_ERR_INVALID;
     const LsdState& st = c->slots[slot].lsd[side];

@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "orb_extract", "get_pyramid_level", "line_extract", "stereo_match_points", "stereo_match_lines", "match_nnr",
     "match", "frontend_batch", "batch_upload", "batch_run", "batch_download", "sync", "batch_io_bytes",
     "last_launch_count", "set_stage_timing", "get_stage_ms", "stream", "tap_blurred_level", "tap_pyramid_level",
-    "tap_fast_candidates", "tap_lsd_scaled", "tap_lsd_angles", "tap_lsd_segments", "tap_lbd_float",
+    "tap_fast_candidates", "tap_lsd_scaled", "tap_lsd_angles", "tap_lsd_segments", "tap_lbd_float", "tap_grow_ns",
     "rectify_set_maps", "rectify", "batch_upload_raw", "feature_grid", "get_features_in_area", "backproject", "bow_set_vocabulary", "bow_transform", "bow_build_vectors", "search_by_projection", "search_by_projection_frame",
     "search_by_projection_reloc", "search_by_projection_loop", "search_by_bow", "match_lines_tracked",
 ]
@@ -539,6 +539,12 @@ class Frontend:
         n = C.c_int(0)
         self.lib.check(self.lib.fn("get_stage_ms")(self.ctx, C.byref(names), C.byref(ms), C.byref(n)))
         return {names[i].decode(): ms[i] for i in range(n.value)}
+
+    def grow_ns(self, n_images):
+        """ns per image in the one-warp-per-image region grower during the last stage-timed pass."""
+        out = np.zeros(n_images, np.uint64)
+        self.lib.check(self.lib.fn("tap_grow_ns")(self.ctx, _ptr(out), n_images))
+        return out
 
     def stream(self):
         return self.lib.fn("stream")(self.ctx)

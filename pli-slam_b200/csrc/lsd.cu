@@ -690,10 +690,13 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[33], int& n, double
 template <bool REFINE>
 __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* lut, const int* gmap, const int* seeds,
                                                       const int* nSeeds, uint32_t* usedAll, int* reg, float* segs,
-                                                      int* nSegsOut, int* err, int imgFirst) {
+                                                      int* nSegsOut, int* err, int imgFirst, unsigned long long* imgNs) {
     __shared__ int ring[GROW_RING];
     __shared__ double s_sum[3][33];
     const int img = imgFirst + blockIdx.x, lane = threadIdx.x;
+    // stage timing only: nanoseconds this image's warp ran (one warp per image: a launch lasts as long as its slowest image)
+    unsigned long long t0 = 0;
+    if (imgNs) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     GrowCtx c;
     c.W = g.Ws; c.H = g.Hs; c.PB = g.Ps; c.lane = lane;
     const size_t base = (size_t)img * c.W * c.H;
@@ -745,6 +748,11 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* l
         }
     }
     if (lane == 0) nSegsOut[img] = nSeg;
+    if (imgNs && lane == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        imgNs[img] = t1 - t0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1322,11 +1330,18 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         // seq (one warp per image) for wide launches and mw (16 warps per image) for <= 128 images are the product path;
         // PLF_LSD_GROWER=stream selects the one-lane-per-region grower (exact, measured slower: profiles/r02_stream_grower.md)
         static const char* s_mode = getenv("PLF_LSD_GROWER");
+        // per-image run time of the one-warp-per-image grower, recorded only while stage timing is on (bench.py reports max / mean)
+        unsigned long long* growNs = nullptr;
+        if (c->stageTiming) {
+            if (!c->d_growNs && dalloc(&c->d_growNs, (size_t)c->nImgMax) != cudaSuccess) { cudaGetLastError(); c->d_growNs = nullptr; }
+            growNs = c->d_growNs;
+            if (growNs) cudaMemsetAsync(growNs + imgFirst, 0, (size_t)nImg * sizeof(unsigned long long), s);
+        }
         const bool wantStream = s_mode && !strcmp(s_mode, "stream");
         const bool wantLane = s_mode && !strcmp(s_mode, "lane");
         if (g.refine >= 1)
             lsd_grow_kernel<true><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
-                                                      c->d_nSegs, c->d_err, imgFirst);
+                                                      c->d_nSegs, c->d_err, imgFirst, growNs);
         else if (wantStream && plf_ensure_stream_buffers(c) == 0) {
             // one lane per region: up to 32 regions of each image in flight in its warp, rectangles fitted afterwards
             const StreamLayout L = stream_layout(g.Ps, g.Ws, g.Hs, g.segCap);
@@ -1345,14 +1360,14 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
             launches += 1;
         } else if (s_mode && !strcmp(s_mode, "seq"))
             lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
-                                                       c->d_nSegs, c->d_err, imgFirst);
+                                                       c->d_nSegs, c->d_err, imgFirst, growNs);
         else if (nImg <= PLF_MW_MAX_IMG && plf_ensure_mw_buffers(c) == 0)
             // few images: several regions of each image in flight (a block of 8 warps per image)
             lsd_grow_mw_kernel<<<nImg, 32 * MW, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_owner, c->d_regMW,
                                                         c->d_segs, c->d_nSegs, c->d_err, imgFirst);
         else
             lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
-                                                       c->d_nSegs, c->d_err, imgFirst);
+                                                       c->d_nSegs, c->d_err, imgFirst, growNs);
     }
     plf_mark(c, "line_keylines");
     const double minLen = c->p.min_line_length * std::min(g.W, g.H);

@@ -125,6 +125,7 @@ struct plf_ctx {
     int* d_regMW = nullptr;          // small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][8][Hs*Ws] region lists, one per wave slot
     int* d_stream = nullptr;         // streaming grower: [nImg][StreamLayout.total] owner map, list chunks, ticket table, region table (lazy)
     int4* d_laneRT = nullptr;        // lane-per-image grower: [nImg][segCap] region table {arena offset, size, angle bits, -} (lazy)
+    unsigned long long* d_growNs = nullptr;  // [nImg] ns every image spent in lsd_grow_kernel (stage timing only, lazy)
     int* d_nReg = nullptr;           // [nImg] regions entered in the table by the streaming / lane-per-image grower
     float* d_segs = nullptr;         // [nImg][segCap][4]
     int* d_nSegs = nullptr;          // [nImg]

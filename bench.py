@@ -446,6 +446,15 @@ def main():
         f0.batch_download(B, results[0])
         for k, v in f0.stage_ms().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v / reps
+    # one warp per image: the grow launch lasts as long as its slowest image - per-image run times
+    grow_img = None
+    try:
+        ns = f0.grow_ns(2 * B).astype(np.float64)
+        if ns.max() > 0:
+            grow_img = {"max": round(float(ns.max()) / 1e6, 2), "mean": round(float(ns.mean()) / 1e6, 2),
+                        "min": round(float(ns.min()) / 1e6, 2), "p99": round(float(np.percentile(ns, 99)) / 1e6, 2), "images": int(2 * B)}
+    except Exception:
+        pass
     f0.set_stage_timing(False)
     barrier()
 
@@ -505,6 +514,7 @@ def main():
             "gpu_launches": launches,
             "latency_ms_single_pair": None if lat_ms is None else round(lat_ms, 2),
             "ms_per_stage": {k: round(v, 4) for k, v in stage_acc.items()},
+            "grow_ms_per_image": grow_img,
             "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",

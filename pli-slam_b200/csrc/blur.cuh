@@ -9,53 +9,59 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 }
 
 // K1b  separable 8-bit Gaussian with integer taps summing to 256 (cv::GaussianBlur fixed-point path), REFLECT_101.
-// 7 taps (shorter kernels are zero-padded, which leaves the arithmetic unchanged).  128x8 output tile per 256-thread
-// block, every thread owns 4 horizontally adjacent pixels:
-//   load   : the (128+8) x 14 source window as aligned 32-bit words (byte-wise with reflection only for border tiles)
+// 7 taps (shorter kernels are zero-padded, which leaves the arithmetic unchanged).  128x32 output tile per 256-thread
+// block (round 2; 128x8 before: the 6 halo rows made the load and the horizontal pass process 1.75 rows per output row,
+// now 1.19), every thread owns 4 horizontally adjacent pixels of 4 rows:
+//   load   : the (128+8) x 38 source window as aligned 32-bit words, a warp per row (the row index is reflected once per
+//            row; bytes are reflected one by one only in words that straddle the left / right image border)
 //   pass 1 : horizontal taps with DP4A on funnel-shifted words; the u16 results of two consecutive rows are packed
 //            into one word so that
 //   pass 2 : the vertical taps are DP2A dot products over row pairs; out = (acc + 32768) >> 16.
 struct BlurJob { const uint8_t* src; uint8_t* dst; int w, h, sp, dp; };
 
 #define BL_TW 128
-#define BL_TH 8
+#define BL_TH PLF_BLUR_TH
 #define BL_ROWS (BL_TH + 6)
 #define BL_WORDS 34             // (128 + 8) bytes, window starts at x0 - 4
 
 __device__ __forceinline__ void blur_tile7(const BlurJob& j, const int* t, int x0, int y0) {
     __shared__ __align__(16) unsigned s_in[BL_ROWS][BL_WORDS + 2];
     __shared__ __align__(16) unsigned s_h[BL_ROWS / 2][BL_TW];        // (row 2r, row 2r+1) u16 pairs
-    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
-    // rows are reflected by index only; a word is loaded whole unless it straddles the left/right image border
-    for (int i = tid; i < BL_ROWS * BL_WORDS; i += 256) {
-        const int iy = i / BL_WORDS, wx = i - iy * BL_WORDS;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int iy = ty; iy < BL_ROWS; iy += 8) {
         int gy = reflect101(y0 - 3 + iy, j.h);
         gy = min(max(gy, 0), j.h - 1);
         const uint8_t* row = j.src + (size_t)gy * j.sp;
-        const int gx = x0 - 4 + wx * 4;
-        unsigned v;
-        if (gx >= 0 && gx + 3 < j.w) {
-            v = *reinterpret_cast<const unsigned*>(row + gx);
-        } else {
-            v = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                int x = reflect101(gx + b, j.w);
-                x = min(max(x, 0), j.w - 1);
-                v |= (unsigned)row[x] << (8 * b);
+        for (int k = 0; k < 2; ++k) {
+            const int wx = tx + 32 * k;
+            if (wx < BL_WORDS) {
+                const int gx = x0 - 4 + wx * 4;
+                unsigned v;
+                if (gx >= 0 && gx + 3 < j.w) {
+                    v = *reinterpret_cast<const unsigned*>(row + gx);
+                } else {
+                    v = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        int x = reflect101(gx + b, j.w);
+                        x = min(max(x, 0), j.w - 1);
+                        v |= (unsigned)row[x] << (8 * b);
+                    }
+                }
+                s_in[iy][wx] = v;
             }
         }
-        s_in[iy][wx] = v;
     }
     __syncthreads();
     const unsigned T0 = (unsigned)t[0] | ((unsigned)t[1] << 8) | ((unsigned)t[2] << 16) | ((unsigned)t[3] << 24);
     const unsigned T1 = (unsigned)t[4] | ((unsigned)t[5] << 8) | ((unsigned)t[6] << 16);
-    if (ty < BL_ROWS / 2) {
-        // rows 2*ty and 2*ty+1, my 4 pixels: output j needs window bytes 4*tx + j + 1 .. + 7
+    for (int pr = ty; pr < BL_ROWS / 2; pr += 8) {
+        // rows 2*pr and 2*pr+1, my 4 pixels: output j needs window bytes 4*tx + j + 1 .. + 7
         unsigned hrow[2][4];
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            const unsigned* r = &s_in[2 * ty + rr][tx];
+            const unsigned* r = &s_in[2 * pr + rr][tx];
             const unsigned w0 = r[0], w1 = r[1], w2 = r[2];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -69,47 +75,44 @@ __device__ __forceinline__ void blur_tile7(const BlurJob& j, const int* t, int x
         o.y = hrow[0][1] | (hrow[1][1] << 16);
         o.z = hrow[0][2] | (hrow[1][2] << 16);
         o.w = hrow[0][3] | (hrow[1][3] << 16);
-        *reinterpret_cast<uint4*>(&s_h[ty][4 * tx]) = o;
+        *reinterpret_cast<uint4*>(&s_h[pr][4 * tx]) = o;
     }
     __syncthreads();
-    const int gx = x0 + 4 * tx, gy = y0 + ty;
-    if (gx < j.w && gy < j.h) {
-        // output row ty uses staged rows ty .. ty+6
-        unsigned acc[4] = {0u, 0u, 0u, 0u};
-        const int p0 = ty >> 1;
-        if (ty & 1) {
-            const unsigned tp[4] = {(unsigned)t[0] << 8, (unsigned)t[1] | ((unsigned)t[2] << 8),
-                                    (unsigned)t[3] | ((unsigned)t[4] << 8), (unsigned)t[5] | ((unsigned)t[6] << 8)};
+    const int gx = x0 + 4 * tx;
+    // an even output row r uses the pairs r/2 .. r/2+3 with taps (t0 t1)(t2 t3)(t4 t5)(t6 -), an odd one (- t0)(t1 t2)(t3 t4)(t5 t6);
+    // ty and ty + 8k have the same parity, so the tap words are formed once
+    const bool odd = ty & 1;
+    // (DP2A multiplies the two u16 halves of its first operand by bytes 0 and 1 of the second)
+    const unsigned tp[4] = {odd ? (unsigned)t[0] << 8 : (unsigned)t[0] | ((unsigned)t[1] << 8),
+                            odd ? (unsigned)t[1] | ((unsigned)t[2] << 8) : (unsigned)t[2] | ((unsigned)t[3] << 8),
+                            odd ? (unsigned)t[3] | ((unsigned)t[4] << 8) : (unsigned)t[4] | ((unsigned)t[5] << 8),
+                            odd ? (unsigned)t[5] | ((unsigned)t[6] << 8) : (unsigned)t[6]};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint4 v = *reinterpret_cast<const uint4*>(&s_h[p0 + k][4 * tx]);
-                acc[0] = __dp2a_lo(v.x, tp[k], acc[0]);
-                acc[1] = __dp2a_lo(v.y, tp[k], acc[1]);
-                acc[2] = __dp2a_lo(v.z, tp[k], acc[2]);
-                acc[3] = __dp2a_lo(v.w, tp[k], acc[3]);
-            }
-        } else {
-            const unsigned tp[4] = {(unsigned)t[0] | ((unsigned)t[1] << 8), (unsigned)t[2] | ((unsigned)t[3] << 8),
-                                    (unsigned)t[4] | ((unsigned)t[5] << 8), (unsigned)t[6]};
+    for (int k = 0; k < BL_TH / 8; ++k) {
+        const int r = ty + 8 * k, gy = y0 + r;
+        if (gx < j.w && gy < j.h) {
+            // output row r uses staged rows r .. r+6
+            unsigned acc[4] = {0u, 0u, 0u, 0u};
+            const int p0 = r >> 1;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint4 v = *reinterpret_cast<const uint4*>(&s_h[p0 + k][4 * tx]);
-                acc[0] = __dp2a_lo(v.x, tp[k], acc[0]);
-                acc[1] = __dp2a_lo(v.y, tp[k], acc[1]);
-                acc[2] = __dp2a_lo(v.z, tp[k], acc[2]);
-                acc[3] = __dp2a_lo(v.w, tp[k], acc[3]);
+            for (int q = 0; q < 4; ++q) {
+                const uint4 v = *reinterpret_cast<const uint4*>(&s_h[p0 + q][4 * tx]);
+                acc[0] = __dp2a_lo(v.x, tp[q], acc[0]);
+                acc[1] = __dp2a_lo(v.y, tp[q], acc[1]);
+                acc[2] = __dp2a_lo(v.z, tp[q], acc[2]);
+                acc[3] = __dp2a_lo(v.w, tp[q], acc[3]);
             }
-        }
-        const unsigned o0 = (acc[0] + 32768u) >> 16, o1 = (acc[1] + 32768u) >> 16;
-        const unsigned o2 = (acc[2] + 32768u) >> 16, o3 = (acc[3] + 32768u) >> 16;
-        uint8_t* d = j.dst + (size_t)gy * j.dp + gx;
-        if (gx + 4 <= j.w && ((j.dp & 3) == 0)) {
-            *reinterpret_cast<unsigned*>(d) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
-        } else {
-            d[0] = (uint8_t)o0;
-            if (gx + 1 < j.w) d[1] = (uint8_t)o1;
-            if (gx + 2 < j.w) d[2] = (uint8_t)o2;
-            if (gx + 3 < j.w) d[3] = (uint8_t)o3;
+            const unsigned o0 = (acc[0] + 32768u) >> 16, o1 = (acc[1] + 32768u) >> 16;
+            const unsigned o2 = (acc[2] + 32768u) >> 16, o3 = (acc[3] + 32768u) >> 16;
+            uint8_t* d = j.dst + (size_t)gy * j.dp + gx;
+            if (gx + 4 <= j.w && ((j.dp & 3) == 0)) {
+                *reinterpret_cast<unsigned*>(d) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+            } else {
+                d[0] = (uint8_t)o0;
+                if (gx + 1 < j.w) d[1] = (uint8_t)o1;
+                if (gx + 2 < j.w) d[2] = (uint8_t)o2;
+                if (gx + 3 < j.w) d[3] = (uint8_t)o3;
+            }
         }
     }
 }

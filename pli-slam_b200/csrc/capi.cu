@@ -248,7 +248,7 @@ static int create_buffers(plf_ctx* c, const plf_params* p, std::vector<PlfCell>&
         std::vector<PlfLin> lin;
         for (int l = 0; l < g.nLevels; ++l) {
             const PlfLevel& lv = g.lv[l];
-            for (int y = 0; y < lv.h; y += 8)
+            for (int y = 0; y < lv.h; y += PLF_BLUR_TH)
                 for (int x = 0; x < lv.w; x += 128) tb.push_back(PlfTile{(short)l, (short)x, (short)y, 0});
             for (int y = PLF_EDGE; y < lv.h - PLF_EDGE; y += 8)
                 for (int x = PLF_EDGE; x < lv.w - PLF_EDGE; x += 128) tf.push_back(PlfTile{(short)l, (short)x, (short)y, 0});

@@ -250,7 +250,7 @@ static int create_buffers(plf_ctx* c, const plf_params* p, std::vector<PlfCell>&
             const PlfLevel& lv = g.lv[l];
             for (int y = 0; y < lv.h; y += PLF_BLUR_TH)
                 for (int x = 0; x < lv.w; x += 128) tb.push_back(PlfTile{(short)l, (short)x, (short)y, 0});
-            for (int y = PLF_EDGE; y < lv.h - PLF_EDGE; y += 8)
+            for (int y = PLF_EDGE; y < lv.h - PLF_EDGE; y += PLF_FAST_TH)
                 for (int x = PLF_EDGE; x < lv.w - PLF_EDGE; x += 128) tf.push_back(PlfTile{(short)l, (short)x, (short)y, 0});
         }
         // cv::resize(INTER_LINEAR) 8U coefficients of level l from level l-1

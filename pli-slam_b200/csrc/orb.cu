@@ -112,7 +112,7 @@ __device__ __forceinline__ int fast_score_packed(const unsigned* N, unsigned cen
 }
 
 #define FS_TW 128
-#define FS_TH 8
+#define FS_TH PLF_FAST_TH              // tile rows (8 until round 2: 14 staged rows per 8 output rows; now 38 per 32)
 #define FS_ROWW 36            // 32-bit words per staged row: (128 + 6 bytes -> 34 words) padded to a multiple of 4
 #define FS_IH (FS_TH + 6)
 // Packed FAST-9 candidate test: every thread owns 4 horizontally adjacent pixels held as 4 bytes of one register, so
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
                                                          const PlfTile* tiles, int imgFirst) {
     __shared__ __align__(16) unsigned s_w[FS_IH][FS_ROWW];
     __shared__ int s_cnt1, s_cnt2;
-    __shared__ unsigned short s_quads[256];                // phase-1 survivors: thread id | valid-pixel mask << 8
+    __shared__ unsigned short s_quads[FS_TW / 4 * FS_TH];  // phase-1 survivors: quad id (row * 32 + column group) | valid-pixel mask << 10
     __shared__ unsigned short s_queue[FS_TW * FS_TH];      // phase-2 survivors: (row << 7) | column
     // tiles cover [19, w-19) x [19, h-19) of every level: the union of all cell detection areas
     const PlfTile t = tiles[blockIdx.x];
@@ -141,10 +141,10 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
     if (tid == 0) { s_cnt1 = 0; s_cnt2 = 0; }
     // the window starts at x0-3 = 16 (mod 128) and level rows are 64-byte aligned: aligned 32-bit loads (the row pitch
     // is padded to 64 B and the pyramid allocation has slack, so the last words never leave the allocation)
-    for (int i = tid; i < FS_IH * 34; i += 256) {
-        const int iy = i / 34, wx = i - iy * 34;
+    for (int iy = ty; iy < FS_IH; iy += 8) {              // a warp per staged row: 34 words
         const uint8_t* row = src + (size_t)min(y0 - 3 + iy, lv.h - 1) * lv.pitch + (x0 - 3);
-        s_w[iy][wx] = *reinterpret_cast<const unsigned*>(row + wx * 4);
+        s_w[iy][tx] = *reinterpret_cast<const unsigned*>(row + tx * 4);
+        if (tx < 2) s_w[iy][32 + tx] = *reinterpret_cast<const unsigned*>(row + (32 + tx) * 4);
     }
     __syncthreads();
     // neighbour bytes of the 4 pixels of quad (qx, qy) at circle offset (dx, dy): bytes [4qx+3+dx, +4) of staged row qy+3+dy
@@ -159,12 +159,14 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
     // ---- phase 1, every thread: the four compass points.  Nine contiguous ring pixels always contain two compass points
     // that are neighbours on the compass, so a pixel without such a pair (polarity-blind, like the full test below) cannot
     // be a corner; most quads of a frame end here.
-    {
-        const unsigned C = nb(tx, ty, 0, 0);
-        const unsigned f0 = fast_gt_const4(__vabsdiffu4(C, nb(tx, ty, 0, 3)), k7f), f4 = fast_gt_const4(__vabsdiffu4(C, nb(tx, ty, 3, 0)), k7f);
-        const unsigned f8 = fast_gt_const4(__vabsdiffu4(C, nb(tx, ty, 0, -3)), k7f), f12 = fast_gt_const4(__vabsdiffu4(C, nb(tx, ty, -3, 0)), k7f);
+#pragma unroll
+    for (int rk = 0; rk < FS_TH / 8; ++rk) {
+        const int ry = ty + 8 * rk;                            // my row of the tile in this round
+        const unsigned C = nb(tx, ry, 0, 0);
+        const unsigned f0 = fast_gt_const4(__vabsdiffu4(C, nb(tx, ry, 0, 3)), k7f), f4 = fast_gt_const4(__vabsdiffu4(C, nb(tx, ry, 3, 0)), k7f);
+        const unsigned f8 = fast_gt_const4(__vabsdiffu4(C, nb(tx, ry, 0, -3)), k7f), f12 = fast_gt_const4(__vabsdiffu4(C, nb(tx, ry, -3, 0)), k7f);
         unsigned quick = ((f0 | f8) & (f4 | f12)) & 0x80808080u;          // = (f0&f4)|(f4&f8)|(f8&f12)|(f12&f0)
-        const int y = y0 + ty;
+        const int y = y0 + ry;
         const bool rowIn = y < lv.h - PLF_EDGE;
         const int xr = lv.w - PLF_EDGE - (x0 + 4 * tx);        // number of valid pixels from my first one
         if (!rowIn || xr <= 0) quick = 0;
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
             base = __shfl_sync(0xffffffffu, base, 0);
             if (quick) {
                 const unsigned m4 = ((quick >> 7) & 1u) | ((quick >> 14) & 2u) | ((quick >> 21) & 4u) | ((quick >> 28) & 8u);
-                s_quads[base + __popc(vote & ((1u << tx) - 1u))] = (unsigned short)(tid | (m4 << 8));
+                s_quads[base + __popc(vote & ((1u << tx) - 1u))] = (unsigned short)((ry * 32 + tx) | (m4 << 10));
             }
         }
     }
@@ -191,8 +193,8 @@ __global__ void __launch_bounds__(256) fast_score_kernel(PlfGeom g, const uint8_
     const int n1 = s_cnt1;
     for (int i = tid; i < n1; i += 256) {
         const int e = s_quads[i];
-        const int qx = e & 31, qy = (e >> 5) & 7;
-        const unsigned m4 = (unsigned)e >> 8;
+        const int qx = e & 31, qy = (e >> 5) & 31;
+        const unsigned m4 = (unsigned)e >> 10;
         const unsigned C = nb(qx, qy, 0, 0);
         unsigned F[16];                                // bit 7 of byte j: |centre - neighbour k| of pixel j exceeds minTh
 #pragma unroll

@@ -14,6 +14,7 @@
 #define PLF_NOTDEF (-1024.0f)
 #define PLF_MW_WARPS 16           // warps (= regions in flight) per image of that grower
 #define PLF_MW_MAX_IMG 128         // launches of at most this many images use the multi-warp (several regions in flight) grower
+#define PLF_FAST_TH 32            // rows of one FAST score tile (orb.cu FS_TH); same for its host-built tile table
 #define PLF_BLUR_TH 32            // rows of one blur tile (blur.cuh); the host builds the tile table of the pyramid blur with it
 #define PLF_GRID_COLS 64          // FRAME_GRID_COLS, include/Frame.h:60
 #define PLF_GRID_ROWS 48          // FRAME_GRID_ROWS, include/Frame.h:59

@@ -123,32 +123,47 @@ __device__ __forceinline__ void blur_tile7(const BlurJob& j, const int* t, int x
 // source bytes as three aligned words per row starting at the word of the first tap (scale <= 2: the taps span at most
 // 12 bytes); each tap pair is picked with one PRMT and weighted with one DP2A.  EXACT = cv::INTER_LINEAR_EXACT (Q8
 // weights, one rounding), otherwise cv::INTER_LINEAR's 11-bit two-stage form.  Returns the 4 result bytes.
+// The column part (table entries, tap offsets, weights, byte selectors) does not depend on the row: resize_prep forms it
+// once, resize_apply uses it for every row a thread produces (4 rows per thread in the kernels).
 struct PlfLin;
-template <bool EXACT>
-__device__ __forceinline__ unsigned resize_quad(const uint8_t* r0, const uint8_t* r1, const void* linX4, int nValid,
-                                                int ya0, int ya1) {
-    const uint4 t0 = reinterpret_cast<const uint4*>(linX4)[0], t1 = reinterpret_cast<const uint4*>(linX4)[1];
+struct ResizeTaps { unsigned wts[4], sel[4]; int o[4]; int base; };
+__device__ __forceinline__ void resize_prep(const void* linX4, int nValid, ResizeTaps& T) {
+    const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(linX4)), t1 = __ldg(reinterpret_cast<const uint4*>(linX4) + 1);
     const unsigned e0[4] = {t0.x, t0.z, t1.x, t1.z}, e1[4] = {t0.y, t0.w, t1.y, t1.w};   // (ofs | a0<<16), (a1 | pad<<16)
-    const int base = (int)(e0[0] & 0xFFFFu) & ~3;
-    const unsigned* w0 = reinterpret_cast<const unsigned*>(r0 + base);
-    const unsigned* w1 = reinterpret_cast<const unsigned*>(r1 + base);
+    T.base = (int)(e0[0] & 0xFFFFu) & ~3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int jj = j < nValid ? j : 0;                                    // entries past the row end are padding
+        T.o[j] = (int)(e0[jj] & 0xFFFFu) - T.base;                            // 0 .. 10
+        T.wts[j] = __byte_perm(e0[jj], e1[jj], 0x5432);                       // a0 | a1 << 16
+        T.sel[j] = (unsigned)(T.o[j] & 3) * 0x11u + 0x10u;                    // bytes (o&3), (o&3)+1 of {lo, hi}
+    }
+}
+template <bool EXACT>
+__device__ __forceinline__ unsigned resize_apply(const ResizeTaps& T, const uint8_t* r0, const uint8_t* r1, int ya0, int ya1) {
+    const unsigned* w0 = reinterpret_cast<const unsigned*>(r0 + T.base);
+    const unsigned* w1 = reinterpret_cast<const unsigned*>(r1 + T.base);
     const unsigned a0 = w0[0], a1 = w0[1], a2 = w0[2], b0 = w1[0], b1 = w1[1], b2 = w1[2];
     unsigned out = 0u;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int jj = j < nValid ? j : 0;                                    // entries past the row end are padding
-        const int o = (int)(e0[jj] & 0xFFFFu) - base;                         // 0 .. 10
-        const unsigned wts = __byte_perm(e0[jj], e1[jj], 0x5432);            // a0 | a1 << 16
-        const unsigned sel = (unsigned)(o & 3) * 0x11u + 0x10u;               // bytes (o&3), (o&3)+1 of {lo, hi}
+        const int o = T.o[j];
         const unsigned loA = o < 4 ? a0 : (o < 8 ? a1 : a2), hiA = o < 4 ? a1 : a2;
         const unsigned loB = o < 4 ? b0 : (o < 8 ? b1 : b2), hiB = o < 4 ? b1 : b2;
-        const int h0 = (int)__dp2a_lo(wts, __byte_perm(loA, hiA, sel), 0u);
-        const int h1 = (int)__dp2a_lo(wts, __byte_perm(loB, hiB, sel), 0u);
+        const int h0 = (int)__dp2a_lo(T.wts[j], __byte_perm(loA, hiA, T.sel[j]), 0u);
+        const int h1 = (int)__dp2a_lo(T.wts[j], __byte_perm(loB, hiB, T.sel[j]), 0u);
         const int v = EXACT ? (h0 * ya0 + h1 * ya1 + 32768) >> 16
                             : (((ya0 * (h0 >> 4)) >> 16) + ((ya1 * (h1 >> 4)) >> 16) + 2) >> 2;
         out |= (unsigned)(v & 0xFF) << (8 * j);
     }
     return out;
+}
+template <bool EXACT>
+__device__ __forceinline__ unsigned resize_quad(const uint8_t* r0, const uint8_t* r1, const void* linX4, int nValid,
+                                                int ya0, int ya1) {
+    ResizeTaps T;
+    resize_prep(linX4, nValid, T);
+    return resize_apply<EXACT>(T, r0, r1, ya0, ya1);
 }
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {

@@ -42,16 +42,23 @@ __global__ void __launch_bounds__(256) blur_image_kernel(const uint8_t* src, siz
 __global__ void __launch_bounds__(256) lsd_upscale_kernel(PlfGeom g, const uint8_t* src, size_t srcImgStride, int sp,
                                                           uint8_t* dst, const PlfLin* linX, const PlfLin* linY,
                                                           int imgFirst) {
-    const int dx = blockIdx.x * 128 + threadIdx.x * 4, dy = blockIdx.y * 8 + threadIdx.y;
-    if (dx >= g.Ws || dy >= g.Hs) return;
+    const int dx = blockIdx.x * 128 + threadIdx.x * 4;
+    if (dx >= g.Ws) return;
     const int img = imgFirst + blockIdx.z;
     const uint8_t* s = src + (size_t)img * srcImgStride;
-    const PlfLin cy = linY[dy];                     // Q8 weights built on the host (a0 = 256 - a1)
-    const uint8_t* r0 = s + (size_t)cy.ofs * sp;
-    const uint8_t* r1 = s + (size_t)min((int)cy.ofs + 1, g.H - 1) * sp;
-    // 4 pixels per thread; the row pitch Ps is a multiple of 128, so the store is always a whole aligned word
-    const unsigned v = resize_quad<true>(r0, r1, linX + dx, min(4, g.Ws - dx), cy.a0, cy.a1);
-    *reinterpret_cast<unsigned*>(dst + (size_t)img * g.Ps * g.Hs + (size_t)dy * g.Ps + dx) = v;
+    ResizeTaps T;                                   // column part: once for the 4 rows of this thread
+    resize_prep(linX + dx, min(4, g.Ws - dx), T);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int dy = blockIdx.y * 32 + threadIdx.y + 8 * k;
+        if (dy >= g.Hs) break;
+        const PlfLin cy = linY[dy];                     // Q8 weights built on the host (a0 = 256 - a1)
+        const uint8_t* r0 = s + (size_t)cy.ofs * sp;
+        const uint8_t* r1 = s + (size_t)min((int)cy.ofs + 1, g.H - 1) * sp;
+        // 4 pixels per thread; the row pitch Ps is a multiple of 128, so the store is always a whole aligned word
+        const unsigned v = resize_apply<true>(T, r0, r1, cy.a0, cy.a1);
+        *reinterpret_cast<unsigned*>(dst + (size_t)img * g.Ps * g.Hs + (size_t)dy * g.Ps + dx) = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1313,7 +1320,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         upStride = imgBytes;
         ++launches;
     }
-    lsd_upscale_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, c->d_lin + c->linLsdX, c->d_lin + c->linLsdY, imgFirst);
+    lsd_upscale_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 31) / 32, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, c->d_lin + c->linLsdX, c->d_lin + c->linLsdY, imgFirst);
     plf_mark(c, "lsd_gradient");
     cudaMemsetAsync(c->d_n2max + imgFirst, 0, nImg * sizeof(int), s);
     lsd_grad_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_n2, c->d_used, c->d_n2max, imgFirst);

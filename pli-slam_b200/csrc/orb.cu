@@ -16,23 +16,32 @@ __device__ const int d_patternT[1024] = {
 
 // ---------------------------------------------------------------------------------------------------------------
 // K1a  pyramid level l from level l-1: cv::resize(INTER_LINEAR) 8U, 11-bit fixed point (src/ORBextractor.cc:1165).
+#define PYR_ROWS 4             // output rows per thread (the column taps are prepared once per thread)
 // 128x8 tiles, 4 output pixels per thread (resize_quad: aligned word loads of the taps, one 32-bit store); each source
 // byte is reused by ~1.4 output pixels in x and y through L1/L2, so the level is read from HBM once.
 __global__ void __launch_bounds__(256) pyr_resize_kernel(PlfGeom g, uint8_t* pyr, const PlfLin* lin, int level, int imgFirst) {
     const PlfLevel& d = g.lv[level];
     const PlfLevel& s = g.lv[level - 1];
-    const int dx = blockIdx.x * 128 + threadIdx.x * 4, dy = blockIdx.y * 8 + threadIdx.y;
-    if (dx >= d.w || dy >= d.h) return;
+    const int dx = blockIdx.x * 128 + threadIdx.x * 4;
+    if (dx >= d.w) return;
     const int img = imgFirst + blockIdx.z;
     const uint8_t* src = pyr + (size_t)img * g.pyrBytes + s.off;
-    uint8_t* dst = pyr + (size_t)img * g.pyrBytes + d.off + (size_t)dy * d.pitch + dx;
-    const PlfLin cy = lin[d.yTab + dy];                            // source index + 11-bit weights, built on the host
-    const uint8_t* r0 = src + (size_t)cy.ofs * s.pitch;
-    const uint8_t* r1 = src + (size_t)min((int)cy.ofs + 1, s.h - 1) * s.pitch;
+    uint8_t* dcol = pyr + (size_t)img * g.pyrBytes + d.off + dx;
     const int nValid = min(4, d.w - dx);
-    const unsigned v = resize_quad<false>(r0, r1, lin + d.xTab + dx, nValid, cy.a0, cy.a1);
-    if (nValid == 4) *reinterpret_cast<unsigned*>(dst) = v;
-    else for (int j = 0; j < nValid; ++j) dst[j] = (uint8_t)(v >> (8 * j));
+    ResizeTaps T;                                                    // column part: once for the 4 rows of this thread
+    resize_prep(lin + d.xTab + dx, nValid, T);
+#pragma unroll
+    for (int k = 0; k < PYR_ROWS; ++k) {
+        const int dy = blockIdx.y * (8 * PYR_ROWS) + threadIdx.y + 8 * k;
+        if (dy >= d.h) break;
+        const PlfLin cy = lin[d.yTab + dy];                            // source index + 11-bit weights, built on the host
+        const uint8_t* r0 = src + (size_t)cy.ofs * s.pitch;
+        const uint8_t* r1 = src + (size_t)min((int)cy.ofs + 1, s.h - 1) * s.pitch;
+        const unsigned v = resize_apply<false>(T, r0, r1, cy.a0, cy.a1);
+        uint8_t* dst = dcol + (size_t)dy * d.pitch;
+        if (nValid == 4) *reinterpret_cast<unsigned*>(dst) = v;
+        else for (int j = 0; j < nValid; ++j) dst[j] = (uint8_t)(v >> (8 * j));
+    }
 }
 
 // all pyramid levels in one launch: blockIdx.x enumerates the 32x32 tiles of every level
@@ -801,7 +810,7 @@ int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1) {
     int launches = 0;
     plf_mark(c, "orb_pyramid");
     for (int l = 1; l < g.nLevels; ++l) {
-        dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 7) / 8, nImg);
+        dim3 grid((g.lv[l].w + 127) / 128, (g.lv[l].h + 8 * PYR_ROWS - 1) / (8 * PYR_ROWS), nImg);
         pyr_resize_kernel<<<grid, dim3(32, 8), 0, s>>>(g, c->d_pyr, c->d_lin, l, imgFirst);
         ++launches;
     }

@@ -160,7 +160,7 @@ __device__ __forceinline__ double lsd_bin_coef(int n2max, int nBins) {
 #define ORD_MLP 8
 __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, const int* gmap, const int* n2max, int* seeds,
                                                          int* nSeeds, int imgFirst) {
-    extern __shared__ int s_cur[];          // [ORD_WARPS][nBins]
+    extern __shared__ int s_cur[];          // [ORD_WARPS][nBins] counters / cursors, then [nBins + 1] bin thresholds
     __shared__ int s_scan[ORD_WARPS];
     __shared__ int s_carry;
     const int img = imgFirst + blockIdx.x;
@@ -175,6 +175,31 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, co
     int* mine = s_cur + warp * nBins;
     for (int i = tid; i < ORD_WARPS * nBins; i += 32 * ORD_WARPS) s_cur[i] = 0;
     if (tid == 0) s_carry = 0;
+    // The bin of a pixel is (int)(sqrt(|g|^2 / 4.0) * coef) in double: monotone in |g|^2, so it is given by the table
+    // T[b] = smallest |g|^2 whose bin is >= b, found per image with the exact expression (a binary search per bin).  A
+    // pixel then takes a float estimate of its bin (off by at most one) and corrects it against T: the same bins as the
+    // double expression at a quarter of the instructions, two of which were double square roots per defined pixel.
+    int* T = s_cur + ORD_WARPS * nBins;
+    {
+        const int top = n2max[img] + 1;                 // no pixel has a larger |g|^2
+        for (int b = tid; b <= nBins; b += 32 * ORD_WARPS) {
+            int lo = 0, hi = top + 1;                   // smallest n in [0, top + 1] with bin(n) >= b (top + 1: none)
+            if (b == nBins) lo = hi = 0x7fffffff;
+            while (lo < hi) {
+                const int mid = lo + ((hi - lo) >> 1);
+                if (mid <= top && lsd_bin(mid, coef) >= b) hi = mid; else lo = mid + 1;
+            }
+            T[b] = (b == 0) ? 0 : lo;
+        }
+    }
+    const float coefh = (float)(coef * 0.5);
+    auto bin_of = [&](int n2) -> int {
+        int b = (int)(__fsqrt_rn((float)n2) * coefh);
+        b = min(max(b, 0), nBins - 1);
+        b -= (n2 < T[b]);
+        b += (n2 >= T[b + 1]);
+        return b;
+    };
     __syncthreads();
     // both walks keep ORD_MLP independent loads in flight per lane (a single dependent load per step leaves the walk
     // bound by memory latency)
@@ -184,7 +209,7 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, co
         for (int u = 0; u < ORD_MLP; ++u) v[u] = (pb + 32 * u < p1) ? N2[pb + 32 * u] : 0;
 #pragma unroll
         for (int u = 0; u < ORD_MLP; ++u)
-            if (v[u]) atomicAdd(&mine[lsd_bin(lsd_n2(v[u]), coef)], 1);
+            if (v[u]) atomicAdd(&mine[bin_of(lsd_n2(v[u]))], 1);
     }
     __syncthreads();
     // cursors: for bins in descending order, for warps in ascending order
@@ -230,7 +255,7 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, co
             if (x >= W) { x -= W; ++y; }
             const int v = vv[u];
             const bool def = v != 0;
-            const int bin = def ? lsd_bin(lsd_n2(v), coef) : 0;
+            const int bin = def ? bin_of(lsd_n2(v)) : 0;
             const unsigned wm = __ballot_sync(0xffffffffu, def);
             if (def) {
                 const unsigned grp = __match_any_sync(wm, bin);
@@ -1326,7 +1351,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     lsd_grad_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_n2, c->d_used, c->d_n2max, imgFirst);
     plf_mark(c, "lsd_order");
     {
-        const size_t smem = (size_t)ORD_WARPS * g.nBins * sizeof(int);
+        const size_t smem = ((size_t)ORD_WARPS * g.nBins + g.nBins + 1) * sizeof(int);
         static size_t s_granted[64] = {};
         if (plf_raise_smem_optin(s_granted, c->device, smem))
             cudaFuncSetAttribute(lsd_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -669,9 +669,17 @@ __global__ void __launch_bounds__(256) orient_desc_kernel(PlfGeom g, const uint8
     const int xa = (x - 18) & ~3;                          // aligned start column; x-18 >= 1
     const int sh0 = (x - 18) - xa;                         // 0..3
     unsigned* pw = s_patch[wl];
-    for (int i = lane; i < 37 * 11; i += 32) {
-        const int r = i / 11, wx = i - r * 11;             // 11 words cover 37 + 3 bytes
-        pw[r * 11 + wx] = *reinterpret_cast<const unsigned*>(blv + (size_t)(y - 18 + r) * lv.pitch + xa + wx * 4);
+    {   // 37 rows x 11 words (37 + 3 bytes): all 13 loads of a lane are issued before the first is stored
+        unsigned v[13];
+#pragma unroll
+        for (int k = 0; k < 13; ++k) {
+            const int i = lane + 32 * k;
+            const int r = i / 11, wx = i - r * 11;
+            v[k] = (i < 37 * 11) ? *reinterpret_cast<const unsigned*>(blv + (size_t)(y - 18 + r) * lv.pitch + xa + wx * 4) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 13; ++k)
+            if (lane + 32 * k < 37 * 11) pw[lane + 32 * k] = v[k];
     }
     const uint8_t* pc = reinterpret_cast<const uint8_t*>(pw) + 18 * 44 + 18 + sh0;      // centre of the staged window
     // moments: lane = column u of the 31x31 patch, loop over rows v (integer sums -> order-free, exact)

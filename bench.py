@@ -50,13 +50,15 @@ BYTES_PER_PAIR = CONFIGS["c2"]["bytes_per_pair"]
 
 
 def shard_streams(n_streams, world_size, rank):
-    """Stream s -> rank s mod world_size.  Returns the stream ids this rank owns."""
-    return list(range(rank, n_streams, world_size))
+    """Stream s -> rank s mod world_size: the product's own sharder (pli-slam_b200/pool.py)."""
+    import plf
+    return plf.shard_streams(n_streams, world_size, rank)
 
 
 def stream_seed(stream, frame):
-    """Seed convention of SURVEY §8d for C5: stream s, frame f -> 10000*(s+1)+f."""
-    return 10_000 * (stream + 1) + frame
+    """Seed convention of SURVEY §8d for C5: stream s, frame f -> 10000*(s+1)+f (pli-slam_b200/pool.py)."""
+    import plf
+    return plf.stream_seed(stream, frame)
 
 
 def _gen_pair(args):
@@ -321,8 +323,8 @@ def main():
         seeds = [cfg["seed0"] + rank * distinct + i for i in range(distinct)]
     Ld, Rd = make_inputs(seeds, W, H)
     ctxs, hostL, hostR, results = [], [], [], []
-    for ci in range(C):
-        f = plf.Frontend(prod, device=local_rank, width=W, height=H, max_batch=B, **WORKLOAD)
+    pool = plf.DevicePool(prod, local_rank, C, args.streams, args.batch, width=W, height=H, **WORKLOAD)
+    for ci, f in enumerate(pool):
         # every call covers `distinct` different pairs (all of them when distinct == pairs_per_call); the contexts rotate them
         idx = (np.arange(B) + ci * (distinct // max(C, 1) + 1)) % distinct
         l = torch.from_numpy(np.ascontiguousarray(Ld[idx])).pin_memory()

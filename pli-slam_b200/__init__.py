@@ -7,3 +7,4 @@ the thin Python host mirror used by tests and bench.py; the C++ host mirror of t
 from .binding import (Frontend, Library, Params, PlfError, BatchResult, load_product, load_oracle, KEYPOINT_DT,
                       KEYLINE_DT, PROJ_QUERY_DT, FRAME_QUERY_DT, TRACK_LINE_DT, ABI_SYMBOLS, PRODUCT_LIB, ORACLE_LIB)
 from .synth import synth_pair, synth_batch, synth_curvy, synth_vocabulary, rectify_maps, EUROC_CALIB
+from .pool import shard_streams, stream_owner, stream_seed, DevicePool

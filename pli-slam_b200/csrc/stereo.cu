@@ -13,19 +13,23 @@ __global__ void __launch_bounds__(256) stereo_points_kernel(PlfGeom g, const uin
                                                             const uint8_t* desc, const int* nKp, float* uRight,
                                                             float* depth, int* sadOut, float mbf, float fx,
                                                             int slotFirst) {
+    // The 8 warps of a block scan the same right keypoints: their row bands (floor(yR - r), ceil(yR + r)), x and octave are
+    // formed once per block into shared memory, 1024 at a time, instead of once per (left, right) pair from the 28-byte
+    // keypoint records.
+    __shared__ int4 s_band[1024];
     const int slot = slotFirst + blockIdx.y;
     const int imgL = slot * 2, imgR = slot * 2 + 1;
     const int lane = threadIdx.x & 31;
     const int iL = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int N = nKp[imgL], Nr = nKp[imgR];
-    if (iL >= N) return;
     float* uR = uRight + (size_t)slot * g.kpCap;
     float* dp = depth + (size_t)slot * g.kpCap;
     int* so = sadOut + (size_t)slot * g.kpCap;
-    if (lane == 0) { uR[iL] = -1.f; dp[iL] = -1.f; so[iL] = -1; }
-    const plf_keypoint kpL = kp[(size_t)imgL * g.kpCap + iL];
+    bool active = iL < N;                           // warp-uniform
+    if (active && lane == 0) { uR[iL] = -1.f; dp[iL] = -1.f; so[iL] = -1; }
+    const plf_keypoint kpL = kp[(size_t)imgL * g.kpCap + (active ? iL : 0)];
     const plf_keypoint* kR = kp + (size_t)imgR * g.kpCap;
-    const uint4* dL4 = reinterpret_cast<const uint4*>(desc + ((size_t)imgL * g.kpCap + iL) * 32);
+    const uint4* dL4 = reinterpret_cast<const uint4*>(desc + ((size_t)imgL * g.kpCap + (active ? iL : 0)) * 32);
     const uint4 dl0 = dL4[0], dl1 = dL4[1];
     const uint4* dR4 = reinterpret_cast<const uint4*>(desc + (size_t)imgR * g.kpCap * 32);
     // mb := mbf/fx (oracle rule), minZ = mb, maxD = mbf/minZ  (Frame.cc:1006-1008)
@@ -34,21 +38,34 @@ __global__ void __launch_bounds__(256) stereo_points_kernel(PlfGeom g, const uin
     const float uL = kpL.x, vL = kpL.y;
     const int row = (int)vL;
     const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, minD);
-    if (maxU < 0) return;
+    if (maxU < 0) active = false;
     int best = 100, bestIdx = 0x7fffffff;   // TH_HIGH
     const int levelL = kpL.octave;
-    for (int iR = lane; iR < Nr; iR += 32) {
-        const plf_keypoint k = kR[iR];
-        const float r = __fmul_rn(2.0f, g.lv[k.octave].scale);
-        const int maxr = (int)ceilf(__fadd_rn(k.y, r)), minr = (int)floorf(__fsub_rn(k.y, r));
-        if (row < minr || row > maxr) continue;
-        if (k.octave < levelL - 1 || k.octave > levelL + 1) continue;
-        if (!(k.x >= minU && k.x <= maxU)) continue;
-        const uint4 a = dR4[iR * 2], b = dR4[iR * 2 + 1];
-        const int d = __popc(a.x ^ dl0.x) + __popc(a.y ^ dl0.y) + __popc(a.z ^ dl0.z) + __popc(a.w ^ dl0.w) +
-                      __popc(b.x ^ dl1.x) + __popc(b.y ^ dl1.y) + __popc(b.z ^ dl1.z) + __popc(b.w ^ dl1.w);
-        if (d < best) { best = d; bestIdx = iR; }   // ascending iR per lane: first minimum kept
+    for (int c0 = 0; c0 < Nr; c0 += 1024) {
+        const int cnt = min(1024, Nr - c0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < cnt; j += 256) {
+            const plf_keypoint k = kR[c0 + j];
+            const float r = __fmul_rn(2.0f, g.lv[k.octave].scale);
+            const int maxr = (int)ceilf(__fadd_rn(k.y, r)), minr = (int)floorf(__fsub_rn(k.y, r));
+            s_band[j] = make_int4(minr, maxr, __float_as_int(k.x), k.octave);
+        }
+        __syncthreads();
+        if (active)
+            for (int j = lane; j < cnt; j += 32) {
+                const int4 k = s_band[j];
+                if (row < k.x || row > k.y) continue;
+                if (k.w < levelL - 1 || k.w > levelL + 1) continue;
+                const float kx = __int_as_float(k.z);
+                if (!(kx >= minU && kx <= maxU)) continue;
+                const int iR = c0 + j;
+                const uint4 a = dR4[iR * 2], b = dR4[iR * 2 + 1];
+                const int d = __popc(a.x ^ dl0.x) + __popc(a.y ^ dl0.y) + __popc(a.z ^ dl0.z) + __popc(a.w ^ dl0.w) +
+                              __popc(b.x ^ dl1.x) + __popc(b.y ^ dl1.y) + __popc(b.z ^ dl1.z) + __popc(b.w ^ dl1.w);
+                if (d < best) { best = d; bestIdx = iR; }   // ascending iR per lane: first minimum kept
+            }
     }
+    if (!active) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const int ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, bestIdx, o);

@@ -152,6 +152,10 @@ inline int match(plf::Context& ctx, const plf::Mat8& desc1, const plf::Mat8& des
     return n;
 }
 
+// Multi-GPU: replicas only (every stereo pair is independent).  Stream s is served by rank / GPU s mod world; the Python twin
+// and the per-rank context pool are pli-slam_b200/pool.py.
+inline int plf_stream_owner(int stream, int world) { return world > 0 ? stream % world : 0; }
+
 // The two stereo members of Frame: fills mvuRight/mvDepth and mvDisparity_l/mvle_l from the state the four extractor
 // calls left in the context.
 class StereoFrontend {

@@ -306,6 +306,7 @@ __device__ __forceinline__ void seq_sum3(double (*buf)[33], double a, double b, 
 }
 
 struct GrowState {
+    int ndep;         // streaming mode: entries of c.deps in use (SW_MAXDEP + 1: too many, the region cannot be verified)
     int n;            // region size
     float sumdx, sumdy;
     float regDeg;     // exact region angle in degrees (fastAtan2 of the sums; the seed's angle for a fresh region) unless `dirty`
@@ -324,8 +325,21 @@ struct GrowCtx {
     uint32_t* owner;    // per pixel: tag of the region that claims it in the current wave, PLF_FREE if none
     uint32_t tag;       // my tag = slot + 1; a lower tag is an earlier seed
     int* invalid;       // per slot: this region overlaps an earlier one of the wave and must be re-grown
+    // streaming (MODE 2, lsd_sw.cuh) only: tag = seed position + 1 (an EARLIER position has the smaller tag)
+    unsigned* robbed;   // shared memory, one word per chunk of the window: bit = a region of that chunk lost a pixel
+    uint32_t* deps;     // shared memory, SW_MAXDEP tags of earlier, uncommitted regions whose claims this region skipped
+    uint32_t floorTag;  // tags below this were committed when the region started: their claims are final
+    int maxN;           // room for the pixel list
+    int* actN;          // shared memory: current size of the region, for the parking heuristic of the other warps
+    bool ldcg;          // experiment switch: owner reads from L2
+    bool final;         // grown by the committing warp: every earlier region is final, nobody can take a pixel from it
 };
 #define PLF_FREE 0xFFFFFFFFu
+#define SW_WIN 1024                 // chunks (of 32 seed positions) between the commit pointer and the scan pointer
+#define SW_MAXDEP 8
+__device__ __forceinline__ void sw_rob(const GrowCtx& c, uint32_t victimTag) {
+    atomicOr(c.robbed + (((victimTag - 1u) >> 5) & (SW_WIN - 1)), 1u << ((victimTag - 1u) & 31u));
+}
 
 // q is a BIT index, y * PB + x
 __device__ __forceinline__ bool used_bit(const uint32_t* used, int q) {
@@ -376,15 +390,21 @@ __device__ __forceinline__ bool lsd_aligned(float thetaDeg, float aDeg, const Al
 // ~100 + 9/accepted-pixel warp instructions per round instead of ~95 per accepted pixel.
 // speculative mode: has an earlier region of the wave taken one of my pixels?  The flags only ever go 0 -> 1 and are written
 // and polled with shared-memory atomics while the regions grow; the authoritative read is after the wave's barrier.
+template <int MODE = 1>
 __device__ __forceinline__ bool grow_is_invalid(const GrowCtx& c) {
     int f = 0;
-    if (c.lane == 0) f = atomicOr(c.invalid + (c.tag - 1), 0);
+    if (MODE == 2) {
+        if (c.lane == 0) f = (int)((atomicOr(c.robbed + (((c.tag - 1u) >> 5) & (SW_WIN - 1)), 0u) >> ((c.tag - 1u) & 31u)) & 1u);
+    } else {
+        if (c.lane == 0) f = atomicOr(c.invalid + (c.tag - 1), 0);
+    }
     return __shfl_sync(0xffffffffu, f, 0) != 0;
 }
 
-template <bool SPEC>
+template <int MODE>
 __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int pk, const float4& r, const AlignTol& tol,
                                            const GrowCtx& c, unsigned dupAll, unsigned& accepted) {
+    constexpr bool SPEC = MODE != 0;
     unsigned pending = __ballot_sync(0xffffffffu, valid);
     if (!pending) return;
     const unsigned dup = dupAll & pending;          // valid lanes holding my pixel (copies share the used bit)
@@ -437,6 +457,11 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
             c.R[at] = pk;
             if (!SPEC) {
                 atomicOr(c.used + (q >> 5), 1u << (q & 31));
+            } else if (MODE == 2) {
+                // claim with my ticket: the earliest ticket keeps a contested pixel; whoever loses one is marked
+                const uint32_t old = atomicMin(c.owner + q, c.tag);
+                if (old < c.tag) sw_rob(c, c.tag);
+                else if (old != PLF_FREE && old > c.tag) sw_rob(c, old);
             } else {
                 // claim in the wave's owner map: the earlier seed (lower tag) wins a contested pixel, the loser is re-grown
                 const uint32_t old = atomicMin(c.owner + q, c.tag);
@@ -444,7 +469,7 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
                 else if (old != PLF_FREE && old > c.tag) atomicOr(c.invalid + (old - 1), 1);
             }
         }
-        if (SPEC && grow_is_invalid(c)) { st.aborted = true; st.n += __popc(acc); return; }
+        if (SPEC && !(MODE == 2 && c.final) && grow_is_invalid<MODE>(c)) { st.aborted = true; st.n += __popc(acc); return; }
         st.n += __popc(acc);
         accepted |= acc;
         if (mm == 0u && v >= 0) {          // the spare lane holds the sums and the angle after all of A
@@ -470,16 +495,23 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
 
 // LSD region_grow from the seed (packed pk0, linear index p) with angle tolerance `tol`; returns the region size, the
 // pixel list is left in c.R[0..n)
-template <bool SPEC>
-__device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, const AlignTol& tol, double& regAngleOut) {
+template <int MODE>
+__device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, const AlignTol& tol, double& regAngleOut,
+                                           int* ndepOut = nullptr) {
+    constexpr bool SPEC = MODE != 0;
     GrowState st;
     st.n = 1;
+    st.ndep = 0;
     st.aborted = false;
     if (c.lane == 0) {
         const int pb = (pk0 >> 16) * c.PB + (pk0 & 0xFFFF);
         c.ring[0] = pk0; c.R[0] = pk0;
         if (!SPEC) atomicOr(c.used + (pb >> 5), 1u << (pb & 31));
-        else {
+        else if (MODE == 2) {
+            const uint32_t old = atomicMin(c.owner + pb, c.tag);
+            if (old < c.tag) sw_rob(c, c.tag);
+            else if (old != PLF_FREE && old > c.tag) sw_rob(c, old);
+        } else {
             const uint32_t old = atomicMin(c.owner + pb, c.tag);
             if (old < c.tag) atomicOr(c.invalid + (c.tag - 1), 1);
             else if (old != PLF_FREE && old > c.tag) atomicOr(c.invalid + (old - 1), 1);
@@ -504,6 +536,9 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
         int q[GROW_SETS], pk[GROW_SETS], code[GROW_SETS];
         float4 r[GROW_SETS];
         bool valid[GROW_SETS];
+        uint32_t relTag[GROW_SETS];      // streaming mode: the earlier, uncommitted ticket whose claim made me skip this pixel
+        if (MODE == 2 && st.n + 8 * 4 * GROW_SETS > c.maxN) { st.aborted = true; break; }     // no room: left to the committing warp
+        if (MODE == 2 && c.lane == 0) *c.actN = st.n;
 #pragma unroll
         for (int s = 0; s < GROW_SETS; ++s) {
             const int e = s * 4 + (c.lane >> 3);
@@ -511,6 +546,7 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
             pk[s] = 0;
             valid[s] = false;
             code[s] = 0;
+            relTag[s] = 0u;
             if (e < nb) {
                 const int rp = inRing ? c.ring[(i + e) & (GROW_RING - 1)] : c.R[i + e];
                 const int xx = (rp & 0xFFFF) + c.ddx, yy = (rp >> 16) + c.ddy;
@@ -518,8 +554,16 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
                     q[s] = yy * c.PB + xx;
                     pk[s] = (yy << 16) | xx;
                     code[s] = c.G[q[s]];                  // issued together with the bitmap word: one round trip
-                    valid[s] = !used_bit(c.used, q[s]);   // unused implies defined: undefined pixels start as used
-                    if (SPEC && valid[s] && c.owner[q[s]] == c.tag) valid[s] = false;     // my own pixels count as used
+                    if (MODE == 2) {
+                        // owner map only: 0 = undefined, a smaller tag = an earlier region's pixel (used), mine = used,
+                        // a larger tag or PLF_FREE = not used in the sequential order (taken from the later region if accepted)
+                        const uint32_t o = c.ldcg ? c.owner[q[s]] : __ldcg(c.owner + q[s]);      // L2: the map is written with atomics by every warp
+                        valid[s] = o > c.tag;
+                        if (!c.final && o < c.tag && o >= c.floorTag) relTag[s] = o;
+                    } else {
+                        valid[s] = !used_bit(c.used, q[s]);   // unused implies defined: undefined pixels start as used
+                        if (SPEC && valid[s] && c.owner[q[s]] == c.tag) valid[s] = false;     // my own pixels count as used
+                    }
                 }
             }
         }
@@ -530,6 +574,23 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
         // the records of the unused candidates only (a cache-resident table; most candidates are used and load nothing)
 #pragma unroll
         for (int s = 0; s < GROW_SETS; ++s) r[s] = valid[s] ? c.LUT[code[s]] : make_float4(PLF_NOTDEF, 0.f, 0.f, 0.f);
+        if (MODE == 2) {
+            // remember which uncommitted earlier regions this one relied on (distinct tags; rare)
+#pragma unroll
+            for (int s = 0; s < GROW_SETS; ++s) {
+                unsigned rm = __ballot_sync(0xffffffffu, relTag[s] != 0u);
+                while (rm) {
+                    const uint32_t t = __shfl_sync(0xffffffffu, relTag[s], __ffs(rm) - 1);
+                    rm &= ~__ballot_sync(0xffffffffu, relTag[s] == t);
+                    if (st.ndep > SW_MAXDEP) continue;
+                    const bool have = c.lane < st.ndep && c.deps[c.lane] == t;
+                    if (__any_sync(0xffffffffu, have)) continue;
+                    if (st.ndep < SW_MAXDEP && c.lane == 0) c.deps[st.ndep] = t;
+                    ++st.ndep;
+                    __syncwarp();
+                }
+            }
+        }
         unsigned acc[GROW_SETS];
 #pragma unroll
         for (int s = 0; s < GROW_SETS; ++s) {
@@ -541,13 +602,14 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
                 for (int t = 0; t < s; ++t)
                     for (unsigned m = acc[t]; m; m &= m - 1u)
                         if (q[s] == __shfl_sync(0xffffffffu, q[t], __ffs(m) - 1)) valid[s] = false;
-                grow_chain<SPEC>(st, valid[s], q[s], pk[s], r[s], tol, c, dupAll[s], acc[s]);
+                grow_chain<MODE>(st, valid[s], q[s], pk[s], r[s], tol, c, dupAll[s], acc[s]);
                 __syncwarp();
             }
         }
         i += nb;
     }
     regAngleOut = (double)(st.dirty ? fast_atan2_deg(st.sumdy, st.sumdx) : st.regDeg) * kDegToRad;
+    if (MODE == 2 && ndepOut) *ndepOut = st.aborted ? -1 : st.ndep;
     return st.n;
 }
 
@@ -683,7 +745,7 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[33], int& n, double
                                                      __dmul_rn(mean, mean))));
     __syncwarp();
     __threadfence_block();
-    n = grow_region<false>(c, pk0, p0, make_align_tol(tau), regAngle);
+    n = grow_region<0>(c, pk0, p0, make_align_tol(tau), regAngle);
     if (n < 2) return false;
     rect_fit<true>(c, s_sum, n, regAngle, prec, rf);
     density = (double)n / __dmul_rn(lsd_dist(rf.x1, rf.y1, rf.x2, rf.y2), rf.width);
@@ -758,7 +820,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* l
             const int p = __shfl_sync(0xffffffffu, myQ, si);
             if (used_bit(c.used, __shfl_sync(0xffffffffu, myB, si))) continue;   // claimed by a region grown earlier in this chunk
             double regAngle;
-            int n = grow_region<false>(c, pk0, p, precTol, regAngle);
+            int n = grow_region<0>(c, pk0, p, precTol, regAngle);
             if (n < g.minRegSize) continue;
             RectFit rf;
             rect_fit<REFINE>(c, s_sum, n, regAngle, prec, rf);
@@ -871,9 +933,9 @@ __global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const f
         if (w < s_nPick) {
             const int pk0 = s_pickPk[w];
             double regAngle;
-            const int n = grow_region<true>(c, pk0, (pk0 >> 16) * c.W + (pk0 & 0xFFFF), precTol, regAngle);
+            const int n = grow_region<1>(c, pk0, (pk0 >> 16) * c.W + (pk0 & 0xFFFF), precTol, regAngle);
             int hasSeg = 0;
-            if (!grow_is_invalid(c) && n >= g.minRegSize) {
+            if (!grow_is_invalid<1>(c) && n >= g.minRegSize) {
                 RectFit rf;
                 rect_fit<false>(c, s_sum[w], n, regAngle, prec, rf);
                 if (lane == 0) { s_seg[w][0] = rf.x1; s_seg[w][1] = rf.y1; s_seg[w][2] = rf.x2; s_seg[w][3] = rf.y2; }
@@ -955,6 +1017,7 @@ __global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const f
     if (threadIdx.x == 0) nSegsOut[img] = min(s_nSeg, g.segCap);
 }
 
+#include "lsd_sw.cuh"
 #include "lsd_stream.cuh"
 #include "lsd_lane.cuh"
 
@@ -1321,6 +1384,25 @@ static int plf_ensure_mw_buffers(plf_ctx* c) {
     return 0;
 }
 
+// the streaming small-batch grower shares the owner map and the list buffers of the wave grower and adds one failed bit per
+// seed position; its shared-memory block (rings, chunk window) needs the opt-in limit
+static int plf_ensure_sw_buffers(plf_ctx* c) {
+    if (plf_ensure_mw_buffers(c) != 0) return 1;
+    if (!c->d_swFailed) {
+        const size_t nLat = std::min<size_t>((size_t)c->nImgMax, PLF_MW_MAX_IMG);
+        if (cudaMalloc((void**)&c->d_swFailed, nLat * (((size_t)c->g.seedCap + 31) / 32) * sizeof(uint32_t)) != cudaSuccess) {
+            c->d_swFailed = nullptr; cudaGetLastError(); return 1;
+        }
+        if (cudaMalloc((void**)&c->d_swPos, nLat * (size_t)c->g.Ps * c->g.Hs * sizeof(int)) != cudaSuccess) {
+            cudaFree(c->d_swFailed); c->d_swFailed = nullptr; c->d_swPos = nullptr; cudaGetLastError(); return 1;
+        }
+    }
+    static size_t s_granted[64] = {};
+    if (plf_raise_smem_optin(s_granted, c->device, sizeof(SwShared)))
+        cudaFuncSetAttribute(lsd_grow_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SwShared));
+    return 0;
+}
+
 int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     const PlfGeom& g = c->g;
     cudaStream_t s = c->stream;
@@ -1393,11 +1475,21 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         } else if (s_mode && !strcmp(s_mode, "seq"))
             lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                        c->d_nSegs, c->d_err, imgFirst, growNs);
-        else if (nImg <= PLF_MW_MAX_IMG && plf_ensure_mw_buffers(c) == 0)
-            // few images: several regions of each image in flight (a block of 8 warps per image)
+        else if (nImg <= PLF_MW_MAX_IMG && s_mode && !strcmp(s_mode, "mw") && plf_ensure_mw_buffers(c) == 0) {
+            // the wave-synchronous predecessor of the streaming grower (kept for comparison)
+            if (c->ownerDirty) {
+                cudaMemsetAsync(c->d_owner, 0xFF, std::min<size_t>((size_t)c->nImgMax, PLF_MW_MAX_IMG) * (size_t)g.Ps * g.Hs * sizeof(uint32_t), s);
+                c->ownerDirty = false;
+            }
             lsd_grow_mw_kernel<<<nImg, 32 * MW, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_owner, c->d_regMW,
                                                         c->d_segs, c->d_nSegs, c->d_err, imgFirst);
-        else
+        } else if (nImg <= PLF_MW_MAX_IMG && plf_ensure_sw_buffers(c) == 0) {
+            // few images: 16 regions of each image in flight, one per warp, streaming with an in-order commit pointer
+            c->ownerDirty = true;
+            static const int s_swFlags = getenv("PLF_SW_FLAGS") ? atoi(getenv("PLF_SW_FLAGS")) : 0;      // experiment switches, see lsd_sw.cuh
+            lsd_grow_sw_kernel<<<nImg, 32 * SW_NW, sizeof(SwShared), s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_owner,
+                                                                         c->d_regMW, c->d_swPos, c->d_swFailed, c->d_segs, c->d_nSegs, c->d_err, imgFirst, s_swFlags);
+        } else
             lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                        c->d_nSegs, c->d_err, imgFirst, growNs);
     }

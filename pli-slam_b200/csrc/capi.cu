@@ -364,7 +364,7 @@ PLF_API int plf_destroy(plf_ctx* c) {
     void* ptrs[] = {c->d_pyr, c->d_blur, c->d_score, c->d_tilesBlur, c->d_tilesFast, c->d_lin, c->d_cells, c->d_cellCount, c->d_cand, c->d_scratch, c->d_lvlKp, c->d_lvlN,
                     c->d_kpTmp, c->d_descTmp, c->d_kp, c->d_desc, c->d_nKp, c->d_mono, c->d_err, c->d_uRight, c->d_depth,
                     c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_n2max, c->d_seeds,
-                    c->d_nSeeds, c->d_n2, c->d_used, c->d_reg, c->d_owner, c->d_regMW, c->d_swFailed, c->d_swPos, c->d_stream, c->d_laneRT, c->d_scr, c->d_growNs, c->d_nReg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
+                    c->d_nSeeds, c->d_n2, c->d_used, c->d_reg, c->d_owner, c->d_regMW, c->d_swPos, c->d_stream, c->d_laneRT, c->d_scr, c->d_growNs, c->d_nReg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
                     c->d_sobel, c->d_lbd, c->d_ldesc, c->d_rowMask, c->d_dirR, c->d_dmat, c->d_m21, c->d_m12, c->d_disp,
                     c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage, c->d_rmap[0], c->d_rmap[1], c->d_gridStart, c->d_gridIdx, c->d_bpPose, c->d_bpX, c->d_bpL, c->d_bowWord, c->d_bowNode, c->d_bowWeight, c->d_projQ, c->d_projCount, c->d_projStart, c->d_projPool,
                     c->voc[0].childFirst, c->voc[0].childCount, c->voc[0].child, c->voc[0].word, c->voc[0].desc, c->voc[0].weight,

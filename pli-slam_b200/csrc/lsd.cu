@@ -335,7 +335,7 @@ struct GrowCtx {
     bool final;         // grown by the committing warp: every earlier region is final, nobody can take a pixel from it
 };
 #define PLF_FREE 0xFFFFFFFFu
-#define SW_WIN 1024                 // chunks (of 32 seed positions) between the commit pointer and the scan pointer
+#define SW_WIN 512                  // chunks (of 32 seed positions) between the commit pointer and the scan pointer
 #define SW_MAXDEP 8
 __device__ __forceinline__ void sw_rob(const GrowCtx& c, uint32_t victimTag) {
     atomicOr(c.robbed + (((victimTag - 1u) >> 5) & (SW_WIN - 1)), 1u << ((victimTag - 1u) & 31u));
@@ -1384,17 +1384,14 @@ static int plf_ensure_mw_buffers(plf_ctx* c) {
     return 0;
 }
 
-// the streaming small-batch grower shares the owner map and the list buffers of the wave grower and adds one failed bit per
-// seed position; its shared-memory block (rings, chunk window) needs the opt-in limit
+// the streaming small-batch grower shares the owner map and the list buffers of the wave grower and adds the seed-list position of
+// every pixel; its shared-memory block (rings, chunk window) needs the opt-in limit
 static int plf_ensure_sw_buffers(plf_ctx* c) {
     if (plf_ensure_mw_buffers(c) != 0) return 1;
-    if (!c->d_swFailed) {
+    if (!c->d_swPos) {
         const size_t nLat = std::min<size_t>((size_t)c->nImgMax, PLF_MW_MAX_IMG);
-        if (cudaMalloc((void**)&c->d_swFailed, nLat * (((size_t)c->g.seedCap + 31) / 32) * sizeof(uint32_t)) != cudaSuccess) {
-            c->d_swFailed = nullptr; cudaGetLastError(); return 1;
-        }
         if (cudaMalloc((void**)&c->d_swPos, nLat * (size_t)c->g.Ps * c->g.Hs * sizeof(int)) != cudaSuccess) {
-            cudaFree(c->d_swFailed); c->d_swFailed = nullptr; c->d_swPos = nullptr; cudaGetLastError(); return 1;
+            c->d_swPos = nullptr; cudaGetLastError(); return 1;
         }
     }
     static size_t s_granted[64] = {};
@@ -1488,7 +1485,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
             c->ownerDirty = true;
             static const int s_swFlags = getenv("PLF_SW_FLAGS") ? atoi(getenv("PLF_SW_FLAGS")) : 0;      // experiment switches, see lsd_sw.cuh
             lsd_grow_sw_kernel<<<nImg, 32 * SW_NW, sizeof(SwShared), s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_owner,
-                                                                         c->d_regMW, c->d_swPos, c->d_swFailed, c->d_segs, c->d_nSegs, c->d_err, imgFirst, s_swFlags);
+                                                                         c->d_regMW, c->d_swPos, c->d_segs, c->d_nSegs, c->d_err, imgFirst, s_swFlags);
         } else
             lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                        c->d_nSegs, c->d_err, imgFirst, growNs);

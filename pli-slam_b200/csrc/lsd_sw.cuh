@@ -45,6 +45,10 @@
 #define SW_HDR 16                   // ints in front of a record's pixel list: tag n flags ndep seg[4] deps[8]
 #define SW_SEGQ 2048                // segments a warp can leave uncommitted
 #define SW_PARK_DIST 2.5f           // px from a growing region's axis
+#define SW_CHDEP 8                  // relied-on tags a chunk can keep in shared memory (more: slow path)
+#define SW_AHEAD (SW_WIN / 2)       // chunks the scan pointer may run ahead of the commit pointer: a slot (robbed / dirty / failed
+                                    // bits) is reused SW_WIN chunks later, so the failed bit of a region outlives every region
+                                    // that could have relied on it
 
 struct SwShared {
     int ring[SW_NW][GROW_RING];
@@ -56,7 +60,10 @@ struct SwShared {
     int chN[SW_WIN];                // records of the chunk
     unsigned robbed[SW_WIN];        // per position: the region lost a pixel
     unsigned dirty[SW_WIN];         // per position: the seed pixel was given back after the chunk was handed out
-    unsigned slow[SW_WIN];          // per position: needs a look at commit (not started, given up, relied on somebody)
+    unsigned slow[SW_WIN];          // per position: needs a look at commit (not started, given up, too many dependencies)
+    unsigned failedW[SW_WIN];       // per position: the region gave pixels back (whoever relied on it must be grown again)
+    uint32_t depTag[SW_WIN][SW_CHDEP];   // tags the records of the chunk relied on
+    int depN[SW_WIN];
     float4 act[SW_NW];              // region being grown by warp w: seed x, y, cos, sin of its level-line angle
     float actDeg[SW_NW];
     int actN[SW_NW];
@@ -68,10 +75,13 @@ struct SwShared {
 #define SW_CNT(i) do { if ((flags & 4) && lane == 0) atomicAdd(&sh.cnt[i], 1); } while (0)
 
 __device__ __forceinline__ uint32_t sw_ld_owner(const uint32_t* p) { return __ldcg(p); }
+__device__ __forceinline__ bool sw_failed(const SwShared& sh, uint32_t tag) {
+    return (*(volatile const unsigned*)&sh.failedW[((tag - 1u) >> 5) & (SW_WIN - 1)] >> ((tag - 1u) & 31u)) & 1u;
+}
 
 // gives the claims of a region back (pixels it still holds), marks their seed positions dirty and tells everybody who
 // relied on the region
-__device__ __forceinline__ void sw_withdraw(SwShared& sh, uint32_t* O, const int* P, uint32_t* failed, const int* list, int n,
+__device__ __forceinline__ void sw_withdraw(SwShared& sh, uint32_t* O, const int* P, const int* list, int n,
                                             uint32_t tag, int PB, int lane) {
     for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + lane;
@@ -85,7 +95,7 @@ __device__ __forceinline__ void sw_withdraw(SwShared& sh, uint32_t* O, const int
         if (pos >= 0 && (pos >> 5) < *(volatile int*)&sh.scanChunk)
             atomicOr(&sh.dirty[(pos >> 5) & (SW_WIN - 1)], 1u << (pos & 31));
     }
-    if (lane == 0) atomicOr(failed + ((tag - 1u) >> 5), 1u << ((tag - 1u) & 31u));
+    if (lane == 0) atomicOr(&sh.failedW[((tag - 1u) >> 5) & (SW_WIN - 1)], 1u << ((tag - 1u) & 31u));
     __syncwarp();
 }
 
@@ -101,7 +111,7 @@ __device__ __forceinline__ void sw_segment(const RectFit& rf, double lsdScale, f
 
 __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, const float4* lut, const int* gmap, const int* seeds,
                                                                 const int* nSeeds, const uint32_t* usedAll, uint32_t* ownerAll,
-                                                                int* regAll, int* posAll, uint32_t* failedAll, float* segs,
+                                                                int* regAll, int* posAll, float* segs,
                                                                 int* nSegsOut, int* err, int imgFirst, int flags) {
     extern __shared__ __align__(16) unsigned char sw_smem[];
     SwShared& sh = *reinterpret_cast<SwShared*>(sw_smem);
@@ -116,8 +126,6 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
     float4* const Sq = reinterpret_cast<float4*>(Rw + warpCap);
     uint32_t* const O = ownerAll + (size_t)blockIdx.x * npb;
     int* const P = posAll + (size_t)blockIdx.x * npb;
-    const int failedWords = (g.seedCap + 31) >> 5;
-    uint32_t* const failed = failedAll + (size_t)blockIdx.x * failedWords;
     const int* S = seeds + (size_t)img * g.seedCap;
     float4* out = reinterpret_cast<float4*>(segs + (size_t)img * g.segCap * 4);
     const int ns = nSeeds[img];
@@ -157,8 +165,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
             const int sd = S[p];
             P[(sd >> 16) * c.PB + (sd & 0xFFFF)] = p;
         }
-        for (int i = threadIdx.x; i < failedWords; i += 32 * SW_NW) failed[i] = 0u;
-        for (int i = threadIdx.x; i < SW_WIN; i += 32 * SW_NW) { sh.chStat[i] = 0; sh.robbed[i] = 0u; sh.dirty[i] = 0u; sh.slow[i] = 0u; }
+        for (int i = threadIdx.x; i < SW_WIN; i += 32 * SW_NW) { sh.chStat[i] = 0; sh.robbed[i] = 0u; sh.dirty[i] = 0u; sh.slow[i] = 0u; sh.failedW[i] = 0u; sh.depN[i] = 0; }
         if (threadIdx.x < SW_NW) sh.actTag[threadIdx.x] = 0u;
         if (threadIdx.x == 0) { sh.scanChunk = 0; sh.commitChunk = 0; sh.lock = 0; sh.nSeg = 0; }
         if (threadIdx.x < 16) sh.cnt[threadIdx.x] = 0;
@@ -215,8 +222,14 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                     __threadfence_block();
                     const int recPack = *(volatile int*)&sh.chRec[slot];
                     const int nRec = *(volatile int*)&sh.chN[slot];
-                    const unsigned bad = *(volatile unsigned*)&sh.robbed[slot] | *(volatile unsigned*)&sh.dirty[slot] |
-                                         *(volatile unsigned*)&sh.slow[slot] | ((flags & 64) ? 1u : 0u);
+                    unsigned bad = *(volatile unsigned*)&sh.robbed[slot] | *(volatile unsigned*)&sh.dirty[slot] |
+                                   *(volatile unsigned*)&sh.slow[slot] | ((flags & 64) ? 1u : 0u);
+                    {
+                        // did a region the chunk's records relied on give pixels back?
+                        const int dn = *(volatile int*)&sh.depN[slot];
+                        const bool fd = lane < dn && sw_failed(sh, *(volatile uint32_t*)&sh.depTag[slot][lane]);
+                        if (dn > 0 && __any_sync(0xffffffffu, fd)) { bad |= 1u; SW_CNT(13); }
+                    }
                     if (bad == 0u) {
                         // fast path: every record of the chunk is final, every other seed is still an earlier region's
                         const int segPack = *(volatile int*)&sh.chSeg[slot];
@@ -246,7 +259,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                             // region; its pixels go back BEFORE anything behind it is looked at (they may free a seed there)
                             if (recIdx < nRec && (uint32_t)rec[0] < tagStar) {
                                 const uint32_t dead = (uint32_t)rec[0];
-                                sw_withdraw(sh, O, P, failed, rec + SW_HDR, rec[1], dead, c.PB, lane);
+                                sw_withdraw(sh, O, P, rec + SW_HDR, rec[1], dead, c.PB, lane);
                                 rec += (SW_HDR + rec[1] + 3) & ~3;
                                 ++recIdx;
                                 cur = (int)((dead - 1u) & 31u) + 1;
@@ -262,10 +275,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                                           !((*(volatile unsigned*)&sh.robbed[slot] >> l) & 1u);
                                 if (ok && nd > 0) {
                                     bool failedDep = false;
-                                    if (lane < nd) {
-                                        const uint32_t d = (uint32_t)rec[8 + lane] - 1u;
-                                        failedDep = (sw_ld_owner(failed + (d >> 5)) >> (d & 31u)) & 1u;
-                                    }
+                                    if (lane < nd) failedDep = sw_failed(sh, (uint32_t)rec[8 + lane]);
                                     ok = !__any_sync(0xffffffffu, failedDep);
                                 }
                                 if (ok) {
@@ -278,7 +288,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                                     done = true;
                                 } else {
                                     SW_CNT(2);
-                                    sw_withdraw(sh, O, P, failed, rec + SW_HDR, n, tagStar, c.PB, lane);
+                                    sw_withdraw(sh, O, P, rec + SW_HDR, n, tagStar, c.PB, lane);
                                 }
                                 rec += (SW_HDR + n + 3) & ~3;
                                 ++recIdx;
@@ -330,12 +340,12 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
         if ((flags & 32) && w > 0) { __nanosleep(1000); continue; }
         if (lane == 0 && head + SW_HDR + 4096 < warpCap && segHead + 32 <= SW_SEGQ) {
             const int s = *(volatile int*)&sh.scanChunk;
-            if (s < nChunks && s < *vCommit + SW_WIN && atomicCAS(&sh.scanChunk, s, s + 1) == s) ch = s;
+            if (s < nChunks && s < *vCommit + SW_AHEAD && atomicCAS(&sh.scanChunk, s, s + 1) == s) ch = s;
         }
         ch = __shfl_sync(0xffffffffu, ch, 0);
         if (ch < 0) { SW_CNT(7); __nanosleep(100); continue; }
         const int slot = ch & (SW_WIN - 1);
-        if (lane == 0) { atomicExch(&sh.robbed[slot], 0u); atomicExch(&sh.dirty[slot], 0u); sh.chStat[slot] = 1; }
+        if (lane == 0) { atomicExch(&sh.robbed[slot], 0u); atomicExch(&sh.dirty[slot], 0u); atomicExch(&sh.failedW[slot], 0u); sh.depN[slot] = 0; sh.chStat[slot] = 1; }
         __syncwarp();
         __threadfence_block();
         const int p = ch * 32 + lane;
@@ -345,7 +355,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
         const uint32_t o0 = seed >= 0 ? sw_ld_owner(O + pb) : 0u;
         unsigned gm = __ballot_sync(0xffffffffu, seed >= 0 && o0 > myTag);
         const int recStart = head, segStart = segHead;
-        int nRec = 0;
+        int nRec = 0, chDep = 0;
         unsigned slowMask = 0u;
         while (gm) {
             const int l = __ffs(gm) - 1;
@@ -374,9 +384,12 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
             }
             int nd = -1, n = 0;
             double regAngle;
-            for (int attempt = 0; attempt < 2; ++attempt) {
+            for (int attempt = 0; attempt < 3; ++attempt) {
                 if (attempt > 0) {
-                    // robbed while growing: whoever took the pixels is mostly done with this neighbourhood; try once more
+                    // robbed while growing (mostly at a junction of two edges): whoever took the pixels needs a few more steps
+                    // in this neighbourhood; wait a little, then try again
+                    const long long tw = clock64() + (attempt == 1 ? 6000 : 24000);
+                    while (clock64() < tw) __nanosleep(200);
                     if (lane == 0) atomicAnd(&sh.robbed[slot], ~(1u << l));
                     __syncwarp();
                     __threadfence_block();
@@ -387,7 +400,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                 if (nd >= 0 && !grow_is_invalid<2>(c)) break;
                 SW_CNT(1);
                 if ((flags & 4) && lane == 0) atomicAdd(&sh.cnt[9], n);
-                sw_withdraw(sh, O, P, failed, Rw + head + SW_HDR, n, tag, c.PB, lane);
+                sw_withdraw(sh, O, P, Rw + head + SW_HDR, n, tag, c.PB, lane);
                 nd = -1;
                 if (flags & 16) break;
             }
@@ -402,7 +415,13 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                 if (lane == 0) Sq[segHead] = make_float4(sg[0], sg[1], sg[2], sg[3]);
                 ++segHead;
             }
-            if (nd > 0) { slowMask |= 1u << l; SW_CNT(12); }
+            if (nd > 0) {
+                SW_CNT(12);
+                if (nd <= SW_MAXDEP && chDep + nd <= SW_CHDEP) {
+                    if (lane < nd) sh.depTag[slot][chDep + lane] = c.deps[lane];
+                    chDep += nd;
+                } else slowMask |= 1u << l;
+            }
             int* hdr = Rw + head;
             if (lane == 0) {
                 hdr[0] = (int)tag; hdr[1] = n; hdr[2] = rflags; hdr[3] = nd;
@@ -420,6 +439,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
             sh.chSeg[slot] = ((segHead - segStart) << 16) | segStart;
             sh.chN[slot] = nRec;
             sh.slow[slot] = slowMask;
+            sh.depN[slot] = chDep;
             __threadfence_block();
             sh.chStat[slot] = 2;
         }
@@ -428,8 +448,8 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
     }
     __syncthreads();
     if ((flags & 4) && threadIdx.x == 0 && blockIdx.x == 0)
-        printf("sw img %d: ns %d chunks %d | recorded %d (%d px, %d with deps) given up %d (%d px, %d retried) failedRec %d grownAtCommit %d (%d px) parked %d | chunks fast %d slow %d | idle spins %d | cycles total %lld commit %lld (regrow %lld) segs %d\n",
-               img, ns, nChunks, sh.cnt[0], sh.cnt[10], sh.cnt[12], sh.cnt[1], sh.cnt[9], sh.cnt[11], sh.cnt[2], sh.cnt[3], sh.cnt[8], sh.cnt[4], sh.cnt[5], sh.cnt[6], sh.cnt[7],
+        printf("sw img %d: ns %d chunks %d | recorded %d (%d px, %d with deps) given up %d (%d px, %d retried) failedRec %d grownAtCommit %d (%d px) parked %d | chunks fast %d slow %d (failed dep %d) | idle spins %d | cycles total %lld commit %lld (regrow %lld) segs %d\n",
+               img, ns, nChunks, sh.cnt[0], sh.cnt[10], sh.cnt[12], sh.cnt[1], sh.cnt[9], sh.cnt[11], sh.cnt[2], sh.cnt[3], sh.cnt[8], sh.cnt[4], sh.cnt[5], sh.cnt[6], sh.cnt[13], sh.cnt[7],
                clock64() - tStart, sh.clk[0], sh.clk[1], sh.nSeg);
     if (threadIdx.x == 0) nSegsOut[img] = min(sh.nSeg, g.segCap);
 }

@@ -125,7 +125,6 @@ struct plf_ctx {
     int* d_reg = nullptr;            // [nImg][Hs*Ws] region pixel list, packed y<<16|x (reused per region)
     uint32_t* d_owner = nullptr;     // small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][Hs][Ps] owner tags of the current wave (PLF_FREE = none)
     int* d_regMW = nullptr;          // small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][8][Hs*Ws] region lists, one per wave slot
-    uint32_t* d_swFailed = nullptr;  // streaming small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][seedCap/32] failed-region bits
     int* d_swPos = nullptr;          // streaming small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][Hs][Ps] seed-list position of every defined pixel
     bool ownerDirty = false;         // d_owner holds the tags of lsd_grow_sw_kernel (lsd_grow_mw_kernel expects PLF_FREE everywhere)
     int* d_stream = nullptr;         // streaming grower: [nImg][StreamLayout.total] owner map, list chunks, ticket table, region table (lazy)

@@ -640,7 +640,7 @@ def test_repeated_calls_replay_the_graph(plf, product, oracle):
 
 def test_large_batch_sequential_grower_matches_oracle(plf, product, oracle):
     """Launches of more than 128 images use the one-warp-per-image region grower (the kernel the benchmark runs); smaller
-    ones use the multi-region grower.  72 pairs (144 images, 8 distinct pairs repeated) against the oracle, exactly, and
+    ones use the streaming multi-warp grower.  72 pairs (144 images, 8 distinct pairs repeated) against the oracle, exactly, and
     against the same pairs sent through a small batch."""
     W, H = 752, 480
     L8, R8 = plf.synth_batch(W, H, [101, 102, 103, 104, 105, 106, 107, 108])
@@ -661,3 +661,24 @@ def test_large_batch_sequential_grower_matches_oracle(plf, product, oracle):
         n, nl = int(ro.n_kp_left[r]), int(ro.n_kl_left[r])
         assert np.array_equal(rg.kp_left[b, :n], ro.kp_left[r, :n]) and np.array_equal(rg.u_right[b, :n], ro.u_right[r, :n])
         assert np.array_equal(rg.line_match12[b, :nl], ro.line_match12[r, :nl])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,batch", [(752, 480, 1), (752, 480, 5), (641, 479, 2), (1241, 376, 3)])
+def test_streaming_small_batch_grower_matches_oracle(plf, product, oracle, W, H, batch):
+    """Launches of at most 128 images go through lsd_grow_sw_kernel (one region per warp, 16 regions of an image in flight,
+    in-order commit pointer): every segment-derived array equal to the oracle with ALL lines kept, over several calls on one
+    context (owner map, position map and record buffers are reused from call to call)."""
+    f = plf.Frontend(product, width=W, height=H, max_batch=batch, lsd_nfeatures=0)
+    o = plf.Frontend(oracle, width=W, height=H, max_batch=batch, lsd_nfeatures=0)
+    for call in range(3):
+        L, R = plf.synth_batch(W, H, [9100 + 17 * call + b for b in range(batch)])
+        rg, ro = f.frontend_batch(L, R), o.frontend_batch(L, R)
+        for b in range(batch):
+            for side in ("left", "right"):
+                nl = int(getattr(ro, "n_kl_" + side)[b])
+                assert int(getattr(rg, "n_kl_" + side)[b]) == nl and nl > 100, (call, b, side)
+                assert np.array_equal(getattr(rg, "kl_" + side)[b, :nl], getattr(ro, "kl_" + side)[b, :nl]), (call, b, side)
+                assert np.array_equal(getattr(rg, "ldesc_" + side)[b, :nl], getattr(ro, "ldesc_" + side)[b, :nl]), (call, b, side)
+            nl = int(ro.n_kl_left[b])
+            assert np.array_equal(rg.line_match12[b, :nl], ro.line_match12[b, :nl]), (call, b)

@@ -236,6 +236,9 @@ static int create_buffers(plf_ctx* c, const plf_params* p, std::vector<PlfCell>&
     const size_t nImg = (size_t)p->max_batch * 2, nSlot = p->max_batch;
     c->nImgMax = (int)nImg;
     PLF_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PLF_CUDA_OK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    PLF_CUDA_OK(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    PLF_CUDA_OK(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
     const size_t npx = (size_t)g.Ws * g.Hs;
     PLF_CUDA_OK(dalloc(&c->d_pyr, nImg * g.pyrBytes + 1024));   // +256: the FAST tile loader reads whole 32-bit words
     PLF_CUDA_OK(dalloc(&c->d_blur, nImg * g.pyrBytes));
@@ -364,7 +367,7 @@ PLF_API int plf_destroy(plf_ctx* c) {
     void* ptrs[] = {c->d_pyr, c->d_blur, c->d_score, c->d_tilesBlur, c->d_tilesFast, c->d_lin, c->d_cells, c->d_cellCount, c->d_cand, c->d_scratch, c->d_lvlKp, c->d_lvlN,
                     c->d_kpTmp, c->d_descTmp, c->d_kp, c->d_desc, c->d_nKp, c->d_mono, c->d_err, c->d_uRight, c->d_depth,
                     c->d_sad, c->d_lsdBlur, c->d_lsdU, c->d_n2max, c->d_seeds,
-                    c->d_nSeeds, c->d_n2, c->d_used, c->d_reg, c->d_owner, c->d_regMW, c->d_swPos, c->d_stream, c->d_laneRT, c->d_scr, c->d_growNs, c->d_nReg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
+                    c->d_nSeeds, c->d_n2, c->d_used, c->d_reg, c->d_owner, c->d_regMW, c->d_swOwner, c->d_swPos, c->d_swReg, c->d_stream, c->d_laneRT, c->d_scr, c->d_growNs, c->d_nReg, c->d_segs, c->d_nSegs, c->d_kl, c->d_klAll, c->d_nKl, c->d_lbdBlur,
                     c->d_sobel, c->d_lbd, c->d_ldesc, c->d_rowMask, c->d_dirR, c->d_dmat, c->d_m21, c->d_m12, c->d_disp,
                     c->d_le, c->d_mA, c->d_mB, c->d_mOut, c->d_mOut2, c->d_stage, c->d_rmap[0], c->d_rmap[1], c->d_gridStart, c->d_gridIdx, c->d_bpPose, c->d_bpX, c->d_bpL, c->d_bowWord, c->d_bowNode, c->d_bowWeight, c->d_projQ, c->d_projCount, c->d_projStart, c->d_projPool,
                     c->voc[0].childFirst, c->voc[0].childCount, c->voc[0].child, c->voc[0].word, c->voc[0].desc, c->voc[0].weight,
@@ -373,6 +376,9 @@ PLF_API int plf_destroy(plf_ctx* c) {
     if (c->graphExec) cudaGraphExecDestroy(c->graphExec);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->evFork) cudaEventDestroy(c->evFork);
+    if (c->evJoin) cudaEventDestroy(c->evJoin);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return PLF_OK;
@@ -695,9 +701,25 @@ PLF_API int plf_batch_run(plf_ctx* c, int batch) {
         return PLF_OK;
     }
     const bool capture = wantGraph && cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    // The point path and the line path share nothing but the input image (level 0 of the pyramid block, read-only for
+    // both), so the line path is forked onto a second stream and joined in front of the stereo matchers: inside one call
+    // the latency-bound region grower runs beside the issue-bound ORB kernels.  Stage timing (marks between the stages of
+    // ONE stream) and PLF_NO_FORK=1 keep the sequential order.
+    static const bool s_noFork = getenv("PLF_NO_FORK") != nullptr;
+    const bool fork = !s_noFork && !c->stageTiming && c->p.has_points && c->p.has_lines && c->stream2;
+    if (fork) {
+        cudaStream_t s1 = c->stream;
+        cudaEventRecord(c->evFork, s1);
+        cudaStreamWaitEvent(c->stream2, c->evFork, 0);
+        c->stream = c->stream2;
+        n += plf_launch_lines(c, 0, 2 * batch);
+        c->stream = s1;
+        cudaEventRecord(c->evJoin, c->stream2);
+    }
     if (c->p.has_points) n += plf_launch_orb(c, 0, 2 * batch, 0, 0);
     else cudaMemsetAsync(c->d_nKp, 0, (size_t)2 * batch * sizeof(int), c->stream);
-    if (c->p.has_lines) n += plf_launch_lines(c, 0, 2 * batch);
+    if (fork) cudaStreamWaitEvent(c->stream, c->evJoin, 0);
+    else if (c->p.has_lines) n += plf_launch_lines(c, 0, 2 * batch);
     if (c->p.has_lines) n += plf_launch_stereo_lines(c, 0, batch);
     if (c->p.has_points) n += plf_launch_stereo_points(c, 0, batch);
     plf_mark(c, "d2h");

@@ -294,14 +294,26 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, co
 
 // Sequential (scalar-loop order) accumulation of three quantities over the pixels of a region: the 32 lanes write
 // their three products to shared memory, then lanes 0..2 each own one accumulator and add the 32 values in order.
-__device__ __forceinline__ void seq_sum3(double (*buf)[33], double a, double b, double c, unsigned cnt, int lane,
+__device__ __forceinline__ void seq_sum3(double (*buf)[34], double a, double b, double c, unsigned cnt, int lane,
                                          double& acc) {
     buf[0][lane] = a;
     buf[1][lane] = b;
     buf[2][lane] = c;
     __syncwarp();
-    if (lane < 3)
-        for (unsigned j = 0; j < cnt; ++j) acc = __dadd_rn(acc, buf[lane][j]);
+    if (lane < 3) {
+        if (cnt == 32) {
+            // full chunk: 16-byte shared loads, the 32 additions in list order (rows are 34 doubles: 16-byte aligned)
+            const double2* row = reinterpret_cast<const double2*>(buf[lane]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const double2 v = row[j];
+                acc = __dadd_rn(acc, v.x);
+                acc = __dadd_rn(acc, v.y);
+            }
+        } else {
+            for (unsigned j = 0; j < cnt; ++j) acc = __dadd_rn(acc, buf[lane][j]);
+        }
+    }
     __syncwarp();
 }
 
@@ -547,6 +559,7 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
             valid[s] = false;
             code[s] = 0;
             relTag[s] = 0u;
+            if (s * 4 >= nb) continue;             // (warp-uniform: a frontier of at most 4 entries skips the second set as a whole)
             if (e < nb) {
                 const int rp = inRing ? c.ring[(i + e) & (GROW_RING - 1)] : c.R[i + e];
                 const int xx = (rp & 0xFFFF) + c.ddx, yy = (rp >> 16) + c.ddy;
@@ -573,7 +586,10 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
         for (int s = 0; s < GROW_SETS; ++s) dupAll[s] = (s * 4 < nb) ? __match_any_sync(0xffffffffu, q[s]) : 0u;
         // the records of the unused candidates only (a cache-resident table; most candidates are used and load nothing)
 #pragma unroll
-        for (int s = 0; s < GROW_SETS; ++s) r[s] = valid[s] ? c.LUT[code[s]] : make_float4(PLF_NOTDEF, 0.f, 0.f, 0.f);
+        for (int s = 0; s < GROW_SETS; ++s) {
+            r[s] = make_float4(PLF_NOTDEF, 0.f, 0.f, 0.f);
+            if (s * 4 < nb && valid[s]) r[s] = c.LUT[code[s]];
+        }
         if (MODE == 2) {
             // remember which uncommitted earlier regions this one relied on (distinct tags; rare)
 #pragma unroll
@@ -617,7 +633,7 @@ struct RectFit { double x1, y1, x2, y2, width; };
 
 // LSD region2rect + get_theta over c.R[0..n): scalar-loop summation order for the weighted sums
 template <bool WIDTH>
-__device__ __forceinline__ void rect_fit(const GrowCtx& c, double (*s_sum)[33], int n, double regAngle, double prec, RectFit& rf) {
+__device__ __forceinline__ void rect_fit(const GrowCtx& c, double (*s_sum)[34], int n, double regAngle, double prec, RectFit& rf) {
     const int lane = c.lane;
     double acc3 = 0;      // lane 0: sum x*w, lane 1: sum y*w, lane 2: sum w
     for (int i0 = 0; i0 < n; i0 += 32) {
@@ -708,7 +724,7 @@ __device__ __forceinline__ double lsd_dist_sq(double x1, double y1, double x2, d
 
 // LSD refine() for refine = 1 (STANDARD): if the rectangle is too sparse, re-grow with a tolerance taken from the local
 // angle spread, then shrink the region radius until it is dense.  Returns false if the region is rejected.
-__device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[33], int& n, double& regAngle, double prec, double densityTh,
+__device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[34], int& n, double& regAngle, double prec, double densityTh,
                            RectFit& rf) {
     const int lane = c.lane, W = c.W;
     double density = (double)n / __dmul_rn(lsd_dist(rf.x1, rf.y1, rf.x2, rf.y2), rf.width);
@@ -786,7 +802,7 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* l
                                                       const int* nSeeds, uint32_t* usedAll, int* reg, float* segs,
                                                       int* nSegsOut, int* err, int imgFirst, unsigned long long* imgNs) {
     __shared__ int ring[GROW_RING];
-    __shared__ double s_sum[3][33];
+    __shared__ __align__(16) double s_sum[3][34];
     const int img = imgFirst + blockIdx.x, lane = threadIdx.x;
     // stage timing only: nanoseconds this image's warp ran (one warp per image: a launch lasts as long as its slowest image)
     unsigned long long t0 = 0;
@@ -867,7 +883,7 @@ __global__ void __launch_bounds__(32 * MW) lsd_grow_mw_kernel(PlfGeom g, const f
                                                             const int* nSeeds, uint32_t* usedAll, uint32_t* ownerAll, int* regAll,
                                                             float* segs, int* nSegsOut, int* err, int imgFirst) {
     __shared__ int ring[MW][GROW_RING];
-    __shared__ double s_sum[MW][3][33];
+    __shared__ __align__(16) double s_sum[MW][3][34];
     __shared__ double s_seg[MW][4];
     __shared__ int s_pickPos[MW], s_pickPk[MW], s_n[MW], s_inv[MW], s_hasSeg[MW];
     __shared__ int s_nPick, s_pos, s_scanEnd, s_nSeg, s_segIdx[MW];
@@ -1384,14 +1400,22 @@ static int plf_ensure_mw_buffers(plf_ctx* c) {
     return 0;
 }
 
-// the streaming small-batch grower shares the owner map and the list buffers of the wave grower and adds the seed-list position of
-// every pixel; its shared-memory block (rings, chunk window) needs the opt-in limit
+// scratch of the streaming small-batch grower (owner map, seed-position map, record buffers: 11 MB per 752x480 image), for up
+// to PLF_SW_MAX_IMG images, allocated the first time a small launch happens; its shared-memory block (rings, chunk window)
+// needs the opt-in limit
 static int plf_ensure_sw_buffers(plf_ctx* c) {
-    if (plf_ensure_mw_buffers(c) != 0) return 1;
-    if (!c->d_swPos) {
-        const size_t nLat = std::min<size_t>((size_t)c->nImgMax, PLF_MW_MAX_IMG);
-        if (cudaMalloc((void**)&c->d_swPos, nLat * (size_t)c->g.Ps * c->g.Hs * sizeof(int)) != cudaSuccess) {
-            c->d_swPos = nullptr; cudaGetLastError(); return 1;
+    if (!c->d_swOwner) {
+        const size_t nLat = std::min<size_t>((size_t)c->nImgMax, PLF_SW_MAX_IMG);
+        const size_t npb = (size_t)c->g.Ps * c->g.Hs, npxA = ((size_t)c->g.Ws * c->g.Hs + 3) & ~(size_t)3;
+        const size_t perImg = npxA + (size_t)PLF_MW_WARPS * PLF_SW_WARPBUF;
+        if (cudaMalloc((void**)&c->d_swOwner, nLat * npb * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMalloc((void**)&c->d_swPos, nLat * npb * sizeof(int)) != cudaSuccess ||
+            cudaMalloc((void**)&c->d_swReg, nLat * perImg * sizeof(int)) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(c->d_swOwner); cudaFree(c->d_swPos); cudaFree(c->d_swReg);
+            c->d_swOwner = nullptr; c->d_swPos = nullptr; c->d_swReg = nullptr;
+            cudaGetLastError();
+            return 1;                      // fall back to the sequential kernel
         }
     }
     static size_t s_granted[64] = {};
@@ -1474,18 +1498,13 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
                                                        c->d_nSegs, c->d_err, imgFirst, growNs);
         else if (nImg <= PLF_MW_MAX_IMG && s_mode && !strcmp(s_mode, "mw") && plf_ensure_mw_buffers(c) == 0) {
             // the wave-synchronous predecessor of the streaming grower (kept for comparison)
-            if (c->ownerDirty) {
-                cudaMemsetAsync(c->d_owner, 0xFF, std::min<size_t>((size_t)c->nImgMax, PLF_MW_MAX_IMG) * (size_t)g.Ps * g.Hs * sizeof(uint32_t), s);
-                c->ownerDirty = false;
-            }
             lsd_grow_mw_kernel<<<nImg, 32 * MW, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_owner, c->d_regMW,
                                                         c->d_segs, c->d_nSegs, c->d_err, imgFirst);
-        } else if (nImg <= PLF_MW_MAX_IMG && plf_ensure_sw_buffers(c) == 0) {
+        } else if (nImg <= PLF_SW_MAX_IMG && plf_ensure_sw_buffers(c) == 0) {
             // few images: 16 regions of each image in flight, one per warp, streaming with an in-order commit pointer
-            c->ownerDirty = true;
             static const int s_swFlags = getenv("PLF_SW_FLAGS") ? atoi(getenv("PLF_SW_FLAGS")) : 0;      // experiment switches, see lsd_sw.cuh
-            lsd_grow_sw_kernel<<<nImg, 32 * SW_NW, sizeof(SwShared), s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_owner,
-                                                                         c->d_regMW, c->d_swPos, c->d_segs, c->d_nSegs, c->d_err, imgFirst, s_swFlags);
+            lsd_grow_sw_kernel<<<nImg, 32 * SW_NW, sizeof(SwShared), s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_swOwner,
+                                                                         c->d_swReg, c->d_swPos, c->d_segs, c->d_nSegs, c->d_err, imgFirst, s_swFlags);
         } else
             lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                        c->d_nSegs, c->d_err, imgFirst, growNs);

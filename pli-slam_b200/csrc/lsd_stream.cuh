@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(32) lsd_stream_kernel(PlfGeom g, const float4*
 // (region table: rtBase + blockIdx.y * rtStride, entries {offset in the image's list arena, size, region angle in degrees as float bits, -})
 __global__ void __launch_bounds__(128) lsd_rect_kernel(PlfGeom g, const int* n2map, const int4* rtBase, size_t rtStride, int* regAll,
                                                       const int* nRegAll, float* segs, int* nSegsOut, int imgFirst) {
-    __shared__ double s_sum[4][3][33];
+    __shared__ __align__(16) double s_sum[4][3][34];
     const int img = imgFirst + blockIdx.y, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nReg = min(nRegAll[img], g.segCap);
     if (blockIdx.x == 0 && threadIdx.x == 0) nSegsOut[img] = nReg;

@@ -52,7 +52,7 @@
 
 struct SwShared {
     int ring[SW_NW][GROW_RING];
-    double sum[SW_NW][3][33];
+    double sum[SW_NW][3][34];
     uint32_t dep[SW_NW][SW_MAXDEP];
     int chStat[SW_WIN];             // 0 not handed out, 1 being scanned / grown, 2 done
     int chRec[SW_WIN];              // warp << 26 | offset of the chunk's first record in that warp's buffer
@@ -61,6 +61,7 @@ struct SwShared {
     unsigned robbed[SW_WIN];        // per position: the region lost a pixel
     unsigned dirty[SW_WIN];         // per position: the seed pixel was given back after the chunk was handed out
     unsigned slow[SW_WIN];          // per position: needs a look at commit (not started, given up, too many dependencies)
+    unsigned slowRec[SW_WIN];       // per position: a RECORD that cannot be checked in shared memory (too many dependencies)
     unsigned failedW[SW_WIN];       // per position: the region gave pixels back (whoever relied on it must be grown again)
     uint32_t depTag[SW_WIN][SW_CHDEP];   // tags the records of the chunk relied on
     int depN[SW_WIN];
@@ -118,9 +119,9 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
     const int img = imgFirst + blockIdx.x, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t npx = (size_t)g.Ws * g.Hs, npb = (size_t)g.Ps * g.Hs;
     const size_t npxA = (npx + 3) & ~(size_t)3;
-    const int warpBuf = (int)(((size_t)(SW_NW - 1) * npx / SW_NW) & ~(size_t)3) - 4;
+    const int warpBuf = PLF_SW_WARPBUF;
     const int warpCap = warpBuf - 4 * SW_SEGQ;                            // pixel lists and record headers; then the segment queue
-    int* const imgReg = regAll + (size_t)blockIdx.x * SW_NW * npx;       // [npx] commit buffer, then SW_NW buffers of warpBuf
+    int* const imgReg = regAll + (size_t)blockIdx.x * (npxA + (size_t)SW_NW * PLF_SW_WARPBUF);   // [npxA] commit buffer, then SW_NW buffers of warpBuf
     int* const Rc = imgReg;
     int* const Rw = imgReg + npxA + (size_t)w * warpBuf;
     float4* const Sq = reinterpret_cast<float4*>(Rw + warpCap);
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
             const int sd = S[p];
             P[(sd >> 16) * c.PB + (sd & 0xFFFF)] = p;
         }
-        for (int i = threadIdx.x; i < SW_WIN; i += 32 * SW_NW) { sh.chStat[i] = 0; sh.robbed[i] = 0u; sh.dirty[i] = 0u; sh.slow[i] = 0u; sh.failedW[i] = 0u; sh.depN[i] = 0; }
+        for (int i = threadIdx.x; i < SW_WIN; i += 32 * SW_NW) { sh.chStat[i] = 0; sh.robbed[i] = 0u; sh.dirty[i] = 0u; sh.slow[i] = 0u; sh.failedW[i] = 0u; sh.slowRec[i] = 0u; sh.depN[i] = 0; }
         if (threadIdx.x < SW_NW) sh.actTag[threadIdx.x] = 0u;
         if (threadIdx.x == 0) { sh.scanChunk = 0; sh.commitChunk = 0; sh.lock = 0; sh.nSeg = 0; }
         if (threadIdx.x < 16) sh.cnt[threadIdx.x] = 0;
@@ -222,14 +223,30 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                     __threadfence_block();
                     const int recPack = *(volatile int*)&sh.chRec[slot];
                     const int nRec = *(volatile int*)&sh.chN[slot];
+                    const long long tq0 = clock64();
+                    bool hardDep = false;
                     unsigned bad = *(volatile unsigned*)&sh.robbed[slot] | *(volatile unsigned*)&sh.dirty[slot] |
                                    *(volatile unsigned*)&sh.slow[slot] | ((flags & 64) ? 1u : 0u);
                     {
                         // did a region the chunk's records relied on give pixels back?
                         const int dn = *(volatile int*)&sh.depN[slot];
                         const bool fd = lane < dn && sw_failed(sh, *(volatile uint32_t*)&sh.depTag[slot][lane]);
-                        if (dn > 0 && __any_sync(0xffffffffu, fd)) { bad |= 1u; SW_CNT(13); }
+                        if (dn > 0 && __any_sync(0xffffffffu, fd)) { bad |= 1u; hardDep = true; SW_CNT(13); }
                     }
+                    if (bad != 0u && !(flags & 64) && *(volatile unsigned*)&sh.robbed[slot] == 0u && !hardDep) {
+                        // only seeds that were not started / given up / given back: if every one of them belongs to an
+                        // earlier region by now there is nothing to grow and the records stand as they are
+                        const unsigned quick = *(volatile unsigned*)&sh.dirty[slot] | *(volatile unsigned*)&sh.slow[slot];
+                        const int p = cc * 32 + lane;
+                        bool open = false;
+                        if ((quick >> lane) & 1u) {
+                            const int seed = p < ns ? S[p] : -1;
+                            open = seed >= 0 && sw_ld_owner(O + (seed >> 16) * c.PB + (seed & 0xFFFF)) >= (uint32_t)p + 1u;
+                        }
+                        if (!__any_sync(0xffffffffu, open) && !(*(volatile unsigned*)&sh.slowRec[slot])) { bad = 0u; SW_CNT(14); }
+                    }
+                    const long long tq1 = clock64();
+                    if ((flags & 4) && lane == 0 && bad == 0u && tq1 - tq0 > 400) atomicAdd((unsigned long long*)&sh.clk[3], (unsigned long long)(tq1 - tq0));
                     if (bad == 0u) {
                         // fast path: every record of the chunk is final, every other seed is still an earlier region's
                         const int segPack = *(volatile int*)&sh.chSeg[slot];
@@ -244,6 +261,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                         SW_CNT(5);
                     } else {
                         SW_CNT(6);
+                        const long long ts0 = clock64();
                         const int p = cc * 32 + lane;
                         const int seed = p < ns ? S[p] : -1;
                         const int pb = seed >= 0 ? (seed >> 16) * c.PB + (seed & 0xFFFF) : 0;
@@ -316,6 +334,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                             }
                             cur = l + 1;
                         }
+                        if ((flags & 4) && lane == 0) atomicAdd((unsigned long long*)&sh.clk[2], (unsigned long long)(clock64() - ts0));
                     }
                     if (lane == 0) {
                         sh.chStat[slot] = 0;
@@ -356,7 +375,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
         unsigned gm = __ballot_sync(0xffffffffu, seed >= 0 && o0 > myTag);
         const int recStart = head, segStart = segHead;
         int nRec = 0, chDep = 0;
-        unsigned slowMask = 0u;
+        unsigned slowMask = 0u, slowRecMask = 0u;
         while (gm) {
             const int l = __ffs(gm) - 1;
             gm &= gm - 1u;
@@ -404,7 +423,12 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                 nd = -1;
                 if (flags & 16) break;
             }
-            if (nd < 0) { slowMask |= 1u << l; continue; }
+            if (nd < 0) {
+                // given up: no record, no claim left; the robbed bit has served (a quick look at the seed is all commit needs)
+                if (lane == 0) atomicAnd(&sh.robbed[slot], ~(1u << l));
+                slowMask |= 1u << l;
+                continue;
+            }
             int rflags = 0;
             float sg[4] = {0.f, 0.f, 0.f, 0.f};
             if (n >= g.minRegSize) {
@@ -420,7 +444,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                 if (nd <= SW_MAXDEP && chDep + nd <= SW_CHDEP) {
                     if (lane < nd) sh.depTag[slot][chDep + lane] = c.deps[lane];
                     chDep += nd;
-                } else slowMask |= 1u << l;
+                } else { slowMask |= 1u << l; slowRecMask |= 1u << l; }
             }
             int* hdr = Rw + head;
             if (lane == 0) {
@@ -439,6 +463,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
             sh.chSeg[slot] = ((segHead - segStart) << 16) | segStart;
             sh.chN[slot] = nRec;
             sh.slow[slot] = slowMask;
+            sh.slowRec[slot] = slowRecMask;
             sh.depN[slot] = chDep;
             __threadfence_block();
             sh.chStat[slot] = 2;
@@ -448,8 +473,8 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
     }
     __syncthreads();
     if ((flags & 4) && threadIdx.x == 0 && blockIdx.x == 0)
-        printf("sw img %d: ns %d chunks %d | recorded %d (%d px, %d with deps) given up %d (%d px, %d retried) failedRec %d grownAtCommit %d (%d px) parked %d | chunks fast %d slow %d (failed dep %d) | idle spins %d | cycles total %lld commit %lld (regrow %lld) segs %d\n",
-               img, ns, nChunks, sh.cnt[0], sh.cnt[10], sh.cnt[12], sh.cnt[1], sh.cnt[9], sh.cnt[11], sh.cnt[2], sh.cnt[3], sh.cnt[8], sh.cnt[4], sh.cnt[5], sh.cnt[6], sh.cnt[13], sh.cnt[7],
-               clock64() - tStart, sh.clk[0], sh.clk[1], sh.nSeg);
+        printf("sw img %d: ns %d chunks %d | recorded %d (%d px, %d with deps) given up %d (%d px, %d retried) failedRec %d grownAtCommit %d (%d px) parked %d | chunks fast %d (%d after a look at the seeds) slow %d (failed dep %d) | idle spins %d | cycles total %lld commit %lld (regrow %lld, slow path incl. regrow %lld, seed looks %lld) segs %d\n",
+               img, ns, nChunks, sh.cnt[0], sh.cnt[10], sh.cnt[12], sh.cnt[1], sh.cnt[9], sh.cnt[11], sh.cnt[2], sh.cnt[3], sh.cnt[8], sh.cnt[4], sh.cnt[5], sh.cnt[14], sh.cnt[6], sh.cnt[13], sh.cnt[7],
+               clock64() - tStart, sh.clk[0], sh.clk[1], sh.clk[2], sh.clk[3], sh.nSeg);
     if (threadIdx.x == 0) nSegsOut[img] = min(sh.nSeg, g.segCap);
 }

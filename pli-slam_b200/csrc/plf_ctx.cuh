@@ -13,6 +13,8 @@
 #define PLF_MINB 16               // minBorder = EDGE_THRESHOLD-3, src/ORBextractor.cc:771
 #define PLF_NOTDEF (-1024.0f)
 #define PLF_MW_WARPS 16           // warps (= regions in flight) per image of that grower
+#define PLF_SW_MAX_IMG 296         // launches of at most this many images use the streaming multi-warp grower (one block per SM: two waves)
+#define PLF_SW_WARPBUF 65536       // ints of uncommitted records (headers + pixel lists + segment queue) per warp of that grower
 #define PLF_MW_MAX_IMG 128         // launches of at most this many images use the multi-warp (several regions in flight) grower
 #define PLF_FAST_TH 32            // rows of one FAST score tile (orb.cu FS_TH); same for its host-built tile table
 #define PLF_BLUR_TH 32            // rows of one blur tile (blur.cuh); the host builds the tile table of the pyramid blur with it
@@ -84,6 +86,8 @@ struct plf_ctx {
     int device = 0;
     int nImgMax = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;                  // plf_batch_run: the line path runs beside the point path (fork / join)
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     std::vector<float> scale, invScale, sigma2, invSigma2;
     std::vector<int> quota;
     // ORB device buffers
@@ -125,8 +129,10 @@ struct plf_ctx {
     int* d_reg = nullptr;            // [nImg][Hs*Ws] region pixel list, packed y<<16|x (reused per region)
     uint32_t* d_owner = nullptr;     // small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][Hs][Ps] owner tags of the current wave (PLF_FREE = none)
     int* d_regMW = nullptr;          // small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][8][Hs*Ws] region lists, one per wave slot
-    int* d_swPos = nullptr;          // streaming small-batch grower: [min(nImg, PLF_MW_MAX_IMG)][Hs][Ps] seed-list position of every defined pixel
-    bool ownerDirty = false;         // d_owner holds the tags of lsd_grow_sw_kernel (lsd_grow_mw_kernel expects PLF_FREE everywhere)
+    // streaming small-batch grower (lsd_grow_sw_kernel), for min(nImg, PLF_SW_MAX_IMG) images, allocated on first use:
+    uint32_t* d_swOwner = nullptr;   // [Hs][Ps] owner tags (seed position + 1)
+    int* d_swPos = nullptr;          // [Hs][Ps] seed-list position of every defined pixel
+    int* d_swReg = nullptr;          // [Hs*Ws rounded to 4] commit buffer + PLF_MW_WARPS x PLF_SW_WARPBUF record buffers
     int* d_stream = nullptr;         // streaming grower: [nImg][StreamLayout.total] owner map, list chunks, ticket table, region table (lazy)
     int4* d_laneRT = nullptr;        // lane-per-image grower: [nImg][segCap] region table {arena offset, size, angle bits, -} (lazy)
     unsigned long long* d_growNs = nullptr;  // [nImg] ns every image spent in lsd_grow_kernel (stage timing only, lazy)

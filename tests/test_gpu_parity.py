@@ -639,17 +639,17 @@ def test_repeated_calls_replay_the_graph(plf, product, oracle):
 
 
 def test_large_batch_sequential_grower_matches_oracle(plf, product, oracle):
-    """Launches of more than 128 images use the one-warp-per-image region grower (the kernel the benchmark runs); smaller
-    ones use the streaming multi-warp grower.  72 pairs (144 images, 8 distinct pairs repeated) against the oracle, exactly, and
+    """Launches of more than 296 images use the one-warp-per-image region grower (the kernel the benchmark runs); smaller
+    ones use the streaming multi-warp grower.  152 pairs (304 images, 8 distinct pairs repeated) against the oracle, exactly, and
     against the same pairs sent through a small batch."""
     W, H = 752, 480
     L8, R8 = plf.synth_batch(W, H, [101, 102, 103, 104, 105, 106, 107, 108])
-    idx = np.arange(72) % 8
-    f = plf.Frontend(product, max_batch=72, lsd_nfeatures=0)
+    idx = np.arange(152) % 8
+    f = plf.Frontend(product, max_batch=152, lsd_nfeatures=0)
     o = plf.Frontend(oracle, max_batch=8, lsd_nfeatures=0)
     rg, ro = f.frontend_batch(L8[idx], R8[idx]), o.frontend_batch(L8, R8)
     small = plf.Frontend(product, max_batch=8, lsd_nfeatures=0).frontend_batch(L8, R8)
-    for b in range(72):
+    for b in range(152):
         r = b % 8
         for side in ("left", "right"):
             nl = int(getattr(ro, "n_kl_" + side)[r])

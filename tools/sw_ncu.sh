@@ -1,0 +1,5 @@
+M=gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,launch__registers_per_thread,lts__t_sector_hit_rate.pct
+ncu --metrics $M --clock-control none -k regex:lsd_grow -s 1 -c 1 --csv --log-file gpurun_out/sw_ncu_sw64.csv python tools/prof_one.py 64 2 > /dev/null 2>&1
+PLF_LSD_GROWER=seq ncu --metrics $M --clock-control none -k regex:lsd_grow -s 1 -c 1 --csv --log-file gpurun_out/sw_ncu_seq64.csv python tools/prof_one.py 64 2 > /dev/null 2>&1
+ncu --metrics $M --clock-control none -k regex:lsd_grow -s 1 -c 1 --csv --log-file gpurun_out/sw_ncu_sw1.csv python tools/prof_one.py 1 2 > /dev/null 2>&1
+python tools/summarize_ncu_csv.py gpurun_out/sw_ncu_sw64.csv sw64; python tools/summarize_ncu_csv.py gpurun_out/sw_ncu_seq64.csv seq64; python tools/summarize_ncu_csv.py gpurun_out/sw_ncu_sw1.csv sw1

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PRODUCT_LIB = os.path.join(ROOT, "pli-slam_b200", "libplf_b200.so")
+PRODUCT_LIB = os.environ.get("PLF_PRODUCT_LIB") or os.path.join(ROOT, "pli-slam_b200", "libplf_b200.so")      # (the override is a developer switch for A/B builds)
 ORACLE_LIB = os.path.join(ROOT, "oracle", "libplf_oracle.so")
 
 PLF_OK = 0

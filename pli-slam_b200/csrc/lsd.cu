@@ -318,6 +318,7 @@ __device__ __forceinline__ void seq_sum3(double (*buf)[34], double a, double b, 
 }
 
 struct GrowState {
+    uint32_t pend;    // streaming mode, per lane: the value my last claim displaced, looked at one round later (PLF_FREE: nothing)
     int ndep;         // streaming mode: entries of c.deps in use (SW_MAXDEP + 1: too many, the region cannot be verified)
     int n;            // region size
     float sumdx, sumdy;
@@ -351,6 +352,11 @@ struct GrowCtx {
 #define SW_MAXDEP 8
 __device__ __forceinline__ void sw_rob(const GrowCtx& c, uint32_t victimTag) {
     atomicOr(c.robbed + (((victimTag - 1u) >> 5) & (SW_WIN - 1)), 1u << ((victimTag - 1u) & 31u));
+}
+// what a claim displaced: an earlier tag -> the claimant lost the pixel; a later tag -> that region lost it
+__device__ __forceinline__ void sw_settle(const GrowCtx& c, uint32_t old) {
+    if (old < c.tag) sw_rob(c, c.tag);
+    else if (old != PLF_FREE && old > c.tag) sw_rob(c, old);
 }
 
 // q is a BIT index, y * PB + x
@@ -470,10 +476,11 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
             if (!SPEC) {
                 atomicOr(c.used + (q >> 5), 1u << (q & 31));
             } else if (MODE == 2) {
-                // claim with my ticket: the earliest ticket keeps a contested pixel; whoever loses one is marked
-                const uint32_t old = atomicMin(c.owner + q, c.tag);
-                if (old < c.tag) sw_rob(c, c.tag);
-                else if (old != PLF_FREE && old > c.tag) sw_rob(c, old);
+                // claim with my ticket: the earliest ticket keeps a contested pixel; whoever loses one is marked — when the
+                // atomic's result has arrived, i.e. at this lane's next claim or at the end of the region (no round trip
+                // on the chain)
+                sw_settle(c, st.pend);
+                st.pend = atomicMin(c.owner + q, c.tag);
             } else {
                 // claim in the wave's owner map: the earlier seed (lower tag) wins a contested pixel, the loser is re-grown
                 const uint32_t old = atomicMin(c.owner + q, c.tag);
@@ -514,15 +521,14 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
     GrowState st;
     st.n = 1;
     st.ndep = 0;
+    st.pend = PLF_FREE;
     st.aborted = false;
     if (c.lane == 0) {
         const int pb = (pk0 >> 16) * c.PB + (pk0 & 0xFFFF);
         c.ring[0] = pk0; c.R[0] = pk0;
         if (!SPEC) atomicOr(c.used + (pb >> 5), 1u << (pb & 31));
         else if (MODE == 2) {
-            const uint32_t old = atomicMin(c.owner + pb, c.tag);
-            if (old < c.tag) sw_rob(c, c.tag);
-            else if (old != PLF_FREE && old > c.tag) sw_rob(c, old);
+            st.pend = atomicMin(c.owner + pb, c.tag);
         } else {
             const uint32_t old = atomicMin(c.owner + pb, c.tag);
             if (old < c.tag) atomicOr(c.invalid + (c.tag - 1), 1);
@@ -625,7 +631,11 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
         i += nb;
     }
     regAngleOut = (double)(st.dirty ? fast_atan2_deg(st.sumdy, st.sumdx) : st.regDeg) * kDegToRad;
-    if (MODE == 2 && ndepOut) *ndepOut = st.aborted ? -1 : st.ndep;
+    if (MODE == 2) {
+        sw_settle(c, st.pend);
+        __syncwarp();
+        if (ndepOut) *ndepOut = st.aborted ? -1 : st.ndep;
+    }
     return st.n;
 }
 
@@ -1407,7 +1417,7 @@ static int plf_ensure_sw_buffers(plf_ctx* c) {
     if (!c->d_swOwner) {
         const size_t nLat = std::min<size_t>((size_t)c->nImgMax, PLF_SW_MAX_IMG);
         const size_t npb = (size_t)c->g.Ps * c->g.Hs, npxA = ((size_t)c->g.Ws * c->g.Hs + 3) & ~(size_t)3;
-        const size_t perImg = npxA + (size_t)PLF_MW_WARPS * PLF_SW_WARPBUF;
+        const size_t perImg = npxA + (size_t)PLF_SW_WARPS * PLF_SW_WARPBUF;
         if (cudaMalloc((void**)&c->d_swOwner, nLat * npb * sizeof(uint32_t)) != cudaSuccess ||
             cudaMalloc((void**)&c->d_swPos, nLat * npb * sizeof(int)) != cudaSuccess ||
             cudaMalloc((void**)&c->d_swReg, nLat * perImg * sizeof(int)) != cudaSuccess) {

@@ -41,9 +41,9 @@
 //    the commit pointer grows it if it is still free when its turn comes.
 // refine >= 1 keeps the sequential kernel (its re-growing un-marks pixels).
 
-#define SW_NW PLF_MW_WARPS
+#define SW_NW PLF_SW_WARPS
 #define SW_HDR 16                   // ints in front of a record's pixel list: tag n flags ndep seg[4] deps[8]
-#define SW_SEGQ 2048                // segments a warp can leave uncommitted
+#define SW_SEGQ 128                 // segments a warp can leave uncommitted (shared memory)
 #define SW_PARK_DIST 2.5f           // px from a growing region's axis
 #define SW_CHDEP 8                  // relied-on tags a chunk can keep in shared memory (more: slow path)
 #define SW_AHEAD (SW_WIN / 2)       // chunks the scan pointer may run ahead of the commit pointer: a slot (robbed / dirty / failed
@@ -65,13 +65,14 @@ struct SwShared {
     unsigned failedW[SW_WIN];       // per position: the region gave pixels back (whoever relied on it must be grown again)
     uint32_t depTag[SW_WIN][SW_CHDEP];   // tags the records of the chunk relied on
     int depN[SW_WIN];
+    float4 segS[SW_NW][SW_SEGQ];    // segments of the uncommitted records, in record order
     float4 act[SW_NW];              // region being grown by warp w: seed x, y, cos, sin of its level-line angle
     float actDeg[SW_NW];
     int actN[SW_NW];
     uint32_t actTag[SW_NW];         // 0 = none
     int scanChunk, commitChunk, lock, nSeg;
     int cnt[16];                    // PLF_SW_FLAGS & 4: statistics
-    long long clk[4];
+    long long clk[8];
 };
 #define SW_CNT(i) do { if ((flags & 4) && lane == 0) atomicAdd(&sh.cnt[i], 1); } while (0)
 
@@ -120,11 +121,11 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
     const size_t npx = (size_t)g.Ws * g.Hs, npb = (size_t)g.Ps * g.Hs;
     const size_t npxA = (npx + 3) & ~(size_t)3;
     const int warpBuf = PLF_SW_WARPBUF;
-    const int warpCap = warpBuf - 4 * SW_SEGQ;                            // pixel lists and record headers; then the segment queue
+    const int warpCap = warpBuf;                                          // record headers and pixel lists
     int* const imgReg = regAll + (size_t)blockIdx.x * (npxA + (size_t)SW_NW * PLF_SW_WARPBUF);   // [npxA] commit buffer, then SW_NW buffers of warpBuf
     int* const Rc = imgReg;
     int* const Rw = imgReg + npxA + (size_t)w * warpBuf;
-    float4* const Sq = reinterpret_cast<float4*>(Rw + warpCap);
+    float4* const Sq = sh.segS[w];
     uint32_t* const O = ownerAll + (size_t)blockIdx.x * npb;
     int* const P = posAll + (size_t)blockIdx.x * npb;
     const int* S = seeds + (size_t)img * g.seedCap;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
         if (threadIdx.x < SW_NW) sh.actTag[threadIdx.x] = 0u;
         if (threadIdx.x == 0) { sh.scanChunk = 0; sh.commitChunk = 0; sh.lock = 0; sh.nSeg = 0; }
         if (threadIdx.x < 16) sh.cnt[threadIdx.x] = 0;
-        if (threadIdx.x < 4) sh.clk[threadIdx.x] = 0;
+        if (threadIdx.x < 8) sh.clk[threadIdx.x] = 0;
     }
     __threadfence_block();
     __syncthreads();
@@ -216,11 +217,62 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                 __threadfence_block();
                 int nSeg = *(volatile int*)&sh.nSeg;
                 while (true) {
+                    const long long ta0 = clock64();
                     cc = *vCommit;
                     if (cc >= nChunks) break;
                     const int slot = cc & (SW_WIN - 1);
                     if (vStat[slot] < 2) break;
                     __threadfence_block();
+                    if (!(flags & 64)) {
+                        // fast path for a RUN of chunks, one per lane: done, nothing robbed / dirty / given up, no relied-on
+                        // region failed -> every record of the run is final (a fast commit changes nothing, and no earlier
+                        // region is alive that could still touch the later chunks of the run); the segments are appended in
+                        // order and the run is published with one fence
+                        const int cj = cc + lane, sj = cj & (SW_WIN - 1);
+                        bool okj = cj < nChunks && lane < SW_AHEAD && vStat[sj] >= 2;
+                        __threadfence_block();
+                        if (okj) okj = (*(volatile unsigned*)&sh.robbed[sj] | *(volatile unsigned*)&sh.dirty[sj] | *(volatile unsigned*)&sh.slow[sj]) == 0u;
+                        if (okj) {
+                            const int dn = *(volatile int*)&sh.depN[sj];
+                            for (int k = 0; k < dn; ++k)
+                                if (sw_failed(sh, *(volatile uint32_t*)&sh.depTag[sj][k])) okj = false;
+                        }
+                        const unsigned fm = __ballot_sync(0xffffffffu, okj);
+                        const int nFast = (fm == 0xffffffffu) ? 32 : __ffs(~fm) - 1;
+                        if (nFast > 0) {
+                            const int segPackJ = lane < nFast ? *(volatile int*)&sh.chSeg[sj] : 0;
+                            const int recWarpJ = lane < nFast ? (*(volatile int*)&sh.chRec[sj] >> 26) : 0;
+                            const int kj = segPackJ >> 16;
+                            int incl = kj;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                                if (lane >= o) incl += t;
+                            }
+                            const int excl = incl - kj, total = __shfl_sync(0xffffffffu, incl, 31);
+                            unsigned sm = __ballot_sync(0xffffffffu, kj > 0);
+                            while (sm) {
+                                const int j = __ffs(sm) - 1;
+                                sm &= sm - 1u;
+                                const int k = __shfl_sync(0xffffffffu, kj, j), off = __shfl_sync(0xffffffffu, excl, j);
+                                const float4* src = sh.segS[__shfl_sync(0xffffffffu, recWarpJ, j)] + (__shfl_sync(0xffffffffu, segPackJ, j) & 0xFFFF);
+                                const int dstI = nSeg + off + lane;
+                                if (lane < k && dstI < g.segCap) out[dstI] = src[lane];
+                            }
+                            if (nSeg + total > g.segCap && lane == 0) atomicOr(err, 2);
+                            nSeg = min(g.segCap, nSeg + total);
+                            if ((flags & 4) && lane == 0) atomicAdd(&sh.cnt[5], nFast);
+                            if (lane < nFast) sh.chStat[sj] = 0;
+                            __syncwarp();
+                            if (lane == 0) {
+                                __threadfence_block();
+                                *vCommit = cc + nFast;
+                            }
+                            __syncwarp();
+                            continue;
+                        }
+                    }
+                    const long long ta1 = clock64();
                     const int recPack = *(volatile int*)&sh.chRec[slot];
                     const int nRec = *(volatile int*)&sh.chN[slot];
                     const long long tq0 = clock64();
@@ -252,7 +304,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                         const int segPack = *(volatile int*)&sh.chSeg[slot];
                         const int k = segPack >> 16;
                         if (k > 0) {
-                            const float4* src = reinterpret_cast<const float4*>(imgReg + npxA + (size_t)(recPack >> 26) * warpBuf + warpCap) + (segPack & 0xFFFF);
+                            const float4* src = sh.segS[recPack >> 26] + (segPack & 0xFFFF);
                             const int room = g.segCap - nSeg;
                             if (lane < k && lane < room) out[nSeg + lane] = src[lane];
                             if (k > room && lane == 0) atomicOr(err, 2);
@@ -336,12 +388,19 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                         }
                         if ((flags & 4) && lane == 0) atomicAdd((unsigned long long*)&sh.clk[2], (unsigned long long)(clock64() - ts0));
                     }
+                    const long long tp0 = clock64();
                     if (lane == 0) {
                         sh.chStat[slot] = 0;
                         __threadfence_block();
                         *vCommit = cc + 1;
                     }
                     __syncwarp();
+                    if ((flags & 4) && lane == 0) {
+                        atomicAdd((unsigned long long*)&sh.clk[4], (unsigned long long)(ta1 - ta0));
+                        atomicAdd((unsigned long long*)&sh.clk[5], (unsigned long long)(tq0 - ta1));
+                        atomicAdd((unsigned long long*)&sh.clk[6], (unsigned long long)(clock64() - tp0));
+                        atomicAdd((unsigned long long*)&sh.clk[7], (unsigned long long)(tp0 - tq1));
+                    }
                 }
                 if ((flags & 4) && lane == 0) atomicAdd((unsigned long long*)&sh.clk[0], (unsigned long long)(clock64() - tc0));
                 if (lane == 0) {
@@ -476,5 +535,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
         printf("sw img %d: ns %d chunks %d | recorded %d (%d px, %d with deps) given up %d (%d px, %d retried) failedRec %d grownAtCommit %d (%d px) parked %d | chunks fast %d (%d after a look at the seeds) slow %d (failed dep %d) | idle spins %d | cycles total %lld commit %lld (regrow %lld, slow path incl. regrow %lld, seed looks %lld) segs %d\n",
                img, ns, nChunks, sh.cnt[0], sh.cnt[10], sh.cnt[12], sh.cnt[1], sh.cnt[9], sh.cnt[11], sh.cnt[2], sh.cnt[3], sh.cnt[8], sh.cnt[4], sh.cnt[5], sh.cnt[14], sh.cnt[6], sh.cnt[13], sh.cnt[7],
                clock64() - tStart, sh.clk[0], sh.clk[1], sh.clk[2], sh.clk[3], sh.nSeg);
+    if ((flags & 4) && threadIdx.x == 0 && blockIdx.x == 0)
+        printf("sw commit split: acquire+fence %lld, table reads %lld, body (fast or slow) %lld, publish %lld\n", sh.clk[4], sh.clk[5], sh.clk[7], sh.clk[6]);
     if (threadIdx.x == 0) nSegsOut[img] = min(sh.nSeg, g.segCap);
 }

@@ -14,6 +14,9 @@
 #define PLF_NOTDEF (-1024.0f)
 #define PLF_MW_WARPS 16           // warps (= regions in flight) per image of that grower
 #define PLF_SW_MAX_IMG 296         // launches of at most this many images use the streaming multi-warp grower (one block per SM: two waves)
+#ifndef PLF_SW_WARPS
+#define PLF_SW_WARPS 16            // warps (= regions in flight) per image of the streaming grower
+#endif
 #define PLF_SW_WARPBUF 65536       // ints of uncommitted records (headers + pixel lists + segment queue) per warp of that grower
 #define PLF_MW_MAX_IMG 128         // launches of at most this many images use the multi-warp (several regions in flight) grower
 #define PLF_FAST_TH 32            // rows of one FAST score tile (orb.cu FS_TH); same for its host-built tile table
@@ -132,7 +135,7 @@ struct plf_ctx {
     // streaming small-batch grower (lsd_grow_sw_kernel), for min(nImg, PLF_SW_MAX_IMG) images, allocated on first use:
     uint32_t* d_swOwner = nullptr;   // [Hs][Ps] owner tags (seed position + 1)
     int* d_swPos = nullptr;          // [Hs][Ps] seed-list position of every defined pixel
-    int* d_swReg = nullptr;          // [Hs*Ws rounded to 4] commit buffer + PLF_MW_WARPS x PLF_SW_WARPBUF record buffers
+    int* d_swReg = nullptr;          // [Hs*Ws rounded to 4] commit buffer + PLF_SW_WARPS x PLF_SW_WARPBUF record buffers
     int* d_stream = nullptr;         // streaming grower: [nImg][StreamLayout.total] owner map, list chunks, ticket table, region table (lazy)
     int4* d_laneRT = nullptr;        // lane-per-image grower: [nImg][segCap] region table {arena offset, size, angle bits, -} (lazy)
     unsigned long long* d_growNs = nullptr;  // [nImg] ns every image spent in lsd_grow_kernel (stage timing only, lazy)

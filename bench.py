@@ -46,6 +46,10 @@ CONFIGS = {
                bytes_per_pair=82_240_000, dominant=("lsd_grow_kernel", "lsd_grow", 9 * 1536 * 864), seed0=2000),
 }
 CONFIGS["c5"] = dict(CONFIGS["c2"], name="euroc_752x480_512_streams_sharded")
+# c2 with TRUE 64-pair calls (one camera stream per call, 16 calls in flight): launches of 128 images go through the streaming
+# multi-warp region grower (2.8x the instructions of the one-warp-per-image kernel, a fifth of its latency)
+CONFIGS["c2_batch64"] = dict(CONFIGS["c2"], name="euroc_752x480_stereo_pointline_true_batch64",
+                             dominant=("lsd_grow_sw_kernel", "lsd_grow", 9 * 902 * 576))
 BYTES_PER_PAIR = CONFIGS["c2"]["bytes_per_pair"]
 
 
@@ -309,6 +313,8 @@ def main():
     cfg = CONFIGS[args.config]
     global W, H, WORKLOAD
     W, H, WORKLOAD = cfg["W"], cfg["H"], dict(cfg["params"])
+    if args.config == "c2_batch64" and args.streams == 8 and args.contexts == 8:
+        args.streams, args.contexts = 1, 16
     if args.config == "c4" and args.streams == 8 and args.contexts == 8:
         args.streams, args.contexts = 2, 4                # 1280x720: 2.6x the pixels and device memory per pair
     B, C = args.batch * args.streams, args.contexts       # pairs per call, calls in flight
@@ -317,7 +323,7 @@ def main():
     my_streams = shard_streams(max(n_streams_total, C * args.streams * world), world, rank)
     distinct = min(args.distinct, B)
     # distinct pairs of this rank: frames f of its first streams, seed convention of SURVEY 8d (c2/c5) or the config's own
-    if args.config in ("c2", "c5"):
+    if args.config in ("c2", "c5", "c2_batch64"):
         seeds = [stream_seed(my_streams[(i // args.batch) % len(my_streams)], i % args.batch) for i in range(distinct)]
     else:
         seeds = [cfg["seed0"] + rank * distinct + i for i in range(distinct)]

@@ -809,7 +809,7 @@ PLF_API int plf_last_launch_count(const plf_ctx* c) { return c ? c->launches : 0
 PLF_API int plf_set_stage_timing(plf_ctx* c, int on) { if (!c) return PLF_ERR_INVALID; c->stageTiming = on != 0; return PLF_OK; }
 /* Per-image run time (ns) of the one-warp-per-image region grower during the last pass that ran with stage timing on: the
  * launch lasts as long as its slowest image, so max / mean says how much of the stage is tail.  Zeros for images that went
- * through another grower (launches of <= 128 images).  Test / benchmark tap, not part of the reference interface. */
+ * through another grower (launches of <= 296 images).  Test / benchmark tap, not part of the reference interface. */
 PLF_API int plf_tap_grow_ns(plf_ctx* c, unsigned long long* out, int n_images) {
     if (!c || !out || n_images < 0 || n_images > c->nImgMax) return fail(PLF_ERR_INVALID, "bad image count");
     if (!c->d_growNs) { for (int i = 0; i < n_images; ++i) out[i] = 0; return PLF_OK; }

@@ -318,6 +318,7 @@ __device__ __forceinline__ void seq_sum3(double (*buf)[34], double a, double b, 
 }
 
 struct GrowState {
+    int nrel;         // streaming mode: entries of the relied-on pixel list (SW_MAXREL + 1: too many)
     uint32_t pend;    // streaming mode, per lane: the value my last claim displaced, looked at one round later (PLF_FREE: nothing)
     int ndep;         // streaming mode: entries of c.deps in use (SW_MAXDEP + 1: too many, the region cannot be verified)
     int n;            // region size
@@ -343,6 +344,8 @@ struct GrowCtx {
     uint32_t* deps;     // shared memory, SW_MAXDEP tags of earlier, uncommitted regions whose claims this region skipped
     uint32_t floorTag;  // tags below this were committed when the region started: their claims are final
     int maxN;           // room for the pixel list
+    int* relTop;        // end of the free part of the record buffer: the pixels skipped as an uncommitted earlier region's
+                        // are listed downwards from here (with repetitions), SW_MAXREL at most
     int* actN;          // shared memory: current size of the region, for the parking heuristic of the other warps
     bool ldcg;          // experiment switch: owner reads from L2
     bool final;         // grown by the committing warp: every earlier region is final, nobody can take a pixel from it
@@ -350,6 +353,7 @@ struct GrowCtx {
 #define PLF_FREE 0xFFFFFFFFu
 #define SW_WIN 512                  // chunks (of 32 seed positions) between the commit pointer and the scan pointer
 #define SW_MAXDEP 8
+#define SW_MAXREL 2048
 __device__ __forceinline__ void sw_rob(const GrowCtx& c, uint32_t victimTag) {
     atomicOr(c.robbed + (((victimTag - 1u) >> 5) & (SW_WIN - 1)), 1u << ((victimTag - 1u) & 31u));
 }
@@ -516,11 +520,12 @@ __device__ __forceinline__ void grow_chain(GrowState& st, bool valid, int q, int
 // pixel list is left in c.R[0..n)
 template <int MODE>
 __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, const AlignTol& tol, double& regAngleOut,
-                                           int* ndepOut = nullptr) {
+                                           int* ndepOut = nullptr, int* nrelOut = nullptr) {
     constexpr bool SPEC = MODE != 0;
     GrowState st;
     st.n = 1;
     st.ndep = 0;
+    st.nrel = 0;
     st.pend = PLF_FREE;
     st.aborted = false;
     if (c.lane == 0) {
@@ -555,7 +560,7 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
         float4 r[GROW_SETS];
         bool valid[GROW_SETS];
         uint32_t relTag[GROW_SETS];      // streaming mode: the earlier, uncommitted ticket whose claim made me skip this pixel
-        if (MODE == 2 && st.n + 8 * 4 * GROW_SETS > c.maxN) { st.aborted = true; break; }     // no room: left to the committing warp
+        if (MODE == 2 && st.n + 2 * st.nrel + 2 * 8 * 4 * GROW_SETS > c.maxN) { st.aborted = true; break; }     // no room: left to the committing warp
         if (MODE == 2 && c.lane == 0) *c.actN = st.n;
 #pragma unroll
         for (int s = 0; s < GROW_SETS; ++s) {
@@ -601,6 +606,14 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
 #pragma unroll
             for (int s = 0; s < GROW_SETS; ++s) {
                 unsigned rm = __ballot_sync(0xffffffffu, relTag[s] != 0u);
+                if (rm && st.nrel <= SW_MAXREL) {
+                    // the pixels themselves, for the commit check of a region whose relied-on region gave pixels back
+                    if (st.nrel + __popc(rm) > SW_MAXREL) st.nrel = SW_MAXREL + 1;
+                    else {
+                        if (relTag[s] != 0u) c.relTop[-1 - st.nrel - __popc(rm & ((1u << c.lane) - 1u))] = q[s];
+                        st.nrel += __popc(rm);
+                    }
+                }
                 while (rm) {
                     const uint32_t t = __shfl_sync(0xffffffffu, relTag[s], __ffs(rm) - 1);
                     rm &= ~__ballot_sync(0xffffffffu, relTag[s] == t);
@@ -635,6 +648,7 @@ __device__ __forceinline__ int grow_region(const GrowCtx& c, int pk0, int p, con
         sw_settle(c, st.pend);
         __syncwarp();
         if (ndepOut) *ndepOut = st.aborted ? -1 : st.ndep;
+        if (nrelOut) *nrelOut = st.nrel;
     }
     return st.n;
 }

@@ -182,8 +182,10 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
     int head = 0, segHead = 0, lastMine = -1;
 
     // grows the region of tag `tag` from seed pk0 into `dst` (list at dst + SW_HDR); returns n, ndep (-1: given up / robbed)
+    int nrelLast = 0;
     auto grow = [&](int* dst, int room, uint32_t tag, int pk0, bool fin, int& ndep, double& regAngle) -> int {
         c.R = dst + SW_HDR;
+        c.relTop = dst + room;
         c.tag = tag;
         c.final = fin;
         c.maxN = fin ? 0x7fffffff : room - SW_HDR;
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
             vActTag[w] = tag;
         }
         __syncwarp();
-        const int n = grow_region<2>(c, pk0, 0, precTol, regAngle, &ndep);
+        const int n = grow_region<2>(c, pk0, 0, precTol, regAngle, &ndep, &nrelLast);
         if (lane == 0) vActTag[w] = 0u;
         __syncwarp();
         return n;
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                             if (recIdx < nRec && (uint32_t)rec[0] < tagStar) {
                                 const uint32_t dead = (uint32_t)rec[0];
                                 sw_withdraw(sh, O, P, rec + SW_HDR, rec[1], dead, c.PB, lane);
-                                rec += (SW_HDR + rec[1] + 3) & ~3;
+                                rec += (SW_HDR + rec[1] + (rec[2] >> 8) + 3) & ~3;
                                 ++recIdx;
                                 cur = (int)((dead - 1u) & 31u) + 1;
                                 continue;
@@ -340,13 +342,23 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                             const int pkStar = __shfl_sync(0xffffffffu, seed, l);
                             bool done = false;
                             if (recIdx < nRec && (uint32_t)rec[0] == tagStar) {
-                                const int n = rec[1], rflags = rec[2], nd = rec[3];
-                                bool ok = oStar == tagStar && nd <= SW_MAXDEP &&
-                                          !((*(volatile unsigned*)&sh.robbed[slot] >> l) & 1u);
+                                const int n = rec[1], rflags = rec[2], nd = rec[3], nrel = rec[2] >> 8;
+                                bool ok = oStar == tagStar && !((*(volatile unsigned*)&sh.robbed[slot] >> l) & 1u);
                                 if (ok && nd > 0) {
-                                    bool failedDep = false;
-                                    if (lane < nd) failedDep = sw_failed(sh, (uint32_t)rec[8 + lane]);
-                                    ok = !__any_sync(0xffffffffu, failedDep);
+                                    bool failedDep = nd > SW_MAXDEP;
+                                    if (lane < nd && lane < SW_MAXDEP) failedDep = sw_failed(sh, (uint32_t)rec[8 + lane]);
+                                    if (__any_sync(0xffffffffu, failedDep)) {
+                                        // a region it relied on gave pixels back (or there were too many to remember): what
+                                        // counts is whether every pixel it skipped as that region's is an earlier region's
+                                        // NOW — all of them are final
+                                        ok = (rflags & 2) != 0;
+                                        for (int i0 = 0; ok && i0 < nrel; i0 += 32) {
+                                            bool open = false;
+                                            if (i0 + lane < nrel) open = sw_ld_owner(O + rec[SW_HDR + n + i0 + lane]) >= tagStar;
+                                            ok = !__any_sync(0xffffffffu, open);
+                                        }
+                                        if (ok) SW_CNT(15);
+                                    }
                                 }
                                 if (ok) {
                                     if (rflags & 1) {
@@ -360,7 +372,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                                     SW_CNT(2);
                                     sw_withdraw(sh, O, P, rec + SW_HDR, n, tagStar, c.PB, lane);
                                 }
-                                rec += (SW_HDR + n + 3) & ~3;
+                                rec += (SW_HDR + n + nrel + 3) & ~3;
                                 ++recIdx;
                             }
                             if (!done) {
@@ -498,6 +510,10 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                 if (lane == 0) Sq[segHead] = make_float4(sg[0], sg[1], sg[2], sg[3]);
                 ++segHead;
             }
+            // the relied-on pixels move from the top of the free space to the end of the pixel list (n + 2 nrel fits: no overlap)
+            const int nrel = (nd > 0 && nrelLast <= SW_MAXREL) ? nrelLast : 0;
+            for (int i = lane; i < nrel; i += 32) Rw[head + SW_HDR + n + i] = Rw[warpCap - 1 - i];
+            const bool relKnown = nd == 0 || nrelLast <= SW_MAXREL;
             if (nd > 0) {
                 SW_CNT(12);
                 if (nd <= SW_MAXDEP && chDep + nd <= SW_CHDEP) {
@@ -507,11 +523,11 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
             }
             int* hdr = Rw + head;
             if (lane == 0) {
-                hdr[0] = (int)tag; hdr[1] = n; hdr[2] = rflags; hdr[3] = nd;
+                hdr[0] = (int)tag; hdr[1] = n; hdr[2] = rflags | (relKnown ? 2 : 0) | (nrel << 8); hdr[3] = nd;
                 hdr[4] = __float_as_int(sg[0]); hdr[5] = __float_as_int(sg[1]); hdr[6] = __float_as_int(sg[2]); hdr[7] = __float_as_int(sg[3]);
             }
             if (lane < SW_MAXDEP) hdr[8 + lane] = (lane < nd) ? (int)c.deps[lane] : 0;
-            head += (SW_HDR + n + 3) & ~3;
+            head += (SW_HDR + n + nrel + 3) & ~3;
             ++nRec;
             SW_CNT(0);
             if ((flags & 4) && lane == 0) atomicAdd(&sh.cnt[10], n);
@@ -532,8 +548,8 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
     }
     __syncthreads();
     if ((flags & 4) && threadIdx.x == 0 && blockIdx.x == 0)
-        printf("sw img %d: ns %d chunks %d | recorded %d (%d px, %d with deps) given up %d (%d px, %d retried) failedRec %d grownAtCommit %d (%d px) parked %d | chunks fast %d (%d after a look at the seeds) slow %d (failed dep %d) | idle spins %d | cycles total %lld commit %lld (regrow %lld, slow path incl. regrow %lld, seed looks %lld) segs %d\n",
-               img, ns, nChunks, sh.cnt[0], sh.cnt[10], sh.cnt[12], sh.cnt[1], sh.cnt[9], sh.cnt[11], sh.cnt[2], sh.cnt[3], sh.cnt[8], sh.cnt[4], sh.cnt[5], sh.cnt[14], sh.cnt[6], sh.cnt[13], sh.cnt[7],
+        printf("sw img %d: ns %d chunks %d | recorded %d (%d px, %d with deps) given up %d (%d px, %d retried) failedRec %d (%d more saved by the pixel check) grownAtCommit %d (%d px) parked %d | chunks fast %d (%d after a look at the seeds) slow %d (failed dep %d) | idle spins %d | cycles total %lld commit %lld (regrow %lld, slow path incl. regrow %lld, seed looks %lld) segs %d\n",
+               img, ns, nChunks, sh.cnt[0], sh.cnt[10], sh.cnt[12], sh.cnt[1], sh.cnt[9], sh.cnt[11], sh.cnt[2], sh.cnt[15], sh.cnt[3], sh.cnt[8], sh.cnt[4], sh.cnt[5], sh.cnt[14], sh.cnt[6], sh.cnt[13], sh.cnt[7],
                clock64() - tStart, sh.clk[0], sh.clk[1], sh.clk[2], sh.clk[3], sh.nSeg);
     if ((flags & 4) && threadIdx.x == 0 && blockIdx.x == 0)
         printf("sw commit split: acquire+fence %lld, table reads %lld, body (fast or slow) %lld, publish %lld\n", sh.clk[4], sh.clk[5], sh.clk[7], sh.clk[6]);

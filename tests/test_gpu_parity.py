@@ -666,7 +666,7 @@ def test_large_batch_sequential_grower_matches_oracle(plf, product, oracle):
 @pytest.mark.gpu
 @pytest.mark.parametrize("W,H,batch", [(752, 480, 1), (752, 480, 5), (641, 479, 2), (1241, 376, 3)])
 def test_streaming_small_batch_grower_matches_oracle(plf, product, oracle, W, H, batch):
-    """Launches of at most 128 images go through lsd_grow_sw_kernel (one region per warp, 16 regions of an image in flight,
+    """Launches of at most 296 images go through lsd_grow_sw_kernel (one region per warp, 16 regions of an image in flight,
     in-order commit pointer): every segment-derived array equal to the oracle with ALL lines kept, over several calls on one
     context (owner map, position map and record buffers are reused from call to call)."""
     f = plf.Frontend(product, width=W, height=H, max_batch=batch, lsd_nfeatures=0)

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
     volatile int* vStat = sh.chStat;
     volatile int* vCommit = &sh.commitChunk;
     volatile uint32_t* vActTag = sh.actTag;
-    int head = 0, segHead = 0, lastMine = -1;
+    int head = 0, segHead = 0, lastMine = -1, idle = 0;
 
     // grows the region of tag `tag` from seed pk0 into `dst` (list at dst + SW_HDR); returns n, ndep (-1: given up / robbed)
     int nrelLast = 0;
@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                     atomicExch(&sh.lock, 0);
                 }
                 __syncwarp();
+                idle = 0;
                 continue;
             }
         }
@@ -433,7 +434,15 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
             if (s < nChunks && s < *vCommit + SW_AHEAD && atomicCAS(&sh.scanChunk, s, s + 1) == s) ch = s;
         }
         ch = __shfl_sync(0xffffffffu, ch, 0);
-        if (ch < 0) { SW_CNT(7); __nanosleep(100); continue; }
+        if (ch < 0) {
+            // nothing to take (window full, buffer full, or the list is handed out): sleep, longer every time — a spinning
+            // warp costs the growing ones of its SM issue slots (a quarter of the kernel's instructions before the back-off)
+            SW_CNT(7);
+            __nanosleep(idle < 3 ? 250 : (idle < 8 ? 1000 : 3000));
+            ++idle;
+            continue;
+        }
+        idle = 0;
         const int slot = ch & (SW_WIN - 1);
         if (lane == 0) { atomicExch(&sh.robbed[slot], 0u); atomicExch(&sh.dirty[slot], 0u); atomicExch(&sh.failedW[slot], 0u); sh.depN[slot] = 0; sh.chStat[slot] = 1; }
         __syncwarp();

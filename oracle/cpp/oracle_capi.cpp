@@ -995,6 +995,7 @@ PLF_API int plf_cpu_batch_io_bytes(const plf_ctx* c, int64_t* a, int64_t* b) {
 }
 PLF_API int plf_cpu_last_launch_count(const plf_ctx*) { return 0; }
 PLF_API int plf_cpu_set_stage_timing(plf_ctx*, int) { return PLF_OK; }
+PLF_API int plf_cpu_set_grower_policy(plf_ctx*, int) { return PLF_OK; }      // one scalar loop here: nothing to choose
 PLF_API int plf_cpu_get_stage_ms(plf_ctx*, const char* const** names, const float** ms, int* n) {
     if (names) *names = nullptr;
     if (ms) *ms = nullptr;

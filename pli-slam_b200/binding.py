@@ -73,7 +73,7 @@ ABI_SYMBOLS = [
     "default_params", "create", "destroy", "last_error", "keypoint_capacity", "keyline_capacity", "get_scale_tables",
     "orb_extract", "get_pyramid_level", "line_extract", "stereo_match_points", "stereo_match_lines", "match_nnr",
     "match", "frontend_batch", "batch_upload", "batch_run", "batch_download", "sync", "batch_io_bytes",
-    "last_launch_count", "set_stage_timing", "get_stage_ms", "stream", "tap_blurred_level", "tap_pyramid_level",
+    "last_launch_count", "set_grower_policy", "set_stage_timing", "get_stage_ms", "stream", "tap_blurred_level", "tap_pyramid_level",
     "tap_fast_candidates", "tap_lsd_scaled", "tap_lsd_angles", "tap_lsd_segments", "tap_lbd_float", "tap_grow_ns",
     "rectify_set_maps", "rectify", "batch_upload_raw", "feature_grid", "get_features_in_area", "backproject", "bow_set_vocabulary", "bow_transform", "bow_build_vectors", "search_by_projection", "search_by_projection_frame",
     "search_by_projection_reloc", "search_by_projection_loop", "search_by_bow", "match_lines_tracked",
@@ -529,6 +529,10 @@ class Frontend:
 
     def launch_count(self):
         return self.lib.fn("last_launch_count")(self.ctx)
+
+    def set_grower_policy(self, policy):
+        """0: automatic (streaming multi-warp grower for launches of <= 296 images), 1: throughput (one warp per image always)."""
+        self.lib.check(self.lib.fn("set_grower_policy")(self.ctx, int(policy)))
 
     def set_stage_timing(self, on):
         self.lib.check(self.lib.fn("set_stage_timing")(self.ctx, int(on)))

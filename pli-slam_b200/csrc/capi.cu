@@ -806,6 +806,16 @@ PLF_API int plf_batch_io_bytes(const plf_ctx* c, int64_t* h2d, int64_t* d2h) {
 }
 
 PLF_API int plf_last_launch_count(const plf_ctx* c) { return c ? c->launches : 0; }
+PLF_API int plf_set_grower_policy(plf_ctx* c, int policy) {
+    if (!c || (policy != PLF_GROWER_AUTO && policy != PLF_GROWER_THROUGHPUT)) return fail(PLF_ERR_INVALID, "bad grower policy");
+    if (c->growerPolicy != policy) {
+        c->growerPolicy = policy;
+        if (c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }      // the captured pass holds the other kernel
+        c->graphBatch = 0;
+        c->warmBatch = 0;                       // the next pass runs eagerly (lazy allocations must not happen under capture)
+    }
+    return PLF_OK;
+}
 PLF_API int plf_set_stage_timing(plf_ctx* c, int on) { if (!c) return PLF_ERR_INVALID; c->stageTiming = on != 0; return PLF_OK; }
 /* Per-image run time (ns) of the one-warp-per-image region grower during the last pass that ran with stage timing on: the
  * launch lasts as long as its slowest image, so max / mean says how much of the stage is tail.  Zeros for images that went

@@ -1524,7 +1524,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
             // the wave-synchronous predecessor of the streaming grower (kept for comparison)
             lsd_grow_mw_kernel<<<nImg, 32 * MW, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_owner, c->d_regMW,
                                                         c->d_segs, c->d_nSegs, c->d_err, imgFirst);
-        } else if (nImg <= PLF_SW_MAX_IMG && plf_ensure_sw_buffers(c) == 0) {
+        } else if (nImg <= PLF_SW_MAX_IMG && c->growerPolicy != PLF_GROWER_THROUGHPUT && plf_ensure_sw_buffers(c) == 0) {
             // few images: 16 regions of each image in flight, one per warp, streaming with an in-order commit pointer
             static const int s_swFlags = getenv("PLF_SW_FLAGS") ? atoi(getenv("PLF_SW_FLAGS")) : 0;      // experiment switches, see lsd_sw.cuh
             lsd_grow_sw_kernel<<<nImg, 32 * SW_NW, sizeof(SwShared), s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_swOwner,

@@ -191,6 +191,7 @@ struct plf_ctx {
     cudaGraphExec_t graphExec = nullptr;  // plf_batch_run of `graphBatch` pairs as one graph (captured on the second call with that size)
     int graphBatch = 0, graphLaunches = 0, warmBatch = 0;
     bool stageTiming = false;
+    int growerPolicy = 0;            // PLF_GROWER_AUTO / PLF_GROWER_THROUGHPUT (plf_set_grower_policy)
     std::vector<cudaEvent_t> ev;          // pool of timing events (marks)
     std::vector<const char*> markNames;   // name of the stage that STARTS at mark i
     std::vector<float> stageMs;

@@ -682,3 +682,24 @@ def test_streaming_small_batch_grower_matches_oracle(plf, product, oracle, W, H,
                 assert np.array_equal(getattr(rg, "ldesc_" + side)[b, :nl], getattr(ro, "ldesc_" + side)[b, :nl]), (call, b, side)
             nl = int(ro.n_kl_left[b])
             assert np.array_equal(rg.line_match12[b, :nl], ro.line_match12[b, :nl]), (call, b)
+
+
+def test_grower_policy_switch_gives_identical_results(plf, product):
+    """plf_set_grower_policy: the streaming multi-warp grower (automatic choice for small launches) and the one-warp-per-image
+    grower (throughput policy) give the same arrays, through the eager pass and the replayed CUDA graph, switching back and forth."""
+    W, H = 752, 480
+    L, R = plf.synth_batch(W, H, [4301, 4302, 4303])
+    f = plf.Frontend(product, max_batch=3, lsd_nfeatures=0)
+    ref = None
+    for policy in (0, 1, 0, 1):
+        f.set_grower_policy(policy)
+        for rep in range(3):                      # eager, capture, replay
+            r = f.frontend_batch(L, R)
+            got = {k: np.array(getattr(r, k), copy=True) for k in ("n_kl_left", "n_kl_right", "kl_left", "kl_right", "ldesc_left", "line_match12", "kp_left", "u_right")}
+            if ref is None:
+                ref = got
+                assert int(ref["n_kl_left"].min()) > 100
+            for k, v in got.items():
+                assert np.array_equal(v, ref[k]), (policy, rep, k)
+    with pytest.raises(Exception):
+        f.set_grower_policy(7)

@@ -482,7 +482,7 @@ def main():
     barrier()
 
     # latency of ONE pair through the batched call on an otherwise idle GPU (host buffers in, results out)
-    lat_ms = None
+    lat_ms = lat5_ms = None
     try:
         f1 = plf.Frontend(prod, device=local_rank, width=W, height=H, max_batch=1, **WORKLOAD)
         o1 = f1.new_result(1, pinned=True)
@@ -492,6 +492,18 @@ def main():
         for k in range(5):
             f1.frontend_batch(Ld[k % distinct:k % distinct + 1], Rd[k % distinct:k % distinct + 1], o1)
         lat_ms = (time.perf_counter() - t1) / 5 * 1e3
+        # ... and through the reference's own five signatures, one call after the other on one context (c2-like configs)
+        if WORKLOAD.get("has_points", 1) and WORKLOAD.get("has_lines", 1):
+            def five(k):
+                kp = f1.orb_extract(0, Ld[k])[1]; f1.orb_extract(1, Rd[k])
+                kl = f1.line_extract(0, Ld[k])[0]; f1.line_extract(1, Rd[k])
+                f1.stereo_match_points(len(kp)); f1.stereo_match_lines(len(kl))
+            for k in range(2):
+                five(k % distinct)
+            t1 = time.perf_counter()
+            for k in range(4):
+                five(k % distinct)
+            lat5_ms = (time.perf_counter() - t1) / 4 * 1e3
         f1.close()
     except Exception:
         pass
@@ -539,6 +551,7 @@ def main():
             "gpu_launches": launches,
             **({"grower_policy": {"auto_pairs_per_s": value, "throughput_pairs_per_s": value_tp}} if value_tp else {}),
             "latency_ms_single_pair": None if lat_ms is None else round(lat_ms, 2),
+            "latency_ms_five_signatures": None if lat5_ms is None else round(lat5_ms, 2),
             "ms_per_stage": {k: round(v, 4) for k, v in stage_acc.items()},
             "grow_ms_per_image": grow_img,
             "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved, "peak": peak,

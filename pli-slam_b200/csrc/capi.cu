@@ -407,7 +407,7 @@ static int check_device_flags(plf_ctx* c) {
     if (e) {
         cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream);
         char buf[128];
-        snprintf(buf, sizeof buf, "device-side capacity overflow, flags=0x%x", e);
+        snprintf(buf, sizeof buf, "device-side capacity overflow (flag 8: streaming region grower stalled), flags=0x%x", e);
         return fail(PLF_ERR_INVALID, buf);
     }
     return PLF_OK;

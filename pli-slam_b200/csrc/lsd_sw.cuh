@@ -71,6 +71,7 @@ struct SwShared {
     int actN[SW_NW];
     uint32_t actTag[SW_NW];         // 0 = none
     int scanChunk, commitChunk, lock, nSeg;
+    int panic;                      // watchdog: a warp found nothing to do for seconds (a protocol stall would otherwise hang the GPU)
     int cnt[16];                    // PLF_SW_FLAGS & 4: statistics
     long long clk[8];
 };
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
         }
         for (int i = threadIdx.x; i < SW_WIN; i += 32 * SW_NW) { sh.chStat[i] = 0; sh.robbed[i] = 0u; sh.dirty[i] = 0u; sh.slow[i] = 0u; sh.failedW[i] = 0u; sh.slowRec[i] = 0u; sh.depN[i] = 0; }
         if (threadIdx.x < SW_NW) sh.actTag[threadIdx.x] = 0u;
-        if (threadIdx.x == 0) { sh.scanChunk = 0; sh.commitChunk = 0; sh.lock = 0; sh.nSeg = 0; }
+        if (threadIdx.x == 0) { sh.scanChunk = 0; sh.commitChunk = 0; sh.lock = 0; sh.nSeg = 0; sh.panic = 0; }
         if (threadIdx.x < 16) sh.cnt[threadIdx.x] = 0;
         if (threadIdx.x < 8) sh.clk[threadIdx.x] = 0;
     }
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
     while (true) {
         int cc = *vCommit;
         if (cc >= nChunks) break;
+        if (*(volatile int*)&sh.panic) break;
         // ---- 1. commit: whoever finds the chunk at the commit pointer done, one warp at a time ----
         if (vStat[cc & (SW_WIN - 1)] >= 2) {
             int got = 0;
@@ -439,7 +441,10 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
             // warp costs the growing ones of its SM issue slots (a quarter of the kernel's instructions before the back-off)
             SW_CNT(7);
             __nanosleep(idle < 3 ? 250 : (idle < 8 ? 1000 : 3000));
-            ++idle;
+            if (++idle > 6000000) {                // ~18 s without anything to take or commit: give up loudly (flag 8), never hang
+                if (lane == 0) { atomicOr(err, 8); atomicExch(&sh.panic, 1); }
+                __syncwarp();
+            }
             continue;
         }
         idle = 0;
@@ -496,12 +501,13 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                     SW_CNT(11);
                 }
                 n = grow(Rw + head, warpCap - head, tag, pk0, false, nd, regAngle);
-                if (nd >= 0 && !grow_is_invalid<2>(c)) break;
+                const bool robbedNow = grow_is_invalid<2>(c);
+                if (nd >= 0 && !robbedNow) break;
                 SW_CNT(1);
                 if ((flags & 4) && lane == 0) atomicAdd(&sh.cnt[9], n);
                 sw_withdraw(sh, O, P, Rw + head + SW_HDR, n, tag, c.PB, lane);
                 nd = -1;
-                if (flags & 16) break;
+                if ((flags & 16) || !robbedNow) break;        // (not robbed: out of room — left to the committing warp, which has room for any region)
             }
             if (nd < 0) {
                 // given up: no record, no claim left; the robbed bit has served (a quick look at the seed is all commit needs)

@@ -890,7 +890,8 @@ __global__ void __launch_bounds__(32) lsd_grow_kernel(PlfGeom g, const float4* l
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K4c'  the same region growing for SMALL batches: several regions of ONE image in flight (a block of MW warps per
+// K4c'  (round 1; superseded on the product path by lsd_grow_sw_kernel, kept behind PLF_LSD_GROWER=mw for comparison)
+// the same region growing for SMALL batches: several regions of ONE image in flight (a block of MW warps per
 // image) with the sequential result.  A region only depends on the `used` state of the pixels it examines, so the next
 // few unused seeds (picked at least MW_DIST pixels apart; seeds on the same edge would only collide) are grown
 // speculatively against the committed bitmap, each claiming its pixels in a per-wave owner map with atomicMin(tag):
@@ -1486,8 +1487,10 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     }
     plf_mark(c, "lsd_grow");
     {
-        // seq (one warp per image) for wide launches and mw (16 warps per image) for <= 128 images are the product path;
-        // PLF_LSD_GROWER=stream selects the one-lane-per-region grower (exact, measured slower: profiles/r02_stream_grower.md)
+        // seq (one warp per image) for wide launches and sw (16 warps per image, streaming: lsd_sw.cuh) for <= 296 images are
+        // the product path (plf_set_grower_policy can keep seq for every size); PLF_LSD_GROWER=seq|mw|stream|lane selects one
+        // of the growers by hand: mw = the wave-synchronous predecessor of sw, stream / lane = the two structures that were
+        // measured and rejected (profiles/r02_grower_experiments.md)
         static const char* s_mode = getenv("PLF_LSD_GROWER");
         // per-image run time of the one-warp-per-image grower, recorded only while stage timing is on (bench.py reports max / mean)
         unsigned long long* growNs = nullptr;

@@ -39,7 +39,11 @@
 //  * Heuristic (efficiency only): a seed that lies on the axis of a region another warp is growing right now, with an
 //    aligned level-line angle and within reach of it, will most likely be swallowed by it: it is not started (parked);
 //    the commit pointer grows it if it is still free when its turn comes.
-// refine >= 1 keeps the sequential kernel (its re-growing un-marks pixels).
+// refine >= 1 keeps the sequential kernel (its re-growing un-marks pixels: the claims of the first growth would have to stay in
+// place until the region commits).
+// PLF_SW_FLAGS (environment, experiment switches; results are exact with every combination): 1 owner map read through L1,
+// 2 parking heuristic on, 4 print the counters of image 0, 16 no second try after a robbery, 32 only warp 0 works, 64 every
+// chunk takes the slow commit path.
 
 #define SW_NW PLF_SW_WARPS
 #define SW_HDR 16                   // ints in front of a record's pixel list: tag n flags ndep seg[4] deps[8]

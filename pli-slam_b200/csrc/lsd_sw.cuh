@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
     }
     __threadfence_block();
     __syncthreads();
+    const long long tInit = clock64() - tStart;
 
     volatile int* vStat = sh.chStat;
     volatile int* vCommit = &sh.commitChunk;
@@ -570,6 +571,8 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
         printf("sw img %d: ns %d chunks %d | recorded %d (%d px, %d with deps) given up %d (%d px, %d retried) failedRec %d (%d more saved by the pixel check) grownAtCommit %d (%d px) parked %d | chunks fast %d (%d after a look at the seeds) slow %d (failed dep %d) | idle spins %d | cycles total %lld commit %lld (regrow %lld, slow path incl. regrow %lld, seed looks %lld) segs %d\n",
                img, ns, nChunks, sh.cnt[0], sh.cnt[10], sh.cnt[12], sh.cnt[1], sh.cnt[9], sh.cnt[11], sh.cnt[2], sh.cnt[15], sh.cnt[3], sh.cnt[8], sh.cnt[4], sh.cnt[5], sh.cnt[14], sh.cnt[6], sh.cnt[13], sh.cnt[7],
                clock64() - tStart, sh.clk[0], sh.clk[1], sh.clk[2], sh.clk[3], sh.nSeg);
+    if ((flags & 4) && threadIdx.x == 0 && blockIdx.x == 0)
+        printf("sw init (owner map, position map): %lld cycles\n", tInit);
     if ((flags & 4) && threadIdx.x == 0 && blockIdx.x == 0)
         printf("sw commit split: acquire+fence %lld, table reads %lld, body (fast or slow) %lld, publish %lld\n", sh.clk[4], sh.clk[5], sh.clk[7], sh.clk[6]);
     if (threadIdx.x == 0) nSegsOut[img] = min(sh.nSeg, g.segCap);

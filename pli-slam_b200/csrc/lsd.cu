@@ -344,6 +344,10 @@ struct GrowCtx {
     uint32_t* deps;     // shared memory, SW_MAXDEP tags of earlier, uncommitted regions whose claims this region skipped
     uint32_t floorTag;  // tags below this were committed when the region started: their claims are final
     int maxN;           // room for the pixel list
+    const int* posMap;  // seed-list position of every pixel (dirty marks when a pixel is given back)
+    unsigned* dirty;    // shared memory, one word per chunk of the window
+    unsigned* failedW;  // shared memory, one word per chunk of the window
+    const int* scanChunk;   // shared memory: chunks handed out so far
     int* relTop;        // end of the free part of the record buffer: the pixels skipped as an uncommitted earlier region's
                         // are listed downwards from here (with repetitions), SW_MAXREL at most
     int* actN;          // shared memory: current size of the region, for the parking heuristic of the other warps
@@ -748,6 +752,22 @@ __device__ __forceinline__ double lsd_dist_sq(double x1, double y1, double x2, d
 
 // LSD refine() for refine = 1 (STANDARD): if the rectangle is too sparse, re-grow with a tolerance taken from the local
 // angle spread, then shrink the region radius until it is dense.  Returns false if the region is rejected.
+// *(reg[i].used) = NOTUSED: the bitmap bit in the sequential kernel; in the streaming kernel (final mode only) the pixel goes
+// back to PLF_FREE and its own seed position is marked dirty — whoever skipped that seed has to look again
+template <int MODE>
+__device__ __forceinline__ void lsd_unmark(const GrowCtx& c, int qb) {
+    if (MODE == 0) {
+        atomicAnd(c.used + (qb >> 5), ~(1u << (qb & 31)));
+    } else {
+        if (atomicCAS(c.owner + qb, c.tag, PLF_FREE) == c.tag) {
+            const int pos = c.posMap[qb];
+            __threadfence_block();
+            if ((pos >> 5) < *(volatile const int*)c.scanChunk) atomicOr(c.dirty + ((pos >> 5) & (SW_WIN - 1)), 1u << (pos & 31));
+        }
+    }
+}
+
+template <int MODE = 0>
 __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[34], int& n, double& regAngle, double prec, double densityTh,
                            RectFit& rf) {
     const int lane = c.lane, W = c.W;
@@ -766,7 +786,7 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[34], int& n, double
         if (lane < cnt) {
             const int rp = c.R[i0 + lane];
             const int ry = rp >> 16, rx = rp & 0xFFFF, qb = ry * c.PB + rx;
-            atomicAnd(c.used + (qb >> 5), ~(1u << (qb & 31)));                    // *(reg[i].used) = NOTUSED
+            lsd_unmark<MODE>(c, qb);                                              // *(reg[i].used) = NOTUSED
             if (lsd_dist(xc, yc, (double)rx, (double)ry) < rf.width) {
                 double d = __dsub_rn((double)c.LUT[c.G[qb]].x * kDegToRad, angC);         // angle_diff_signed
                 while (d <= -kPi) d += 2 * kPi;
@@ -785,7 +805,9 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[34], int& n, double
                                                      __dmul_rn(mean, mean))));
     __syncwarp();
     __threadfence_block();
-    n = grow_region<0>(c, pk0, p0, make_align_tol(tau), regAngle);
+    if (MODE == 2 && lane == 0)       // whoever relied on this region's first growth has to look at the pixels again
+        atomicOr(c.failedW + (((c.tag - 1u) >> 5) & (SW_WIN - 1)), 1u << ((c.tag - 1u) & 31u));
+    n = grow_region<MODE>(c, pk0, p0, make_align_tol(tau), regAngle);
     if (n < 2) return false;
     rect_fit<true>(c, s_sum, n, regAngle, prec, rf);
     density = (double)n / __dmul_rn(lsd_dist(rf.x1, rf.y1, rf.x2, rf.y2), rf.width);
@@ -802,16 +824,22 @@ __device__ bool lsd_refine(const GrowCtx& c, double (*s_sum)[34], int& n, double
                 const int rp = c.R[i];
                 const int ry = rp >> 16, rx = rp & 0xFFFF;
                 if (lsd_dist_sq(xc, yc, (double)rx, (double)ry) > radSq) {
-                    const int q = ry * c.PB + rx;
-                    atomicAnd(c.used + (q >> 5), ~(1u << (q & 31)));
+                    if (MODE == 0) lsd_unmark<MODE>(c, ry * c.PB + rx);
                     c.R[i] = c.R[sz - 1];
+                    if (MODE != 0) c.R[sz - 1] = rp;      // the removed pixels collect behind the list, un-marked below by all lanes
                     --sz;
                     --i;
                 }
             }
         }
+        const int nBefore = n;
         n = __shfl_sync(0xffffffffu, sz, 0);
         __syncwarp();
+        if (MODE != 0)
+            for (int i = n + lane; i < nBefore; i += 32) {
+                const int rp = c.R[i];
+                lsd_unmark<MODE>(c, (rp >> 16) * c.PB + (rp & 0xFFFF));
+            }
         if (n < 2) return false;
         rect_fit<true>(c, s_sum, n, regAngle, prec, rf);
         density = (double)n / __dmul_rn(lsd_dist(rf.x1, rf.y1, rf.x2, rf.y2), rf.width);
@@ -1445,7 +1473,10 @@ static int plf_ensure_sw_buffers(plf_ctx* c) {
     }
     static size_t s_granted[64] = {};
     if (plf_raise_smem_optin(s_granted, c->device, sizeof(SwShared)))
-        cudaFuncSetAttribute(lsd_grow_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SwShared));
+    {
+        cudaFuncSetAttribute(lsd_grow_sw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SwShared));
+        cudaFuncSetAttribute(lsd_grow_sw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SwShared));
+    }
     return 0;
 }
 
@@ -1501,7 +1532,12 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         }
         const bool wantStream = s_mode && !strcmp(s_mode, "stream");
         const bool wantLane = s_mode && !strcmp(s_mode, "lane");
-        if (g.refine >= 1)
+        static const int s_swFlags = getenv("PLF_SW_FLAGS") ? atoi(getenv("PLF_SW_FLAGS")) : 0;      // experiment switches, see lsd_sw.cuh
+        if (g.refine >= 1 && !s_mode && nImg <= PLF_SW_MAX_IMG && c->growerPolicy != PLF_GROWER_THROUGHPUT && plf_ensure_sw_buffers(c) == 0)
+            // few images, refine = 1: the streaming grower; regions that need refining are left to its committing warp
+            lsd_grow_sw_kernel<true><<<nImg, 32 * SW_NW, sizeof(SwShared), s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_swOwner,
+                                                                               c->d_swReg, c->d_swPos, c->d_segs, c->d_nSegs, c->d_err, imgFirst, s_swFlags);
+        else if (g.refine >= 1)
             lsd_grow_kernel<true><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                       c->d_nSegs, c->d_err, imgFirst, growNs);
         else if (wantStream && plf_ensure_stream_buffers(c) == 0) {
@@ -1529,8 +1565,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
                                                         c->d_segs, c->d_nSegs, c->d_err, imgFirst);
         } else if (nImg <= PLF_SW_MAX_IMG && c->growerPolicy != PLF_GROWER_THROUGHPUT && plf_ensure_sw_buffers(c) == 0) {
             // few images: 16 regions of each image in flight, one per warp, streaming with an in-order commit pointer
-            static const int s_swFlags = getenv("PLF_SW_FLAGS") ? atoi(getenv("PLF_SW_FLAGS")) : 0;      // experiment switches, see lsd_sw.cuh
-            lsd_grow_sw_kernel<<<nImg, 32 * SW_NW, sizeof(SwShared), s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_swOwner,
+            lsd_grow_sw_kernel<false><<<nImg, 32 * SW_NW, sizeof(SwShared), s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_swOwner,
                                                                          c->d_swReg, c->d_swPos, c->d_segs, c->d_nSegs, c->d_err, imgFirst, s_swFlags);
         } else
             lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,

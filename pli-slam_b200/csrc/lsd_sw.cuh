@@ -39,8 +39,10 @@
 //  * Heuristic (efficiency only): a seed that lies on the axis of a region another warp is growing right now, with an
 //    aligned level-line angle and within reach of it, will most likely be swallowed by it: it is not started (parked);
 //    the commit pointer grows it if it is still free when its turn comes.
-// refine >= 1 keeps the sequential kernel (its re-growing un-marks pixels: the claims of the first growth would have to stay in
-// place until the region commits).
+// refine = 1 (re-growing with a tolerance from the local angle spread, radius reduction): a region that un-marks pixels would
+// have to keep the claims of its first growth in place until it commits — an earlier region that takes a given-back pixel could
+// otherwise no longer be noticed — so speculative warps only detect that a region is too sparse and leave it to the committing
+// warp, which grows AND refines it in final mode (every earlier region final; given-back pixels marked dirty, failed bit set).
 // PLF_SW_FLAGS (environment, experiment switches; results are exact with every combination): 1 owner map read through L1,
 // 2 parking heuristic on, 4 print the counters of image 0, 16 no second try after a robbery, 32 only warp 0 works, 64 every
 // chunk takes the slow commit path.
@@ -116,6 +118,7 @@ __device__ __forceinline__ void sw_segment(const RectFit& rf, double lsdScale, f
     }
 }
 
+template <bool REFINE>
 __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, const float4* lut, const int* gmap, const int* seeds,
                                                                 const int* nSeeds, const uint32_t* usedAll, uint32_t* ownerAll,
                                                                 int* regAll, int* posAll, float* segs,
@@ -151,6 +154,10 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
     c.robbed = sh.robbed;
     c.deps = sh.dep[w];
     c.actN = &sh.actN[w];
+    c.posMap = P;
+    c.dirty = sh.dirty;
+    c.failedW = sh.failedW;
+    c.scanChunk = &sh.scanChunk;
     c.ldcg = (flags & 1) != 0;
     const long long tStart = clock64();
     {
@@ -390,10 +397,16 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
                                 __syncwarp();
                                 int nd;
                                 double regAngle;
-                                const int n = grow(Rc, 0, tagStar, pkStar, true, nd, regAngle);
-                                if (n >= g.minRegSize) {
-                                    RectFit rf;
-                                    rect_fit<false>(c, sh.sum[w], n, regAngle, prec, rf);
+                                int n = grow(Rc, 0, tagStar, pkStar, true, nd, regAngle);
+                                bool keep = n >= g.minRegSize;
+                                RectFit rf;
+                                if (keep) {
+                                    rect_fit<REFINE>(c, sh.sum[w], n, regAngle, prec, rf);
+                                    // refine = 1: re-growing and radius reduction happen here only, where every earlier region
+                                    // is final; pixels the region gives back are marked dirty, its failed bit tells whoever relied on it
+                                    if (REFINE) keep = lsd_refine<2>(c, sh.sum[w], n, regAngle, prec, g.densityTh, rf);
+                                }
+                                if (keep) {
                                     float sg[4];
                                     sw_segment(rf, g.lsdScale, sg);
                                     if (nSeg < g.segCap) {
@@ -524,7 +537,14 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
             float sg[4] = {0.f, 0.f, 0.f, 0.f};
             if (n >= g.minRegSize) {
                 RectFit rf;
-                rect_fit<false>(c, sh.sum[w], n, regAngle, prec, rf);
+                rect_fit<REFINE>(c, sh.sum[w], n, regAngle, prec, rf);
+                if (REFINE && (double)n / __dmul_rn(lsd_dist(rf.x1, rf.y1, rf.x2, rf.y2), rf.width) < g.densityTh) {
+                    // too sparse: refine() would re-grow it and give pixels back — only the committing warp does that
+                    SW_CNT(1);
+                    sw_withdraw(sh, O, P, Rw + head + SW_HDR, n, tag, c.PB, lane);
+                    slowMask |= 1u << l;
+                    continue;
+                }
                 sw_segment(rf, g.lsdScale, sg);
                 rflags = 1;
                 if (lane == 0) Sq[segHead] = make_float4(sg[0], sg[1], sg[2], sg[3]);

@@ -664,13 +664,14 @@ def test_large_batch_sequential_grower_matches_oracle(plf, product, oracle):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("W,H,batch", [(752, 480, 1), (752, 480, 5), (641, 479, 2), (1241, 376, 3)])
-def test_streaming_small_batch_grower_matches_oracle(plf, product, oracle, W, H, batch):
+@pytest.mark.parametrize("W,H,batch,refine", [(752, 480, 1, 0), (752, 480, 5, 0), (641, 479, 2, 0), (1241, 376, 3, 0), (752, 480, 2, 1)])
+def test_streaming_small_batch_grower_matches_oracle(plf, product, oracle, W, H, batch, refine):
     """Launches of at most 296 images go through lsd_grow_sw_kernel (one region per warp, 16 regions of an image in flight,
     in-order commit pointer): every segment-derived array equal to the oracle with ALL lines kept, over several calls on one
-    context (owner map, position map and record buffers are reused from call to call)."""
-    f = plf.Frontend(product, width=W, height=H, max_batch=batch, lsd_nfeatures=0)
-    o = plf.Frontend(oracle, width=W, height=H, max_batch=batch, lsd_nfeatures=0)
+    context (owner map, position map and record buffers are reused from call to call).  refine = 1: regions that need
+    refining are grown and refined by the kernel's committing warp."""
+    f = plf.Frontend(product, width=W, height=H, max_batch=batch, lsd_nfeatures=0, lsd_refine=refine)
+    o = plf.Frontend(oracle, width=W, height=H, max_batch=batch, lsd_nfeatures=0, lsd_refine=refine)
     for call in range(3):
         L, R = plf.synth_batch(W, H, [9100 + 17 * call + b for b in range(batch)])
         rg, ro = f.frontend_batch(L, R), o.frontend_batch(L, R)

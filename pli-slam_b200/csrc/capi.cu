@@ -239,6 +239,9 @@ static int create_buffers(plf_ctx* c, const plf_params* p, std::vector<PlfCell>&
     PLF_CUDA_OK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     PLF_CUDA_OK(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
     PLF_CUDA_OK(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+    PLF_CUDA_OK(cudaStreamCreateWithFlags(&c->streamSpec[0], cudaStreamNonBlocking));
+    PLF_CUDA_OK(cudaStreamCreateWithFlags(&c->streamSpec[1], cudaStreamNonBlocking));
+    PLF_CUDA_OK(cudaEventCreateWithFlags(&c->evUp, cudaEventDisableTiming));
     const size_t npx = (size_t)g.Ws * g.Hs;
     PLF_CUDA_OK(dalloc(&c->d_pyr, nImg * g.pyrBytes + 1024));   // +256: the FAST tile loader reads whole 32-bit words
     PLF_CUDA_OK(dalloc(&c->d_blur, nImg * g.pyrBytes));
@@ -376,6 +379,10 @@ PLF_API int plf_destroy(plf_ctx* c) {
     if (c->graphExec) cudaGraphExecDestroy(c->graphExec);
     if (c->h_counts) cudaFreeHost(c->h_counts);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (int k = 0; k < 2; ++k) if (c->streamSpec[k]) { cudaStreamSynchronize(c->streamSpec[k]); cudaStreamDestroy(c->streamSpec[k]); }
+    if (c->evUp) cudaEventDestroy(c->evUp);
+    if (c->d_cmp) cudaFree(c->d_cmp);
+    if (c->d_cmpFlag) cudaFree(c->d_cmpFlag);
     if (c->evFork) cudaEventDestroy(c->evFork);
     if (c->evJoin) cudaEventDestroy(c->evJoin);
     if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -413,6 +420,55 @@ static int check_device_flags(plf_ctx* c) {
     return PLF_OK;
 }
 
+// ---- speculative line path of the single-image entry points --------------------------------------------------------
+// The reference hands one image to ORBextractor::operator() and to Lineextractor::operator() of the same side (four threads,
+// src/Frame.cc:128-135); through this ABI the four calls come one after the other.  Once the library has SEEN
+// plf_line_extract(side) arrive with the image plf_orb_extract(side) had, plf_orb_extract starts the line path of its image on
+// a side stream as well, and plf_line_extract — after comparing its image with the uploaded one, byte for byte, on the device —
+// only collects the result: the two line extractions of a pair then overlap each other and the ORB kernels
+// (five signatures of one pair: 22.7 -> see DESIGN.md).  Anything else that touches the context first waits for the side streams.
+__global__ void __launch_bounds__(256) image_equal_kernel(const uint8_t* a, int ap, const uint8_t* b, int bp, int w, int h, int* differs) {
+    const int y = blockIdx.y, x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (y >= h || x >= w) return;
+    bool d = false;
+    for (int k = 0; k < 4 && x + k < w; ++k) d |= a[(size_t)y * ap + x + k] != b[(size_t)y * bp + x + k];
+    if (d) atomicOr(differs, 1);
+}
+
+static void plf_spec_join(plf_ctx* c, int side) {
+    if (c->specPending[side]) {
+        cudaStreamSynchronize(c->streamSpec[side]);
+        c->specPending[side] = false;
+        if (++c->specMisses >= 2) c->specEnabled = false;      // results nobody collected: stop guessing
+    }
+}
+
+// every entry point but plf_orb_extract / plf_line_extract / plf_stereo_match_points: device, and nothing speculative in flight
+cudaError_t plf_enter(plf_ctx* c) {
+    const cudaError_t e = cudaSetDevice(c->device);
+    plf_spec_join(c, 0);
+    plf_spec_join(c, 1);
+    c->orbFresh[0] = c->orbFresh[1] = false;
+    return e;
+}
+
+// is `img` the image that sits in level 0 of this side's pyramid block?  (exact, on the device; ~50 us)
+static int plf_same_image(plf_ctx* c, int side, const uint8_t* img, int stride, bool* same) {
+    const PlfGeom& g = c->g;
+    if (!c->d_cmp) {
+        PLF_CUDA_OK(cudaMalloc((void**)&c->d_cmp, (size_t)g.W * g.H));
+        PLF_CUDA_OK(cudaMalloc((void**)&c->d_cmpFlag, sizeof(int)));
+    }
+    PLF_CUDA_OK(cudaMemcpy2DAsync(c->d_cmp, g.W, img, stride, g.W, g.H, cudaMemcpyHostToDevice, c->stream));
+    PLF_CUDA_OK(cudaMemsetAsync(c->d_cmpFlag, 0, sizeof(int), c->stream));
+    image_equal_kernel<<<dim3((g.W + 1023) / 1024, g.H), 256, 0, c->stream>>>(c->d_cmp, g.W, c->d_pyr + (size_t)side * g.pyrBytes + g.lv[0].off,
+                                                                              g.lv[0].pitch, g.W, g.H, c->d_cmpFlag);
+    PLF_CUDA_OK(cudaMemcpyAsync(&c->h_counts[3], c->d_cmpFlag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
+    *same = c->h_counts[3] == 0;
+    return PLF_OK;
+}
+
 static int upload_image(plf_ctx* c, int img, const uint8_t* src, int stride) {
     const PlfGeom& g = c->g;
     PLF_CUDA_OK(cudaMemcpy2DAsync(c->d_pyr + (size_t)img * g.pyrBytes + g.lv[0].off, g.lv[0].pitch, src, stride, g.W, g.H,
@@ -426,8 +482,22 @@ PLF_API int plf_orb_extract(plf_ctx* c, int side, const uint8_t* img, int w, int
     if (!img || w <= 0 || h <= 0) return PLF_ERR_EMPTY_IMAGE;
     if (w != c->g.W || h != c->g.H || stride < w) return fail(PLF_ERR_INVALID, "image size differs from context");
     PLF_CUDA_OK(cudaSetDevice(c->device));
+    plf_spec_join(c, side);                   // a line path nobody collected still reads this side's level 0
     int rc = upload_image(c, side, img, stride);
     if (rc) return rc;
+    c->orbFresh[side] = true;
+    static const bool s_noSpec = getenv("PLF_NO_SPEC") != nullptr || getenv("PLF_LSD_GROWER") != nullptr;
+    if (c->specEnabled && !s_noSpec && c->p.has_lines && !c->stageTiming) {
+        // the line path of this image, beside the ORB kernels and beside the other side's line path
+        cudaStream_t s1 = c->stream;
+        cudaEventRecord(c->evUp, s1);
+        cudaStreamWaitEvent(c->streamSpec[side], c->evUp, 0);
+        c->stream = c->streamSpec[side];
+        plf_launch_lines(c, side, 1);
+        c->stream = s1;
+        c->specPending[side] = true;
+        c->lineValid[side] = false;           // this side's line results are being replaced
+    }
     c->launches = plf_launch_orb(c, side, 1, lap0, lap1);
     PLF_CUDA_OK(cudaGetLastError());
     PLF_CUDA_OK(cudaMemcpyAsync(&c->h_counts[1], c->d_nKp + side, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -452,7 +522,7 @@ static int copy_level_out(plf_ctx* c, const uint8_t* base, int slot, int side, i
     if (w) *w = lv.w;
     if (h) *h = lv.h;
     if (!out) return PLF_OK;
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     PLF_CUDA_OK(cudaMemcpy2DAsync(out, out_stride, base + (size_t)(slot * 2 + side) * c->g.pyrBytes + lv.off, lv.pitch, lv.w, lv.h, cudaMemcpyDeviceToHost, c->stream));
     PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
     return PLF_OK;
@@ -470,7 +540,7 @@ PLF_API int plf_tap_blurred_level(plf_ctx* c, int slot, int side, int level, uin
 
 PLF_API int plf_tap_fast_candidates(plf_ctx* c, int slot, int side, int level, float* xyr, int cap, int* n) {
     if (!c || slot < 0 || slot * 2 + 1 >= c->nImgMax + 1 || side < 0 || side > 1 || level < 0 || level >= c->g.nLevels) return fail(PLF_ERR_INVALID, "bad slot/side/level");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     const PlfGeom& g = c->g;
     const PlfLevel& lv = g.lv[level];
     const int img = slot * 2 + side;
@@ -497,7 +567,7 @@ PLF_API int plf_tap_fast_candidates(plf_ctx* c, int slot, int side, int level, f
 PLF_API int plf_stereo_match_points(plf_ctx* c, float* u_right, float* depth, int cap) {
     if (!c) return PLF_ERR_INVALID;
     if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "stereo_match_points before both orb_extract calls");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(cudaSetDevice(c->device));                 // (point buffers only: a line path in flight on a side stream is left alone)
     c->launches = plf_launch_stereo_points(c, 0, 1);
     PLF_CUDA_OK(cudaGetLastError());
     PLF_CUDA_OK(cudaMemcpyAsync(&c->h_counts[1], c->d_nKp, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -516,11 +586,31 @@ PLF_API int plf_line_extract(plf_ctx* c, int side, const uint8_t* img, int w, in
     if (w != c->g.W || h != c->g.H || stride < w) return fail(PLF_ERR_INVALID, "image size differs from context");
     PLF_CUDA_OK(cudaSetDevice(c->device));
     if (!c->p.has_lines) { if (n) *n = 0; c->lineValid[side] = true; cudaMemsetAsync(c->d_nKl + side, 0, sizeof(int), c->stream); return PLF_OK; }
-    int rc = upload_image(c, side, img, stride);
-    if (rc) return rc;
-    // NOTE: the image lands in level 0 of this side's pyramid block; like the reference's Frame, callers pass the same
-    // image to orb_extract and line_extract of one side.
-    c->launches = plf_launch_lines(c, side, 1);
+    int rc = PLF_OK;
+    bool collected = false;
+    if (c->orbFresh[side] && (c->specPending[side] || (!c->specEnabled && c->specMisses < 2))) {
+        // level 0 of this side holds the image plf_orb_extract was handed: the same one?
+        bool same = false;
+        rc = plf_same_image(c, side, img, stride, &same);
+        if (rc) return rc;
+        if (same && c->specPending[side]) {
+            PLF_CUDA_OK(cudaStreamSynchronize(c->streamSpec[side]));      // the line path started by plf_orb_extract: collect it
+            c->specPending[side] = false;
+            c->specMisses = 0;
+            collected = true;
+        } else if (same) {
+            c->specEnabled = true;                                         // learnt: from the next frame on, start it early
+        }
+    }
+    if (!collected) {
+        plf_spec_join(c, side);
+        rc = upload_image(c, side, img, stride);
+        if (rc) return rc;
+        c->orbFresh[side] = false;
+        // NOTE: the image lands in level 0 of this side's pyramid block; like the reference's Frame, callers pass the same
+        // image to orb_extract and line_extract of one side.
+        c->launches = plf_launch_lines(c, side, 1);
+    }
     PLF_CUDA_OK(cudaGetLastError());
     PLF_CUDA_OK(cudaMemcpyAsync(&c->h_counts[1], c->d_nKl + side, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     rc = check_device_flags(c);
@@ -538,7 +628,7 @@ PLF_API int plf_line_extract(plf_ctx* c, int side, const uint8_t* img, int w, in
 PLF_API int plf_stereo_match_lines(plf_ctx* c, float* disp_se, double* le, int32_t* match12, int cap) {
     if (!c) return PLF_ERR_INVALID;
     if (!c->lineValid[0] || !c->lineValid[1]) return fail(PLF_ERR_STATE, "stereo_match_lines before both line_extract calls");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     c->launches = plf_launch_stereo_lines(c, 0, 1);
     PLF_CUDA_OK(cudaGetLastError());
     PLF_CUDA_OK(cudaMemcpyAsync(&c->h_counts[1], c->d_nKl, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -572,7 +662,7 @@ static int ensure_match_scratch(plf_ctx* c, int n) {
 static int match_impl(plf_ctx* c, const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr, int best_lr,
                       int32_t* m12, int* nm) {
     if (!c || n1 < 0 || n2 < 0 || (n1 && !d1) || (n2 && !d2) || (n1 && !m12)) return fail(PLF_ERR_INVALID, "bad descriptors");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     if (nm) *nm = 0;
     if (n1 == 0) return PLF_OK;
     int rc = ensure_match_scratch(c, std::max(n1, n2));
@@ -611,7 +701,7 @@ PLF_API int plf_tap_lsd_scaled(plf_ctx* c, int slot, int side, uint8_t* out, int
     if (w) *w = c->g.Ws;
     if (h) *h = c->g.Hs;
     if (!out) return PLF_OK;
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     PLF_CUDA_OK(cudaMemcpy2DAsync(out, out_stride, c->d_lsdU + (size_t)(slot * 2 + side) * c->g.Ps * c->g.Hs, c->g.Ps, c->g.Ws, c->g.Hs, cudaMemcpyDeviceToHost, c->stream));
     PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
     return PLF_OK;
@@ -621,7 +711,7 @@ PLF_API int plf_tap_lsd_angles(plf_ctx* c, int slot, int side, float* out, int* 
     if (w) *w = c->g.Ws;
     if (h) *h = c->g.Hs;
     if (!out) return PLF_OK;
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     const size_t npx = (size_t)c->g.Ws * c->g.Hs;
     // the angle of a defined pixel is the .x of its record in the per-device table, indexed by the pixel's gradient code
     std::vector<int> code(npx);
@@ -635,7 +725,7 @@ PLF_API int plf_tap_lsd_angles(plf_ctx* c, int slot, int side, float* out, int* 
 }
 PLF_API int plf_tap_lsd_segments(plf_ctx* c, int slot, int side, float* xyxy, int cap, int* n) {
     if (!c || !c->p.has_lines || slot < 0 || slot * 2 + 1 >= c->nImgMax + 1 || side < 0 || side > 1) return fail(PLF_ERR_INVALID, "bad slot/side");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     const int img = slot * 2 + side;
     int m = 0;
     PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -647,7 +737,7 @@ PLF_API int plf_tap_lsd_segments(plf_ctx* c, int slot, int side, float* xyxy, in
 }
 PLF_API int plf_tap_lbd_float(plf_ctx* c, int slot, int side, float* out, int cap, int* n) {
     if (!c || slot < 0 || slot * 2 + 1 >= c->nImgMax + 1 || side < 0 || side > 1) return fail(PLF_ERR_INVALID, "bad slot/side");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     const int img = slot * 2 + side;
     int m = 0;
     PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -661,7 +751,7 @@ PLF_API int plf_tap_lbd_float(plf_ctx* c, int slot, int side, float* out, int ca
 // ---- batch ---------------------------------------------------------------------------------------------------------
 PLF_API int plf_batch_upload(plf_ctx* c, const uint8_t* left, const uint8_t* right, int batch, int stride) {
     if (!c || !left || !right || batch < 1 || batch > c->p.max_batch || stride < c->g.W) return fail(PLF_ERR_INVALID, "bad batch");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     const PlfGeom& g = c->g;
     c->nMarks = 0;
     plf_mark(c, "h2d");
@@ -684,7 +774,7 @@ PLF_API int plf_batch_upload(plf_ctx* c, const uint8_t* left, const uint8_t* rig
 
 PLF_API int plf_batch_run(plf_ctx* c, int batch) {
     if (!c || batch < 1 || batch > c->batchResident) return fail(PLF_ERR_INVALID, "bad batch (upload first)");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     int n = 0;
     if (c->nMarks && strcmp(c->markNames[0], "h2d") != 0) c->nMarks = 0;   // run without a fresh upload: restart marks
     if (c->nMarks > 1 && !(c->nMarks == 2 && strcmp(c->markNames[1], "rectify") == 0)) c->nMarks = 0;
@@ -743,7 +833,7 @@ PLF_API int plf_batch_run(plf_ctx* c, int batch) {
 
 PLF_API int plf_batch_download(plf_ctx* c, int batch, plf_frame_out* o) {
     if (!c || !o || batch < 1 || batch > c->batchResident) return fail(PLF_ERR_INVALID, "bad batch");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     const PlfGeom& g = c->g;
     if (o->kp_cap < g.kpCap || o->kl_cap < g.klCap) return fail(PLF_ERR_INVALID, "output capacity smaller than plf_keypoint_capacity/plf_keyline_capacity");
     cudaStream_t s = c->stream;
@@ -791,7 +881,7 @@ PLF_API int plf_frontend_batch(plf_ctx* c, const uint8_t* left, const uint8_t* r
 
 PLF_API int plf_sync(plf_ctx* c) {
     if (!c) return PLF_ERR_INVALID;
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
     return PLF_OK;
 }
@@ -823,7 +913,7 @@ PLF_API int plf_set_stage_timing(plf_ctx* c, int on) { if (!c) return PLF_ERR_IN
 PLF_API int plf_tap_grow_ns(plf_ctx* c, unsigned long long* out, int n_images) {
     if (!c || !out || n_images < 0 || n_images > c->nImgMax) return fail(PLF_ERR_INVALID, "bad image count");
     if (!c->d_growNs) { for (int i = 0; i < n_images; ++i) out[i] = 0; return PLF_OK; }
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
     PLF_CUDA_OK(cudaMemcpy(out, c->d_growNs, (size_t)n_images * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return PLF_OK;

@@ -18,7 +18,7 @@ PLF_API int plf_feature_grid(plf_ctx* c, int first_slot, int n_slots, int32_t* c
         idx_stride < c->g.kpCap)
         return fail(PLF_ERR_INVALID, "bad slot range / idx_stride smaller than plf_keypoint_capacity");
     if (!c->orbValid[0]) return fail(PLF_ERR_STATE, "feature_grid before the left keypoints were extracted");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     constexpr int NC1 = PLF_GRID_COLS * PLF_GRID_ROWS + 1;
     if (!c->d_gridStart) {
         PLF_CUDA_OK(dalloc(&c->d_gridStart, (size_t)c->p.max_batch * NC1));
@@ -42,7 +42,7 @@ PLF_API int plf_get_features_in_area(const plf_keypoint* kps, const int32_t* cel
 // device half shared by the two overloads: feature grid of the slot, candidate counts, candidate pool (CSR by query)
 static int window_candidates(plf_ctx* c, int slot, const std::vector<PlfWinQ>& q, std::vector<int>& start, std::vector<int2>& pool) {
     const int nq = (int)q.size();
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     cudaStream_t s = c->stream;
     constexpr int NC1 = PLF_GRID_COLS * PLF_GRID_ROWS + 1;
     if (!c->d_gridStart) {
@@ -94,7 +94,7 @@ PLF_API int plf_search_by_projection(plf_ctx* c, int slot, const plf_proj_query*
     if (n_matches) *n_matches = 0;
     {   // occupied[] is indexed by feature: it must cover the slot's left keypoints
         int N = 0;
-        PLF_CUDA_OK(cudaSetDevice(c->device));
+        PLF_CUDA_OK(plf_enter(c));
         PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
         PLF_CUDA_OK(cudaMemcpy(&N, c->d_nKp + slot * 2, 4, cudaMemcpyDeviceToHost));
         if (n_features < N) return fail(PLF_ERR_INVALID, "occupied[] is shorter than the slot's keypoint count");
@@ -157,7 +157,7 @@ static int search_projected(plf_ctx* c, int slot, const plf_frame_query* queries
         return fail(PLF_ERR_INVALID, "bad arguments");
     const int check_orientation = rule.orientation;
     if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "search_by_projection before the frame was extracted and stereo-matched");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     // the current frame's keypoint count and angles (rotation histogram)
     const int img = slot * 2;
     int N = 0;
@@ -276,7 +276,7 @@ PLF_API int plf_search_by_bow(plf_ctx* c, int slot, const uint8_t* kf_desc, cons
         (n_features && (!f_node || !match)))
         return fail(PLF_ERR_INVALID, "bad arguments");
     if (!c->orbValid[0]) return fail(PLF_ERR_STATE, "search_by_bow before the frame was extracted");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     cudaStream_t s = c->stream;
     const int img = slot * 2;
     int N = 0;
@@ -380,7 +380,7 @@ PLF_API int plf_match_lines_tracked(plf_ctx* c, int mode, const uint8_t* desc1, 
         return fail(PLF_ERR_INVALID, "bad arguments");
     if (n_assigned) *n_assigned = 0;
     if (n1 == 0) return PLF_OK;
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     cudaStream_t s = c->stream;
     const size_t oD1 = 0, oD2 = oD1 + align256((size_t)n1 * 32), oL1 = oD2 + align256((size_t)n2 * 32);
     const size_t oK2 = oL1 + align256((size_t)n1 * sizeof(plf_track_line)), oDisp = oK2 + align256((size_t)n2 * sizeof(plf_keyline));
@@ -449,7 +449,7 @@ PLF_API int plf_bow_set_vocabulary(plf_ctx* c, int which, int n_nodes, int level
             }
         }
     }
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
     PlfVocab& v = c->voc[which];
     void* old[] = {v.childFirst, v.childCount, v.child, v.word, v.desc, v.weight};
@@ -478,7 +478,7 @@ PLF_API int plf_bow_transform(plf_ctx* c, int which, int first_slot, int n_slots
         return fail(PLF_ERR_INVALID, "bad slot range / stride beyond the descriptor capacity");
     if (!c->voc[which].nNodes) return fail(PLF_ERR_STATE, "bow_transform before bow_set_vocabulary");
     if (which ? !(c->p.has_lines && c->lineValid[0]) : !c->orbValid[0]) return fail(PLF_ERR_STATE, "bow_transform before the descriptors exist");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     const size_t cap = (size_t)std::max(c->g.kpCap, c->g.klCap);
     if (!c->d_bowWord) {
         PLF_CUDA_OK(dalloc(&c->d_bowWord, (size_t)c->p.max_batch * cap));
@@ -508,7 +508,7 @@ PLF_API int plf_backproject(plf_ctx* c, int first_slot, int n_slots, const float
         return fail(PLF_ERR_INVALID, "bad slot range / rows beyond the keypoint or keyline capacity");
     if (!c->orbValid[0] || !c->orbValid[1]) return fail(PLF_ERR_STATE, "backproject before the stereo matches exist");
     if (l3d && !c->p.has_lines) return fail(PLF_ERR_STATE, "line back-projection on a context without lines");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     if (!c->d_bpPose) {
         PLF_CUDA_OK(dalloc(&c->d_bpPose, (size_t)c->p.max_batch * 12));
         PLF_CUDA_OK(dalloc(&c->d_bpX, (size_t)c->p.max_batch * c->g.kpCap * 3));
@@ -540,7 +540,7 @@ static cudaError_t stage_reserve(plf_ctx* c, size_t bytes) {
 PLF_API int plf_rectify_set_maps(plf_ctx* c, int side, const float* mx, const float* my, int src_w, int src_h) {
     if (!c || side < 0 || side > 1 || !mx || !my || src_w < 2 || src_h < 2 || src_w > 32767 || src_h > 32767)
         return fail(PLF_ERR_INVALID, "bad rectification maps");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     const size_t n = (size_t)c->g.W * c->g.H;
     // cv::remap's own conversion of the float maps: cvRound(map * 32) (round half to even), integer part saturated
     // to int16, 5-bit fractions; done once here instead of once per frame
@@ -563,7 +563,7 @@ PLF_API int plf_rectify(plf_ctx* c, int side, const uint8_t* raw, int raw_stride
     if (!c || side < 0 || side > 1 || !raw || !out) return fail(PLF_ERR_INVALID, "bad arguments");
     if (!c->d_rmap[side]) return fail(PLF_ERR_STATE, "rectify before rectify_set_maps");
     if (raw_stride < c->srcW[side] || out_stride < c->g.W) return fail(PLF_ERR_INVALID, "bad stride");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     const size_t bytes = (size_t)c->srcH[side] * raw_stride;
     PLF_CUDA_OK(stage_reserve(c, bytes));
     PLF_CUDA_OK(cudaMemcpyAsync(c->d_stage, raw, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -581,7 +581,7 @@ PLF_API int plf_batch_upload_raw(plf_ctx* c, const uint8_t* left, const uint8_t*
     if (!c || !left || !right || batch < 1 || batch > c->p.max_batch) return fail(PLF_ERR_INVALID, "bad batch");
     if (!c->d_rmap[0] || !c->d_rmap[1]) return fail(PLF_ERR_STATE, "batch_upload_raw before rectify_set_maps");
     if (raw_stride < c->srcW[0] || raw_stride < c->srcW[1]) return fail(PLF_ERR_INVALID, "bad stride");
-    PLF_CUDA_OK(cudaSetDevice(c->device));
+    PLF_CUDA_OK(plf_enter(c));
     c->nMarks = 0;
     plf_mark(c, "h2d");
     const size_t b0 = (size_t)batch * c->srcH[0] * raw_stride, b1 = (size_t)batch * c->srcH[1] * raw_stride;

@@ -1533,7 +1533,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         const bool wantStream = s_mode && !strcmp(s_mode, "stream");
         const bool wantLane = s_mode && !strcmp(s_mode, "lane");
         static const int s_swFlags = getenv("PLF_SW_FLAGS") ? atoi(getenv("PLF_SW_FLAGS")) : 0;      // experiment switches, see lsd_sw.cuh
-        if (g.refine >= 1 && !s_mode && nImg <= PLF_SW_MAX_IMG && c->growerPolicy != PLF_GROWER_THROUGHPUT && plf_ensure_sw_buffers(c) == 0)
+        if (g.refine >= 1 && !s_mode && imgFirst + nImg <= std::min(c->nImgMax, PLF_SW_MAX_IMG) && c->growerPolicy != PLF_GROWER_THROUGHPUT && plf_ensure_sw_buffers(c) == 0)
             // few images, refine = 1: the streaming grower; regions that need refining are left to its committing warp
             lsd_grow_sw_kernel<true><<<nImg, 32 * SW_NW, sizeof(SwShared), s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_swOwner,
                                                                                c->d_swReg, c->d_swPos, c->d_segs, c->d_nSegs, c->d_err, imgFirst, s_swFlags);
@@ -1563,7 +1563,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
             // the wave-synchronous predecessor of the streaming grower (kept for comparison)
             lsd_grow_mw_kernel<<<nImg, 32 * MW, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_owner, c->d_regMW,
                                                         c->d_segs, c->d_nSegs, c->d_err, imgFirst);
-        } else if (nImg <= PLF_SW_MAX_IMG && c->growerPolicy != PLF_GROWER_THROUGHPUT && plf_ensure_sw_buffers(c) == 0) {
+        } else if (imgFirst + nImg <= std::min(c->nImgMax, PLF_SW_MAX_IMG) && c->growerPolicy != PLF_GROWER_THROUGHPUT && plf_ensure_sw_buffers(c) == 0) {
             // few images: 16 regions of each image in flight, one per warp, streaming with an in-order commit pointer
             lsd_grow_sw_kernel<false><<<nImg, 32 * SW_NW, sizeof(SwShared), s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_swOwner,
                                                                          c->d_swReg, c->d_swPos, c->d_segs, c->d_nSegs, c->d_err, imgFirst, s_swFlags);

@@ -130,12 +130,12 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
     const size_t npxA = (npx + 3) & ~(size_t)3;
     const int warpBuf = PLF_SW_WARPBUF;
     const int warpCap = warpBuf;                                          // record headers and pixel lists
-    int* const imgReg = regAll + (size_t)blockIdx.x * (npxA + (size_t)SW_NW * PLF_SW_WARPBUF);   // [npxA] commit buffer, then SW_NW buffers of warpBuf
+    int* const imgReg = regAll + (size_t)img * (npxA + (size_t)SW_NW * PLF_SW_WARPBUF);   // [npxA] commit buffer, then SW_NW buffers of warpBuf
     int* const Rc = imgReg;
     int* const Rw = imgReg + npxA + (size_t)w * warpBuf;
     float4* const Sq = sh.segS[w];
-    uint32_t* const O = ownerAll + (size_t)blockIdx.x * npb;
-    int* const P = posAll + (size_t)blockIdx.x * npb;
+    uint32_t* const O = ownerAll + (size_t)img * npb;      // scratch by IMAGE index: launches for different images may overlap
+    int* const P = posAll + (size_t)img * npb;
     const int* S = seeds + (size_t)img * g.seedCap;
     float4* out = reinterpret_cast<float4*>(segs + (size_t)img * g.segCap * 4);
     const int ns = nSeeds[img];

@@ -91,6 +91,16 @@ struct plf_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;                  // plf_batch_run: the line path runs beside the point path (fork / join)
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    // plf_orb_extract starts the LINE path of the image it was handed on a side stream (speculatively: the reference passes the
+    // same image to both extractors of a side, src/Frame.cc:128-135), plf_line_extract collects it after an exact comparison
+    cudaStream_t streamSpec[2] = {nullptr, nullptr};
+    cudaEvent_t evUp = nullptr;
+    bool specPending[2] = {false, false};   // line path of the image in level 0 of this side is running / done on streamSpec[side]
+    bool orbFresh[2] = {false, false};      // level 0 of this side still holds the image plf_orb_extract uploaded
+    bool specEnabled = false;               // learnt: line_extract(side) was called with the image orb_extract(side) had
+    int specMisses = 0;
+    uint8_t* d_cmp = nullptr;               // staging copy of the image plf_line_extract was handed (W x H)
+    int* d_cmpFlag = nullptr;
     std::vector<float> scale, invScale, sigma2, invSigma2;
     std::vector<int> quota;
     // ORB device buffers
@@ -201,6 +211,7 @@ struct plf_ctx {
 // Stage marks: when stage timing is on, every launcher drops a CUDA event on the context stream before each stage;
 // the elapsed times between consecutive marks are the ms/stage figures of bench.py.
 void plf_mark(plf_ctx* c, const char* name);
+extern "C" cudaError_t plf_enter(plf_ctx* c);      // cudaSetDevice + wait for a speculative line path on the side streams (capi.cu)
 
 // --- stage launchers (each returns the number of kernel launches it issued) ---------------------------------------
 int plf_launch_orb(plf_ctx* c, int imgFirst, int nImg, int lap0, int lap1);

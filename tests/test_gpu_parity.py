@@ -704,3 +704,54 @@ def test_grower_policy_switch_gives_identical_results(plf, product):
                 assert np.array_equal(v, ref[k]), (policy, rep, k)
     with pytest.raises(Exception):
         f.set_grower_policy(7)
+
+
+def test_single_image_calls_with_speculative_line_path(plf, product, oracle):
+    """plf_orb_extract starts the line path of its image on a side stream once the library has seen plf_line_extract arrive
+    with the same image; plf_line_extract compares on the device and collects.  Every call order gives the oracle's arrays:
+    the reference's order over several frames (learning frame, then collected results), a DIFFERENT image handed to
+    line_extract (miss), ORB-only frames (results nobody collects), lines before ORB, a batched call in between."""
+    W, H = 752, 480
+    f = plf.Frontend(product, max_batch=2, lsd_nfeatures=0)
+    o = plf.Frontend(oracle, max_batch=2, lsd_nfeatures=0)
+    imgs = [plf.synth_pair(W, H, 5200 + k) for k in range(9)]
+    want = {}
+
+    def lines(fr, side, img):
+        kl, ld = fr.line_extract(side, img)
+        return np.array(kl, copy=True), np.array(ld, copy=True)
+
+    def expect(k, side):
+        if (k, side) not in want:
+            want[(k, side)] = lines(o, side, imgs[k][side])
+        return want[(k, side)]
+
+    def check(got, k, side, tag):
+        kl, ld = expect(k, side)
+        assert len(got[0]) == len(kl) and len(kl) > 100, (tag, k, side)
+        assert np.array_equal(got[0], kl) and np.array_equal(got[1], ld), (tag, k, side)
+
+    # the reference's order, five frames: ORB left, ORB right, lines left, lines right, both matchers
+    for k in range(5):
+        L, R = imgs[k]
+        kp = f.orb_extract(0, L)[1]; f.orb_extract(1, R)
+        gl, gr = lines(f, 0, L), lines(f, 1, R)
+        check(gl, k, 0, "ref order"); check(gr, k, 1, "ref order")
+        f.stereo_match_points(len(kp)); f.stereo_match_lines(len(gl[0]))
+    # a different image handed to line_extract than to orb_extract of that side
+    f.orb_extract(0, imgs[5][0]); f.orb_extract(1, imgs[5][1])
+    check(lines(f, 0, imgs[6][0]), 6, 0, "miss"); check(lines(f, 1, imgs[5][1]), 5, 1, "after miss")
+    # ORB only (whatever was started is never collected), then the reference's order again
+    for k in (6, 7):
+        f.orb_extract(0, imgs[k][0]); f.orb_extract(1, imgs[k][1])
+    check(lines(f, 0, imgs[7][0]), 7, 0, "after orb only"); check(lines(f, 1, imgs[7][1]), 7, 1, "after orb only")
+    # lines before ORB, and a batched call in between
+    check(lines(f, 0, imgs[8][0]), 8, 0, "lines first"); f.orb_extract(0, imgs[8][0])
+    Lb, Rb = plf.synth_batch(W, H, [5200, 5201])
+    rb = f.frontend_batch(Lb, Rb)
+    assert int(rb.n_kl_left[0]) == len(expect(0, 0)[0]) and np.array_equal(rb.kl_left[0, :len(expect(0, 0)[0])], expect(0, 0)[0])
+    f.orb_extract(1, imgs[8][1]); check(lines(f, 1, imgs[8][1]), 8, 1, "after batch")
+    for k in range(3):
+        L, R = imgs[k]
+        f.orb_extract(0, L); f.orb_extract(1, R)
+        check(lines(f, 0, L), k, 0, "again"); check(lines(f, 1, R), k, 1, "again")

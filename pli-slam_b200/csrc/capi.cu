@@ -522,7 +522,7 @@ static int copy_level_out(plf_ctx* c, const uint8_t* base, int slot, int side, i
     if (w) *w = lv.w;
     if (h) *h = lv.h;
     if (!out) return PLF_OK;
-    PLF_CUDA_OK(plf_enter(c));
+    PLF_CUDA_OK(cudaSetDevice(c->device));                 // (reads the point path's pyramid only: a line path on a side stream is left alone)
     PLF_CUDA_OK(cudaMemcpy2DAsync(out, out_stride, base + (size_t)(slot * 2 + side) * c->g.pyrBytes + lv.off, lv.pitch, lv.w, lv.h, cudaMemcpyDeviceToHost, c->stream));
     PLF_CUDA_OK(cudaStreamSynchronize(c->stream));
     return PLF_OK;

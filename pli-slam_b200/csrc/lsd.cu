@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(256) lsd_lut_kernel(float4* lut) {
     lut[i] = make_float4(a, (float)cs, (float)sn, __int_as_float(gx * gx + gy * gy));
 }
 
-__global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, int* gmap, uint32_t* used, int* n2max, int imgFirst) {
+__global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t* U, int* gmap, uint32_t* used, int* n2max, int imgFirst,
+                                                      uint32_t* owner) {
     // 128x8 tiles, 4 horizontally adjacent pixels per thread (aligned 32-bit loads of the u8 image, one 16-byte store of
     // the gradient-code map per thread, one bitmap word per 8 threads): 2x2 gradient and |g|^2; a pixel is defined iff
     // |g|^2 > n2Thresh, the integer image of LSD's "norm > rho" test (exact: host-searched with the same IEEE sqrt).
@@ -125,6 +126,11 @@ __global__ void __launch_bounds__(256) lsd_grad_kernel(PlfGeom g, const uint8_t*
         // gradient-code map (0 = undefined) and the grower's bitmap with the undefined pixels pre-marked as used: the
         // grower never looks at the record of an undefined pixel
         *reinterpret_cast<int4*>(gmap + (size_t)img * g.Ps * g.Hs + (size_t)y * g.Ps + x) = make_int4(gv[0], gv[1], gv[2], gv[3]);
+        // small launches: the owner map of the streaming grower (0 = undefined, PLF_FREE = unclaimed), so that its blocks need
+        // not walk the bitmap first
+        if (owner)
+            *reinterpret_cast<uint4*>(owner + (size_t)img * g.Ps * g.Hs + (size_t)y * g.Ps + x) =
+                make_uint4(gv[0] ? 0xFFFFFFFFu : 0u, gv[1] ? 0xFFFFFFFFu : 0u, gv[2] ? 0xFFFFFFFFu : 0u, gv[3] ? 0xFFFFFFFFu : 0u);
         unsigned w = ((gv[0] == 0) | ((gv[1] == 0) << 1) | ((gv[2] == 0) << 2) | ((gv[3] == 0) << 3)) << (4 * (threadIdx.x & 7));
         w |= __shfl_xor_sync(0xffffffffu, w, 1);
         w |= __shfl_xor_sync(0xffffffffu, w, 2);
@@ -159,7 +165,7 @@ __device__ __forceinline__ double lsd_bin_coef(int n2max, int nBins) {
 #define ORD_WARPS 16
 #define ORD_MLP 8
 __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, const int* gmap, const int* n2max, int* seeds,
-                                                         int* nSeeds, int imgFirst) {
+                                                         int* nSeeds, int imgFirst, int* posMap) {
     extern __shared__ int s_cur[];          // [ORD_WARPS][nBins] counters / cursors, then [nBins + 1] bin thresholds
     __shared__ int s_scan[ORD_WARPS];
     __shared__ int s_carry;
@@ -263,6 +269,7 @@ __global__ void __launch_bounds__(32 * ORD_WARPS) lsd_order_kernel(PlfGeom g, co
                 __syncwarp(wm);
                 if ((grp & lt) == 0) mine[bin] = b + __popc(grp);
                 out[b + __popc(grp & lt)] = (y << 16) | x;             // packed (y<<16 | x)
+                if (posMap) posMap[(size_t)img * g.Ps * g.Hs + (size_t)y * W + x] = b + __popc(grp & lt);     // streaming grower: pixel -> position
             }
             __syncwarp();
             x += 32;
@@ -1507,14 +1514,19 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
     lsd_upscale_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 31) / 32, nImg), dim3(32, 8), 0, s>>>(g, upSrc, upStride, ip, c->d_lsdU, c->d_lin + c->linLsdX, c->d_lin + c->linLsdY, imgFirst);
     plf_mark(c, "lsd_gradient");
     cudaMemsetAsync(c->d_n2max + imgFirst, 0, nImg * sizeof(int), s);
-    lsd_grad_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_n2, c->d_used, c->d_n2max, imgFirst);
+    // will the streaming grower run?  (same condition as below) then the gradient and order kernels fill its owner / position maps
+    static const char* s_modeEarly = getenv("PLF_LSD_GROWER");
+    const bool swWill = !s_modeEarly && imgFirst + nImg <= std::min(c->nImgMax, PLF_SW_MAX_IMG) && c->growerPolicy != PLF_GROWER_THROUGHPUT &&
+                        plf_ensure_sw_buffers(c) == 0;
+    lsd_grad_kernel<<<dim3((g.Ws + 127) / 128, (g.Hs + 7) / 8, nImg), dim3(32, 8), 0, s>>>(g, c->d_lsdU, c->d_n2, c->d_used, c->d_n2max, imgFirst,
+                                                                                           swWill ? c->d_swOwner : nullptr);
     plf_mark(c, "lsd_order");
     {
         const size_t smem = ((size_t)ORD_WARPS * g.nBins + g.nBins + 1) * sizeof(int);
         static size_t s_granted[64] = {};
         if (plf_raise_smem_optin(s_granted, c->device, smem))
             cudaFuncSetAttribute(lsd_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        lsd_order_kernel<<<nImg, 32 * ORD_WARPS, smem, s>>>(g, c->d_n2, c->d_n2max, c->d_seeds, c->d_nSeeds, imgFirst);
+        lsd_order_kernel<<<nImg, 32 * ORD_WARPS, smem, s>>>(g, c->d_n2, c->d_n2max, c->d_seeds, c->d_nSeeds, imgFirst, swWill ? c->d_swPos : nullptr);
     }
     plf_mark(c, "lsd_grow");
     {
@@ -1536,7 +1548,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         if (g.refine >= 1 && !s_mode && imgFirst + nImg <= std::min(c->nImgMax, PLF_SW_MAX_IMG) && c->growerPolicy != PLF_GROWER_THROUGHPUT && plf_ensure_sw_buffers(c) == 0)
             // few images, refine = 1: the streaming grower; regions that need refining are left to its committing warp
             lsd_grow_sw_kernel<true><<<nImg, 32 * SW_NW, sizeof(SwShared), s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_swOwner,
-                                                                               c->d_swReg, c->d_swPos, c->d_segs, c->d_nSegs, c->d_err, imgFirst, s_swFlags);
+                                                                               c->d_swReg, c->d_swPos, c->d_segs, c->d_nSegs, c->d_err, imgFirst, s_swFlags | (swWill ? 128 : 0));
         else if (g.refine >= 1)
             lsd_grow_kernel<true><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                       c->d_nSegs, c->d_err, imgFirst, growNs);
@@ -1566,7 +1578,7 @@ int plf_launch_lines(plf_ctx* c, int imgFirst, int nImg) {
         } else if (imgFirst + nImg <= std::min(c->nImgMax, PLF_SW_MAX_IMG) && c->growerPolicy != PLF_GROWER_THROUGHPUT && plf_ensure_sw_buffers(c) == 0) {
             // few images: 16 regions of each image in flight, one per warp, streaming with an in-order commit pointer
             lsd_grow_sw_kernel<false><<<nImg, 32 * SW_NW, sizeof(SwShared), s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_swOwner,
-                                                                         c->d_swReg, c->d_swPos, c->d_segs, c->d_nSegs, c->d_err, imgFirst, s_swFlags);
+                                                                         c->d_swReg, c->d_swPos, c->d_segs, c->d_nSegs, c->d_err, imgFirst, s_swFlags | (swWill ? 128 : 0));
         } else
             lsd_grow_kernel<false><<<nImg, 32, 0, s>>>(g, lut, c->d_n2, c->d_seeds, c->d_nSeeds, c->d_used, c->d_reg, c->d_segs,
                                                        c->d_nSegs, c->d_err, imgFirst, growNs);

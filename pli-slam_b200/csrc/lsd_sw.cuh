@@ -169,15 +169,17 @@ __global__ void __launch_bounds__(32 * SW_NW) lsd_grow_sw_kernel(PlfGeom g, cons
     // ---- owner map of a fresh image from the gradient kernel's bitmap (undefined pixels are pre-marked used), the
     //      position of every defined pixel in the seed list, tables ----
     {
-        const uint32_t* used = usedAll + (size_t)img * (g.Ps >> 5) * g.Hs;
-        const int nWords = (int)(npb >> 5);
-        for (int wd = w; wd < nWords; wd += SW_NW) {
-            const uint32_t bits = used[wd];
-            O[(size_t)wd * 32 + lane] = ((bits >> lane) & 1u) ? 0u : PLF_FREE;
-        }
-        for (int p = threadIdx.x; p < ns; p += 32 * SW_NW) {
-            const int sd = S[p];
-            P[(sd >> 16) * c.PB + (sd & 0xFFFF)] = p;
+        if (!(flags & 128)) {            // (flag 128: lsd_grad_kernel / lsd_order_kernel have filled both maps already)
+            const uint32_t* used = usedAll + (size_t)img * (g.Ps >> 5) * g.Hs;
+            const int nWords = (int)(npb >> 5);
+            for (int wd = w; wd < nWords; wd += SW_NW) {
+                const uint32_t bits = used[wd];
+                O[(size_t)wd * 32 + lane] = ((bits >> lane) & 1u) ? 0u : PLF_FREE;
+            }
+            for (int p = threadIdx.x; p < ns; p += 32 * SW_NW) {
+                const int sd = S[p];
+                P[(sd >> 16) * c.PB + (sd & 0xFFFF)] = p;
+            }
         }
         for (int i = threadIdx.x; i < SW_WIN; i += 32 * SW_NW) { sh.chStat[i] = 0; sh.robbed[i] = 0u; sh.dirty[i] = 0u; sh.slow[i] = 0u; sh.failedW[i] = 0u; sh.slowRec[i] = 0u; sh.depN[i] = 0; }
         if (threadIdx.x < SW_NW) sh.actTag[threadIdx.x] = 0u;

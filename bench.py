@@ -47,7 +47,7 @@ CONFIGS = {
 }
 CONFIGS["c5"] = dict(CONFIGS["c2"], name="euroc_752x480_512_streams_sharded")
 # c2 with TRUE 64-pair calls (one camera stream per call, 16 calls in flight): launches of 128 images go through the streaming
-# multi-warp region grower (2.8x the instructions of the one-warp-per-image kernel, a fifth of its latency)
+# multi-warp region grower (1.9x the instructions of the one-warp-per-image kernel, a sixth of its latency)
 CONFIGS["c2_batch64"] = dict(CONFIGS["c2"], name="euroc_752x480_stereo_pointline_true_batch64",
                              dominant=("lsd_grow_sw_kernel", "lsd_grow", 9 * 902 * 576))
 BYTES_PER_PAIR = CONFIGS["c2"]["bytes_per_pair"]

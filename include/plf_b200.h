@@ -211,7 +211,7 @@ PLF_API int PLF_FN(set_stage_timing)(plf_ctx* ctx, int on);
 PLF_API int PLF_FN(get_stage_ms)(plf_ctx* ctx, const char* const** names, const float** ms, int* n_stages);
 /* Which region grower the line path uses (no counterpart in the reference: its LSD is one scalar loop).  Results are identical.
  *   PLF_GROWER_AUTO (default): launches of at most 296 images run 16 regions of every image concurrently (a single pair in
- *     ~12 ms instead of ~70; 2.8x the instructions), wider launches one warp per image.
+ *     ~11 ms instead of ~70; 1.9x the instructions), wider launches one warp per image.
  *   PLF_GROWER_THROUGHPUT: always one warp per image — for callers that keep MANY small or medium calls in flight and care
  *     about pairs per second, not about the latency of one call.  The oracle ignores the setting. */
 #define PLF_GROWER_AUTO 0

@@ -414,7 +414,7 @@ static int check_device_flags(plf_ctx* c) {
     if (e) {
         cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream);
         char buf[128];
-        snprintf(buf, sizeof buf, "device-side capacity overflow (flag 8: streaming region grower stalled), flags=0x%x", e);
+        snprintf(buf, sizeof buf, "%s, flags=0x%x", (e & 8) ? "streaming region grower stalled (watchdog)" : "device-side capacity overflow", e);
         return fail(PLF_ERR_INVALID, buf);
     }
     return PLF_OK;
@@ -772,6 +772,29 @@ PLF_API int plf_batch_upload(plf_ctx* c, const uint8_t* left, const uint8_t* rig
     return PLF_OK;
 }
 
+// Frame::Frame(stereo) returns before both matchers when the left image has no keypoints or no keylines
+// (`if(mvKeys.empty()) return; if(mvKeys_Line.empty()) return;`, src/Frame.cc:147-150): such a slot keeps the initial values
+// of the match arrays (mvuRight / mvDepth -1, no line match, disparities -1, line equations 0).  The matchers have run for
+// every slot of the batch; this kernel puts the initial values back where the constructor would not have called them.
+__global__ void __launch_bounds__(256) frame_gate_kernel(PlfGeom g, const int* nKp, const int* nKl, int hasPoints, int hasLines,
+                                                         float* uRight, float* depth, int* m12, float* disp, double* le) {
+    const int slot = blockIdx.x;
+    const int nk = nKp[slot * 2], nl = nKl[slot * 2];
+    if (!((hasPoints && nk == 0) || (hasLines && nl == 0))) return;
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+        uRight[(size_t)slot * g.kpCap + i] = -1.f;
+        depth[(size_t)slot * g.kpCap + i] = -1.f;
+    }
+    for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+        m12[(size_t)slot * g.klCap + i] = -1;
+        disp[((size_t)slot * g.klCap + i) * 2] = -1.f;
+        disp[((size_t)slot * g.klCap + i) * 2 + 1] = -1.f;
+        le[((size_t)slot * g.klCap + i) * 3] = 0.0;
+        le[((size_t)slot * g.klCap + i) * 3 + 1] = 0.0;
+        le[((size_t)slot * g.klCap + i) * 3 + 2] = 0.0;
+    }
+}
+
 PLF_API int plf_batch_run(plf_ctx* c, int batch) {
     if (!c || batch < 1 || batch > c->batchResident) return fail(PLF_ERR_INVALID, "bad batch (upload first)");
     PLF_CUDA_OK(plf_enter(c));
@@ -812,6 +835,11 @@ PLF_API int plf_batch_run(plf_ctx* c, int batch) {
     else if (c->p.has_lines) n += plf_launch_lines(c, 0, 2 * batch);
     if (c->p.has_lines) n += plf_launch_stereo_lines(c, 0, batch);
     if (c->p.has_points) n += plf_launch_stereo_points(c, 0, batch);
+    if (c->p.has_points && c->p.has_lines) {
+        frame_gate_kernel<<<batch, 256, 0, c->stream>>>(c->g, c->d_nKp, c->d_nKl, c->p.has_points, c->p.has_lines, c->d_uRight, c->d_depth,
+                                                        c->d_m12, c->d_disp, reinterpret_cast<double*>(c->d_le));
+        ++n;
+    }
     plf_mark(c, "d2h");
     if (capture) {
         cudaGraph_t graph = nullptr;

@@ -755,3 +755,33 @@ def test_single_image_calls_with_speculative_line_path(plf, product, oracle):
         L, R = imgs[k]
         f.orb_extract(0, L); f.orb_extract(1, R)
         check(lines(f, 0, L), k, 0, "again"); check(lines(f, 1, R), k, 1, "again")
+
+
+def test_frame_constructor_returns_before_the_matchers(plf, product, oracle):
+    """src/Frame.cc:147-150: no keypoints or no keylines in the LEFT image -> neither stereo matcher runs and the match arrays keep
+    their initial values.  A ramp (lines, no corners), isolated dots (corners, no lines), stripes and an ordinary pair in one
+    batched call, every array against the oracle."""
+    W, H = 752, 480
+    yy, xx = np.mgrid[0:H, 0:W]
+    dots = np.full((H, W), 60, np.uint8)
+    for cy in range(40, H - 40, 57):
+        for cx in range(40, W - 40, 61):
+            dots[cy - 1:cy + 2, cx - 1:cx + 2] = 250
+    ordinary = plf.synth_pair(W, H, 77)
+    L = np.stack([((xx * 3) % 256).astype(np.uint8), dots, (((xx // 5) % 2) * 255).astype(np.uint8), ordinary[0]])
+    R = np.stack([np.roll(L[0], -3, axis=1), np.roll(dots, -4, axis=1), np.roll(L[2], -3, axis=1), ordinary[1]])
+    f = plf.Frontend(product, max_batch=4, lsd_nfeatures=0)
+    o = plf.Frontend(oracle, max_batch=4, lsd_nfeatures=0)
+    for rep in range(3):                          # eager pass, graph capture, graph replay
+        rg, ro = f.frontend_batch(L, R), o.frontend_batch(L, R)
+        assert int(ro.n_kp_left[0]) == 0 and int(ro.n_kl_left[0]) > 0          # ramp: lines only
+        assert int(ro.n_kp_left[1]) > 0 and int(ro.n_kl_left[1]) == 0          # dots: corners only
+        assert int(ro.n_kp_left[3]) > 500 and int(ro.n_kl_left[3]) > 100
+        for b in range(4):
+            nk, nl = int(ro.n_kp_left[b]), int(ro.n_kl_left[b])
+            assert int(rg.n_kp_left[b]) == nk and int(rg.n_kl_left[b]) == nl, (rep, b)
+            assert np.array_equal(rg.kp_left[b, :nk], ro.kp_left[b, :nk]) and np.array_equal(rg.kl_left[b, :nl], ro.kl_left[b, :nl]), (rep, b)
+            assert np.array_equal(rg.u_right[b, :nk], ro.u_right[b, :nk]) and np.array_equal(rg.depth[b, :nk], ro.depth[b, :nk]), (rep, b)
+            assert np.array_equal(rg.line_match12[b, :nl], ro.line_match12[b, :nl]), (rep, b)
+            assert np.array_equal(rg.disp_se[b, :nl], ro.disp_se[b, :nl]) and np.allclose(rg.le[b, :nl], ro.le[b, :nl], rtol=1e-12, atol=0), (rep, b)
+        assert (ro.u_right[1, :int(ro.n_kp_left[1])] == -1).all() and (ro.line_match12[0, :int(ro.n_kl_left[0])] == -1).all()

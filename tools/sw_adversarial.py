@@ -56,6 +56,13 @@ try:
     for b, name in enumerate(names):
         n = int(ro.n_kl_left[b])
         ok = int(rg.n_kl_left[b]) == n and np.array_equal(rg.kl_left[b, :n], ro.kl_left[b, :n]) and np.array_equal(rg.line_match12[b, :n], ro.line_match12[b, :n])
+        nk, nkr = int(ro.n_kp_left[b]), int(ro.n_kp_right[b])
+        okp = (int(rg.n_kp_left[b]) == nk and int(rg.n_kp_right[b]) == nkr and np.array_equal(rg.kp_left[b, :nk], ro.kp_left[b, :nk])
+               and np.array_equal(rg.kp_right[b, :nkr], ro.kp_right[b, :nkr]) and np.array_equal(rg.desc_left[b, :nk], ro.desc_left[b, :nk])
+               and np.array_equal(rg.u_right[b, :nk], ro.u_right[b, :nk]) and np.array_equal(rg.depth[b, :nk], ro.depth[b, :nk])
+               and np.array_equal(rg.disp_se[b, :n], ro.disp_se[b, :n]))
+        print("batched %-12s %5d keypoints %5d lines: %s" % (name, nk, n, "equal" if ok and okp else "DIFFERENT (lines %s, points %s)" % (ok, okp)), flush=True)
+        ok = ok and okp
         bad += not ok
         if not ok:
             print("batched %-12s DIFFERENT" % name)

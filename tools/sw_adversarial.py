@@ -1,11 +1,11 @@
 """Degenerate and adversarial images through the streaming region grower (single-image and small batched calls) against the
 oracle: blank, constant ramp (one region larger than a warp's record buffer), noise (thousands of tiny regions), checkerboard
-(corners everywhere), stripes, concentric rings, a ramp with noise.  python tools/sw_adversarial.py [refine]"""
+(corners everywhere), stripes, concentric rings, a ramp with noise.  python tools/sw_adversarial.py [refine [W H]]"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, plf
-W, H = 752, 480
 refine = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+W, H = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (752, 480)
 rng = np.random.default_rng(7)
 yy, xx = np.mgrid[0:H, 0:W]
 imgs = {
@@ -24,8 +24,8 @@ imgs = {
     "one_edge": np.where(xx + 0.37 * yy < 400, 40, 210).astype(np.uint8),
 }
 names = list(imgs)
-f = plf.Frontend(plf.load_product(), max_batch=len(names), lsd_nfeatures=0, lsd_refine=refine)
-o = plf.Frontend(plf.load_oracle(), max_batch=len(names), lsd_nfeatures=0, lsd_refine=refine)
+f = plf.Frontend(plf.load_product(), width=W, height=H, max_batch=len(names), lsd_nfeatures=0, lsd_refine=refine)
+o = plf.Frontend(plf.load_oracle(), width=W, height=H, max_batch=len(names), lsd_nfeatures=0, lsd_refine=refine)
 bad = 0
 for name in names:
     im = np.ascontiguousarray(imgs[name])

@@ -65,3 +65,29 @@ for kw in (dict(has_points=0), dict(has_lines=0), dict(n_features=100, n_levels=
             print("batched %s %-11s DIFFERENT (%d kp, %d lines)" % (kw, name, nk, nl))
     print("batched", kw, "compared")
 print("differences:", bad)
+
+# the widened entry points on degenerate batches (no keypoints / no lines / ordinary), against the oracle
+names2 = ["blank", "ramp_steep", "dots", "ordinary"]
+Lb = np.stack([imgs[n] for n in names2]); Rb = np.roll(Lb, -4, axis=2)
+B = len(names2)
+outs = []
+for lib in (plf.load_product(), plf.load_oracle()):
+    fr = plf.Frontend(lib, max_batch=B)
+    res = fr.frontend_batch(Lb, Rb)
+    st, ix = fr.feature_grid(0, B)
+    x3d, l3d = fr.backproject(np.tile(np.eye(3, dtype=np.float32), (B, 1, 1)), np.zeros((B, 3), np.float32), 435.2, 367.4, 252.2)
+    fr.bow_set_vocabulary(0, plf.synth_vocabulary(10, 4, seed=1)); fr.bow_set_vocabulary(1, plf.synth_vocabulary(6, 3, seed=2, ragged=0.0))
+    bw = fr.bow_transform(0, B); bl = fr.bow_transform(1, B)
+    outs.append(dict(st=np.array(st), ix=np.array(ix), x3d=np.array(x3d), l3d=np.array(l3d), bw=[np.array(a) for a in bw], bl=[np.array(a) for a in bl]))
+for key in ("st", "ix", "x3d", "l3d"):
+    if key == "ix":      # only the first st[b, -1] indices of a slot are defined
+        same = all(np.array_equal(outs[0]["ix"][b, :int(outs[1]["st"][b, -1])], outs[1]["ix"][b, :int(outs[1]["st"][b, -1])]) for b in range(B))
+    else:
+        same = outs[0][key].shape == outs[1][key].shape and np.array_equal(outs[0][key], outs[1][key])
+    bad += not same
+    print("widened %-4s: %s" % (key, "equal" if same else "DIFFERENT"))
+for key in ("bw", "bl"):
+    same = len(outs[0][key]) == len(outs[1][key]) and all(a.shape == b.shape and np.array_equal(a, b) for a, b in zip(outs[0][key], outs[1][key]))
+    bad += not same
+    print("widened %-4s: %s" % (key, "equal" if same else "DIFFERENT"))
+print("differences (all):", bad)
